@@ -1,0 +1,119 @@
+"""tests/util.py -- helpers shared by the parity tests and tests/golden/gen_golden.py."""
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import tracegen  # noqa: E402
+
+GOLDEN = os.path.join(HERE, "golden")
+DEC_CHARS = "ADS"  # decision codes 0,1,2
+
+
+def hx(v):
+    return None if v is None else float(v).hex()
+
+
+def unhx(s):
+    return None if s is None else float.fromhex(s)
+
+
+def state_hex(st):
+    return {"count": hx(st["count"]), "drop_next": hx(st["drop_next"]),
+            "first_above_time": hx(st["first_above_time"]), "dropping": bool(st["dropping"]),
+            "last_empty": hx(st["last_empty"])}
+
+
+def state_unhex(st):
+    if st is None:
+        return None
+    return {"count": unhx(st["count"]), "drop_next": unhx(st["drop_next"]),
+            "first_above_time": unhx(st["first_above_time"]), "dropping": bool(st["dropping"]),
+            "last_empty": unhx(st["last_empty"])}
+
+
+def rle(s):
+    out, i = [], 0
+    while i < len(s):
+        j = i
+        while j < len(s) and s[j] == s[i]:
+            j += 1
+        out.append("%s%d" % (s[i], j - i))
+        i = j
+    return "".join(out)
+
+
+def unrle_codes(r):
+    """'A3D2' -> uint8 array [0,0,0,1,1]"""
+    out, i = [], 0
+    while i < len(r):
+        ch = r[i]
+        j = i + 1
+        while j < len(r) and r[j].isdigit():
+            j += 1
+        out.append(np.full(int(r[i + 1:j]), DEC_CHARS.index(ch), np.uint8))
+        i = j
+    return np.concatenate(out) if out else np.zeros(0, np.uint8)
+
+
+def codes_to_rle(dec):
+    return rle("".join(DEC_CHARS[int(d)] for d in dec))
+
+
+def crc_i32(a):
+    return zlib.crc32(np.ascontiguousarray(a, dtype=np.int32).tobytes()) & 0xFFFFFFFF
+
+
+def make_trace(spec):
+    """golden trace spec -> (start_ns, now_ns, flags|None) numpy arrays."""
+    if spec["kind"] == "explicit":
+        start = np.array(spec["start_ns"], dtype=np.int64)
+        now = np.array(spec["now_ns"], dtype=np.int64)
+    else:
+        start, now = tracegen.gen_trace(spec["n"], seed=spec["seed"], **dict(spec["params"]))
+    bs = spec.get("backstep")
+    if bs:  # alternate blocks of `every` claims are shifted back by `ns`
+        blk = (np.arange(len(now)) // bs["every"]) % 2
+        now = now - blk.astype(np.int64) * np.int64(bs["ns"])
+    flags = None
+    fs = spec.get("flags")
+    if fs:  # deterministic flags from hash32
+        flags = make_flags(len(now), fs["seed"], fs.get("cancel_mod", 0), fs.get("empty_mod", 0))
+    return start, now, flags
+
+
+def make_flags(n, seed, cancel_mod=0, empty_mod=0):
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        k = ((idx + np.uint64(1)) & np.uint64(0xFFFFFFFF)).astype(np.uint32) * np.uint32(0x9E3779B9)
+        h = tracegen._hash32_np(np.uint32(seed & 0xFFFFFFFF) ^ k).astype(np.int64)
+    flags = np.ones(n, np.uint8)
+    if cancel_mod:
+        flags[(h % cancel_mod) == 0] = 0
+    if empty_mod:
+        flags[((h >> 8) % empty_mod) == 0] |= 2
+    return flags
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def same_bits(a, b):
+    """bit-for-bit equality of two doubles (None == None)."""
+    if a is None or b is None:
+        return a is None and b is None
+    return np.float64(a).tobytes() == np.float64(b).tobytes()
+
+
+def assert_state_equal(got, want, ctx=""):
+    for k in ("count", "drop_next", "first_above_time", "last_empty"):
+        assert same_bits(got[k], want[k]), "%s state.%s: got %r want %r" % (ctx, k, got[k], want[k])
+    assert bool(got["dropping"]) == bool(want["dropping"]), "%s state.dropping" % ctx
