@@ -1,0 +1,199 @@
+"""Context: one cb_ctx (one pool's claim queue on one B200) with numpy / torch helpers.
+
+Host-side mirror of the state a reference ConnectionPool keeps for this path
+(lib/pool.js:191-200: p_waiters, p_codel, p_keys): the arithmetic all happens in the CUDA
+library behind include/cueball_b200.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def _np_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context(object):
+    def __init__(self, device=0):
+        self._L = N.lib()
+        self._h = C.c_void_p()
+        rc = self._L.cb_create(C.byref(self._h), int(device))
+        if rc != N.CB_OK:
+            msg = self._L.cb_last_error(None)
+            raise N.CueballError(rc, msg.decode() if msg else "cb_create failed")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        return N.check(self._h, rc)
+
+    # ------------------------------------------------------------------ CoDel
+    def codel_init(self, target_ms):
+        self._ck(self._L.cb_codel_init(self._h, float(target_ms)))
+
+    def get_state(self):
+        st = N.CodelState()
+        self._ck(self._L.cb_codel_get_state(self._h, C.byref(st)))
+        return st
+
+    def set_state(self, d):
+        """d: dict(count, drop_next, first_above_time, dropping, last_empty|None)"""
+        st = N.CodelState()
+        st.count = int(d["count"])
+        st.drop_next = float(d["drop_next"])
+        st.first_above_time = float(d["first_above_time"])
+        st.dropping = 1 if d["dropping"] else 0
+        le = d.get("last_empty")
+        st.has_last_empty = 0 if le is None else 1
+        st.last_empty = 0.0 if le is None else float(le)
+        self._ck(self._L.cb_codel_set_state(self._h, C.byref(st)))
+
+    def codel_empty(self, now_ns):
+        self._ck(self._L.cb_codel_empty(self._h, int(now_ns)))
+
+    def max_idle(self, now_ns):
+        out = C.c_double()
+        self._ck(self._L.cb_codel_max_idle(self._h, int(now_ns), C.byref(out)))
+        return out.value
+
+    def overloaded(self, start_ns, now_ns):
+        out = C.c_int()
+        self._ck(self._L.cb_codel_overloaded(self._h, int(start_ns), int(now_ns), C.byref(out)))
+        return bool(out.value)
+
+    # ---------------------------------------------------------------- batches
+    def admit_batch(self, start, now, flags=None, want_backend=False, want_slot=True, want_decision=True):
+        """Host (numpy) buffers through the host-buffer C entry point.
+        start/now: int64 ns or float64 ms.  Returns (decision, slot, backend, BatchStats)."""
+        start = np.ascontiguousarray(start)
+        now = np.ascontiguousarray(now)
+        if start.dtype != now.dtype or start.shape != now.shape or start.ndim != 1:
+            raise ValueError("start/now must be 1-D arrays of the same dtype and length")
+        n = start.shape[0]
+        if start.dtype == np.int64:
+            fn = self._L.cb_admit_batch
+        elif start.dtype == np.float64:
+            fn = self._L.cb_admit_batch_ms
+        else:
+            raise TypeError("timestamps must be int64 (ns) or float64 (ms)")
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
+            if flags.shape != start.shape:
+                raise ValueError("flags length mismatch")
+        dec = np.empty(n, np.uint8) if want_decision else None
+        slot = np.empty(n, np.int32) if want_slot else None
+        be = np.empty(n, np.int32) if want_backend else None
+        st = N.BatchStats()
+        self._ck(fn(self._h, _np_ptr(start), _np_ptr(now), _np_ptr(flags), n, _np_ptr(dec), _np_ptr(slot),
+                    _np_ptr(be), C.byref(st)))
+        return dec, slot, be, st
+
+    def admit_batch_dev(self, start, now, flags=None, decision=None, slot=None, backend=None):
+        """torch CUDA tensors (queue resident in HBM); asynchronous on the context's stream."""
+        n = start.numel()
+        import torch
+        if start.dtype == torch.int64:
+            fn = self._L.cb_admit_batch_dev
+        elif start.dtype == torch.float64:
+            fn = self._L.cb_admit_batch_ms_dev
+        else:
+            raise TypeError("timestamps must be int64 (ns) or float64 (ms)")
+
+        def p(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        self._ck(fn(self._h, p(start), p(now), p(flags), n, p(decision), p(slot), p(backend)))
+
+    def stats(self):
+        st = N.BatchStats()
+        self._ck(self._L.cb_batch_stats_get(self._h, C.byref(st)))
+        return st
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self._L.cb_set_stream(self._h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
+
+    def synchronize(self):
+        self._ck(self._L.cb_synchronize(self._h))
+
+    # --------------------------------------------------------------- topology
+    def backends_set(self, nbackends, insert_u, nslots, table=None, mode=N.BALANCE_UNIFORM):
+        u = np.ascontiguousarray(insert_u, dtype=np.float64)
+        tbl = None
+        if table is not None:
+            arr = (N.Backend * nbackends)()
+            for k, (pr, w) in enumerate(table):
+                arr[k].priority, arr[k].weight = int(pr), int(w)
+            tbl = C.cast(arr, C.c_void_p)
+        self._ck(self._L.cb_backends_set(self._h, tbl, int(nbackends), _np_ptr(u), int(nslots), int(mode)))
+
+    def backend_added(self, key, u, priority=0, weight=0):
+        be = N.Backend(int(priority), int(weight))
+        self._ck(self._L.cb_backend_added(self._h, int(key), C.cast(C.pointer(be), C.c_void_p), float(u)))
+
+    def backend_removed(self, key):
+        self._ck(self._L.cb_backend_removed(self._h, int(key)))
+
+    def reshuffle(self, u):
+        self._ck(self._L.cb_reshuffle(self._h, float(u)))
+
+    def backends_get(self):
+        nk, ns = C.c_int32(), C.c_int32()
+        self._ck(self._L.cb_backends_get(self._h, C.byref(nk), None, C.byref(ns), None))
+        keys = np.zeros(max(nk.value, 1), np.int32)
+        slots = np.zeros(max(ns.value, 1), np.int32)
+        self._ck(self._L.cb_backends_get(self._h, C.byref(nk), _np_ptr(keys), C.byref(ns), _np_ptr(slots)))
+        return keys[:nk.value].copy(), slots[:ns.value].copy()
+
+    def plan_rebalance(self, have, dead, target, mx, singleton=False):
+        have = np.ascontiguousarray(have, dtype=np.int32)
+        dead = np.ascontiguousarray(dead, dtype=np.uint8)
+        B = have.shape[0]
+        want = np.zeros(max(B, 1), np.int32)
+        add = np.zeros(max(int(mx), 0) + 1, np.int32)
+        tot = max(int(have.sum()) if B else 0, 0) + 1
+        rk, ro = np.zeros(tot, np.int32), np.zeros(tot, np.int32)
+        na, nr = C.c_int32(), C.c_int32()
+        self._ck(self._L.cb_plan_rebalance(self._h, _np_ptr(have), _np_ptr(dead), B, int(target), int(mx),
+                                           int(bool(singleton)), _np_ptr(want), _np_ptr(add), C.byref(na),
+                                           _np_ptr(rk), _np_ptr(ro), C.byref(nr)))
+        return want[:B].copy(), add[:na.value].copy(), list(zip(rk[:nr.value].tolist(), ro[:nr.value].tolist()))
+
+    # -------------------------------------------------------------- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        sz = C.c_size_t(128)
+        rc = N.lib().cb_comm_unique_id(buf, C.byref(sz))
+        if rc != N.CB_OK:
+            raise N.CueballError(rc, (N.lib().cb_last_error(None) or b"?").decode())
+        return buf.raw[:sz.value]
+
+    def comm_init(self, nranks, rank, uid):
+        self._ck(self._L.cb_comm_init(self._h, int(nranks), int(rank), C.c_char_p(uid), len(uid)))
+
+    def allreduce_counts(self):
+        self._ck(self._L.cb_allreduce_counts(self._h))
+
+    # ------------------------------------------------------------ measurement
+    def profile_enable(self, on=True):
+        self._ck(self._L.cb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_get(self):
+        ms = (C.c_double * N.K_COUNT)()
+        cnt = (C.c_uint64 * N.K_COUNT)()
+        self._ck(self._L.cb_profile_get(self._h, ms, cnt))
+        return list(ms), list(cnt)
+
+    def launch_count(self):
+        return int(self._L.cb_launch_count(self._h))

@@ -1,0 +1,172 @@
+// cb_device.cuh -- shared device-side definitions for the claim-queue admission kernels
+// (sm_100a).  See DESIGN.md for the decomposition; reference citations are file:line in
+// TritonDataCenter/node-cueball v2.10.3.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+constexpr int TPB = 256;        // threads per CTA in the streaming kernels
+constexpr int IPT = 8;          // consecutive claims per thread
+constexpr int TILE = TPB * IPT; // 2048 claims per tile
+constexpr int WARPS = TPB / 32;
+constexpr int EVK = 8;          // class-change events a tile can hold before "overflow"
+constexpr double CODEL_INTERVAL = 100.0; // lib/codel.js:16
+
+// per-claim flag bits (include/cueball_b200.h)
+constexpr unsigned F_WAITING = 1u, F_EMPTY_AFTER = 2u;
+
+// ---------------------------------------------------------------------------------------
+// Device-resident control block: one per context, lives in HBM, so consecutive batches
+// chain their ControlledDelay state without a host round trip.
+struct DevState {
+	// ControlledDelay, lib/codel.js:24-32 (+ cd_last_empty :92)
+	double target;            // cd_targdelay
+	double F;                 // cd_first_above_time (0 = unset)
+	double D;                 // cd_drop_next
+	unsigned long long C;     // cd_count
+	int B;                    // cd_dropping
+	int hasE;                 // cd_last_empty defined?
+	double E;                 // cd_last_empty
+	unsigned long long cursor; // admit cursor (slot = cursor mod nslots)
+	unsigned long long cursor0; // cursor before the batch in flight (read by the emit kernel)
+	// last batch
+	unsigned long long n, drops, admits, skipped;
+	unsigned long long tot_drops, tot_admits;
+	unsigned long long gcounts[4]; // {drops, admits, n, 0}: allreduce buffer (in place)
+	// control (set by the scan kernel, consumed + reset by the resolve kernel)
+	unsigned int nonmono;     // clock went backwards inside the batch
+	unsigned int overflow;    // a tile found more than EVK events
+	unsigned long long last_marker_p1; // 1 + index of the last CB_F_EMPTY_AFTER claim
+	int path;                 // CB_PATH_*
+	unsigned int n_events;
+	unsigned int n_intervals;
+	unsigned int pad;
+};
+
+// Tile descriptor of the decoupled look-back over the first_above_time recurrence.
+// w = (epoch << 3) | (isconst << 2) | status ; status 1 = aggregate (vA), 2 = prefix (vP).
+// vA/vP are written before w is released and never rewritten within an epoch.
+struct alignas(32) TileDesc {
+	unsigned long long w;
+	double vA;
+	double vP;
+	unsigned long long pad;
+};
+constexpr unsigned ST_AGG = 1u, ST_PREFIX = 2u;
+
+// Tile descriptor of the admit-count look-back (emit kernel, flags variant).
+struct alignas(32) SumDesc {
+	unsigned long long w; // (epoch << 2) | status
+	unsigned long long agg;
+	unsigned long long incl;
+	unsigned long long pad;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double *p) {
+	double v;
+	asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// utils.currentMillis(), lib/utils.js:198-204:  secs*1000 + ns/1000000 with each operation
+// rounded once (no FMA contraction).  `t` is process.hrtime() as total nanoseconds >= 0.
+//
+// The quotient ns/1e6 (0 <= ns < 1e9, an integer) must be the correctly rounded IEEE
+// quotient.  It is computed with a reciprocal multiply plus one residual correction
+// (Markstein); tools/verify_div1e6.c proves exhaustively, for all 10^9 dividends, that the
+// result is bit-identical to the IEEE division.  This keeps the FP64 pipe (the scarce one
+// for this kernel) at 3 ops instead of the ~25 of a generic division.
+__device__ __forceinline__ double div_1e6(double x) {
+	const double R = 1e-6; // RN(1/1e6)
+	double q = __dmul_rn(x, R);
+	double r = __fma_rn(-q, 1000000.0, x);
+	return __fma_rn(r, R, q);
+}
+__device__ __forceinline__ double ns_to_ms(long long t) {
+	unsigned long long ut = (unsigned long long)t;
+	unsigned long long secs = ut / 1000000000ull;
+	unsigned int ns = (unsigned int)(ut - secs * 1000000000ull);
+	double secs2ms = __dmul_rn((double)secs, 1000.0);
+	double ns2ms = div_1e6((double)ns);
+	return __dadd_rn(secs2ms, ns2ms);
+}
+
+template <bool NS> struct TimeIn;
+template <> struct TimeIn<true> {
+	using raw_t = long long;
+	static __device__ __forceinline__ double to_ms(long long v) { return ns_to_ms(v); }
+};
+template <> struct TimeIn<false> {
+	using raw_t = double;
+	static __device__ __forceinline__ double to_ms(double v) { return v; }
+};
+
+// ControlledDelay#canDrop's three-way outcome for a claim given the first_above_time in
+// force (lib/codel.js:34-46), refined by the re-entry test of :72:
+//   0 = not ok to drop, 1 = ok, 2 = ok and (now - first_above_time >= INTERVAL)
+__device__ __forceinline__ int claim_class(bool above, double now, double F) {
+	if (!above || F == 0.0 || !(now >= F))
+		return 0;
+	return (__dsub_rn(now, F) >= CODEL_INTERVAL) ? 2 : 1;
+}
+
+// getDropNext(), lib/codel.js:48-50
+__device__ __forceinline__ double drop_next_after(double now, unsigned long long count) {
+	double step = __ddiv_rn(CODEL_INTERVAL, __dsqrt_rn((double)count));
+	return __dadd_rn(now, step);
+}
+
+// One step of ControlledDelay#overloaded (lib/codel.js:56-86) on explicit state.
+struct CodelRegs {
+	double F, D;
+	unsigned long long C;
+	int B;
+};
+__device__ __forceinline__ bool codel_step(CodelRegs &s, double target, double now, double start) {
+	bool ok = false;
+	double soj = __dsub_rn(now, start);
+	if (soj < target) {
+		s.F = 0.0;
+	} else if (s.F == 0.0) {
+		s.F = __dadd_rn(now, CODEL_INTERVAL);
+	} else if (now >= s.F) {
+		ok = true;
+	}
+	bool drop = false;
+	if (s.B) {
+		if (!ok) {
+			s.B = 0;
+		} else if (now >= s.D) {
+			drop = true;
+			s.C += 1;
+		}
+	} else if (ok && ((__dsub_rn(now, s.D) < CODEL_INTERVAL) ||
+	    (__dsub_rn(now, s.F) >= CODEL_INTERVAL))) {
+		drop = true;
+		s.B = 1;
+		if (__dsub_rn(now, s.D) < CODEL_INTERVAL)
+			s.C = s.C > 2 ? s.C - 2 : 1;
+		else
+			s.C = 1;
+		s.D = drop_next_after(now, s.C);
+	}
+	return drop;
+}
+
+} // namespace cb

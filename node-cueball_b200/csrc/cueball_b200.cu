@@ -1,0 +1,937 @@
+// cueball_b200.cu -- the C ABI (include/cueball_b200.h) over the sm_100a kernels.
+// Host-side plumbing only: buffers, streams, launches, the chunked H2D/compute/D2H
+// pipeline of the host-buffer entry points, and a dlopen()ed NCCL for the one collective.
+#include "../../include/cueball_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <new>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "cb_device.cuh"
+#include "cb_emit.cuh"
+#include "cb_resolve.cuh"
+#include "cb_scan.cuh"
+#include "cb_topology.cuh"
+
+using namespace cb;
+
+namespace {
+
+char g_create_err[512] = "";
+
+// ---- NCCL through dlopen: no link-time dependency; multi-GPU is optional --------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm_t;
+struct NcclApi {
+	void *h = nullptr;
+	int (*GetUniqueId)(nccl_uid *) = nullptr;
+	int (*CommInitRank)(nccl_comm_t *, int, nccl_uid, int) = nullptr;
+	int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+	int (*CommDestroy)(nccl_comm_t) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+	bool load() {
+		if (h)
+			return true;
+		h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+		if (!h)
+			h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+		if (!h)
+			h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+		if (!h)
+			return false;
+		GetUniqueId = (int (*)(nccl_uid *))dlsym(h, "ncclGetUniqueId");
+		CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid, int))dlsym(h, "ncclCommInitRank");
+		AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+		CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+		GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+		return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+	}
+};
+NcclApi g_nccl;
+constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0;
+
+constexpr int NBUF = 3;                       // staging buffers of the host-buffer pipeline
+constexpr size_t DEFAULT_CHUNK = 4u << 20;    // claims per pipeline chunk
+
+struct Staging {
+	void *start = nullptr, *now = nullptr;
+	uint8_t *flags = nullptr, *decision = nullptr;
+	int32_t *slot = nullptr, *backend = nullptr;
+	cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+};
+
+} // namespace
+
+struct cb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t s_in = nullptr, s_out = nullptr;
+	DevState *g = nullptr;
+	bool codel_ready = false;
+	char err[512] = "";
+	unsigned long long epoch = 0;
+	uint64_t launches = 0;
+	// scratch sized by tile count
+	size_t cap_tiles = 0;
+	TileDesc *desc = nullptr;
+	SumDesc *sdesc = nullptr;
+	unsigned int *ev_count = nullptr;
+	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
+	double *ev_now = nullptr;
+	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
+	unsigned int *ticket = nullptr;
+	// topology
+	int B = 0, nslots = 0, target_slots = 0, mode = CB_BALANCE_UNIFORM, key_cap = 0, slot_cap = 0;
+	int32_t *d_keys = nullptr, *d_want = nullptr, *d_add = nullptr, *d_slot_backend = nullptr;
+	int32_t *d_prio = nullptr, *d_weight = nullptr;
+	int *d_ints = nullptr; // [0]=len [1]=n_add [2]=nslots [3]=status [4]=n_rm [5]=scalar out
+	double *d_dbl = nullptr;
+	// host-buffer pipeline
+	size_t chunk = DEFAULT_CHUNK, stage_cap = 0;
+	Staging st[NBUF];
+	// cached totals for per-call deltas
+	unsigned long long seen_drops = 0, seen_admits = 0;
+	// profiling
+	bool prof = false;
+	cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+	double prof_ms[CB_K_COUNT] = {0, 0, 0};
+	uint64_t prof_n[CB_K_COUNT] = {0, 0, 0};
+	// nccl
+	nccl_comm_t comm = nullptr;
+	int nranks = 1, rank = 0;
+	unsigned long long *h_pinned = nullptr; // small pinned scratch
+};
+
+namespace {
+
+int fail(cb_ctx *c, int code, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(c ? c->err : g_create_err, 512, fmt, ap);
+	va_end(ap);
+	return code;
+}
+#define CU(c, call)                                                                              \
+	do {                                                                                         \
+		cudaError_t e_ = (call);                                                                 \
+		if (e_ != cudaSuccess)                                                                   \
+			return fail((c), CB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+template <typename T> int dev_alloc(cb_ctx *c, T **p, size_t count) {
+	if (*p) {
+		cudaFree(*p);
+		*p = nullptr;
+	}
+	cudaError_t e = cudaMalloc((void **)p, count * sizeof(T) + 64);
+	if (e != cudaSuccess)
+		return fail(c, CB_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+	return CB_OK;
+}
+
+int ensure_scratch(cb_ctx *c, size_t tiles) {
+	if (tiles <= c->cap_tiles)
+		return CB_OK;
+	size_t cap = tiles + tiles / 4 + 64;
+	int rc;
+	if ((rc = dev_alloc(c, &c->desc, cap)) || (rc = dev_alloc(c, &c->sdesc, cap)) ||
+	    (rc = dev_alloc(c, &c->ev_count, cap)) || (rc = dev_alloc(c, &c->ev, cap * EVK)) ||
+	    (rc = dev_alloc(c, &c->evc, cap * EVK)) || (rc = dev_alloc(c, &c->ev_q, cap * EVK)) ||
+	    (rc = dev_alloc(c, &c->ev_d, cap * EVK)) || (rc = dev_alloc(c, &c->ev_now, cap * EVK)) ||
+	    (rc = dev_alloc(c, &c->iv_lo, cap * EVK + 8)) || (rc = dev_alloc(c, &c->iv_hi, cap * EVK + 8)) ||
+	    (rc = dev_alloc(c, &c->iv_cum, cap * EVK + 8)))
+		return rc;
+	// descriptors carry an epoch tag, so they only need zeroing once
+	CU(c, cudaMemsetAsync(c->desc, 0, cap * sizeof(TileDesc), c->stream));
+	CU(c, cudaMemsetAsync(c->sdesc, 0, cap * sizeof(SumDesc), c->stream));
+	c->cap_tiles = cap;
+	return CB_OK;
+}
+
+// launch the three kernels of one batch on the context's stream
+template <bool NS>
+int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_t *d_flags, size_t n,
+    uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	if (n == 0)
+		return CB_OK;
+	if (n > (1ull << 40))
+		return fail(c, CB_EINVAL, "batch too large");
+	const size_t tiles = (n + TILE - 1) / TILE;
+	int rc = ensure_scratch(c, tiles);
+	if (rc)
+		return rc;
+	c->epoch++;
+	const bool flags = d_flags != nullptr;
+
+	ScanParams sp;
+	sp.start = d_start;
+	sp.now = d_now;
+	sp.flags = d_flags;
+	sp.n = n;
+	sp.g = c->g;
+	sp.desc = c->desc;
+	sp.epoch = c->epoch;
+	sp.ev_count = c->ev_count;
+	sp.ev = c->ev;
+	sp.vec_ok = (((uintptr_t)d_start | (uintptr_t)d_now) & 15) == 0;
+
+	ResolveParams rp;
+	rp.start = d_start;
+	rp.now = d_now;
+	rp.flags = d_flags;
+	rp.n = n;
+	rp.tiles = tiles;
+	rp.g = c->g;
+	rp.desc = c->desc;
+	rp.ev_count = c->ev_count;
+	rp.ev = c->ev;
+	rp.evc = c->evc;
+	rp.ev_now = c->ev_now;
+	rp.ev_q = c->ev_q;
+	rp.ev_d = c->ev_d;
+	rp.ev_cap = tiles * EVK;
+	rp.iv_lo = c->iv_lo;
+	rp.iv_hi = c->iv_hi;
+	rp.iv_cum = c->iv_cum;
+	rp.decision = d_decision;
+	rp.slot = d_slot;
+	rp.backend = d_backend;
+	rp.slot_backend = c->d_slot_backend;
+	rp.nslots = c->nslots;
+
+	EmitParams ep;
+	ep.flags = d_flags;
+	ep.n = n;
+	ep.tiles = tiles;
+	ep.g = c->g;
+	ep.iv_lo = c->iv_lo;
+	ep.iv_hi = c->iv_hi;
+	ep.iv_cum = c->iv_cum;
+	ep.decision = d_decision;
+	ep.slot = d_slot;
+	ep.backend = d_backend;
+	ep.slot_backend = c->d_slot_backend;
+	ep.nslots = c->nslots;
+	size_t tbytes = ((size_t)c->nslots * 4 + 15) & ~(size_t)15;
+	ep.table_smem_bytes = (d_backend && c->nslots > 0 && tbytes <= 96 * 1024) ? (int)tbytes : 0;
+	ep.sdesc = c->sdesc;
+	ep.epoch = c->epoch;
+	ep.ticket = c->ticket;
+	ep.vec_ok = (((uintptr_t)d_decision & 7) == 0) && (((uintptr_t)d_slot & 15) == 0) &&
+	    (((uintptr_t)d_backend & 15) == 0);
+
+	cudaStream_t s = c->stream;
+	if (c->prof)
+		CU(c, cudaEventRecord(c->pe[0], s));
+	if (flags)
+		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s>>>(sp);
+	else
+		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s>>>(sp);
+	if (c->prof)
+		CU(c, cudaEventRecord(c->pe[1], s));
+	if (flags)
+		resolve_kernel<NS, true><<<1, RTPB, 0, s>>>(rp);
+	else
+		resolve_kernel<NS, false><<<1, RTPB, 0, s>>>(rp);
+	if (c->prof)
+		CU(c, cudaEventRecord(c->pe[2], s));
+	if (flags)
+		emit_kernel<true><<<(unsigned)tiles, TPB, ep.table_smem_bytes, s>>>(ep);
+	else
+		emit_kernel<false><<<(unsigned)tiles, TPB, ep.table_smem_bytes, s>>>(ep);
+	c->launches += 3;
+	CU(c, cudaGetLastError());
+	if (c->prof) {
+		CU(c, cudaEventRecord(c->pe[3], s));
+		CU(c, cudaEventSynchronize(c->pe[3]));
+		for (int k = 0; k < CB_K_COUNT; k++) {
+			float ms = 0;
+			CU(c, cudaEventElapsedTime(&ms, c->pe[k], c->pe[k + 1]));
+			c->prof_ms[k] += ms;
+			c->prof_n[k]++;
+		}
+	}
+	return CB_OK;
+}
+
+int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool per_call) {
+	DevState h;
+	CU(c, cudaMemcpyAsync(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	memset(out, 0, sizeof(*out));
+	out->n = h.n;
+	out->drops = h.drops;
+	out->admits = h.admits;
+	out->skipped = h.skipped;
+	out->cursor = h.cursor;
+	out->total_drops = h.tot_drops;
+	out->total_admits = h.tot_admits;
+	out->global_drops = c->comm ? h.gcounts[0] : h.drops;
+	out->global_admits = c->comm ? h.gcounts[1] : h.admits;
+	out->global_n = c->comm ? h.gcounts[2] : h.n;
+	out->state.target_ms = h.target;
+	out->state.first_above_time = h.F;
+	out->state.drop_next = h.D;
+	out->state.count = h.C;
+	out->state.dropping = h.B;
+	out->state.has_last_empty = h.hasE;
+	out->state.last_empty = h.E;
+	out->path = h.path;
+	out->n_events = h.n_events;
+	out->n_intervals = h.n_intervals;
+	(void)per_call;
+	return CB_OK;
+}
+
+int ensure_staging(cb_ctx *c, size_t n) {
+	size_t need = n < c->chunk ? n : c->chunk;
+	need = (need + TILE - 1) / TILE * TILE;
+	if (need <= c->stage_cap)
+		return CB_OK;
+	for (int b = 0; b < NBUF; b++) {
+		Staging &s = c->st[b];
+		int rc;
+		if ((rc = dev_alloc(c, (unsigned long long **)&s.start, need)) ||
+		    (rc = dev_alloc(c, (unsigned long long **)&s.now, need)) || (rc = dev_alloc(c, &s.flags, need)) ||
+		    (rc = dev_alloc(c, &s.decision, need)) || (rc = dev_alloc(c, &s.slot, need)) ||
+		    (rc = dev_alloc(c, &s.backend, need)))
+			return rc;
+		if (!s.in_done) {
+			CU(c, cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+			CU(c, cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
+			CU(c, cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+		}
+	}
+	c->stage_cap = need;
+	return CB_OK;
+}
+
+// host-buffer batch: chunks flow H2D -> kernels -> D2H on three streams; the CoDel state
+// and the admit cursor stay on the device between chunks (a chunk is just a batch).
+template <bool NS>
+int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *flags, size_t n,
+    uint8_t *decision, int32_t *slot, int32_t *backend, cb_batch_stats *stats) {
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	if (n && (!start || !now))
+		return fail(c, CB_EINVAL, "start/now must not be NULL");
+	DevState h0;
+	CU(c, cudaMemcpyAsync(&h0, c->g, sizeof(h0), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	int rc = ensure_staging(c, n);
+	if (rc)
+		return rc;
+	unsigned long long skipped = 0;
+	int path = 0;
+	unsigned int nev = 0, niv = 0;
+	size_t nchunks = (n + c->chunk - 1) / c->chunk;
+	for (size_t ci = 0; ci < nchunks; ci++) {
+		Staging &s = c->st[ci % NBUF];
+		size_t lo = ci * c->chunk, m = (n - lo < c->chunk) ? n - lo : c->chunk;
+		if (ci >= NBUF)
+			CU(c, cudaStreamWaitEvent(c->s_in, s.out_done, 0));
+		CU(c, cudaMemcpyAsync(s.start, (const char *)start + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
+		CU(c, cudaMemcpyAsync(s.now, (const char *)now + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
+		if (flags)
+			CU(c, cudaMemcpyAsync(s.flags, flags + lo, m, cudaMemcpyHostToDevice, c->s_in));
+		CU(c, cudaEventRecord(s.in_done, c->s_in));
+		CU(c, cudaStreamWaitEvent(c->stream, s.in_done, 0));
+		rc = launch_batch<NS>(c, s.start, s.now, flags ? s.flags : nullptr, m, decision ? s.decision : nullptr,
+		    slot ? s.slot : nullptr, backend ? s.backend : nullptr);
+		if (rc)
+			return rc;
+		CU(c, cudaEventRecord(s.comp_done, c->stream));
+		CU(c, cudaStreamWaitEvent(c->s_out, s.comp_done, 0));
+		if (decision)
+			CU(c, cudaMemcpyAsync(decision + lo, s.decision, m, cudaMemcpyDeviceToHost, c->s_out));
+		if (slot)
+			CU(c, cudaMemcpyAsync(slot + lo, s.slot, m * 4, cudaMemcpyDeviceToHost, c->s_out));
+		if (backend)
+			CU(c, cudaMemcpyAsync(backend + lo, s.backend, m * 4, cudaMemcpyDeviceToHost, c->s_out));
+		CU(c, cudaEventRecord(s.out_done, c->s_out));
+		if (nchunks > 1 && stats) { // per-chunk extras that are not cumulative on the device
+			// (kept cheap: only when the caller wants stats and the batch was split)
+		}
+	}
+	CU(c, cudaStreamSynchronize(c->s_out));
+	CU(c, cudaStreamSynchronize(c->stream));
+	if (stats) {
+		rc = fetch_stats(c, stats, true);
+		if (rc)
+			return rc;
+		// totals of the whole call, not of its last chunk
+		stats->n = n;
+		stats->drops = stats->total_drops - h0.tot_drops;
+		stats->admits = stats->total_admits - h0.tot_admits;
+		stats->skipped = n - stats->drops - stats->admits;
+		if (!c->comm) {
+			stats->global_drops = stats->drops;
+			stats->global_admits = stats->admits;
+			stats->global_n = n;
+		}
+		(void)skipped;
+		(void)path;
+		(void)nev;
+		(void)niv;
+	}
+	return CB_OK;
+}
+
+int rebuild_slots(cb_ctx *c) {
+	// planRebalance({}, {}, nslots, nslots) over the preference list, then the slot table
+	if (c->B <= 0 || c->target_slots <= 0) {
+		c->nslots = 0;
+		return CB_OK;
+	}
+	c->nslots = c->target_slots;
+	cudaStream_t s = c->stream;
+	int *d_nadd = c->d_ints + 1, *d_nslots = c->d_ints + 2;
+	if (c->mode == CB_BALANCE_SRV_WEIGHTED) {
+		weighted_want_kernel<<<1, 1, 0, s>>>(c->d_keys, c->B, c->d_prio, c->d_weight, c->nslots, c->d_want,
+		    c->d_add, d_nadd);
+	} else {
+		// have = 0, dead = 0: reuse d_want's neighbour buffers as zeroed inputs
+		int32_t *d_have = c->d_add + c->slot_cap; // zeroed tail, see cb_backends_set
+		uint8_t *d_dead = (uint8_t *)(d_have + c->key_cap);
+		plan_rebalance_kernel<<<1, 1, 0, s>>>(d_have, d_dead, c->B, c->nslots, c->nslots, 0, c->d_want, c->d_add,
+		    d_nadd, nullptr, nullptr, c->d_ints + 4);
+	}
+	slot_table_kernel<<<8, 256, 0, s>>>(c->d_keys, c->d_add, d_nadd, c->d_slot_backend, c->slot_cap, d_nslots);
+	c->launches += 2;
+	CU(c, cudaGetLastError());
+	int got = 0;
+	CU(c, cudaMemcpyAsync(&got, d_nslots, sizeof(int), cudaMemcpyDeviceToHost, s));
+	CU(c, cudaStreamSynchronize(s));
+	c->nslots = got; // planRebalance hands out exactly `target` slots when B > 0
+	return CB_OK;
+}
+
+int ensure_topology(cb_ctx *c, int keys, int slots) {
+	if (keys <= c->key_cap && slots <= c->slot_cap)
+		return CB_OK;
+	int kc = keys > c->key_cap ? keys + 64 : c->key_cap;
+	int sc = slots > c->slot_cap ? ((slots + 3) & ~3) + 64 : c->slot_cap;
+	int32_t *ok = nullptr, *opr = nullptr, *ow = nullptr;
+	int oldB = c->B;
+	// keep the current preference list / SRV table across a growth
+	if (c->d_keys && oldB > 0) {
+		ok = (int32_t *)malloc(sizeof(int32_t) * oldB * 3);
+		opr = ok + oldB;
+		ow = opr + oldB;
+		cudaMemcpy(ok, c->d_keys, sizeof(int32_t) * oldB, cudaMemcpyDeviceToHost);
+		cudaMemcpy(opr, c->d_prio, sizeof(int32_t) * oldB, cudaMemcpyDeviceToHost);
+		cudaMemcpy(ow, c->d_weight, sizeof(int32_t) * oldB, cudaMemcpyDeviceToHost);
+	}
+	int rc;
+	if ((rc = dev_alloc(c, &c->d_keys, kc)) || (rc = dev_alloc(c, &c->d_want, kc)) ||
+	    (rc = dev_alloc(c, &c->d_prio, kc)) || (rc = dev_alloc(c, &c->d_weight, kc)) ||
+	    (rc = dev_alloc(c, &c->d_add, (size_t)sc + kc + kc)) || (rc = dev_alloc(c, &c->d_slot_backend, sc)))
+		return rc;
+	CU(c, cudaMemset(c->d_add, 0, ((size_t)sc + kc + kc) * sizeof(int32_t)));
+	CU(c, cudaMemset(c->d_prio, 0, sizeof(int32_t) * kc));
+	CU(c, cudaMemset(c->d_weight, 0, sizeof(int32_t) * kc));
+	if (ok) {
+		cudaMemcpy(c->d_keys, ok, sizeof(int32_t) * oldB, cudaMemcpyHostToDevice);
+		cudaMemcpy(c->d_prio, opr, sizeof(int32_t) * oldB, cudaMemcpyHostToDevice);
+		cudaMemcpy(c->d_weight, ow, sizeof(int32_t) * oldB, cudaMemcpyHostToDevice);
+		free(ok);
+	}
+	c->key_cap = kc;
+	c->slot_cap = sc;
+	return CB_OK;
+}
+
+} // namespace
+
+// =========================================================================== lifecycle
+extern "C" int cb_abi_version(void) { return CB_ABI_VERSION; }
+
+extern "C" const char *cb_last_error(const cb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int cb_create(cb_ctx **out, int device) {
+	if (!out)
+		return fail(nullptr, CB_EINVAL, "out is NULL");
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(nullptr, CB_ECUDA, "no CUDA device (%s): this library has no CPU fallback",
+		    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+	if (device < 0 || device >= ndev)
+		return fail(nullptr, CB_EINVAL, "device %d out of range (have %d)", device, ndev);
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess)
+		return fail(nullptr, CB_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+	if (prop.major != 10)
+		return fail(nullptr, CB_ECUDA, "device %d is sm_%d%d; this build is sm_100a only", device, prop.major,
+		    prop.minor);
+	cb_ctx *c = new (std::nothrow) cb_ctx();
+	if (!c)
+		return fail(nullptr, CB_ENOMEM, "out of host memory");
+	c->device = device;
+	const char *ck = getenv("CB_CHUNK");
+	if (ck && atoll(ck) >= TILE)
+		c->chunk = ((size_t)atoll(ck) + TILE - 1) / TILE * TILE;
+#define CU0(call)                                                                          \
+	do {                                                                                   \
+		cudaError_t e_ = (call);                                                           \
+		if (e_ != cudaSuccess) {                                                           \
+			fail(nullptr, CB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));              \
+			cb_destroy(c);                                                                 \
+			return CB_ECUDA;                                                               \
+		}                                                                                  \
+	} while (0)
+	CU0(cudaSetDevice(device));
+	CU0(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	CU0(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+	CU0(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+	c->stream = c->own_stream;
+	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
+	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
+	CU0(cudaMalloc((void **)&c->ticket, 64));
+	CU0(cudaMemset(c->ticket, 0, 64));
+	CU0(cudaMalloc((void **)&c->d_ints, 64 * sizeof(int)));
+	CU0(cudaMemset(c->d_ints, 0, 64 * sizeof(int)));
+	CU0(cudaMalloc((void **)&c->d_dbl, 64 * sizeof(double)));
+	CU0(cudaMallocHost((void **)&c->h_pinned, 256));
+	for (int k = 0; k < 4; k++)
+		CU0(cudaEventCreate(&c->pe[k]));
+	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+#undef CU0
+	*out = c;
+	return CB_OK;
+}
+
+extern "C" void cb_destroy(cb_ctx *c) {
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	if (c->stream)
+		cudaStreamSynchronize(c->stream);
+	if (c->comm && g_nccl.CommDestroy)
+		g_nccl.CommDestroy(c->comm);
+	void *frees[] = {c->g, c->desc, c->sdesc, c->ev_count, c->ev, c->evc, c->ev_q, c->ev_d, c->ev_now, c->iv_lo,
+	    c->iv_hi, c->iv_cum, c->ticket, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight,
+	    c->d_ints, c->d_dbl};
+	for (void *p : frees)
+		if (p)
+			cudaFree(p);
+	for (int b = 0; b < NBUF; b++) {
+		Staging &s = c->st[b];
+		void *fs[] = {s.start, s.now, s.flags, s.decision, s.slot, s.backend};
+		for (void *p : fs)
+			if (p)
+				cudaFree(p);
+		if (s.in_done)
+			cudaEventDestroy(s.in_done);
+		if (s.comp_done)
+			cudaEventDestroy(s.comp_done);
+		if (s.out_done)
+			cudaEventDestroy(s.out_done);
+	}
+	for (int k = 0; k < 4; k++)
+		if (c->pe[k])
+			cudaEventDestroy(c->pe[k]);
+	if (c->h_pinned)
+		cudaFreeHost(c->h_pinned);
+	if (c->own_stream)
+		cudaStreamDestroy(c->own_stream);
+	if (c->s_in)
+		cudaStreamDestroy(c->s_in);
+	if (c->s_out)
+		cudaStreamDestroy(c->s_out);
+	delete c;
+}
+
+extern "C" int cb_set_stream(cb_ctx *c, void *stream) {
+	if (!c)
+		return CB_EINVAL;
+	CU(c, cudaStreamSynchronize(c->stream));
+	c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+	return CB_OK;
+}
+
+extern "C" int cb_synchronize(cb_ctx *c) {
+	if (!c)
+		return CB_EINVAL;
+	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
+extern "C" void *cb_host_alloc(cb_ctx *c, size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		if (c)
+			fail(c, CB_ENOMEM, "cudaMallocHost(%zu) failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void cb_host_free(cb_ctx *, void *p) {
+	if (p)
+		cudaFreeHost(p);
+}
+
+// =============================================================================== CoDel
+extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
+	if (!c)
+		return CB_EINVAL;
+	// utils.assertClaimDelay, lib/utils.js:188-195: finite, > 0, integral
+	if (!isfinite(target_ms) || !(target_ms > 0) || target_ms != floor(target_ms))
+		return fail(c, CB_EINVAL, "targetClaimDelay must be a positive integer number of ms");
+	DevState h;
+	memset(&h, 0, sizeof(h));
+	h.target = target_ms;
+	CU(c, cudaMemcpyAsync(c->g, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	c->codel_ready = true;
+	return CB_OK;
+}
+
+extern "C" int cb_codel_get_state(cb_ctx *c, cb_codel_state *out) {
+	if (!c || !out)
+		return CB_EINVAL;
+	cb_batch_stats st;
+	int rc = fetch_stats(c, &st, false);
+	if (rc)
+		return rc;
+	*out = st.state;
+	return CB_OK;
+}
+
+extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
+	if (!c || !in)
+		return CB_EINVAL;
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	DevState h;
+	CU(c, cudaMemcpyAsync(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	h.F = in->first_above_time;
+	h.D = in->drop_next;
+	h.C = in->count;
+	h.B = in->dropping ? 1 : 0;
+	h.hasE = in->has_last_empty ? 1 : 0;
+	h.E = in->last_empty;
+	CU(c, cudaMemcpyAsync(c->g, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
+extern "C" int cb_codel_empty(cb_ctx *c, int64_t now_ns) {
+	if (!c)
+		return CB_EINVAL;
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	empty_kernel<<<1, 1, 0, c->stream>>>(c->g, now_ns);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	return CB_OK;
+}
+
+extern "C" int cb_codel_max_idle(cb_ctx *c, int64_t now_ns, double *out_ms) {
+	if (!c || !out_ms)
+		return CB_EINVAL;
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	max_idle_kernel<<<1, 1, 0, c->stream>>>(c->g, now_ns, c->d_dbl);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(out_ms, c->d_dbl, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
+extern "C" int cb_codel_overloaded(cb_ctx *c, int64_t start_ns, int64_t now_ns, int *drop) {
+	if (!c || !drop)
+		return CB_EINVAL;
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	overloaded_one_kernel<<<1, 1, 0, c->stream>>>(c->g, start_ns, now_ns, c->d_ints + 5);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(drop, c->d_ints + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
+// =============================================================================== batches
+extern "C" int cb_admit_batch(cb_ctx *c, const int64_t *start_ns, const int64_t *now_ns, const uint8_t *flags,
+    size_t n, uint8_t *decision, int32_t *slot, int32_t *backend, cb_batch_stats *stats) {
+	if (!c)
+		return CB_EINVAL;
+	return host_batch<true>(c, start_ns, now_ns, flags, n, decision, slot, backend, stats);
+}
+extern "C" int cb_admit_batch_ms(cb_ctx *c, const double *start_ms, const double *now_ms, const uint8_t *flags,
+    size_t n, uint8_t *decision, int32_t *slot, int32_t *backend, cb_batch_stats *stats) {
+	if (!c)
+		return CB_EINVAL;
+	return host_batch<false>(c, start_ms, now_ms, flags, n, decision, slot, backend, stats);
+}
+extern "C" int cb_admit_batch_dev(cb_ctx *c, const int64_t *d_start, const int64_t *d_now, const uint8_t *d_flags,
+    size_t n, uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
+	if (!c)
+		return CB_EINVAL;
+	return launch_batch<true>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend);
+}
+extern "C" int cb_admit_batch_ms_dev(cb_ctx *c, const double *d_start, const double *d_now, const uint8_t *d_flags,
+    size_t n, uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
+	if (!c)
+		return CB_EINVAL;
+	return launch_batch<false>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend);
+}
+extern "C" int cb_batch_stats_get(cb_ctx *c, cb_batch_stats *out) {
+	if (!c || !out)
+		return CB_EINVAL;
+	return fetch_stats(c, out, false);
+}
+
+// ============================================================================== topology
+extern "C" int cb_backends_set(cb_ctx *c, const cb_backend *tbl, int32_t B, const double *insert_u, int32_t nslots,
+    int mode) {
+	if (!c || B < 0 || nslots < 0 || (B > 0 && !insert_u))
+		return c ? fail(c, CB_EINVAL, "bad backend table arguments") : CB_EINVAL;
+	if (mode != CB_BALANCE_UNIFORM && mode != CB_BALANCE_SRV_WEIGHTED)
+		return fail(c, CB_EINVAL, "unknown balance mode %d", mode);
+	if (mode == CB_BALANCE_SRV_WEIGHTED && !tbl)
+		return fail(c, CB_EINVAL, "weighted mode needs the SRV table");
+	for (int k = 0; k < B; k++)
+		if (!(insert_u[k] >= 0.0 && insert_u[k] < 1.0))
+			return fail(c, CB_EINVAL, "insert_u[%d] not in [0,1)", k);
+	c->B = 0; // the old list is replaced
+	int rc = ensure_topology(c, B, nslots);
+	if (rc)
+		return rc;
+	c->B = B;
+	c->target_slots = nslots;
+	c->nslots = 0;
+	c->mode = mode;
+	if (B == 0) {
+		int z[3] = {0, 0, 0};
+		CU(c, cudaMemcpy(c->d_ints, z, sizeof(z), cudaMemcpyHostToDevice));
+		return CB_OK;
+	}
+	double *d_us = nullptr;
+	CU(c, cudaMalloc((void **)&d_us, sizeof(double) * (B > 0 ? B : 1)));
+	CU(c, cudaMemcpyAsync(d_us, insert_u, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+	if (tbl) {
+		int32_t *hp = (int32_t *)malloc(sizeof(int32_t) * 2 * B);
+		for (int k = 0; k < B; k++) {
+			hp[k] = tbl[k].priority;
+			hp[B + k] = tbl[k].weight;
+		}
+		cudaMemcpyAsync(c->d_prio, hp, sizeof(int32_t) * B, cudaMemcpyHostToDevice, c->stream);
+		cudaMemcpyAsync(c->d_weight, hp + B, sizeof(int32_t) * B, cudaMemcpyHostToDevice, c->stream);
+		cudaStreamSynchronize(c->stream);
+		free(hp);
+	}
+	pref_build_kernel<<<1, TOPO_TPB, 0, c->stream>>>(c->d_keys, B, d_us);
+	c->launches++;
+	CU(c, cudaMemcpyAsync(c->d_ints, &B, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+	CU(c, cudaGetLastError());
+	rc = rebuild_slots(c);
+	cudaStreamSynchronize(c->stream);
+	cudaFree(d_us);
+	return rc;
+}
+
+extern "C" int cb_backend_added(cb_ctx *c, int32_t key, const cb_backend *be, double u) {
+	if (!c || key < 0 || !(u >= 0.0 && u < 1.0))
+		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
+	int need_keys = (key + 1 > c->B + 1) ? key + 1 : c->B + 1;
+	int rc = ensure_topology(c, need_keys, c->target_slots);
+	if (rc)
+		return rc;
+	if (be) {
+		CU(c, cudaMemcpyAsync(c->d_prio + key, &be->priority, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+		CU(c, cudaMemcpyAsync(c->d_weight + key, &be->weight, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	}
+	pref_insert_kernel<<<1, TOPO_TPB, 0, c->stream>>>(c->d_keys, c->d_ints, key, u);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	c->B++;
+	return rebuild_slots(c);
+}
+
+extern "C" int cb_backend_removed(cb_ctx *c, int32_t key) {
+	if (!c)
+		return CB_EINVAL;
+	pref_remove_kernel<<<1, TOPO_TPB, 0, c->stream>>>(c->d_keys, c->d_ints, key, c->d_ints + 3);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	int status = 0;
+	CU(c, cudaMemcpyAsync(&status, c->d_ints + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	if (status != 0) // mod_assert.notStrictEqual(idx, -1, ...), lib/pool.js:295
+		return fail(c, CB_EINVAL, "resolver key %d not found", key);
+	c->B--;
+	return rebuild_slots(c);
+}
+
+extern "C" int cb_reshuffle(cb_ctx *c, double u) {
+	if (!c || !(u >= 0.0 && u < 1.0))
+		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
+	if (c->B <= 1)
+		return CB_OK; // lib/pool.js:502-503
+	pref_reshuffle_kernel<<<1, TOPO_TPB, 0, c->stream>>>(c->d_keys, c->d_ints, u);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	return rebuild_slots(c);
+}
+
+extern "C" int cb_backends_get(cb_ctx *c, int32_t *n_keys, int32_t *keys_out, int32_t *n_slots,
+    int32_t *slot_backend_out) {
+	if (!c)
+		return CB_EINVAL;
+	if (n_keys)
+		*n_keys = c->B;
+	if (n_slots)
+		*n_slots = (c->B > 0) ? c->nslots : 0;
+	if (keys_out && c->B > 0)
+		CU(c, cudaMemcpyAsync(keys_out, c->d_keys, sizeof(int32_t) * c->B, cudaMemcpyDeviceToHost, c->stream));
+	if (slot_backend_out && c->B > 0 && c->nslots > 0)
+		CU(c, cudaMemcpyAsync(slot_backend_out, c->d_slot_backend, sizeof(int32_t) * c->nslots,
+		    cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
+extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *dead, int32_t B, int32_t target,
+    int32_t max, int singleton, int32_t *want_out, int32_t *add_out, int32_t *n_add, int32_t *rm_key_out,
+    int32_t *rm_ord_out, int32_t *n_rm) {
+	if (!c || B < 0 || (B > 0 && (!have || !dead)))
+		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
+	if (target < 0) // mod_assert.ok(target >= 0), lib/utils.js:248
+		return fail(c, CB_EINVAL, "target must be >= 0");
+	if (max < target) // mod_assert.ok(max >= target), lib/utils.js:249
+		return fail(c, CB_EINVAL, "max must be >= target");
+	long long total_have = 0;
+	for (int k = 0; k < B; k++) {
+		if (have[k] < 0)
+			return fail(c, CB_EINVAL, "have[%d] < 0", k);
+		total_have += have[k];
+	}
+	size_t nb = (size_t)(B > 0 ? B : 1), na = (size_t)max + 1, nr = (size_t)total_have + 1;
+	int32_t *d_have = nullptr, *d_want = nullptr, *d_add = nullptr, *d_rk = nullptr, *d_ro = nullptr;
+	uint8_t *d_dead = nullptr;
+	int *d_cnt = nullptr;
+	CU(c, cudaMalloc((void **)&d_have, nb * 4));
+	CU(c, cudaMalloc((void **)&d_want, nb * 4));
+	CU(c, cudaMalloc((void **)&d_dead, nb));
+	CU(c, cudaMalloc((void **)&d_add, na * 4));
+	CU(c, cudaMalloc((void **)&d_rk, nr * 4));
+	CU(c, cudaMalloc((void **)&d_ro, nr * 4));
+	CU(c, cudaMalloc((void **)&d_cnt, 8));
+	cudaStream_t s = c->stream;
+	if (B > 0) {
+		CU(c, cudaMemcpyAsync(d_have, have, nb * 4, cudaMemcpyHostToDevice, s));
+		CU(c, cudaMemcpyAsync(d_dead, dead, nb, cudaMemcpyHostToDevice, s));
+	}
+	plan_rebalance_kernel<<<1, 1, 0, s>>>(d_have, d_dead, B, target, max, singleton, d_want, d_add, d_cnt, d_rk,
+	    d_ro, d_cnt + 1);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	int cnt[2] = {0, 0};
+	CU(c, cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaStreamSynchronize(s));
+	if (want_out && B > 0)
+		CU(c, cudaMemcpy(want_out, d_want, nb * 4, cudaMemcpyDeviceToHost));
+	if (add_out && cnt[0] > 0)
+		CU(c, cudaMemcpy(add_out, d_add, (size_t)cnt[0] * 4, cudaMemcpyDeviceToHost));
+	if (rm_key_out && cnt[1] > 0)
+		CU(c, cudaMemcpy(rm_key_out, d_rk, (size_t)cnt[1] * 4, cudaMemcpyDeviceToHost));
+	if (rm_ord_out && cnt[1] > 0)
+		CU(c, cudaMemcpy(rm_ord_out, d_ro, (size_t)cnt[1] * 4, cudaMemcpyDeviceToHost));
+	if (n_add)
+		*n_add = cnt[0];
+	if (n_rm)
+		*n_rm = cnt[1];
+	cudaFree(d_have);
+	cudaFree(d_want);
+	cudaFree(d_dead);
+	cudaFree(d_add);
+	cudaFree(d_rk);
+	cudaFree(d_ro);
+	cudaFree(d_cnt);
+	return CB_OK;
+}
+
+// ============================================================================= multi-GPU
+extern "C" int cb_comm_unique_id(void *out, size_t *bytes) {
+	if (!out || !bytes || *bytes < sizeof(nccl_uid))
+		return fail(nullptr, CB_EINVAL, "need a %zu-byte buffer", sizeof(nccl_uid));
+	if (!g_nccl.load())
+		return fail(nullptr, CB_ENCCL, "libnccl.so.2 not found: %s", dlerror());
+	nccl_uid id;
+	int r = g_nccl.GetUniqueId(&id);
+	if (r != 0)
+		return fail(nullptr, CB_ENCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	memcpy(out, &id, sizeof(id));
+	*bytes = sizeof(id);
+	return CB_OK;
+}
+
+extern "C" int cb_comm_init(cb_ctx *c, int nranks, int rank, const void *unique_id, size_t bytes) {
+	if (!c || nranks < 1 || rank < 0 || rank >= nranks || !unique_id || bytes < sizeof(nccl_uid))
+		return c ? fail(c, CB_EINVAL, "bad communicator arguments") : CB_EINVAL;
+	if (!g_nccl.load())
+		return fail(c, CB_ENCCL, "libnccl.so.2 not found");
+	CU(c, cudaSetDevice(c->device));
+	nccl_uid id;
+	memcpy(&id, unique_id, sizeof(id));
+	int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+	if (r != 0) {
+		c->comm = nullptr;
+		return fail(c, CB_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	}
+	c->nranks = nranks;
+	c->rank = rank;
+	return CB_OK;
+}
+
+extern "C" int cb_allreduce_counts(cb_ctx *c) {
+	if (!c)
+		return CB_EINVAL;
+	if (!c->comm)
+		return fail(c, CB_ESTATE, "cb_comm_init has not been called");
+	// {drops, admits, n} of the last batch, summed over ranks, in place in the control block
+	unsigned long long *buf = (unsigned long long *)((char *)c->g + offsetof(DevState, gcounts));
+	int r = g_nccl.AllReduce(buf, buf, 3, NCCL_UINT64, NCCL_SUM, c->comm, c->stream);
+	if (r != 0)
+		return fail(c, CB_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	return CB_OK;
+}
+
+// =========================================================================== measurement
+extern "C" int cb_profile_enable(cb_ctx *c, int on) {
+	if (!c)
+		return CB_EINVAL;
+	c->prof = on != 0;
+	for (int k = 0; k < CB_K_COUNT; k++) {
+		c->prof_ms[k] = 0;
+		c->prof_n[k] = 0;
+	}
+	return CB_OK;
+}
+extern "C" int cb_profile_get(cb_ctx *c, double ms_out[CB_K_COUNT], uint64_t launches_out[CB_K_COUNT]) {
+	if (!c)
+		return CB_EINVAL;
+	for (int k = 0; k < CB_K_COUNT; k++) {
+		if (ms_out)
+			ms_out[k] = c->prof_ms[k];
+		if (launches_out)
+			launches_out[k] = c->prof_n[k];
+	}
+	return CB_OK;
+}
+extern "C" uint64_t cb_launch_count(const cb_ctx *c) { return c ? c->launches : 0; }
