@@ -1,0 +1,380 @@
+#!/usr/bin/env python3
+"""bench.py -- claim-queue admissions/sec (CoDel + backend-slot pick) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+A "step" is one pass of the hot path (scan -> resolve -> emit kernels behind
+cb_admit_batch_dev) over one batch of synthetic pending claims.  Workloads are the
+BASELINE.json configs:
+
+    c2  2^20 claims / step,   64 backends,  256 slots     (configs[1]; default at N=1)
+    c3  2^24 claims / step, 1024 backends, 4096 slots     (configs[2])
+    c4  2^23 claims / step / GPU, 4096 backends           (configs[3]: 64M over 8 GPUs)
+    c5  2^24 claims / step / GPU, sustained overload       (configs[4]: streamed chunks)
+
+The (W+K) batches of a run are consecutive segments of ONE seeded trace, all resident in HBM
+before the timed region, so every step reads cold data (the run's inputs are many times the
+126 MB L2) and the ControlledDelay state chains from batch to batch on the device.
+
+Metric value = claims decided per second, whole job (all ranks), inputs resident in HBM.
+`e2e` = the same through the host-buffer C entry point (pinned host arrays in, decisions and
+slots back on the host every step).  `roofline` is for the dominant kernel (the scan kernel:
+16 algorithmic bytes per claim) from CUDA events recorded around each kernel on
+the launching stream in a separate profiling pass.  `cpu_baseline` is the C restatement of the
+reference path (oracle/, pinned bit-for-bit to the reference's own JS) on one host core.
+
+--impl reference times the reference's OWN JavaScript (lib/queue.js + lib/codel.js verbatim)
+under the SpiderMonkey engine vendored in the reference tree (oracle/_ref), one core -- the
+path is a sequential state machine and Node itself is single threaded.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from oracle import tracegen  # noqa: E402  (input generator only; not on the timed path)
+
+WORKLOADS = {
+    #        claims/step/GPU  backends  slots   generator extras
+    "c2": dict(n=1 << 20, B=64, S=256, gen={}),
+    "c3": dict(n=1 << 24, B=1024, S=4096, gen={}),
+    "c4": dict(n=1 << 23, B=4096, S=16384, gen={}),
+    "c5": dict(n=1 << 24, B=4096, S=16384, gen={"all_overloaded_from": 1 << 20}),
+}
+TARGET_MS = 5
+ALG_BYTES_SCAN = 16      # start_ns 8 + now_ns 8 (read once by the scan kernel)
+ALG_BYTES_STEP = 21      # + decision 1 + slot 4
+REF_SAMPLE = 1 << 18     # claims per step for --impl reference (bounded CPU sample)
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_trace(wl, total_claims, rank):
+    w = WORKLOADS[wl]
+    seed = tracegen.SEED + 7919 * rank
+    return tracegen.gen_trace(total_claims, seed=seed, target_ns=TARGET_MS * 1_000_000, **w["gen"])
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args, wl):
+    """The reference's own CPU implementation of the path on this box's host cores."""
+    from oracle import oracle as O
+    from oracle import ref
+    w = WORKLOADS[wl]
+    n = min(REF_SAMPLE, w["n"])
+    params = dict(t0=10**9, de=1000, target_ns=TARGET_MS * 1_000_000, unit=1 << 16, start_overloaded=False,
+                  all_overloaded_from=w["gen"].get("all_overloaded_from", -1))
+    times, decided = [], 0
+    kind = "reference" if ref.available() else "port"
+    for step in range(args.warmup + args.steps):
+        seed = tracegen.SEED + step
+        if kind == "reference":
+            r = ref.bench(seed, n, params, TARGET_MS, w["S"])
+            dt = r["drain_ms"] / 1e3
+        else:
+            s, nw = tracegen.gen_trace(n, seed=seed, **{k: v for k, v in params.items()})
+            cd = O.new_codel(TARGET_MS)
+            t0 = time.perf_counter()
+            O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)
+            dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(max(dt, 1e-9))
+            decided += n
+    total = sum(times)
+    value = decided / total
+    sample = ("%d claims per step of the %s trace spec (same generator, JS side); timed: the drain loop "
+              "lib/pool.js:733-753 = Queue.shift + ControlledDelay.overloaded per claim" % (n, wl))
+    line = {
+        "impl": "reference", "metric": "claim-queue admissions/sec (CoDel + backend-slot pick)",
+        "value": value, "unit": "claims/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
+        "config": {"workload": wl, "claims_per_step": n, "backends": w["B"], "slots": w["S"],
+                   "target_ms": TARGET_MS, "engine": ("reference lib/queue.js+lib/codel.js verbatim under SpiderMonkey 1.7 "
+                                                      "(vendored in the reference tree; Node.js is not installed)"
+                                                      if kind == "reference" else "C restatement (oracle/), linked-list queue")},
+        "cpu_baseline": {"value": value, "unit": "claims/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "claims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ CUDA arm
+def cpu_baseline(wl):
+    """The oracle's C restatement (flat-array variant = the fastest honest CPU form), 1 core,
+    on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    w = WORKLOADS[wl]
+    n = min(1 << 24, 4 * w["n"])
+    s, nw = tracegen.gen_trace(n, target_ns=TARGET_MS * 1_000_000, **w["gen"])
+    best = None
+    for _ in range(3):
+        cd = O.new_codel(TARGET_MS)
+        t0 = time.perf_counter()
+        O.drain(cd, s, nw, nslots=w["S"], variant="flat", want_out=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    cd = O.new_codel(TARGET_MS)
+    t0 = time.perf_counter()
+    m = min(n, 1 << 22)
+    O.drain(cd, s[:m], nw[:m], nslots=w["S"], variant="list", want_out=True)
+    dl = time.perf_counter() - t0
+    return {"value": n / best, "unit": "claims/s", "cores": 1, "kind": "port",
+            "sample": "%d claims of the %s trace, best of 3; C restatement of lib/codel.js + lib/pool.js:733-753 over flat "
+                      "arrays (oracle/cueball_oracle.c, -O2 -ffp-contract=off)" % (n, wl),
+            "linked_list_variant_claims_per_s": m / dl}
+
+
+def run_cuda(args, wl, extra=True):
+    import torch
+    import torch.distributed as dist
+
+    import cueball_b200 as cb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOADS[wl]
+    n, K, W = w["n"], args.steps, args.warmup
+    nb = W + K
+    start, now = make_trace(wl, n * nb, rank)
+
+    ctx = cb.Context(local)
+    ctx.codel_init(TARGET_MS)
+    ctx.backends_set(w["B"], tracegen.gen_insert_draws(w["B"]), w["S"])
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:  # one communicator per context, id from rank 0
+        obj = [cb.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(world, rank, obj[0])
+
+    d_start = torch.from_numpy(start).to(dev)
+    d_now = torch.from_numpy(now).to(dev)
+    d_dec = torch.empty(n * nb, dtype=torch.uint8, device=dev)
+    d_slot = torch.empty(n * nb, dtype=torch.int32, device=dev)
+
+    def step_dev(b):
+        lo, hi = b * n, (b + 1) * n
+        ctx.admit_batch_dev(d_start[lo:hi], d_now[lo:hi], None, d_dec[lo:hi], d_slot[lo:hi])
+        if world > 1:
+            ctx.allreduce_counts()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for b in range(W):
+        step_dev(b)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for b in range(W, W + K):
+        step_dev(b)
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    st = ctx.stats()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = world * n * K / (ms / 1e3)
+
+    # ---- per-kernel profile pass (CUDA events around each kernel, same stream) --------------
+    ctx.set_state({"count": 0, "drop_next": 0.0, "first_above_time": 0.0, "dropping": False, "last_empty": None})
+    ctx.profile_enable(True)
+    for b in range(W, W + min(K, 20)):
+        lo, hi = b * n, (b + 1) * n
+        ctx.admit_batch_dev(d_start[lo:hi], d_now[lo:hi], None, d_dec[lo:hi], d_slot[lo:hi])
+    kms, kcnt = ctx.profile_get()
+    ctx.profile_enable(False)
+    scan_ms = kms[cb._native.K_SCAN] / max(kcnt[cb._native.K_SCAN], 1)
+    peak, peak_src = peaks()
+    achieved = ALG_BYTES_SCAN * n / (scan_ms / 1e3) / 1e9
+    roof = {"bound": "hbm", "kernel": "cb::scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": TRAFFIC.get(wl), "peak_source": peak_src,
+            "alg_bytes_per_claim": ALG_BYTES_SCAN,
+            "kernel_ms": {"scan": scan_ms, "resolve": kms[1] / max(kcnt[1], 1), "emit": kms[2] / max(kcnt[2], 1)},
+            "step": {"alg_bytes_per_claim": ALG_BYTES_STEP,
+                     "achieved": ALG_BYTES_STEP * n * K / (ms / 1e3) / 1e9 / 1.0,
+                     "frac": ALG_BYTES_STEP * n * K / (ms / 1e3) / 1e9 / peak}}
+
+    # ---- end to end: host buffers through the public entry point ----------------------------
+    ke = min(K, 10)
+    hs = torch.from_numpy(start[W * n:(W + ke) * n]).pin_memory().numpy()
+    hn = torch.from_numpy(now[W * n:(W + ke) * n]).pin_memory().numpy()
+    hdec = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+    hslot = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+    ctx.set_stream(None)
+    ctx.set_state({"count": 0, "drop_next": 0.0, "first_above_time": 0.0, "dropping": False, "last_empty": None})
+    ctx.admit_batch(hs[:n], hn[:n])  # warm the staging buffers
+    ctx.admit_batch(hs[:n], hn[:n])
+    barrier()
+    t0 = time.perf_counter()
+    drops = 0
+    for b in range(ke):
+        dec, slot, _, est = ctx.admit_batch(hs[b * n:(b + 1) * n], hn[b * n:(b + 1) * n],
+                                            out_decision=hdec, out_slot=hslot)
+        drops += est.drops  # the step's result is read on the host
+    barrier()
+    te = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([te], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e = {"value": world * n * ke / te, "unit": "claims/s", "h2d_bytes_per_step": 16 * n,
+           "d2h_bytes_per_step": 5 * n + 176, "steps": ke, "host_memory": "pinned inputs and outputs"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return None
+    line = {
+        "metric": "claim-queue admissions/sec (CoDel + backend-slot pick)", "value": value, "unit": "claims/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
+        "config": {"workload": wl, "claims_per_step_per_gpu": n, "backends": w["B"], "slots": w["S"],
+                   "target_ms": TARGET_MS, "interval_ms": 100, "parallelism": "queue segment per GPU" if world > 1 else "1 GPU",
+                   "collective": "1 ncclAllReduce(3 x u64) per step" if world > 1 else None,
+                   "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
+                         % (nb, 16.0 * n * nb / 1e6),
+                   "state": "ControlledDelay state chained on device across steps",
+                   "admit_fraction": st.total_admits / max(st.total_admits + st.total_drops, 1)},
+        "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }
+    if extra:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    if world > 1:
+        line["global_drops_last_step"] = st.global_drops
+        dist.destroy_process_group()
+    return line
+
+
+# DRAM traffic per scan-kernel launch from `ncu --set full` captures (profiles/): bytes
+TRAFFIC = {}
+_tp = os.path.join(ROOT, "profiles", "traffic.json")
+if os.path.exists(_tp):
+    with open(_tp) as _f:
+        TRAFFIC = json.load(_f)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the cpu_baseline leg and the c3 side measurement")
+    args = ap.parse_args()
+    wl = args.workload or ("c2" if args.gpus == 1 else "c4")
+    dk, dw = {"c2": (50, 5), "c3": (10, 3), "c4": (20, 3), "c5": (10, 3)}[wl]
+    args.steps = args.steps if args.steps is not None else dk
+    args.warmup = max(3, args.warmup if args.warmup is not None else dw)
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, wl)
+        return
+    line = run_cuda(args, wl, extra=not args.no_extra)
+    if line is None:
+        return
+    if not args.no_extra and args.gpus == 1 and wl == "c2":
+        # the HBM-roofline-relevant size: one 16M-claim batch per step (BASELINE config C3)
+        a3 = argparse.Namespace(gpus=1, steps=5, warmup=3)
+        c3 = run_cuda(a3, "c3", extra=False)
+        line["c3"] = {k: c3[k] for k in ("value", "unit", "ms_per_step", "steps", "roofline", "e2e", "gpu_launches")}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

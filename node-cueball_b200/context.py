@@ -74,9 +74,11 @@ class Context(object):
         return bool(out.value)
 
     # ---------------------------------------------------------------- batches
-    def admit_batch(self, start, now, flags=None, want_backend=False, want_slot=True, want_decision=True):
+    def admit_batch(self, start, now, flags=None, want_backend=False, want_slot=True, want_decision=True,
+                    out_decision=None, out_slot=None, out_backend=None):
         """Host (numpy) buffers through the host-buffer C entry point.
-        start/now: int64 ns or float64 ms.  Returns (decision, slot, backend, BatchStats)."""
+        start/now: int64 ns or float64 ms.  Returns (decision, slot, backend, BatchStats).
+        out_* let the caller supply (e.g. pinned) output arrays."""
         start = np.ascontiguousarray(start)
         now = np.ascontiguousarray(now)
         if start.dtype != now.dtype or start.shape != now.shape or start.ndim != 1:
@@ -92,9 +94,12 @@ class Context(object):
             flags = np.ascontiguousarray(flags, dtype=np.uint8)
             if flags.shape != start.shape:
                 raise ValueError("flags length mismatch")
-        dec = np.empty(n, np.uint8) if want_decision else None
-        slot = np.empty(n, np.int32) if want_slot else None
-        be = np.empty(n, np.int32) if want_backend else None
+        dec = out_decision if out_decision is not None else (np.empty(n, np.uint8) if want_decision else None)
+        slot = out_slot if out_slot is not None else (np.empty(n, np.int32) if want_slot else None)
+        be = out_backend if out_backend is not None else (np.empty(n, np.int32) if want_backend else None)
+        for a, dt in ((dec, np.uint8), (slot, np.int32), (be, np.int32)):
+            if a is not None and (a.dtype != dt or a.shape[0] < n or not a.flags["C_CONTIGUOUS"]):
+                raise ValueError("bad output array")
         st = N.BatchStats()
         self._ck(fn(self._h, _np_ptr(start), _np_ptr(now), _np_ptr(flags), n, _np_ptr(dec), _np_ptr(slot),
                     _np_ptr(be), C.byref(st)))
