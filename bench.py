@@ -219,7 +219,9 @@ def run_cuda(args, wl, extra=True):
     ctx = cb.Context(local)
     ctx.codel_init(TARGET_MS)
     ctx.backends_set(w["B"], tracegen.gen_insert_draws(w["B"]), w["S"])
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy-default) stream: the library's kernels and the timing events share it
+    stream = torch.cuda.Stream(device=dev)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     if world > 1:  # one communicator per context, id from rank 0
         obj = [cb.Context.comm_unique_id() if rank == 0 else None]
@@ -230,6 +232,7 @@ def run_cuda(args, wl, extra=True):
     d_now = torch.from_numpy(now).to(dev)
     d_dec = torch.empty(n * nb, dtype=torch.uint8, device=dev)
     d_slot = torch.empty(n * nb, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
 
     def step_dev(b):
         lo, hi = b * n, (b + 1) * n

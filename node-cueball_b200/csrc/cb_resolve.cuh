@@ -19,6 +19,7 @@
 // (CB_PATH_SEQUENTIAL), writing the outputs itself.
 #pragma once
 #include "cb_device.cuh"
+#include "cb_scan.cuh"
 
 namespace cb {
 
@@ -31,7 +32,7 @@ struct ResolveParams {
 	unsigned long long n;
 	unsigned long long tiles;
 	DevState *g;
-	const TileDesc *desc;
+	const unsigned long long *desc;
 	const unsigned int *ev_count;
 	const unsigned long long *ev;
 	// compacted, ordered events + per-event speculation
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			k += has2 ? 2 : 1;
 		}
 		// ---- final ControlledDelay state -------------------------------------------------
-		double F = ld_relaxed_f64(&p.desc[p.tiles - 1].vP);
+		double F = materialise<NS>(ld_relaxed_u64(&p.desc[p.tiles - 1]) & DESC_CODE_MASK, p.now, g);
 		if (FLAGS) {
 			const unsigned long long lm = g->last_marker_p1;
 			if (lm) {

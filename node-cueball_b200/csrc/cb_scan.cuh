@@ -1,39 +1,60 @@
-// cb_scan.cuh -- pass 1 of the admission path: the streaming scan kernel.
+// cb_scan.cuh -- pass 1 of the admission path: the streaming scan kernel (v2).
 //
 // Reads every claim's (start, now[, flags]) exactly once from HBM (16 B/claim, 17 with
-// flags), converts to milliseconds like utils.currentMillis() (lib/utils.js:198-204),
-// evaluates ControlledDelay#canDrop (lib/codel.js:34-46) for ALL claims in parallel and
-// reduces the stream to the handful of positions where the canDrop class changes.
+// flags), evaluates ControlledDelay#canDrop (lib/codel.js:34-46) for ALL claims in parallel
+// and reduces the stream to the handful of positions where the canDrop class changes.
 //
 // canDrop's only loop-carried variable is cd_first_above_time (F).  Per claim it is
 // rewritten by one of three functions
 //      !above                : F' = 0                      CONST(0)
 //       above, marker before : F' = now+100                CONST(now+100)
 //       above                : F' = F ? F : now+100        PASS(now+100)
-// which compose associatively ("last CONST wins, then the first PASS fills a zero"), so
-// F before every claim is an exclusive scan: thread-serial over 8 claims, ballot+shuffle
-// across the warp, shared memory across the CTA, decoupled look-back across tiles.
-// (A CB_F_EMPTY_AFTER marker -- codel.empty(), lib/codel.js:91-94 -- is applied as a reset
-// in front of the NEXT claim, which is equivalent and keeps the carried value meaningful.)
+// which compose associatively ("last CONST wins, then the first PASS fills a zero").  Every
+// non-zero F is `now[a] + 100` for some claim index a, so compositions are carried as
+// INDICES (integer-only, one 64-bit look-back descriptor per tile) and turned into doubles
+// only where a claim's class needs the value.
+//
+// Layout: a CTA owns a tile of 2048 consecutive claims, a warp a chunk of 256 = 4 rows of 64;
+// in a row lane l owns claims 2l and 2l+1, i.e. one fully coalesced 128-bit load per array
+// per row, no shared-memory staging.  Phase 1 (integers only) classifies above/below --
+// sojourn vs target is decided on the int64 nanoseconds whenever the gap to the target
+// exceeds the worst-case rounding of the millisecond doubles, and exactly as
+// utils.currentMillis() (lib/utils.js:198-204) otherwise -- and builds the row/warp/tile
+// compositions.  Phase 2 touches FP64 only in rows that contain above-target claims.
+// The decoupled look-back across tiles runs per warp, and only for warps whose leading claims
+// actually inherit F from an earlier tile: healthy traffic does no look-back at all.
+// (A CB_F_EMPTY_AFTER marker -- codel.empty(), lib/codel.js:91-94 -- is applied as a reset in
+// front of the NEXT claim, which is equivalent and keeps the carried value meaningful.)
 #pragma once
 #include "cb_device.cuh"
 
 namespace cb {
 
-struct Agg { // a composed F-update: F_out = isconst ? v : (F_in ? F_in : v)
+constexpr int ROWS = 4;            // rows of 64 claims per warp chunk
+constexpr int CHUNK = ROWS * 64;   // 256 claims per warp
+static_assert(CHUNK * WARPS == TILE, "tile geometry");
+
+// index-coded F: 0 = F is 0, 1 = the batch's carried-in F, a+2 = now[a] + 100
+constexpr unsigned long long CODE_ZERO = 0, CODE_CARRY = 1;
+// tile descriptor word: [epoch:21 | status:2 | isconst:1 | code:40]
+constexpr int DESC_EPOCH_SHIFT = 43, DESC_STATUS_SHIFT = 41, DESC_CONST_SHIFT = 40;
+constexpr unsigned long long DESC_CODE_MASK = (1ull << 40) - 1;
+constexpr unsigned long long DESC_EPOCH_MASK = (1ull << 21) - 1;
+
+struct IAgg { // composed F-update in index form: F_out = isconst ? code : (F_in ? F_in : code)
 	bool isconst;
-	double v;
+	unsigned long long code;
 };
-__device__ __forceinline__ Agg compose(const Agg &a, const Agg &b) { // a first, then b
+__device__ __forceinline__ IAgg icompose(const IAgg &a, const IAgg &b) { // a first, then b
 	if (b.isconst)
 		return b;
-	Agg r;
+	IAgg r;
 	r.isconst = a.isconst;
-	r.v = (a.v != 0.0) ? a.v : b.v;
+	r.code = (a.code != CODE_ZERO) ? a.code : b.code;
 	return r;
 }
-__device__ __forceinline__ double apply_agg(const Agg &a, double Fin) {
-	return a.isconst ? a.v : (Fin != 0.0 ? Fin : a.v);
+__device__ __forceinline__ unsigned long long iapply(const IAgg &a, unsigned long long in_code) {
+	return a.isconst ? a.code : (in_code != CODE_ZERO ? in_code : a.code);
 }
 
 __device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
@@ -44,330 +65,392 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
 	return r;
 }
 
-// Coalesced load of one warp's 256 consecutive 8-byte elements of two arrays, transposed
-// through a conflict-free XOR-swizzled shared-memory stage so that lane L ends up with
-// elements [8L, 8L+8).  All 8 global loads are issued before the first shared store.
-template <typename T>
-__device__ __forceinline__ void load_warp_blocked2(const T *__restrict__ a, const T *__restrict__ b,
-    T (&oa)[IPT], T (&ob)[IPT], uint4 *stage, int lane) {
-	static_assert(sizeof(T) == 8, "8-byte elements");
-	const uint4 *pa = reinterpret_cast<const uint4 *>(a);
-	const uint4 *pb = reinterpret_cast<const uint4 *>(b);
-	uint4 va[4], vb[4];
-#pragma unroll
-	for (int r = 0; r < 4; r++)
-		va[r] = ld_stream_v4(pa + r * 32 + lane);
-#pragma unroll
-	for (int r = 0; r < 4; r++)
-		vb[r] = ld_stream_v4(pb + r * 32 + lane);
-#pragma unroll
-	for (int r = 0; r < 4; r++) {
-		int g = r * 32 + lane;
-		stage[g ^ ((g >> 3) & 7)] = va[r];
-	}
-	__syncwarp();
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		int g = 4 * lane + k;
-		uint4 x = stage[g ^ ((g >> 3) & 7)];
-		unsigned long long lo = ((unsigned long long)x.y << 32) | x.x;
-		unsigned long long hi = ((unsigned long long)x.w << 32) | x.z;
-		oa[2 * k] = *reinterpret_cast<T *>(&lo);
-		oa[2 * k + 1] = *reinterpret_cast<T *>(&hi);
-	}
-	__syncwarp();
-#pragma unroll
-	for (int r = 0; r < 4; r++) {
-		int g = r * 32 + lane;
-		stage[g ^ ((g >> 3) & 7)] = vb[r];
-	}
-	__syncwarp();
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		int g = 4 * lane + k;
-		uint4 x = stage[g ^ ((g >> 3) & 7)];
-		unsigned long long lo = ((unsigned long long)x.y << 32) | x.x;
-		unsigned long long hi = ((unsigned long long)x.w << 32) | x.z;
-		ob[2 * k] = *reinterpret_cast<T *>(&lo);
-		ob[2 * k + 1] = *reinterpret_cast<T *>(&hi);
-	}
-	__syncwarp();
-}
-
 struct ScanParams {
 	const void *start;
 	const void *now;
 	const uint8_t *flags; // may be null
 	unsigned long long n;
 	DevState *g;
-	TileDesc *desc;
-	unsigned long long epoch;
-	unsigned int *ev_count;  // [tiles]
-	unsigned long long *ev;  // [tiles][EVK]  (index << 2) | class
-	int vec_ok;              // start/now 16-byte aligned
+	unsigned long long *desc; // one word per tile
+	unsigned long long epoch; // 1 .. 2^21-1
+	unsigned int *ev_count;   // [tiles]
+	unsigned long long *ev;   // [tiles][EVK]  (index << 2) | class
+	int vec_ok;               // start/now 16-byte aligned
+	long long target_ns;      // target in ns (integer-domain sojourn test)
 };
 
-template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(TPB, 3) scan_kernel(const ScanParams p) {
+template <bool NS> struct Raw;
+template <> struct Raw<true> {
+	using t = long long;
+	// sojourn vs target in the integer domain; returns 0 below, 1 above, 2 = too close
+	static __device__ __forceinline__ int quick(long long st, long long nw, long long tgt) {
+		const long long d = nw - st;
+		const long long m = (nw >> 50) + 2; // > 2.5 ulp(now_ms) expressed in ns
+		if (d >= tgt + m)
+			return 1;
+		if (d < tgt - m)
+			return 0;
+		return 2;
+	}
+	static __device__ __forceinline__ bool less(long long a, long long b) { return a < b; }
+};
+template <> struct Raw<false> {
+	using t = double;
+	static __device__ __forceinline__ int quick(double, double, long long) { return 2; }
+	static __device__ __forceinline__ bool less(double a, double b) { return a < b; }
+};
+
+template <bool NS>
+__device__ __forceinline__ bool is_above(typename Raw<NS>::t st, typename Raw<NS>::t nw, long long tgt_ns,
+    double target) {
+	const int q = Raw<NS>::quick(st, nw, tgt_ns);
+	if (q != 2)
+		return q == 1;
+	return !(__dsub_rn(TimeIn<NS>::to_ms(nw), TimeIn<NS>::to_ms(st)) < target); // lib/codel.js:35-37
+}
+
+// value of an index-coded F
+template <bool NS>
+__device__ __forceinline__ double materialise(unsigned long long code, const void *now, const DevState *g) {
+	if (code == CODE_ZERO)
+		return 0.0;
+	if (code == CODE_CARRY)
+		return g->F;
 	using raw_t = typename TimeIn<NS>::raw_t;
-	__shared__ uint4 s_stage[WARPS][128];   // 2 KB per warp
-	__shared__ double s_wv[WARPS];
-	__shared__ int s_wconst[WARPS];
-	__shared__ double s_wlastnow[WARPS];
-	__shared__ int s_wlastc[WARPS];
-	__shared__ double s_Fc;
-	__shared__ int s_cprev;
+	const raw_t v = reinterpret_cast<const raw_t *>(now)[code - 2];
+	return __dadd_rn(TimeIn<NS>::to_ms(v), CODEL_INTERVAL);
+}
+
+// Decoupled look-back: F (index-coded) after the last claim of tile t-1.
+__device__ __forceinline__ unsigned long long lookback(const ScanParams &p, unsigned long long t, int lane) {
+	long long base = (long long)t - 1;
+	while (true) {
+		const long long k = base - lane;
+		unsigned long long code = 0;
+		bool term = false;
+		if (k >= 0) {
+			unsigned long long w;
+			do {
+				w = ld_acquire(&p.desc[k]);
+			} while ((w >> DESC_EPOCH_SHIFT) != p.epoch);
+			const unsigned int st = (unsigned int)(w >> DESC_STATUS_SHIFT) & 3u;
+			const bool isc = ((w >> DESC_CONST_SHIFT) & 1ull) != 0;
+			code = w & DESC_CODE_MASK;
+			term = (st == ST_PREFIX) || isc;
+		} else if (k == -1) {
+			code = (p.g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
+			term = true;
+		}
+		const unsigned int tm = __ballot_sync(0xffffffffu, term);
+		if (tm) {
+			const int f = __ffs(tm) - 1; // nearest terminator: tile T = base - f
+			const unsigned long long cT = __shfl_sync(0xffffffffu, code, f);
+			if (cT != CODE_ZERO)
+				return cT;
+			const long long T = base - f;
+			// tiles T+1 .. t-1 are PASS tiles: the first of them fills the zero
+			return (T + 1 <= (long long)t - 1) ? ((unsigned long long)(T + 1) * TILE + 2) : CODE_ZERO;
+		}
+		base -= 32;
+	}
+}
+
+template <bool NS, bool FLAGS>
+__global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
+	using raw_t = typename Raw<NS>::t;
+	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
 	__shared__ unsigned int s_evn;
 	__shared__ unsigned long long s_ev[EVK];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const unsigned long long t = blockIdx.x;
 	const unsigned long long ts = t * (unsigned long long)TILE;
-	const unsigned long long i0 = ts + (unsigned long long)tid * IPT;
+	const unsigned long long cs = ts + (unsigned long long)warp * CHUNK; // chunk start
 	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
 	const raw_t *gnow = reinterpret_cast<const raw_t *>(p.now);
 	const double target = p.g->target;
+	const long long tgt_ns = p.target_ns;
+	const unsigned int lt_mask = (1u << lane) - 1u;
 	if (tid == 0)
 		s_evn = 0;
 
-	// ---- load this thread's 8 consecutive claims ------------------------------------
-	const bool full = (ts + TILE <= p.n);
-	int nvalid = IPT;
-	raw_t rs[IPT], rn[IPT];
+	// ---- loads: one 128-bit load per array per row (claims 2l, 2l+1) -----------------------
+	raw_t rs[ROWS][2], rn[ROWS][2];
+	unsigned int fl[ROWS]; // this lane's two flag bytes per row
+	const bool full = (cs + CHUNK <= p.n);
 	if (full && p.vec_ok) {
-		load_warp_blocked2<raw_t>(gstart + ts + warp * 256, gnow + ts + warp * 256, rs, rn,
-		    s_stage[warp], lane);
-	} else {
-		long long rem = (long long)p.n - (long long)i0;
-		nvalid = rem >= IPT ? IPT : (rem > 0 ? (int)rem : 0);
+		uint4 a[ROWS], b[ROWS];
 #pragma unroll
-		for (int j = 0; j < IPT; j++) {
-			if (j < nvalid) {
-				rs[j] = gstart[i0 + j];
-				rn[j] = gnow[i0 + j];
-			} else {
-				rs[j] = raw_t(0);
-				rn[j] = raw_t(0);
+		for (int r = 0; r < ROWS; r++)
+			a[r] = ld_stream_v4(gstart + cs + r * 64 + 2 * lane);
+#pragma unroll
+		for (int r = 0; r < ROWS; r++)
+			b[r] = ld_stream_v4(gnow + cs + r * 64 + 2 * lane);
+#pragma unroll
+		for (int r = 0; r < ROWS; r++) {
+			unsigned long long x0 = ((unsigned long long)a[r].y << 32) | a[r].x;
+			unsigned long long x1 = ((unsigned long long)a[r].w << 32) | a[r].z;
+			unsigned long long y0 = ((unsigned long long)b[r].y << 32) | b[r].x;
+			unsigned long long y1 = ((unsigned long long)b[r].w << 32) | b[r].z;
+			rs[r][0] = *reinterpret_cast<raw_t *>(&x0);
+			rs[r][1] = *reinterpret_cast<raw_t *>(&x1);
+			rn[r][0] = *reinterpret_cast<raw_t *>(&y0);
+			rn[r][1] = *reinterpret_cast<raw_t *>(&y1);
+		}
+	} else {
+#pragma unroll
+		for (int r = 0; r < ROWS; r++) {
+#pragma unroll
+			for (int j = 0; j < 2; j++) {
+				const unsigned long long i = cs + r * 64 + 2 * lane + j;
+				rs[r][j] = (i < p.n) ? gstart[i] : raw_t(0);
+				rn[r][j] = (i < p.n) ? gnow[i] : raw_t(0);
 			}
 		}
 	}
-	unsigned long long fl8 = 0x0101010101010101ull; // all waiting, no markers
-	unsigned int fprev = 0;                         // flags of claim i0-1
-	if (FLAGS) {
-		if (nvalid == IPT && ((reinterpret_cast<uintptr_t>(p.flags) & 7) == 0)) {
-			fl8 = *reinterpret_cast<const unsigned long long *>(p.flags + i0);
-		} else {
-			fl8 = 0;
-			for (int j = 0; j < nvalid; j++)
-				fl8 |= (unsigned long long)p.flags[i0 + j] << (8 * j);
-		}
-		unsigned int lastb = (unsigned int)(fl8 >> 56);
-		fprev = __shfl_up_sync(0xffffffffu, lastb, 1);
-		if (lane == 0)
-			fprev = (i0 > 0 && nvalid > 0) ? p.flags[i0 - 1] : 0;
-	}
-	// the claim just before the tile (needed for its class and for the monotone check);
-	// issued early so the latency hides behind the conversions below
-	raw_t pstart = raw_t(0), pnow = raw_t(0);
-	unsigned int pfl = F_WAITING, ppfl = 0;
-	if (tid == 0 && t > 0) {
-		pstart = gstart[ts - 1];
-		pnow = gnow[ts - 1];
+#pragma unroll
+	for (int r = 0; r < ROWS; r++) {
+		fl[r] = 0x0101u; // waiting, no markers
 		if (FLAGS) {
-			pfl = p.flags[ts - 1];
-			ppfl = ts >= 2 ? p.flags[ts - 2] : 0;
+			const unsigned long long i = cs + r * 64 + 2 * lane;
+			unsigned int f0 = (i < p.n) ? p.flags[i] : 0u;
+			unsigned int f1 = (i + 1 < p.n) ? p.flags[i + 1] : 0u;
+			fl[r] = f0 | (f1 << 8);
 		}
+	}
+	// The claim just before this warp's chunk (same address in every lane: one broadcast
+	// transaction): its class may end an "ok" run exactly at the chunk boundary, its marker
+	// resets F in front of our first claim, and the clock must not step back across it.
+	const bool have_prev = (cs > 0) && (cs < p.n);
+	raw_t prev_now = raw_t(0);
+	unsigned int prev_bits = 0; // bit0 above, bit1 marker-before, bit2 own marker
+	if (have_prev) {
+		const raw_t pstart = gstart[cs - 1];
+		prev_now = gnow[cs - 1];
+		const unsigned int pf = FLAGS ? p.flags[cs - 1] : 1u, ppf = (FLAGS && cs >= 2) ? p.flags[cs - 2] : 0u;
+		prev_bits = (is_above<NS>(pstart, prev_now, tgt_ns, target) ? 1u : 0u) | ((ppf & F_EMPTY_AFTER) ? 2u : 0u) |
+		    ((pf & F_EMPTY_AFTER) ? 4u : 0u);
 	}
 
-	// ---- per-claim conversion, above flag, thread aggregate -------------------------
-	double nw[IPT];
-	unsigned int above = 0, mk = 0; // bit j: claim j above target / carries a marker
-	Agg ta;
-	ta.isconst = false;
-	ta.v = 0.0;
+	// ---- phase 1: above bits, CONST/PASS types, row -> warp composition (integers only) ----
+	unsigned int A0[ROWS], A1[ROWS], C0[ROWS], C1[ROWS]; // ballots: above / CONST-type, per claim slot
+	int nv[ROWS];                                        // valid claims in the row
+	IAgg wagg;
+	wagg.isconst = false;
+	wagg.code = CODE_ZERO;
 	bool nonmono = false;
+	unsigned int carry_mk = (prev_bits >> 2) & 1u; // marker of the claim before the row (warp-uniform)
+	unsigned long long last_marker = 0;
 #pragma unroll
-	for (int j = 0; j < IPT; j++) {
-		nw[j] = TimeIn<NS>::to_ms(rn[j]);
-		double st = TimeIn<NS>::to_ms(rs[j]);
-		if (j < nvalid) {
-			bool ab = !(__dsub_rn(nw[j], st) < target);
-			bool mprev = FLAGS && (((j == 0 ? fprev : (unsigned int)(fl8 >> (8 * (j - 1)))) & F_EMPTY_AFTER) != 0);
-			if (FLAGS && ((fl8 >> (8 * j)) & F_EMPTY_AFTER))
-				mk |= 1u << j;
-			if (ab)
-				above |= 1u << j;
-			if (!ab) {
-				ta.isconst = true;
-				ta.v = 0.0;
-			} else if (mprev) {
-				ta.isconst = true;
-				ta.v = __dadd_rn(nw[j], CODEL_INTERVAL);
-			} else if (ta.v == 0.0) {
-				ta.v = __dadd_rn(nw[j], CODEL_INTERVAL);
+	for (int r = 0; r < ROWS; r++) {
+		const unsigned long long rbase = cs + r * 64;
+		long long rem = (long long)p.n - (long long)rbase;
+		nv[r] = rem >= 64 ? 64 : (rem > 0 ? (int)rem : 0);
+		const bool v0 = 2 * lane < nv[r], v1 = 2 * lane + 1 < nv[r];
+		const bool ab0 = v0 && is_above<NS>(rs[r][0], rn[r][0], tgt_ns, target);
+		const bool ab1 = v1 && is_above<NS>(rs[r][1], rn[r][1], tgt_ns, target);
+		bool mp0 = false, mp1 = false;
+		if (FLAGS) {
+			const unsigned int mk0 = (fl[r] >> 1) & 1u, mk1 = (fl[r] >> 9) & 1u; // own markers
+			unsigned int up = __shfl_up_sync(0xffffffffu, mk1, 1);
+			if (lane == 0)
+				up = carry_mk;
+			mp0 = up != 0;
+			mp1 = mk0 != 0;
+			carry_mk = __shfl_sync(0xffffffffu, mk1, 31);
+			if (v1 && mk1)
+				last_marker = rbase + 2 * lane + 2;
+			else if (v0 && mk0)
+				last_marker = rbase + 2 * lane + 1;
+		}
+		const bool c0 = v0 && (!ab0 || mp0), c1 = v1 && (!ab1 || mp1);
+		A0[r] = __ballot_sync(0xffffffffu, ab0);
+		A1[r] = __ballot_sync(0xffffffffu, ab1);
+		C0[r] = __ballot_sync(0xffffffffu, c0);
+		C1[r] = __ballot_sync(0xffffffffu, c1);
+		// monotone clock (raw domain: ns-monotone implies ms-monotone)
+		if (v1 && Raw<NS>::less(rn[r][1], rn[r][0]))
+			nonmono = true;
+		{
+			raw_t prevn = __shfl_up_sync(0xffffffffu, rn[r][1], 1);
+			bool haveprevn = lane > 0;
+			if (r > 0) {
+				const raw_t pr = __shfl_sync(0xffffffffu, rn[r - 1][1], 31);
+				if (lane == 0) {
+					prevn = pr;
+					haveprevn = true;
+				}
+			} else if (lane == 0 && have_prev) {
+				prevn = prev_now;
+				haveprevn = true;
 			}
-			if (j > 0 && nw[j] < nw[j - 1])
+			if (v0 && haveprevn && Raw<NS>::less(rn[r][0], prevn))
 				nonmono = true;
 		}
-	}
-
-	// ---- warp-level exclusive composition (ballot: last CONST lane before me) --------
-	const unsigned int cm = __ballot_sync(0xffffffffu, ta.isconst);
-	Agg ex; // composition of lanes < lane
-	{
-		unsigned int prior = cm & ((1u << lane) - 1u);
-		int jl = prior ? (31 - __clz(prior)) : 0;
-		double vj = __shfl_sync(0xffffffffu, ta.v, jl);
-		int nx = prior ? (jl + 1) : 0; // first PASS lane after the CONST lane (or lane 0)
-		double vnx = __shfl_sync(0xffffffffu, ta.v, nx & 31);
-		if (prior) {
-			ex.isconst = true;
-			ex.v = (vj != 0.0) ? vj : ((nx < lane) ? vnx : 0.0);
+		// row composition in index form
+		IAgg ra;
+		const unsigned int cm = C0[r] | C1[r];
+		if (cm) {
+			const int L = 31 - __clz(cm);
+			const int j = (C1[r] >> L) & 1u;
+			const int ppos = 2 * L + j;
+			const bool abp = ((j ? A1[r] : A0[r]) >> L) & 1u; // CONST and above => marker before
+			ra.isconst = true;
+			ra.code = abp ? (rbase + ppos + 2) : CODE_ZERO;
+			if (ra.code == CODE_ZERO && ppos + 1 < nv[r])
+				ra.code = rbase + ppos + 1 + 2; // the next claim is a PASS (above) claim
 		} else {
-			ex.isconst = false;
-			ex.v = (lane > 0) ? vnx : 0.0;
+			ra.isconst = false;
+			ra.code = nv[r] > 0 ? (rbase + 2) : CODE_ZERO;
 		}
+		wagg = icompose(wagg, ra);
 	}
-	{
-		Agg winc = compose(ex, ta); // inclusive at this lane; lane 31 holds the warp's
-		double wv = __shfl_sync(0xffffffffu, winc.v, 31);
-		int wc = __shfl_sync(0xffffffffu, (int)winc.isconst, 31);
-		double prevnow = __shfl_up_sync(0xffffffffu, nw[IPT - 1], 1);
-		if (lane > 0 && nvalid > 0 && nw[0] < prevnow)
-			nonmono = true;
-		if (lane == 31) {
-			s_wv[warp] = wv;
-			s_wconst[warp] = wc;
-			s_wlastnow[warp] = nw[IPT - 1];
-		}
-	}
+	if (lane == 0)
+		s_wagg[warp] = ((unsigned long long)wagg.isconst << 63) | wagg.code;
 	__syncthreads();
 
-	// ---- CTA-level: exclusive over warps, tile aggregate --------------------------------
-	Agg wex;
+	// ---- CTA composition: exclusive over warps, tile aggregate --------------------------------
+	IAgg wex, tile_agg;
 	wex.isconst = false;
-	wex.v = 0.0;
-	Agg tile_agg = wex;
+	wex.code = CODE_ZERO;
+	tile_agg = wex;
 #pragma unroll
 	for (int w = 0; w < WARPS; w++) {
-		Agg a;
-		a.isconst = s_wconst[w] != 0;
-		a.v = s_wv[w];
+		IAgg a;
+		const unsigned long long x = s_wagg[w];
+		a.isconst = (x >> 63) != 0;
+		a.code = x & DESC_CODE_MASK;
 		if (w == warp)
 			wex = tile_agg;
-		tile_agg = compose(tile_agg, a);
+		tile_agg = icompose(tile_agg, a);
 	}
-	if (lane == 0 && warp > 0 && nvalid > 0 && nw[0] < s_wlastnow[warp - 1])
-		nonmono = true;
 
-	// ---- decoupled look-back across tiles (warp 0) ---------------------------------------
-	if (warp == 0) {
-		double Fc;
+	// ---- does this warp inherit F from before the tile? ---------------------------------------
+	// F_in is used (i) by the chunk's leading PASS claims, (ii) for the class of the claim just
+	// before the chunk (an "ok" run may end exactly at the chunk boundary).
+	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
+	const bool prev_ok_possible = have_prev && (prev_bits & 1u) && !(prev_bits & 2u);
+	const bool need_F = first_is_pass || prev_ok_possible;
+	unsigned long long Fc_code = CODE_ZERO; // F after the previous tile's last claim (index-coded)
+	const unsigned long long ep = p.epoch << DESC_EPOCH_SHIFT;
+	if (warp == 0) { // warp 0 owns the tile's descriptor
 		if (t == 0) {
-			Fc = p.g->F;
+			Fc_code = (p.g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
+			if (lane == 0)
+				st_release(&p.desc[t], ep | ((unsigned long long)ST_PREFIX << DESC_STATUS_SHIFT) |
+				    (iapply(tile_agg, Fc_code) & DESC_CODE_MASK));
+		} else if (tile_agg.isconst) {
+			// the inclusive value does not depend on earlier tiles: publish it right away
+			if (lane == 0)
+				st_release(&p.desc[t], ep | ((unsigned long long)ST_PREFIX << DESC_STATUS_SHIFT) |
+				    (1ull << DESC_CONST_SHIFT) | (tile_agg.code & DESC_CODE_MASK));
+			if (need_F)
+				Fc_code = lookback(p, t, lane);
 		} else {
-			if (lane == 0) {
-				p.desc[t].vA = tile_agg.v;
-				st_release(&p.desc[t].w, (p.epoch << 3) | ((unsigned long long)tile_agg.isconst << 2) | ST_AGG);
-			}
-			long long base = (long long)t - 1;
-			double next_v0 = 0.0;
-			const double Fin = p.g->F;
-			while (true) {
-				long long k = base - lane;
-				double val = 0.0;
-				bool term = false;
-				if (k >= 0) {
-					unsigned long long w;
-					do {
-						w = ld_acquire(&p.desc[k].w);
-					} while ((w >> 3) != p.epoch);
-					const unsigned int st = (unsigned int)(w & 3ull);
-					const bool isc = ((w >> 2) & 1ull) != 0;
-					val = (st == ST_PREFIX) ? ld_relaxed_f64(&p.desc[k].vP) : ld_relaxed_f64(&p.desc[k].vA);
-					term = (st == ST_PREFIX) || isc;
-				} else if (k == -1) {
-					val = Fin;
-					term = true;
-				}
-				const unsigned int tm = __ballot_sync(0xffffffffu, term);
-				if (tm) {
-					const int f = __ffs(tm) - 1;
-					const double vT = __shfl_sync(0xffffffffu, val, f);
-					double vn = __shfl_sync(0xffffffffu, val, f > 0 ? f - 1 : 0);
-					if (f == 0)
-						vn = next_v0;
-					Fc = (vT != 0.0) ? vT : vn;
-					break;
-				}
-				next_v0 = __shfl_sync(0xffffffffu, val, 31);
-				base -= 32;
-			}
+			if (lane == 0)
+				st_release(&p.desc[t], ep | ((unsigned long long)ST_AGG << DESC_STATUS_SHIFT) |
+				    (tile_agg.code & DESC_CODE_MASK));
+			Fc_code = lookback(p, t, lane);
+			if (lane == 0)
+				st_release(&p.desc[t], ep | ((unsigned long long)ST_PREFIX << DESC_STATUS_SHIFT) |
+				    (iapply(tile_agg, Fc_code) & DESC_CODE_MASK));
 		}
-		if (lane == 0) {
-			p.desc[t].vA = tile_agg.v;
-			p.desc[t].vP = apply_agg(tile_agg, Fc);
-			st_release(&p.desc[t].w, (p.epoch << 3) | ((unsigned long long)tile_agg.isconst << 2) | ST_PREFIX);
-			// class of the claim just before the tile, from F after it (= Fc) -- see DESIGN.md
-			int cprev = 0;
-			if (t > 0) {
-				double pn = TimeIn<NS>::to_ms(pnow), ps = TimeIn<NS>::to_ms(pstart);
-				bool pab = !(__dsub_rn(pn, ps) < target);
-				bool pm = FLAGS && (ppfl & F_EMPTY_AFTER);
-				cprev = (pab && !pm) ? claim_class(true, pn, Fc) : 0;
-				if (nvalid > 0 && nw[0] < pn)
-					nonmono = true;
-			}
-			s_Fc = Fc;
-			s_cprev = cprev;
-		}
+	} else if (need_F && !wex.isconst) {
+		Fc_code = (t == 0) ? ((p.g->F != 0.0) ? CODE_CARRY : CODE_ZERO) : lookback(p, t, lane);
 	}
-	__syncthreads();
 
-	// ---- classify: F before each claim is now known -----------------------------------
-	double F = apply_agg(ex, apply_agg(wex, s_Fc));
-	unsigned int cls = 0; // 2 bits per claim
-	int clast = 0;
+	// ---- phase 2: classes and events, FP64 only in rows with above-target claims ---------------
+	double F = 0.0; // F in force before the chunk's first claim (before its marker-before reset)
+	if (need_F)
+		F = materialise<NS>(iapply(wex, Fc_code), p.now, p.g);
+	int c_last = 0; // class of the claim before the current row
+	if (prev_ok_possible && F != 0.0)
+		c_last = claim_class(true, TimeIn<NS>::to_ms(prev_now), F);
 #pragma unroll
-	for (int j = 0; j < IPT; j++) {
-		if (j < nvalid) {
-			const bool ab = (above >> j) & 1u;
-			const bool mprev = FLAGS && (((j == 0 ? fprev : (unsigned int)(fl8 >> (8 * (j - 1)))) & F_EMPTY_AFTER) != 0);
-			const double Fp = mprev ? 0.0 : F;
-			const int c = claim_class(ab, nw[j], Fp);
-			cls |= (unsigned int)c << (2 * j);
-			clast = c;
-			F = ab ? ((Fp != 0.0) ? Fp : __dadd_rn(nw[j], CODEL_INTERVAL)) : 0.0;
-		}
-	}
-	// class of the claim before this thread's first claim
-	int cbefore = __shfl_up_sync(0xffffffffu, clast, 1);
-	if (lane == 31)
-		s_wlastc[warp] = clast;
-	__syncthreads();
-	if (lane == 0)
-		cbefore = (warp == 0) ? s_cprev : s_wlastc[warp - 1];
-
-	// ---- events: positions where the class changes (rare) -------------------------------
-	if (nvalid > 0) {
-		int cp = cbefore;
-#pragma unroll
-		for (int j = 0; j < IPT; j++) {
-			if (j < nvalid) {
-				const int c = (cls >> (2 * j)) & 3;
-				if (c != cp) {
-					unsigned int pos = atomicAdd(&s_evn, 1u);
-					if (pos < EVK)
-						s_ev[pos] = ((i0 + j) << 2) | (unsigned long long)c;
-				}
-				cp = c;
+	for (int r = 0; r < ROWS; r++) {
+		if (nv[r] == 0)
+			break;
+		const unsigned long long rbase = cs + r * 64;
+		if ((A0[r] | A1[r]) == 0u) { // nobody above target: every class is 0, F ends at 0
+			if (c_last != 0 && lane == 0) {
+				unsigned int pos = atomicAdd(&s_evn, 1u);
+				if (pos < EVK)
+					s_ev[pos] = (rbase << 2);
 			}
+			c_last = 0;
+			F = 0.0;
+			continue;
 		}
-		if (FLAGS && mk) {
-			int jm = 31 - __clz(mk);
-			if (jm < nvalid)
-				atomicMax(&p.g->last_marker_p1, i0 + jm + 1);
+		const bool v0 = 2 * lane < nv[r], v1 = 2 * lane + 1 < nv[r];
+		const bool ab0 = (A0[r] >> lane) & 1u, ab1 = (A1[r] >> lane) & 1u;
+		const bool k0 = (C0[r] >> lane) & 1u, k1 = (C1[r] >> lane) & 1u; // CONST-type
+		const double n0 = TimeIn<NS>::to_ms(rn[r][0]), n1 = TimeIn<NS>::to_ms(rn[r][1]);
+		// lane summary: F after my two claims if F were 0 before them
+		double lv;
+		if (k1) {
+			lv = ab1 ? __dadd_rn(n1, CODEL_INTERVAL) : 0.0;
+		} else if (k0) {
+			lv = ab0 ? __dadd_rn(n0, CODEL_INTERVAL) : 0.0;
+			if (lv == 0.0 && v1)
+				lv = __dadd_rn(n1, CODEL_INTERVAL);
+		} else {
+			lv = v0 ? __dadd_rn(n0, CODEL_INTERVAL) : 0.0;
 		}
+		// F before my claim 0: last CONST lane before me, then the PASS lane after it
+		const unsigned int cm = C0[r] | C1[r];
+		const unsigned int prior = cm & lt_mask;
+		const int Lq = prior ? (31 - __clz(prior)) : 0;
+		const double vq = __shfl_sync(0xffffffffu, lv, Lq);
+		const int nx = prior ? (Lq + 1) : 0;
+		const double vnx = __shfl_sync(0xffffffffu, lv, nx & 31);
+		double Fp;
+		if (prior)
+			Fp = (vq != 0.0) ? vq : ((nx < lane) ? vnx : 0.0);
+		else
+			Fp = (F != 0.0) ? F : ((lane > 0) ? vnx : 0.0);
+		// my two claims in order
+		int c0 = 0, c1 = 0;
+		{
+			const double Fuse = (k0 && ab0) ? 0.0 : Fp; // CONST and above = a marker resets F first
+			c0 = v0 ? claim_class(ab0, n0, Fuse) : 0;
+			Fp = v0 ? (ab0 ? ((Fuse != 0.0) ? Fuse : __dadd_rn(n0, CODEL_INTERVAL)) : 0.0) : Fp;
+		}
+		{
+			const double Fuse = (k1 && ab1) ? 0.0 : Fp;
+			c1 = v1 ? claim_class(ab1, n1, Fuse) : c0;
+			Fp = v1 ? (ab1 ? ((Fuse != 0.0) ? Fuse : __dadd_rn(n1, CODEL_INTERVAL)) : 0.0) : Fp;
+		}
+		if (!v0)
+			c0 = 0;
+		// events
+		int cprev = __shfl_up_sync(0xffffffffu, v1 ? c1 : c0, 1);
+		if (lane == 0)
+			cprev = c_last;
+		if (v0 && c0 != cprev) {
+			unsigned int pos = atomicAdd(&s_evn, 1u);
+			if (pos < EVK)
+				s_ev[pos] = ((rbase + 2 * lane) << 2) | (unsigned long long)c0;
+		}
+		if (v1 && c1 != c0) {
+			unsigned int pos = atomicAdd(&s_evn, 1u);
+			if (pos < EVK)
+				s_ev[pos] = ((rbase + 2 * lane + 1) << 2) | (unsigned long long)c1;
+		}
+		// carry to the next row: state after the row's last valid claim
+		const int Lend = (nv[r] - 1) >> 1;
+		F = __shfl_sync(0xffffffffu, Fp, Lend);
+		c_last = __shfl_sync(0xffffffffu, (nv[r] & 1) ? c0 : c1, Lend);
+	}
+
+	if (FLAGS) {
+		unsigned long long m = last_marker;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const unsigned long long y = __shfl_xor_sync(0xffffffffu, m, o);
+			m = y > m ? y : m;
+		}
+		if (lane == 0 && m)
+			atomicMax(&p.g->last_marker_p1, m);
 	}
 	if (nonmono)
 		p.g->nonmono = 1u;

@@ -79,7 +79,9 @@ struct cb_ctx {
 	uint64_t launches = 0;
 	// scratch sized by tile count
 	size_t cap_tiles = 0;
-	TileDesc *desc = nullptr;
+	unsigned long long *desc = nullptr; // scan look-back: one index-coded word per tile
+	double target_ms = 0;
+	unsigned long long scan_epoch = 0;  // 21-bit tag inside the scan descriptors
 	SumDesc *sdesc = nullptr;
 	unsigned int *ev_count = nullptr;
 	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
@@ -148,7 +150,8 @@ int ensure_scratch(cb_ctx *c, size_t tiles) {
 	    (rc = dev_alloc(c, &c->iv_cum, cap * EVK + 8)))
 		return rc;
 	// descriptors carry an epoch tag, so they only need zeroing once
-	CU(c, cudaMemsetAsync(c->desc, 0, cap * sizeof(TileDesc), c->stream));
+	CU(c, cudaMemsetAsync(c->desc, 0, cap * sizeof(unsigned long long), c->stream));
+	c->scan_epoch = 0;
 	CU(c, cudaMemsetAsync(c->sdesc, 0, cap * sizeof(SumDesc), c->stream));
 	c->cap_tiles = cap;
 	return CB_OK;
@@ -169,6 +172,10 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	if (rc)
 		return rc;
 	c->epoch++;
+	if (++c->scan_epoch > DESC_EPOCH_MASK) { // the 21-bit tag wrapped: invalidate stale descriptors
+		CU(c, cudaMemsetAsync(c->desc, 0, c->cap_tiles * sizeof(unsigned long long), c->stream));
+		c->scan_epoch = 1;
+	}
 	const bool flags = d_flags != nullptr;
 
 	ScanParams sp;
@@ -178,7 +185,8 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	sp.n = n;
 	sp.g = c->g;
 	sp.desc = c->desc;
-	sp.epoch = c->epoch;
+	sp.epoch = c->scan_epoch;
+	sp.target_ns = (long long)(c->target_ms * 1000000.0);
 	sp.ev_count = c->ev_count;
 	sp.ev = c->ev;
 	sp.vec_ok = (((uintptr_t)d_start | (uintptr_t)d_now) & 15) == 0;
@@ -592,6 +600,7 @@ extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
 	DevState h;
 	memset(&h, 0, sizeof(h));
 	h.target = target_ms;
+	c->target_ms = target_ms;
 	CU(c, cudaMemcpyAsync(c->g, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
 	c->codel_ready = true;

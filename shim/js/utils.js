@@ -1,0 +1,23 @@
+/*
+ * shim/js/utils.js -- planRebalance with the reference's signature (lib/utils.js:239-393)
+ * computed by cb_plan_rebalance.  Not executed in this repository (no Node.js here).
+ */
+'use strict';
+const native = require('../napi/build/Release/cueball_b200.node');
+var ctx = null;
+
+function planRebalance(inSpares, dead, target, max, singleton) {
+	if (ctx === null) ctx = native.create(0);
+	var keys = Object.keys(inSpares);
+	var have = new Int32Array(keys.length), dd = new Uint8Array(keys.length);
+	keys.forEach(function (k, i) {
+		have[i] = (inSpares[k] || []).length;
+		dd[i] = dead[k] === true ? 1 : 0;
+	});
+	var r = native.planRebalance(ctx, have, dd, target, max, !!singleton);
+	var plan = { add: [], remove: [] }, i;
+	for (i = 0; i < r.add.length; i++) plan.add.push(keys[r.add[i]]);
+	for (i = 0; i < r.rmKey.length; i++) plan.remove.push(inSpares[keys[r.rmKey[i]]][r.rmOrd[i]]);
+	return (plan);
+}
+module.exports = { planRebalance: planRebalance };

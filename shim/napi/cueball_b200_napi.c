@@ -1,0 +1,249 @@
+/*
+ * shim/napi/cueball_b200_napi.c -- N-API addon over the C ABI of include/cueball_b200.h.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S ENVIRONMENT: there is no Node.js toolchain
+ * (no `node`, no node_api.h).  It is the binding a maintainer would add
+ * (see INTEGRATION.md); build with node-gyp against libcueball_b200.so:
+ *
+ *   { "targets": [{ "target_name": "cueball_b200", "sources": ["cueball_b200_napi.c"],
+ *       "include_dirs": ["../../include"], "libraries": ["-lcueball_b200"] }] }
+ *
+ * JS surface (consumed by shim/js/*.js):
+ *   create(device) -> ctx (external)                      destroy(ctx)
+ *   codelInit(ctx, targetMs)                              new ControlledDelay(), lib/codel.js:24
+ *   overloaded(ctx, startNs: BigInt, nowNs: BigInt) -> bool   lib/codel.js:56
+ *   empty(ctx, nowNs)                                     lib/codel.js:91
+ *   getMaxIdle(ctx, nowNs) -> ms                          lib/codel.js:109
+ *   admitBatch(ctx, start: BigInt64Array, now: BigInt64Array, flags: Uint8Array|null,
+ *              decision: Uint8Array, slot: Int32Array|null) -> {drops, admits, skipped}
+ *                                                          the drain loop lib/pool.js:733-753
+ *   backendAdded(ctx, key, u) / backendRemoved(ctx, key) / reshuffle(ctx, u)
+ *                                                          lib/pool.js:285-313, 501-519
+ *   planRebalance(ctx, have: Int32Array, dead: Uint8Array, target, max, singleton)
+ *              -> {want: Int32Array, add: Int32Array, rmKey: Int32Array, rmOrd: Int32Array}
+ *                                                          lib/utils.js:239-393
+ * Errors: CB_EINVAL -> throws (the reference throws AssertionError for programmer errors);
+ * everything else -> throws Error(cb_last_error()).
+ */
+#include <node_api.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "cueball_b200.h"
+
+#define NAPI_CALL(env, call)                                          \
+	do {                                                              \
+		if ((call) != napi_ok) {                                      \
+			napi_throw_error((env), NULL, "N-API call failed: " #call); \
+			return NULL;                                              \
+		}                                                             \
+	} while (0)
+
+static cb_ctx *
+get_ctx(napi_env env, napi_value v)
+{
+	void *p = NULL;
+	if (napi_get_value_external(env, v, &p) != napi_ok || p == NULL)
+		napi_throw_type_error(env, NULL, "ctx expected");
+	return (cb_ctx *)p;
+}
+
+static napi_value
+throw_cb(napi_env env, cb_ctx *ctx, int rc)
+{
+	if (rc == CB_EINVAL)
+		napi_throw_type_error(env, "AssertionError", cb_last_error(ctx));
+	else
+		napi_throw_error(env, NULL, cb_last_error(ctx));
+	return NULL;
+}
+
+static void
+ctx_finalize(napi_env env, void *data, void *hint)
+{
+	(void)env; (void)hint;
+	cb_destroy((cb_ctx *)data);
+}
+
+static napi_value
+Create(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1], out; int32_t dev = 0; cb_ctx *ctx = NULL;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc > 0) napi_get_value_int32(env, argv[0], &dev);
+	int rc = cb_create(&ctx, dev);
+	if (rc != CB_OK) return throw_cb(env, NULL, rc);
+	NAPI_CALL(env, napi_create_external(env, ctx, ctx_finalize, NULL, &out));
+	return out;
+}
+
+static napi_value
+CodelInit(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2]; double target;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	NAPI_CALL(env, napi_get_value_double(env, argv[1], &target));
+	int rc = cb_codel_init(ctx, target);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static int64_t
+big(napi_env env, napi_value v)
+{
+	int64_t x = 0; bool lossless = false;
+	napi_get_value_bigint_int64(env, v, &x, &lossless);
+	return x;
+}
+
+static napi_value
+Overloaded(napi_env env, napi_callback_info info)
+{
+	size_t argc = 3; napi_value argv[3], out; int drop = 0;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	int rc = cb_codel_overloaded(ctx, big(env, argv[1]), big(env, argv[2]), &drop);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_get_boolean(env, drop != 0, &out));
+	return out;
+}
+
+static napi_value
+Empty(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2];
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	int rc = cb_codel_empty(ctx, big(env, argv[1]));
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+GetMaxIdle(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2], out; double ms = 0;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	int rc = cb_codel_max_idle(ctx, big(env, argv[1]), &ms);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_create_double(env, ms, &out));
+	return out;
+}
+
+static void *
+typed(napi_env env, napi_value v, size_t *len)
+{
+	napi_valuetype t; void *data = NULL; napi_typedarray_type tt; napi_value ab; size_t off;
+	if (napi_typeof(env, v, &t) != napi_ok || t == napi_null || t == napi_undefined) return NULL;
+	if (napi_get_typedarray_info(env, v, &tt, len, &data, &ab, &off) != napi_ok) return NULL;
+	return data;
+}
+
+static napi_value
+AdmitBatch(napi_env env, napi_callback_info info)
+{
+	size_t argc = 6, n = 0, m = 0; napi_value argv[6], out, v;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	const int64_t *start = typed(env, argv[1], &n);
+	const int64_t *now = typed(env, argv[2], &m);
+	const uint8_t *flags = typed(env, argv[3], &m);
+	uint8_t *decision = typed(env, argv[4], &m);
+	int32_t *slot = typed(env, argv[5], &m);
+	cb_batch_stats st;
+	int rc = cb_admit_batch(ctx, start, now, flags, n, decision, slot, NULL, &st);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_create_object(env, &out));
+	napi_create_double(env, (double)st.drops, &v);   napi_set_named_property(env, out, "drops", v);
+	napi_create_double(env, (double)st.admits, &v);  napi_set_named_property(env, out, "admits", v);
+	napi_create_double(env, (double)st.skipped, &v); napi_set_named_property(env, out, "skipped", v);
+	return out;
+}
+
+static napi_value
+BackendAdded(napi_env env, napi_callback_info info)
+{
+	size_t argc = 3; napi_value argv[3]; int32_t key; double u;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	napi_get_value_int32(env, argv[1], &key); napi_get_value_double(env, argv[2], &u);
+	int rc = cb_backend_added(ctx, key, NULL, u);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+BackendRemoved(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2]; int32_t key;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	napi_get_value_int32(env, argv[1], &key);
+	int rc = cb_backend_removed(ctx, key);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+Reshuffle(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2]; double u;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	napi_get_value_double(env, argv[1], &u);
+	int rc = cb_reshuffle(ctx, u);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+i32array(napi_env env, const int32_t *src, size_t n)
+{
+	napi_value ab, ta; void *data;
+	napi_create_arraybuffer(env, n * 4, &data, &ab);
+	for (size_t i = 0; i < n; i++) ((int32_t *)data)[i] = src[i];
+	napi_create_typedarray(env, napi_int32_array, n, ab, 0, &ta);
+	return ta;
+}
+
+static napi_value
+PlanRebalance(napi_env env, napi_callback_info info)
+{
+	size_t argc = 6, B = 0, m = 0; napi_value argv[6], out; int32_t target, max; bool single = false;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	cb_ctx *ctx = get_ctx(env, argv[0]);
+	const int32_t *have = typed(env, argv[1], &B);
+	const uint8_t *dead = typed(env, argv[2], &m);
+	napi_get_value_int32(env, argv[3], &target); napi_get_value_int32(env, argv[4], &max);
+	if (argc > 5) napi_get_value_bool(env, argv[5], &single);
+	size_t tot = 0; for (size_t k = 0; k < B; k++) tot += (size_t)have[k];
+	int32_t *want = calloc(B + 1, 4), *add = calloc((size_t)(max > 0 ? max : 0) + 1, 4);
+	int32_t *rk = calloc(tot + 1, 4), *ro = calloc(tot + 1, 4), na = 0, nr = 0;
+	int rc = cb_plan_rebalance(ctx, have, dead, (int32_t)B, target, max, single, want, add, &na, rk, ro, &nr);
+	if (rc == CB_OK) {
+		napi_create_object(env, &out);
+		napi_set_named_property(env, out, "want", i32array(env, want, B));
+		napi_set_named_property(env, out, "add", i32array(env, add, (size_t)na));
+		napi_set_named_property(env, out, "rmKey", i32array(env, rk, (size_t)nr));
+		napi_set_named_property(env, out, "rmOrd", i32array(env, ro, (size_t)nr));
+	}
+	free(want); free(add); free(rk); free(ro);
+	return rc == CB_OK ? out : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+Init(napi_env env, napi_value exports)
+{
+	napi_property_descriptor d[] = {
+		{ "create", NULL, Create, NULL, NULL, NULL, napi_default, NULL },
+		{ "codelInit", NULL, CodelInit, NULL, NULL, NULL, napi_default, NULL },
+		{ "overloaded", NULL, Overloaded, NULL, NULL, NULL, napi_default, NULL },
+		{ "empty", NULL, Empty, NULL, NULL, NULL, napi_default, NULL },
+		{ "getMaxIdle", NULL, GetMaxIdle, NULL, NULL, NULL, napi_default, NULL },
+		{ "admitBatch", NULL, AdmitBatch, NULL, NULL, NULL, napi_default, NULL },
+		{ "backendAdded", NULL, BackendAdded, NULL, NULL, NULL, napi_default, NULL },
+		{ "backendRemoved", NULL, BackendRemoved, NULL, NULL, NULL, napi_default, NULL },
+		{ "reshuffle", NULL, Reshuffle, NULL, NULL, NULL, napi_default, NULL },
+		{ "planRebalance", NULL, PlanRebalance, NULL, NULL, NULL, napi_default, NULL },
+	};
+	napi_define_properties(env, exports, sizeof (d) / sizeof (d[0]), d);
+	return exports;
+}
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)
