@@ -44,9 +44,11 @@ from oracle import tracegen  # noqa: E402  (input generator only; not on the tim
 
 WORKLOADS = {
     #        claims/step/GPU  backends  slots   generator extras
-    "c2": dict(n=1 << 20, B=64, S=256, gen={}),
-    "c3": dict(n=1 << 24, B=1024, S=4096, gen={}),
-    "c4": dict(n=1 << 23, B=4096, S=16384, gen={}),
+    # healthy/overloaded phases of (1..4)x / (2..9)x 0.52 s at 1 us arrivals: several dropping
+    # episodes per run, healthy stretches longer than the 300 ms the backlog needs to drain
+    "c2": dict(n=1 << 20, B=64, S=256, gen={"unit": 1 << 19}),
+    "c3": dict(n=1 << 24, B=1024, S=4096, gen={"unit": 1 << 19}),
+    "c4": dict(n=1 << 23, B=4096, S=16384, gen={"unit": 1 << 19}),
     "c5": dict(n=1 << 24, B=4096, S=16384, gen={"all_overloaded_from": 1 << 20}),
 }
 TARGET_MS = 5
@@ -130,8 +132,8 @@ def run_reference(args, wl):
     from oracle import ref
     w = WORKLOADS[wl]
     n = min(REF_SAMPLE, w["n"])
-    params = dict(t0=10**9, de=1000, target_ns=TARGET_MS * 1_000_000, unit=1 << 16, start_overloaded=False,
-                  all_overloaded_from=w["gen"].get("all_overloaded_from", -1))
+    params = dict(t0=10**9, de=1000, target_ns=TARGET_MS * 1_000_000, unit=w["gen"].get("unit", 1 << 16),
+                  start_overloaded=False, all_overloaded_from=w["gen"].get("all_overloaded_from", -1))
     times, decided = [], 0
     kind = "reference" if ref.available() else "port"
     for step in range(args.warmup + args.steps):

@@ -8,6 +8,12 @@
 // With a flags array (cancelled handles, lib/pool.js:738-740) the admit rank is a prefix sum
 // of (waiting && !drop): block scan + decoupled look-back over per-tile admit counts.
 //
+// A tile (2048 claims) is classified once against the interval list: no drop inside (the
+// common case), entirely dropped (inside one episode), or mixed (an episode boundary crosses
+// it; only these tiles walk the list per claim).  Each thread writes two groups of 4
+// consecutive claims, so every store instruction of a warp covers one contiguous 128 B
+// (decisions) or 512 B (slots / backends) span.
+//
 // The slot -> backend table (built from the preference list and planRebalance) is staged in
 // shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA when `backend` is
 // requested; it is at most nslots*4 bytes.
@@ -15,6 +21,11 @@
 #include "cb_device.cuh"
 
 namespace cb {
+
+constexpr int EG = 2;              // groups per thread
+constexpr int EGW = 4;             // consecutive claims per group
+constexpr int EHALF = TPB * EGW;   // 1024: group g of thread t starts at ts + g*EHALF + t*EGW
+static_assert(EG * EHALF == TILE, "emit geometry");
 
 struct EmitParams {
 	const uint8_t *flags;
@@ -38,25 +49,59 @@ __device__ __forceinline__ unsigned int smem_u32(const void *p) {
 	return (unsigned int)__cvta_generic_to_shared(p);
 }
 
+// drop bits of the 4 claims [i0, i0+4) and the number of (CoDel-level) drops before i0
+__device__ __forceinline__ unsigned int drops_general(const EmitParams &p, unsigned int m, unsigned int jstart,
+    unsigned long long i0, int nvalid, unsigned long long total_drops, unsigned long long &drops_before) {
+	unsigned int j = jstart;
+	while (j < m && p.iv_hi[j] < i0) // first interval with hi >= i0 (few steps from the tile's first)
+		j++;
+	if (j >= m) {
+		drops_before = total_drops;
+		return 0u;
+	}
+	unsigned long long ilo = p.iv_lo[j], ihi = p.iv_hi[j];
+	drops_before = p.iv_cum[j] + (i0 > ilo ? i0 - ilo : 0ull);
+	unsigned int bits = 0;
+#pragma unroll
+	for (int k = 0; k < EGW; k++) {
+		const unsigned long long i = i0 + k;
+		while (j < m && i > ihi) {
+			j++;
+			if (j < m) {
+				ilo = p.iv_lo[j];
+				ihi = p.iv_hi[j];
+			}
+		}
+		if (k < nvalid && j < m && i >= ilo)
+			bits |= 1u << k;
+	}
+	return bits;
+}
+
 template <bool FLAGS>
-__global__ void __launch_bounds__(TPB, 4) emit_kernel(const EmitParams p) {
+__global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 	extern __shared__ __align__(16) unsigned char s_dyn[]; // backend table stage
 	__shared__ __align__(8) unsigned long long s_mbar;
-	__shared__ unsigned int s_wsum[WARPS];
+	__shared__ unsigned int s_wsum[2][WARPS];
 	__shared__ unsigned long long s_tile_excl;
+	__shared__ unsigned int s_case, s_j, s_basemod;
+	__shared__ unsigned long long s_dtile;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
 	if (g->path == 1) // the sequential path already wrote every output
 		return;
 	const unsigned long long t = blockIdx.x;
-	const unsigned long long i0 = t * (unsigned long long)TILE + (unsigned long long)tid * IPT;
+	const unsigned long long ts = t * (unsigned long long)TILE;
 	const bool want_backend = (p.backend != nullptr) && (p.nslots > 0);
 	const bool stage_table = want_backend && (p.table_smem_bytes > 0);
+	const unsigned int m = g->n_intervals;
+	const unsigned long long total_drops = g->gcounts[3];
+	const unsigned int S = (unsigned int)p.nslots;
 
-	// ---- kick off the TMA bulk copy of the slot->backend table ------------------------
-	if (stage_table) {
-		if (tid == 0) {
+	if (tid == 0) {
+		// ---- kick off the TMA bulk copy of the slot->backend table -------------------------
+		if (stage_table) {
 			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar)));
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_mbar)),
@@ -68,89 +113,109 @@ __global__ void __launch_bounds__(TPB, 4) emit_kernel(const EmitParams p) {
 			    "l"(p.slot_backend), "r"((unsigned int)p.table_smem_bytes), "r"(smem_u32(&s_mbar))
 			    : "memory");
 		}
-		__syncthreads(); // the barrier must be initialised before anyone polls it
-	}
-
-	long long rem = (long long)p.n - (long long)i0;
-	const int nvalid = rem >= IPT ? IPT : (rem > 0 ? (int)rem : 0);
-
-	// ---- drop flags from the interval list ----------------------------------------------
-	const unsigned int m = g->n_intervals;
-	unsigned int dropbits = 0;
-	unsigned long long drops_before = 0; // drops (CoDel level) among claims < i0
-	if (m > 0 && nvalid > 0) {
-		// first interval with hi >= i0
+		// ---- classify the tile against the interval list -------------------------------------
+		unsigned long long te = ts + TILE;
+		if (te > p.n)
+			te = p.n;
 		unsigned int lo = 0, hi = m;
-		while (lo < hi) {
+		while (lo < hi) { // first interval with hi >= ts
 			unsigned int mid = (lo + hi) >> 1;
-			if (p.iv_hi[mid] >= i0)
+			if (p.iv_hi[mid] >= ts)
 				hi = mid;
 			else
 				lo = mid + 1;
 		}
-		unsigned int j = lo;
-		if (j < m) {
-			unsigned long long ilo = p.iv_lo[j], ihi = p.iv_hi[j];
-			drops_before = p.iv_cum[j] + (i0 > ilo ? i0 - ilo : 0ull);
-#pragma unroll
-			for (int k = 0; k < IPT; k++) {
-				const unsigned long long i = i0 + k;
-				while (j < m && i > ihi) {
-					j++;
-					if (j < m) {
-						ilo = p.iv_lo[j];
-						ihi = p.iv_hi[j];
-					}
-				}
-				if (j < m && i >= ilo)
-					dropbits |= 1u << k;
+		unsigned int kase = 0;
+		unsigned long long D = total_drops;
+		if (lo < m) {
+			const unsigned long long ilo = p.iv_lo[lo], ihi = p.iv_hi[lo], cum = p.iv_cum[lo];
+			if (ilo >= te) {
+				kase = 0;
+				D = cum;
+			} else if (ilo <= ts && ihi >= te - 1) {
+				kase = 1;
+				D = cum + (ts - ilo);
+			} else {
+				kase = 2;
+				D = 0;
 			}
-		} else {
-			drops_before = g->gcounts[3];
 		}
+		s_case = kase;
+		s_j = lo;
+		s_dtile = D;
+		s_basemod = (S > 0 && kase == 0) ? (unsigned int)((g->cursor0 + (ts - D)) % (unsigned long long)S) : 0u;
+	}
+	__syncthreads(); // also: the barrier is initialised before anyone polls it
+	const unsigned int kase = s_case;
+
+	unsigned int dropbits[EG], waitbits[EG], admitbits[EG], validbits[EG];
+	unsigned long long rank0[EG]; // admits before the group's first claim (whole batch)
+	unsigned long long gi0[EG];
+	int nval[EG];
+#pragma unroll
+	for (int gI = 0; gI < EG; gI++) {
+		gi0[gI] = ts + (unsigned long long)gI * EHALF + (unsigned long long)tid * EGW;
+		long long rem = (long long)p.n - (long long)gi0[gI];
+		nval[gI] = rem >= EGW ? EGW : (rem > 0 ? (int)rem : 0);
+		validbits[gI] = (1u << nval[gI]) - 1u;
+		unsigned long long db = 0;
+		if (kase == 0) {
+			dropbits[gI] = 0;
+			db = s_dtile;
+		} else if (kase == 1) {
+			dropbits[gI] = validbits[gI];
+			db = s_dtile + (gi0[gI] - ts);
+		} else {
+			dropbits[gI] = drops_general(p, m, s_j, gi0[gI], nval[gI], total_drops, db);
+		}
+		waitbits[gI] = 0xfu;
+		if (FLAGS) {
+			waitbits[gI] = 0;
+			if (nval[gI] == EGW && ((reinterpret_cast<uintptr_t>(p.flags) & 3) == 0)) {
+				const unsigned int f4 = *reinterpret_cast<const unsigned int *>(p.flags + gi0[gI]);
+#pragma unroll
+				for (int k = 0; k < EGW; k++)
+					waitbits[gI] |= ((f4 >> (8 * k)) & 1u) << k;
+			} else {
+				for (int k = 0; k < nval[gI]; k++)
+					waitbits[gI] |= (unsigned int)(p.flags[gi0[gI] + k] & 1u) << k;
+			}
+		}
+		admitbits[gI] = waitbits[gI] & ~dropbits[gI] & validbits[gI];
+		rank0[gI] = gi0[gI] - db; // closed form (no flags)
 	}
 
-	// ---- waiting flags, admit rank ----------------------------------------------------------
-	unsigned int waitbits = 0xffu;
 	if (FLAGS) {
-		waitbits = 0;
-		if (nvalid == IPT && ((reinterpret_cast<uintptr_t>(p.flags) & 7) == 0)) {
-			unsigned long long f8 = *reinterpret_cast<const unsigned long long *>(p.flags + i0);
+		// admit rank = prefix sum of (waiting && !drop): group 0 of every thread, then group 1
+		unsigned int a[EG], x[EG];
 #pragma unroll
-			for (int k = 0; k < IPT; k++)
-				waitbits |= (unsigned int)((f8 >> (8 * k)) & 1ull) << k;
-		} else {
-			for (int k = 0; k < nvalid; k++)
-				waitbits |= (unsigned int)(p.flags[i0 + k] & 1u) << k;
-		}
-	}
-	const unsigned int validbits = (nvalid == IPT) ? 0xffu : ((1u << nvalid) - 1u);
-	const unsigned int admitbits = waitbits & ~dropbits & validbits;
-	unsigned long long rank0; // admits before claim i0 (whole batch)
-	if (!FLAGS) {
-		rank0 = i0 - drops_before;
-	} else {
-		// block exclusive scan of per-thread admit counts
-		unsigned int a = __popc(admitbits), x = a;
+		for (int gI = 0; gI < EG; gI++) {
+			a[gI] = __popc(admitbits[gI]);
+			x[gI] = a[gI];
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
-			if (lane >= o)
-				x += y;
+			for (int o = 1; o < 32; o <<= 1) {
+				unsigned int y = __shfl_up_sync(0xffffffffu, x[gI], o);
+				if (lane >= o)
+					x[gI] += y;
+			}
+			if (lane == 31)
+				s_wsum[gI][warp] = x[gI];
 		}
-		if (lane == 31)
-			s_wsum[warp] = x;
 		__syncthreads();
-		unsigned int wex = 0, total = 0;
+		unsigned int wex[EG] = {0, 0}, tot[EG] = {0, 0};
 #pragma unroll
-		for (int w = 0; w < WARPS; w++) {
-			if (w == warp)
-				wex = total;
-			total += s_wsum[w];
+		for (int gI = 0; gI < EG; gI++) {
+#pragma unroll
+			for (int w = 0; w < WARPS; w++) {
+				if (w == warp)
+					wex[gI] = tot[gI];
+				tot[gI] += s_wsum[gI][w];
+			}
 		}
+		const unsigned int total = tot[0] + tot[1];
 		// per-tile counters of real timeouts / skipped handles
-		unsigned int dwait = __popc(waitbits & dropbits & validbits);
-		unsigned int skip = __popc(~waitbits & validbits);
+		unsigned int dwait = __popc(waitbits[0] & dropbits[0] & validbits[0]) + __popc(waitbits[1] & dropbits[1] & validbits[1]);
+		unsigned int skip = __popc(~waitbits[0] & validbits[0]) + __popc(~waitbits[1] & validbits[1]);
 		dwait = __reduce_add_sync(0xffffffffu, dwait);
 		skip = __reduce_add_sync(0xffffffffu, skip);
 		if (lane == 0) {
@@ -183,20 +248,17 @@ __global__ void __launch_bounds__(TPB, 4) emit_kernel(const EmitParams p) {
 						term = true;
 					}
 					const unsigned int tm = __ballot_sync(0xffffffffu, term);
+					unsigned long long v = val;
 					if (tm) {
 						const int f = __ffs(tm) - 1; // nearest terminator; sum lanes 0..f
-						unsigned long long v = (lane <= f) ? val : 0ull;
-#pragma unroll
-						for (int o = 16; o > 0; o >>= 1)
-							v += __shfl_xor_sync(0xffffffffu, v, o);
-						excl += v;
-						break;
+						v = (lane <= f) ? val : 0ull;
 					}
-					unsigned long long v = val;
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1)
 						v += __shfl_xor_sync(0xffffffffu, v, o);
 					excl += v;
+					if (tm)
+						break;
 					base -= 32;
 				}
 			}
@@ -208,76 +270,86 @@ __global__ void __launch_bounds__(TPB, 4) emit_kernel(const EmitParams p) {
 			}
 		}
 		__syncthreads();
-		rank0 = s_tile_excl + wex + (x - a);
+		rank0[0] = s_tile_excl + wex[0] + (x[0] - a[0]);
+		rank0[1] = s_tile_excl + tot[0] + wex[1] + (x[1] - a[1]);
 	}
 
-	// ---- slots / backends -----------------------------------------------------------------
-	int32_t sl[IPT];
-	uint8_t dec[IPT];
-	unsigned int scur = 0;
-	if (p.nslots > 0)
-		scur = (unsigned int)((g->cursor0 + rank0) % (unsigned long long)p.nslots);
+	// ---- slots / backends, vector stores ------------------------------------------------------
+	const int32_t *tb = reinterpret_cast<const int32_t *>(s_dyn);
+	bool table_ready = false;
 #pragma unroll
-	for (int k = 0; k < IPT; k++) {
-		const bool adm = (admitbits >> k) & 1u;
-		dec[k] = ((waitbits >> k) & 1u) ? (uint8_t)((dropbits >> k) & 1u) : (uint8_t)2;
-		sl[k] = (adm && p.nslots > 0) ? (int32_t)scur : -1;
-		if (adm) {
-			scur++;
-			if (scur == (unsigned int)p.nslots)
-				scur = 0;
+	for (int gI = 0; gI < EG; gI++) {
+		if (nval[gI] == 0)
+			continue;
+		unsigned int scur = 0;
+		if (S > 0) {
+			if (!FLAGS && kase == 0) {
+				// tile-uniform base + a small offset: no 64-bit division per thread
+				unsigned int off = (unsigned int)(gi0[gI] - ts);
+				scur = (S >= (unsigned int)TILE) ? s_basemod + off : (s_basemod + off) % S;
+				if (scur >= S)
+					scur -= S;
+			} else {
+				scur = (unsigned int)((g->cursor0 + rank0[gI]) % (unsigned long long)S);
+			}
 		}
-	}
-	if (nvalid == IPT && p.vec_ok) {
-		if (p.decision) {
-			unsigned long long d8 = 0;
+		int32_t sl[EGW];
+		unsigned int d4 = 0;
 #pragma unroll
-			for (int k = 0; k < IPT; k++)
-				d8 |= (unsigned long long)dec[k] << (8 * k);
-			*reinterpret_cast<unsigned long long *>(p.decision + i0) = d8;
+		for (int k = 0; k < EGW; k++) {
+			const bool adm = (admitbits[gI] >> k) & 1u;
+			const unsigned int dk = ((waitbits[gI] >> k) & 1u) ? ((dropbits[gI] >> k) & 1u) : 2u;
+			d4 |= dk << (8 * k);
+			sl[k] = (adm && S > 0) ? (int32_t)scur : -1;
+			if (adm) {
+				scur++;
+				if (scur == S)
+					scur = 0;
+			}
+		}
+		const bool vec = (nval[gI] == EGW) && p.vec_ok;
+		if (p.decision) {
+			if (vec)
+				*reinterpret_cast<unsigned int *>(p.decision + gi0[gI]) = d4;
+			else
+				for (int k = 0; k < nval[gI]; k++)
+					p.decision[gi0[gI] + k] = (uint8_t)(d4 >> (8 * k));
 		}
 		if (p.slot) {
-			int4 *o = reinterpret_cast<int4 *>(p.slot + i0);
-			o[0] = make_int4(sl[0], sl[1], sl[2], sl[3]);
-			o[1] = make_int4(sl[4], sl[5], sl[6], sl[7]);
+			if (vec)
+				*reinterpret_cast<int4 *>(p.slot + gi0[gI]) = make_int4(sl[0], sl[1], sl[2], sl[3]);
+			else
+				for (int k = 0; k < nval[gI]; k++)
+					p.slot[gi0[gI] + k] = sl[k];
 		}
-	} else {
-		for (int k = 0; k < nvalid; k++) {
-			if (p.decision)
-				p.decision[i0 + k] = dec[k];
-			if (p.slot)
-				p.slot[i0 + k] = sl[k];
-		}
-	}
-	if (p.backend) {
-		int32_t be[IPT];
-		if (stage_table) {
-			// wait for the bulk copy (phase 0)
-			unsigned int done = 0;
-			while (!done) {
-				asm volatile("{\n\t.reg .pred q;\n\t"
-				             "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
-				             "selp.u32 %0, 1, 0, q;\n\t}"
-				             : "=r"(done)
-				             : "r"(smem_u32(&s_mbar))
-				             : "memory");
+		if (p.backend) {
+			int32_t be[EGW];
+			if (stage_table) {
+				if (!table_ready) { // wait for the bulk copy (phase 0)
+					unsigned int done = 0;
+					while (!done) {
+						asm volatile("{\n\t.reg .pred q;\n\t"
+						             "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
+						             "selp.u32 %0, 1, 0, q;\n\t}"
+						             : "=r"(done)
+						             : "r"(smem_u32(&s_mbar))
+						             : "memory");
+					}
+					table_ready = true;
+				}
+#pragma unroll
+				for (int k = 0; k < EGW; k++)
+					be[k] = (sl[k] >= 0) ? tb[sl[k]] : -1;
+			} else {
+#pragma unroll
+				for (int k = 0; k < EGW; k++)
+					be[k] = (sl[k] >= 0) ? __ldg(p.slot_backend + sl[k]) : -1;
 			}
-			const int32_t *tb = reinterpret_cast<const int32_t *>(s_dyn);
-#pragma unroll
-			for (int k = 0; k < IPT; k++)
-				be[k] = (sl[k] >= 0) ? tb[sl[k]] : -1;
-		} else {
-#pragma unroll
-			for (int k = 0; k < IPT; k++)
-				be[k] = (sl[k] >= 0) ? __ldg(p.slot_backend + sl[k]) : -1;
-		}
-		if (nvalid == IPT && p.vec_ok) {
-			int4 *o = reinterpret_cast<int4 *>(p.backend + i0);
-			o[0] = make_int4(be[0], be[1], be[2], be[3]);
-			o[1] = make_int4(be[4], be[5], be[6], be[7]);
-		} else {
-			for (int k = 0; k < nvalid; k++)
-				p.backend[i0 + k] = be[k];
+			if (vec)
+				*reinterpret_cast<int4 *>(p.backend + gi0[gI]) = make_int4(be[0], be[1], be[2], be[3]);
+			else
+				for (int k = 0; k < nval[gI]; k++)
+					p.backend[gi0[gI] + k] = be[k];
 		}
 	}
 

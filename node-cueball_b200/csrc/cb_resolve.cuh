@@ -1,18 +1,27 @@
 // cb_resolve.cuh -- pass 2: resolve the dropping episodes (one CTA).
 //
-// Input: the class-change events of pass 1.  Between two events every claim has the same
-// canDrop class, so ControlledDelay#overloaded (lib/codel.js:56-86) acts on a whole stretch
-// in closed form:
-//   class 0 stretch : cd_dropping := false, nothing dropped
-//   class>0, dropping     : claims with now >= cd_drop_next are dropped (a suffix: the clock
-//                           is monotone) and counted                      codel.js:65-68
-//   class>0, not dropping : the state is entered at the stretch's FIRST claim iff
-//                           class==2 or now - drop_next < 100             codel.js:70-83
-// so the sequential recurrence over (drop_next, count, dropping) runs over EVENTS (a few
-// per 100 ms of stream), not over claims.  The only non-O(1) step, "first claim with
-// now >= drop_next", is a lower_bound on the monotone clock; all of them are speculated in
-// parallel (one warp per event, assuming count==1 on entry, which is what a monotone
-// clock produces except for a rounding coincidence) before the serial chain runs.
+// Input: per tile, the class-change events the scan kernel found locally, plus the tile's
+// record (where the above-target run inherited from earlier tiles closes; what F the tile
+// leaves behind; the class of its last claim).
+//
+// Step A  pairs every closing tile with the tile that opened the run (a block-wide max-scan
+//         over "last tile with a CONST claim") and evaluates the run's unclassified stretch:
+//         the class there is monotone in the clock, so its (at most two) crossings are
+//         lower_bound searches, done by one warp per long run.  This is what replaces a
+//         tile-to-tile look-back chain: a run spanning thousands of tiles costs two searches.
+// Step B  merges run events and local events into one ordered list (block scan).
+// Step C  Between two events every claim has the same canDrop class, so
+//         ControlledDelay#overloaded (lib/codel.js:56-86) acts on a whole stretch in closed form:
+//           class 0 stretch        : cd_dropping := false, nothing dropped
+//           class>0, dropping      : claims with now >= cd_drop_next are dropped (a suffix: the
+//                                    clock is monotone) and counted            codel.js:65-68
+//           class>0, not dropping  : the state is entered at the stretch's FIRST claim iff
+//                                    class==2 or now - drop_next < 100          codel.js:70-83
+//         so the sequential recurrence over (drop_next, count, dropping) runs over EVENTS (a few
+//         per 100 ms of stream), not over claims.  Its only non-O(1) step, "first claim with
+//         now >= drop_next", is a lower_bound on the monotone clock; all of them are speculated
+//         in parallel (one warp per event, assuming count==1 on entry, which is what a monotone
+//         clock produces except for a rounding coincidence) before the serial chain runs.
 //
 // If the clock went backwards inside the batch (or a tile overflowed its event slots) the
 // decomposition does not apply and warp 0 runs the exact per-claim state machine instead
@@ -32,7 +41,16 @@ struct ResolveParams {
 	unsigned long long n;
 	unsigned long long tiles;
 	DevState *g;
-	const unsigned long long *desc;
+	const unsigned int *rec_fc;         // per-tile records from the scan kernel
+	const unsigned long long *rec_code;
+	const unsigned int *rec_cend;
+	// cross-tile run events (<= 3 per closing tile; slot `tiles` = the run open at batch end)
+	unsigned long long *xev;            // [(tiles+1)*3]
+	unsigned int *xcnt;                 // [tiles+1]
+	// heavy jobs: runs whose unclassified stretch really crosses a class boundary
+	unsigned long long *hj_lo, *hj_b;   // [tiles+1]
+	double *hj_F;
+	unsigned int *hj_info;              // tile slot | cend0 << 28
 	const unsigned int *ev_count;
 	const unsigned long long *ev;
 	// compacted, ordered events + per-event speculation
@@ -84,6 +102,38 @@ __device__ unsigned long long warp_lower_bound(const void *now, unsigned long lo
 		if (f > 0)
 			lo = pprev + 1;
 		hi = pf; // answer in [lo, pf]; pf itself satisfies the predicate
+		if (lo >= hi)
+			return hi;
+	}
+}
+// first index in [lo,hi) whose canDrop class w.r.t. F is >= level, else hi (class is monotone in
+// the clock inside an above-target run)
+template <bool NS>
+__device__ unsigned long long warp_first_class(const void *now, unsigned long long lo, unsigned long long hi,
+    double F, int level, int lane) {
+	while (true) {
+		unsigned long long s = hi - lo;
+		if (s == 0)
+			return hi;
+		if (s <= 32) {
+			bool pr = (lane < s) && (claim_class(true, now_at<NS>(now, lo + lane), F) >= level);
+			unsigned int m = __ballot_sync(0xffffffffu, pr);
+			return m ? lo + (__ffs(m) - 1) : hi;
+		}
+		unsigned long long chunk = (s + 31) / 32;
+		unsigned long long pidx = lo + (unsigned long long)(lane + 1) * chunk - 1;
+		if (pidx > hi - 1)
+			pidx = hi - 1;
+		bool pr = claim_class(true, now_at<NS>(now, pidx), F) >= level;
+		unsigned int m = __ballot_sync(0xffffffffu, pr);
+		if (!m)
+			return hi;
+		int f = __ffs(m) - 1;
+		unsigned long long pf = __shfl_sync(0xffffffffu, pidx, f);
+		unsigned long long pprev = __shfl_sync(0xffffffffu, pidx, f > 0 ? f - 1 : 0);
+		if (f > 0)
+			lo = pprev + 1;
+		hi = pf;
 		if (lo >= hi)
 			return hi;
 	}
@@ -213,10 +263,124 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		return;
 	}
 
-	// ---- 1. compact the per-tile event slots into one ordered list ---------------------
-	for (unsigned long long tb = 0; tb < p.tiles; tb += RTPB) {
+	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
+	__shared__ int s_wmax[32];
+	__shared__ long long s_prevconst; // last tile with a CONST claim seen so far (-1: none yet)
+	__shared__ unsigned int s_nheavy;
+	if (tid == 0) {
+		s_prevconst = -1;
+		s_nheavy = 0;
+	}
+	__syncthreads();
+	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
+	for (unsigned long long tb = 0; tb < p.tiles + 1; tb += RTPB) {
+		const unsigned long long t = tb + tid;
+		// slot `tiles` is a virtual closing tile at index n (the run still open at batch end)
+		const bool is_tail = (t == p.tiles);
+		const unsigned int fc = (t < p.tiles) ? p.rec_fc[t] : (is_tail ? 0u : FC_NONE);
+		const bool hc = (t <= p.tiles) && fc != FC_NONE;
+		// exclusive max-scan of (hc ? t : -1) over the block
+		int v = (hc && !is_tail) ? (int)(t - tb) : -1; // block-local index
+		int x = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			int y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o)
+				x = max(x, y);
+		}
+		if (lane == 31)
+			s_wmax[warp] = x;
+		__syncthreads();
+		int wprev = -1;
+		for (int w = 0; w < warp; w++)
+			wprev = max(wprev, s_wmax[w]);
+		int ex = __shfl_up_sync(0xffffffffu, x, 1);
+		if (lane == 0)
+			ex = -1;
+		ex = max(ex, wprev);
+		const long long T0 = (ex >= 0) ? (long long)(tb + ex) : s_prevconst;
+		if (hc) {
+			const unsigned long long code0 = (T0 < 0) ? carry_code : p.rec_code[T0];
+			const unsigned int cend0 = (T0 < 0) ? 0u : p.rec_cend[T0];
+			const unsigned long long lo = (unsigned long long)(T0 + 1) * TILE;
+			const unsigned long long close_idx = is_tail ? p.n : (t * TILE + fc); // first claim after the run
+			unsigned int cnt = 0;
+			int final_c = (int)cend0;
+			if (lo < close_idx) { // unclassified stretch [lo, close_idx)
+				double F;
+				if (code0 == CODE_ZERO)
+					F = __dadd_rn(now_at<NS>(p.now, lo), CODEL_INTERVAL); // the stretch's first claim opens the run
+				else if (code0 == CODE_CARRY)
+					F = g->F;
+				else
+					F = __dadd_rn(now_at<NS>(p.now, code0 - 2), CODEL_INTERVAL);
+				const int cb = claim_class(true, now_at<NS>(p.now, close_idx - 1), F);
+				if (cb > final_c) { // the class rises inside the stretch: find where (one warp, below)
+					const unsigned int h = atomicAdd(&s_nheavy, 1u);
+					p.hj_lo[h] = lo;
+					p.hj_b[h] = close_idx - 1;
+					p.hj_F[h] = F;
+					p.hj_info[h] = (unsigned int)t | (cend0 << 28);
+					final_c = cb;
+				}
+			}
+			if (final_c >= 1 && !is_tail) // the run ends at a CONST claim (class 0)
+				p.xev[t * 3 + 2] = (close_idx << 2);
+			cnt = (final_c >= 1 && !is_tail) ? 4u : 0u; // bit 2: close event present
+			p.xcnt[t] = cnt;
+		} else if (t <= p.tiles) {
+			p.xcnt[t] = 0;
+		}
+		__syncthreads();
+		if (tid == RTPB - 1) {
+			const int blockmax = max(x, wprev);
+			if (blockmax >= 0)
+				s_prevconst = (long long)(tb + blockmax);
+		}
+		__syncthreads();
+	}
+	// long runs: class crossings by binary search, one warp per run
+	const unsigned int nheavy = s_nheavy;
+	for (unsigned int h = warp; h < nheavy; h += RTPB / 32) {
+		const unsigned long long lo = p.hj_lo[h], b = p.hj_b[h];
+		const double F = p.hj_F[h];
+		const unsigned int info = p.hj_info[h];
+		const unsigned int slot = info & 0x0fffffffu;
+		const int cend0 = (int)(info >> 28);
+		unsigned int bits = p.xcnt[slot];
+		unsigned long long e0 = ~0ull, e1 = ~0ull;
+		unsigned long long pos = lo;
+		int cur = cend0;
+		if (cur == 0) {
+			pos = warp_first_class<NS>(p.now, lo, b + 1, F, 1, lane);
+			cur = claim_class(true, now_at<NS>(p.now, pos), F); // 1 or 2
+			e0 = (pos << 2) | (unsigned long long)cur;
+		}
+		if (cur == 1) {
+			const unsigned long long p2 = warp_first_class<NS>(p.now, pos, b + 1, F, 2, lane);
+			if (p2 <= b)
+				e1 = (p2 << 2) | 2ull;
+		}
+		if (lane == 0) {
+			if (e0 != ~0ull) {
+				p.xev[slot * 3 + 0] = e0;
+				bits |= 1u;
+			}
+			if (e1 != ~0ull) {
+				p.xev[slot * 3 + 1] = e1;
+				bits |= 2u;
+			}
+			p.xcnt[slot] = bits;
+		}
+	}
+	__syncthreads();
+
+	// ---- B. merge run events and local events into one ordered list -----------------------------
+	for (unsigned long long tb = 0; tb < p.tiles + 1; tb += RTPB) {
 		unsigned long long t = tb + tid;
-		unsigned int cnt = (t < p.tiles) ? p.ev_count[t] : 0u;
+		const unsigned int xb = (t <= p.tiles) ? p.xcnt[t] : 0u;
+		const unsigned int lc = (t < p.tiles) ? p.ev_count[t] : 0u;
+		const unsigned int cnt = __popc(xb) + lc;
 		// block exclusive scan of cnt
 		unsigned int x = cnt;
 #pragma unroll
@@ -244,11 +408,20 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		__syncthreads();
 		unsigned int off = s_base + s_warp[warp] + (x - cnt);
 		if (cnt) {
+			// run events of the tile's close come first (crossing(s) <= close index <= local events)
+			if ((xb & 1u) && off < p.ev_cap)
+				p.evc[off++] = p.xev[t * 3 + 0];
+			if ((xb & 2u) && off < p.ev_cap)
+				p.evc[off++] = p.xev[t * 3 + 1];
+			if ((xb & 4u) && off < p.ev_cap)
+				p.evc[off++] = p.xev[t * 3 + 2];
+		}
+		if (lc) {
 			// a tile's events were appended unordered: sort its <= EVK entries by index
 			unsigned long long e[EVK];
 #pragma unroll
 			for (int j = 0; j < EVK; j++)
-				e[j] = (j < (int)cnt) ? p.ev[t * EVK + j] : ~0ull;
+				e[j] = (j < (int)lc) ? p.ev[t * EVK + j] : ~0ull;
 #pragma unroll
 			for (int a = 1; a < EVK; a++) {
 #pragma unroll
@@ -262,7 +435,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			}
 #pragma unroll
 			for (int j = 0; j < EVK; j++)
-				if (j < (int)cnt && off + j < p.ev_cap)
+				if (j < (int)lc && off + j < p.ev_cap)
 					p.evc[off + j] = e[j];
 		}
 		__syncthreads();
@@ -271,7 +444,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		__syncthreads();
 	}
 	const unsigned int nev = s_base;
-	if (nev > p.ev_cap) { // cannot happen with ev_cap = tiles*EVK; defensive: exact path
+	if (nev > p.ev_cap) { // cannot happen with ev_cap = (tiles+1)*(EVK+3); defensive: exact path
 		if (warp == 0)
 			sequential_path<NS>(p, lane);
 		return;
@@ -381,7 +554,21 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			k += has2 ? 2 : 1;
 		}
 		// ---- final ControlledDelay state -------------------------------------------------
-		double F = materialise<NS>(ld_relaxed_u64(&p.desc[p.tiles - 1]) & DESC_CODE_MASK, p.now, g);
+		// F after the batch's last claim: the last tile with a CONST claim fixes it, later (all
+		// PASS) tiles inherit it or, if it is 0, the first of them opens the run
+		double F;
+		{
+			const long long Tl = s_prevconst;
+			const unsigned long long code0 = (Tl < 0) ? carry_code : p.rec_code[Tl];
+			if (code0 == CODE_CARRY)
+				F = g->F;
+			else if (code0 != CODE_ZERO)
+				F = __dadd_rn(now_at<NS>(p.now, code0 - 2), CODEL_INTERVAL);
+			else if ((unsigned long long)(Tl + 1) < p.tiles)
+				F = __dadd_rn(now_at<NS>(p.now, (unsigned long long)(Tl + 1) * TILE), CODEL_INTERVAL);
+			else
+				F = 0.0;
+		}
 		if (FLAGS) {
 			const unsigned long long lm = g->last_marker_p1;
 			if (lm) {

@@ -1,4 +1,4 @@
-// cb_scan.cuh -- pass 1 of the admission path: the streaming scan kernel (v2).
+// cb_scan.cuh -- pass 1 of the admission path: the streaming scan kernel (v3).
 //
 // Reads every claim's (start, now[, flags]) exactly once from HBM (16 B/claim, 17 with
 // flags), evaluates ControlledDelay#canDrop (lib/codel.js:34-46) for ALL claims in parallel
@@ -21,8 +21,14 @@
 // exceeds the worst-case rounding of the millisecond doubles, and exactly as
 // utils.currentMillis() (lib/utils.js:198-204) otherwise -- and builds the row/warp/tile
 // compositions.  Phase 2 touches FP64 only in rows that contain above-target claims.
-// The decoupled look-back across tiles runs per warp, and only for warps whose leading claims
-// actually inherit F from an earlier tile: healthy traffic does no look-back at all.
+//
+// Tiles are INDEPENDENT: there is no look-back.  A tile classifies only the claims whose F
+// is determined inside the tile (everything from its first CONST claim on).  Its leading PASS
+// claims belong to an above-target run that was opened in an earlier tile; for those the tile
+// just records where the run closes.  The resolve kernel pairs each close with the open it
+// belongs to and finds the (at most two) class crossings of such a long run by binary search
+// on the monotone clock -- a run spanning thousands of tiles (sustained overload) costs two
+// searches instead of a serialised chain of tile-to-tile waits.
 // (A CB_F_EMPTY_AFTER marker -- codel.empty(), lib/codel.js:91-94 -- is applied as a reset in
 // front of the NEXT claim, which is equivalent and keeps the carried value meaningful.)
 #pragma once
@@ -36,10 +42,8 @@ static_assert(CHUNK * WARPS == TILE, "tile geometry");
 
 // index-coded F: 0 = F is 0, 1 = the batch's carried-in F, a+2 = now[a] + 100
 constexpr unsigned long long CODE_ZERO = 0, CODE_CARRY = 1;
-// tile descriptor word: [epoch:21 | status:2 | isconst:1 | code:40]
-constexpr int DESC_EPOCH_SHIFT = 43, DESC_STATUS_SHIFT = 41, DESC_CONST_SHIFT = 40;
 constexpr unsigned long long DESC_CODE_MASK = (1ull << 40) - 1;
-constexpr unsigned long long DESC_EPOCH_MASK = (1ull << 21) - 1;
+constexpr unsigned int FC_NONE = 0xffffffffu; // tile record: no CONST claim in the tile
 
 struct IAgg { // composed F-update in index form: F_out = isconst ? code : (F_in ? F_in : code)
 	bool isconst;
@@ -71,8 +75,10 @@ struct ScanParams {
 	const uint8_t *flags; // may be null
 	unsigned long long n;
 	DevState *g;
-	unsigned long long *desc; // one word per tile
-	unsigned long long epoch; // 1 .. 2^21-1
+	// per-tile record: first CONST position, F after the tile (index-coded), class of its last claim
+	unsigned int *rec_fc;          // [tiles] tile-local position of the first CONST claim, or FC_NONE
+	unsigned long long *rec_code;  // [tiles] valid when rec_fc != FC_NONE
+	unsigned int *rec_cend;        // [tiles] valid when rec_fc != FC_NONE
 	unsigned int *ev_count;   // [tiles]
 	unsigned long long *ev;   // [tiles][EVK]  (index << 2) | class
 	int vec_ok;               // start/now 16-byte aligned
@@ -121,44 +127,11 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 	return __dadd_rn(TimeIn<NS>::to_ms(v), CODEL_INTERVAL);
 }
 
-// Decoupled look-back: F (index-coded) after the last claim of tile t-1.
-__device__ __forceinline__ unsigned long long lookback(const ScanParams &p, unsigned long long t, int lane) {
-	long long base = (long long)t - 1;
-	while (true) {
-		const long long k = base - lane;
-		unsigned long long code = 0;
-		bool term = false;
-		if (k >= 0) {
-			unsigned long long w;
-			do {
-				w = ld_acquire(&p.desc[k]);
-			} while ((w >> DESC_EPOCH_SHIFT) != p.epoch);
-			const unsigned int st = (unsigned int)(w >> DESC_STATUS_SHIFT) & 3u;
-			const bool isc = ((w >> DESC_CONST_SHIFT) & 1ull) != 0;
-			code = w & DESC_CODE_MASK;
-			term = (st == ST_PREFIX) || isc;
-		} else if (k == -1) {
-			code = (p.g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
-			term = true;
-		}
-		const unsigned int tm = __ballot_sync(0xffffffffu, term);
-		if (tm) {
-			const int f = __ffs(tm) - 1; // nearest terminator: tile T = base - f
-			const unsigned long long cT = __shfl_sync(0xffffffffu, code, f);
-			if (cT != CODE_ZERO)
-				return cT;
-			const long long T = base - f;
-			// tiles T+1 .. t-1 are PASS tiles: the first of them fills the zero
-			return (T + 1 <= (long long)t - 1) ? ((unsigned long long)(T + 1) * TILE + 2) : CODE_ZERO;
-		}
-		base -= 32;
-	}
-}
-
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
+	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
 	__shared__ unsigned int s_evn;
 	__shared__ unsigned long long s_ev[EVK];
 
@@ -241,6 +214,7 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 	bool nonmono = false;
 	unsigned int carry_mk = (prev_bits >> 2) & 1u; // marker of the claim before the row (warp-uniform)
 	unsigned long long last_marker = 0;
+	unsigned int wfc = FC_NONE; // chunk-local position of the first CONST claim
 #pragma unroll
 	for (int r = 0; r < ROWS; r++) {
 		const unsigned long long rbase = cs + r * 64;
@@ -291,6 +265,10 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 		IAgg ra;
 		const unsigned int cm = C0[r] | C1[r];
 		if (cm) {
+			if (wfc == FC_NONE) {
+				const int Lf = __ffs(cm) - 1;
+				wfc = r * 64 + 2 * Lf + (((C0[r] >> Lf) & 1u) ? 0 : 1);
+			}
 			const int L = 31 - __clz(cm);
 			const int j = (C1[r] >> L) & 1u;
 			const int ppos = 2 * L + j;
@@ -305,8 +283,10 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 		}
 		wagg = icompose(wagg, ra);
 	}
-	if (lane == 0)
+	if (lane == 0) {
 		s_wagg[warp] = ((unsigned long long)wagg.isconst << 63) | wagg.code;
+		s_wfc[warp] = wfc;
+	}
 	__syncthreads();
 
 	// ---- CTA composition: exclusive over warps, tile aggregate --------------------------------
@@ -325,44 +305,26 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 		tile_agg = icompose(tile_agg, a);
 	}
 
-	// ---- does this warp inherit F from before the tile? ---------------------------------------
-	// F_in is used (i) by the chunk's leading PASS claims, (ii) for the class of the claim just
-	// before the chunk (an "ok" run may end exactly at the chunk boundary).
-	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
-	const bool prev_ok_possible = have_prev && (prev_bits & 1u) && !(prev_bits & 2u);
-	const bool need_F = first_is_pass || prev_ok_possible;
-	unsigned long long Fc_code = CODE_ZERO; // F after the previous tile's last claim (index-coded)
-	const unsigned long long ep = p.epoch << DESC_EPOCH_SHIFT;
-	if (warp == 0) { // warp 0 owns the tile's descriptor
-		if (t == 0) {
-			Fc_code = (p.g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
-			if (lane == 0)
-				st_release(&p.desc[t], ep | ((unsigned long long)ST_PREFIX << DESC_STATUS_SHIFT) |
-				    (iapply(tile_agg, Fc_code) & DESC_CODE_MASK));
-		} else if (tile_agg.isconst) {
-			// the inclusive value does not depend on earlier tiles: publish it right away
-			if (lane == 0)
-				st_release(&p.desc[t], ep | ((unsigned long long)ST_PREFIX << DESC_STATUS_SHIFT) |
-				    (1ull << DESC_CONST_SHIFT) | (tile_agg.code & DESC_CODE_MASK));
-			if (need_F)
-				Fc_code = lookback(p, t, lane);
-		} else {
-			if (lane == 0)
-				st_release(&p.desc[t], ep | ((unsigned long long)ST_AGG << DESC_STATUS_SHIFT) |
-				    (tile_agg.code & DESC_CODE_MASK));
-			Fc_code = lookback(p, t, lane);
-			if (lane == 0)
-				st_release(&p.desc[t], ep | ((unsigned long long)ST_PREFIX << DESC_STATUS_SHIFT) |
-				    (iapply(tile_agg, Fc_code) & DESC_CODE_MASK));
-		}
-	} else if (need_F && !wex.isconst) {
-		Fc_code = (t == 0) ? ((p.g->F != 0.0) ? CODE_CARRY : CODE_ZERO) : lookback(p, t, lane);
+	// ---- the tile's record (thread 0): where the inherited run closes, what the tile leaves open
+	if (tid == 0) {
+		unsigned int fc = FC_NONE;
+#pragma unroll
+		for (int w = WARPS - 1; w >= 0; w--)
+			if (s_wfc[w] != FC_NONE)
+				fc = w * CHUNK + s_wfc[w];
+		p.rec_fc[t] = fc;
+		p.rec_code[t] = tile_agg.code;
 	}
 
 	// ---- phase 2: classes and events, FP64 only in rows with above-target claims ---------------
+	// `known`: F before the next claim is determined inside this tile.  Leading PASS claims of
+	// the tile (before its first CONST claim) are left to the resolve kernel.
+	bool known = wex.isconst;
+	const bool prev_ok_possible = known && have_prev && (prev_bits & 1u) && !(prev_bits & 2u);
+	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
 	double F = 0.0; // F in force before the chunk's first claim (before its marker-before reset)
-	if (need_F)
-		F = materialise<NS>(iapply(wex, Fc_code), p.now, p.g);
+	if (known && (first_is_pass || prev_ok_possible))
+		F = materialise<NS>(wex.code, p.now, p.g);
 	int c_last = 0; // class of the claim before the current row
 	if (prev_ok_possible && F != 0.0)
 		c_last = claim_class(true, TimeIn<NS>::to_ms(prev_now), F);
@@ -371,6 +333,16 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 		if (nv[r] == 0)
 			break;
 		const unsigned long long rbase = cs + r * 64;
+		const unsigned int cmr = C0[r] | C1[r];
+		if (!known && cmr == 0u)
+			continue; // still inside the run inherited from an earlier tile: nothing to classify
+		// first classifiable position of the row (64 = none masked): the row's first CONST claim
+		int fpos = 0;
+		if (!known) {
+			const int Lf = __ffs(cmr) - 1;
+			fpos = 2 * Lf + (((C0[r] >> Lf) & 1u) ? 0 : 1);
+		}
+		known = true;
 		if ((A0[r] | A1[r]) == 0u) { // nobody above target: every class is 0, F ends at 0
 			if (c_last != 0 && lane == 0) {
 				unsigned int pos = atomicAdd(&s_evn, 1u);
@@ -420,8 +392,10 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 			c1 = v1 ? claim_class(ab1, n1, Fuse) : c0;
 			Fp = v1 ? (ab1 ? ((Fuse != 0.0) ? Fuse : __dadd_rn(n1, CODEL_INTERVAL)) : 0.0) : Fp;
 		}
-		if (!v0)
-			c0 = 0;
+		if (!v0 || 2 * lane < fpos)
+			c0 = 0; // unclassified (inherited run): no class, no event
+		if (2 * lane + 1 < fpos)
+			c1 = 0;
 		// events
 		int cprev = __shfl_up_sync(0xffffffffu, v1 ? c1 : c0, 1);
 		if (lane == 0)
@@ -442,6 +416,14 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 		c_last = __shfl_sync(0xffffffffu, (nv[r] & 1) ? c0 : c1, Lend);
 	}
 
+	// class of the tile's last claim (the warp that owns it), for the run the tile leaves open
+	{
+		unsigned long long te = ts + TILE;
+		if (te > p.n)
+			te = p.n;
+		if (lane == 0 && cs < te && te <= cs + CHUNK)
+			p.rec_cend[t] = (unsigned int)c_last;
+	}
 	if (FLAGS) {
 		unsigned long long m = last_marker;
 #pragma unroll

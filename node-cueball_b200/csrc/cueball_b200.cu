@@ -79,9 +79,11 @@ struct cb_ctx {
 	uint64_t launches = 0;
 	// scratch sized by tile count
 	size_t cap_tiles = 0;
-	unsigned long long *desc = nullptr; // scan look-back: one index-coded word per tile
 	double target_ms = 0;
-	unsigned long long scan_epoch = 0;  // 21-bit tag inside the scan descriptors
+	// per-tile run records (scan -> resolve) and resolve scratch
+	unsigned int *rec_fc = nullptr, *rec_cend = nullptr, *xcnt = nullptr, *hj_info = nullptr;
+	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr;
+	double *hj_F = nullptr;
 	SumDesc *sdesc = nullptr;
 	unsigned int *ev_count = nullptr;
 	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
@@ -141,17 +143,20 @@ int ensure_scratch(cb_ctx *c, size_t tiles) {
 	if (tiles <= c->cap_tiles)
 		return CB_OK;
 	size_t cap = tiles + tiles / 4 + 64;
+	const size_t evcap = (cap + 1) * (EVK + 3);
 	int rc;
-	if ((rc = dev_alloc(c, &c->desc, cap)) || (rc = dev_alloc(c, &c->sdesc, cap)) ||
-	    (rc = dev_alloc(c, &c->ev_count, cap)) || (rc = dev_alloc(c, &c->ev, cap * EVK)) ||
-	    (rc = dev_alloc(c, &c->evc, cap * EVK)) || (rc = dev_alloc(c, &c->ev_q, cap * EVK)) ||
-	    (rc = dev_alloc(c, &c->ev_d, cap * EVK)) || (rc = dev_alloc(c, &c->ev_now, cap * EVK)) ||
-	    (rc = dev_alloc(c, &c->iv_lo, cap * EVK + 8)) || (rc = dev_alloc(c, &c->iv_hi, cap * EVK + 8)) ||
-	    (rc = dev_alloc(c, &c->iv_cum, cap * EVK + 8)))
+	if ((rc = dev_alloc(c, &c->sdesc, cap)) || (rc = dev_alloc(c, &c->ev_count, cap)) ||
+	    (rc = dev_alloc(c, &c->ev, cap * EVK)) || (rc = dev_alloc(c, &c->rec_fc, cap)) ||
+	    (rc = dev_alloc(c, &c->rec_code, cap)) || (rc = dev_alloc(c, &c->rec_cend, cap)) ||
+	    (rc = dev_alloc(c, &c->xev, (cap + 1) * 3)) || (rc = dev_alloc(c, &c->xcnt, cap + 1)) ||
+	    (rc = dev_alloc(c, &c->hj_lo, cap + 1)) || (rc = dev_alloc(c, &c->hj_b, cap + 1)) ||
+	    (rc = dev_alloc(c, &c->hj_F, cap + 1)) || (rc = dev_alloc(c, &c->hj_info, cap + 1)) ||
+	    (rc = dev_alloc(c, &c->evc, evcap)) || (rc = dev_alloc(c, &c->ev_q, evcap)) ||
+	    (rc = dev_alloc(c, &c->ev_d, evcap)) || (rc = dev_alloc(c, &c->ev_now, evcap)) ||
+	    (rc = dev_alloc(c, &c->iv_lo, evcap + 8)) || (rc = dev_alloc(c, &c->iv_hi, evcap + 8)) ||
+	    (rc = dev_alloc(c, &c->iv_cum, evcap + 8)))
 		return rc;
-	// descriptors carry an epoch tag, so they only need zeroing once
-	CU(c, cudaMemsetAsync(c->desc, 0, cap * sizeof(unsigned long long), c->stream));
-	c->scan_epoch = 0;
+	// the emit kernel's sum descriptors carry an epoch tag, so they only need zeroing once
 	CU(c, cudaMemsetAsync(c->sdesc, 0, cap * sizeof(SumDesc), c->stream));
 	c->cap_tiles = cap;
 	return CB_OK;
@@ -172,10 +177,6 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	if (rc)
 		return rc;
 	c->epoch++;
-	if (++c->scan_epoch > DESC_EPOCH_MASK) { // the 21-bit tag wrapped: invalidate stale descriptors
-		CU(c, cudaMemsetAsync(c->desc, 0, c->cap_tiles * sizeof(unsigned long long), c->stream));
-		c->scan_epoch = 1;
-	}
 	const bool flags = d_flags != nullptr;
 
 	ScanParams sp;
@@ -184,8 +185,9 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	sp.flags = d_flags;
 	sp.n = n;
 	sp.g = c->g;
-	sp.desc = c->desc;
-	sp.epoch = c->scan_epoch;
+	sp.rec_fc = c->rec_fc;
+	sp.rec_code = c->rec_code;
+	sp.rec_cend = c->rec_cend;
 	sp.target_ns = (long long)(c->target_ms * 1000000.0);
 	sp.ev_count = c->ev_count;
 	sp.ev = c->ev;
@@ -198,14 +200,22 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	rp.n = n;
 	rp.tiles = tiles;
 	rp.g = c->g;
-	rp.desc = c->desc;
+	rp.rec_fc = c->rec_fc;
+	rp.rec_code = c->rec_code;
+	rp.rec_cend = c->rec_cend;
+	rp.xev = c->xev;
+	rp.xcnt = c->xcnt;
+	rp.hj_lo = c->hj_lo;
+	rp.hj_b = c->hj_b;
+	rp.hj_F = c->hj_F;
+	rp.hj_info = c->hj_info;
 	rp.ev_count = c->ev_count;
 	rp.ev = c->ev;
 	rp.evc = c->evc;
 	rp.ev_now = c->ev_now;
 	rp.ev_q = c->ev_q;
 	rp.ev_d = c->ev_d;
-	rp.ev_cap = tiles * EVK;
+	rp.ev_cap = (tiles + 1) * (EVK + 3);
 	rp.iv_lo = c->iv_lo;
 	rp.iv_hi = c->iv_hi;
 	rp.iv_cum = c->iv_cum;
@@ -528,7 +538,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		cudaStreamSynchronize(c->stream);
 	if (c->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(c->comm);
-	void *frees[] = {c->g, c->desc, c->sdesc, c->ev_count, c->ev, c->evc, c->ev_q, c->ev_d, c->ev_now, c->iv_lo,
+	void *frees[] = {c->g, c->rec_fc, c->rec_code, c->rec_cend, c->xev, c->xcnt, c->hj_lo, c->hj_b, c->hj_F, c->hj_info, c->sdesc, c->ev_count, c->ev, c->evc, c->ev_q, c->ev_d, c->ev_now, c->iv_lo,
 	    c->iv_hi, c->iv_cum, c->ticket, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight,
 	    c->d_ints, c->d_dbl};
 	for (void *p : frees)
