@@ -24,6 +24,8 @@ namespace cb {
 
 constexpr int EG = 2;              // groups per thread
 constexpr int EGW = 4;             // consecutive claims per group
+constexpr int IVS_MAX = 64;        // interval lists up to this length are staged in shared memory
+constexpr int EMIT_TABLE_OFF = 0;  // backend table offset inside the dynamic shared memory
 constexpr int EHALF = TPB * EGW;   // 1024: group g of thread t starts at ts + g*EHALF + t*EGW
 static_assert(EG * EHALF == TILE, "emit geometry");
 
@@ -50,17 +52,18 @@ __device__ __forceinline__ unsigned int smem_u32(const void *p) {
 }
 
 // drop bits of the 4 claims [i0, i0+4) and the number of (CoDel-level) drops before i0
-__device__ __forceinline__ unsigned int drops_general(const EmitParams &p, unsigned int m, unsigned int jstart,
-    unsigned long long i0, int nvalid, unsigned long long total_drops, unsigned long long &drops_before) {
+__device__ __forceinline__ unsigned int drops_general(const unsigned long long *iv_lo, const unsigned long long *iv_hi,
+    const unsigned long long *iv_cum, unsigned int m, unsigned int jstart, unsigned long long i0, int nvalid,
+    unsigned long long total_drops, unsigned long long &drops_before) {
 	unsigned int j = jstart;
-	while (j < m && p.iv_hi[j] < i0) // first interval with hi >= i0 (few steps from the tile's first)
+	while (j < m && iv_hi[j] < i0) // first interval with hi >= i0 (few steps from the tile's first)
 		j++;
 	if (j >= m) {
 		drops_before = total_drops;
 		return 0u;
 	}
-	unsigned long long ilo = p.iv_lo[j], ihi = p.iv_hi[j];
-	drops_before = p.iv_cum[j] + (i0 > ilo ? i0 - ilo : 0ull);
+	unsigned long long ilo = iv_lo[j], ihi = iv_hi[j];
+	drops_before = iv_cum[j] + (i0 > ilo ? i0 - ilo : 0ull);
 	unsigned int bits = 0;
 #pragma unroll
 	for (int k = 0; k < EGW; k++) {
@@ -68,8 +71,8 @@ __device__ __forceinline__ unsigned int drops_general(const EmitParams &p, unsig
 		while (j < m && i > ihi) {
 			j++;
 			if (j < m) {
-				ilo = p.iv_lo[j];
-				ihi = p.iv_hi[j];
+				ilo = iv_lo[j];
+				ihi = iv_hi[j];
 			}
 		}
 		if (k < nvalid && j < m && i >= ilo)
@@ -84,8 +87,7 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 	__shared__ __align__(8) unsigned long long s_mbar;
 	__shared__ unsigned int s_wsum[2][WARPS];
 	__shared__ unsigned long long s_tile_excl;
-	__shared__ unsigned int s_case, s_j, s_basemod;
-	__shared__ unsigned long long s_dtile;
+	__shared__ unsigned long long s_ivlo[IVS_MAX], s_ivhi[IVS_MAX], s_ivcum[IVS_MAX];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
@@ -99,54 +101,65 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 	const unsigned long long total_drops = g->gcounts[3];
 	const unsigned int S = (unsigned int)p.nslots;
 
-	if (tid == 0) {
-		// ---- kick off the TMA bulk copy of the slot->backend table -------------------------
-		if (stage_table) {
-			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar)));
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_mbar)),
-			    "r"((unsigned int)p.table_smem_bytes)
-			    : "memory");
-			asm volatile(
-			    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-			        smem_u32(s_dyn)),
-			    "l"(p.slot_backend), "r"((unsigned int)p.table_smem_bytes), "r"(smem_u32(&s_mbar))
-			    : "memory");
+	// ---- kick off the TMA bulk copy of the slot->backend table ------------------------------
+	if (stage_table && tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar)));
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_mbar)),
+		    "r"((unsigned int)p.table_smem_bytes)
+		    : "memory");
+		asm volatile(
+		    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+		        smem_u32(s_dyn + EMIT_TABLE_OFF)),
+		    "l"(p.slot_backend), "r"((unsigned int)p.table_smem_bytes), "r"(smem_u32(&s_mbar))
+		    : "memory");
+	}
+	// ---- the interval list: short lists are staged in shared memory so that no thread waits on
+	// another's dependent global loads; every thread then classifies the tile itself
+	const bool iv_smem = m <= IVS_MAX;
+	if (iv_smem) {
+		for (unsigned int k = tid; k < m; k += TPB) {
+			s_ivlo[k] = p.iv_lo[k];
+			s_ivhi[k] = p.iv_hi[k];
+			s_ivcum[k] = p.iv_cum[k];
 		}
-		// ---- classify the tile against the interval list -------------------------------------
+	}
+	__syncthreads(); // also: the mbarrier is initialised before anyone polls it
+	const unsigned long long *ivlo = iv_smem ? s_ivlo : p.iv_lo;
+	const unsigned long long *ivhi = iv_smem ? s_ivhi : p.iv_hi;
+	const unsigned long long *ivcum = iv_smem ? s_ivcum : p.iv_cum;
+	unsigned int kase = 0, jtile = 0, basemod = 0;
+	unsigned long long dtile = total_drops;
+	{
+		// classify the tile against the interval list (warp-uniform, broadcast reads)
 		unsigned long long te = ts + TILE;
 		if (te > p.n)
 			te = p.n;
 		unsigned int lo = 0, hi = m;
 		while (lo < hi) { // first interval with hi >= ts
-			unsigned int mid = (lo + hi) >> 1;
-			if (p.iv_hi[mid] >= ts)
+			const unsigned int mid = (lo + hi) >> 1;
+			if (ivhi[mid] >= ts)
 				hi = mid;
 			else
 				lo = mid + 1;
 		}
-		unsigned int kase = 0;
-		unsigned long long D = total_drops;
+		jtile = lo;
 		if (lo < m) {
-			const unsigned long long ilo = p.iv_lo[lo], ihi = p.iv_hi[lo], cum = p.iv_cum[lo];
+			const unsigned long long ilo = ivlo[lo], ihi = ivhi[lo], cum = ivcum[lo];
 			if (ilo >= te) {
 				kase = 0;
-				D = cum;
+				dtile = cum;
 			} else if (ilo <= ts && ihi >= te - 1) {
 				kase = 1;
-				D = cum + (ts - ilo);
+				dtile = cum + (ts - ilo);
 			} else {
 				kase = 2;
-				D = 0;
+				dtile = 0;
 			}
 		}
-		s_case = kase;
-		s_j = lo;
-		s_dtile = D;
-		s_basemod = (S > 0 && kase == 0) ? (unsigned int)((g->cursor0 + (ts - D)) % (unsigned long long)S) : 0u;
+		if (S > 0 && kase == 0)
+			basemod = (unsigned int)((g->cursor0 + (ts - dtile)) % (unsigned long long)S);
 	}
-	__syncthreads(); // also: the barrier is initialised before anyone polls it
-	const unsigned int kase = s_case;
 
 	unsigned int dropbits[EG], waitbits[EG], admitbits[EG], validbits[EG];
 	unsigned long long rank0[EG]; // admits before the group's first claim (whole batch)
@@ -161,12 +174,12 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 		unsigned long long db = 0;
 		if (kase == 0) {
 			dropbits[gI] = 0;
-			db = s_dtile;
+			db = dtile;
 		} else if (kase == 1) {
 			dropbits[gI] = validbits[gI];
-			db = s_dtile + (gi0[gI] - ts);
+			db = dtile + (gi0[gI] - ts);
 		} else {
-			dropbits[gI] = drops_general(p, m, s_j, gi0[gI], nval[gI], total_drops, db);
+			dropbits[gI] = drops_general(ivlo, ivhi, ivcum, m, jtile, gi0[gI], nval[gI], total_drops, db);
 		}
 		waitbits[gI] = 0xfu;
 		if (FLAGS) {
@@ -286,7 +299,7 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 			if (!FLAGS && kase == 0) {
 				// tile-uniform base + a small offset: no 64-bit division per thread
 				unsigned int off = (unsigned int)(gi0[gI] - ts);
-				scur = (S >= (unsigned int)TILE) ? s_basemod + off : (s_basemod + off) % S;
+				scur = (S >= (unsigned int)TILE) ? basemod + off : (basemod + off) % S;
 				if (scur >= S)
 					scur -= S;
 			} else {

@@ -44,6 +44,7 @@ struct ResolveParams {
 	const unsigned int *rec_fc;         // per-tile records from the scan kernel
 	const unsigned long long *rec_code;
 	const unsigned int *rec_cend;
+	const void *tile_now0;              // raw clock of every tile's first claim (coarse search index)
 	// cross-tile run events (<= 3 per closing tile; slot `tiles` = the run open at batch end)
 	unsigned long long *xev;            // [(tiles+1)*3]
 	unsigned int *xcnt;                 // [tiles+1]
@@ -75,65 +76,76 @@ __device__ __forceinline__ double now_at(const void *now, unsigned long long i) 
 	return TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(now)[i]);
 }
 
-// first index in [lo,hi) with now >= D, else hi.  Warp-cooperative 32-ary search.
-template <bool NS>
-__device__ unsigned long long warp_lower_bound(const void *now, unsigned long long lo,
-    unsigned long long hi, double D, int lane) {
-	while (true) {
-		unsigned long long s = hi - lo;
-		if (s == 0)
-			return hi;
-		if (s <= 32) {
-			bool pr = (lane < s) && (now_at<NS>(now, lo + lane) >= D);
-			unsigned int m = __ballot_sync(0xffffffffu, pr);
-			return m ? lo + (__ffs(m) - 1) : hi;
-		}
-		unsigned long long chunk = (s + 31) / 32;
-		unsigned long long pidx = lo + (unsigned long long)(lane + 1) * chunk - 1;
-		if (pidx > hi - 1)
-			pidx = hi - 1;
-		bool pr = now_at<NS>(now, pidx) >= D;
-		unsigned int m = __ballot_sync(0xffffffffu, pr);
-		if (!m)
-			return hi;
-		int f = __ffs(m) - 1;
-		unsigned long long pf = __shfl_sync(0xffffffffu, pidx, f);
-		unsigned long long pprev = __shfl_sync(0xffffffffu, pidx, f > 0 ? f - 1 : 0);
-		if (f > 0)
-			lo = pprev + 1;
-		hi = pf; // answer in [lo, pf]; pf itself satisfies the predicate
-		if (lo >= hi)
-			return hi;
+// Monotone predicates on the clock: level 0: now >= x (drop_next test, codel.js:65);
+// level 1/2: canDrop class w.r.t. first_above_time x is >= level.
+struct Pred {
+	double x;
+	int level;
+	__device__ __forceinline__ bool operator()(double now) const {
+		return level == 0 ? (now >= x) : (claim_class(true, now, x) >= level);
 	}
-}
-// first index in [lo,hi) whose canDrop class w.r.t. F is >= level, else hi (class is monotone in
-// the clock inside an above-target run)
+};
+
+// First index in [lo,hi) whose clock satisfies the (monotone) predicate, else hi.
+// Two levels: a coarse index of the clock at every G-th claim lives in shared memory (no DRAM
+// round trip), then a 64-ary warp-cooperative search over at most G claims: 2 dependent DRAM
+// accesses for G = 2048 instead of 5 for a plain 32-ary search over 2^24 claims.
 template <bool NS>
-__device__ unsigned long long warp_first_class(const void *now, unsigned long long lo, unsigned long long hi,
-    double F, int level, int lane) {
+__device__ unsigned long long warp_search(const void *now, const double *s_idx, unsigned long long G,
+    unsigned long long lo, unsigned long long hi, const Pred pr, int lane) {
+	if (hi <= lo)
+		return hi;
+	{
+		const unsigned long long ka = lo / G + 1, kb = (hi - 1) / G; // coarse boundaries inside (lo, hi-1]
+		if (ka <= kb) {
+			unsigned long long a = ka, b = kb + 1;
+			while (a < b) { // first boundary whose clock satisfies the predicate (smem, all lanes alike)
+				const unsigned long long mid = (a + b) >> 1;
+				if (pr(s_idx[mid]))
+					b = mid;
+				else
+					a = mid + 1;
+			}
+			if (a > ka)
+				lo = (a - 1) * G + 1; // boundary a-1 fails: the answer lies beyond it
+			if (a <= kb)
+				hi = a * G; // claim a*G satisfies: the answer is at most a*G (= the fallback `hi`)
+		}
+	}
 	while (true) {
-		unsigned long long s = hi - lo;
+		const unsigned long long s = hi - lo;
 		if (s == 0)
 			return hi;
-		if (s <= 32) {
-			bool pr = (lane < s) && (claim_class(true, now_at<NS>(now, lo + lane), F) >= level);
-			unsigned int m = __ballot_sync(0xffffffffu, pr);
-			return m ? lo + (__ffs(m) - 1) : hi;
-		}
-		unsigned long long chunk = (s + 31) / 32;
-		unsigned long long pidx = lo + (unsigned long long)(lane + 1) * chunk - 1;
-		if (pidx > hi - 1)
-			pidx = hi - 1;
-		bool pr = claim_class(true, now_at<NS>(now, pidx), F) >= level;
-		unsigned int m = __ballot_sync(0xffffffffu, pr);
-		if (!m)
+		if (s <= 64) {
+			const bool p0 = (lane < s) && pr(now_at<NS>(now, lo + lane));
+			const bool p1 = (lane + 32 < s) && pr(now_at<NS>(now, lo + 32 + lane));
+			const unsigned int m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+			if (m0)
+				return lo + (__ffs(m0) - 1);
+			if (m1)
+				return lo + 32 + (__ffs(m1) - 1);
 			return hi;
-		int f = __ffs(m) - 1;
-		unsigned long long pf = __shfl_sync(0xffffffffu, pidx, f);
-		unsigned long long pprev = __shfl_sync(0xffffffffu, pidx, f > 0 ? f - 1 : 0);
-		if (f > 0)
-			lo = pprev + 1;
-		hi = pf;
+		}
+		const unsigned long long chunk = (s + 63) / 64;
+		unsigned long long i0 = lo + (unsigned long long)(lane + 1) * chunk - 1;
+		unsigned long long i1 = lo + (unsigned long long)(lane + 33) * chunk - 1;
+		if (i0 > hi - 1)
+			i0 = hi - 1;
+		if (i1 > hi - 1)
+			i1 = hi - 1;
+		const bool p0 = pr(now_at<NS>(now, i0)), p1 = pr(now_at<NS>(now, i1));
+		const unsigned int m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+		if (!(m0 | m1))
+			return hi;
+		// first satisfying probe j in 0..63 and the probe before it
+		const int j = m0 ? (__ffs(m0) - 1) : (32 + __ffs(m1) - 1);
+		const unsigned long long pj = __shfl_sync(0xffffffffu, (j < 32) ? i0 : i1, j & 31);
+		if (j > 0) {
+			const int jp = j - 1;
+			const unsigned long long pp = __shfl_sync(0xffffffffu, (jp < 32) ? i0 : i1, jp & 31);
+			lo = pp + 1;
+		}
+		hi = pj; // pj itself satisfies the predicate
 		if (lo >= hi)
 			return hi;
 	}
@@ -243,18 +255,28 @@ __device__ void sequential_path(const ResolveParams &p, int lane) {
 	}
 }
 
+constexpr int RT = 8;          // tile slots per thread per pass (8192 per pass)
+constexpr int NIDX_MAX = 8192; // coarse clock index entries kept in shared memory (64 KB)
+
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p) {
+	extern __shared__ __align__(16) double s_idx[]; // clock (ms) at claim k*G, k < nidx
 	__shared__ unsigned int s_warp[32];
+	__shared__ int s_wmax[32];
 	__shared__ unsigned int s_base;
 	__shared__ unsigned int s_nev;
 	__shared__ int s_fallback;
+	__shared__ long long s_prevconst; // last tile with a CONST claim seen so far (-1: none)
+	__shared__ unsigned int s_nheavy;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
+	using raw_t = typename TimeIn<NS>::raw_t;
 
 	if (tid == 0) {
 		s_fallback = (g->nonmono != 0u) || (g->overflow != 0u);
 		s_base = 0;
+		s_prevconst = -1;
+		s_nheavy = 0;
 	}
 	__syncthreads();
 	if (s_fallback) {
@@ -262,29 +284,35 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			sequential_path<NS>(p, lane);
 		return;
 	}
+	// coarse clock index: every `stride`-th tile's first claim
+	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
+	const unsigned long long G = stride * TILE;
+	const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
+	for (unsigned int k = tid; k < nidx; k += RTPB)
+		s_idx[k] = TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(p.tile_now0)[(unsigned long long)k * stride]);
+	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
 
 	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
-	__shared__ int s_wmax[32];
-	__shared__ long long s_prevconst; // last tile with a CONST claim seen so far (-1: none yet)
-	__shared__ unsigned int s_nheavy;
-	if (tid == 0) {
-		s_prevconst = -1;
-		s_nheavy = 0;
-	}
-	__syncthreads();
-	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
-	for (unsigned long long tb = 0; tb < p.tiles + 1; tb += RTPB) {
-		const unsigned long long t = tb + tid;
-		// slot `tiles` is a virtual closing tile at index n (the run still open at batch end)
-		const bool is_tail = (t == p.tiles);
-		const unsigned int fc = (t < p.tiles) ? p.rec_fc[t] : (is_tail ? 0u : FC_NONE);
-		const bool hc = (t <= p.tiles) && fc != FC_NONE;
-		// exclusive max-scan of (hc ? t : -1) over the block
-		int v = (hc && !is_tail) ? (int)(t - tb) : -1; // block-local index
-		int x = v;
+	// One pass handles RT consecutive tiles per thread with every load of a stage issued
+	// together, so the pass costs a handful of dependent memory round trips, not RT of them.
+	for (unsigned long long base = 0; base < p.tiles; base += (unsigned long long)RTPB * RT) {
+		const unsigned long long t0 = base + (unsigned long long)tid * RT;
+		unsigned int fc[RT];
+		int T0l[RT]; // block-local slot of the opener, -1 = before this thread, resolved below
+		int lastc = -1;
+#pragma unroll
+		for (int k = 0; k < RT; k++)
+			fc[k] = (t0 + k < p.tiles) ? p.rec_fc[t0 + k] : FC_NONE;
+#pragma unroll
+		for (int k = 0; k < RT; k++) {
+			T0l[k] = lastc;
+			if (fc[k] != FC_NONE)
+				lastc = tid * RT + k;
+		}
+		int x = lastc;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
-			int y = __shfl_up_sync(0xffffffffu, x, o);
+			const int y = __shfl_up_sync(0xffffffffu, x, o);
 			if (lane >= o)
 				x = max(x, y);
 		}
@@ -298,48 +326,99 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		if (lane == 0)
 			ex = -1;
 		ex = max(ex, wprev);
-		const long long T0 = (ex >= 0) ? (long long)(tb + ex) : s_prevconst;
-		if (hc) {
-			const unsigned long long code0 = (T0 < 0) ? carry_code : p.rec_code[T0];
-			const unsigned int cend0 = (T0 < 0) ? 0u : p.rec_cend[T0];
-			const unsigned long long lo = (unsigned long long)(T0 + 1) * TILE;
-			const unsigned long long close_idx = is_tail ? p.n : (t * TILE + fc); // first claim after the run
-			unsigned int cnt = 0;
-			int final_c = (int)cend0;
-			if (lo < close_idx) { // unclassified stretch [lo, close_idx)
-				double F;
-				if (code0 == CODE_ZERO)
-					F = __dadd_rn(now_at<NS>(p.now, lo), CODEL_INTERVAL); // the stretch's first claim opens the run
-				else if (code0 == CODE_CARRY)
-					F = g->F;
+		const long long Tbefore = (ex >= 0) ? (long long)(base + ex) : s_prevconst;
+		// stage 1: the opener's record
+		long long T0[RT];
+		unsigned long long code0[RT];
+		unsigned int cend0[RT];
+#pragma unroll
+		for (int k = 0; k < RT; k++) {
+			T0[k] = (T0l[k] >= 0) ? (long long)(base + T0l[k]) : Tbefore;
+			code0[k] = carry_code;
+			cend0[k] = 0;
+			if (fc[k] != FC_NONE && T0[k] >= 0) {
+				code0[k] = p.rec_code[T0[k]];
+				cend0[k] = p.rec_cend[T0[k]];
+			}
+		}
+		// stage 2: clock at the run's defining claim and at the stretch's last claim
+		double Fv[RT], nb[RT];
+		bool stretch[RT];
+#pragma unroll
+		for (int k = 0; k < RT; k++) {
+			const unsigned long long lo = (unsigned long long)(T0[k] + 1) * TILE;
+			const unsigned long long close_idx = (t0 + k) * TILE + fc[k];
+			stretch[k] = (fc[k] != FC_NONE) && (lo < close_idx);
+			Fv[k] = 0.0;
+			nb[k] = 0.0;
+			if (stretch[k]) {
+				if (code0[k] == CODE_CARRY)
+					Fv[k] = g->F;
 				else
-					F = __dadd_rn(now_at<NS>(p.now, code0 - 2), CODEL_INTERVAL);
-				const int cb = claim_class(true, now_at<NS>(p.now, close_idx - 1), F);
-				if (cb > final_c) { // the class rises inside the stretch: find where (one warp, below)
-					const unsigned int h = atomicAdd(&s_nheavy, 1u);
-					p.hj_lo[h] = lo;
-					p.hj_b[h] = close_idx - 1;
-					p.hj_F[h] = F;
-					p.hj_info[h] = (unsigned int)t | (cend0 << 28);
-					final_c = cb;
+					Fv[k] = __dadd_rn(now_at<NS>(p.now, code0[k] == CODE_ZERO ? lo : code0[k] - 2), CODEL_INTERVAL);
+				nb[k] = now_at<NS>(p.now, close_idx - 1);
+			}
+		}
+		// stage 3: does the class rise inside the stretch?  close event?
+#pragma unroll
+		for (int k = 0; k < RT; k++) {
+			if (t0 + k >= p.tiles)
+				continue;
+			unsigned int bits = 0;
+			if (fc[k] != FC_NONE) {
+				const unsigned long long close_idx = (t0 + k) * TILE + fc[k];
+				int final_c = (int)cend0[k];
+				if (stretch[k]) {
+					const int cb = claim_class(true, nb[k], Fv[k]);
+					if (cb > final_c) { // find where (one warp per such run, below)
+						const unsigned int h = atomicAdd(&s_nheavy, 1u);
+						p.hj_lo[h] = (unsigned long long)(T0[k] + 1) * TILE;
+						p.hj_b[h] = close_idx - 1;
+						p.hj_F[h] = Fv[k];
+						p.hj_info[h] = (unsigned int)(t0 + k) | (cend0[k] << 28);
+						final_c = cb;
+					}
+				}
+				if (final_c >= 1) { // the run ends at a CONST claim (class 0)
+					p.xev[(t0 + k) * 3 + 2] = (close_idx << 2);
+					bits = 4u;
 				}
 			}
-			if (final_c >= 1 && !is_tail) // the run ends at a CONST claim (class 0)
-				p.xev[t * 3 + 2] = (close_idx << 2);
-			cnt = (final_c >= 1 && !is_tail) ? 4u : 0u; // bit 2: close event present
-			p.xcnt[t] = cnt;
-		} else if (t <= p.tiles) {
-			p.xcnt[t] = 0;
+			p.xcnt[t0 + k] = bits;
 		}
 		__syncthreads();
 		if (tid == RTPB - 1) {
 			const int blockmax = max(x, wprev);
 			if (blockmax >= 0)
-				s_prevconst = (long long)(tb + blockmax);
+				s_prevconst = (long long)(base + blockmax);
 		}
 		__syncthreads();
 	}
-	// long runs: class crossings by binary search, one warp per run
+	// the run still open at the end of the batch: a virtual closing slot `tiles` at index n
+	if (tid == 0) {
+		const long long T0 = s_prevconst;
+		const unsigned long long code0 = (T0 < 0) ? carry_code : p.rec_code[T0];
+		const unsigned int cend0 = (T0 < 0) ? 0u : p.rec_cend[T0];
+		const unsigned long long lo = (unsigned long long)(T0 + 1) * TILE;
+		if (lo < p.n) {
+			double F;
+			if (code0 == CODE_CARRY)
+				F = g->F;
+			else
+				F = __dadd_rn(now_at<NS>(p.now, code0 == CODE_ZERO ? lo : code0 - 2), CODEL_INTERVAL);
+			const int cb = claim_class(true, now_at<NS>(p.now, p.n - 1), F);
+			if (cb > (int)cend0) {
+				const unsigned int h = atomicAdd(&s_nheavy, 1u);
+				p.hj_lo[h] = lo;
+				p.hj_b[h] = p.n - 1;
+				p.hj_F[h] = F;
+				p.hj_info[h] = (unsigned int)p.tiles | (cend0 << 28);
+			}
+		}
+		p.xcnt[p.tiles] = 0;
+	}
+	__syncthreads();
+	// long runs: class crossings by search, one warp per run
 	const unsigned int nheavy = s_nheavy;
 	for (unsigned int h = warp; h < nheavy; h += RTPB / 32) {
 		const unsigned long long lo = p.hj_lo[h], b = p.hj_b[h];
@@ -352,12 +431,18 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		unsigned long long pos = lo;
 		int cur = cend0;
 		if (cur == 0) {
-			pos = warp_first_class<NS>(p.now, lo, b + 1, F, 1, lane);
+			Pred pr;
+			pr.x = F;
+			pr.level = 1;
+			pos = warp_search<NS>(p.now, s_idx, G, lo, b + 1, pr, lane);
 			cur = claim_class(true, now_at<NS>(p.now, pos), F); // 1 or 2
 			e0 = (pos << 2) | (unsigned long long)cur;
 		}
 		if (cur == 1) {
-			const unsigned long long p2 = warp_first_class<NS>(p.now, pos, b + 1, F, 2, lane);
+			Pred pr;
+			pr.x = F;
+			pr.level = 2;
+			const unsigned long long p2 = warp_search<NS>(p.now, s_idx, G, pos, b + 1, pr, lane);
 			if (p2 <= b)
 				e1 = (p2 << 2) | 2ull;
 		}
@@ -376,16 +461,20 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	__syncthreads();
 
 	// ---- B. merge run events and local events into one ordered list -----------------------------
-	for (unsigned long long tb = 0; tb < p.tiles + 1; tb += RTPB) {
-		unsigned long long t = tb + tid;
-		const unsigned int xb = (t <= p.tiles) ? p.xcnt[t] : 0u;
-		const unsigned int lc = (t < p.tiles) ? p.ev_count[t] : 0u;
-		const unsigned int cnt = __popc(xb) + lc;
-		// block exclusive scan of cnt
+	for (unsigned long long base = 0; base < p.tiles; base += (unsigned long long)RTPB * RT) {
+		const unsigned long long t0 = base + (unsigned long long)tid * RT;
+		unsigned int xb[RT], lc[RT], cnt = 0;
+#pragma unroll
+		for (int k = 0; k < RT; k++) {
+			const bool in = t0 + k < p.tiles;
+			xb[k] = in ? p.xcnt[t0 + k] : 0u;
+			lc[k] = in ? p.ev_count[t0 + k] : 0u;
+			cnt += __popc(xb[k]) + lc[k];
+		}
 		unsigned int x = cnt;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
-			unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+			const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
 			if (lane >= o)
 				x += y;
 		}
@@ -393,62 +482,70 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			s_warp[warp] = x;
 		__syncthreads();
 		if (warp == 0) {
-			unsigned int w = s_warp[lane];
+			const unsigned int w = s_warp[lane];
 			unsigned int ws = w;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
-				unsigned int y = __shfl_up_sync(0xffffffffu, ws, o);
+				const unsigned int y = __shfl_up_sync(0xffffffffu, ws, o);
 				if (lane >= o)
 					ws += y;
 			}
 			s_warp[lane] = ws - w; // exclusive
 			if (lane == 31)
-				s_nev = ws;        // chunk total
+				s_nev = ws;        // pass total
 		}
 		__syncthreads();
 		unsigned int off = s_base + s_warp[warp] + (x - cnt);
 		if (cnt) {
-			// run events of the tile's close come first (crossing(s) <= close index <= local events)
-			if ((xb & 1u) && off < p.ev_cap)
-				p.evc[off++] = p.xev[t * 3 + 0];
-			if ((xb & 2u) && off < p.ev_cap)
-				p.evc[off++] = p.xev[t * 3 + 1];
-			if ((xb & 4u) && off < p.ev_cap)
-				p.evc[off++] = p.xev[t * 3 + 2];
-		}
-		if (lc) {
-			// a tile's events were appended unordered: sort its <= EVK entries by index
-			unsigned long long e[EVK];
+			for (int k = 0; k < RT; k++) {
+				const unsigned long long t = t0 + k;
+				// run events of the tile's close come first (crossings <= close index <= local events)
+				if ((xb[k] & 1u) && off < p.ev_cap)
+					p.evc[off++] = p.xev[t * 3 + 0];
+				if ((xb[k] & 2u) && off < p.ev_cap)
+					p.evc[off++] = p.xev[t * 3 + 1];
+				if ((xb[k] & 4u) && off < p.ev_cap)
+					p.evc[off++] = p.xev[t * 3 + 2];
+				if (lc[k]) {
+					// a tile's events were appended unordered: sort its <= EVK entries by index
+					unsigned long long e[EVK];
 #pragma unroll
-			for (int j = 0; j < EVK; j++)
-				e[j] = (j < (int)lc) ? p.ev[t * EVK + j] : ~0ull;
+					for (int j = 0; j < EVK; j++)
+						e[j] = (j < (int)lc[k]) ? p.ev[t * EVK + j] : ~0ull;
 #pragma unroll
-			for (int a = 1; a < EVK; a++) {
+					for (int a = 1; a < EVK; a++) {
 #pragma unroll
-				for (int b = EVK - 1; b >= 1; b--) {
-					if (b >= a && e[b] < e[b - 1]) {
-						unsigned long long tmp = e[b];
-						e[b] = e[b - 1];
-						e[b - 1] = tmp;
+						for (int b = EVK - 1; b >= 1; b--) {
+							if (b >= a && e[b] < e[b - 1]) {
+								const unsigned long long tmp = e[b];
+								e[b] = e[b - 1];
+								e[b - 1] = tmp;
+							}
+						}
 					}
+#pragma unroll
+					for (int j = 0; j < EVK; j++)
+						if (j < (int)lc[k] && off < p.ev_cap)
+							p.evc[off++] = e[j];
 				}
 			}
-#pragma unroll
-			for (int j = 0; j < EVK; j++)
-				if (j < (int)lc && off + j < p.ev_cap)
-					p.evc[off + j] = e[j];
 		}
 		__syncthreads();
 		if (tid == 0)
 			s_base += s_nev;
 		__syncthreads();
 	}
-	const unsigned int nev = s_base;
-	if (nev > p.ev_cap) { // cannot happen with ev_cap = (tiles+1)*(EVK+3); defensive: exact path
-		if (warp == 0)
-			sequential_path<NS>(p, lane);
-		return;
+	if (tid == 0) { // the tail slot's events come last
+		const unsigned int xbt = p.xcnt[p.tiles];
+		unsigned int off = s_base;
+		if ((xbt & 1u) && off < p.ev_cap)
+			p.evc[off++] = p.xev[p.tiles * 3 + 0];
+		if ((xbt & 2u) && off < p.ev_cap)
+			p.evc[off++] = p.xev[p.tiles * 3 + 1];
+		s_base = off;
 	}
+	__syncthreads();
+	const unsigned int nev = s_base;
 
 	// ---- 2. per event (one warp each): run end q, now at the event, speculated drop start
 	const double D_in = g->D;
@@ -473,10 +570,15 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		}
 		double nowk = now_at<NS>(p.now, idx);
 		unsigned long long d;
-		if (k == 0 && idx == 0 && B_in) // batch opens inside a dropping episode
-			d = warp_lower_bound<NS>(p.now, idx, q + 1, D_in, lane);
-		else
-			d = warp_lower_bound<NS>(p.now, idx + 1, q + 1, __dadd_rn(nowk, CODEL_INTERVAL), lane);
+		Pred pr;
+		pr.level = 0;
+		if (k == 0 && idx == 0 && B_in) { // batch opens inside a dropping episode
+			pr.x = D_in;
+			d = warp_search<NS>(p.now, s_idx, G, idx, q + 1, pr, lane);
+		} else {
+			pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
+			d = warp_search<NS>(p.now, s_idx, G, idx + 1, q + 1, pr, lane);
+		}
 		if (lane == 0) {
 			p.ev_now[k] = nowk;
 			p.ev_q[k] = q;

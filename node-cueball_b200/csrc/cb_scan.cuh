@@ -33,6 +33,7 @@
 // front of the NEXT claim, which is equivalent and keeps the carried value meaningful.)
 #pragma once
 #include "cb_device.cuh"
+#include <type_traits>
 
 namespace cb {
 
@@ -79,6 +80,7 @@ struct ScanParams {
 	unsigned int *rec_fc;          // [tiles] tile-local position of the first CONST claim, or FC_NONE
 	unsigned long long *rec_code;  // [tiles] valid when rec_fc != FC_NONE
 	unsigned int *rec_cend;        // [tiles] valid when rec_fc != FC_NONE
+	void *tile_now0;               // [tiles] raw clock of the tile's first claim (coarse search index)
 	unsigned int *ev_count;   // [tiles]
 	unsigned long long *ev;   // [tiles][EVK]  (index << 2) | class
 	int vec_ok;               // start/now 16-byte aligned
@@ -205,47 +207,48 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 		    ((pf & F_EMPTY_AFTER) ? 4u : 0u);
 	}
 
-	// ---- phase 1: above bits, CONST/PASS types, row -> warp composition (integers only) ----
+	// ---- phase 1: above bits, CONST/PASS types (integers only) --------------------------------
 	unsigned int A0[ROWS], A1[ROWS], C0[ROWS], C1[ROWS]; // ballots: above / CONST-type, per claim slot
 	int nv[ROWS];                                        // valid claims in the row
-	IAgg wagg;
-	wagg.isconst = false;
-	wagg.code = CODE_ZERO;
 	bool nonmono = false;
-	unsigned int carry_mk = (prev_bits >> 2) & 1u; // marker of the claim before the row (warp-uniform)
 	unsigned long long last_marker = 0;
-	unsigned int wfc = FC_NONE; // chunk-local position of the first CONST claim
+	auto phase1 = [&](auto full_tag) {
+		constexpr bool FULL = decltype(full_tag)::value; // every claim of the chunk exists
+		unsigned int carry_mk = (prev_bits >> 2) & 1u;   // marker of the claim before the row (warp-uniform)
 #pragma unroll
-	for (int r = 0; r < ROWS; r++) {
-		const unsigned long long rbase = cs + r * 64;
-		long long rem = (long long)p.n - (long long)rbase;
-		nv[r] = rem >= 64 ? 64 : (rem > 0 ? (int)rem : 0);
-		const bool v0 = 2 * lane < nv[r], v1 = 2 * lane + 1 < nv[r];
-		const bool ab0 = v0 && is_above<NS>(rs[r][0], rn[r][0], tgt_ns, target);
-		const bool ab1 = v1 && is_above<NS>(rs[r][1], rn[r][1], tgt_ns, target);
-		bool mp0 = false, mp1 = false;
-		if (FLAGS) {
-			const unsigned int mk0 = (fl[r] >> 1) & 1u, mk1 = (fl[r] >> 9) & 1u; // own markers
-			unsigned int up = __shfl_up_sync(0xffffffffu, mk1, 1);
-			if (lane == 0)
-				up = carry_mk;
-			mp0 = up != 0;
-			mp1 = mk0 != 0;
-			carry_mk = __shfl_sync(0xffffffffu, mk1, 31);
-			if (v1 && mk1)
-				last_marker = rbase + 2 * lane + 2;
-			else if (v0 && mk0)
-				last_marker = rbase + 2 * lane + 1;
-		}
-		const bool c0 = v0 && (!ab0 || mp0), c1 = v1 && (!ab1 || mp1);
-		A0[r] = __ballot_sync(0xffffffffu, ab0);
-		A1[r] = __ballot_sync(0xffffffffu, ab1);
-		C0[r] = __ballot_sync(0xffffffffu, c0);
-		C1[r] = __ballot_sync(0xffffffffu, c1);
-		// monotone clock (raw domain: ns-monotone implies ms-monotone)
-		if (v1 && Raw<NS>::less(rn[r][1], rn[r][0]))
-			nonmono = true;
-		{
+		for (int r = 0; r < ROWS; r++) {
+			const unsigned long long rbase = cs + r * 64;
+			if (FULL) {
+				nv[r] = 64;
+			} else {
+				const long long rem = (long long)p.n - (long long)rbase;
+				nv[r] = rem >= 64 ? 64 : (rem > 0 ? (int)rem : 0);
+			}
+			const bool v0 = FULL || (2 * lane < nv[r]), v1 = FULL || (2 * lane + 1 < nv[r]);
+			const bool ab0 = v0 && is_above<NS>(rs[r][0], rn[r][0], tgt_ns, target);
+			const bool ab1 = v1 && is_above<NS>(rs[r][1], rn[r][1], tgt_ns, target);
+			A0[r] = __ballot_sync(0xffffffffu, ab0);
+			A1[r] = __ballot_sync(0xffffffffu, ab1);
+			if (FLAGS) {
+				const unsigned int mk0 = (fl[r] >> 1) & 1u, mk1 = (fl[r] >> 9) & 1u; // own markers
+				unsigned int up = __shfl_up_sync(0xffffffffu, mk1, 1);
+				if (lane == 0)
+					up = carry_mk;
+				carry_mk = __shfl_sync(0xffffffffu, mk1, 31);
+				if (v1 && mk1)
+					last_marker = rbase + 2 * lane + 2;
+				else if (v0 && mk0)
+					last_marker = rbase + 2 * lane + 1;
+				C0[r] = __ballot_sync(0xffffffffu, v0 && (!ab0 || up != 0));
+				C1[r] = __ballot_sync(0xffffffffu, v1 && (!ab1 || mk0 != 0));
+			} else if (FULL) {
+				C0[r] = ~A0[r]; // without markers a claim is CONST-type iff it is below target
+				C1[r] = ~A1[r];
+			} else {
+				C0[r] = __ballot_sync(0xffffffffu, v0) & ~A0[r];
+				C1[r] = __ballot_sync(0xffffffffu, v1) & ~A1[r];
+			}
+			// monotone clock (raw domain: ns-monotone implies ms-monotone)
 			raw_t prevn = __shfl_up_sync(0xffffffffu, rn[r][1], 1);
 			bool haveprevn = lane > 0;
 			if (r > 0) {
@@ -258,30 +261,53 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 				prevn = prev_now;
 				haveprevn = true;
 			}
-			if (v0 && haveprevn && Raw<NS>::less(rn[r][0], prevn))
+			if ((v1 && Raw<NS>::less(rn[r][1], rn[r][0])) || (v0 && haveprevn && Raw<NS>::less(rn[r][0], prevn)))
 				nonmono = true;
 		}
-		// row composition in index form
-		IAgg ra;
-		const unsigned int cm = C0[r] | C1[r];
-		if (cm) {
-			if (wfc == FC_NONE) {
-				const int Lf = __ffs(cm) - 1;
-				wfc = r * 64 + 2 * Lf + (((C0[r] >> Lf) & 1u) ? 0 : 1);
+	};
+	if (full)
+		phase1(std::true_type{});
+	else
+		phase1(std::false_type{});
+
+	// ---- chunk composition in index form, straight from the ballots -------------------------------
+	IAgg wagg;
+	unsigned int wfc = FC_NONE; // chunk-local position of the first CONST claim
+	{
+		unsigned int cm_l = 0, c1_l = 0, a0_l = 0, a1_l = 0, cm_f = 0, c0_f = 0;
+		int r_l = -1, r_f = -1, nvt = 0;
+#pragma unroll
+		for (int r = 0; r < ROWS; r++) {
+			const unsigned int cm = C0[r] | C1[r];
+			nvt += nv[r];
+			if (cm) {
+				if (r_f < 0) {
+					r_f = r;
+					cm_f = cm;
+					c0_f = C0[r];
+				}
+				r_l = r;
+				cm_l = cm;
+				c1_l = C1[r];
+				a0_l = A0[r];
+				a1_l = A1[r];
 			}
-			const int L = 31 - __clz(cm);
-			const int j = (C1[r] >> L) & 1u;
-			const int ppos = 2 * L + j;
-			const bool abp = ((j ? A1[r] : A0[r]) >> L) & 1u; // CONST and above => marker before
-			ra.isconst = true;
-			ra.code = abp ? (rbase + ppos + 2) : CODE_ZERO;
-			if (ra.code == CODE_ZERO && ppos + 1 < nv[r])
-				ra.code = rbase + ppos + 1 + 2; // the next claim is a PASS (above) claim
-		} else {
-			ra.isconst = false;
-			ra.code = nv[r] > 0 ? (rbase + 2) : CODE_ZERO;
 		}
-		wagg = icompose(wagg, ra);
+		if (r_l >= 0) {
+			const int L = 31 - __clz(cm_l);
+			const int j = (c1_l >> L) & 1u;
+			const int pos = r_l * 64 + 2 * L + j;             // last CONST claim of the chunk
+			const bool abp = ((j ? a1_l : a0_l) >> L) & 1u;   // CONST and above => a marker precedes it
+			wagg.isconst = true;
+			wagg.code = abp ? (cs + pos + 2) : CODE_ZERO;
+			if (wagg.code == CODE_ZERO && pos + 1 < nvt)
+				wagg.code = cs + pos + 1 + 2; // the claim after it is a PASS (above) claim and sets F
+			const int Lf = __ffs(cm_f) - 1;
+			wfc = r_f * 64 + 2 * Lf + (((c0_f >> Lf) & 1u) ? 0 : 1);
+		} else {
+			wagg.isconst = false;
+			wagg.code = nvt > 0 ? (cs + 2) : CODE_ZERO;
+		}
 	}
 	if (lane == 0) {
 		s_wagg[warp] = ((unsigned long long)wagg.isconst << 63) | wagg.code;
@@ -314,6 +340,7 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 				fc = w * CHUNK + s_wfc[w];
 		p.rec_fc[t] = fc;
 		p.rec_code[t] = tile_agg.code;
+		reinterpret_cast<raw_t *>(p.tile_now0)[t] = rn[0][0]; // thread 0 owns the tile's first claim
 	}
 
 	// ---- phase 2: classes and events, FP64 only in rows with above-target claims ---------------

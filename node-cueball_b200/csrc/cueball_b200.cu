@@ -84,6 +84,7 @@ struct cb_ctx {
 	unsigned int *rec_fc = nullptr, *rec_cend = nullptr, *xcnt = nullptr, *hj_info = nullptr;
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr;
 	double *hj_F = nullptr;
+	unsigned long long *tile_now0 = nullptr;
 	SumDesc *sdesc = nullptr;
 	unsigned int *ev_count = nullptr;
 	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
@@ -148,6 +149,7 @@ int ensure_scratch(cb_ctx *c, size_t tiles) {
 	if ((rc = dev_alloc(c, &c->sdesc, cap)) || (rc = dev_alloc(c, &c->ev_count, cap)) ||
 	    (rc = dev_alloc(c, &c->ev, cap * EVK)) || (rc = dev_alloc(c, &c->rec_fc, cap)) ||
 	    (rc = dev_alloc(c, &c->rec_code, cap)) || (rc = dev_alloc(c, &c->rec_cend, cap)) ||
+	    (rc = dev_alloc(c, &c->tile_now0, cap)) ||
 	    (rc = dev_alloc(c, &c->xev, (cap + 1) * 3)) || (rc = dev_alloc(c, &c->xcnt, cap + 1)) ||
 	    (rc = dev_alloc(c, &c->hj_lo, cap + 1)) || (rc = dev_alloc(c, &c->hj_b, cap + 1)) ||
 	    (rc = dev_alloc(c, &c->hj_F, cap + 1)) || (rc = dev_alloc(c, &c->hj_info, cap + 1)) ||
@@ -188,6 +190,7 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	sp.rec_fc = c->rec_fc;
 	sp.rec_code = c->rec_code;
 	sp.rec_cend = c->rec_cend;
+	sp.tile_now0 = c->tile_now0;
 	sp.target_ns = (long long)(c->target_ms * 1000000.0);
 	sp.ev_count = c->ev_count;
 	sp.ev = c->ev;
@@ -203,6 +206,7 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	rp.rec_fc = c->rec_fc;
 	rp.rec_code = c->rec_code;
 	rp.rec_cend = c->rec_cend;
+	rp.tile_now0 = c->tile_now0;
 	rp.xev = c->xev;
 	rp.xcnt = c->xcnt;
 	rp.hj_lo = c->hj_lo;
@@ -256,9 +260,9 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s));
 	if (flags)
-		resolve_kernel<NS, true><<<1, RTPB, 0, s>>>(rp);
+		resolve_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	else
-		resolve_kernel<NS, false><<<1, RTPB, 0, s>>>(rp);
+		resolve_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[2], s));
 	if (flags)
@@ -523,6 +527,10 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	CU0(cudaMallocHost((void **)&c->h_pinned, 256));
 	for (int k = 0; k < 4; k++)
 		CU0(cudaEventCreate(&c->pe[k]));
+	CU0(cudaFuncSetAttribute(resolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(resolve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(resolve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 #undef CU0
@@ -538,7 +546,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		cudaStreamSynchronize(c->stream);
 	if (c->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(c->comm);
-	void *frees[] = {c->g, c->rec_fc, c->rec_code, c->rec_cend, c->xev, c->xcnt, c->hj_lo, c->hj_b, c->hj_F, c->hj_info, c->sdesc, c->ev_count, c->ev, c->evc, c->ev_q, c->ev_d, c->ev_now, c->iv_lo,
+	void *frees[] = {c->g, c->rec_fc, c->rec_code, c->rec_cend, c->xev, c->xcnt, c->hj_lo, c->hj_b, c->hj_F, c->hj_info, c->tile_now0, c->sdesc, c->ev_count, c->ev, c->evc, c->ev_q, c->ev_d, c->ev_now, c->iv_lo,
 	    c->iv_hi, c->iv_cum, c->ticket, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight,
 	    c->d_ints, c->d_dbl};
 	for (void *p : frees)
