@@ -7,9 +7,9 @@
 
 namespace cb {
 
-constexpr int TPB = 256;        // threads per CTA in the streaming kernels
+constexpr int TPB = 512;        // threads per CTA in the streaming kernels
 constexpr int IPT = 8;          // consecutive claims per thread
-constexpr int TILE = TPB * IPT; // 2048 claims per tile
+constexpr int TILE = TPB * IPT; // 4096 claims per tile
 constexpr int WARPS = TPB / 32;
 constexpr int EVK = 8;          // class-change events a tile can hold before "overflow"
 constexpr double CODEL_INTERVAL = 100.0; // lib/codel.js:16

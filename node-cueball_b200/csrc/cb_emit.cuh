@@ -40,6 +40,7 @@ struct EmitParams {
 	int32_t *backend;
 	const int32_t *slot_backend; // device table, nslots entries (padded to 16 B)
 	int nslots;
+	unsigned long long slot_magic; // floor((2^64-1) / nslots): division-free modulo
 	int table_smem_bytes;        // 0 = read the table through L1/L2 instead
 	SumDesc *sdesc;
 	unsigned long long epoch;
@@ -49,6 +50,14 @@ struct EmitParams {
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) {
 	return (unsigned int)__cvta_generic_to_shared(p);
+}
+// x mod S without a 64-bit division: q = mulhi(x, floor((2^64-1)/S)) is floor(x/S) or one less
+__device__ __forceinline__ unsigned int fastmod(unsigned long long x, unsigned int S, unsigned long long magic) {
+	const unsigned long long q = __umul64hi(x, magic);
+	unsigned long long r = x - q * (unsigned long long)S;
+	while (r >= S)
+		r -= S;
+	return (unsigned int)r;
 }
 
 // drop bits of the 4 claims [i0, i0+4) and the number of (CoDel-level) drops before i0
@@ -82,7 +91,7 @@ __device__ __forceinline__ unsigned int drops_general(const unsigned long long *
 }
 
 template <bool FLAGS>
-__global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
+__global__ void __launch_bounds__(TPB, 3) emit_kernel(const EmitParams p) {
 	extern __shared__ __align__(16) unsigned char s_dyn[]; // backend table stage
 	__shared__ __align__(8) unsigned long long s_mbar;
 	__shared__ unsigned int s_wsum[2][WARPS];
@@ -136,12 +145,19 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 		if (te > p.n)
 			te = p.n;
 		unsigned int lo = 0, hi = m;
-		while (lo < hi) { // first interval with hi >= ts
-			const unsigned int mid = (lo + hi) >> 1;
-			if (ivhi[mid] >= ts)
-				hi = mid;
-			else
-				lo = mid + 1;
+		if (iv_smem) {
+			// intervals are sorted: count those that end before the tile (<= 64: two per lane)
+			const unsigned int b0 = __ballot_sync(0xffffffffu, (unsigned int)lane < m && s_ivhi[lane] < ts);
+			const unsigned int b1 = __ballot_sync(0xffffffffu, (unsigned int)lane + 32u < m && s_ivhi[lane + 32] < ts);
+			lo = __popc(b0) + __popc(b1);
+		} else {
+			while (lo < hi) { // first interval with hi >= ts
+				const unsigned int mid = (lo + hi) >> 1;
+				if (ivhi[mid] >= ts)
+					hi = mid;
+				else
+					lo = mid + 1;
+			}
 		}
 		jtile = lo;
 		if (lo < m) {
@@ -158,7 +174,7 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 			}
 		}
 		if (S > 0 && kase == 0)
-			basemod = (unsigned int)((g->cursor0 + (ts - dtile)) % (unsigned long long)S);
+			basemod = fastmod(g->cursor0 + (ts - dtile), S, p.slot_magic);
 	}
 
 	unsigned int dropbits[EG], waitbits[EG], admitbits[EG], validbits[EG];
@@ -303,21 +319,42 @@ __global__ void __launch_bounds__(TPB, 6) emit_kernel(const EmitParams p) {
 				if (scur >= S)
 					scur -= S;
 			} else {
-				scur = (unsigned int)((g->cursor0 + rank0[gI]) % (unsigned long long)S);
+				scur = fastmod(g->cursor0 + rank0[gI], S, p.slot_magic);
 			}
 		}
 		int32_t sl[EGW];
 		unsigned int d4 = 0;
+		if (!FLAGS && kase == 1) { // inside one dropping episode: every claim of the tile times out
+			d4 = 0x01010101u;
 #pragma unroll
-		for (int k = 0; k < EGW; k++) {
-			const bool adm = (admitbits[gI] >> k) & 1u;
-			const unsigned int dk = ((waitbits[gI] >> k) & 1u) ? ((dropbits[gI] >> k) & 1u) : 2u;
-			d4 |= dk << (8 * k);
-			sl[k] = (adm && S > 0) ? (int32_t)scur : -1;
-			if (adm) {
-				scur++;
-				if (scur == S)
-					scur = 0;
+			for (int k = 0; k < EGW; k++)
+				sl[k] = -1;
+		} else if (!FLAGS && kase == 0 && nval[gI] == EGW) { // no drop in the tile: four admits in a row
+			d4 = 0;
+#pragma unroll
+			for (int k = 0; k < EGW; k++) {
+				unsigned int v = scur + k;
+				if (v >= S)
+					v -= S;
+				sl[k] = S > 0 ? (int32_t)v : -1;
+			}
+			if (S > 0 && S < (unsigned int)EGW) { // degenerate tiny tables wrap more than once
+#pragma unroll
+				for (int k = 0; k < EGW; k++)
+					sl[k] = (int32_t)((scur + k) % S);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < EGW; k++) {
+				const bool adm = (admitbits[gI] >> k) & 1u;
+				const unsigned int dk = ((waitbits[gI] >> k) & 1u) ? ((dropbits[gI] >> k) & 1u) : 2u;
+				d4 |= dk << (8 * k);
+				sl[k] = (adm && S > 0) ? (int32_t)scur : -1;
+				if (adm) {
+					scur++;
+					if (scur == S)
+						scur = 0;
+				}
 			}
 		}
 		const bool vec = (nval[gI] == EGW) && p.vec_ok;

@@ -257,10 +257,15 @@ __device__ void sequential_path(const ResolveParams &p, int lane) {
 
 constexpr int RT = 8;          // tile slots per thread per pass (8192 per pass)
 constexpr int NIDX_MAX = 8192; // coarse clock index entries kept in shared memory (64 KB)
+constexpr int SEV_MAX = 1024;  // events kept in shared memory for the serial chain (32 KB)
 
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p) {
 	extern __shared__ __align__(16) double s_idx[]; // clock (ms) at claim k*G, k < nidx
+	// the event list and its per-event speculation live in shared memory when they fit, so the
+	// serial chain (thread 0) never waits on global memory
+	__shared__ unsigned long long s_evc[SEV_MAX], s_evq[SEV_MAX], s_evd[SEV_MAX];
+	__shared__ double s_evnow[SEV_MAX];
 	__shared__ unsigned int s_warp[32];
 	__shared__ int s_wmax[32];
 	__shared__ unsigned int s_base;
@@ -272,41 +277,43 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	DevState *g = p.g;
 	using raw_t = typename TimeIn<NS>::raw_t;
 
+	// coarse clock index: every `stride`-th tile's first claim (loaded while thread 0 checks
+	// whether the scan kernel asked for the exact sequential path)
+	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
+	const unsigned long long G = stride * TILE;
+	const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
 	if (tid == 0) {
 		s_fallback = (g->nonmono != 0u) || (g->overflow != 0u);
 		s_base = 0;
 		s_prevconst = -1;
 		s_nheavy = 0;
 	}
+	for (unsigned int k = tid; k < nidx; k += RTPB)
+		s_idx[k] = TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(p.tile_now0)[(unsigned long long)k * stride]);
 	__syncthreads();
 	if (s_fallback) {
 		if (warp == 0)
 			sequential_path<NS>(p, lane);
 		return;
 	}
-	// coarse clock index: every `stride`-th tile's first claim
-	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
-	const unsigned long long G = stride * TILE;
-	const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
-	for (unsigned int k = tid; k < nidx; k += RTPB)
-		s_idx[k] = TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(p.tile_now0)[(unsigned long long)k * stride]);
 	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
 
 	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
 	// One pass handles RT consecutive tiles per thread with every load of a stage issued
 	// together, so the pass costs a handful of dependent memory round trips, not RT of them.
-	for (unsigned long long base = 0; base < p.tiles; base += (unsigned long long)RTPB * RT) {
+	// (slot `tiles` is a virtual closing tile at index n: the run still open at the end of the batch)
+	for (unsigned long long base = 0; base < p.tiles + 1; base += (unsigned long long)RTPB * RT) {
 		const unsigned long long t0 = base + (unsigned long long)tid * RT;
 		unsigned int fc[RT];
 		int T0l[RT]; // block-local slot of the opener, -1 = before this thread, resolved below
 		int lastc = -1;
 #pragma unroll
 		for (int k = 0; k < RT; k++)
-			fc[k] = (t0 + k < p.tiles) ? p.rec_fc[t0 + k] : FC_NONE;
+			fc[k] = (t0 + k < p.tiles) ? p.rec_fc[t0 + k] : ((t0 + k == p.tiles) ? 0u : FC_NONE);
 #pragma unroll
 		for (int k = 0; k < RT; k++) {
 			T0l[k] = lastc;
-			if (fc[k] != FC_NONE)
+			if (fc[k] != FC_NONE && t0 + k < p.tiles)
 				lastc = tid * RT + k;
 		}
 		int x = lastc;
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 #pragma unroll
 		for (int k = 0; k < RT; k++) {
 			const unsigned long long lo = (unsigned long long)(T0[k] + 1) * TILE;
-			const unsigned long long close_idx = (t0 + k) * TILE + fc[k];
+			const unsigned long long close_idx = (t0 + k == p.tiles) ? p.n : (t0 + k) * TILE + fc[k];
 			stretch[k] = (fc[k] != FC_NONE) && (lo < close_idx);
 			Fv[k] = 0.0;
 			nb[k] = 0.0;
@@ -362,24 +369,25 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		// stage 3: does the class rise inside the stretch?  close event?
 #pragma unroll
 		for (int k = 0; k < RT; k++) {
-			if (t0 + k >= p.tiles)
+			if (t0 + k > p.tiles)
 				continue;
+			const bool is_tail = (t0 + k == p.tiles);
 			unsigned int bits = 0;
 			if (fc[k] != FC_NONE) {
-				const unsigned long long close_idx = (t0 + k) * TILE + fc[k];
+				const unsigned long long close_idx = is_tail ? p.n : (t0 + k) * TILE + fc[k];
 				int final_c = (int)cend0[k];
 				if (stretch[k]) {
 					const int cb = claim_class(true, nb[k], Fv[k]);
-					if (cb > final_c) { // find where (one warp per such run, below)
+					if (cb > final_c) { // find where (two warps per such run, below)
 						const unsigned int h = atomicAdd(&s_nheavy, 1u);
 						p.hj_lo[h] = (unsigned long long)(T0[k] + 1) * TILE;
 						p.hj_b[h] = close_idx - 1;
 						p.hj_F[h] = Fv[k];
-						p.hj_info[h] = (unsigned int)(t0 + k) | (cend0[k] << 28);
+						p.hj_info[h] = (unsigned int)(t0 + k) | (cend0[k] << 28) | ((unsigned int)cb << 30);
 						final_c = cb;
 					}
 				}
-				if (final_c >= 1) { // the run ends at a CONST claim (class 0)
+				if (final_c >= 1 && !is_tail) { // the run ends at a CONST claim (class 0)
 					p.xev[(t0 + k) * 3 + 2] = (close_idx << 2);
 					bits = 4u;
 				}
@@ -394,80 +402,48 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		}
 		__syncthreads();
 	}
-	// the run still open at the end of the batch: a virtual closing slot `tiles` at index n
-	if (tid == 0) {
-		const long long T0 = s_prevconst;
-		const unsigned long long code0 = (T0 < 0) ? carry_code : p.rec_code[T0];
-		const unsigned int cend0 = (T0 < 0) ? 0u : p.rec_cend[T0];
-		const unsigned long long lo = (unsigned long long)(T0 + 1) * TILE;
-		if (lo < p.n) {
-			double F;
-			if (code0 == CODE_CARRY)
-				F = g->F;
-			else
-				F = __dadd_rn(now_at<NS>(p.now, code0 == CODE_ZERO ? lo : code0 - 2), CODEL_INTERVAL);
-			const int cb = claim_class(true, now_at<NS>(p.now, p.n - 1), F);
-			if (cb > (int)cend0) {
-				const unsigned int h = atomicAdd(&s_nheavy, 1u);
-				p.hj_lo[h] = lo;
-				p.hj_b[h] = p.n - 1;
-				p.hj_F[h] = F;
-				p.hj_info[h] = (unsigned int)p.tiles | (cend0 << 28);
-			}
-		}
-		p.xcnt[p.tiles] = 0;
-	}
-	__syncthreads();
-	// long runs: class crossings by search, one warp per run
+	// long runs: the two possible class crossings are independent searches -> one warp each
 	const unsigned int nheavy = s_nheavy;
-	for (unsigned int h = warp; h < nheavy; h += RTPB / 32) {
-		const unsigned long long lo = p.hj_lo[h], b = p.hj_b[h];
-		const double F = p.hj_F[h];
+	for (unsigned int sub = warp; sub < 2 * nheavy; sub += RTPB / 32) {
+		const unsigned int h = sub >> 1, level = 1 + (sub & 1u);
 		const unsigned int info = p.hj_info[h];
 		const unsigned int slot = info & 0x0fffffffu;
-		const int cend0 = (int)(info >> 28);
-		unsigned int bits = p.xcnt[slot];
-		unsigned long long e0 = ~0ull, e1 = ~0ull;
-		unsigned long long pos = lo;
-		int cur = cend0;
-		if (cur == 0) {
-			Pred pr;
-			pr.x = F;
-			pr.level = 1;
-			pos = warp_search<NS>(p.now, s_idx, G, lo, b + 1, pr, lane);
-			cur = claim_class(true, now_at<NS>(p.now, pos), F); // 1 or 2
-			e0 = (pos << 2) | (unsigned long long)cur;
-		}
-		if (cur == 1) {
-			Pred pr;
-			pr.x = F;
-			pr.level = 2;
-			const unsigned long long p2 = warp_search<NS>(p.now, s_idx, G, pos, b + 1, pr, lane);
-			if (p2 <= b)
-				e1 = (p2 << 2) | 2ull;
-		}
-		if (lane == 0) {
-			if (e0 != ~0ull) {
-				p.xev[slot * 3 + 0] = e0;
-				bits |= 1u;
+		const int cend0 = (int)((info >> 28) & 3u), cb = (int)(info >> 30);
+		if ((level == 1 && cend0 != 0) || (level == 2 && cb != 2))
+			continue; // that crossing does not exist in this stretch
+		const unsigned long long lo = p.hj_lo[h], b = p.hj_b[h];
+		const double F = p.hj_F[h];
+		Pred pr;
+		pr.x = F;
+		pr.level = (int)level;
+		const unsigned long long pos = warp_search<NS>(p.now, s_idx, G, lo, b + 1, pr, lane); // exists: class(b) >= level
+		if (level == 1) {
+			const int c = claim_class(true, now_at<NS>(p.now, pos), F); // 1, or 2 when both crossings coincide
+			if (lane == 0) {
+				p.xev[slot * 3 + 0] = (pos << 2) | (unsigned long long)c;
+				atomicOr(&p.xcnt[slot], 1u);
 			}
-			if (e1 != ~0ull) {
-				p.xev[slot * 3 + 1] = e1;
-				bits |= 2u;
+		} else {
+			// a separate event only if the class was already 1 just before it
+			bool separate = (cend0 == 1);
+			if (cend0 == 0 && pos > lo)
+				separate = claim_class(true, now_at<NS>(p.now, pos - 1), F) >= 1;
+			if (lane == 0 && separate) {
+				p.xev[slot * 3 + 1] = (pos << 2) | 2ull;
+				atomicOr(&p.xcnt[slot], 2u);
 			}
-			p.xcnt[slot] = bits;
 		}
 	}
 	__syncthreads();
 
 	// ---- B. merge run events and local events into one ordered list -----------------------------
-	for (unsigned long long base = 0; base < p.tiles; base += (unsigned long long)RTPB * RT) {
+	for (unsigned long long base = 0; base < p.tiles + 1; base += (unsigned long long)RTPB * RT) {
 		const unsigned long long t0 = base + (unsigned long long)tid * RT;
 		unsigned int xb[RT], lc[RT], cnt = 0;
 #pragma unroll
 		for (int k = 0; k < RT; k++) {
 			const bool in = t0 + k < p.tiles;
-			xb[k] = in ? p.xcnt[t0 + k] : 0u;
+			xb[k] = (t0 + k <= p.tiles) ? p.xcnt[t0 + k] : 0u;
 			lc[k] = in ? p.ev_count[t0 + k] : 0u;
 			cnt += __popc(xb[k]) + lc[k];
 		}
@@ -535,40 +511,35 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			s_base += s_nev;
 		__syncthreads();
 	}
-	if (tid == 0) { // the tail slot's events come last
-		const unsigned int xbt = p.xcnt[p.tiles];
-		unsigned int off = s_base;
-		if ((xbt & 1u) && off < p.ev_cap)
-			p.evc[off++] = p.xev[p.tiles * 3 + 0];
-		if ((xbt & 2u) && off < p.ev_cap)
-			p.evc[off++] = p.xev[p.tiles * 3 + 1];
-		s_base = off;
-	}
-	__syncthreads();
 	const unsigned int nev = s_base;
 
 	// ---- 2. per event (one warp each): run end q, now at the event, speculated drop start
+	const bool ev_smem = nev <= SEV_MAX;
+	unsigned long long *evc = ev_smem ? s_evc : p.evc;
+	unsigned long long *ev_q = ev_smem ? s_evq : p.ev_q;
+	unsigned long long *ev_d = ev_smem ? s_evd : p.ev_d;
+	double *ev_now = ev_smem ? s_evnow : p.ev_now;
+	if (ev_smem) {
+		for (unsigned int k = tid; k < nev; k += RTPB)
+			s_evc[k] = p.evc[k];
+		__syncthreads();
+	}
 	const double D_in = g->D;
 	const int B_in = g->B;
 	for (unsigned int k = warp; k < nev; k += RTPB / 32) {
-		unsigned long long w = p.evc[k];
-		int c = (int)(w & 3ull);
-		unsigned long long idx = w >> 2;
+		const unsigned long long w = evc[k];
+		const unsigned long long w1 = (k + 1 < nev) ? evc[k + 1] : 3ull, w2 = (k + 2 < nev) ? evc[k + 2] : 3ull;
+		const int c = (int)(w & 3ull);
+		const unsigned long long idx = w >> 2;
 		if (c == 0)
 			continue;
 		// the run ends right before the next class-0 event (at most two events ahead)
 		unsigned long long q = p.n - 1;
-		if (k + 1 < nev) {
-			unsigned long long w1 = p.evc[k + 1];
-			if ((w1 & 3ull) == 0)
-				q = (w1 >> 2) - 1;
-			else if (k + 2 < nev) {
-				unsigned long long w2 = p.evc[k + 2];
-				if ((w2 & 3ull) == 0)
-					q = (w2 >> 2) - 1;
-			}
-		}
-		double nowk = now_at<NS>(p.now, idx);
+		if ((w1 & 3ull) == 0)
+			q = (w1 >> 2) - 1;
+		else if ((w1 & 3ull) != 3ull && (w2 & 3ull) == 0)
+			q = (w2 >> 2) - 1;
+		const double nowk = now_at<NS>(p.now, idx);
 		unsigned long long d;
 		Pred pr;
 		pr.level = 0;
@@ -580,9 +551,9 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			d = warp_search<NS>(p.now, s_idx, G, idx + 1, q + 1, pr, lane);
 		}
 		if (lane == 0) {
-			p.ev_now[k] = nowk;
-			p.ev_q[k] = q;
-			p.ev_d[k] = d;
+			ev_now[k] = nowk;
+			ev_q[k] = q;
+			ev_d[k] = d;
 		}
 	}
 	__syncthreads();
@@ -594,11 +565,11 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		int B = g->B;
 		unsigned long long drops = 0;
 		unsigned int niv = 0;
-		if (nev == 0 || (p.evc[0] >> 2) > 0)
+		if (nev == 0 || (evc[0] >> 2) > 0)
 			B = 0; // the batch starts with class-0 claims
 		unsigned int k = 0;
 		while (k < nev) {
-			const unsigned long long w = p.evc[k];
+			const unsigned long long w = evc[k];
 			const int c = (int)(w & 3ull);
 			if (c == 0) {
 				B = 0;
@@ -606,10 +577,10 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 				continue;
 			}
 			const unsigned long long pidx = w >> 2;
-			const bool has2 = (c == 1) && (k + 1 < nev) && ((p.evc[k + 1] & 3ull) == 2);
-			const unsigned long long q = p.ev_q[k];
+			const bool has2 = (c == 1) && (k + 1 < nev) && ((evc[k + 1] & 3ull) == 2);
+			const unsigned long long q = ev_q[k];
 			if (B) { // lib/codel.js:62-68, episode carried in from the previous batch
-				const unsigned long long d = p.ev_d[k];
+				const unsigned long long d = ev_d[k];
 				if (d <= q) {
 					p.iv_lo[niv] = d;
 					p.iv_hi[niv] = q;
@@ -620,15 +591,15 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 				}
 			} else { // lib/codel.js:70-83
 				long long e = -1;
-				double now_e = p.ev_now[k];
-				unsigned long long dspec = p.ev_d[k];
+				double now_e = ev_now[k];
+				unsigned long long dspec = ev_d[k];
 				bool cond1 = __dsub_rn(now_e, D) < CODEL_INTERVAL;
 				if (c == 2 || cond1) {
 					e = (long long)pidx;
 				} else if (has2) {
-					e = (long long)(p.evc[k + 1] >> 2);
-					now_e = p.ev_now[k + 1];
-					dspec = p.ev_d[k + 1];
+					e = (long long)(evc[k + 1] >> 2);
+					now_e = ev_now[k + 1];
+					dspec = ev_d[k + 1];
 					cond1 = __dsub_rn(now_e, D) < CODEL_INTERVAL;
 				}
 				if (e >= 0) {

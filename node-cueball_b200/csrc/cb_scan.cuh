@@ -92,12 +92,14 @@ template <> struct Raw<true> {
 	using t = long long;
 	// sojourn vs target in the integer domain; returns 0 below, 1 above, 2 = too close
 	static __device__ __forceinline__ int quick(long long st, long long nw, long long tgt) {
-		const long long d = nw - st;
-		const long long m = (nw >> 50) + 2; // > 2.5 ulp(now_ms) expressed in ns
-		if (d >= tgt + m)
-			return 1;
-		if (d < tgt - m)
-			return 0;
+		// e = sojourn - target in ns; the double-millisecond comparison of lib/codel.js:35-37 can
+		// only disagree with sign(e) when |e| < m, m = 2 + now>>50 ns (> 2.5 ulp(now_ms))
+		const unsigned int mh = (unsigned int)(nw >> 50);
+		const long long s = nw - st - (tgt - 2) + (long long)mh; // e + m
+		if (s < 0)
+			return 0; // e < -m: certainly below target
+		if ((unsigned long long)s >= 2ull * (mh + 2u))
+			return 1; // e >= m: certainly at/above target
 		return 2;
 	}
 	static __device__ __forceinline__ bool less(long long a, long long b) { return a < b; }
@@ -130,7 +132,7 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 }
 
 template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
 	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
@@ -315,29 +317,42 @@ __global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 	}
 	__syncthreads();
 
-	// ---- CTA composition: exclusive over warps, tile aggregate --------------------------------
-	IAgg wex, tile_agg;
+	// ---- CTA composition: what precedes this warp inside the tile (exclusive), index form -------
+	IAgg wex;
 	wex.isconst = false;
 	wex.code = CODE_ZERO;
-	tile_agg = wex;
-#pragma unroll
-	for (int w = 0; w < WARPS; w++) {
-		IAgg a;
-		const unsigned long long x = s_wagg[w];
-		a.isconst = (x >> 63) != 0;
-		a.code = x & DESC_CODE_MASK;
-		if (w == warp)
-			wex = tile_agg;
-		tile_agg = icompose(tile_agg, a);
+	{
+		int w = warp - 1;
+		for (; w >= 0; w--) { // nearest earlier warp with a CONST claim (usually the previous one)
+			const unsigned long long x = s_wagg[w];
+			if (x >> 63) {
+				wex.isconst = true;
+				wex.code = x & DESC_CODE_MASK;
+				if (wex.code == CODE_ZERO && w + 1 < warp)
+					wex.code = s_wagg[w + 1] & DESC_CODE_MASK; // the PASS warp after it sets F
+				break;
+			}
+		}
+		if (w < 0 && warp > 0)
+			wex.code = s_wagg[0] & DESC_CODE_MASK; // all earlier warps are PASS: the first one's claim
 	}
 
 	// ---- the tile's record (thread 0): where the inherited run closes, what the tile leaves open
 	if (tid == 0) {
+		IAgg tile_agg;
+		tile_agg.isconst = false;
+		tile_agg.code = CODE_ZERO;
 		unsigned int fc = FC_NONE;
 #pragma unroll
-		for (int w = WARPS - 1; w >= 0; w--)
-			if (s_wfc[w] != FC_NONE)
+		for (int w = 0; w < WARPS; w++) {
+			IAgg a;
+			const unsigned long long x = s_wagg[w];
+			a.isconst = (x >> 63) != 0;
+			a.code = x & DESC_CODE_MASK;
+			tile_agg = icompose(tile_agg, a);
+			if (fc == FC_NONE && s_wfc[w] != FC_NONE)
 				fc = w * CHUNK + s_wfc[w];
+		}
 		p.rec_fc[t] = fc;
 		p.rec_code[t] = tile_agg.code;
 		reinterpret_cast<raw_t *>(p.tile_now0)[t] = rn[0][0]; // thread 0 owns the tile's first claim

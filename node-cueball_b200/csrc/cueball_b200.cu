@@ -242,6 +242,7 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	ep.backend = d_backend;
 	ep.slot_backend = c->d_slot_backend;
 	ep.nslots = c->nslots;
+	ep.slot_magic = c->nslots > 0 ? (~0ull) / (unsigned long long)c->nslots : 0ull;
 	size_t tbytes = ((size_t)c->nslots * 4 + 15) & ~(size_t)15;
 	ep.table_smem_bytes = (d_backend && c->nslots > 0 && tbytes <= 96 * 1024) ? (int)tbytes : 0;
 	ep.sdesc = c->sdesc;
