@@ -219,6 +219,9 @@ int cb_allreduce_counts(cb_ctx *ctx); /* async on the context's stream */
 int cb_profile_enable(cb_ctx *ctx, int on);
 int cb_profile_get(cb_ctx *ctx, double ms_out[CB_K_COUNT], uint64_t launches_out[CB_K_COUNT]);
 uint64_t cb_launch_count(const cb_ctx *ctx); /* kernels launched so far by this context */
+/* %globaltimer stamps (ns) the resolve kernel of the last batch took at its phase boundaries:
+ * [6] entry, [0] pairing, [1] run searches, [2] merge, [3] speculation, [4] serial chain, [5] done */
+int cb_debug_timestamps(cb_ctx *ctx, uint64_t out[16]);
 
 #ifdef __cplusplus
 }

@@ -200,5 +200,10 @@ class Context(object):
         self._ck(self._L.cb_profile_get(self._h, ms, cnt))
         return list(ms), list(cnt)
 
+    def debug_timestamps(self):
+        out = (C.c_uint64 * 16)()
+        self._ck(self._L.cb_debug_timestamps(self._h, out))
+        return list(out)
+
     def launch_count(self):
         return int(self._L.cb_launch_count(self._h))

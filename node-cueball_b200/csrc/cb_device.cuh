@@ -43,6 +43,7 @@ struct DevState {
 	unsigned int n_events;
 	unsigned int n_intervals;
 	unsigned int pad;
+	unsigned long long dbg[16]; // resolve-kernel phase timestamps (globaltimer ns), measurement only
 };
 
 // Tile descriptor of the decoupled look-back over the first_above_time recurrence.
@@ -64,6 +65,11 @@ struct alignas(32) SumDesc {
 	unsigned long long pad;
 };
 
+__device__ __forceinline__ unsigned long long gtimer() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
 __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
 	unsigned long long v;
 	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -8,26 +8,25 @@
 // With a flags array (cancelled handles, lib/pool.js:738-740) the admit rank is a prefix sum
 // of (waiting && !drop): block scan + decoupled look-back over per-tile admit counts.
 //
-// A tile (2048 claims) is classified once against the interval list: no drop inside (the
-// common case), entirely dropped (inside one episode), or mixed (an episode boundary crosses
-// it; only these tiles walk the list per claim).  Each thread writes two groups of 4
-// consecutive claims, so every store instruction of a warp covers one contiguous 128 B
-// (decisions) or 512 B (slots / backends) span.
-//
-// The slot -> backend table (built from the preference list and planRebalance) is staged in
-// shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA when `backend` is
-// requested; it is at most nslots*4 bytes.
+// Persistent CTAs stride over the tiles (4096 claims), so the per-CTA set-up -- the interval
+// list staged in shared memory, the TMA bulk copy of the slot->backend table, the control
+// block reads -- is paid once per CTA, not once per tile.  A tile is classified against the
+// interval list with two ballots: no drop inside (the common case), entirely dropped (inside
+// one episode), or mixed (an episode boundary crosses it; only these tiles walk the list per
+// claim).  Every thread writes four groups of 4 consecutive claims, so each store instruction
+// of a warp covers one contiguous 128 B (decisions) or 512 B (slots / backends) span.
 #pragma once
 #include "cb_device.cuh"
 
 namespace cb {
 
-constexpr int EG = 2;              // groups per thread
-constexpr int EGW = 4;             // consecutive claims per group
-constexpr int IVS_MAX = 64;        // interval lists up to this length are staged in shared memory
-constexpr int EMIT_TABLE_OFF = 0;  // backend table offset inside the dynamic shared memory
-constexpr int EHALF = TPB * EGW;   // 1024: group g of thread t starts at ts + g*EHALF + t*EGW
-static_assert(EG * EHALF == TILE, "emit geometry");
+constexpr int ETPB = 256;               // threads per emit CTA
+constexpr int EGW = 4;                  // consecutive claims per group
+constexpr int EG = TILE / (ETPB * EGW); // groups per thread per tile (4)
+constexpr int ESTR = ETPB * EGW;        // 1024: group g of thread t starts at ts + g*ESTR + t*EGW
+constexpr int EWARPS = ETPB / 32;
+constexpr int IVS_MAX = 64;             // interval lists up to this length are staged in shared memory
+static_assert(EG * ESTR == TILE, "emit geometry");
 
 struct EmitParams {
 	const uint8_t *flags;
@@ -41,11 +40,11 @@ struct EmitParams {
 	const int32_t *slot_backend; // device table, nslots entries (padded to 16 B)
 	int nslots;
 	unsigned long long slot_magic; // floor((2^64-1) / nslots): division-free modulo
-	int table_smem_bytes;        // 0 = read the table through L1/L2 instead
+	int table_smem_bytes;          // 0 = read the table through L1/L2 instead
 	SumDesc *sdesc;
 	unsigned long long epoch;
-	unsigned int *ticket;        // CTA completion counter (flags variant finalisation)
-	int vec_ok;                  // outputs suitably aligned for vector stores
+	unsigned int *ticket;          // CTA completion counter (flags variant finalisation)
+	int vec_ok;                    // outputs suitably aligned for vector stores
 };
 
 __device__ __forceinline__ unsigned int smem_u32(const void *p) {
@@ -58,6 +57,17 @@ __device__ __forceinline__ unsigned int fastmod(unsigned long long x, unsigned i
 	while (r >= S)
 		r -= S;
 	return (unsigned int)r;
+}
+__device__ __forceinline__ void wait_table(unsigned long long *mbar) {
+	unsigned int done = 0;
+	while (!done) {
+		asm volatile("{\n\t.reg .pred q;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
+		             "selp.u32 %0, 1, 0, q;\n\t}"
+		             : "=r"(done)
+		             : "r"(smem_u32(mbar))
+		             : "memory");
+	}
 }
 
 // drop bits of the 4 claims [i0, i0+4) and the number of (CoDel-level) drops before i0
@@ -91,10 +101,10 @@ __device__ __forceinline__ unsigned int drops_general(const unsigned long long *
 }
 
 template <bool FLAGS>
-__global__ void __launch_bounds__(TPB, 3) emit_kernel(const EmitParams p) {
+__global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	extern __shared__ __align__(16) unsigned char s_dyn[]; // backend table stage
 	__shared__ __align__(8) unsigned long long s_mbar;
-	__shared__ unsigned int s_wsum[2][WARPS];
+	__shared__ unsigned int s_wsum[EG][EWARPS];
 	__shared__ unsigned long long s_tile_excl;
 	__shared__ unsigned long long s_ivlo[IVS_MAX], s_ivhi[IVS_MAX], s_ivcum[IVS_MAX];
 
@@ -102,32 +112,28 @@ __global__ void __launch_bounds__(TPB, 3) emit_kernel(const EmitParams p) {
 	DevState *g = p.g;
 	if (g->path == 1) // the sequential path already wrote every output
 		return;
-	const unsigned long long t = blockIdx.x;
-	const unsigned long long ts = t * (unsigned long long)TILE;
 	const bool want_backend = (p.backend != nullptr) && (p.nslots > 0);
 	const bool stage_table = want_backend && (p.table_smem_bytes > 0);
 	const unsigned int m = g->n_intervals;
 	const unsigned long long total_drops = g->gcounts[3];
+	const unsigned long long cursor0 = g->cursor0;
 	const unsigned int S = (unsigned int)p.nslots;
 
-	// ---- kick off the TMA bulk copy of the slot->backend table ------------------------------
-	if (stage_table && tid == 0) {
+	// ---- per-CTA set-up --------------------------------------------------------------------
+	if (stage_table && tid == 0) { // TMA bulk copy of the slot->backend table
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar)));
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_mbar)),
 		    "r"((unsigned int)p.table_smem_bytes)
 		    : "memory");
-		asm volatile(
-		    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-		        smem_u32(s_dyn + EMIT_TABLE_OFF)),
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+		                 smem_u32(s_dyn)),
 		    "l"(p.slot_backend), "r"((unsigned int)p.table_smem_bytes), "r"(smem_u32(&s_mbar))
 		    : "memory");
 	}
-	// ---- the interval list: short lists are staged in shared memory so that no thread waits on
-	// another's dependent global loads; every thread then classifies the tile itself
-	const bool iv_smem = m <= IVS_MAX;
+	const bool iv_smem = m <= IVS_MAX; // short interval lists live in shared memory
 	if (iv_smem) {
-		for (unsigned int k = tid; k < m; k += TPB) {
+		for (unsigned int k = tid; k < m; k += ETPB) {
 			s_ivlo[k] = p.iv_lo[k];
 			s_ivhi[k] = p.iv_hi[k];
 			s_ivcum[k] = p.iv_cum[k];
@@ -137,213 +143,249 @@ __global__ void __launch_bounds__(TPB, 3) emit_kernel(const EmitParams p) {
 	const unsigned long long *ivlo = iv_smem ? s_ivlo : p.iv_lo;
 	const unsigned long long *ivhi = iv_smem ? s_ivhi : p.iv_hi;
 	const unsigned long long *ivcum = iv_smem ? s_ivcum : p.iv_cum;
-	unsigned int kase = 0, jtile = 0, basemod = 0;
-	unsigned long long dtile = total_drops;
-	{
-		// classify the tile against the interval list (warp-uniform, broadcast reads)
+	const int32_t *tb = reinterpret_cast<const int32_t *>(s_dyn);
+	bool table_ready = false;
+
+	for (unsigned long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+		const unsigned long long ts = t * (unsigned long long)TILE;
 		unsigned long long te = ts + TILE;
 		if (te > p.n)
 			te = p.n;
-		unsigned int lo = 0, hi = m;
-		if (iv_smem) {
-			// intervals are sorted: count those that end before the tile (<= 64: two per lane)
-			const unsigned int b0 = __ballot_sync(0xffffffffu, (unsigned int)lane < m && s_ivhi[lane] < ts);
-			const unsigned int b1 = __ballot_sync(0xffffffffu, (unsigned int)lane + 32u < m && s_ivhi[lane + 32] < ts);
-			lo = __popc(b0) + __popc(b1);
-		} else {
-			while (lo < hi) { // first interval with hi >= ts
-				const unsigned int mid = (lo + hi) >> 1;
-				if (ivhi[mid] >= ts)
-					hi = mid;
-				else
-					lo = mid + 1;
-			}
-		}
-		jtile = lo;
-		if (lo < m) {
-			const unsigned long long ilo = ivlo[lo], ihi = ivhi[lo], cum = ivcum[lo];
-			if (ilo >= te) {
-				kase = 0;
-				dtile = cum;
-			} else if (ilo <= ts && ihi >= te - 1) {
-				kase = 1;
-				dtile = cum + (ts - ilo);
-			} else {
-				kase = 2;
-				dtile = 0;
-			}
-		}
-		if (S > 0 && kase == 0)
-			basemod = fastmod(g->cursor0 + (ts - dtile), S, p.slot_magic);
-	}
+		const bool full_tile = (te - ts) == (unsigned long long)TILE;
 
-	unsigned int dropbits[EG], waitbits[EG], admitbits[EG], validbits[EG];
-	unsigned long long rank0[EG]; // admits before the group's first claim (whole batch)
-	unsigned long long gi0[EG];
-	int nval[EG];
-#pragma unroll
-	for (int gI = 0; gI < EG; gI++) {
-		gi0[gI] = ts + (unsigned long long)gI * EHALF + (unsigned long long)tid * EGW;
-		long long rem = (long long)p.n - (long long)gi0[gI];
-		nval[gI] = rem >= EGW ? EGW : (rem > 0 ? (int)rem : 0);
-		validbits[gI] = (1u << nval[gI]) - 1u;
-		unsigned long long db = 0;
-		if (kase == 0) {
-			dropbits[gI] = 0;
-			db = dtile;
-		} else if (kase == 1) {
-			dropbits[gI] = validbits[gI];
-			db = dtile + (gi0[gI] - ts);
-		} else {
-			dropbits[gI] = drops_general(ivlo, ivhi, ivcum, m, jtile, gi0[gI], nval[gI], total_drops, db);
+		// ---- classify the tile against the interval list (warp-uniform) -----------------------
+		unsigned int kase = 0, jtile = 0;
+		unsigned long long dtile = total_drops;
+		{
+			unsigned int lo = 0, hi = m;
+			if (iv_smem) { // sorted: count the intervals that end before the tile (two per lane)
+				const unsigned int b0 = __ballot_sync(0xffffffffu, (unsigned int)lane < m && s_ivhi[lane] < ts);
+				const unsigned int b1 = __ballot_sync(0xffffffffu,
+				    (unsigned int)lane + 32u < m && s_ivhi[(lane + 32) & (IVS_MAX - 1)] < ts);
+				lo = __popc(b0) + __popc(b1);
+			} else {
+				while (lo < hi) { // first interval with hi >= ts
+					const unsigned int mid = (lo + hi) >> 1;
+					if (ivhi[mid] >= ts)
+						hi = mid;
+					else
+						lo = mid + 1;
+				}
+			}
+			jtile = lo;
+			if (lo < m) {
+				const unsigned long long ilo = ivlo[lo], ihi = ivhi[lo], cum = ivcum[lo];
+				if (ilo >= te) {
+					kase = 0;
+					dtile = cum;
+				} else if (ilo <= ts && ihi >= te - 1) {
+					kase = 1;
+					dtile = cum + (ts - ilo);
+				} else {
+					kase = 2;
+					dtile = 0;
+				}
+			}
 		}
-		waitbits[gI] = 0xfu;
+
+		if (!FLAGS && kase != 2 && full_tile && p.vec_ok) {
+			// ---- fast path: the whole tile is admitted, or the whole tile timed out -------------
+			unsigned int base = 0;
+			if (kase == 0 && S > 0)
+				base = fastmod(cursor0 + (ts - dtile), S, p.slot_magic);
+			if (want_backend && stage_table && !table_ready && kase == 0) {
+				wait_table(&s_mbar);
+				table_ready = true;
+			}
+			unsigned int *dec4 = p.decision ? reinterpret_cast<unsigned int *>(p.decision + ts) : nullptr;
+			int4 *sl4 = p.slot ? reinterpret_cast<int4 *>(p.slot + ts) : nullptr;
+			int4 *be4 = p.backend ? reinterpret_cast<int4 *>(p.backend + ts) : nullptr;
+#pragma unroll
+			for (int gI = 0; gI < EG; gI++) {
+				const unsigned int q4 = gI * ETPB + tid; // index of the group of 4 inside the tile
+				int4 sv = make_int4(-1, -1, -1, -1), bv = make_int4(-1, -1, -1, -1);
+				if (kase == 0 && S > 0) {
+					unsigned int s0 = base + q4 * EGW;
+					if (S >= (unsigned int)TILE + EGW) { // at most one wrap inside the tile
+						if (s0 >= S)
+							s0 -= S;
+					} else {
+						s0 %= S;
+					}
+					unsigned int s1 = s0 + 1, s2 = s0 + 2, s3 = s0 + 3;
+					if (S >= EGW) {
+						s1 = s1 >= S ? s1 - S : s1;
+						s2 = s2 >= S ? s2 - S : s2;
+						s3 = s3 >= S ? s3 - S : s3;
+					} else {
+						s1 %= S;
+						s2 %= S;
+						s3 %= S;
+					}
+					sv = make_int4((int)s0, (int)s1, (int)s2, (int)s3);
+					if (be4) {
+						if (stage_table)
+							bv = make_int4(tb[s0], tb[s1], tb[s2], tb[s3]);
+						else
+							bv = make_int4(__ldg(p.slot_backend + s0), __ldg(p.slot_backend + s1),
+							    __ldg(p.slot_backend + s2), __ldg(p.slot_backend + s3));
+					}
+				}
+				if (dec4)
+					dec4[q4] = kase == 1 ? 0x01010101u : 0u;
+				if (sl4)
+					sl4[q4] = sv;
+				if (be4)
+					be4[q4] = bv;
+			}
+			continue;
+		}
+
+		// ---- general path: partial tiles, episode boundaries, flags -----------------------------
+		unsigned int dropbits[EG], waitbits[EG], admitbits[EG], validbits[EG];
+		unsigned long long rank0[EG]; // admits before the group's first claim (whole batch)
+		unsigned long long gi0[EG];
+		int nval[EG];
+#pragma unroll
+		for (int gI = 0; gI < EG; gI++) {
+			gi0[gI] = ts + (unsigned long long)gI * ESTR + (unsigned long long)tid * EGW;
+			long long rem = (long long)p.n - (long long)gi0[gI];
+			nval[gI] = rem >= EGW ? EGW : (rem > 0 ? (int)rem : 0);
+			validbits[gI] = (1u << nval[gI]) - 1u;
+			unsigned long long db = 0;
+			if (kase == 0) {
+				dropbits[gI] = 0;
+				db = dtile;
+			} else if (kase == 1) {
+				dropbits[gI] = validbits[gI];
+				db = dtile + (gi0[gI] - ts);
+			} else {
+				dropbits[gI] = drops_general(ivlo, ivhi, ivcum, m, jtile, gi0[gI], nval[gI], total_drops, db);
+			}
+			waitbits[gI] = 0xfu;
+			if (FLAGS) {
+				waitbits[gI] = 0;
+				if (nval[gI] == EGW && ((reinterpret_cast<uintptr_t>(p.flags) & 3) == 0)) {
+					const unsigned int f4 = *reinterpret_cast<const unsigned int *>(p.flags + gi0[gI]);
+#pragma unroll
+					for (int k = 0; k < EGW; k++)
+						waitbits[gI] |= ((f4 >> (8 * k)) & 1u) << k;
+				} else {
+					for (int k = 0; k < nval[gI]; k++)
+						waitbits[gI] |= (unsigned int)(p.flags[gi0[gI] + k] & 1u) << k;
+				}
+			}
+			admitbits[gI] = waitbits[gI] & ~dropbits[gI] & validbits[gI];
+			rank0[gI] = gi0[gI] - db; // closed form (no flags)
+		}
+
 		if (FLAGS) {
-			waitbits[gI] = 0;
-			if (nval[gI] == EGW && ((reinterpret_cast<uintptr_t>(p.flags) & 3) == 0)) {
-				const unsigned int f4 = *reinterpret_cast<const unsigned int *>(p.flags + gi0[gI]);
+			// admit rank = prefix sum of (waiting && !drop): group 0 of every thread, then group 1, ...
+			unsigned int a[EG], x[EG];
 #pragma unroll
-				for (int k = 0; k < EGW; k++)
-					waitbits[gI] |= ((f4 >> (8 * k)) & 1u) << k;
-			} else {
-				for (int k = 0; k < nval[gI]; k++)
-					waitbits[gI] |= (unsigned int)(p.flags[gi0[gI] + k] & 1u) << k;
+			for (int gI = 0; gI < EG; gI++) {
+				a[gI] = __popc(admitbits[gI]);
+				x[gI] = a[gI];
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					unsigned int y = __shfl_up_sync(0xffffffffu, x[gI], o);
+					if (lane >= o)
+						x[gI] += y;
+				}
+				if (lane == 31)
+					s_wsum[gI][warp] = x[gI];
 			}
-		}
-		admitbits[gI] = waitbits[gI] & ~dropbits[gI] & validbits[gI];
-		rank0[gI] = gi0[gI] - db; // closed form (no flags)
-	}
-
-	if (FLAGS) {
-		// admit rank = prefix sum of (waiting && !drop): group 0 of every thread, then group 1
-		unsigned int a[EG], x[EG];
+			__syncthreads();
+			unsigned int wex[EG], gbase[EG], total = 0;
 #pragma unroll
-		for (int gI = 0; gI < EG; gI++) {
-			a[gI] = __popc(admitbits[gI]);
-			x[gI] = a[gI];
+			for (int gI = 0; gI < EG; gI++) {
+				unsigned int tot = 0;
+				wex[gI] = 0;
 #pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				unsigned int y = __shfl_up_sync(0xffffffffu, x[gI], o);
-				if (lane >= o)
-					x[gI] += y;
+				for (int w = 0; w < EWARPS; w++) {
+					if (w == warp)
+						wex[gI] = tot;
+					tot += s_wsum[gI][w];
+				}
+				gbase[gI] = total;
+				total += tot;
 			}
-			if (lane == 31)
-				s_wsum[gI][warp] = x[gI];
-		}
-		__syncthreads();
-		unsigned int wex[EG] = {0, 0}, tot[EG] = {0, 0};
+			// per-tile counters of real timeouts / skipped handles
+			unsigned int dwait = 0, skip = 0;
 #pragma unroll
-		for (int gI = 0; gI < EG; gI++) {
-#pragma unroll
-			for (int w = 0; w < WARPS; w++) {
-				if (w == warp)
-					wex[gI] = tot[gI];
-				tot[gI] += s_wsum[gI][w];
+			for (int gI = 0; gI < EG; gI++) {
+				dwait += __popc(waitbits[gI] & dropbits[gI] & validbits[gI]);
+				skip += __popc(~waitbits[gI] & validbits[gI]);
 			}
-		}
-		const unsigned int total = tot[0] + tot[1];
-		// per-tile counters of real timeouts / skipped handles
-		unsigned int dwait = __popc(waitbits[0] & dropbits[0] & validbits[0]) + __popc(waitbits[1] & dropbits[1] & validbits[1]);
-		unsigned int skip = __popc(~waitbits[0] & validbits[0]) + __popc(~waitbits[1] & validbits[1]);
-		dwait = __reduce_add_sync(0xffffffffu, dwait);
-		skip = __reduce_add_sync(0xffffffffu, skip);
-		if (lane == 0) {
-			if (dwait)
-				atomicAdd(&g->drops, (unsigned long long)dwait);
-			if (skip)
-				atomicAdd(&g->skipped, (unsigned long long)skip);
-		}
-		// decoupled look-back over tile admit totals (warp 0)
-		if (warp == 0) {
-			unsigned long long excl = 0;
-			if (t > 0) {
+			dwait = __reduce_add_sync(0xffffffffu, dwait);
+			skip = __reduce_add_sync(0xffffffffu, skip);
+			if (lane == 0) {
+				if (dwait)
+					atomicAdd(&g->drops, (unsigned long long)dwait);
+				if (skip)
+					atomicAdd(&g->skipped, (unsigned long long)skip);
+			}
+			// decoupled look-back over tile admit totals (warp 0)
+			if (warp == 0) {
+				unsigned long long excl = 0;
+				if (t > 0) {
+					if (lane == 0) {
+						p.sdesc[t].agg = total;
+						st_release(&p.sdesc[t].w, (p.epoch << 2) | ST_AGG);
+					}
+					long long base = (long long)t - 1;
+					while (true) {
+						long long k = base - lane;
+						unsigned long long val = 0;
+						bool term = false;
+						if (k >= 0) {
+							unsigned long long w;
+							do {
+								w = ld_acquire(&p.sdesc[k].w);
+							} while ((w >> 2) != p.epoch);
+							term = (w & 3ull) == ST_PREFIX;
+							val = term ? ld_relaxed_u64(&p.sdesc[k].incl) : ld_relaxed_u64(&p.sdesc[k].agg);
+						} else if (k == -1) {
+							term = true;
+						}
+						const unsigned int tm = __ballot_sync(0xffffffffu, term);
+						unsigned long long v = val;
+						if (tm) {
+							const int f = __ffs(tm) - 1; // nearest terminator; sum lanes 0..f
+							v = (lane <= f) ? val : 0ull;
+						}
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1)
+							v += __shfl_xor_sync(0xffffffffu, v, o);
+						excl += v;
+						if (tm)
+							break;
+						base -= 32;
+					}
+				}
 				if (lane == 0) {
 					p.sdesc[t].agg = total;
-					st_release(&p.sdesc[t].w, (p.epoch << 2) | ST_AGG);
+					p.sdesc[t].incl = excl + total;
+					st_release(&p.sdesc[t].w, (p.epoch << 2) | ST_PREFIX);
+					s_tile_excl = excl;
 				}
-				long long base = (long long)t - 1;
-				while (true) {
-					long long k = base - lane;
-					unsigned long long val = 0;
-					bool term = false;
-					if (k >= 0) {
-						unsigned long long w;
-						do {
-							w = ld_acquire(&p.sdesc[k].w);
-						} while ((w >> 2) != p.epoch);
-						term = (w & 3ull) == ST_PREFIX;
-						val = term ? ld_relaxed_u64(&p.sdesc[k].incl) : ld_relaxed_u64(&p.sdesc[k].agg);
-					} else if (k == -1) {
-						term = true;
-					}
-					const unsigned int tm = __ballot_sync(0xffffffffu, term);
-					unsigned long long v = val;
-					if (tm) {
-						const int f = __ffs(tm) - 1; // nearest terminator; sum lanes 0..f
-						v = (lane <= f) ? val : 0ull;
-					}
+			}
+			__syncthreads();
 #pragma unroll
-					for (int o = 16; o > 0; o >>= 1)
-						v += __shfl_xor_sync(0xffffffffu, v, o);
-					excl += v;
-					if (tm)
-						break;
-					base -= 32;
-				}
-			}
-			if (lane == 0) {
-				p.sdesc[t].agg = total;
-				p.sdesc[t].incl = excl + total;
-				st_release(&p.sdesc[t].w, (p.epoch << 2) | ST_PREFIX);
-				s_tile_excl = excl;
-			}
+			for (int gI = 0; gI < EG; gI++)
+				rank0[gI] = s_tile_excl + gbase[gI] + wex[gI] + (x[gI] - a[gI]);
 		}
-		__syncthreads();
-		rank0[0] = s_tile_excl + wex[0] + (x[0] - a[0]);
-		rank0[1] = s_tile_excl + tot[0] + wex[1] + (x[1] - a[1]);
-	}
 
-	// ---- slots / backends, vector stores ------------------------------------------------------
-	const int32_t *tb = reinterpret_cast<const int32_t *>(s_dyn);
-	bool table_ready = false;
+		// ---- slots / backends, vector stores ------------------------------------------------------
 #pragma unroll
-	for (int gI = 0; gI < EG; gI++) {
-		if (nval[gI] == 0)
-			continue;
-		unsigned int scur = 0;
-		if (S > 0) {
-			if (!FLAGS && kase == 0) {
-				// tile-uniform base + a small offset: no 64-bit division per thread
-				unsigned int off = (unsigned int)(gi0[gI] - ts);
-				scur = (S >= (unsigned int)TILE) ? basemod + off : (basemod + off) % S;
-				if (scur >= S)
-					scur -= S;
-			} else {
-				scur = fastmod(g->cursor0 + rank0[gI], S, p.slot_magic);
-			}
-		}
-		int32_t sl[EGW];
-		unsigned int d4 = 0;
-		if (!FLAGS && kase == 1) { // inside one dropping episode: every claim of the tile times out
-			d4 = 0x01010101u;
-#pragma unroll
-			for (int k = 0; k < EGW; k++)
-				sl[k] = -1;
-		} else if (!FLAGS && kase == 0 && nval[gI] == EGW) { // no drop in the tile: four admits in a row
-			d4 = 0;
-#pragma unroll
-			for (int k = 0; k < EGW; k++) {
-				unsigned int v = scur + k;
-				if (v >= S)
-					v -= S;
-				sl[k] = S > 0 ? (int32_t)v : -1;
-			}
-			if (S > 0 && S < (unsigned int)EGW) { // degenerate tiny tables wrap more than once
-#pragma unroll
-				for (int k = 0; k < EGW; k++)
-					sl[k] = (int32_t)((scur + k) % S);
-			}
-		} else {
+		for (int gI = 0; gI < EG; gI++) {
+			if (nval[gI] == 0)
+				continue;
+			unsigned int scur = 0;
+			if (S > 0)
+				scur = fastmod(cursor0 + rank0[gI], S, p.slot_magic);
+			int32_t sl[EGW];
+			unsigned int d4 = 0;
 #pragma unroll
 			for (int k = 0; k < EGW; k++) {
 				const bool adm = (admitbits[gI] >> k) & 1u;
@@ -356,51 +398,45 @@ __global__ void __launch_bounds__(TPB, 3) emit_kernel(const EmitParams p) {
 						scur = 0;
 				}
 			}
-		}
-		const bool vec = (nval[gI] == EGW) && p.vec_ok;
-		if (p.decision) {
-			if (vec)
-				*reinterpret_cast<unsigned int *>(p.decision + gi0[gI]) = d4;
-			else
-				for (int k = 0; k < nval[gI]; k++)
-					p.decision[gi0[gI] + k] = (uint8_t)(d4 >> (8 * k));
-		}
-		if (p.slot) {
-			if (vec)
-				*reinterpret_cast<int4 *>(p.slot + gi0[gI]) = make_int4(sl[0], sl[1], sl[2], sl[3]);
-			else
-				for (int k = 0; k < nval[gI]; k++)
-					p.slot[gi0[gI] + k] = sl[k];
-		}
-		if (p.backend) {
-			int32_t be[EGW];
-			if (stage_table) {
-				if (!table_ready) { // wait for the bulk copy (phase 0)
-					unsigned int done = 0;
-					while (!done) {
-						asm volatile("{\n\t.reg .pred q;\n\t"
-						             "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\t"
-						             "selp.u32 %0, 1, 0, q;\n\t}"
-						             : "=r"(done)
-						             : "r"(smem_u32(&s_mbar))
-						             : "memory");
-					}
-					table_ready = true;
-				}
-#pragma unroll
-				for (int k = 0; k < EGW; k++)
-					be[k] = (sl[k] >= 0) ? tb[sl[k]] : -1;
-			} else {
-#pragma unroll
-				for (int k = 0; k < EGW; k++)
-					be[k] = (sl[k] >= 0) ? __ldg(p.slot_backend + sl[k]) : -1;
+			const bool vec = (nval[gI] == EGW) && p.vec_ok;
+			if (p.decision) {
+				if (vec)
+					*reinterpret_cast<unsigned int *>(p.decision + gi0[gI]) = d4;
+				else
+					for (int k = 0; k < nval[gI]; k++)
+						p.decision[gi0[gI] + k] = (uint8_t)(d4 >> (8 * k));
 			}
-			if (vec)
-				*reinterpret_cast<int4 *>(p.backend + gi0[gI]) = make_int4(be[0], be[1], be[2], be[3]);
-			else
-				for (int k = 0; k < nval[gI]; k++)
-					p.backend[gi0[gI] + k] = be[k];
+			if (p.slot) {
+				if (vec)
+					*reinterpret_cast<int4 *>(p.slot + gi0[gI]) = make_int4(sl[0], sl[1], sl[2], sl[3]);
+				else
+					for (int k = 0; k < nval[gI]; k++)
+						p.slot[gi0[gI] + k] = sl[k];
+			}
+			if (p.backend) {
+				int32_t be[EGW];
+				if (stage_table) {
+					if (!table_ready) { // wait for the bulk copy (phase 0)
+						wait_table(&s_mbar);
+						table_ready = true;
+					}
+#pragma unroll
+					for (int k = 0; k < EGW; k++)
+						be[k] = (sl[k] >= 0) ? tb[sl[k]] : -1;
+				} else {
+#pragma unroll
+					for (int k = 0; k < EGW; k++)
+						be[k] = (sl[k] >= 0) ? __ldg(p.slot_backend + sl[k]) : -1;
+				}
+				if (vec)
+					*reinterpret_cast<int4 *>(p.backend + gi0[gI]) = make_int4(be[0], be[1], be[2], be[3]);
+				else
+					for (int k = 0; k < nval[gI]; k++)
+						p.backend[gi0[gI] + k] = be[k];
+			}
 		}
+		if (FLAGS)
+			__syncthreads(); // s_wsum / s_tile_excl are reused by the next tile
 	}
 
 	// ---- flags variant: the last CTA to finish publishes the batch totals -----------------
@@ -409,7 +445,7 @@ __global__ void __launch_bounds__(TPB, 3) emit_kernel(const EmitParams p) {
 		__syncthreads();
 		if (tid == 0) {
 			unsigned int done = atomicAdd(p.ticket, 1u);
-			if (done == (unsigned int)(p.tiles - 1)) {
+			if (done == gridDim.x - 1) {
 				*p.ticket = 0;
 				__threadfence();
 				const unsigned long long admits = ld_relaxed_u64(&p.sdesc[p.tiles - 1].incl);

@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
 	using raw_t = typename TimeIn<NS>::raw_t;
+	if (tid == 0)
+		g->dbg[6] = gtimer();
 
 	// coarse clock index: every `stride`-th tile's first claim (loaded while thread 0 checks
 	// whether the scan kernel asked for the exact sequential path)
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
 
+	if (tid == 0) g->dbg[0] = gtimer();
 	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
 	// One pass handles RT consecutive tiles per thread with every load of a stage issued
 	// together, so the pass costs a handful of dependent memory round trips, not RT of them.
@@ -402,6 +405,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		}
 		__syncthreads();
 	}
+	if (tid == 0) g->dbg[1] = gtimer();
 	// long runs: the two possible class crossings are independent searches -> one warp each
 	const unsigned int nheavy = s_nheavy;
 	for (unsigned int sub = warp; sub < 2 * nheavy; sub += RTPB / 32) {
@@ -436,6 +440,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	__syncthreads();
 
+	if (tid == 0) g->dbg[2] = gtimer();
 	// ---- B. merge run events and local events into one ordered list -----------------------------
 	for (unsigned long long base = 0; base < p.tiles + 1; base += (unsigned long long)RTPB * RT) {
 		const unsigned long long t0 = base + (unsigned long long)tid * RT;
@@ -513,6 +518,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	const unsigned int nev = s_base;
 
+	if (tid == 0) g->dbg[3] = gtimer();
 	// ---- 2. per event (one warp each): run end q, now at the event, speculated drop start
 	const bool ev_smem = nev <= SEV_MAX;
 	unsigned long long *evc = ev_smem ? s_evc : p.evc;
@@ -558,6 +564,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	__syncthreads();
 
+	if (tid == 0) g->dbg[4] = gtimer();
 	// ---- 3. the serial chain over events (thread 0) -----------------------------------
 	if (tid == 0) {
 		double D = g->D;
@@ -652,6 +659,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			}
 			g->last_marker_p1 = 0;
 		}
+		g->dbg[5] = gtimer();
 		g->F = F;
 		g->D = D;
 		g->C = C;

@@ -85,6 +85,7 @@ struct cb_ctx {
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr;
 	double *hj_F = nullptr;
 	unsigned long long *tile_now0 = nullptr;
+	int emit_grid = 148 * 4; // persistent emit CTAs (set from the device's SM count)
 	SumDesc *sdesc = nullptr;
 	unsigned int *ev_count = nullptr;
 	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
@@ -266,10 +267,14 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 		resolve_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[2], s));
+	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
+	// tile's CTA to be resident or earlier in the same CTA's sequence: both hold for a grid that
+	// does not exceed the resident capacity (tiles are visited in increasing order per CTA)
+	const unsigned egrid = (unsigned)(tiles < (size_t)c->emit_grid ? tiles : (size_t)c->emit_grid);
 	if (flags)
-		emit_kernel<true><<<(unsigned)tiles, TPB, ep.table_smem_bytes, s>>>(ep);
+		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	else
-		emit_kernel<false><<<(unsigned)tiles, TPB, ep.table_smem_bytes, s>>>(ep);
+		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	c->launches += 3;
 	CU(c, cudaGetLastError());
 	if (c->prof) {
@@ -501,6 +506,7 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	if (!c)
 		return fail(nullptr, CB_ENOMEM, "out of host memory");
 	c->device = device;
+	c->emit_grid = prop.multiProcessorCount * 4; // 4 x 256-thread CTAs per SM are resident (<= 96 KB smem each only without a staged table: see launch)
 	const char *ck = getenv("CB_CHUNK");
 	if (ck && atoll(ck) >= TILE)
 		c->chunk = ((size_t)atoll(ck) + TILE - 1) / TILE * TILE;
@@ -963,3 +969,14 @@ extern "C" int cb_profile_get(cb_ctx *c, double ms_out[CB_K_COUNT], uint64_t lau
 	return CB_OK;
 }
 extern "C" uint64_t cb_launch_count(const cb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int cb_debug_timestamps(cb_ctx *c, uint64_t out[16]) {
+	if (!c || !out)
+		return CB_EINVAL;
+	DevState h;
+	CU(c, cudaMemcpyAsync(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	for (int k = 0; k < 16; k++)
+		out[k] = h.dbg[k];
+	return CB_OK;
+}
