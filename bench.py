@@ -250,6 +250,7 @@ def run_cuda(args, wl, extra=True):
     # ---- device-resident timing ------------------------------------------------------------
     for b in range(W):
         step_dev(b)
+    ctx.synchronize()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -259,8 +260,10 @@ def run_cuda(args, wl, extra=True):
     e0.record(stream)
     for b in range(W, W + K):
         step_dev(b)
+    ctx.join()  # the timing stream waits for the last batch of the pipeline
     e1.record(stream)
     barrier()
+    ctx.synchronize()
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
@@ -333,6 +336,7 @@ def run_cuda(args, wl, extra=True):
                    "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
                          % (nb, 16.0 * n * nb / 1e6),
                    "state": "ControlledDelay state chained on device across steps",
+                   "pipeline": "3 batches in flight: scan(k+1) | resolve(k) | emit(k-1) on three streams",
                    "admit_fraction": st.total_admits / max(st.total_admits + st.total_drops, 1)},
         "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }

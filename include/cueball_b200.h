@@ -110,9 +110,15 @@ int cb_create(cb_ctx **out, int device);
 void cb_destroy(cb_ctx *ctx);
 const char *cb_last_error(const cb_ctx *ctx); /* ctx may be NULL: last create error */
 int cb_abi_version(void);
-/* run the context's work on a caller-owned CUDA stream (cudaStream_t); NULL = own stream */
+/* Order the context's work after a caller-owned CUDA stream (cudaStream_t); NULL = own stream.
+ * Device-buffer batches are PIPELINED: up to `depth` batches are in flight on internal streams
+ * (scan of batch k+1 overlaps resolve of batch k and emit of batch k-1).  Every batch starts
+ * after the work already queued on the caller's stream; its outputs are complete after
+ * cb_join() (stream-ordered) or cb_synchronize()/cb_batch_stats_get() (host-blocking). */
 int cb_set_stream(cb_ctx *ctx, void *cuda_stream);
-int cb_synchronize(cb_ctx *ctx);
+int cb_set_pipeline_depth(cb_ctx *ctx, int depth); /* 1 = strictly in order on one stream; default 3 */
+int cb_join(cb_ctx *ctx);        /* the caller's stream waits for every batch enqueued so far */
+int cb_synchronize(cb_ctx *ctx); /* the host waits for every batch enqueued so far */
 /* pinned host memory for the *_batch host-buffer calls */
 void *cb_host_alloc(cb_ctx *ctx, size_t bytes);
 void cb_host_free(cb_ctx *ctx, void *p);

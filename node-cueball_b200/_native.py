@@ -18,7 +18,7 @@ K_SCAN, K_RESOLVE, K_EMIT, K_COUNT = 0, 1, 2, 3
 
 # every symbol include/cueball_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
-    "cb_create", "cb_destroy", "cb_last_error", "cb_abi_version", "cb_set_stream", "cb_synchronize",
+    "cb_create", "cb_destroy", "cb_last_error", "cb_abi_version", "cb_set_stream", "cb_set_pipeline_depth", "cb_join", "cb_synchronize",
     "cb_host_alloc", "cb_host_free", "cb_codel_init", "cb_codel_get_state", "cb_codel_set_state",
     "cb_codel_empty", "cb_codel_max_idle", "cb_admit_batch", "cb_admit_batch_ms", "cb_admit_batch_dev",
     "cb_admit_batch_ms_dev", "cb_batch_stats_get", "cb_codel_overloaded", "cb_backends_set",
@@ -78,6 +78,8 @@ def lib():
     L.cb_abi_version.restype = C.c_int
     L.cb_set_stream.argtypes = [vp, vp]
     L.cb_synchronize.argtypes = [vp]
+    L.cb_set_pipeline_depth.argtypes = [vp, C.c_int]
+    L.cb_join.argtypes = [vp]
     L.cb_host_alloc.argtypes = [vp, sz]
     L.cb_host_alloc.restype = vp
     L.cb_host_free.argtypes = [vp, vp]

@@ -131,6 +131,13 @@ class Context(object):
     def synchronize(self):
         self._ck(self._L.cb_synchronize(self._h))
 
+    def join(self):
+        """The caller's stream waits for every batch enqueued so far (stream-ordered)."""
+        self._ck(self._L.cb_join(self._h))
+
+    def set_pipeline_depth(self, depth):
+        self._ck(self._L.cb_set_pipeline_depth(self._h, int(depth)))
+
     # --------------------------------------------------------------- topology
     def backends_set(self, nbackends, insert_u, nslots, table=None, mode=N.BALANCE_UNIFORM):
         u = np.ascontiguousarray(insert_u, dtype=np.float64)

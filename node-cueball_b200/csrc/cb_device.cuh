@@ -18,8 +18,11 @@ constexpr double CODEL_INTERVAL = 100.0; // lib/codel.js:16
 constexpr unsigned F_WAITING = 1u, F_EMPTY_AFTER = 2u;
 
 // ---------------------------------------------------------------------------------------
-// Device-resident control block: one per context, lives in HBM, so consecutive batches
-// chain their ControlledDelay state without a host round trip.
+// Device-resident state.  DevState is the pool's persistent state (one per context): the
+// ControlledDelay fields and the admit cursor; consecutive batches chain through it without a
+// host round trip.  BatchCtl is the per-batch control block: up to CB_LANES batches are in
+// flight at once (scan of batch k+1 overlaps resolve of batch k and emit of batch k-1), each on
+// its own lane with its own BatchCtl and scratch.
 struct DevState {
 	// ControlledDelay, lib/codel.js:24-32 (+ cd_last_empty :92)
 	double target;            // cd_targdelay
@@ -30,31 +33,23 @@ struct DevState {
 	int hasE;                 // cd_last_empty defined?
 	double E;                 // cd_last_empty
 	unsigned long long cursor; // admit cursor (slot = cursor mod nslots)
-	unsigned long long cursor0; // cursor before the batch in flight (read by the emit kernel)
-	// last batch
-	unsigned long long n, drops, admits, skipped;
 	unsigned long long tot_drops, tot_admits;
-	unsigned long long gcounts[4]; // {drops, admits, n, 0}: allreduce buffer (in place)
-	// control (set by the scan kernel, consumed + reset by the resolve kernel)
-	unsigned int nonmono;     // clock went backwards inside the batch
-	unsigned int overflow;    // a tile found more than EVK events
+};
+struct BatchCtl {
+	unsigned long long n, drops, admits, skipped;
+	unsigned long long cursor0;    // admit cursor before this batch (read by the emit kernel)
+	unsigned long long gcounts[4]; // {drops, admits, n, CoDel-level drops}: [0..2] = allreduce buffer
+	// set by the scan kernel, consumed + reset by the resolve kernel
+	unsigned int nonmono;          // clock went backwards inside the batch
+	unsigned int overflow;         // a tile found more than EVK events
 	unsigned long long last_marker_p1; // 1 + index of the last CB_F_EMPTY_AFTER claim
-	int path;                 // CB_PATH_*
+	int path;                      // CB_PATH_*
 	unsigned int n_events;
 	unsigned int n_intervals;
 	unsigned int pad;
-	unsigned long long dbg[16]; // resolve-kernel phase timestamps (globaltimer ns), measurement only
+	unsigned long long dbg[16];    // resolve-kernel phase timestamps (globaltimer ns), measurement only
 };
 
-// Tile descriptor of the decoupled look-back over the first_above_time recurrence.
-// w = (epoch << 3) | (isconst << 2) | status ; status 1 = aggregate (vA), 2 = prefix (vP).
-// vA/vP are written before w is released and never rewritten within an epoch.
-struct alignas(32) TileDesc {
-	unsigned long long w;
-	double vA;
-	double vP;
-	unsigned long long pad;
-};
 constexpr unsigned ST_AGG = 1u, ST_PREFIX = 2u;
 
 // Tile descriptor of the admit-count look-back (emit kernel, flags variant).

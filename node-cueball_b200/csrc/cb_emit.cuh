@@ -33,6 +33,7 @@ struct EmitParams {
 	unsigned long long n;
 	unsigned long long tiles;
 	DevState *g;
+	BatchCtl *bc;
 	const unsigned long long *iv_lo, *iv_hi, *iv_cum;
 	uint8_t *decision;
 	int32_t *slot;
@@ -110,13 +111,14 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
-	if (g->path == 1) // the sequential path already wrote every output
+	BatchCtl *bc = p.bc;
+	if (bc->path == 1) // the sequential path already wrote every output
 		return;
 	const bool want_backend = (p.backend != nullptr) && (p.nslots > 0);
 	const bool stage_table = want_backend && (p.table_smem_bytes > 0);
-	const unsigned int m = g->n_intervals;
-	const unsigned long long total_drops = g->gcounts[3];
-	const unsigned long long cursor0 = g->cursor0;
+	const unsigned int m = bc->n_intervals;
+	const unsigned long long total_drops = bc->gcounts[3];
+	const unsigned long long cursor0 = bc->cursor0;
 	const unsigned int S = (unsigned int)p.nslots;
 
 	// ---- per-CTA set-up --------------------------------------------------------------------
@@ -321,9 +323,9 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 			skip = __reduce_add_sync(0xffffffffu, skip);
 			if (lane == 0) {
 				if (dwait)
-					atomicAdd(&g->drops, (unsigned long long)dwait);
+					atomicAdd(&bc->drops, (unsigned long long)dwait);
 				if (skip)
-					atomicAdd(&g->skipped, (unsigned long long)skip);
+					atomicAdd(&bc->skipped, (unsigned long long)skip);
 			}
 			// decoupled look-back over tile admit totals (warp 0)
 			if (warp == 0) {
@@ -449,13 +451,13 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 				*p.ticket = 0;
 				__threadfence();
 				const unsigned long long admits = ld_relaxed_u64(&p.sdesc[p.tiles - 1].incl);
-				const unsigned long long drops = atomicAdd(&g->drops, 0ull);
-				g->admits = admits;
-				g->cursor = g->cursor0 + admits;
+				const unsigned long long drops = atomicAdd(&bc->drops, 0ull);
+				bc->admits = admits;
+				g->cursor = bc->cursor0 + admits;
 				g->tot_drops += drops;
 				g->tot_admits += admits;
-				g->gcounts[0] = drops;
-				g->gcounts[1] = admits;
+				bc->gcounts[0] = drops;
+				bc->gcounts[1] = admits;
 			}
 		}
 	}

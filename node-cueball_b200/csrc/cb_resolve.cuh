@@ -41,6 +41,7 @@ struct ResolveParams {
 	unsigned long long n;
 	unsigned long long tiles;
 	DevState *g;
+	BatchCtl *bc;
 	const unsigned int *rec_fc;         // per-tile records from the scan kernel
 	const unsigned long long *rec_code;
 	const unsigned int *rec_cend;
@@ -169,6 +170,7 @@ template <bool NS>
 __device__ void sequential_path(const ResolveParams &p, int lane) {
 	using raw_t = typename TimeIn<NS>::raw_t;
 	DevState *g = p.g;
+	BatchCtl *bc = p.bc;
 	CodelRegs s;
 	s.F = g->F;
 	s.D = g->D;
@@ -235,23 +237,24 @@ __device__ void sequential_path(const ResolveParams &p, int lane) {
 		g->B = s.B;
 		g->E = E;
 		g->hasE = hasE;
+		bc->cursor0 = g->cursor;
 		g->cursor = cursor;
-		g->n = p.n;
-		g->drops = drops;
-		g->admits = admits;
-		g->skipped = skipped;
+		bc->n = p.n;
+		bc->drops = drops;
+		bc->admits = admits;
+		bc->skipped = skipped;
 		g->tot_drops += drops;
 		g->tot_admits += admits;
-		g->gcounts[0] = drops;
-		g->gcounts[1] = admits;
-		g->gcounts[2] = p.n;
-		g->gcounts[3] = 0;
-		g->path = 1;
-		g->n_events = 0;
-		g->n_intervals = 0;
-		g->nonmono = 0;
-		g->overflow = 0;
-		g->last_marker_p1 = 0;
+		bc->gcounts[0] = drops;
+		bc->gcounts[1] = admits;
+		bc->gcounts[2] = p.n;
+		bc->gcounts[3] = 0;
+		bc->path = 1;
+		bc->n_events = 0;
+		bc->n_intervals = 0;
+		bc->nonmono = 0;
+		bc->overflow = 0;
+		bc->last_marker_p1 = 0;
 	}
 }
 
@@ -275,9 +278,10 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	__shared__ unsigned int s_nheavy;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
+	BatchCtl *bc = p.bc;
 	using raw_t = typename TimeIn<NS>::raw_t;
 	if (tid == 0)
-		g->dbg[6] = gtimer();
+		bc->dbg[6] = gtimer();
 
 	// coarse clock index: every `stride`-th tile's first claim (loaded while thread 0 checks
 	// whether the scan kernel asked for the exact sequential path)
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	const unsigned long long G = stride * TILE;
 	const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
 	if (tid == 0) {
-		s_fallback = (g->nonmono != 0u) || (g->overflow != 0u);
+		s_fallback = (bc->nonmono != 0u) || (bc->overflow != 0u);
 		s_base = 0;
 		s_prevconst = -1;
 		s_nheavy = 0;
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
 
-	if (tid == 0) g->dbg[0] = gtimer();
+	if (tid == 0) bc->dbg[0] = gtimer();
 	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
 	// One pass handles RT consecutive tiles per thread with every load of a stage issued
 	// together, so the pass costs a handful of dependent memory round trips, not RT of them.
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		}
 		__syncthreads();
 	}
-	if (tid == 0) g->dbg[1] = gtimer();
+	if (tid == 0) bc->dbg[1] = gtimer();
 	// long runs: the two possible class crossings are independent searches -> one warp each
 	const unsigned int nheavy = s_nheavy;
 	for (unsigned int sub = warp; sub < 2 * nheavy; sub += RTPB / 32) {
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	__syncthreads();
 
-	if (tid == 0) g->dbg[2] = gtimer();
+	if (tid == 0) bc->dbg[2] = gtimer();
 	// ---- B. merge run events and local events into one ordered list -----------------------------
 	for (unsigned long long base = 0; base < p.tiles + 1; base += (unsigned long long)RTPB * RT) {
 		const unsigned long long t0 = base + (unsigned long long)tid * RT;
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	const unsigned int nev = s_base;
 
-	if (tid == 0) g->dbg[3] = gtimer();
+	if (tid == 0) bc->dbg[3] = gtimer();
 	// ---- 2. per event (one warp each): run end q, now at the event, speculated drop start
 	const bool ev_smem = nev <= SEV_MAX;
 	unsigned long long *evc = ev_smem ? s_evc : p.evc;
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	}
 	__syncthreads();
 
-	if (tid == 0) g->dbg[4] = gtimer();
+	if (tid == 0) bc->dbg[4] = gtimer();
 	// ---- 3. the serial chain over events (thread 0) -----------------------------------
 	if (tid == 0) {
 		double D = g->D;
@@ -650,41 +654,41 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 				F = 0.0;
 		}
 		if (FLAGS) {
-			const unsigned long long lm = g->last_marker_p1;
+			const unsigned long long lm = bc->last_marker_p1;
 			if (lm) {
 				g->E = now_at<NS>(p.now, lm - 1);
 				g->hasE = 1;
 				if (lm == p.n)
 					F = 0.0; // trailing empty(): lib/codel.js:93
 			}
-			g->last_marker_p1 = 0;
+			bc->last_marker_p1 = 0;
 		}
-		g->dbg[5] = gtimer();
+		bc->dbg[5] = gtimer();
 		g->F = F;
 		g->D = D;
 		g->C = C;
 		g->B = B;
-		g->n = p.n;
-		g->path = 0;
-		g->n_events = nev;
-		g->n_intervals = niv;
-		g->gcounts[2] = p.n;
-		g->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)
-		g->cursor0 = g->cursor;
+		bc->n = p.n;
+		bc->path = 0;
+		bc->n_events = nev;
+		bc->n_intervals = niv;
+		bc->gcounts[2] = p.n;
+		bc->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)
+		bc->cursor0 = g->cursor;
 		if (!FLAGS) {
 			const unsigned long long admits = p.n - drops;
-			g->drops = drops;
-			g->admits = admits;
-			g->skipped = 0;
+			bc->drops = drops;
+			bc->admits = admits;
+			bc->skipped = 0;
 			g->tot_drops += drops;
 			g->tot_admits += admits;
-			g->gcounts[0] = drops;
-			g->gcounts[1] = admits;
+			bc->gcounts[0] = drops;
+			bc->gcounts[1] = admits;
 			g->cursor += admits; // the emit kernel works from cursor0
 		} else {
-			g->drops = 0; // accumulated by the emit kernel (waiting handles only)
-			g->admits = 0;
-			g->skipped = 0;
+			bc->drops = 0; // accumulated by the emit kernel (waiting handles only)
+			bc->admits = 0;
+			bc->skipped = 0;
 		}
 	}
 }

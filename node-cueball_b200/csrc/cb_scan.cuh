@@ -75,7 +75,8 @@ struct ScanParams {
 	const void *now;
 	const uint8_t *flags; // may be null
 	unsigned long long n;
-	DevState *g;
+	BatchCtl *b;   // per-batch control block (nonmono / overflow / last marker)
+	double target; // cd_targdelay (ms)
 	// per-tile record: first CONST position, F after the tile (index-coded), class of its last claim
 	unsigned int *rec_fc;          // [tiles] tile-local position of the first CONST claim, or FC_NONE
 	unsigned long long *rec_code;  // [tiles] valid when rec_fc != FC_NONE
@@ -125,7 +126,7 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 	if (code == CODE_ZERO)
 		return 0.0;
 	if (code == CODE_CARRY)
-		return g->F;
+		return g ? g->F : 0.0;
 	using raw_t = typename TimeIn<NS>::raw_t;
 	const raw_t v = reinterpret_cast<const raw_t *>(now)[code - 2];
 	return __dadd_rn(TimeIn<NS>::to_ms(v), CODEL_INTERVAL);
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	const unsigned long long cs = ts + (unsigned long long)warp * CHUNK; // chunk start
 	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
 	const raw_t *gnow = reinterpret_cast<const raw_t *>(p.now);
-	const double target = p.g->target;
+	const double target = p.target;
 	const long long tgt_ns = p.target_ns;
 	const unsigned int lt_mask = (1u << lane) - 1u;
 	if (tid == 0)
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
 	double F = 0.0; // F in force before the chunk's first claim (before its marker-before reset)
 	if (known && (first_is_pass || prev_ok_possible))
-		F = materialise<NS>(wex.code, p.now, p.g);
+		F = materialise<NS>(wex.code, p.now, nullptr); // never CODE_CARRY inside a tile
 	int c_last = 0; // class of the claim before the current row
 	if (prev_ok_possible && F != 0.0)
 		c_last = claim_class(true, TimeIn<NS>::to_ms(prev_now), F);
@@ -474,15 +475,15 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 			m = y > m ? y : m;
 		}
 		if (lane == 0 && m)
-			atomicMax(&p.g->last_marker_p1, m);
+			atomicMax(&p.b->last_marker_p1, m);
 	}
 	if (nonmono)
-		p.g->nonmono = 1u;
+		p.b->nonmono = 1u;
 	__syncthreads();
 	if (tid == 0) {
 		unsigned int cnt = s_evn;
 		if (cnt > EVK) {
-			p.g->overflow = 1u;
+			p.b->overflow = 1u;
 			cnt = EVK;
 		}
 		p.ev_count[t] = cnt;

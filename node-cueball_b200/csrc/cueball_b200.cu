@@ -1,6 +1,8 @@
 // cueball_b200.cu -- the C ABI (include/cueball_b200.h) over the sm_100a kernels.
-// Host-side plumbing only: buffers, streams, launches, the chunked H2D/compute/D2H
-// pipeline of the host-buffer entry points, and a dlopen()ed NCCL for the one collective.
+// Host-side plumbing only: buffers, streams, launches, the batch pipeline (scan of batch k+1
+// overlaps resolve of batch k and emit of batch k-1 on three streams), the chunked
+// H2D/compute/D2H pipeline of the host-buffer entry points, and a dlopen()ed NCCL for the one
+// collective.
 #include "../../include/cueball_b200.h"
 
 #include <cuda_runtime.h>
@@ -55,43 +57,55 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0;
 
+constexpr int CB_LANES = 3;                   // batches in flight (scan | resolve | emit)
 constexpr int NBUF = 3;                       // staging buffers of the host-buffer pipeline
 constexpr size_t DEFAULT_CHUNK = 4u << 20;    // claims per pipeline chunk
+
+// per-batch scratch: everything one batch's three kernels hand to each other
+struct Lane {
+	size_t cap_tiles = 0;
+	BatchCtl *ctl = nullptr;
+	SumDesc *sdesc = nullptr;
+	unsigned int *ev_count = nullptr, *rec_fc = nullptr, *rec_cend = nullptr, *xcnt = nullptr, *hj_info = nullptr;
+	unsigned int *ticket = nullptr;
+	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
+	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr, *tile_now0 = nullptr;
+	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
+	double *ev_now = nullptr, *hj_F = nullptr;
+	cudaEvent_t scan_done = nullptr, res_done = nullptr, emit_done = nullptr, coll_done = nullptr;
+	bool used = false, coll_pending = false;
+	unsigned long long epoch = 0;
+};
 
 struct Staging {
 	void *start = nullptr, *now = nullptr;
 	uint8_t *flags = nullptr, *decision = nullptr;
 	int32_t *slot = nullptr, *backend = nullptr;
-	cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+	cudaEvent_t in_done = nullptr, out_done = nullptr;
 };
 
 } // namespace
 
 struct cb_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;     // "main" stream: the caller's, or own_stream
 	cudaStream_t own_stream = nullptr;
+	bool user_stream = false;
+	cudaStream_t st_scan = nullptr, st_res = nullptr, st_emit = nullptr, st_coll = nullptr;
 	cudaStream_t s_in = nullptr, s_out = nullptr;
+	cudaEvent_t ev_user = nullptr;
 	DevState *g = nullptr;
 	bool codel_ready = false;
-	char err[512] = "";
-	unsigned long long epoch = 0;
-	uint64_t launches = 0;
-	// scratch sized by tile count
-	size_t cap_tiles = 0;
 	double target_ms = 0;
-	// per-tile run records (scan -> resolve) and resolve scratch
-	unsigned int *rec_fc = nullptr, *rec_cend = nullptr, *xcnt = nullptr, *hj_info = nullptr;
-	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr;
-	double *hj_F = nullptr;
-	unsigned long long *tile_now0 = nullptr;
-	int emit_grid = 148 * 4; // persistent emit CTAs (set from the device's SM count)
-	SumDesc *sdesc = nullptr;
-	unsigned int *ev_count = nullptr;
-	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
-	double *ev_now = nullptr;
-	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
-	unsigned int *ticket = nullptr;
+	char err[512] = "";
+	uint64_t launches = 0;
+	// batch pipeline
+	int depth = CB_LANES;
+	Lane lane[CB_LANES];
+	unsigned long long seq = 0;        // batches enqueued so far
+	int last_lane = -1;
+	bool last_flags = false;
+	int emit_grid = 148 * 4;           // persistent emit CTAs (from the device's SM count)
 	// topology
 	int B = 0, nslots = 0, target_slots = 0, mode = CB_BALANCE_UNIFORM, key_cap = 0, slot_cap = 0;
 	int32_t *d_keys = nullptr, *d_want = nullptr, *d_add = nullptr, *d_slot_backend = nullptr;
@@ -101,8 +115,6 @@ struct cb_ctx {
 	// host-buffer pipeline
 	size_t chunk = DEFAULT_CHUNK, stage_cap = 0;
 	Staging st[NBUF];
-	// cached totals for per-call deltas
-	unsigned long long seen_drops = 0, seen_admits = 0;
 	// profiling
 	bool prof = false;
 	cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -111,7 +123,6 @@ struct cb_ctx {
 	// nccl
 	nccl_comm_t comm = nullptr;
 	int nranks = 1, rank = 0;
-	unsigned long long *h_pinned = nullptr; // small pinned scratch
 };
 
 namespace {
@@ -141,45 +152,68 @@ template <typename T> int dev_alloc(cb_ctx *c, T **p, size_t count) {
 	return CB_OK;
 }
 
-int ensure_scratch(cb_ctx *c, size_t tiles) {
-	if (tiles <= c->cap_tiles)
-		return CB_OK;
-	size_t cap = tiles + tiles / 4 + 64;
-	const size_t evcap = (cap + 1) * (EVK + 3);
-	int rc;
-	if ((rc = dev_alloc(c, &c->sdesc, cap)) || (rc = dev_alloc(c, &c->ev_count, cap)) ||
-	    (rc = dev_alloc(c, &c->ev, cap * EVK)) || (rc = dev_alloc(c, &c->rec_fc, cap)) ||
-	    (rc = dev_alloc(c, &c->rec_code, cap)) || (rc = dev_alloc(c, &c->rec_cend, cap)) ||
-	    (rc = dev_alloc(c, &c->tile_now0, cap)) ||
-	    (rc = dev_alloc(c, &c->xev, (cap + 1) * 3)) || (rc = dev_alloc(c, &c->xcnt, cap + 1)) ||
-	    (rc = dev_alloc(c, &c->hj_lo, cap + 1)) || (rc = dev_alloc(c, &c->hj_b, cap + 1)) ||
-	    (rc = dev_alloc(c, &c->hj_F, cap + 1)) || (rc = dev_alloc(c, &c->hj_info, cap + 1)) ||
-	    (rc = dev_alloc(c, &c->evc, evcap)) || (rc = dev_alloc(c, &c->ev_q, evcap)) ||
-	    (rc = dev_alloc(c, &c->ev_d, evcap)) || (rc = dev_alloc(c, &c->ev_now, evcap)) ||
-	    (rc = dev_alloc(c, &c->iv_lo, evcap + 8)) || (rc = dev_alloc(c, &c->iv_hi, evcap + 8)) ||
-	    (rc = dev_alloc(c, &c->iv_cum, evcap + 8)))
-		return rc;
-	// the emit kernel's sum descriptors carry an epoch tag, so they only need zeroing once
-	CU(c, cudaMemsetAsync(c->sdesc, 0, cap * sizeof(SumDesc), c->stream));
-	c->cap_tiles = cap;
+// wait for every batch in flight (and the main stream)
+int drain(cb_ctx *c) {
+	CU(c, cudaStreamSynchronize(c->st_scan));
+	CU(c, cudaStreamSynchronize(c->st_res));
+	CU(c, cudaStreamSynchronize(c->st_emit));
+	CU(c, cudaStreamSynchronize(c->st_coll));
+	CU(c, cudaStreamSynchronize(c->stream));
 	return CB_OK;
 }
 
-// launch the three kernels of one batch on the context's stream
+int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
+	if (tiles <= L.cap_tiles)
+		return CB_OK;
+	// growing a lane's scratch: nothing of this lane may be in flight
+	if (L.used) {
+		CU(c, cudaEventSynchronize(L.emit_done));
+		if (L.coll_pending)
+			CU(c, cudaEventSynchronize(L.coll_done));
+	}
+	size_t cap = tiles + tiles / 4 + 64;
+	const size_t evcap = (cap + 1) * (EVK + 3);
+	int rc;
+	if ((rc = dev_alloc(c, &L.sdesc, cap)) || (rc = dev_alloc(c, &L.ev_count, cap)) ||
+	    (rc = dev_alloc(c, &L.ev, cap * EVK)) || (rc = dev_alloc(c, &L.rec_fc, cap)) ||
+	    (rc = dev_alloc(c, &L.rec_code, cap)) || (rc = dev_alloc(c, &L.rec_cend, cap)) ||
+	    (rc = dev_alloc(c, &L.tile_now0, cap)) || (rc = dev_alloc(c, &L.xev, (cap + 1) * 3)) ||
+	    (rc = dev_alloc(c, &L.xcnt, cap + 1)) || (rc = dev_alloc(c, &L.hj_lo, cap + 1)) ||
+	    (rc = dev_alloc(c, &L.hj_b, cap + 1)) || (rc = dev_alloc(c, &L.hj_F, cap + 1)) ||
+	    (rc = dev_alloc(c, &L.hj_info, cap + 1)) || (rc = dev_alloc(c, &L.evc, evcap)) ||
+	    (rc = dev_alloc(c, &L.ev_q, evcap)) || (rc = dev_alloc(c, &L.ev_d, evcap)) ||
+	    (rc = dev_alloc(c, &L.ev_now, evcap)) || (rc = dev_alloc(c, &L.iv_lo, evcap + 8)) ||
+	    (rc = dev_alloc(c, &L.iv_hi, evcap + 8)) || (rc = dev_alloc(c, &L.iv_cum, evcap + 8)))
+		return rc;
+	// the emit kernel's sum descriptors carry an epoch tag, so they only need zeroing once
+	CU(c, cudaMemset(L.sdesc, 0, cap * sizeof(SumDesc)));
+	L.cap_tiles = cap;
+	return CB_OK;
+}
+
+// Enqueue the three kernels of one batch.  depth 1 (or profiling): all three on the main
+// stream, in order.  depth > 1: scan / resolve / emit go to their own streams, chained by
+// events, so consecutive batches overlap; `in_ready` (optional) gates the scan on the batch's
+// inputs, and the batch's emit_done event is returned through `out_done`.
 template <bool NS>
-int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_t *d_flags, size_t n,
-    uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
+int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_t *d_flags, size_t n,
+    uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend, cudaEvent_t in_ready, cudaEvent_t *out_done) {
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	if (out_done)
+		*out_done = nullptr;
 	if (n == 0)
 		return CB_OK;
 	if (n > (1ull << 40))
 		return fail(c, CB_EINVAL, "batch too large");
+	const bool piped = (c->depth > 1) && !c->prof;
+	const int li = piped ? (int)(c->seq % (unsigned long long)c->depth) : 0;
+	Lane &L = c->lane[li];
 	const size_t tiles = (n + TILE - 1) / TILE;
-	int rc = ensure_scratch(c, tiles);
+	int rc = ensure_scratch(c, L, tiles);
 	if (rc)
 		return rc;
-	c->epoch++;
+	L.epoch++;
 	const bool flags = d_flags != nullptr;
 
 	ScanParams sp;
@@ -187,15 +221,16 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	sp.now = d_now;
 	sp.flags = d_flags;
 	sp.n = n;
-	sp.g = c->g;
-	sp.rec_fc = c->rec_fc;
-	sp.rec_code = c->rec_code;
-	sp.rec_cend = c->rec_cend;
-	sp.tile_now0 = c->tile_now0;
-	sp.target_ns = (long long)(c->target_ms * 1000000.0);
-	sp.ev_count = c->ev_count;
-	sp.ev = c->ev;
+	sp.b = L.ctl;
+	sp.target = c->target_ms;
+	sp.rec_fc = L.rec_fc;
+	sp.rec_code = L.rec_code;
+	sp.rec_cend = L.rec_cend;
+	sp.tile_now0 = L.tile_now0;
+	sp.ev_count = L.ev_count;
+	sp.ev = L.ev;
 	sp.vec_ok = (((uintptr_t)d_start | (uintptr_t)d_now) & 15) == 0;
+	sp.target_ns = (long long)(c->target_ms * 1000000.0);
 
 	ResolveParams rp;
 	rp.start = d_start;
@@ -204,26 +239,27 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	rp.n = n;
 	rp.tiles = tiles;
 	rp.g = c->g;
-	rp.rec_fc = c->rec_fc;
-	rp.rec_code = c->rec_code;
-	rp.rec_cend = c->rec_cend;
-	rp.tile_now0 = c->tile_now0;
-	rp.xev = c->xev;
-	rp.xcnt = c->xcnt;
-	rp.hj_lo = c->hj_lo;
-	rp.hj_b = c->hj_b;
-	rp.hj_F = c->hj_F;
-	rp.hj_info = c->hj_info;
-	rp.ev_count = c->ev_count;
-	rp.ev = c->ev;
-	rp.evc = c->evc;
-	rp.ev_now = c->ev_now;
-	rp.ev_q = c->ev_q;
-	rp.ev_d = c->ev_d;
+	rp.bc = L.ctl;
+	rp.rec_fc = L.rec_fc;
+	rp.rec_code = L.rec_code;
+	rp.rec_cend = L.rec_cend;
+	rp.tile_now0 = L.tile_now0;
+	rp.xev = L.xev;
+	rp.xcnt = L.xcnt;
+	rp.hj_lo = L.hj_lo;
+	rp.hj_b = L.hj_b;
+	rp.hj_F = L.hj_F;
+	rp.hj_info = L.hj_info;
+	rp.ev_count = L.ev_count;
+	rp.ev = L.ev;
+	rp.evc = L.evc;
+	rp.ev_now = L.ev_now;
+	rp.ev_q = L.ev_q;
+	rp.ev_d = L.ev_d;
 	rp.ev_cap = (tiles + 1) * (EVK + 3);
-	rp.iv_lo = c->iv_lo;
-	rp.iv_hi = c->iv_hi;
-	rp.iv_cum = c->iv_cum;
+	rp.iv_lo = L.iv_lo;
+	rp.iv_hi = L.iv_hi;
+	rp.iv_cum = L.iv_cum;
 	rp.decision = d_decision;
 	rp.slot = d_slot;
 	rp.backend = d_backend;
@@ -235,9 +271,10 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	ep.n = n;
 	ep.tiles = tiles;
 	ep.g = c->g;
-	ep.iv_lo = c->iv_lo;
-	ep.iv_hi = c->iv_hi;
-	ep.iv_cum = c->iv_cum;
+	ep.bc = L.ctl;
+	ep.iv_lo = L.iv_lo;
+	ep.iv_hi = L.iv_hi;
+	ep.iv_cum = L.iv_cum;
 	ep.decision = d_decision;
 	ep.slot = d_slot;
 	ep.backend = d_backend;
@@ -245,40 +282,74 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	ep.nslots = c->nslots;
 	ep.slot_magic = c->nslots > 0 ? (~0ull) / (unsigned long long)c->nslots : 0ull;
 	size_t tbytes = ((size_t)c->nslots * 4 + 15) & ~(size_t)15;
-	ep.table_smem_bytes = (d_backend && c->nslots > 0 && tbytes <= 96 * 1024) ? (int)tbytes : 0;
-	ep.sdesc = c->sdesc;
-	ep.epoch = c->epoch;
-	ep.ticket = c->ticket;
+	ep.table_smem_bytes = (d_backend && c->nslots > 0 && tbytes <= 48 * 1024) ? (int)tbytes : 0;
+	ep.sdesc = L.sdesc;
+	ep.epoch = L.epoch;
+	ep.ticket = L.ticket;
 	ep.vec_ok = (((uintptr_t)d_decision & 7) == 0) && (((uintptr_t)d_slot & 15) == 0) &&
 	    (((uintptr_t)d_backend & 15) == 0);
-
-	cudaStream_t s = c->stream;
-	if (c->prof)
-		CU(c, cudaEventRecord(c->pe[0], s));
-	if (flags)
-		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s>>>(sp);
-	else
-		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s>>>(sp);
-	if (c->prof)
-		CU(c, cudaEventRecord(c->pe[1], s));
-	if (flags)
-		resolve_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-	else
-		resolve_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-	if (c->prof)
-		CU(c, cudaEventRecord(c->pe[2], s));
 	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
-	// tile's CTA to be resident or earlier in the same CTA's sequence: both hold for a grid that
-	// does not exceed the resident capacity (tiles are visited in increasing order per CTA)
+	// earlier tile to be resident or earlier in the same CTA's sequence: both hold for a grid
+	// within the resident capacity (a CTA visits its tiles in increasing order)
 	const unsigned egrid = (unsigned)(tiles < (size_t)c->emit_grid ? tiles : (size_t)c->emit_grid);
+
+	cudaStream_t s_scan = piped ? c->st_scan : c->stream;
+	cudaStream_t s_res = piped ? c->st_res : c->stream;
+	cudaStream_t s_emit = piped ? c->st_emit : c->stream;
+	if (piped) {
+		if (c->user_stream) { // the caller's earlier work (e.g. filling the inputs) comes first
+			CU(c, cudaEventRecord(c->ev_user, c->stream));
+			CU(c, cudaStreamWaitEvent(s_scan, c->ev_user, 0));
+		}
+		if (L.used) { // this lane's scratch is free once its previous batch has been emitted
+			CU(c, cudaStreamWaitEvent(s_scan, L.emit_done, 0));
+			if (L.coll_pending)
+				CU(c, cudaStreamWaitEvent(s_scan, L.coll_done, 0));
+		}
+	}
+	if (in_ready)
+		CU(c, cudaStreamWaitEvent(s_scan, in_ready, 0));
+	if (c->prof)
+		CU(c, cudaEventRecord(c->pe[0], s_scan));
 	if (flags)
-		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
+		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
 	else
-		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
+		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
+	if (c->prof)
+		CU(c, cudaEventRecord(c->pe[1], s_scan));
+	if (piped) {
+		CU(c, cudaEventRecord(L.scan_done, s_scan));
+		CU(c, cudaStreamWaitEvent(s_res, L.scan_done, 0));
+		// a flags batch finishes its cursor/totals in its emit kernel: the next resolve needs them
+		if (c->last_flags && c->last_lane >= 0 && c->last_lane != li)
+			CU(c, cudaStreamWaitEvent(s_res, c->lane[c->last_lane].emit_done, 0));
+	}
+	if (flags)
+		resolve_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s_res>>>(rp);
+	else
+		resolve_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s_res>>>(rp);
+	if (c->prof)
+		CU(c, cudaEventRecord(c->pe[2], s_res));
+	if (piped) {
+		CU(c, cudaEventRecord(L.res_done, s_res));
+		CU(c, cudaStreamWaitEvent(s_emit, L.res_done, 0));
+	}
+	if (flags)
+		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s_emit>>>(ep);
+	else
+		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s_emit>>>(ep);
 	c->launches += 3;
 	CU(c, cudaGetLastError());
+	CU(c, cudaEventRecord(L.emit_done, s_emit));
+	L.used = true;
+	L.coll_pending = false;
+	c->last_lane = li;
+	c->last_flags = flags;
+	c->seq++;
+	if (out_done)
+		*out_done = L.emit_done;
 	if (c->prof) {
-		CU(c, cudaEventRecord(c->pe[3], s));
+		CU(c, cudaEventRecord(c->pe[3], s_emit));
 		CU(c, cudaEventSynchronize(c->pe[3]));
 		for (int k = 0; k < CB_K_COUNT; k++) {
 			float ms = 0;
@@ -290,21 +361,27 @@ int launch_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_
 	return CB_OK;
 }
 
-int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool per_call) {
+int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	DevState h;
-	CU(c, cudaMemcpyAsync(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
+	BatchCtl b;
+	memset(&b, 0, sizeof(b));
+	CU(c, cudaMemcpy(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost));
+	if (c->last_lane >= 0)
+		CU(c, cudaMemcpy(&b, c->lane[c->last_lane].ctl, sizeof(b), cudaMemcpyDeviceToHost));
 	memset(out, 0, sizeof(*out));
-	out->n = h.n;
-	out->drops = h.drops;
-	out->admits = h.admits;
-	out->skipped = h.skipped;
+	out->n = b.n;
+	out->drops = b.drops;
+	out->admits = b.admits;
+	out->skipped = b.skipped;
 	out->cursor = h.cursor;
 	out->total_drops = h.tot_drops;
 	out->total_admits = h.tot_admits;
-	out->global_drops = c->comm ? h.gcounts[0] : h.drops;
-	out->global_admits = c->comm ? h.gcounts[1] : h.admits;
-	out->global_n = c->comm ? h.gcounts[2] : h.n;
+	out->global_drops = c->comm ? b.gcounts[0] : b.drops;
+	out->global_admits = c->comm ? b.gcounts[1] : b.admits;
+	out->global_n = c->comm ? b.gcounts[2] : b.n;
 	out->state.target_ms = h.target;
 	out->state.first_above_time = h.F;
 	out->state.drop_next = h.D;
@@ -312,10 +389,9 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool per_call) {
 	out->state.dropping = h.B;
 	out->state.has_last_empty = h.hasE;
 	out->state.last_empty = h.E;
-	out->path = h.path;
-	out->n_events = h.n_events;
-	out->n_intervals = h.n_intervals;
-	(void)per_call;
+	out->path = b.path;
+	out->n_events = b.n_events;
+	out->n_intervals = b.n_intervals;
 	return CB_OK;
 }
 
@@ -324,9 +400,11 @@ int ensure_staging(cb_ctx *c, size_t n) {
 	need = (need + TILE - 1) / TILE * TILE;
 	if (need <= c->stage_cap)
 		return CB_OK;
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	for (int b = 0; b < NBUF; b++) {
 		Staging &s = c->st[b];
-		int rc;
 		if ((rc = dev_alloc(c, (unsigned long long **)&s.start, need)) ||
 		    (rc = dev_alloc(c, (unsigned long long **)&s.now, need)) || (rc = dev_alloc(c, &s.flags, need)) ||
 		    (rc = dev_alloc(c, &s.decision, need)) || (rc = dev_alloc(c, &s.slot, need)) ||
@@ -334,7 +412,6 @@ int ensure_staging(cb_ctx *c, size_t n) {
 			return rc;
 		if (!s.in_done) {
 			CU(c, cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
-			CU(c, cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
 			CU(c, cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
 		}
 	}
@@ -342,8 +419,8 @@ int ensure_staging(cb_ctx *c, size_t n) {
 	return CB_OK;
 }
 
-// host-buffer batch: chunks flow H2D -> kernels -> D2H on three streams; the CoDel state
-// and the admit cursor stay on the device between chunks (a chunk is just a batch).
+// host-buffer batch: chunks flow H2D -> kernels -> D2H; the CoDel state and the admit cursor
+// stay on the device between chunks (a chunk is just a batch of the pipeline).
 template <bool NS>
 int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *flags, size_t n,
     uint8_t *decision, int32_t *slot, int32_t *backend, cb_batch_stats *stats) {
@@ -351,19 +428,18 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	if (n && (!start || !now))
 		return fail(c, CB_EINVAL, "start/now must not be NULL");
-	DevState h0;
-	CU(c, cudaMemcpyAsync(&h0, c->g, sizeof(h0), cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
-	int rc = ensure_staging(c, n);
+	int rc = drain(c);
 	if (rc)
 		return rc;
-	unsigned long long skipped = 0;
-	int path = 0;
-	unsigned int nev = 0, niv = 0;
-	size_t nchunks = (n + c->chunk - 1) / c->chunk;
+	DevState h0;
+	CU(c, cudaMemcpy(&h0, c->g, sizeof(h0), cudaMemcpyDeviceToHost));
+	rc = ensure_staging(c, n);
+	if (rc)
+		return rc;
+	const size_t nchunks = (n + c->chunk - 1) / c->chunk;
 	for (size_t ci = 0; ci < nchunks; ci++) {
 		Staging &s = c->st[ci % NBUF];
-		size_t lo = ci * c->chunk, m = (n - lo < c->chunk) ? n - lo : c->chunk;
+		const size_t lo = ci * c->chunk, m = (n - lo < c->chunk) ? n - lo : c->chunk;
 		if (ci >= NBUF)
 			CU(c, cudaStreamWaitEvent(c->s_in, s.out_done, 0));
 		CU(c, cudaMemcpyAsync(s.start, (const char *)start + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
@@ -371,13 +447,13 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		if (flags)
 			CU(c, cudaMemcpyAsync(s.flags, flags + lo, m, cudaMemcpyHostToDevice, c->s_in));
 		CU(c, cudaEventRecord(s.in_done, c->s_in));
-		CU(c, cudaStreamWaitEvent(c->stream, s.in_done, 0));
-		rc = launch_batch<NS>(c, s.start, s.now, flags ? s.flags : nullptr, m, decision ? s.decision : nullptr,
-		    slot ? s.slot : nullptr, backend ? s.backend : nullptr);
+		cudaEvent_t done = nullptr;
+		rc = enqueue_batch<NS>(c, s.start, s.now, flags ? s.flags : nullptr, m, decision ? s.decision : nullptr,
+		    slot ? s.slot : nullptr, backend ? s.backend : nullptr, s.in_done, &done);
 		if (rc)
 			return rc;
-		CU(c, cudaEventRecord(s.comp_done, c->stream));
-		CU(c, cudaStreamWaitEvent(c->s_out, s.comp_done, 0));
+		if (done)
+			CU(c, cudaStreamWaitEvent(c->s_out, done, 0));
 		if (decision)
 			CU(c, cudaMemcpyAsync(decision + lo, s.decision, m, cudaMemcpyDeviceToHost, c->s_out));
 		if (slot)
@@ -385,14 +461,10 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		if (backend)
 			CU(c, cudaMemcpyAsync(backend + lo, s.backend, m * 4, cudaMemcpyDeviceToHost, c->s_out));
 		CU(c, cudaEventRecord(s.out_done, c->s_out));
-		if (nchunks > 1 && stats) { // per-chunk extras that are not cumulative on the device
-			// (kept cheap: only when the caller wants stats and the batch was split)
-		}
 	}
 	CU(c, cudaStreamSynchronize(c->s_out));
-	CU(c, cudaStreamSynchronize(c->stream));
 	if (stats) {
-		rc = fetch_stats(c, stats, true);
+		rc = fetch_stats(c, stats);
 		if (rc)
 			return rc;
 		// totals of the whole call, not of its last chunk
@@ -405,10 +477,10 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 			stats->global_admits = stats->admits;
 			stats->global_n = n;
 		}
-		(void)skipped;
-		(void)path;
-		(void)nev;
-		(void)niv;
+	} else {
+		rc = drain(c);
+		if (rc)
+			return rc;
 	}
 	return CB_OK;
 }
@@ -506,10 +578,13 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	if (!c)
 		return fail(nullptr, CB_ENOMEM, "out of host memory");
 	c->device = device;
-	c->emit_grid = prop.multiProcessorCount * 4; // 4 x 256-thread CTAs per SM are resident (<= 96 KB smem each only without a staged table: see launch)
+	c->emit_grid = prop.multiProcessorCount * 4;
 	const char *ck = getenv("CB_CHUNK");
 	if (ck && atoll(ck) >= TILE)
 		c->chunk = ((size_t)atoll(ck) + TILE - 1) / TILE * TILE;
+	const char *dp = getenv("CB_PIPELINE_DEPTH");
+	if (dp && atoi(dp) >= 1 && atoi(dp) <= CB_LANES)
+		c->depth = atoi(dp);
 #define CU0(call)                                                                          \
 	do {                                                                                   \
 		cudaError_t e_ = (call);                                                           \
@@ -521,25 +596,38 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	} while (0)
 	CU0(cudaSetDevice(device));
 	CU0(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	CU0(cudaStreamCreateWithFlags(&c->st_scan, cudaStreamNonBlocking));
+	CU0(cudaStreamCreateWithFlags(&c->st_res, cudaStreamNonBlocking));
+	CU0(cudaStreamCreateWithFlags(&c->st_emit, cudaStreamNonBlocking));
+	CU0(cudaStreamCreateWithFlags(&c->st_coll, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+	CU0(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
-	CU0(cudaMalloc((void **)&c->ticket, 64));
-	CU0(cudaMemset(c->ticket, 0, 64));
+	for (int l = 0; l < CB_LANES; l++) {
+		Lane &L = c->lane[l];
+		CU0(cudaMalloc((void **)&L.ctl, sizeof(BatchCtl)));
+		CU0(cudaMemset(L.ctl, 0, sizeof(BatchCtl)));
+		CU0(cudaMalloc((void **)&L.ticket, 64));
+		CU0(cudaMemset(L.ticket, 0, 64));
+		CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
+		CU0(cudaEventCreateWithFlags(&L.res_done, cudaEventDisableTiming));
+		CU0(cudaEventCreateWithFlags(&L.emit_done, cudaEventDisableTiming));
+		CU0(cudaEventCreateWithFlags(&L.coll_done, cudaEventDisableTiming));
+	}
 	CU0(cudaMalloc((void **)&c->d_ints, 64 * sizeof(int)));
 	CU0(cudaMemset(c->d_ints, 0, 64 * sizeof(int)));
 	CU0(cudaMalloc((void **)&c->d_dbl, 64 * sizeof(double)));
-	CU0(cudaMallocHost((void **)&c->h_pinned, 256));
 	for (int k = 0; k < 4; k++)
 		CU0(cudaEventCreate(&c->pe[k]));
 	CU0(cudaFuncSetAttribute(resolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(resolve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(resolve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 #undef CU0
 	*out = c;
 	return CB_OK;
@@ -549,13 +637,26 @@ extern "C" void cb_destroy(cb_ctx *c) {
 	if (!c)
 		return;
 	cudaSetDevice(c->device);
-	if (c->stream)
-		cudaStreamSynchronize(c->stream);
+	cudaStream_t all[] = {c->st_scan, c->st_res, c->st_emit, c->st_coll, c->s_in, c->s_out, c->own_stream};
+	for (cudaStream_t s : all)
+		if (s)
+			cudaStreamSynchronize(s);
 	if (c->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(c->comm);
-	void *frees[] = {c->g, c->rec_fc, c->rec_code, c->rec_cend, c->xev, c->xcnt, c->hj_lo, c->hj_b, c->hj_F, c->hj_info, c->tile_now0, c->sdesc, c->ev_count, c->ev, c->evc, c->ev_q, c->ev_d, c->ev_now, c->iv_lo,
-	    c->iv_hi, c->iv_cum, c->ticket, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight,
-	    c->d_ints, c->d_dbl};
+	for (int l = 0; l < CB_LANES; l++) {
+		Lane &L = c->lane[l];
+		void *fr[] = {L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
+		    L.ev_q, L.ev_d, L.rec_code, L.xev, L.hj_lo, L.hj_b, L.tile_now0, L.iv_lo, L.iv_hi, L.iv_cum, L.ev_now, L.hj_F};
+		for (void *p : fr)
+			if (p)
+				cudaFree(p);
+		cudaEvent_t evs[] = {L.scan_done, L.res_done, L.emit_done, L.coll_done};
+		for (cudaEvent_t e : evs)
+			if (e)
+				cudaEventDestroy(e);
+	}
+	void *frees[] = {c->g, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight, c->d_ints,
+	    c->d_dbl};
 	for (void *p : frees)
 		if (p)
 			cudaFree(p);
@@ -567,38 +668,58 @@ extern "C" void cb_destroy(cb_ctx *c) {
 				cudaFree(p);
 		if (s.in_done)
 			cudaEventDestroy(s.in_done);
-		if (s.comp_done)
-			cudaEventDestroy(s.comp_done);
 		if (s.out_done)
 			cudaEventDestroy(s.out_done);
 	}
 	for (int k = 0; k < 4; k++)
 		if (c->pe[k])
 			cudaEventDestroy(c->pe[k]);
-	if (c->h_pinned)
-		cudaFreeHost(c->h_pinned);
-	if (c->own_stream)
-		cudaStreamDestroy(c->own_stream);
-	if (c->s_in)
-		cudaStreamDestroy(c->s_in);
-	if (c->s_out)
-		cudaStreamDestroy(c->s_out);
+	if (c->ev_user)
+		cudaEventDestroy(c->ev_user);
+	for (cudaStream_t s : all)
+		if (s)
+			cudaStreamDestroy(s);
 	delete c;
 }
 
 extern "C" int cb_set_stream(cb_ctx *c, void *stream) {
 	if (!c)
 		return CB_EINVAL;
-	CU(c, cudaStreamSynchronize(c->stream));
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+	c->user_stream = stream != nullptr;
+	return CB_OK;
+}
+
+extern "C" int cb_set_pipeline_depth(cb_ctx *c, int depth) {
+	if (!c || depth < 1 || depth > CB_LANES)
+		return c ? fail(c, CB_EINVAL, "pipeline depth must be 1..%d", CB_LANES) : CB_EINVAL;
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	c->depth = depth;
+	return CB_OK;
+}
+
+// make the main (caller's) stream wait for every batch enqueued so far
+extern "C" int cb_join(cb_ctx *c) {
+	if (!c)
+		return CB_EINVAL;
+	if (c->last_lane >= 0 && c->depth > 1) {
+		Lane &L = c->lane[c->last_lane];
+		CU(c, cudaStreamWaitEvent(c->stream, L.emit_done, 0)); // emits run in order on one stream
+		if (L.coll_pending)
+			CU(c, cudaStreamWaitEvent(c->stream, L.coll_done, 0));
+	}
 	return CB_OK;
 }
 
 extern "C" int cb_synchronize(cb_ctx *c) {
 	if (!c)
 		return CB_EINVAL;
-	CU(c, cudaStreamSynchronize(c->stream));
-	return CB_OK;
+	return drain(c);
 }
 
 extern "C" void *cb_host_alloc(cb_ctx *c, size_t bytes) {
@@ -622,12 +743,14 @@ extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
 	// utils.assertClaimDelay, lib/utils.js:188-195: finite, > 0, integral
 	if (!isfinite(target_ms) || !(target_ms > 0) || target_ms != floor(target_ms))
 		return fail(c, CB_EINVAL, "targetClaimDelay must be a positive integer number of ms");
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	DevState h;
 	memset(&h, 0, sizeof(h));
 	h.target = target_ms;
 	c->target_ms = target_ms;
-	CU(c, cudaMemcpyAsync(c->g, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
+	CU(c, cudaMemcpy(c->g, &h, sizeof(h), cudaMemcpyHostToDevice));
 	c->codel_ready = true;
 	return CB_OK;
 }
@@ -636,7 +759,7 @@ extern "C" int cb_codel_get_state(cb_ctx *c, cb_codel_state *out) {
 	if (!c || !out)
 		return CB_EINVAL;
 	cb_batch_stats st;
-	int rc = fetch_stats(c, &st, false);
+	int rc = fetch_stats(c, &st);
 	if (rc)
 		return rc;
 	*out = st.state;
@@ -648,17 +771,18 @@ extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
 		return CB_EINVAL;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	DevState h;
-	CU(c, cudaMemcpyAsync(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
+	CU(c, cudaMemcpy(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost));
 	h.F = in->first_above_time;
 	h.D = in->drop_next;
 	h.C = in->count;
 	h.B = in->dropping ? 1 : 0;
 	h.hasE = in->has_last_empty ? 1 : 0;
 	h.E = in->last_empty;
-	CU(c, cudaMemcpyAsync(c->g, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
+	CU(c, cudaMemcpy(c->g, &h, sizeof(h), cudaMemcpyHostToDevice));
 	return CB_OK;
 }
 
@@ -667,9 +791,13 @@ extern "C" int cb_codel_empty(cb_ctx *c, int64_t now_ns) {
 		return CB_EINVAL;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	empty_kernel<<<1, 1, 0, c->stream>>>(c->g, now_ns);
 	c->launches++;
 	CU(c, cudaGetLastError());
+	CU(c, cudaStreamSynchronize(c->stream));
 	return CB_OK;
 }
 
@@ -678,6 +806,9 @@ extern "C" int cb_codel_max_idle(cb_ctx *c, int64_t now_ns, double *out_ms) {
 		return CB_EINVAL;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	max_idle_kernel<<<1, 1, 0, c->stream>>>(c->g, now_ns, c->d_dbl);
 	c->launches++;
 	CU(c, cudaGetLastError());
@@ -691,6 +822,9 @@ extern "C" int cb_codel_overloaded(cb_ctx *c, int64_t start_ns, int64_t now_ns, 
 		return CB_EINVAL;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	int rc = drain(c);
+	if (rc)
+		return rc;
 	overloaded_one_kernel<<<1, 1, 0, c->stream>>>(c->g, start_ns, now_ns, c->d_ints + 5);
 	c->launches++;
 	CU(c, cudaGetLastError());
@@ -716,18 +850,18 @@ extern "C" int cb_admit_batch_dev(cb_ctx *c, const int64_t *d_start, const int64
     size_t n, uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
 	if (!c)
 		return CB_EINVAL;
-	return launch_batch<true>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend);
+	return enqueue_batch<true>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend, nullptr, nullptr);
 }
 extern "C" int cb_admit_batch_ms_dev(cb_ctx *c, const double *d_start, const double *d_now, const uint8_t *d_flags,
     size_t n, uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
 	if (!c)
 		return CB_EINVAL;
-	return launch_batch<false>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend);
+	return enqueue_batch<false>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend, nullptr, nullptr);
 }
 extern "C" int cb_batch_stats_get(cb_ctx *c, cb_batch_stats *out) {
 	if (!c || !out)
 		return CB_EINVAL;
-	return fetch_stats(c, out, false);
+	return fetch_stats(c, out);
 }
 
 // ============================================================================== topology
@@ -742,6 +876,11 @@ extern "C" int cb_backends_set(cb_ctx *c, const cb_backend *tbl, int32_t B, cons
 	for (int k = 0; k < B; k++)
 		if (!(insert_u[k] >= 0.0 && insert_u[k] < 1.0))
 			return fail(c, CB_EINVAL, "insert_u[%d] not in [0,1)", k);
+	{
+		int rc0 = drain(c); // the emit kernels of batches in flight read the slot table
+		if (rc0)
+			return rc0;
+	}
 	c->B = 0; // the old list is replaced
 	int rc = ensure_topology(c, B, nslots);
 	if (rc)
@@ -782,6 +921,11 @@ extern "C" int cb_backends_set(cb_ctx *c, const cb_backend *tbl, int32_t B, cons
 extern "C" int cb_backend_added(cb_ctx *c, int32_t key, const cb_backend *be, double u) {
 	if (!c || key < 0 || !(u >= 0.0 && u < 1.0))
 		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
+	{
+		int rc0 = drain(c);
+		if (rc0)
+			return rc0;
+	}
 	int need_keys = (key + 1 > c->B + 1) ? key + 1 : c->B + 1;
 	int rc = ensure_topology(c, need_keys, c->target_slots);
 	if (rc)
@@ -800,6 +944,11 @@ extern "C" int cb_backend_added(cb_ctx *c, int32_t key, const cb_backend *be, do
 extern "C" int cb_backend_removed(cb_ctx *c, int32_t key) {
 	if (!c)
 		return CB_EINVAL;
+	{
+		int rc0 = drain(c);
+		if (rc0)
+			return rc0;
+	}
 	pref_remove_kernel<<<1, TOPO_TPB, 0, c->stream>>>(c->d_keys, c->d_ints, key, c->d_ints + 3);
 	c->launches++;
 	CU(c, cudaGetLastError());
@@ -817,6 +966,11 @@ extern "C" int cb_reshuffle(cb_ctx *c, double u) {
 		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
 	if (c->B <= 1)
 		return CB_OK; // lib/pool.js:502-503
+	{
+		int rc0 = drain(c);
+		if (rc0)
+			return rc0;
+	}
 	pref_reshuffle_kernel<<<1, TOPO_TPB, 0, c->stream>>>(c->d_keys, c->d_ints, u);
 	c->launches++;
 	CU(c, cudaGetLastError());
@@ -938,11 +1092,24 @@ extern "C" int cb_allreduce_counts(cb_ctx *c) {
 		return CB_EINVAL;
 	if (!c->comm)
 		return fail(c, CB_ESTATE, "cb_comm_init has not been called");
-	// {drops, admits, n} of the last batch, summed over ranks, in place in the control block
-	unsigned long long *buf = (unsigned long long *)((char *)c->g + offsetof(DevState, gcounts));
-	int r = g_nccl.AllReduce(buf, buf, 3, NCCL_UINT64, NCCL_SUM, c->comm, c->stream);
+	if (c->last_lane < 0)
+		return CB_OK;
+	// {drops, admits, n} of the last batch, summed over ranks, in place in its control block.
+	// The counts are final after the resolve kernel (after the emit kernel for a flags batch); the
+	// collective runs on its own stream so it never stalls the next batch's kernels.
+	Lane &L = c->lane[c->last_lane];
+	const bool piped = (c->depth > 1) && !c->prof;
+	cudaStream_t s = piped ? c->st_coll : c->stream;
+	if (piped)
+		CU(c, cudaStreamWaitEvent(s, c->last_flags ? L.emit_done : L.res_done, 0));
+	unsigned long long *buf = (unsigned long long *)((char *)L.ctl + offsetof(BatchCtl, gcounts));
+	int r = g_nccl.AllReduce(buf, buf, 3, NCCL_UINT64, NCCL_SUM, c->comm, s);
 	if (r != 0)
 		return fail(c, CB_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+	if (piped) {
+		CU(c, cudaEventRecord(L.coll_done, s));
+		L.coll_pending = true;
+	}
 	return CB_OK;
 }
 
@@ -973,10 +1140,14 @@ extern "C" uint64_t cb_launch_count(const cb_ctx *c) { return c ? c->launches : 
 extern "C" int cb_debug_timestamps(cb_ctx *c, uint64_t out[16]) {
 	if (!c || !out)
 		return CB_EINVAL;
-	DevState h;
-	CU(c, cudaMemcpyAsync(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-	CU(c, cudaStreamSynchronize(c->stream));
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	BatchCtl b;
+	memset(&b, 0, sizeof(b));
+	if (c->last_lane >= 0)
+		CU(c, cudaMemcpy(&b, c->lane[c->last_lane].ctl, sizeof(b), cudaMemcpyDeviceToHost));
 	for (int k = 0; k < 16; k++)
-		out[k] = h.dbg[k];
+		out[k] = b.dbg[k];
 	return CB_OK;
 }
