@@ -45,6 +45,16 @@ static_assert(CHUNK * WARPS == TILE, "tile geometry");
 constexpr unsigned long long CODE_ZERO = 0, CODE_CARRY = 1;
 constexpr unsigned long long DESC_CODE_MASK = (1ull << 40) - 1;
 constexpr unsigned int FC_NONE = 0xffffffffu; // tile record: no CONST claim in the tile
+constexpr int EVW = 4;                        // class-change events one warp chunk can hold
+
+// named barriers: arrive without waiting / wait for all TPB threads
+__device__ __forceinline__ void bar_arrive(int id) {
+	__threadfence_block();
+	asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(TPB) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id) {
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPB) : "memory");
+}
 
 struct IAgg { // composed F-update in index form: F_out = isconst ? code : (F_in ? F_in : code)
 	bool isconst;
@@ -137,8 +147,9 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
 	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
-	__shared__ unsigned int s_evn;
-	__shared__ unsigned long long s_ev[EVK];
+	__shared__ unsigned int s_evn[WARPS];                 // per-warp event counters (no cross-warp init race)
+	__shared__ unsigned long long s_ev[WARPS][EVW];
+	__shared__ unsigned int s_leftclosed;                 // the claim before the tile is below target
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const unsigned long long t = blockIdx.x;
@@ -149,8 +160,9 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	const double target = p.target;
 	const long long tgt_ns = p.target_ns;
 	const unsigned int lt_mask = (1u << lane) - 1u;
-	if (tid == 0)
-		s_evn = 0;
+	if (lane == 0)
+		s_evn[warp] = 0;
+	__syncwarp();
 
 	// ---- loads: one 128-bit load per array per row (claims 2l, 2l+1) -----------------------
 	raw_t rs[ROWS][2], rn[ROWS][2];
@@ -315,14 +327,21 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	if (lane == 0) {
 		s_wagg[warp] = ((unsigned long long)wagg.isconst << 63) | wagg.code;
 		s_wfc[warp] = wfc;
+		if (warp == 0)
+			s_leftclosed = (t > 0 && !(prev_bits & 1u)) ? 1u : 0u;
 	}
-	__syncthreads();
-
-	// ---- CTA composition: what precedes this warp inside the tile (exclusive), index form -------
+	// Only warps whose leading claims inherit F from an earlier warp (and warp 0, which writes the
+	// tile's record) wait for the others; everybody else just signals and moves on.
+	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
+	const bool prev_above = have_prev && (prev_bits & 1u) && !(prev_bits & 2u);
+	const bool need_wex = (warp == 0) || first_is_pass || prev_above;
 	IAgg wex;
 	wex.isconst = false;
 	wex.code = CODE_ZERO;
-	{
+	bool left_closed = false;
+	if (need_wex) {
+		bar_sync(1);
+		left_closed = s_leftclosed != 0u;
 		int w = warp - 1;
 		for (; w >= 0; w--) { // nearest earlier warp with a CONST claim (usually the previous one)
 			const unsigned long long x = s_wagg[w];
@@ -336,6 +355,8 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 		}
 		if (w < 0 && warp > 0)
 			wex.code = s_wagg[0] & DESC_CODE_MASK; // all earlier warps are PASS: the first one's claim
+	} else {
+		bar_arrive(1);
 	}
 
 	// ---- the tile's record (thread 0): where the inherited run closes, what the tile leaves open
@@ -354,6 +375,8 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 			if (fc == FC_NONE && s_wfc[w] != FC_NONE)
 				fc = w * CHUNK + s_wfc[w];
 		}
+		if (left_closed)
+			fc = 0; // nothing crosses the tile's left edge: it anchors itself (resolve sees an empty stretch)
 		p.rec_fc[t] = fc;
 		p.rec_code[t] = tile_agg.code;
 		reinterpret_cast<raw_t *>(p.tile_now0)[t] = rn[0][0]; // thread 0 owns the tile's first claim
@@ -362,11 +385,15 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	// ---- phase 2: classes and events, FP64 only in rows with above-target claims ---------------
 	// `known`: F before the next claim is determined inside this tile.  Leading PASS claims of
 	// the tile (before its first CONST claim) are left to the resolve kernel.
-	bool known = wex.isconst;
-	const bool prev_ok_possible = known && have_prev && (prev_bits & 1u) && !(prev_bits & 2u);
-	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
+	// `known`: F before the chunk's first claim is determined inside this tile.
+	//   - an earlier warp of the tile has a CONST claim (wex.isconst), or
+	//   - the tile is left-closed (the claim before it is below target, so F is 0 at its edge and
+	//     the tile's first claim opens whatever run there is), or
+	//   - this warp needs nothing from before (its first claim is CONST-type, previous claim not ok)
+	bool known = wex.isconst || left_closed || !need_wex || (warp == 0 && !first_is_pass && !prev_above);
+	const bool prev_ok_possible = known && prev_above;
 	double F = 0.0; // F in force before the chunk's first claim (before its marker-before reset)
-	if (known && (first_is_pass || prev_ok_possible))
+	if ((wex.isconst || (left_closed && warp > 0)) && (first_is_pass || prev_ok_possible))
 		F = materialise<NS>(wex.code, p.now, nullptr); // never CODE_CARRY inside a tile
 	int c_last = 0; // class of the claim before the current row
 	if (prev_ok_possible && F != 0.0)
@@ -388,9 +415,9 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 		known = true;
 		if ((A0[r] | A1[r]) == 0u) { // nobody above target: every class is 0, F ends at 0
 			if (c_last != 0 && lane == 0) {
-				unsigned int pos = atomicAdd(&s_evn, 1u);
-				if (pos < EVK)
-					s_ev[pos] = (rbase << 2);
+				unsigned int pos = atomicAdd(&s_evn[warp], 1u);
+				if (pos < EVW)
+					s_ev[warp][pos] = (rbase << 2);
 			}
 			c_last = 0;
 			F = 0.0;
@@ -444,14 +471,14 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 		if (lane == 0)
 			cprev = c_last;
 		if (v0 && c0 != cprev) {
-			unsigned int pos = atomicAdd(&s_evn, 1u);
-			if (pos < EVK)
-				s_ev[pos] = ((rbase + 2 * lane) << 2) | (unsigned long long)c0;
+			unsigned int pos = atomicAdd(&s_evn[warp], 1u);
+			if (pos < EVW)
+				s_ev[warp][pos] = ((rbase + 2 * lane) << 2) | (unsigned long long)c0;
 		}
 		if (v1 && c1 != c0) {
-			unsigned int pos = atomicAdd(&s_evn, 1u);
-			if (pos < EVK)
-				s_ev[pos] = ((rbase + 2 * lane + 1) << 2) | (unsigned long long)c1;
+			unsigned int pos = atomicAdd(&s_evn[warp], 1u);
+			if (pos < EVW)
+				s_ev[warp][pos] = ((rbase + 2 * lane + 1) << 2) | (unsigned long long)c1;
 		}
 		// carry to the next row: state after the row's last valid claim
 		const int Lend = (nv[r] - 1) >> 1;
@@ -479,17 +506,36 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	}
 	if (nonmono)
 		p.b->nonmono = 1u;
-	__syncthreads();
-	if (tid == 0) {
-		unsigned int cnt = s_evn;
-		if (cnt > EVK) {
-			p.b->overflow = 1u;
+	// ---- flush: warp 0 gathers every warp's events into the tile's slots ------------------------
+	if (warp != 0) {
+		bar_arrive(2);
+		return;
+	}
+	bar_sync(2);
+	{
+		unsigned int cnt = 0;
+		bool over = false;
+#pragma unroll
+		for (int w = 0; w < WARPS; w++) {
+			const unsigned int cw = s_evn[w];
+			over |= cw > (unsigned int)EVW;
+			const unsigned int use = cw > (unsigned int)EVW ? (unsigned int)EVW : cw;
+			if ((unsigned int)lane < use) {
+				if (cnt + lane < (unsigned int)EVK)
+					p.ev[t * EVK + cnt + lane] = s_ev[w][lane];
+			}
+			cnt += use;
+		}
+		if (cnt > (unsigned int)EVK) {
+			over = true;
 			cnt = EVK;
 		}
-		p.ev_count[t] = cnt;
+		if (lane == 0) {
+			if (over)
+				p.b->overflow = 1u;
+			p.ev_count[t] = cnt;
+		}
 	}
-	if (tid < EVK && tid < s_evn)
-		p.ev[t * EVK + tid] = s_ev[tid];
 }
 
 } // namespace cb
