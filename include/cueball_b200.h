@@ -219,14 +219,15 @@ int cb_allreduce_counts(cb_ctx *ctx); /* async on the context's stream */
  * When enabled, every batch records events around each kernel; cb_profile_get
  * synchronises and returns accumulated milliseconds and launch counts. */
 #define CB_K_SCAN 0    /* pass 1: timestamps -> CoDel classes / events (reads 16 B/claim) */
-#define CB_K_RESOLVE 1 /* episode resolution (serial over episodes, tiny) */
+#define CB_K_RESOLVE 1 /* prepare + commit kernels: episode resolution (serial over episodes, tiny) */
 #define CB_K_EMIT 2    /* pass 3: decisions + slots (writes 5 B/claim) */
 #define CB_K_COUNT 3
 int cb_profile_enable(cb_ctx *ctx, int on);
 int cb_profile_get(cb_ctx *ctx, double ms_out[CB_K_COUNT], uint64_t launches_out[CB_K_COUNT]);
 uint64_t cb_launch_count(const cb_ctx *ctx); /* kernels launched so far by this context */
-/* %globaltimer stamps (ns) the resolve kernel of the last batch took at its phase boundaries:
- * [6] entry, [0] pairing, [1] run searches, [2] merge, [3] speculation, [4] serial chain, [5] done */
+/* %globaltimer stamps (ns) of the last batch's prepare / commit kernels at their phase boundaries:
+ * prepare [6] entry, [0] pairing, [1] run searches, [2] merge, [3] speculation, [4] end;
+ * commit [7] entry, [5] done */
 int cb_debug_timestamps(cb_ctx *ctx, uint64_t out[16]);
 
 #ifdef __cplusplus

@@ -48,6 +48,16 @@ struct BatchCtl {
 	unsigned int n_intervals;
 	unsigned int pad;
 	unsigned long long dbg[16];    // resolve-kernel phase timestamps (globaltimer ns), measurement only
+	// prepare kernel -> commit kernel
+	unsigned int nev_prep;         // events prepared (without the carried run's)
+	unsigned int cj_exists;        // the batch begins inside a stretch inherited from the previous batch
+	unsigned int cj_closes;        // ... and a CONST claim closes it inside this batch
+	unsigned int anchored;         // some tile of the batch fixes first_above_time
+	unsigned long long cj_close;   // index of the first claim after that stretch (n if it never closes)
+	double F_anchor;               // first_above_time after the batch when anchored
+	double now0p100;               // now[0] + 100
+	double E_val;                  // cd_last_empty if the batch carries an empty() marker
+	unsigned int hasE_new, trailing_marker;
 };
 
 constexpr unsigned ST_AGG = 1u, ST_PREFIX = 2u;

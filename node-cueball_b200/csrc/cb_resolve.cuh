@@ -1,31 +1,31 @@
-// cb_resolve.cuh -- pass 2: resolve the dropping episodes (one CTA).
+// cb_resolve.cuh -- pass 2: resolve the dropping episodes.  Two single-CTA kernels:
 //
-// Input: per tile, the class-change events the scan kernel found locally, plus the tile's
-// record (where the above-target run inherited from earlier tiles closes; what F the tile
-// leaves behind; the class of its last claim).
+// prepare_kernel  (independent of the ControlledDelay state -> overlaps freely with the
+//                 neighbouring batches of the pipeline)
+//   A  pairs every closing tile with the tile that opened the run (a block-wide max-scan over
+//      "last tile with a CONST claim") and evaluates the run's unclassified stretch: the class
+//      there is monotone in the clock, so its (at most two) crossings are lower_bound searches,
+//      one warp each.  This replaces a tile-to-tile look-back chain: a run spanning thousands of
+//      tiles costs two searches.  The stretch inherited from the PREVIOUS batch (it depends on
+//      the carried first_above_time) is only described, for the commit kernel.
+//   B  merges run events and local events into one ordered list (block scan).
+//   S  per event, speculates "first claim with now >= now_event + 100" (the drop_next a fresh
+//      episode would get, lib/codel.js:48-50,82) with a two-level search.
 //
-// Step A  pairs every closing tile with the tile that opened the run (a block-wide max-scan
-//         over "last tile with a CONST claim") and evaluates the run's unclassified stretch:
-//         the class there is monotone in the clock, so its (at most two) crossings are
-//         lower_bound searches, done by one warp per long run.  This is what replaces a
-//         tile-to-tile look-back chain: a run spanning thousands of tiles costs two searches.
-// Step B  merges run events and local events into one ordered list (block scan).
-// Step C  Between two events every claim has the same canDrop class, so
-//         ControlledDelay#overloaded (lib/codel.js:56-86) acts on a whole stretch in closed form:
-//           class 0 stretch        : cd_dropping := false, nothing dropped
-//           class>0, dropping      : claims with now >= cd_drop_next are dropped (a suffix: the
-//                                    clock is monotone) and counted            codel.js:65-68
-//           class>0, not dropping  : the state is entered at the stretch's FIRST claim iff
-//                                    class==2 or now - drop_next < 100          codel.js:70-83
-//         so the sequential recurrence over (drop_next, count, dropping) runs over EVENTS (a few
-//         per 100 ms of stream), not over claims.  Its only non-O(1) step, "first claim with
-//         now >= drop_next", is a lower_bound on the monotone clock; all of them are speculated
-//         in parallel (one warp per event, assuming count==1 on entry, which is what a monotone
-//         clock produces except for a rounding coincidence) before the serial chain runs.
+// commit_kernel   (the only part serial across batches: a few microseconds)
+//   resolves the carried stretch (if the batch begins inside a run), then runs
+//   ControlledDelay#overloaded (lib/codel.js:56-86) over EVENTS, not claims: between two events
+//   every claim has the same canDrop class, so a whole stretch is handled in closed form
+//       class 0 stretch        : cd_dropping := false, nothing dropped
+//       class>0, dropping      : claims with now >= cd_drop_next are dropped (a suffix: the clock
+//                                is monotone) and counted                     codel.js:65-68
+//       class>0, not dropping  : the state is entered at the stretch's FIRST claim iff
+//                                class==2 or now - drop_next < 100             codel.js:70-83
+//   and writes the drop intervals plus the new ControlledDelay state.
 //
 // If the clock went backwards inside the batch (or a tile overflowed its event slots) the
-// decomposition does not apply and warp 0 runs the exact per-claim state machine instead
-// (CB_PATH_SEQUENTIAL), writing the outputs itself.
+// decomposition does not apply and one warp of the commit kernel runs the exact per-claim state
+// machine instead (CB_PATH_SEQUENTIAL), writing the outputs itself.
 #pragma once
 #include "cb_device.cuh"
 #include "cb_scan.cuh"
@@ -46,6 +46,7 @@ struct ResolveParams {
 	const unsigned long long *rec_code;
 	const unsigned int *rec_cend;
 	const void *tile_now0;              // raw clock of every tile's first claim (coarse search index)
+	double *idx_ms;                     // [<= NIDX_MAX] the coarse index in ms (prepare -> commit)
 	// cross-tile run events (<= 3 per closing tile; slot `tiles` = the run open at batch end)
 	unsigned long long *xev;            // [(tiles+1)*3]
 	unsigned int *xcnt;                 // [tiles+1]
@@ -262,13 +263,12 @@ constexpr int RT = 8;          // tile slots per thread per pass (8192 per pass)
 constexpr int NIDX_MAX = 8192; // coarse clock index entries kept in shared memory (64 KB)
 constexpr int SEV_MAX = 1024;  // events kept in shared memory for the serial chain (32 KB)
 
+constexpr int EV_FRONT = 3;    // slots kept free in front of the event list for the carried run's events
+constexpr int CTPB = 128;      // threads of the commit kernel
+
 template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p) {
+__global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p) {
 	extern __shared__ __align__(16) double s_idx[]; // clock (ms) at claim k*G, k < nidx
-	// the event list and its per-event speculation live in shared memory when they fit, so the
-	// serial chain (thread 0) never waits on global memory
-	__shared__ unsigned long long s_evc[SEV_MAX], s_evq[SEV_MAX], s_evd[SEV_MAX];
-	__shared__ double s_evnow[SEV_MAX];
 	__shared__ unsigned int s_warp[32];
 	__shared__ int s_wmax[32];
 	__shared__ unsigned int s_base;
@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	__shared__ long long s_prevconst; // last tile with a CONST claim seen so far (-1: none)
 	__shared__ unsigned int s_nheavy;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	DevState *g = p.g;
 	BatchCtl *bc = p.bc;
 	using raw_t = typename TimeIn<NS>::raw_t;
 	if (tid == 0)
@@ -294,15 +293,20 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		s_prevconst = -1;
 		s_nheavy = 0;
 	}
-	for (unsigned int k = tid; k < nidx; k += RTPB)
-		s_idx[k] = TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(p.tile_now0)[(unsigned long long)k * stride]);
-	__syncthreads();
-	if (s_fallback) {
-		if (warp == 0)
-			sequential_path<NS>(p, lane);
-		return;
+	for (unsigned int k = tid; k < nidx; k += RTPB) {
+		const double v = TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(p.tile_now0)[(unsigned long long)k * stride]);
+		s_idx[k] = v;
+		p.idx_ms[k] = v; // the commit kernel searches the same index (from L2)
 	}
-	const unsigned long long carry_code = (g->F != 0.0) ? CODE_CARRY : CODE_ZERO;
+	__syncthreads();
+	if (s_fallback)
+		return; // the commit kernel runs the exact sequential path
+	const unsigned long long carry_code = CODE_CARRY; // the carried first_above_time is the commit kernel's business
+	if (tid == 0) {
+		bc->cj_exists = 0;
+		bc->cj_close = 0;
+		bc->cj_closes = 0;
+	}
 
 	if (tid == 0) bc->dbg[0] = gtimer();
 	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
@@ -365,11 +369,16 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			stretch[k] = (fc[k] != FC_NONE) && (lo < close_idx);
 			Fv[k] = 0.0;
 			nb[k] = 0.0;
+			if (stretch[k] && code0[k] == CODE_CARRY) { // inherited from the previous batch: commit's job
+				stretch[k] = false;
+				bc->cj_exists = 1;
+				bc->cj_close = close_idx;
+				bc->cj_closes = (t0 + k == p.tiles) ? 0u : 1u;
+				code0[k] = CODE_ZERO;
+				cend0[k] = 4u; // marks "carried": no close event from here either
+			}
 			if (stretch[k]) {
-				if (code0[k] == CODE_CARRY)
-					Fv[k] = g->F;
-				else
-					Fv[k] = __dadd_rn(now_at<NS>(p.now, code0[k] == CODE_ZERO ? lo : code0[k] - 2), CODEL_INTERVAL);
+				Fv[k] = __dadd_rn(now_at<NS>(p.now, code0[k] == CODE_ZERO ? lo : code0[k] - 2), CODEL_INTERVAL);
 				nb[k] = now_at<NS>(p.now, close_idx - 1);
 			}
 		}
@@ -390,11 +399,11 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 						p.hj_lo[h] = (unsigned long long)(T0[k] + 1) * TILE;
 						p.hj_b[h] = close_idx - 1;
 						p.hj_F[h] = Fv[k];
-						p.hj_info[h] = (unsigned int)(t0 + k) | (cend0[k] << 28) | ((unsigned int)cb << 30);
+						p.hj_info[h] = (unsigned int)(t0 + k) | ((cend0[k] & 3u) << 28) | ((unsigned int)cb << 30);
 						final_c = cb;
 					}
 				}
-				if (final_c >= 1 && !is_tail) { // the run ends at a CONST claim (class 0)
+				if (final_c >= 1 && final_c < 4 && !is_tail) { // the run ends at a CONST claim (class 0)
 					p.xev[(t0 + k) * 3 + 2] = (close_idx << 2);
 					bits = 4u;
 				}
@@ -485,12 +494,12 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			for (int k = 0; k < RT; k++) {
 				const unsigned long long t = t0 + k;
 				// run events of the tile's close come first (crossings <= close index <= local events)
-				if ((xb[k] & 1u) && off < p.ev_cap)
-					p.evc[off++] = p.xev[t * 3 + 0];
-				if ((xb[k] & 2u) && off < p.ev_cap)
-					p.evc[off++] = p.xev[t * 3 + 1];
-				if ((xb[k] & 4u) && off < p.ev_cap)
-					p.evc[off++] = p.xev[t * 3 + 2];
+				if ((xb[k] & 1u) && off + EV_FRONT < p.ev_cap)
+					p.evc[EV_FRONT + off++] = p.xev[t * 3 + 0];
+				if ((xb[k] & 2u) && off + EV_FRONT < p.ev_cap)
+					p.evc[EV_FRONT + off++] = p.xev[t * 3 + 1];
+				if ((xb[k] & 4u) && off + EV_FRONT < p.ev_cap)
+					p.evc[EV_FRONT + off++] = p.xev[t * 3 + 2];
 				if (lc[k]) {
 					// a tile's events were appended unordered: sort its <= EVK entries by index
 					unsigned long long e[EVK];
@@ -510,8 +519,8 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 					}
 #pragma unroll
 					for (int j = 0; j < EVK; j++)
-						if (j < (int)lc[k] && off < p.ev_cap)
-							p.evc[off++] = e[j];
+						if (j < (int)lc[k] && off + EV_FRONT < p.ev_cap)
+							p.evc[EV_FRONT + off++] = e[j];
 				}
 			}
 		}
@@ -521,21 +530,15 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		__syncthreads();
 	}
 	const unsigned int nev = s_base;
+	if (nev + EV_FRONT > p.ev_cap) // cannot happen with ev_cap = (tiles+1)*(EVK+3)+EV_FRONT
+		return;
 
 	if (tid == 0) bc->dbg[3] = gtimer();
 	// ---- 2. per event (one warp each): run end q, now at the event, speculated drop start
-	const bool ev_smem = nev <= SEV_MAX;
-	unsigned long long *evc = ev_smem ? s_evc : p.evc;
-	unsigned long long *ev_q = ev_smem ? s_evq : p.ev_q;
-	unsigned long long *ev_d = ev_smem ? s_evd : p.ev_d;
-	double *ev_now = ev_smem ? s_evnow : p.ev_now;
-	if (ev_smem) {
-		for (unsigned int k = tid; k < nev; k += RTPB)
-			s_evc[k] = p.evc[k];
-		__syncthreads();
-	}
-	const double D_in = g->D;
-	const int B_in = g->B;
+	unsigned long long *evc = p.evc + EV_FRONT;
+	unsigned long long *ev_q = p.ev_q + EV_FRONT;
+	unsigned long long *ev_d = p.ev_d + EV_FRONT;
+	double *ev_now = p.ev_now + EV_FRONT;
 	for (unsigned int k = warp; k < nev; k += RTPB / 32) {
 		const unsigned long long w = evc[k];
 		const unsigned long long w1 = (k + 1 < nev) ? evc[k + 1] : 3ull, w2 = (k + 2 < nev) ? evc[k + 2] : 3ull;
@@ -553,13 +556,8 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		unsigned long long d;
 		Pred pr;
 		pr.level = 0;
-		if (k == 0 && idx == 0 && B_in) { // batch opens inside a dropping episode
-			pr.x = D_in;
-			d = warp_search<NS>(p.now, s_idx, G, idx, q + 1, pr, lane);
-		} else {
-			pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
-			d = warp_search<NS>(p.now, s_idx, G, idx + 1, q + 1, pr, lane);
-		}
+		pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
+		d = warp_search<NS>(p.now, s_idx, G, idx + 1, q + 1, pr, lane);
 		if (lane == 0) {
 			ev_now[k] = nowk;
 			ev_q[k] = q;
@@ -569,6 +567,145 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 	__syncthreads();
 
 	if (tid == 0) bc->dbg[4] = gtimer();
+	// ---- hand-over to the commit kernel ---------------------------------------------------------
+	if (tid == 0) {
+		bc->nev_prep = nev;
+		// F after the batch's last claim when some tile fixes it inside the batch: the last tile with
+		// a CONST claim decides, later (all PASS) tiles inherit or, if it is 0, the first of them
+		// opens the run
+		const long long Tl = s_prevconst;
+		bc->anchored = (Tl >= 0) ? 1u : 0u;
+		double F = 0.0;
+		if (Tl >= 0) {
+			const unsigned long long code0 = p.rec_code[Tl];
+			if (code0 != CODE_ZERO)
+				F = __dadd_rn(now_at<NS>(p.now, code0 - 2), CODEL_INTERVAL);
+			else if ((unsigned long long)(Tl + 1) < p.tiles)
+				F = __dadd_rn(now_at<NS>(p.now, (unsigned long long)(Tl + 1) * TILE), CODEL_INTERVAL);
+		}
+		bc->F_anchor = F;
+		bc->now0p100 = __dadd_rn(now_at<NS>(p.now, 0), CODEL_INTERVAL);
+		bc->hasE_new = 0;
+		bc->trailing_marker = 0;
+		if (FLAGS) {
+			const unsigned long long lm = bc->last_marker_p1;
+			if (lm) {
+				bc->E_val = now_at<NS>(p.now, lm - 1); // lib/codel.js:92
+				bc->hasE_new = 1;
+				bc->trailing_marker = (lm == p.n) ? 1u : 0u;
+			}
+			bc->last_marker_p1 = 0;
+		}
+		bc->dbg[4] = gtimer();
+	}
+}
+
+// The commit kernel: everything that depends on the ControlledDelay state carried from the
+// previous batch.  One small CTA; runs strictly in batch order.
+template <bool NS, bool FLAGS>
+__global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) {
+	__shared__ unsigned long long s_evc[SEV_MAX], s_evq[SEV_MAX], s_evd[SEV_MAX];
+	__shared__ double s_evnow[SEV_MAX];
+	__shared__ unsigned int s_ncar;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	DevState *g = p.g;
+	BatchCtl *bc = p.bc;
+	if (tid == 0)
+		bc->dbg[7] = gtimer();
+	if ((bc->nonmono != 0u) || (bc->overflow != 0u)) {
+		if (warp == 0)
+			sequential_path<NS>(p, lane);
+		return;
+	}
+	const unsigned int nevp = bc->nev_prep;
+	const bool ev_smem = nevp + EV_FRONT <= SEV_MAX;
+	unsigned long long *evc = ev_smem ? s_evc : p.evc;
+	unsigned long long *ev_q = ev_smem ? s_evq : p.ev_q;
+	unsigned long long *ev_d = ev_smem ? s_evd : p.ev_d;
+	double *ev_now = ev_smem ? s_evnow : p.ev_now;
+	if (ev_smem) {
+		for (unsigned int k = tid; k < nevp; k += CTPB) {
+			s_evc[EV_FRONT + k] = p.evc[EV_FRONT + k];
+			s_evq[EV_FRONT + k] = p.ev_q[EV_FRONT + k];
+			s_evd[EV_FRONT + k] = p.ev_d[EV_FRONT + k];
+			s_evnow[EV_FRONT + k] = p.ev_now[EV_FRONT + k];
+		}
+	}
+	if (tid == 0)
+		s_ncar = 0;
+	const double F_in = g->F, D_in = g->D;
+	const int B_in = g->B;
+	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
+	const unsigned long long G = stride * TILE;
+	__syncthreads();
+
+	// ---- the stretch inherited from the previous batch (claims [0, close) are all above target) --
+	if (bc->cj_exists) {
+		const unsigned long long close = bc->cj_close;
+		const double F = (F_in != 0.0) ? F_in : bc->now0p100; // F == 0: claim 0 opens the run itself
+		const int cb = claim_class(true, now_at<NS>(p.now, close - 1), F);
+		// crossings: warp 0 -> first class >= 1, warp 1 -> first class 2 (independent searches)
+		if (cb >= 1 && warp < 2 && (warp == 0 || cb == 2)) {
+			Pred pr;
+			pr.x = F;
+			pr.level = warp + 1;
+			const unsigned long long pos = warp_search<NS>(p.now, p.idx_ms, G, 0, close, pr, lane);
+			if (warp == 0) {
+				const int c = claim_class(true, now_at<NS>(p.now, pos), F);
+				if (lane == 0)
+					evc[0] = (pos << 2) | (unsigned long long)c; // staged at slot 0, compacted below
+			} else {
+				bool separate = pos > 0 && claim_class(true, now_at<NS>(p.now, pos - 1), F) >= 1;
+				if (lane == 0)
+					evc[1] = separate ? ((pos << 2) | 2ull) : ~0ull;
+			}
+		}
+		__syncthreads();
+		if (tid == 0) {
+			// compact into [EV_FRONT - ncar, EV_FRONT): crossing(s), then the close event
+			unsigned long long tmp[3];
+			unsigned int nc = 0;
+			if (cb >= 1) {
+				tmp[nc++] = evc[0];
+				if (cb == 2 && evc[1] != ~0ull)
+					tmp[nc++] = evc[1];
+				if (bc->cj_closes)
+					tmp[nc++] = (close << 2);
+			}
+			for (unsigned int k = 0; k < nc; k++)
+				evc[EV_FRONT - nc + k] = tmp[k];
+			s_ncar = nc;
+		}
+		__syncthreads();
+		// speculation for the carried run's events (one warp each)
+		const unsigned int nc = s_ncar;
+		if ((unsigned int)warp < nc) {
+			const unsigned int k = EV_FRONT - nc + warp;
+			const unsigned long long w = evc[k];
+			const int c = (int)(w & 3ull);
+			if (c != 0) {
+				const unsigned long long idx = w >> 2, q = close - 1;
+				const double nowk = now_at<NS>(p.now, idx);
+				Pred pr;
+				pr.level = 0;
+				unsigned long long d;
+				if (warp == 0 && idx == 0 && B_in) { // the batch opens inside a dropping episode
+					pr.x = D_in;
+					d = warp_search<NS>(p.now, p.idx_ms, G, idx, q + 1, pr, lane);
+				} else {
+					pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
+					d = warp_search<NS>(p.now, p.idx_ms, G, idx + 1, q + 1, pr, lane);
+				}
+				if (lane == 0) {
+					ev_now[k] = nowk;
+					ev_q[k] = q;
+					ev_d[k] = d;
+				}
+			}
+		}
+		__syncthreads();
+	}
+
 	// ---- 3. the serial chain over events (thread 0) -----------------------------------
 	if (tid == 0) {
 		double D = g->D;
@@ -576,9 +713,10 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		int B = g->B;
 		unsigned long long drops = 0;
 		unsigned int niv = 0;
-		if (nev == 0 || (evc[0] >> 2) > 0)
+		const unsigned int k0 = EV_FRONT - s_ncar, nev = EV_FRONT + nevp;
+		if (k0 == nev || (evc[k0] >> 2) > 0)
 			B = 0; // the batch starts with class-0 claims
-		unsigned int k = 0;
+		unsigned int k = k0;
 		while (k < nev) {
 			const unsigned long long w = evc[k];
 			const int c = (int)(w & 3ull);
@@ -638,30 +776,18 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 			k += has2 ? 2 : 1;
 		}
 		// ---- final ControlledDelay state -------------------------------------------------
-		// F after the batch's last claim: the last tile with a CONST claim fixes it, later (all
-		// PASS) tiles inherit it or, if it is 0, the first of them opens the run
 		double F;
-		{
-			const long long Tl = s_prevconst;
-			const unsigned long long code0 = (Tl < 0) ? carry_code : p.rec_code[Tl];
-			if (code0 == CODE_CARRY)
-				F = g->F;
-			else if (code0 != CODE_ZERO)
-				F = __dadd_rn(now_at<NS>(p.now, code0 - 2), CODEL_INTERVAL);
-			else if ((unsigned long long)(Tl + 1) < p.tiles)
-				F = __dadd_rn(now_at<NS>(p.now, (unsigned long long)(Tl + 1) * TILE), CODEL_INTERVAL);
-			else
-				F = 0.0;
-		}
+		if (bc->anchored)
+			F = bc->F_anchor;
+		else // the whole batch is one above-target run without a reset: F is inherited, or opened by claim 0
+			F = (F_in != 0.0) ? F_in : bc->now0p100;
 		if (FLAGS) {
-			const unsigned long long lm = bc->last_marker_p1;
-			if (lm) {
-				g->E = now_at<NS>(p.now, lm - 1);
+			if (bc->hasE_new) {
+				g->E = bc->E_val;
 				g->hasE = 1;
-				if (lm == p.n)
+				if (bc->trailing_marker)
 					F = 0.0; // trailing empty(): lib/codel.js:93
 			}
-			bc->last_marker_p1 = 0;
 		}
 		bc->dbg[5] = gtimer();
 		g->F = F;
@@ -670,7 +796,7 @@ __global__ void __launch_bounds__(RTPB, 1) resolve_kernel(const ResolveParams p)
 		g->B = B;
 		bc->n = p.n;
 		bc->path = 0;
-		bc->n_events = nev;
+		bc->n_events = nev - k0;
 		bc->n_intervals = niv;
 		bc->gcounts[2] = p.n;
 		bc->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)

@@ -71,8 +71,9 @@ struct Lane {
 	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr, *tile_now0 = nullptr;
 	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
-	double *ev_now = nullptr, *hj_F = nullptr;
-	cudaEvent_t scan_done = nullptr, res_done = nullptr, emit_done = nullptr, coll_done = nullptr;
+	double *ev_now = nullptr, *hj_F = nullptr, *idx_ms = nullptr;
+	cudaStream_t st_prep = nullptr; // this lane's prepare kernel (independent of the other lanes')
+	cudaEvent_t scan_done = nullptr, prep_done = nullptr, res_done = nullptr, emit_done = nullptr, coll_done = nullptr;
 	bool used = false, coll_pending = false;
 	unsigned long long epoch = 0;
 };
@@ -155,6 +156,8 @@ template <typename T> int dev_alloc(cb_ctx *c, T **p, size_t count) {
 // wait for every batch in flight (and the main stream)
 int drain(cb_ctx *c) {
 	CU(c, cudaStreamSynchronize(c->st_scan));
+	for (int l = 0; l < CB_LANES; l++)
+		CU(c, cudaStreamSynchronize(c->lane[l].st_prep));
 	CU(c, cudaStreamSynchronize(c->st_res));
 	CU(c, cudaStreamSynchronize(c->st_emit));
 	CU(c, cudaStreamSynchronize(c->st_coll));
@@ -172,7 +175,7 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 			CU(c, cudaEventSynchronize(L.coll_done));
 	}
 	size_t cap = tiles + tiles / 4 + 64;
-	const size_t evcap = (cap + 1) * (EVK + 3);
+	const size_t evcap = (cap + 1) * (EVK + 3) + EV_FRONT;
 	int rc;
 	if ((rc = dev_alloc(c, &L.sdesc, cap)) || (rc = dev_alloc(c, &L.ev_count, cap)) ||
 	    (rc = dev_alloc(c, &L.ev, cap * EVK)) || (rc = dev_alloc(c, &L.rec_fc, cap)) ||
@@ -184,6 +187,8 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 	    (rc = dev_alloc(c, &L.ev_q, evcap)) || (rc = dev_alloc(c, &L.ev_d, evcap)) ||
 	    (rc = dev_alloc(c, &L.ev_now, evcap)) || (rc = dev_alloc(c, &L.iv_lo, evcap + 8)) ||
 	    (rc = dev_alloc(c, &L.iv_hi, evcap + 8)) || (rc = dev_alloc(c, &L.iv_cum, evcap + 8)))
+		return rc;
+	if (!L.idx_ms && (rc = dev_alloc(c, &L.idx_ms, NIDX_MAX)))
 		return rc;
 	// the emit kernel's sum descriptors carry an epoch tag, so they only need zeroing once
 	CU(c, cudaMemset(L.sdesc, 0, cap * sizeof(SumDesc)));
@@ -244,6 +249,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.rec_code = L.rec_code;
 	rp.rec_cend = L.rec_cend;
 	rp.tile_now0 = L.tile_now0;
+	rp.idx_ms = L.idx_ms;
 	rp.xev = L.xev;
 	rp.xcnt = L.xcnt;
 	rp.hj_lo = L.hj_lo;
@@ -256,7 +262,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.ev_now = L.ev_now;
 	rp.ev_q = L.ev_q;
 	rp.ev_d = L.ev_d;
-	rp.ev_cap = (tiles + 1) * (EVK + 3);
+	rp.ev_cap = (tiles + 1) * (EVK + 3) + EV_FRONT;
 	rp.iv_lo = L.iv_lo;
 	rp.iv_hi = L.iv_hi;
 	rp.iv_cum = L.iv_cum;
@@ -317,17 +323,28 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s_scan));
+	// prepare: independent of the ControlledDelay state -> its own stream, overlaps other lanes
+	cudaStream_t s_prep = piped ? L.st_prep : c->stream;
 	if (piped) {
 		CU(c, cudaEventRecord(L.scan_done, s_scan));
-		CU(c, cudaStreamWaitEvent(s_res, L.scan_done, 0));
-		// a flags batch finishes its cursor/totals in its emit kernel: the next resolve needs them
+		CU(c, cudaStreamWaitEvent(s_prep, L.scan_done, 0));
+	}
+	if (flags)
+		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s_prep>>>(rp);
+	else
+		prepare_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s_prep>>>(rp);
+	// commit: the only stage that is serial across batches (stream order on st_res)
+	if (piped) {
+		CU(c, cudaEventRecord(L.prep_done, s_prep));
+		CU(c, cudaStreamWaitEvent(s_res, L.prep_done, 0));
+		// a flags batch finishes its cursor/totals in its emit kernel: the next commit needs them
 		if (c->last_flags && c->last_lane >= 0 && c->last_lane != li)
 			CU(c, cudaStreamWaitEvent(s_res, c->lane[c->last_lane].emit_done, 0));
 	}
 	if (flags)
-		resolve_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s_res>>>(rp);
+		commit_kernel<NS, true><<<1, CTPB, 0, s_res>>>(rp);
 	else
-		resolve_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s_res>>>(rp);
+		commit_kernel<NS, false><<<1, CTPB, 0, s_res>>>(rp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[2], s_res));
 	if (piped) {
@@ -338,7 +355,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s_emit>>>(ep);
 	else
 		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s_emit>>>(ep);
-	c->launches += 3;
+	c->launches += 4;
 	CU(c, cudaGetLastError());
 	CU(c, cudaEventRecord(L.emit_done, s_emit));
 	L.used = true;
@@ -614,6 +631,8 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		CU0(cudaMemset(L.ticket, 0, 64));
 		CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.res_done, cudaEventDisableTiming));
+		CU0(cudaEventCreateWithFlags(&L.prep_done, cudaEventDisableTiming));
+		CU0(cudaStreamCreateWithFlags(&L.st_prep, cudaStreamNonBlocking));
 		CU0(cudaEventCreateWithFlags(&L.emit_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.coll_done, cudaEventDisableTiming));
 	}
@@ -622,10 +641,10 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	CU0(cudaMalloc((void **)&c->d_dbl, 64 * sizeof(double)));
 	for (int k = 0; k < 4; k++)
 		CU0(cudaEventCreate(&c->pe[k]));
-	CU0(cudaFuncSetAttribute(resolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(resolve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(resolve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(prepare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(prepare_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(prepare_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 #undef CU0
@@ -645,12 +664,16 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		g_nccl.CommDestroy(c->comm);
 	for (int l = 0; l < CB_LANES; l++) {
 		Lane &L = c->lane[l];
-		void *fr[] = {L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
+		if (L.st_prep) {
+			cudaStreamSynchronize(L.st_prep);
+			cudaStreamDestroy(L.st_prep);
+		}
+		void *fr[] = {L.idx_ms, L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
 		    L.ev_q, L.ev_d, L.rec_code, L.xev, L.hj_lo, L.hj_b, L.tile_now0, L.iv_lo, L.iv_hi, L.iv_cum, L.ev_now, L.hj_F};
 		for (void *p : fr)
 			if (p)
 				cudaFree(p);
-		cudaEvent_t evs[] = {L.scan_done, L.res_done, L.emit_done, L.coll_done};
+		cudaEvent_t evs[] = {L.scan_done, L.prep_done, L.res_done, L.emit_done, L.coll_done};
 		for (cudaEvent_t e : evs)
 			if (e)
 				cudaEventDestroy(e);

@@ -18,12 +18,12 @@ dev = torch.device("cuda:0")
 ds, dn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
 dd = torch.empty(n * 4, dtype=torch.uint8, device=dev)
 sl = torch.empty(n * 4, dtype=torch.int32, device=dev)
-names = ["entry->pair", "pair->search", "search->merge", "merge->spec", "spec->chain", "chain->done"]
+names = ["prep:entry->pair", "pair->search", "search->merge", "merge->spec", "spec->end", "(gap)", "commit"]
 for b in range(4):
     lo, hi = b * n, (b + 1) * n
     ctx.admit_batch_dev(ds[lo:hi], dn[lo:hi], None, dd[lo:hi], sl[lo:hi])
     t = ctx.debug_timestamps()
-    seq = [t[6], t[0], t[1], t[2], t[3], t[4], t[5]]
+    seq = [t[6], t[0], t[1], t[2], t[3], t[4], t[7], t[5]]
     st = ctx.stats()
     print(wl, "batch", b, "events", st.n_events, "intervals", st.n_intervals,
           " ".join("%s=%.1fus" % (nm, (seq[i + 1] - seq[i]) / 1e3) for i, nm in enumerate(names)),
