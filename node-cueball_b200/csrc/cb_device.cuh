@@ -7,9 +7,8 @@
 
 namespace cb {
 
-constexpr int TPB = 512;        // threads per CTA in the streaming kernels
-constexpr int IPT = 8;          // consecutive claims per thread
-constexpr int TILE = TPB * IPT; // 4096 claims per tile
+constexpr int TILE = 4096;       // claims per tile (scan, prepare and emit agree on it)
+constexpr int TPB = 1024;        // threads of a scan CTA: 32 warps x 128 claims
 constexpr int WARPS = TPB / 32;
 constexpr int EVK = 8;          // class-change events a tile can hold before "overflow"
 constexpr double CODEL_INTERVAL = 100.0; // lib/codel.js:16
