@@ -43,7 +43,8 @@ namespace cb {
 
 constexpr int ROWS = 2;            // rows of 64 claims per warp chunk
 constexpr int CHUNK = ROWS * 64;   // 128 claims per warp
-constexpr int NSTAGE = 2;          // TMA ring depth (tiles in flight per CTA)
+constexpr int NSTAGE = 3;          // TMA ring depth (tiles in flight per CTA: 192 KB of the SM's 227 KB)
+constexpr int NSCR = NSTAGE + 1;   // depth of the per-tile scratch / named-barrier rotation
 constexpr int STAGE_BYTES = TILE * 16; // start (32 KB) + now (32 KB) of one tile
 constexpr int SCAN_SMEM = NSTAGE * STAGE_BYTES;
 static_assert(CHUNK * WARPS == TILE, "tile geometry");
@@ -183,13 +184,14 @@ __global__ void __launch_bounds__(TPB, 1) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	extern __shared__ __align__(128) unsigned char s_ring[]; // NSTAGE x (start | now) of one tile
 	__shared__ __align__(8) unsigned long long s_full[NSTAGE];
-	// per-tile scratch is double-buffered by tile parity: fast warps already work on the next tile
-	// while warp 0 still flushes the previous one
-	__shared__ unsigned long long s_wagg2[2][WARPS];       // isconst << 63 | code
-	__shared__ unsigned int s_wfc2[2][WARPS];              // chunk-local position of the warp's first CONST claim
-	__shared__ unsigned int s_evn2[2][WARPS];              // per-warp event counters
-	__shared__ unsigned long long s_ev2[2][WARPS][EVW];
-	__shared__ unsigned int s_leftclosed2[2];              // the claim before the tile is below target
+	// per-tile scratch rotates over NSCR buffers: fast warps run up to NSTAGE tiles ahead of warp 0's
+	// flush (tile it+NSTAGE is requested once every warp has passed barrier 1 of tile it, and warp 0
+	// reaches barrier 1 of tile it+1 only after flushing tile it)
+	__shared__ unsigned long long s_wagg2[NSCR][WARPS];    // isconst << 63 | code
+	__shared__ unsigned int s_wfc2[NSCR][WARPS];           // chunk-local position of the warp's first CONST claim
+	__shared__ unsigned int s_evn2[NSCR][WARPS];           // per-warp event counters
+	__shared__ unsigned long long s_ev2[NSCR][WARPS][EVW];
+	__shared__ unsigned int s_leftclosed2[NSCR];           // the claim before the tile is below target
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(TPB, 1) scan_kernel(const ScanParams p) {
 
 	unsigned int it = 0;
 	for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-	const int par = it & 1;                 // tile parity: scratch buffer and barrier ids
+	const int par = it % NSCR;              // scratch buffer and barrier ids of this tile
 	const int stage = it % NSTAGE;
 	const unsigned int ring_parity = (it / NSTAGE) & 1u;
 	unsigned long long *s_wagg = s_wagg2[par];
@@ -423,6 +425,13 @@ __global__ void __launch_bounds__(TPB, 1) scan_kernel(const ScanParams p) {
 	bool left_closed = false;
 	if (need_wex) {
 		bar_sync(BAR1);
+		if (tid == 0) {
+			// every warp has copied its rows out of this ring stage: refill it with the tile this CTA
+			// will process NSTAGE iterations from now (overlaps the rest of this tile and the next ones)
+			const unsigned long long tn = t + (unsigned long long)NSTAGE * gridDim.x;
+			if (tn < nfull)
+				tma_request<raw_t>(s_ring + stage * STAGE_BYTES, &s_full[stage], gstart, gnow, tn);
+		}
 		left_closed = s_leftclosed2[par] != 0u;
 		int w = warp - 1;
 		for (; w >= 0; w--) { // nearest earlier warp with a CONST claim (usually the previous one)
@@ -614,11 +623,6 @@ __global__ void __launch_bounds__(TPB, 1) scan_kernel(const ScanParams p) {
 			if (over)
 				p.b->overflow = 1u;
 			p.ev_count[t] = cnt;
-			// every warp has passed its last read of this ring stage: refill it with the tile this
-			// CTA will process NSTAGE iterations from now
-			const unsigned long long tn = t + (unsigned long long)NSTAGE * gridDim.x;
-			if (tn < nfull)
-				tma_request<raw_t>(s_ring + stage * STAGE_BYTES, &s_full[stage], gstart, gnow, tn);
 		}
 	}
 	// Without the TMA ring nothing stops a fast warp from lapping the named barriers of a slower
