@@ -22,11 +22,11 @@ namespace cb {
 
 constexpr int ETPB = 256;               // threads per emit CTA
 constexpr int EGW = 4;                  // consecutive claims per group
-constexpr int EG = TILE / (ETPB * EGW); // groups per thread per tile (4)
+constexpr int EG = ETILE / (ETPB * EGW); // groups per thread per tile (4)
 constexpr int ESTR = ETPB * EGW;        // 1024: group g of thread t starts at ts + g*ESTR + t*EGW
 constexpr int EWARPS = ETPB / 32;
 constexpr int IVS_MAX = 64;             // interval lists up to this length are staged in shared memory
-static_assert(EG * ESTR == TILE, "emit geometry");
+static_assert(EG * ESTR == ETILE, "emit geometry");
 
 struct EmitParams {
 	const uint8_t *flags;
@@ -149,11 +149,11 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	bool table_ready = false;
 
 	for (unsigned long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-		const unsigned long long ts = t * (unsigned long long)TILE;
-		unsigned long long te = ts + TILE;
+		const unsigned long long ts = t * (unsigned long long)ETILE;
+		unsigned long long te = ts + ETILE;
 		if (te > p.n)
 			te = p.n;
-		const bool full_tile = (te - ts) == (unsigned long long)TILE;
+		const bool full_tile = (te - ts) == (unsigned long long)ETILE;
 
 		// ---- classify the tile against the interval list (warp-uniform) -----------------------
 		unsigned int kase = 0, jtile = 0;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 				int4 sv = make_int4(-1, -1, -1, -1), bv = make_int4(-1, -1, -1, -1);
 				if (kase == 0 && S > 0) {
 					unsigned int s0 = base + q4 * EGW;
-					if (S >= (unsigned int)TILE + EGW) { // at most one wrap inside the tile
+					if (S >= (unsigned int)ETILE + EGW) { // at most one wrap inside the tile
 						if (s0 >= S)
 							s0 -= S;
 					} else {

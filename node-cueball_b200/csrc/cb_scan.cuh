@@ -14,10 +14,10 @@
 // INDICES (integer-only, one 64-bit look-back descriptor per tile) and turned into doubles
 // only where a claim's class needs the value.
 //
-// Layout: persistent CTAs (one per SM, 32 warps) stride over tiles of 4096 consecutive claims;
+// Layout: persistent CTAs (two per SM, 16 warps each) stride over tiles of 2048 consecutive claims;
 // a warp owns a chunk of 128 = 2 rows of 64; in a row lane l owns claims 2l and 2l+1.  The raw
 // timestamps of the NEXT tiles are always in flight: one elected thread feeds a 2-stage
-// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier, 64 KB per tile), so the
+// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier, 32 KB per tile), so the
 // bytes in flight per SM do not depend on registers or occupancy; a warp reads its rows with
 // conflict-free 128-bit shared loads.  (Unaligned inputs and the ragged last tile fall back to
 // coalesced 128-bit / scalar global loads.)  Phase 1 (integers only) classifies above/below --
@@ -43,9 +43,9 @@ namespace cb {
 
 constexpr int ROWS = 2;            // rows of 64 claims per warp chunk
 constexpr int CHUNK = ROWS * 64;   // 128 claims per warp
-constexpr int NSTAGE = 3;          // TMA ring depth (tiles in flight per CTA: 192 KB of the SM's 227 KB)
+constexpr int NSTAGE = 3;          // TMA ring depth (tiles in flight per CTA: 2 CTAs x 96 KB of the SM's 227 KB)
 constexpr int NSCR = NSTAGE + 1;   // depth of the per-tile scratch / named-barrier rotation
-constexpr int STAGE_BYTES = TILE * 16; // start (32 KB) + now (32 KB) of one tile
+constexpr int STAGE_BYTES = TILE * 16; // start (16 KB) + now (16 KB) of one tile
 constexpr int SCAN_SMEM = NSTAGE * STAGE_BYTES;
 static_assert(CHUNK * WARPS == TILE, "tile geometry");
 
@@ -180,7 +180,7 @@ __device__ __forceinline__ void tma_request(unsigned char *stage, unsigned long 
 }
 
 template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(TPB, 1) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	extern __shared__ __align__(128) unsigned char s_ring[]; // NSTAGE x (start | now) of one tile
 	__shared__ __align__(8) unsigned long long s_full[NSTAGE];
@@ -433,19 +433,19 @@ __global__ void __launch_bounds__(TPB, 1) scan_kernel(const ScanParams p) {
 				tma_request<raw_t>(s_ring + stage * STAGE_BYTES, &s_full[stage], gstart, gnow, tn);
 		}
 		left_closed = s_leftclosed2[par] != 0u;
-		int w = warp - 1;
-		for (; w >= 0; w--) { // nearest earlier warp with a CONST claim (usually the previous one)
-			const unsigned long long x = s_wagg[w];
-			if (x >> 63) {
-				wex.isconst = true;
-				wex.code = x & DESC_CODE_MASK;
-				if (wex.code == CODE_ZERO && w + 1 < warp)
-					wex.code = s_wagg[w + 1] & DESC_CODE_MASK; // the PASS warp after it sets F
-				break;
-			}
+		// nearest earlier warp with a CONST claim: lane w looks at warp w's aggregate, one ballot
+		const unsigned long long xw = (lane < WARPS) ? s_wagg[lane] : 0ull;
+		const unsigned int cmask = __ballot_sync(0xffffffffu, (lane < warp) && (xw >> 63)) ;
+		if (cmask) {
+			const int w = 31 - __clz(cmask);
+			wex.isconst = true;
+			wex.code = __shfl_sync(0xffffffffu, xw, w) & DESC_CODE_MASK;
+			const unsigned long long nxt = __shfl_sync(0xffffffffu, xw, (w + 1) & 31) & DESC_CODE_MASK;
+			if (wex.code == CODE_ZERO && w + 1 < warp)
+				wex.code = nxt; // the PASS warp after it sets F
+		} else if (warp > 0) {
+			wex.code = __shfl_sync(0xffffffffu, xw, 0) & DESC_CODE_MASK; // all earlier warps are PASS: the first one's claim
 		}
-		if (w < 0 && warp > 0)
-			wex.code = s_wagg[0] & DESC_CODE_MASK; // all earlier warps are PASS: the first one's claim
 	} else {
 		bar_arrive(BAR1);
 	}

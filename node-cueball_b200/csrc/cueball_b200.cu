@@ -215,7 +215,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	const bool piped = (c->depth > 1) && !c->prof;
 	const int li = piped ? (int)(c->seq % (unsigned long long)c->depth) : 0;
 	Lane &L = c->lane[li];
-	const size_t tiles = (n + TILE - 1) / TILE;
+	const size_t tiles = (n + TILE - 1) / TILE;      // scan / prepare tiles
+	const size_t etiles = (n + ETILE - 1) / ETILE;   // emit tiles
 	int rc = ensure_scratch(c, L, tiles);
 	if (rc)
 		return rc;
@@ -276,7 +277,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	EmitParams ep;
 	ep.flags = d_flags;
 	ep.n = n;
-	ep.tiles = tiles;
+	ep.tiles = etiles;
 	ep.g = c->g;
 	ep.bc = L.ctl;
 	ep.iv_lo = L.iv_lo;
@@ -298,8 +299,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
 	// earlier tile to be resident or earlier in the same CTA's sequence: both hold for a grid
 	// within the resident capacity (a CTA visits its tiles in increasing order)
-	const unsigned egrid = (unsigned)(tiles < (size_t)c->emit_grid ? tiles : (size_t)c->emit_grid);
-	// scan: one persistent 1024-thread CTA per SM (128 KB TMA ring each)
+	const unsigned egrid = (unsigned)(etiles < (size_t)c->emit_grid ? etiles : (size_t)c->emit_grid);
+	// scan: two persistent 512-thread CTAs per SM (96 KB TMA ring each)
 	const unsigned sgrid = (unsigned)(tiles < (size_t)c->scan_grid ? tiles : (size_t)c->scan_grid);
 
 	cudaStream_t s_scan = piped ? c->st_scan : c->stream;
@@ -417,7 +418,7 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
 
 int ensure_staging(cb_ctx *c, size_t n) {
 	size_t need = n < c->chunk ? n : c->chunk;
-	need = (need + TILE - 1) / TILE * TILE;
+	need = (need + ETILE - 1) / ETILE * ETILE;
 	if (need <= c->stage_cap)
 		return CB_OK;
 	int rc = drain(c);
@@ -599,10 +600,10 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		return fail(nullptr, CB_ENOMEM, "out of host memory");
 	c->device = device;
 	c->emit_grid = prop.multiProcessorCount * 4;
-	c->scan_grid = prop.multiProcessorCount;
+	c->scan_grid = prop.multiProcessorCount * 2;
 	const char *ck = getenv("CB_CHUNK");
-	if (ck && atoll(ck) >= TILE)
-		c->chunk = ((size_t)atoll(ck) + TILE - 1) / TILE * TILE;
+	if (ck && atoll(ck) >= ETILE)
+		c->chunk = ((size_t)atoll(ck) + ETILE - 1) / ETILE * ETILE;
 	const char *dp = getenv("CB_PIPELINE_DEPTH");
 	if (dp && atoi(dp) >= 1 && atoi(dp) <= CB_LANES)
 		c->depth = atoi(dp);
