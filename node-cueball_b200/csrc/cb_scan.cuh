@@ -14,13 +14,9 @@
 // INDICES (integer-only, one 64-bit look-back descriptor per tile) and turned into doubles
 // only where a claim's class needs the value.
 //
-// Layout: persistent CTAs (two per SM, 16 warps each) stride over tiles of 2048 consecutive claims;
-// a warp owns a chunk of 128 = 2 rows of 64; in a row lane l owns claims 2l and 2l+1.  The raw
-// timestamps of the NEXT tiles are always in flight: one elected thread feeds a 2-stage
-// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier, 32 KB per tile), so the
-// bytes in flight per SM do not depend on registers or occupancy; a warp reads its rows with
-// conflict-free 128-bit shared loads.  (Unaligned inputs and the ragged last tile fall back to
-// coalesced 128-bit / scalar global loads.)  Phase 1 (integers only) classifies above/below --
+// Layout: a CTA owns a tile of 2048 consecutive claims, a warp a chunk of 256 = 4 rows of 64;
+// in a row lane l owns claims 2l and 2l+1, i.e. one fully coalesced 128-bit load per array
+// per row, no shared-memory staging.  Phase 1 (integers only) classifies above/below --
 // sojourn vs target is decided on the int64 nanoseconds whenever the gap to the target
 // exceeds the worst-case rounding of the millisecond doubles, and exactly as
 // utils.currentMillis() (lib/utils.js:198-204) otherwise -- and builds the row/warp/tile
@@ -41,12 +37,8 @@
 
 namespace cb {
 
-constexpr int ROWS = 2;            // rows of 64 claims per warp chunk
-constexpr int CHUNK = ROWS * 64;   // 128 claims per warp
-constexpr int NSTAGE = 3;          // TMA ring depth (tiles in flight per CTA: 2 CTAs x 96 KB of the SM's 227 KB)
-constexpr int NSCR = NSTAGE + 1;   // depth of the per-tile scratch / named-barrier rotation
-constexpr int STAGE_BYTES = TILE * 16; // start (16 KB) + now (16 KB) of one tile
-constexpr int SCAN_SMEM = NSTAGE * STAGE_BYTES;
+constexpr int ROWS = 4;            // rows of 64 claims per warp chunk
+constexpr int CHUNK = ROWS * 64;   // 256 claims per warp
 static_assert(CHUNK * WARPS == TILE, "tile geometry");
 
 // index-coded F: 0 = F is 0, 1 = the batch's carried-in F, a+2 = now[a] + 100
@@ -150,84 +142,24 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 	return __dadd_rn(TimeIn<NS>::to_ms(v), CODEL_INTERVAL);
 }
 
-__device__ __forceinline__ unsigned int s2u(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
-	unsigned int done = 0;
-	while (!done) {
-		asm volatile("{\n\t.reg .pred q;\n\t"
-		             "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-		             "selp.u32 %0, 1, 0, q;\n\t}"
-		             : "=r"(done)
-		             : "r"(s2u(bar)), "r"(parity)
-		             : "memory");
-	}
-}
-// one thread: request tile `t` (start + now, 32 KB each) into ring stage `st`
-template <typename raw_t>
-__device__ __forceinline__ void tma_request(unsigned char *stage, unsigned long long *bar, const raw_t *gstart,
-    const raw_t *gnow, unsigned long long t) {
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of the stage are done
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"((unsigned int)STAGE_BYTES)
-	             : "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-	                 s2u(stage)),
-	    "l"(gstart + t * TILE), "r"((unsigned int)(TILE * 8)), "r"(s2u(bar))
-	    : "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-	                 s2u(stage + TILE * 8)),
-	    "l"(gnow + t * TILE), "r"((unsigned int)(TILE * 8)), "r"(s2u(bar))
-	    : "memory");
-}
-
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
-	extern __shared__ __align__(128) unsigned char s_ring[]; // NSTAGE x (start | now) of one tile
-	__shared__ __align__(8) unsigned long long s_full[NSTAGE];
-	// per-tile scratch rotates over NSCR buffers: fast warps run up to NSTAGE tiles ahead of warp 0's
-	// flush (tile it+NSTAGE is requested once every warp has passed barrier 1 of tile it, and warp 0
-	// reaches barrier 1 of tile it+1 only after flushing tile it)
-	__shared__ unsigned long long s_wagg2[NSCR][WARPS];    // isconst << 63 | code
-	__shared__ unsigned int s_wfc2[NSCR][WARPS];           // chunk-local position of the warp's first CONST claim
-	__shared__ unsigned int s_evn2[NSCR][WARPS];           // per-warp event counters
-	__shared__ unsigned long long s_ev2[NSCR][WARPS][EVW];
-	__shared__ unsigned int s_leftclosed2[NSCR];           // the claim before the tile is below target
+	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
+	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
+	__shared__ unsigned int s_evn[WARPS];                 // per-warp event counters (no cross-warp init race)
+	__shared__ unsigned long long s_ev[WARPS][EVW];
+	__shared__ unsigned int s_leftclosed;                 // the claim before the tile is below target
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned long long t = blockIdx.x;
+	const unsigned long long ts = t * (unsigned long long)TILE;
+	const unsigned long long cs = ts + (unsigned long long)warp * CHUNK; // chunk start
 	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
 	const raw_t *gnow = reinterpret_cast<const raw_t *>(p.now);
 	const double target = p.target;
 	const long long tgt_ns = p.target_ns;
 	const unsigned int lt_mask = (1u << lane) - 1u;
-	const unsigned long long ntiles = (p.n + TILE - 1) / TILE;
-	const unsigned long long nfull = p.vec_ok ? (p.n / TILE) : 0ull; // tiles [0, nfull) come through TMA
-
-	if (tid == 0) {
-#pragma unroll
-		for (int st = 0; st < NSTAGE; st++)
-			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s2u(&s_full[st])));
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-		for (int st = 0; st < NSTAGE; st++) {
-			const unsigned long long tt = blockIdx.x + (unsigned long long)st * gridDim.x;
-			if (tt < nfull)
-				tma_request<raw_t>(s_ring + st * STAGE_BYTES, &s_full[st], gstart, gnow, tt);
-		}
-	}
-	__syncthreads();
-
-	unsigned int it = 0;
-	for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-	const int par = it % NSCR;              // scratch buffer and barrier ids of this tile
-	const int stage = it % NSTAGE;
-	const unsigned int ring_parity = (it / NSTAGE) & 1u;
-	unsigned long long *s_wagg = s_wagg2[par];
-	unsigned int *s_wfc = s_wfc2[par];
-	unsigned int *s_evn = s_evn2[par];
-	unsigned long long(*s_ev)[EVW] = s_ev2[par];
-	const int BAR1 = 1 + 2 * par, BAR2 = 2 + 2 * par;
-	const unsigned long long ts = t * (unsigned long long)TILE;
-	const unsigned long long cs = ts + (unsigned long long)warp * CHUNK; // chunk start
 	if (lane == 0)
 		s_evn[warp] = 0;
 	__syncwarp();
@@ -236,23 +168,7 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	raw_t rs[ROWS][2], rn[ROWS][2];
 	unsigned int fl[ROWS]; // this lane's two flag bytes per row
 	const bool full = (cs + CHUNK <= p.n);
-	if (t < nfull) {
-		mbar_wait(&s_full[stage], ring_parity); // the tile's 64 KB have landed
-		const uint4 *sa = reinterpret_cast<const uint4 *>(s_ring + stage * STAGE_BYTES) + warp * (CHUNK / 2);
-		const uint4 *sb = reinterpret_cast<const uint4 *>(s_ring + stage * STAGE_BYTES + TILE * 8) + warp * (CHUNK / 2);
-#pragma unroll
-		for (int r = 0; r < ROWS; r++) {
-			const uint4 a = sa[r * 32 + lane], b = sb[r * 32 + lane];
-			unsigned long long x0 = ((unsigned long long)a.y << 32) | a.x;
-			unsigned long long x1 = ((unsigned long long)a.w << 32) | a.z;
-			unsigned long long y0 = ((unsigned long long)b.y << 32) | b.x;
-			unsigned long long y1 = ((unsigned long long)b.w << 32) | b.z;
-			rs[r][0] = *reinterpret_cast<raw_t *>(&x0);
-			rs[r][1] = *reinterpret_cast<raw_t *>(&x1);
-			rn[r][0] = *reinterpret_cast<raw_t *>(&y0);
-			rn[r][1] = *reinterpret_cast<raw_t *>(&y1);
-		}
-	} else if (full && p.vec_ok) {
+	if (full && p.vec_ok) {
 		uint4 a[ROWS], b[ROWS];
 #pragma unroll
 		for (int r = 0; r < ROWS; r++)
@@ -412,7 +328,7 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 		s_wagg[warp] = ((unsigned long long)wagg.isconst << 63) | wagg.code;
 		s_wfc[warp] = wfc;
 		if (warp == 0)
-			s_leftclosed2[par] = (t > 0 && !(prev_bits & 1u)) ? 1u : 0u;
+			s_leftclosed = (t > 0 && !(prev_bits & 1u)) ? 1u : 0u;
 	}
 	// Only warps whose leading claims inherit F from an earlier warp (and warp 0, which writes the
 	// tile's record) wait for the others; everybody else just signals and moves on.
@@ -424,18 +340,11 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	wex.code = CODE_ZERO;
 	bool left_closed = false;
 	if (need_wex) {
-		bar_sync(BAR1);
-		if (tid == 0) {
-			// every warp has copied its rows out of this ring stage: refill it with the tile this CTA
-			// will process NSTAGE iterations from now (overlaps the rest of this tile and the next ones)
-			const unsigned long long tn = t + (unsigned long long)NSTAGE * gridDim.x;
-			if (tn < nfull)
-				tma_request<raw_t>(s_ring + stage * STAGE_BYTES, &s_full[stage], gstart, gnow, tn);
-		}
-		left_closed = s_leftclosed2[par] != 0u;
+		bar_sync(1);
+		left_closed = s_leftclosed != 0u;
 		// nearest earlier warp with a CONST claim: lane w looks at warp w's aggregate, one ballot
 		const unsigned long long xw = (lane < WARPS) ? s_wagg[lane] : 0ull;
-		const unsigned int cmask = __ballot_sync(0xffffffffu, (lane < warp) && (xw >> 63)) ;
+		const unsigned int cmask = __ballot_sync(0xffffffffu, (lane < warp) && (xw >> 63));
 		if (cmask) {
 			const int w = 31 - __clz(cmask);
 			wex.isconst = true;
@@ -447,7 +356,7 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 			wex.code = __shfl_sync(0xffffffffu, xw, 0) & DESC_CODE_MASK; // all earlier warps are PASS: the first one's claim
 		}
 	} else {
-		bar_arrive(BAR1);
+		bar_arrive(1);
 	}
 
 	// ---- the tile's record (thread 0): where the inherited run closes, what the tile leaves open
@@ -599,12 +508,14 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 		p.b->nonmono = 1u;
 	// ---- flush: warp 0 gathers every warp's events into the tile's slots ------------------------
 	if (warp != 0) {
-		bar_arrive(BAR2);
-	} else {
-		bar_sync(BAR2);
+		bar_arrive(2);
+		return;
+	}
+	bar_sync(2);
+	{
 		unsigned int cnt = 0;
 		bool over = false;
-#pragma unroll 4
+#pragma unroll
 		for (int w = 0; w < WARPS; w++) {
 			const unsigned int cw = s_evn[w];
 			over |= cw > (unsigned int)EVW;
@@ -625,11 +536,6 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 			p.ev_count[t] = cnt;
 		}
 	}
-	// Without the TMA ring nothing stops a fast warp from lapping the named barriers of a slower
-	// one (ids repeat every second tile): close the iteration with a full barrier in that mode.
-	if (nfull == 0)
-		__syncthreads();
-	} // tile loop
 }
 
 } // namespace cb

@@ -107,7 +107,6 @@ struct cb_ctx {
 	int last_lane = -1;
 	bool last_flags = false;
 	int emit_grid = 148 * 4;           // persistent emit CTAs (from the device's SM count)
-	int scan_grid = 148;               // persistent scan CTAs: one per SM
 	// topology
 	int B = 0, nslots = 0, target_slots = 0, mode = CB_BALANCE_UNIFORM, key_cap = 0, slot_cap = 0;
 	int32_t *d_keys = nullptr, *d_want = nullptr, *d_add = nullptr, *d_slot_backend = nullptr;
@@ -300,8 +299,6 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	// earlier tile to be resident or earlier in the same CTA's sequence: both hold for a grid
 	// within the resident capacity (a CTA visits its tiles in increasing order)
 	const unsigned egrid = (unsigned)(etiles < (size_t)c->emit_grid ? etiles : (size_t)c->emit_grid);
-	// scan: two persistent 512-thread CTAs per SM (96 KB TMA ring each)
-	const unsigned sgrid = (unsigned)(tiles < (size_t)c->scan_grid ? tiles : (size_t)c->scan_grid);
 
 	cudaStream_t s_scan = piped ? c->st_scan : c->stream;
 	cudaStream_t s_res = piped ? c->st_res : c->stream;
@@ -322,9 +319,9 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[0], s_scan));
 	if (flags)
-		scan_kernel<NS, true><<<sgrid, TPB, SCAN_SMEM, s_scan>>>(sp);
+		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
 	else
-		scan_kernel<NS, false><<<sgrid, TPB, SCAN_SMEM, s_scan>>>(sp);
+		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s_scan));
 	// prepare: independent of the ControlledDelay state -> its own stream, overlaps other lanes
@@ -600,7 +597,6 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		return fail(nullptr, CB_ENOMEM, "out of host memory");
 	c->device = device;
 	c->emit_grid = prop.multiProcessorCount * 4;
-	c->scan_grid = prop.multiProcessorCount * 2;
 	const char *ck = getenv("CB_CHUNK");
 	if (ck && atoll(ck) >= ETILE)
 		c->chunk = ((size_t)atoll(ck) + ETILE - 1) / ETILE * ETILE;
@@ -650,10 +646,6 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	CU0(cudaFuncSetAttribute(prepare_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(prepare_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
-	CU0(cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
-	CU0(cudaFuncSetAttribute(scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
-	CU0(cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM));
 	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 #undef CU0
