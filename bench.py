@@ -40,7 +40,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from oracle import tracegen  # noqa: E402  (input generator only; not on the timed path)
+from cueball_b200 import tracegen  # noqa: E402  (input generator only)
 
 WORKLOADS = {
     #        claims/step/GPU  backends  slots   generator extras

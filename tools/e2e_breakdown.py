@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""tools/e2e_breakdown.py -- where the host-buffer entry point's time goes at a given batch size:
+raw pinned H2D / D2H copy times next to cb_admit_batch for several staging chunk sizes."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+chunks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+
+from cueball_b200 import tracegen  # noqa: E402  (input generator only)
+
+
+def t(f, reps=20):
+    f()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        f()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+dev = torch.device("cuda", 0)
+h = torch.empty(2 * n, dtype=torch.int64).pin_memory()
+d = torch.empty(2 * n, dtype=torch.int64, device=dev)
+ho = torch.empty(5 * n, dtype=torch.uint8).pin_memory()
+do = torch.empty(5 * n, dtype=torch.uint8, device=dev)
+print("n=%d  H2D %.1f MB: %.3f ms   D2H %.1f MB: %.3f ms" % (
+    n, 16 * n / 1e6, t(lambda: d.copy_(h, non_blocking=True)), 5 * n / 1e6, t(lambda: ho.copy_(do, non_blocking=True))))
+
+s, nw = tracegen.gen_trace(n, seed=5, t0=10 ** 12, de=1 << 19, target_ns=5_000_000, unit=1 << 19)
+hs = torch.from_numpy(s).pin_memory().numpy()
+hn = torch.from_numpy(nw).pin_memory().numpy()
+hdec = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+hslot = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+for ch in chunks:
+    if ch:
+        os.environ["CB_CHUNK"] = str(ch)
+    else:
+        os.environ.pop("CB_CHUNK", None)
+    import cueball_b200 as cb
+    ctx = cb.Context(0)
+    ctx.codel_init(5.0)
+    ctx.backends_set(64, tracegen.gen_insert_draws(64), 256)
+
+    def call():
+        ctx.set_state({"count": 0, "drop_next": 0.0, "first_above_time": 0.0, "dropping": False, "last_empty": None})
+        ctx.admit_batch(hs, hn, out_decision=hdec, out_slot=hslot)
+
+    def call_nostate():
+        ctx.admit_batch(hs, hn, out_decision=hdec, out_slot=hslot)
+
+    print("chunk=%-8s admit_batch %.3f ms (with set_state %.3f ms) -> %.3g claims/s" % (
+        ch or "default", t(call_nostate), t(call), n / t(call_nostate) * 1e3))
+    del ctx

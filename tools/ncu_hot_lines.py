@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/ncu_hot_lines.py <report.ncu-rep> [topN] -- source lines ranked by warp-stall samples
+"""tools/ncu_hot_lines.py <report.ncu-rep> [topN] [kernel-regex] [ins] -- source lines ranked by warp-stall samples (or by executed instructions with "ins")
 (needs -lineinfo at compile time and --import-source on at capture time)."""
 import csv
 import io
@@ -10,7 +10,10 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
+    kern = sys.argv[3] if len(sys.argv) > 3 else None
+    by_ins = len(sys.argv) > 4 and sys.argv[4] == "ins"
+    out = subprocess.run(["ncu", "-i", rep] + (["-k", "regex:" + kern] if kern else []) +
+                         ["--page", "source", "--print-source", "cuda,sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     cur_file, hdr, acc = None, None, {}
@@ -39,7 +42,7 @@ def main():
     tot = sum(a[0] for a in acc.values()) or 1
     toti = sum(a[1] for a in acc.values()) or 1
     print("total samples %d, warp instructions %d" % (tot, toti))
-    for (f, ln), a in sorted(acc.items(), key=lambda kv: -kv[1][0])[:top]:
+    for (f, ln), a in sorted(acc.items(), key=lambda kv: -kv[1][1 if by_ins else 0])[:top]:
         print("%5.1f%% smp %5.1f%% ins  %s:%s  %s" % (100.0 * a[0] / tot, 100.0 * a[1] / toti, f, ln, a[2]))
 
 

@@ -4,7 +4,7 @@ import numpy as np
 import torch
 sys.path.insert(0, ".")
 import cueball_b200 as cb
-from oracle import tracegen
+from cueball_b200 import tracegen  # noqa: E402  (input generator only)
 import bench
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
