@@ -229,6 +229,9 @@ uint64_t cb_launch_count(const cb_ctx *ctx); /* kernels launched so far by this 
  * prepare [6] entry, [0] pairing, [1] run searches, [2] merge, [3] speculation, [4] end;
  * commit [7] entry, [5] done */
 int cb_debug_timestamps(cb_ctx *ctx, uint64_t out[16]);
+/* Same for the batch that last used pipeline lane `lane` (0 .. depth-1): out[8]/[9] scan first-CTA
+ * start / last-tile end, [6]/[4] prepare, [7]/[5] commit, [10]/[11] emit (tools/pipeline_timeline.py). */
+int cb_debug_lane_timestamps(cb_ctx *ctx, int lane, uint64_t out[16]);
 
 #ifdef __cplusplus
 }

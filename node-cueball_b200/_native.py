@@ -24,7 +24,7 @@ SYMBOLS = [
     "cb_admit_batch_ms_dev", "cb_batch_stats_get", "cb_codel_overloaded", "cb_backends_set",
     "cb_backend_added", "cb_backend_removed", "cb_reshuffle", "cb_backends_get", "cb_plan_rebalance",
     "cb_comm_unique_id", "cb_comm_init", "cb_allreduce_counts", "cb_profile_enable", "cb_profile_get",
-    "cb_launch_count", "cb_debug_timestamps",
+    "cb_launch_count", "cb_debug_timestamps", "cb_debug_lane_timestamps",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
     L.cb_launch_count.argtypes = [vp]
     L.cb_launch_count.restype = u64
     L.cb_debug_timestamps.argtypes = [vp, C.POINTER(u64)]
+    L.cb_debug_lane_timestamps.argtypes = [vp, C.c_int, C.POINTER(u64)]
     _lib = L
     return L
 

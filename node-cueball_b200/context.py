@@ -120,6 +120,14 @@ class Context(object):
             return None if t is None else C.c_void_p(t.data_ptr())
         self._ck(fn(self._h, p(start), p(now), p(flags), n, p(decision), p(slot), p(backend)))
 
+    def admit_batch_ptr(self, start, now, flags, n, decision, slot, backend, ns=True):
+        """Same call with raw device addresses (ints, 0/None for absent arrays): what a native
+        caller of the C ABI does, without the per-call tensor bookkeeping of admit_batch_dev."""
+        fn = self._L.cb_admit_batch_dev if ns else self._L.cb_admit_batch_ms_dev
+        rc = fn(self._h, start, now, flags or None, n, decision or None, slot or None, backend or None)
+        if rc:
+            self._ck(rc)
+
     def stats(self):
         st = N.BatchStats()
         self._ck(self._L.cb_batch_stats_get(self._h, C.byref(st)))
@@ -210,6 +218,11 @@ class Context(object):
     def debug_timestamps(self):
         out = (C.c_uint64 * 16)()
         self._ck(self._L.cb_debug_timestamps(self._h, out))
+        return list(out)
+
+    def debug_lane_timestamps(self, lane):
+        out = (C.c_uint64 * 16)()
+        self._ck(self._L.cb_debug_lane_timestamps(self._h, int(lane), out))
         return list(out)
 
     def launch_count(self):

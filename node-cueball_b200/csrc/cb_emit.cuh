@@ -44,6 +44,8 @@ struct EmitParams {
 	int table_smem_bytes;          // 0 = read the table through L1/L2 instead
 	SumDesc *sdesc;
 	unsigned long long epoch;
+	unsigned long long *chain; // commit chain word: a flags batch passes it on from here
+	unsigned long long seq;
 	unsigned int *ticket;          // CTA completion counter (flags variant finalisation)
 	int vec_ok;                    // outputs suitably aligned for vector stores
 };
@@ -112,6 +114,8 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	DevState *g = p.g;
 	BatchCtl *bc = p.bc;
+	if (tid == 0 && blockIdx.x == 0)
+		bc->dbg[10] = gtimer(); // timeline stamp (tools/pipeline_timeline.py)
 	if (bc->path == 1) // the sequential path already wrote every output
 		return;
 	const bool want_backend = (p.backend != nullptr) && (p.nslots > 0);
@@ -441,6 +445,8 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 			__syncthreads(); // s_wsum / s_tile_excl are reused by the next tile
 	}
 
+	if (tid == 0 && blockIdx.x == gridDim.x - 1)
+		bc->dbg[11] = gtimer();
 	// ---- flags variant: the last CTA to finish publishes the batch totals -----------------
 	if (FLAGS) {
 		__threadfence();
@@ -458,6 +464,8 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 				g->tot_admits += admits;
 				bc->gcounts[0] = drops;
 				bc->gcounts[1] = admits;
+				__threadfence();
+				st_release(&p.chain[0], p.seq + 1); // the next batch's commit may read the cursor now
 			}
 		}
 	}

@@ -47,6 +47,8 @@ struct ResolveParams {
 	const unsigned int *rec_cend;
 	const void *tile_now0;              // raw clock of every tile's first claim (coarse search index)
 	double *idx_ms;                     // [<= NIDX_MAX] the coarse index in ms (prepare -> commit)
+	unsigned long long *chain;          // [0] batches whose state is committed, [1] hand-over timeouts
+	unsigned long long seq;             // this batch's position in the chain
 	// cross-tile run events (<= 3 per closing tile; slot `tiles` = the run open at batch end)
 	unsigned long long *xev;            // [(tiles+1)*3]
 	unsigned int *xcnt;                 // [tiles+1]
@@ -604,6 +606,7 @@ __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p)
 // previous batch.  One small CTA; runs strictly in batch order.
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) {
+	extern __shared__ __align__(16) double s_cidx[]; // the coarse clock index (prepare wrote it to idx_ms)
 	__shared__ unsigned long long s_evc[SEV_MAX], s_evq[SEV_MAX], s_evd[SEV_MAX];
 	__shared__ double s_evnow[SEV_MAX];
 	__shared__ unsigned int s_ncar;
@@ -612,32 +615,59 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 	BatchCtl *bc = p.bc;
 	if (tid == 0)
 		bc->dbg[7] = gtimer();
-	if ((bc->nonmono != 0u) || (bc->overflow != 0u)) {
-		if (warp == 0)
-			sequential_path<NS>(p, lane);
-		return;
-	}
-	const unsigned int nevp = bc->nev_prep;
+	const bool fallback = (bc->nonmono != 0u) || (bc->overflow != 0u);
+
+	// ---- everything that does not depend on the carried state: done while the previous batch's
+	// commit may still be running --------------------------------------------------------------
+	const unsigned int nevp = fallback ? 0u : bc->nev_prep;
 	const bool ev_smem = nevp + EV_FRONT <= SEV_MAX;
 	unsigned long long *evc = ev_smem ? s_evc : p.evc;
 	unsigned long long *ev_q = ev_smem ? s_evq : p.ev_q;
 	unsigned long long *ev_d = ev_smem ? s_evd : p.ev_d;
 	double *ev_now = ev_smem ? s_evnow : p.ev_now;
-	if (ev_smem) {
-		for (unsigned int k = tid; k < nevp; k += CTPB) {
-			s_evc[EV_FRONT + k] = p.evc[EV_FRONT + k];
-			s_evq[EV_FRONT + k] = p.ev_q[EV_FRONT + k];
-			s_evd[EV_FRONT + k] = p.ev_d[EV_FRONT + k];
-			s_evnow[EV_FRONT + k] = p.ev_now[EV_FRONT + k];
-		}
-	}
-	if (tid == 0)
-		s_ncar = 0;
-	const double F_in = g->F, D_in = g->D;
-	const int B_in = g->B;
 	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
 	const unsigned long long G = stride * TILE;
+	if (!fallback) {
+		if (ev_smem) {
+			for (unsigned int k = tid; k < nevp; k += CTPB) {
+				s_evc[EV_FRONT + k] = p.evc[EV_FRONT + k];
+				s_evq[EV_FRONT + k] = p.ev_q[EV_FRONT + k];
+				s_evd[EV_FRONT + k] = p.ev_d[EV_FRONT + k];
+				s_evnow[EV_FRONT + k] = p.ev_now[EV_FRONT + k];
+			}
+		}
+		const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
+		for (unsigned int k = tid; k < nidx; k += CTPB)
+			s_cidx[k] = p.idx_ms[k];
+	}
+	if (tid == 0) {
+		s_ncar = 0;
+		// ---- hand-over: wait until the previous batch has committed its state.  It was launched
+		// before this one (possibly on another stream), so it is running or about to; the bound only
+		// keeps a broken chain from hanging the device.
+		const unsigned long long t0 = gtimer();
+		while (ld_acquire(&p.chain[0]) != p.seq) {
+			if (gtimer() - t0 > 4000000000ull) {
+				atomicAdd(&p.chain[1], 1ull);
+				break;
+			}
+		}
+		bc->dbg[12] = gtimer();
+	}
 	__syncthreads();
+	if (fallback) {
+		if (warp == 0) {
+			sequential_path<NS>(p, lane);
+			__syncwarp();
+			if (lane == 0) {
+				__threadfence();
+				st_release(&p.chain[0], p.seq + 1);
+			}
+		}
+		return;
+	}
+	const double F_in = g->F, D_in = g->D;
+	const int B_in = g->B;
 
 	// ---- the stretch inherited from the previous batch (claims [0, close) are all above target) --
 	if (bc->cj_exists) {
@@ -649,7 +679,7 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 			Pred pr;
 			pr.x = F;
 			pr.level = warp + 1;
-			const unsigned long long pos = warp_search<NS>(p.now, p.idx_ms, G, 0, close, pr, lane);
+			const unsigned long long pos = warp_search<NS>(p.now, s_cidx, G, 0, close, pr, lane);
 			if (warp == 0) {
 				const int c = claim_class(true, now_at<NS>(p.now, pos), F);
 				if (lane == 0)
@@ -691,10 +721,10 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 				unsigned long long d;
 				if (warp == 0 && idx == 0 && B_in) { // the batch opens inside a dropping episode
 					pr.x = D_in;
-					d = warp_search<NS>(p.now, p.idx_ms, G, idx, q + 1, pr, lane);
+					d = warp_search<NS>(p.now, s_cidx, G, idx, q + 1, pr, lane);
 				} else {
 					pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
-					d = warp_search<NS>(p.now, p.idx_ms, G, idx + 1, q + 1, pr, lane);
+					d = warp_search<NS>(p.now, s_cidx, G, idx + 1, q + 1, pr, lane);
 				}
 				if (lane == 0) {
 					ev_now[k] = nowk;
@@ -706,8 +736,10 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 		__syncthreads();
 	}
 
-	// ---- 3. the serial chain over events (thread 0) -----------------------------------
-	if (tid == 0) {
+	// ---- 3. the serial chain over events: warp 0, every lane carrying the same scalars so that
+	// the searches a failed speculation needs are warp-wide (3-4 dependent accesses, not 20+) ----
+	if (warp == 0) {
+		const bool wr = (lane == 0);
 		double D = g->D;
 		unsigned long long C = g->C;
 		int B = g->B;
@@ -731,9 +763,11 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 			if (B) { // lib/codel.js:62-68, episode carried in from the previous batch
 				const unsigned long long d = ev_d[k];
 				if (d <= q) {
-					p.iv_lo[niv] = d;
-					p.iv_hi[niv] = q;
-					p.iv_cum[niv] = drops;
+					if (wr) {
+						p.iv_lo[niv] = d;
+						p.iv_hi[niv] = q;
+						p.iv_cum[niv] = drops;
+					}
 					niv++;
 					drops += q - d + 1;
 					C += q - d + 1;
@@ -756,17 +790,25 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 					D = drop_next_after(now_e, C);
 					B = 1;
 					unsigned long long d = dspec;
-					if (C != 1) // speculation assumed count == 1 (drop_next = now + 100)
-						d = thread_lower_bound<NS>(p.now, (unsigned long long)e + 1, q + 1, D);
-					p.iv_lo[niv] = (unsigned long long)e;
-					p.iv_hi[niv] = (unsigned long long)e;
-					p.iv_cum[niv] = drops;
+					if (C != 1) { // speculation assumed count == 1 (drop_next = now + 100)
+						Pred pr;
+						pr.level = 0;
+						pr.x = D;
+						d = warp_search<NS>(p.now, s_cidx, G, (unsigned long long)e + 1, q + 1, pr, lane);
+					}
+					if (wr) {
+						p.iv_lo[niv] = (unsigned long long)e;
+						p.iv_hi[niv] = (unsigned long long)e;
+						p.iv_cum[niv] = drops;
+					}
 					niv++;
 					drops += 1;
 					if (d <= q) {
-						p.iv_lo[niv] = d;
-						p.iv_hi[niv] = q;
-						p.iv_cum[niv] = drops;
+						if (wr) {
+							p.iv_lo[niv] = d;
+							p.iv_hi[niv] = q;
+							p.iv_cum[niv] = drops;
+						}
 						niv++;
 						drops += q - d + 1;
 						C += q - d + 1;
@@ -783,38 +825,46 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 			F = (F_in != 0.0) ? F_in : bc->now0p100;
 		if (FLAGS) {
 			if (bc->hasE_new) {
-				g->E = bc->E_val;
-				g->hasE = 1;
+				if (wr) {
+					g->E = bc->E_val;
+					g->hasE = 1;
+				}
 				if (bc->trailing_marker)
 					F = 0.0; // trailing empty(): lib/codel.js:93
 			}
 		}
-		bc->dbg[5] = gtimer();
-		g->F = F;
-		g->D = D;
-		g->C = C;
-		g->B = B;
-		bc->n = p.n;
-		bc->path = 0;
-		bc->n_events = nev - k0;
-		bc->n_intervals = niv;
-		bc->gcounts[2] = p.n;
-		bc->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)
-		bc->cursor0 = g->cursor;
-		if (!FLAGS) {
-			const unsigned long long admits = p.n - drops;
-			bc->drops = drops;
-			bc->admits = admits;
-			bc->skipped = 0;
-			g->tot_drops += drops;
-			g->tot_admits += admits;
-			bc->gcounts[0] = drops;
-			bc->gcounts[1] = admits;
-			g->cursor += admits; // the emit kernel works from cursor0
-		} else {
-			bc->drops = 0; // accumulated by the emit kernel (waiting handles only)
-			bc->admits = 0;
-			bc->skipped = 0;
+		if (wr) {
+			bc->dbg[5] = gtimer();
+			g->F = F;
+			g->D = D;
+			g->C = C;
+			g->B = B;
+			bc->n = p.n;
+			bc->path = 0;
+			bc->n_events = nev - k0;
+			bc->n_intervals = niv;
+			bc->gcounts[2] = p.n;
+			bc->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)
+			bc->cursor0 = g->cursor;
+			if (!FLAGS) {
+				const unsigned long long admits = p.n - drops;
+				bc->drops = drops;
+				bc->admits = admits;
+				bc->skipped = 0;
+				g->tot_drops += drops;
+				g->tot_admits += admits;
+				bc->gcounts[0] = drops;
+				bc->gcounts[1] = admits;
+				g->cursor += admits; // the emit kernel works from cursor0
+				// the next batch's commit may go ahead (a flags batch finishes the cursor in its emit
+				// kernel, which then passes the chain on)
+				__threadfence();
+				st_release(&p.chain[0], p.seq + 1);
+			} else {
+				bc->drops = 0; // accumulated by the emit kernel (waiting handles only)
+				bc->admits = 0;
+				bc->skipped = 0;
+			}
 		}
 	}
 }

@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const unsigned long long t = blockIdx.x;
+	if (tid == 0 && blockIdx.x == 0)
+		p.b->dbg[8] = gtimer(); // timeline stamp (tools/pipeline_timeline.py)
 	const unsigned long long ts = t * (unsigned long long)TILE;
 	const unsigned long long cs = ts + (unsigned long long)warp * CHUNK; // chunk start
 	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
@@ -534,6 +536,8 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 			if (over)
 				p.b->overflow = 1u;
 			p.ev_count[t] = cnt;
+			if (t + 1 == gridDim.x)
+				p.b->dbg[9] = gtimer(); // the last tile's CTA is among the last to retire
 		}
 	}
 }

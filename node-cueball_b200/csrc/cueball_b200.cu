@@ -57,7 +57,8 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0;
 
-constexpr int CB_LANES = 3;                   // batches in flight (scan | resolve | emit)
+constexpr int CB_LANES = 8;                   // most batches in flight (lanes)
+constexpr int CB_DEFAULT_DEPTH = 5;           // lanes used unless CB_PIPELINE_DEPTH / cb_set_pipeline_depth says otherwise
 constexpr int NBUF = 3;                       // staging buffers of the host-buffer pipeline
 constexpr size_t DEFAULT_CHUNK = 4u << 20;    // claims per pipeline chunk
 
@@ -72,8 +73,8 @@ struct Lane {
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr, *tile_now0 = nullptr;
 	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
 	double *ev_now = nullptr, *hj_F = nullptr, *idx_ms = nullptr;
-	cudaStream_t st_prep = nullptr; // this lane's prepare kernel (independent of the other lanes')
-	cudaEvent_t scan_done = nullptr, prep_done = nullptr, res_done = nullptr, emit_done = nullptr, coll_done = nullptr;
+	cudaStream_t st = nullptr; // all four kernels of the lane's batch run here, in order
+	cudaEvent_t res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
 	bool used = false, coll_pending = false;
 	unsigned long long epoch = 0;
 };
@@ -92,7 +93,7 @@ struct cb_ctx {
 	cudaStream_t stream = nullptr;     // "main" stream: the caller's, or own_stream
 	cudaStream_t own_stream = nullptr;
 	bool user_stream = false;
-	cudaStream_t st_scan = nullptr, st_res = nullptr, st_emit = nullptr, st_coll = nullptr;
+	cudaStream_t st_coll = nullptr;
 	cudaStream_t s_in = nullptr, s_out = nullptr;
 	cudaEvent_t ev_user = nullptr;
 	DevState *g = nullptr;
@@ -101,9 +102,11 @@ struct cb_ctx {
 	char err[512] = "";
 	uint64_t launches = 0;
 	// batch pipeline
-	int depth = CB_LANES;
+	int depth = CB_DEFAULT_DEPTH;
 	Lane lane[CB_LANES];
 	unsigned long long seq = 0;        // batches enqueued so far
+	unsigned long long *d_chain = nullptr; // [0] batches committed, [1] hand-over timeouts (device)
+	unsigned long long chain_seq = 0;      // batches enqueued
 	int last_lane = -1;
 	bool last_flags = false;
 	int emit_grid = 148 * 4;           // persistent emit CTAs (from the device's SM count)
@@ -155,11 +158,8 @@ template <typename T> int dev_alloc(cb_ctx *c, T **p, size_t count) {
 
 // wait for every batch in flight (and the main stream)
 int drain(cb_ctx *c) {
-	CU(c, cudaStreamSynchronize(c->st_scan));
 	for (int l = 0; l < CB_LANES; l++)
-		CU(c, cudaStreamSynchronize(c->lane[l].st_prep));
-	CU(c, cudaStreamSynchronize(c->st_res));
-	CU(c, cudaStreamSynchronize(c->st_emit));
+		CU(c, cudaStreamSynchronize(c->lane[l].st));
 	CU(c, cudaStreamSynchronize(c->st_coll));
 	CU(c, cudaStreamSynchronize(c->stream));
 	return CB_OK;
@@ -170,7 +170,7 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 		return CB_OK;
 	// growing a lane's scratch: nothing of this lane may be in flight
 	if (L.used) {
-		CU(c, cudaEventSynchronize(L.emit_done));
+		CU(c, cudaStreamSynchronize(L.st));
 		if (L.coll_pending)
 			CU(c, cudaEventSynchronize(L.coll_done));
 	}
@@ -196,10 +196,10 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 	return CB_OK;
 }
 
-// Enqueue the three kernels of one batch.  depth 1 (or profiling): all three on the main
-// stream, in order.  depth > 1: scan / resolve / emit go to their own streams, chained by
-// events, so consecutive batches overlap; `in_ready` (optional) gates the scan on the batch's
-// inputs, and the batch's emit_done event is returned through `out_done`.
+// Enqueue the four kernels of one batch.  depth 1 (or profiling): all on the main stream, in
+// order.  depth > 1: the batch goes to its lane's stream (lanes rotate), the commit kernels are
+// chained across lanes by one event, so consecutive batches overlap; `in_ready` (optional) gates
+// the scan on the batch's inputs, and the batch's emit_done event is returned through `out_done`.
 template <bool NS>
 int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8_t *d_flags, size_t n,
     uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend, cudaEvent_t in_ready, cudaEvent_t *out_done) {
@@ -251,6 +251,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.rec_cend = L.rec_cend;
 	rp.tile_now0 = L.tile_now0;
 	rp.idx_ms = L.idx_ms;
+	rp.chain = c->d_chain;
+	rp.seq = c->chain_seq;
 	rp.xev = L.xev;
 	rp.xcnt = L.xcnt;
 	rp.hj_lo = L.hj_lo;
@@ -293,6 +295,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	ep.sdesc = L.sdesc;
 	ep.epoch = L.epoch;
 	ep.ticket = L.ticket;
+	ep.chain = c->d_chain;
+	ep.seq = c->chain_seq;
 	ep.vec_ok = (((uintptr_t)d_decision & 7) == 0) && (((uintptr_t)d_slot & 15) == 0) &&
 	    (((uintptr_t)d_backend & 15) == 0);
 	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
@@ -300,65 +304,55 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	// within the resident capacity (a CTA visits its tiles in increasing order)
 	const unsigned egrid = (unsigned)(etiles < (size_t)c->emit_grid ? etiles : (size_t)c->emit_grid);
 
-	cudaStream_t s_scan = piped ? c->st_scan : c->stream;
-	cudaStream_t s_res = piped ? c->st_res : c->stream;
-	cudaStream_t s_emit = piped ? c->st_emit : c->stream;
+	// One stream per lane: scan -> prepare -> commit -> emit of a batch are stream-ordered, batches
+	// of different lanes overlap freely.  The only cross-lane edge is the ControlledDelay state:
+	// commit(k) follows commit(k-1) (emit(k-1) when that batch had waiting-flags, which finishes
+	// the slot cursor in its emit kernel); that edge is a device-side chain word, not an event.
+	cudaStream_t s = piped ? L.st : c->stream;
 	if (piped) {
 		if (c->user_stream) { // the caller's earlier work (e.g. filling the inputs) comes first
 			CU(c, cudaEventRecord(c->ev_user, c->stream));
-			CU(c, cudaStreamWaitEvent(s_scan, c->ev_user, 0));
+			CU(c, cudaStreamWaitEvent(s, c->ev_user, 0));
 		}
-		if (L.used) { // this lane's scratch is free once its previous batch has been emitted
-			CU(c, cudaStreamWaitEvent(s_scan, L.emit_done, 0));
-			if (L.coll_pending)
-				CU(c, cudaStreamWaitEvent(s_scan, L.coll_done, 0));
-		}
+		if (L.used && L.coll_pending) // the collective of the lane's previous batch owns its control block
+			CU(c, cudaStreamWaitEvent(s, L.coll_done, 0));
 	}
 	if (in_ready)
-		CU(c, cudaStreamWaitEvent(s_scan, in_ready, 0));
+		CU(c, cudaStreamWaitEvent(s, in_ready, 0));
 	if (c->prof)
-		CU(c, cudaEventRecord(c->pe[0], s_scan));
+		CU(c, cudaEventRecord(c->pe[0], s));
 	if (flags)
-		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
+		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s>>>(sp);
 	else
-		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s_scan>>>(sp);
+		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s>>>(sp);
 	if (c->prof)
-		CU(c, cudaEventRecord(c->pe[1], s_scan));
-	// prepare: independent of the ControlledDelay state -> its own stream, overlaps other lanes
-	cudaStream_t s_prep = piped ? L.st_prep : c->stream;
-	if (piped) {
-		CU(c, cudaEventRecord(L.scan_done, s_scan));
-		CU(c, cudaStreamWaitEvent(s_prep, L.scan_done, 0));
-	}
+		CU(c, cudaEventRecord(c->pe[1], s));
+	// prepare: independent of the ControlledDelay state, so it overlaps the other lanes' commits
 	if (flags)
-		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s_prep>>>(rp);
+		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	else
-		prepare_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s_prep>>>(rp);
-	// commit: the only stage that is serial across batches (stream order on st_res)
-	if (piped) {
-		CU(c, cudaEventRecord(L.prep_done, s_prep));
-		CU(c, cudaStreamWaitEvent(s_res, L.prep_done, 0));
-		// a flags batch finishes its cursor/totals in its emit kernel: the next commit needs them
-		if (c->last_flags && c->last_lane >= 0 && c->last_lane != li)
-			CU(c, cudaStreamWaitEvent(s_res, c->lane[c->last_lane].emit_done, 0));
-	}
+		prepare_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
+	// commit: the only stage that is serial across batches.  The order is kept inside the kernels:
+	// commit(k) spins (one thread) on the chain word until batch k-1 has published its state, so
+	// the hand-over costs an L2 round trip instead of a cross-stream event (~5 us measured).
+	const size_t cidx_bytes = ((tiles + ((tiles + NIDX_MAX - 1) / NIDX_MAX) - 1) / ((tiles + NIDX_MAX - 1) / NIDX_MAX)) * sizeof(double);
 	if (flags)
-		commit_kernel<NS, true><<<1, CTPB, 0, s_res>>>(rp);
+		commit_kernel<NS, true><<<1, CTPB, cidx_bytes, s>>>(rp);
 	else
-		commit_kernel<NS, false><<<1, CTPB, 0, s_res>>>(rp);
+		commit_kernel<NS, false><<<1, CTPB, cidx_bytes, s>>>(rp);
+	c->chain_seq++;
 	if (c->prof)
-		CU(c, cudaEventRecord(c->pe[2], s_res));
-	if (piped) {
-		CU(c, cudaEventRecord(L.res_done, s_res));
-		CU(c, cudaStreamWaitEvent(s_emit, L.res_done, 0));
-	}
+		CU(c, cudaEventRecord(c->pe[2], s));
+	if (piped && c->comm) // the drop-count collective starts from here
+		CU(c, cudaEventRecord(L.res_done, s));
 	if (flags)
-		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s_emit>>>(ep);
+		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	else
-		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s_emit>>>(ep);
+		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	c->launches += 4;
 	CU(c, cudaGetLastError());
-	CU(c, cudaEventRecord(L.emit_done, s_emit));
+	if (out_done || (piped && flags && c->comm))
+		CU(c, cudaEventRecord(L.emit_done, s));
 	L.used = true;
 	L.coll_pending = false;
 	c->last_lane = li;
@@ -367,7 +361,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	if (out_done)
 		*out_done = L.emit_done;
 	if (c->prof) {
-		CU(c, cudaEventRecord(c->pe[3], s_emit));
+		CU(c, cudaEventRecord(c->pe[3], s));
 		CU(c, cudaEventSynchronize(c->pe[3]));
 		for (int k = 0; k < CB_K_COUNT; k++) {
 			float ms = 0;
@@ -386,6 +380,11 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
 	DevState h;
 	BatchCtl b;
 	memset(&b, 0, sizeof(b));
+	unsigned long long chain[2] = {0, 0};
+	CU(c, cudaMemcpy(chain, c->d_chain, sizeof(chain), cudaMemcpyDeviceToHost));
+	if (chain[1] != 0 || chain[0] != c->chain_seq)
+		return fail(c, CB_ESTATE, "commit chain broken: %llu of %llu batches committed, %llu hand-over timeouts", chain[0],
+		    c->chain_seq, chain[1]);
 	CU(c, cudaMemcpy(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost));
 	if (c->last_lane >= 0)
 		CU(c, cudaMemcpy(&b, c->lane[c->last_lane].ctl, sizeof(b), cudaMemcpyDeviceToHost));
@@ -454,10 +453,22 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 	rc = ensure_staging(c, n);
 	if (rc)
 		return rc;
-	const size_t nchunks = (n + c->chunk - 1) / c->chunk;
+	// Staging chunk: a batch that would fit one chunk is still cut in ~3 so that the copy-in of
+	// one piece overlaps the kernels and the copy-out of the previous ones (measured with
+	// tools/e2e_breakdown.py: 1M claims 1.04 ms as one chunk, 0.50-0.54 ms as 2-4 chunks).
+	size_t chunk = c->chunk;
+	{
+		size_t third = ((n + 2) / 3 + ETILE - 1) / ETILE * ETILE;
+		const size_t floor_chunk = 64 * (size_t)ETILE; // 256K claims: below this the per-chunk cost wins
+		if (third < floor_chunk)
+			third = floor_chunk;
+		if (third < chunk)
+			chunk = third;
+	}
+	const size_t nchunks = (n + chunk - 1) / chunk;
 	for (size_t ci = 0; ci < nchunks; ci++) {
 		Staging &s = c->st[ci % NBUF];
-		const size_t lo = ci * c->chunk, m = (n - lo < c->chunk) ? n - lo : c->chunk;
+		const size_t lo = ci * chunk, m = (n - lo < chunk) ? n - lo : chunk;
 		if (ci >= NBUF)
 			CU(c, cudaStreamWaitEvent(c->s_in, s.out_done, 0));
 		CU(c, cudaMemcpyAsync(s.start, (const char *)start + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
@@ -614,9 +625,6 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	} while (0)
 	CU0(cudaSetDevice(device));
 	CU0(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-	CU0(cudaStreamCreateWithFlags(&c->st_scan, cudaStreamNonBlocking));
-	CU0(cudaStreamCreateWithFlags(&c->st_res, cudaStreamNonBlocking));
-	CU0(cudaStreamCreateWithFlags(&c->st_emit, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->st_coll, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -624,16 +632,17 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
+	CU0(cudaMalloc((void **)&c->d_chain, 2 * sizeof(unsigned long long)));
+	CU0(cudaMemset(c->d_chain, 0, 2 * sizeof(unsigned long long)));
 	for (int l = 0; l < CB_LANES; l++) {
 		Lane &L = c->lane[l];
 		CU0(cudaMalloc((void **)&L.ctl, sizeof(BatchCtl)));
 		CU0(cudaMemset(L.ctl, 0, sizeof(BatchCtl)));
 		CU0(cudaMalloc((void **)&L.ticket, 64));
 		CU0(cudaMemset(L.ticket, 0, 64));
-		CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.res_done, cudaEventDisableTiming));
-		CU0(cudaEventCreateWithFlags(&L.prep_done, cudaEventDisableTiming));
-		CU0(cudaStreamCreateWithFlags(&L.st_prep, cudaStreamNonBlocking));
+		CU0(cudaEventCreateWithFlags(&L.join_ev, cudaEventDisableTiming));
+		CU0(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
 		CU0(cudaEventCreateWithFlags(&L.emit_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.coll_done, cudaEventDisableTiming));
 	}
@@ -646,6 +655,10 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	CU0(cudaFuncSetAttribute(prepare_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(prepare_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(commit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(commit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(commit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(commit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 #undef CU0
@@ -657,7 +670,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 	if (!c)
 		return;
 	cudaSetDevice(c->device);
-	cudaStream_t all[] = {c->st_scan, c->st_res, c->st_emit, c->st_coll, c->s_in, c->s_out, c->own_stream};
+	cudaStream_t all[] = {c->st_coll, c->s_in, c->s_out, c->own_stream};
 	for (cudaStream_t s : all)
 		if (s)
 			cudaStreamSynchronize(s);
@@ -665,21 +678,21 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		g_nccl.CommDestroy(c->comm);
 	for (int l = 0; l < CB_LANES; l++) {
 		Lane &L = c->lane[l];
-		if (L.st_prep) {
-			cudaStreamSynchronize(L.st_prep);
-			cudaStreamDestroy(L.st_prep);
+		if (L.st) {
+			cudaStreamSynchronize(L.st);
+			cudaStreamDestroy(L.st);
 		}
 		void *fr[] = {L.idx_ms, L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
 		    L.ev_q, L.ev_d, L.rec_code, L.xev, L.hj_lo, L.hj_b, L.tile_now0, L.iv_lo, L.iv_hi, L.iv_cum, L.ev_now, L.hj_F};
 		for (void *p : fr)
 			if (p)
 				cudaFree(p);
-		cudaEvent_t evs[] = {L.scan_done, L.prep_done, L.res_done, L.emit_done, L.coll_done};
+		cudaEvent_t evs[] = {L.res_done, L.emit_done, L.coll_done, L.join_ev};
 		for (cudaEvent_t e : evs)
 			if (e)
 				cudaEventDestroy(e);
 	}
-	void *frees[] = {c->g, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight, c->d_ints,
+	void *frees[] = {c->g, c->d_chain, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight, c->d_ints,
 	    c->d_dbl};
 	for (void *p : frees)
 		if (p)
@@ -732,10 +745,15 @@ extern "C" int cb_join(cb_ctx *c) {
 	if (!c)
 		return CB_EINVAL;
 	if (c->last_lane >= 0 && c->depth > 1) {
-		Lane &L = c->lane[c->last_lane];
-		CU(c, cudaStreamWaitEvent(c->stream, L.emit_done, 0)); // emits run in order on one stream
-		if (L.coll_pending)
-			CU(c, cudaStreamWaitEvent(c->stream, L.coll_done, 0));
+		for (int l = 0; l < CB_LANES; l++) {
+			Lane &L = c->lane[l];
+			if (!L.used)
+				continue;
+			CU(c, cudaEventRecord(L.join_ev, L.st));
+			CU(c, cudaStreamWaitEvent(c->stream, L.join_ev, 0));
+			if (L.coll_pending)
+				CU(c, cudaStreamWaitEvent(c->stream, L.coll_done, 0));
+		}
 	}
 	return CB_OK;
 }
@@ -1141,6 +1159,9 @@ extern "C" int cb_allreduce_counts(cb_ctx *c) {
 extern "C" int cb_profile_enable(cb_ctx *c, int on) {
 	if (!c)
 		return CB_EINVAL;
+	int rc = drain(c); // batches in flight were enqueued under the other mode
+	if (rc)
+		return rc;
 	c->prof = on != 0;
 	for (int k = 0; k < CB_K_COUNT; k++) {
 		c->prof_ms[k] = 0;
@@ -1160,6 +1181,21 @@ extern "C" int cb_profile_get(cb_ctx *c, double ms_out[CB_K_COUNT], uint64_t lau
 	return CB_OK;
 }
 extern "C" uint64_t cb_launch_count(const cb_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int cb_debug_lane_timestamps(cb_ctx *c, int lane, uint64_t out[16]) {
+	if (!c || !out || lane < 0 || lane >= CB_LANES)
+		return CB_EINVAL;
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	BatchCtl b;
+	memset(&b, 0, sizeof(b));
+	if (c->lane[lane].ctl)
+		CU(c, cudaMemcpy(&b, c->lane[lane].ctl, sizeof(b), cudaMemcpyDeviceToHost));
+	for (int k = 0; k < 16; k++)
+		out[k] = b.dbg[k];
+	return CB_OK;
+}
 
 extern "C" int cb_debug_timestamps(cb_ctx *c, uint64_t out[16]) {
 	if (!c || !out)

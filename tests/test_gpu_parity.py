@@ -146,6 +146,34 @@ def test_device_resident_api_and_streaming_batches(cb):
     assert st.cursor == ost.cursor and st.total_drops == ost.drops
 
 
+@pytest.mark.parametrize("depth", [1, 2, 5, 8])
+def test_raw_pointer_calls_any_pipeline_depth(cb, depth):
+    """admit_batch_ptr (raw device addresses, the native caller's form) over many small batches with
+    1..8 batches in flight: decisions, slots and the carried state equal one sequential drain."""
+    import torch
+    n, m, tgt = 1_200_000, 37_500, 5
+    start, now = tracegen.gen_trace(n, seed=77, de=1_000, unit=1 << 13)
+    ctx = cb.Context(0)
+    ctx.codel_init(tgt)
+    ctx.backends_set(8, tracegen.gen_insert_draws(8), 61)
+    ctx.set_pipeline_depth(depth)
+    dev = torch.device("cuda:0")
+    ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+    dec = torch.empty(n, dtype=torch.uint8, device=dev)
+    slot = torch.empty(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for lo in range(0, n, m):
+        k = min(m, n - lo)
+        ctx.admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo, None, k,
+                            dec.data_ptr() + lo, slot.data_ptr() + 4 * lo, None)
+    st = ctx.stats()
+    od, os_, ostate, ost = oracle_run(start, now, None, tgt, 61)
+    assert np.array_equal(dec.cpu().numpy(), od)
+    assert np.array_equal(slot.cpu().numpy(), os_)
+    util.assert_state_equal(gpu_state(st), ostate)
+    assert st.cursor == ost.cursor and st.total_drops == ost.drops
+
+
 def test_host_pipeline_chunking(cb, monkeypatch):
     """The host-buffer entry point splits into chunks (H2D/compute/D2H overlap): same answer."""
     monkeypatch.setenv("CB_CHUNK", "65536")
