@@ -213,6 +213,23 @@ int cb_comm_unique_id(void *out, size_t *bytes); /* ncclGetUniqueId; bytes in/ou
 int cb_comm_init(cb_ctx *ctx, int nranks, int rank, const void *unique_id, size_t bytes);
 int cb_allreduce_counts(cb_ctx *ctx); /* async on the context's stream */
 
+/* One logical queue over R GPUs: batch k of rank r is the queue segment that
+ * follows batch k of rank r-1 (and batch k of rank 0 follows batch k-1 of rank R-1), exactly as if
+ * one ConnectionPool had drained the concatenation.  The ControlledDelay state and the admit cursor
+ * travel round a ring of device mailboxes: the kernel that commits a batch waits for its
+ * predecessor's state in this rank's mailbox and stores its own result into the next rank's mailbox
+ * through NVLink peer memory -- no host round trip, no collective on the data path.  Every rank must
+ * submit the same number of batches; rank r's cb_codel_get_state is the state after its latest
+ * segment (the last rank's is the queue's).
+ *   cb_ring_mailbox : this context's mailbox as a CUDA IPC handle (64 bytes; for other processes)
+ *                     and/or as a device pointer (for contexts of the same process).
+ *   cb_ring_connect : join a ring of `nranks` as `rank`, given the NEXT rank's ((rank+1)%nranks)
+ *                     mailbox by IPC handle or by pointer; nranks == 0 leaves the ring.  Call it on
+ *                     every rank before the first batch, after cb_codel_init / cb_codel_set_state
+ *                     (rank 0's state at that moment is the queue's initial state). */
+int cb_ring_mailbox(cb_ctx *ctx, void *ipc_handle_out, size_t *len, void **local_ptr_out);
+int cb_ring_connect(cb_ctx *ctx, int nranks, int rank, const void *next_ipc_handle, void *next_local_ptr);
+
 /* ------------------------------------------------------------- measurement */
 
 /* Per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg).

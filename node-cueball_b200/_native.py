@@ -25,6 +25,7 @@ SYMBOLS = [
     "cb_backend_added", "cb_backend_removed", "cb_reshuffle", "cb_backends_get", "cb_plan_rebalance",
     "cb_comm_unique_id", "cb_comm_init", "cb_allreduce_counts", "cb_profile_enable", "cb_profile_get",
     "cb_launch_count", "cb_debug_timestamps", "cb_debug_lane_timestamps",
+    "cb_ring_mailbox", "cb_ring_connect",
 ]
 
 
@@ -111,6 +112,8 @@ def lib():
     L.cb_launch_count.restype = u64
     L.cb_debug_timestamps.argtypes = [vp, C.POINTER(u64)]
     L.cb_debug_lane_timestamps.argtypes = [vp, C.c_int, C.POINTER(u64)]
+    L.cb_ring_mailbox.argtypes = [vp, vp, C.POINTER(sz), C.POINTER(vp)]
+    L.cb_ring_connect.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     _lib = L
     return L
 

@@ -220,6 +220,20 @@ class Context(object):
         self._ck(self._L.cb_debug_timestamps(self._h, out))
         return list(out)
 
+    # ------------------------------------------------ one queue over several GPUs
+    def ring_mailbox(self):
+        """(ipc_handle: bytes, local_ptr: int) of this context's mailbox."""
+        buf = C.create_string_buffer(64)
+        ln = C.c_size_t(64)
+        ptr = C.c_void_p()
+        self._ck(self._L.cb_ring_mailbox(self._h, buf, C.byref(ln), C.byref(ptr)))
+        return buf.raw[:ln.value], int(ptr.value)
+
+    def ring_connect(self, nranks, rank, next_handle=None, next_ptr=None):
+        hb = C.create_string_buffer(next_handle, len(next_handle)) if next_handle else None
+        self._ck(self._L.cb_ring_connect(self._h, int(nranks), int(rank), hb,
+                                         C.c_void_p(next_ptr) if next_ptr else None))
+
     def debug_lane_timestamps(self, lane):
         out = (C.c_uint64 * 16)()
         self._ck(self._L.cb_debug_lane_timestamps(self._h, int(lane), out))

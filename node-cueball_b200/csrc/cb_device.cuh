@@ -70,6 +70,25 @@ struct alignas(32) SumDesc {
 	unsigned long long pad;
 };
 
+// The commit chain.  Batches commit their ControlledDelay state strictly in queue order; the
+// order is kept on the device: a commit kernel spins until `*wait_word == wait_val`, and the batch
+// publishes `*post_word = post_val` once its state (and admit cursor) is final.
+//   one GPU:        wait_word == post_word == the context's chain word; the state stays in DevState.
+//   one queue over R GPUs (ring): wait_word is this rank's mailbox, written by the previous rank over
+//   NVLink peer memory; the state arrives in the mailbox (in_state) and is pushed on to the next
+//   rank's mailbox (post_state) before its word is released at system scope.
+struct ChainMem {
+	unsigned long long seq; // the chain word / mailbox sequence number
+	unsigned long long err; // hand-over timeouts (a broken chain must not hang the device)
+	DevState st;            // ring mode: the state handed to this rank
+};
+struct ChainLink {
+	unsigned long long *wait_word, *post_word, *err;
+	unsigned long long wait_val, post_val, timeout_ns;
+	const DevState *in_state;
+	DevState *post_state;
+};
+
 __device__ __forceinline__ unsigned long long gtimer() {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -83,6 +102,14 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 __device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
 	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ double ld_relaxed_f64(const double *p) {
 	double v;
 	asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -92,6 +119,49 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 	unsigned long long v;
 	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
+}
+
+__device__ __forceinline__ void chain_copy_state(DevState *dst, const DevState *src) {
+	dst->F = src->F;
+	dst->D = src->D;
+	dst->C = src->C;
+	dst->B = src->B;
+	dst->hasE = src->hasE;
+	dst->E = src->E;
+	dst->cursor = src->cursor;
+	dst->tot_drops = src->tot_drops;
+	dst->tot_admits = src->tot_admits;
+}
+// one thread: wait for the previous batch of the queue; in ring mode take over its state
+__device__ __forceinline__ void chain_wait(const ChainLink &ln, DevState *g) {
+	const unsigned long long t0 = gtimer();
+	if (ln.in_state) {
+		while (ld_acquire_sys(ln.wait_word) != ln.wait_val) {
+			if (gtimer() - t0 > ln.timeout_ns) {
+				atomicAdd(ln.err, 1ull);
+				break;
+			}
+		}
+		chain_copy_state(g, ln.in_state);
+	} else {
+		while (ld_acquire(ln.wait_word) != ln.wait_val) {
+			if (gtimer() - t0 > ln.timeout_ns) {
+				atomicAdd(ln.err, 1ull);
+				break;
+			}
+		}
+	}
+}
+// one thread, after the batch's last write to DevState
+__device__ __forceinline__ void chain_post(const ChainLink &ln, const DevState *g) {
+	if (ln.post_state) {
+		chain_copy_state(ln.post_state, g); // peer memory (NVLink) unless the ring has one member
+		__threadfence_system();
+		st_release_sys(ln.post_word, ln.post_val);
+	} else {
+		__threadfence();
+		st_release(ln.post_word, ln.post_val);
+	}
 }
 
 // ---------------------------------------------------------------------------------------

@@ -44,8 +44,7 @@ struct EmitParams {
 	int table_smem_bytes;          // 0 = read the table through L1/L2 instead
 	SumDesc *sdesc;
 	unsigned long long epoch;
-	unsigned long long *chain; // commit chain word: a flags batch passes it on from here
-	unsigned long long seq;
+	ChainLink link; // a flags batch passes the commit chain on from here (its cursor is final then)
 	unsigned int *ticket;          // CTA completion counter (flags variant finalisation)
 	int vec_ok;                    // outputs suitably aligned for vector stores
 };
@@ -464,8 +463,7 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 				g->tot_admits += admits;
 				bc->gcounts[0] = drops;
 				bc->gcounts[1] = admits;
-				__threadfence();
-				st_release(&p.chain[0], p.seq + 1); // the next batch's commit may read the cursor now
+				chain_post(p.link, g); // the next batch's commit may read the cursor now
 			}
 		}
 	}

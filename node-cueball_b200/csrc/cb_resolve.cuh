@@ -47,8 +47,7 @@ struct ResolveParams {
 	const unsigned int *rec_cend;
 	const void *tile_now0;              // raw clock of every tile's first claim (coarse search index)
 	double *idx_ms;                     // [<= NIDX_MAX] the coarse index in ms (prepare -> commit)
-	unsigned long long *chain;          // [0] batches whose state is committed, [1] hand-over timeouts
-	unsigned long long seq;             // this batch's position in the chain
+	ChainLink link;                     // this batch's place in the commit chain
 	// cross-tile run events (<= 3 per closing tile; slot `tiles` = the run open at batch end)
 	unsigned long long *xev;            // [(tiles+1)*3]
 	unsigned int *xcnt;                 // [tiles+1]
@@ -645,13 +644,7 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 		// ---- hand-over: wait until the previous batch has committed its state.  It was launched
 		// before this one (possibly on another stream), so it is running or about to; the bound only
 		// keeps a broken chain from hanging the device.
-		const unsigned long long t0 = gtimer();
-		while (ld_acquire(&p.chain[0]) != p.seq) {
-			if (gtimer() - t0 > 4000000000ull) {
-				atomicAdd(&p.chain[1], 1ull);
-				break;
-			}
-		}
+		chain_wait(p.link, g);
 		bc->dbg[12] = gtimer();
 	}
 	__syncthreads();
@@ -659,10 +652,8 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 		if (warp == 0) {
 			sequential_path<NS>(p, lane);
 			__syncwarp();
-			if (lane == 0) {
-				__threadfence();
-				st_release(&p.chain[0], p.seq + 1);
-			}
+			if (lane == 0)
+				chain_post(p.link, g);
 		}
 		return;
 	}
@@ -858,8 +849,7 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 				g->cursor += admits; // the emit kernel works from cursor0
 				// the next batch's commit may go ahead (a flags batch finishes the cursor in its emit
 				// kernel, which then passes the chain on)
-				__threadfence();
-				st_release(&p.chain[0], p.seq + 1);
+				chain_post(p.link, g);
 			} else {
 				bc->drops = 0; // accumulated by the emit kernel (waiting handles only)
 				bc->admits = 0;

@@ -105,8 +105,12 @@ struct cb_ctx {
 	int depth = CB_DEFAULT_DEPTH;
 	Lane lane[CB_LANES];
 	unsigned long long seq = 0;        // batches enqueued so far
-	unsigned long long *d_chain = nullptr; // [0] batches committed, [1] hand-over timeouts (device)
-	unsigned long long chain_seq = 0;      // batches enqueued
+	ChainMem *d_chain = nullptr;           // the chain word; in ring mode this rank's mailbox
+	unsigned long long chain_seq = 0;      // batches enqueued (since the ring was connected, in ring mode)
+	// one logical queue over several GPUs: the state goes round a ring of mailboxes (peer memory)
+	int ring_n = 0, ring_rank = 0;
+	ChainMem *ring_next = nullptr;         // the next rank's mailbox
+	bool ring_next_ipc = false;            // ... opened from an IPC handle (to be closed)
 	int last_lane = -1;
 	bool last_flags = false;
 	int emit_grid = 148 * 4;           // persistent emit CTAs (from the device's SM count)
@@ -153,6 +157,15 @@ template <typename T> int dev_alloc(cb_ctx *c, T **p, size_t count) {
 	cudaError_t e = cudaMalloc((void **)p, count * sizeof(T) + 64);
 	if (e != cudaSuccess)
 		return fail(c, CB_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+	return CB_OK;
+}
+
+static int ring_close(cb_ctx *c) {
+	if (c->ring_next && c->ring_next_ipc)
+		cudaIpcCloseMemHandle(c->ring_next);
+	c->ring_next = nullptr;
+	c->ring_next_ipc = false;
+	c->ring_n = 0;
 	return CB_OK;
 }
 
@@ -251,8 +264,25 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.rec_cend = L.rec_cend;
 	rp.tile_now0 = L.tile_now0;
 	rp.idx_ms = L.idx_ms;
-	rp.chain = c->d_chain;
-	rp.seq = c->chain_seq;
+	{
+		ChainLink &ln = rp.link;
+		ln.err = &c->d_chain->err;
+		ln.wait_word = &c->d_chain->seq;
+		if (c->ring_n > 0) {
+			ln.wait_val = c->chain_seq * (unsigned long long)c->ring_n + (unsigned long long)c->ring_rank;
+			ln.in_state = &c->d_chain->st;
+			ln.post_word = &c->ring_next->seq;
+			ln.post_state = &c->ring_next->st;
+			ln.timeout_ns = 30000000000ull; // the other ranks are other processes: allow for start-up skew
+		} else {
+			ln.wait_val = c->chain_seq;
+			ln.in_state = nullptr;
+			ln.post_word = &c->d_chain->seq;
+			ln.post_state = nullptr;
+			ln.timeout_ns = 4000000000ull;
+		}
+		ln.post_val = ln.wait_val + 1;
+	}
 	rp.xev = L.xev;
 	rp.xcnt = L.xcnt;
 	rp.hj_lo = L.hj_lo;
@@ -295,8 +325,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	ep.sdesc = L.sdesc;
 	ep.epoch = L.epoch;
 	ep.ticket = L.ticket;
-	ep.chain = c->d_chain;
-	ep.seq = c->chain_seq;
+	ep.link = rp.link;
 	ep.vec_ok = (((uintptr_t)d_decision & 7) == 0) && (((uintptr_t)d_slot & 15) == 0) &&
 	    (((uintptr_t)d_backend & 15) == 0);
 	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
@@ -382,7 +411,7 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
 	memset(&b, 0, sizeof(b));
 	unsigned long long chain[2] = {0, 0};
 	CU(c, cudaMemcpy(chain, c->d_chain, sizeof(chain), cudaMemcpyDeviceToHost));
-	if (chain[1] != 0 || chain[0] != c->chain_seq)
+	if (chain[1] != 0 || (c->ring_n == 0 && chain[0] != c->chain_seq))
 		return fail(c, CB_ESTATE, "commit chain broken: %llu of %llu batches committed, %llu hand-over timeouts", chain[0],
 		    c->chain_seq, chain[1]);
 	CU(c, cudaMemcpy(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost));
@@ -632,8 +661,8 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
-	CU0(cudaMalloc((void **)&c->d_chain, 2 * sizeof(unsigned long long)));
-	CU0(cudaMemset(c->d_chain, 0, 2 * sizeof(unsigned long long)));
+	CU0(cudaMalloc((void **)&c->d_chain, sizeof(ChainMem)));
+	CU0(cudaMemset(c->d_chain, 0, sizeof(ChainMem)));
 	for (int l = 0; l < CB_LANES; l++) {
 		Lane &L = c->lane[l];
 		CU0(cudaMalloc((void **)&L.ctl, sizeof(BatchCtl)));
@@ -692,6 +721,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 			if (e)
 				cudaEventDestroy(e);
 	}
+	ring_close(c);
 	void *frees[] = {c->g, c->d_chain, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight, c->d_ints,
 	    c->d_dbl};
 	for (void *p : frees)
@@ -1126,6 +1156,67 @@ extern "C" int cb_comm_init(cb_ctx *c, int nranks, int rank, const void *unique_
 	}
 	c->nranks = nranks;
 	c->rank = rank;
+	return CB_OK;
+}
+
+// ---- one logical queue over several GPUs ------------------------------------------------------
+extern "C" int cb_ring_mailbox(cb_ctx *c, void *ipc_handle_out, size_t *len, void **local_ptr_out) {
+	if (!c)
+		return CB_EINVAL;
+	if (ipc_handle_out) {
+		if (!len || *len < sizeof(cudaIpcMemHandle_t))
+			return fail(c, CB_EINVAL, "the IPC handle needs %zu bytes", sizeof(cudaIpcMemHandle_t));
+		cudaIpcMemHandle_t h;
+		CU(c, cudaIpcGetMemHandle(&h, c->d_chain));
+		memcpy(ipc_handle_out, &h, sizeof(h));
+		*len = sizeof(h);
+	}
+	if (local_ptr_out)
+		*local_ptr_out = c->d_chain;
+	return CB_OK;
+}
+
+extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next_ipc_handle, void *next_local_ptr) {
+	if (!c)
+		return CB_EINVAL;
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	ring_close(c);
+	if (nranks == 0) { // back to an independent queue: the chain word restarts at the batch count
+		c->chain_seq = 0;
+		CU(c, cudaMemset(c->d_chain, 0, 2 * sizeof(unsigned long long)));
+		return CB_OK;
+	}
+	if (nranks < 1 || rank < 0 || rank >= nranks)
+		return fail(c, CB_EINVAL, "bad ring geometry");
+	if ((next_ipc_handle != nullptr) == (next_local_ptr != nullptr) && nranks > 1)
+		return fail(c, CB_EINVAL, "give the next rank's mailbox either as an IPC handle or as a pointer of this process");
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	if (nranks == 1 && !next_ipc_handle && !next_local_ptr) {
+		c->ring_next = c->d_chain;
+	} else if (next_ipc_handle) {
+		cudaIpcMemHandle_t h;
+		memcpy(&h, next_ipc_handle, sizeof(h));
+		void *ptr = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess)
+			return fail(c, CB_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+		c->ring_next = (ChainMem *)ptr;
+		c->ring_next_ipc = true;
+	} else {
+		c->ring_next = (ChainMem *)next_local_ptr;
+	}
+	// this rank's mailbox: sequence 0, holding this rank's current state (rank 0 starts the queue
+	// from it; the others overwrite it with what they receive)
+	ChainMem m;
+	memset(&m, 0, sizeof(m));
+	CU(c, cudaMemcpy(&m.st, c->g, sizeof(DevState), cudaMemcpyDeviceToHost));
+	CU(c, cudaMemcpy(c->d_chain, &m, sizeof(m), cudaMemcpyHostToDevice));
+	c->ring_n = nranks;
+	c->ring_rank = rank;
+	c->chain_seq = 0;
 	return CB_OK;
 }
 

@@ -174,6 +174,58 @@ def test_raw_pointer_calls_any_pipeline_depth(cb, depth):
     assert st.cursor == ost.cursor and st.total_drops == ost.drops
 
 
+@pytest.mark.parametrize("R,with_flags", [(1, False), (2, False), (3, True), (4, False)])
+def test_one_queue_over_a_ring_of_contexts(cb, R, with_flags):
+    """one logical queue cut into segments that R contexts drain in turn (segment (k, r)
+    follows (k, r-1)); the ControlledDelay state and the admit cursor travel through the ring of device
+    mailboxes.  Here the ring members are contexts of one process on one GPU (mailboxes given by
+    pointer; across processes the same words are reached through CUDA IPC, tests/ring_check.py).
+    Decisions, slots and the final state equal ONE sequential drain of the whole queue."""
+    import torch
+    tgt, nslots = 5, 97
+    rng = np.random.RandomState(1234 + R)
+    steps = 6
+    seg = [[int(x) for x in rng.randint(1, 150_000, size=R)] for _ in range(steps)]
+    seg[1][0] = 1          # a one-claim segment
+    seg[2][R - 1] = 333_333
+    n = sum(sum(x) for x in seg)
+    start, now = tracegen.gen_trace(n, seed=91 + R, de=1_500, unit=1 << 13)
+    flags = util.make_flags(n, 17, cancel_mod=7, empty_mod=40_009) if with_flags else None
+    dev = torch.device("cuda:0")
+    ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+    tf = torch.from_numpy(flags).to(dev) if with_flags else None
+    dec = torch.empty(n, dtype=torch.uint8, device=dev)
+    slot = torch.empty(n, dtype=torch.int32, device=dev)
+    ctxs = []
+    for r in range(R):
+        c = cb.Context(0)
+        c.codel_init(tgt)
+        c.backends_set(16, tracegen.gen_insert_draws(16), nslots)
+        ctxs.append(c)
+    boxes = [c.ring_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.ring_connect(R, r, next_ptr=boxes[(r + 1) % R][1])
+    torch.cuda.synchronize()
+    lo = 0
+    for k in range(steps):
+        for r in range(R):
+            m = seg[k][r]
+            ctxs[r].admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo,
+                                    tf.data_ptr() + lo if with_flags else None, m,
+                                    dec.data_ptr() + lo, slot.data_ptr() + 4 * lo, None)
+            lo += m
+    st = ctxs[R - 1].stats()  # the last rank's state is the queue's
+    for c in ctxs:
+        c.synchronize()
+    od, os_, ostate, ost = oracle_run(start, now, flags, tgt, nslots)
+    assert np.array_equal(dec.cpu().numpy(), od)
+    assert np.array_equal(slot.cpu().numpy(), os_)
+    util.assert_state_equal(gpu_state(st), ostate)
+    assert st.cursor == ost.cursor and st.total_drops == ost.drops and st.total_admits == ost.admits
+    for c in ctxs:
+        c.ring_connect(0, 0)
+
+
 def test_host_pipeline_chunking(cb, monkeypatch):
     """The host-buffer entry point splits into chunks (H2D/compute/D2H overlap): same answer."""
     monkeypatch.setenv("CB_CHUNK", "65536")
