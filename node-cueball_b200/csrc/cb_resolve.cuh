@@ -32,7 +32,7 @@
 
 namespace cb {
 
-constexpr int RTPB = 1024;
+constexpr int RTPB = 512; // half an SM's threads: the CTA fits the slot one retiring scan CTA frees
 
 struct ResolveParams {
 	const void *start;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p)
 			s_warp[warp] = x;
 		__syncthreads();
 		if (warp == 0) {
-			const unsigned int w = s_warp[lane];
+			const unsigned int w = lane < RTPB / 32 ? s_warp[lane] : 0u;
 			unsigned int ws = w;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {

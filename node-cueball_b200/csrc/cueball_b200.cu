@@ -73,8 +73,9 @@ struct Lane {
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr, *tile_now0 = nullptr;
 	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
 	double *ev_now = nullptr, *hj_F = nullptr, *idx_ms = nullptr;
-	cudaStream_t st = nullptr; // all four kernels of the lane's batch run here, in order
-	cudaEvent_t res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
+	cudaStream_t st = nullptr;    // the lane's scan kernel (lowest priority: it fills every SM)
+	cudaStream_t st_hi = nullptr; // prepare, commit, emit (highest priority: they take the first slot that frees up)
+	cudaEvent_t scan_done = nullptr, res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
 	bool used = false, coll_pending = false;
 	unsigned long long epoch = 0;
 };
@@ -171,8 +172,10 @@ static int ring_close(cb_ctx *c) {
 
 // wait for every batch in flight (and the main stream)
 int drain(cb_ctx *c) {
-	for (int l = 0; l < CB_LANES; l++)
+	for (int l = 0; l < CB_LANES; l++) {
 		CU(c, cudaStreamSynchronize(c->lane[l].st));
+		CU(c, cudaStreamSynchronize(c->lane[l].st_hi));
+	}
 	CU(c, cudaStreamSynchronize(c->st_coll));
 	CU(c, cudaStreamSynchronize(c->stream));
 	return CB_OK;
@@ -184,6 +187,7 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 	// growing a lane's scratch: nothing of this lane may be in flight
 	if (L.used) {
 		CU(c, cudaStreamSynchronize(L.st));
+		CU(c, cudaStreamSynchronize(L.st_hi));
 		if (L.coll_pending)
 			CU(c, cudaEventSynchronize(L.coll_done));
 	}
@@ -357,6 +361,12 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s));
 	// prepare: independent of the ControlledDelay state, so it overlaps the other lanes' commits
+	cudaStream_t s_scan = s;
+	if (piped) {
+		CU(c, cudaEventRecord(L.scan_done, s_scan));
+		s = L.st_hi;
+		CU(c, cudaStreamWaitEvent(s, L.scan_done, 0));
+	}
 	if (flags)
 		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	else
@@ -380,8 +390,10 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	c->launches += 4;
 	CU(c, cudaGetLastError());
-	if (out_done || (piped && flags && c->comm))
+	if (out_done || piped)
 		CU(c, cudaEventRecord(L.emit_done, s));
+	if (piped) // the lane's next scan reuses this batch's scratch
+		CU(c, cudaStreamWaitEvent(s_scan, L.emit_done, 0));
 	L.used = true;
 	L.coll_pending = false;
 	c->last_lane = li;
@@ -671,7 +683,13 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		CU0(cudaMemset(L.ticket, 0, 64));
 		CU0(cudaEventCreateWithFlags(&L.res_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.join_ev, cudaEventDisableTiming));
-		CU0(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+		{
+			int least = 0, greatest = 0;
+			CU0(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+			CU0(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, least));
+			CU0(cudaStreamCreateWithPriority(&L.st_hi, cudaStreamNonBlocking, greatest));
+			CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
+		}
 		CU0(cudaEventCreateWithFlags(&L.emit_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.coll_done, cudaEventDisableTiming));
 	}
@@ -707,6 +725,12 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		g_nccl.CommDestroy(c->comm);
 	for (int l = 0; l < CB_LANES; l++) {
 		Lane &L = c->lane[l];
+		if (L.st_hi) {
+			cudaStreamSynchronize(L.st_hi);
+			cudaStreamDestroy(L.st_hi);
+		}
+		if (L.scan_done)
+			cudaEventDestroy(L.scan_done);
 		if (L.st) {
 			cudaStreamSynchronize(L.st);
 			cudaStreamDestroy(L.st);
@@ -779,7 +803,7 @@ extern "C" int cb_join(cb_ctx *c) {
 			Lane &L = c->lane[l];
 			if (!L.used)
 				continue;
-			CU(c, cudaEventRecord(L.join_ev, L.st));
+			CU(c, cudaEventRecord(L.join_ev, L.st_hi));
 			CU(c, cudaStreamWaitEvent(c->stream, L.join_ev, 0));
 			if (L.coll_pending)
 				CU(c, cudaStreamWaitEvent(c->stream, L.coll_done, 0));

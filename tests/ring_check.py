@@ -23,6 +23,7 @@ from cueball_b200 import tracegen
 
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+warm = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # untimed leading steps (timing runs)
 check = os.environ.get("RING_CHECK", "1") != "0"
 R = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -50,8 +51,10 @@ ctx.set_stream(stream.cuda_stream)
 dist.barrier()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(stream)
 for k in range(steps):
+    if k == warm:
+        ctx.join()
+        e0.record(stream)
     lo = k * m
     ctx.admit_batch_ptr(ds.data_ptr() + 8 * lo, dn.data_ptr() + 8 * lo, None, m, dd.data_ptr() + lo, sl.data_ptr() + 4 * lo, None)
 ctx.join()
@@ -75,6 +78,6 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     ms = float(t.item())
     print({"one_queue_ring": True, "n_gpus": R, "claims_per_segment": m, "steps": steps,
-           "ms_per_step": ms / steps, "claims_per_s": n / (ms / 1e3),
+           "ms_per_step": ms / (steps - warm), "claims_per_s": m * R * (steps - warm) / (ms / 1e3),
            "bit_exact_vs_single_queue_oracle": bool(flag.item()) if check else None})
 dist.destroy_process_group()

@@ -39,8 +39,8 @@ for lane in range(depth):
 rows.sort()
 t0 = rows[0][0]
 print("%s depth %d, %d batches of %d claims; times in us relative to the first listed batch's scan start" % (wl, depth, nb, n))
-print("lane  scan[start end]   prepare[start end]   commit[start end]   emit[start end]")
+print("lane  scan[start end]   prepare[start end]   commit[start handed-over end]   emit[start end]")
 prev_commit_end = None
 for _, lane, t in rows:
     f = lambda k: (t[k] - t0) / 1e3
-    print("%4d  %7.1f %7.1f   %7.1f %7.1f   %7.1f %7.1f   %7.1f %7.1f" % (lane, f(8), f(9), f(6), f(4), f(7), f(5), f(10), f(11)))
+    print("%4d  %7.1f %7.1f   %7.1f %7.1f   %7.1f %7.1f %7.1f   %7.1f %7.1f" % (lane, f(8), f(9), f(6), f(4), f(7), f(12), f(5), f(10), f(11)))
