@@ -69,6 +69,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs next to GPU `index` (what numactl / a production host does):
+    pinned host buffers are then allocated on the GPU's own NUMA node, and the end-to-end leg
+    measures the PCIe link instead of the inter-socket fabric.  Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -209,6 +228,7 @@ def run_cuda(args, wl, extra=True):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -325,7 +345,8 @@ def run_cuda(args, wl, extra=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
     e2e = {"value": world * n * ke / te, "unit": "claims/s", "h2d_bytes_per_step": 16 * n,
-           "d2h_bytes_per_step": 5 * n + 176, "steps": ke, "host_memory": "pinned inputs and outputs"}
+           "d2h_bytes_per_step": 5 * n + 176, "steps": ke, "host_memory": "pinned inputs and outputs",
+           "cpu_affinity": ("%d CPUs of the GPU's NUMA node" % numa_cpus) if numa_cpus else "unbound"}
 
     if rank != 0:
         if world > 1:
@@ -341,7 +362,8 @@ def run_cuda(args, wl, extra=True):
                    "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
                          % (nb, 16.0 * n * nb / 1e6),
                    "state": "ControlledDelay state chained on device across steps",
-                   "pipeline": "3 batches in flight: scan(k+1) | resolve(k) | emit(k-1) on three streams",
+                   "pipeline": "up to 5 batches in flight (one lane each: scan on a low-priority stream, prepare/commit/emit on "
+                               "a high-priority one); commits ordered by a device-side chain word",
                    "admit_fraction": st.total_admits / max(st.total_admits + st.total_drops, 1)},
         "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "host_enqueue_ms_per_step": host_ms,
@@ -372,7 +394,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the cpu_baseline leg and the c3 side measurement")
     args = ap.parse_args()
     wl = args.workload or ("c2" if args.gpus == 1 else "c4")
-    dk, dw = {"c2": (50, 5), "c3": (10, 3), "c4": (20, 3), "c5": (10, 3)}[wl]
+    dk, dw = {"c2": (200, 10), "c3": (15, 4), "c4": (30, 5), "c5": (15, 4)}[wl]
     args.steps = args.steps if args.steps is not None else dk
     args.warmup = max(3, args.warmup if args.warmup is not None else dw)
     rank = int(os.environ.get("RANK", "0"))
@@ -385,7 +407,7 @@ def main():
         return
     if not args.no_extra and args.gpus == 1 and wl == "c2":
         # the HBM-roofline-relevant size: one 16M-claim batch per step (BASELINE config C3)
-        a3 = argparse.Namespace(gpus=1, steps=5, warmup=3)
+        a3 = argparse.Namespace(gpus=1, steps=15, warmup=4)
         c3 = run_cuda(a3, "c3", extra=False)
         line["c3"] = {k: c3[k] for k in ("value", "unit", "ms_per_step", "steps", "roofline", "e2e", "gpu_launches")}
     print(json.dumps(line))

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "cb_device.cuh"
 #include "cb_emit.cuh"
@@ -109,6 +110,9 @@ struct cb_ctx {
 	ChainMem *d_chain = nullptr;           // the chain word; in ring mode this rank's mailbox
 	unsigned long long chain_seq = 0;      // batches enqueued (since the ring was connected, in ring mode)
 	// one logical queue over several GPUs: the state goes round a ring of mailboxes (peer memory)
+	// totals as of the last cb_batch_stats_get-style read, valid while no batch has been enqueued since
+	bool tot_valid = false;
+	unsigned long long tot_seq = 0, tot_drops_h = 0, tot_admits_h = 0, tot_epoch = 0, epoch = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
 	bool ring_next_ipc = false;            // ... opened from an IPC handle (to be closed)
@@ -429,6 +433,11 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
 	CU(c, cudaMemcpy(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost));
 	if (c->last_lane >= 0)
 		CU(c, cudaMemcpy(&b, c->lane[c->last_lane].ctl, sizeof(b), cudaMemcpyDeviceToHost));
+	c->tot_valid = true;
+	c->tot_seq = c->chain_seq;
+	c->tot_epoch = c->epoch;
+	c->tot_drops_h = h.tot_drops;
+	c->tot_admits_h = h.tot_admits;
 	memset(out, 0, sizeof(*out));
 	out->n = b.n;
 	out->drops = b.drops;
@@ -486,11 +495,26 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	if (n && (!start || !now))
 		return fail(c, CB_EINVAL, "start/now must not be NULL");
-	int rc = drain(c);
-	if (rc)
-		return rc;
+	static const bool dbg_t = getenv("CB_DEBUG_E2E") != nullptr;
+	auto tnow = []() {
+		struct timespec ts;
+		clock_gettime(CLOCK_MONOTONIC, &ts);
+		return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+	};
+	const double T0 = dbg_t ? tnow() : 0;
+	int rc;
 	DevState h0;
-	CU(c, cudaMemcpy(&h0, c->g, sizeof(h0), cudaMemcpyDeviceToHost));
+	if (c->tot_valid && c->tot_seq == c->chain_seq && c->tot_epoch == c->epoch) {
+		// nothing ran since the totals were last read (which drained the pipeline): no round trip
+		h0.tot_drops = c->tot_drops_h;
+		h0.tot_admits = c->tot_admits_h;
+	} else {
+		rc = drain(c);
+		if (rc)
+			return rc;
+		CU(c, cudaMemcpy(&h0, c->g, sizeof(h0), cudaMemcpyDeviceToHost));
+	}
+	const double T1 = dbg_t ? tnow() : 0;
 	rc = ensure_staging(c, n);
 	if (rc)
 		return rc;
@@ -532,7 +556,12 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 			CU(c, cudaMemcpyAsync(backend + lo, s.backend, m * 4, cudaMemcpyDeviceToHost, c->s_out));
 		CU(c, cudaEventRecord(s.out_done, c->s_out));
 	}
+	const double T2 = dbg_t ? tnow() : 0;
 	CU(c, cudaStreamSynchronize(c->s_out));
+	const double T3 = dbg_t ? tnow() : 0;
+	if (dbg_t)
+		fprintf(stderr, "[cb e2e] n=%zu chunks=%zu  entry sync+state %.0f us | enqueue %.0f us | wait %.0f us\n", n, nchunks,
+		    T1 - T0, T2 - T1, T3 - T2);
 	if (stats) {
 		rc = fetch_stats(c, stats);
 		if (rc)
@@ -836,6 +865,7 @@ extern "C" void cb_host_free(cb_ctx *, void *p) {
 extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
 	if (!c)
 		return CB_EINVAL;
+	c->tot_valid = false;
 	// utils.assertClaimDelay, lib/utils.js:188-195: finite, > 0, integral
 	if (!isfinite(target_ms) || !(target_ms > 0) || target_ms != floor(target_ms))
 		return fail(c, CB_EINVAL, "targetClaimDelay must be a positive integer number of ms");
@@ -865,6 +895,7 @@ extern "C" int cb_codel_get_state(cb_ctx *c, cb_codel_state *out) {
 extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
 	if (!c || !in)
 		return CB_EINVAL;
+	c->tot_valid = false;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	int rc = drain(c);
@@ -885,6 +916,7 @@ extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
 extern "C" int cb_codel_empty(cb_ctx *c, int64_t now_ns) {
 	if (!c)
 		return CB_EINVAL;
+	c->tot_valid = false;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	int rc = drain(c);
@@ -916,6 +948,7 @@ extern "C" int cb_codel_max_idle(cb_ctx *c, int64_t now_ns, double *out_ms) {
 extern "C" int cb_codel_overloaded(cb_ctx *c, int64_t start_ns, int64_t now_ns, int *drop) {
 	if (!c || !drop)
 		return CB_EINVAL;
+	c->tot_valid = false;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	int rc = drain(c);
@@ -1203,6 +1236,7 @@ extern "C" int cb_ring_mailbox(cb_ctx *c, void *ipc_handle_out, size_t *len, voi
 extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next_ipc_handle, void *next_local_ptr) {
 	if (!c)
 		return CB_EINVAL;
+	c->tot_valid = false;
 	int rc = drain(c);
 	if (rc)
 		return rc;
