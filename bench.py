@@ -35,6 +35,10 @@ import sys
 import tempfile
 import time
 
+# more hardware work queues than the default 8, so that the pipeline's streams do not share one
+# (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -348,6 +352,8 @@ def run_cuda(args, wl, extra=True):
            "d2h_bytes_per_step": 5 * n + 176, "steps": ke, "host_memory": "pinned inputs and outputs",
            "cpu_affinity": ("%d CPUs of the GPU's NUMA node" % numa_cpus) if numa_cpus else "unbound"}
 
+    ctx.synchronize()
+    ctx.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -395,6 +401,8 @@ def main():
     args = ap.parse_args()
     wl = args.workload or ("c2" if args.gpus == 1 else "c4")
     dk, dw = {"c2": (200, 10), "c3": (15, 4), "c4": (30, 5), "c5": (15, 4)}[wl]
+    if args.impl == "reference":
+        dk, dw = 8, 3  # ~0.6 s of single-threaded JS per step
     args.steps = args.steps if args.steps is not None else dk
     args.warmup = max(3, args.warmup if args.warmup is not None else dw)
     rank = int(os.environ.get("RANK", "0"))

@@ -177,11 +177,26 @@ static int ring_close(cb_ctx *c) {
 // wait for every batch in flight (and the main stream)
 int drain(cb_ctx *c) {
 	for (int l = 0; l < CB_LANES; l++) {
-		CU(c, cudaStreamSynchronize(c->lane[l].st));
-		CU(c, cudaStreamSynchronize(c->lane[l].st_hi));
+		if (c->lane[l].st)
+			CU(c, cudaStreamSynchronize(c->lane[l].st));
+		if (c->lane[l].st_hi)
+			CU(c, cudaStreamSynchronize(c->lane[l].st_hi));
 	}
 	CU(c, cudaStreamSynchronize(c->st_coll));
 	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
+// A lane's two streams are created when the lane is first used: the device multiplexes streams
+// onto a few hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and every stream that
+// exists makes it likelier that two busy ones share a queue and serialise.
+int lane_streams(cb_ctx *c, Lane &L) {
+	if (L.st)
+		return CB_OK;
+	int least = 0, greatest = 0;
+	CU(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+	CU(c, cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, least));
+	CU(c, cudaStreamCreateWithPriority(&L.st_hi, cudaStreamNonBlocking, greatest));
 	return CB_OK;
 }
 
@@ -190,8 +205,10 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 		return CB_OK;
 	// growing a lane's scratch: nothing of this lane may be in flight
 	if (L.used) {
-		CU(c, cudaStreamSynchronize(L.st));
-		CU(c, cudaStreamSynchronize(L.st_hi));
+		if (L.st)
+			CU(c, cudaStreamSynchronize(L.st));
+		if (L.st_hi)
+			CU(c, cudaStreamSynchronize(L.st_hi));
 		if (L.coll_pending)
 			CU(c, cudaEventSynchronize(L.coll_done));
 	}
@@ -240,6 +257,13 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	int rc = ensure_scratch(c, L, tiles);
 	if (rc)
 		return rc;
+	if (piped) {
+		// size every active lane on the first batch of a new size: the allocations (which synchronise)
+		// happen once, up front, not one lane at a time over the next `depth` batches
+		for (int l = 0; l < c->depth; l++)
+			if ((rc = ensure_scratch(c, c->lane[l], tiles)) || (rc = lane_streams(c, c->lane[l])))
+				return rc;
+	}
 	L.epoch++;
 	const bool flags = d_flags != nullptr;
 
@@ -712,13 +736,7 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		CU0(cudaMemset(L.ticket, 0, 64));
 		CU0(cudaEventCreateWithFlags(&L.res_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.join_ev, cudaEventDisableTiming));
-		{
-			int least = 0, greatest = 0;
-			CU0(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-			CU0(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, least));
-			CU0(cudaStreamCreateWithPriority(&L.st_hi, cudaStreamNonBlocking, greatest));
-			CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
-		}
+		CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.emit_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.coll_done, cudaEventDisableTiming));
 	}
@@ -830,7 +848,7 @@ extern "C" int cb_join(cb_ctx *c) {
 	if (c->last_lane >= 0 && c->depth > 1) {
 		for (int l = 0; l < CB_LANES; l++) {
 			Lane &L = c->lane[l];
-			if (!L.used)
+			if (!L.used || !L.st_hi)
 				continue;
 			CU(c, cudaEventRecord(L.join_ev, L.st_hi));
 			CU(c, cudaStreamWaitEvent(c->stream, L.join_ev, 0));
