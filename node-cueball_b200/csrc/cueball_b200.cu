@@ -719,7 +719,13 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	} while (0)
 	CU0(cudaSetDevice(device));
 	CU0(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-	CU0(cudaStreamCreateWithFlags(&c->st_coll, cudaStreamNonBlocking));
+	{
+		// the drop-count collective is tiny and latency-bound: highest priority, or its kernel queues
+		// behind every scan CTA of the batches in flight
+		int least = 0, greatest = 0;
+		CU0(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+		CU0(cudaStreamCreateWithPriority(&c->st_coll, cudaStreamNonBlocking, greatest));
+	}
 	CU0(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
 	CU0(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
