@@ -113,11 +113,22 @@ template <> struct Raw<true> {
 			return 1; // e >= m: certainly at/above target
 		return 2;
 	}
+	// the same test against two precomputed bounds (lo = tgt - m, hi = tgt + m for a margin m that
+	// is at least every claim's own 2 + now>>50): sojourn < lo -> 0, sojourn >= hi -> 1, else 2
+	static __device__ __forceinline__ int quick2(long long st, long long nw, long long lo, long long hi) {
+		const long long e = nw - st;
+		return e < lo ? 0 : (e >= hi ? 1 : 2);
+	}
+	static __device__ __forceinline__ long long margin_of(long long hi_or) { return 2 + (hi_or >> 18); }
+	static __device__ __forceinline__ long long hi_word(long long x) { return x >> 32; }
 	static __device__ __forceinline__ bool less(long long a, long long b) { return a < b; }
 };
 template <> struct Raw<false> {
 	using t = double;
 	static __device__ __forceinline__ int quick(double, double, long long) { return 2; }
+	static __device__ __forceinline__ int quick2(double, double, long long, long long) { return 2; }
+	static __device__ __forceinline__ long long margin_of(long long) { return 0; }
+	static __device__ __forceinline__ long long hi_word(double) { return 0; }
 	static __device__ __forceinline__ bool less(double a, double b) { return a < b; }
 };
 
@@ -125,6 +136,15 @@ template <bool NS>
 __device__ __forceinline__ bool is_above(typename Raw<NS>::t st, typename Raw<NS>::t nw, long long tgt_ns,
     double target) {
 	const int q = Raw<NS>::quick(st, nw, tgt_ns);
+	if (q != 2)
+		return q == 1;
+	return !(__dsub_rn(TimeIn<NS>::to_ms(nw), TimeIn<NS>::to_ms(st)) < target); // lib/codel.js:35-37
+}
+
+template <bool NS>
+__device__ __forceinline__ bool is_above2(typename Raw<NS>::t st, typename Raw<NS>::t nw, long long lo, long long hi,
+    double target) {
+	const int q = Raw<NS>::quick2(st, nw, lo, hi);
 	if (q != 2)
 		return q == 1;
 	return !(__dsub_rn(TimeIn<NS>::to_ms(nw), TimeIn<NS>::to_ms(st)) < target); // lib/codel.js:35-37
@@ -143,7 +163,7 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 }
 
 template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
 	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
@@ -225,6 +245,24 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 	}
 
 	// ---- phase 1: above bits, CONST/PASS types (integers only) --------------------------------
+	// One margin for all of this lane's claims: the OR of their clocks' high words bounds each
+	// claim's own now>>50 from above, and a wider margin only sends a claim within a few ns of the
+	// target to the exact double comparison.  (A negative clock makes the margin negative: every
+	// claim then takes the exact path.)
+	long long q_lo, q_hi;
+	{
+		long long hi_or = 0;
+#pragma unroll
+		for (int r = 0; r < ROWS; r++)
+			hi_or |= Raw<NS>::hi_word(rn[r][0]) | Raw<NS>::hi_word(rn[r][1]);
+		const long long m = Raw<NS>::margin_of(hi_or);
+		q_lo = tgt_ns - m;
+		q_hi = tgt_ns + m;
+		if (m < 2) { // negative clocks: no shortcut
+			q_lo = (long long)0x8000000000000000ull;
+			q_hi = (long long)0x7fffffffffffffffull;
+		}
+	}
 	unsigned int A0[ROWS], A1[ROWS], C0[ROWS], C1[ROWS]; // ballots: above / CONST-type, per claim slot
 	int nv[ROWS];                                        // valid claims in the row
 	bool nonmono = false;
@@ -242,8 +280,17 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 				nv[r] = rem >= 64 ? 64 : (rem > 0 ? (int)rem : 0);
 			}
 			const bool v0 = FULL || (2 * lane < nv[r]), v1 = FULL || (2 * lane + 1 < nv[r]);
-			const bool ab0 = v0 && is_above<NS>(rs[r][0], rn[r][0], tgt_ns, target);
-			const bool ab1 = v1 && is_above<NS>(rs[r][1], rn[r][1], tgt_ns, target);
+			// integer test first; the exact double comparison only if some claim of the row is within
+			// the margin of the target (one warp-uniform branch per row instead of one per claim)
+			const int q0 = Raw<NS>::quick2(rs[r][0], rn[r][0], q_lo, q_hi);
+			const int q1 = Raw<NS>::quick2(rs[r][1], rn[r][1], q_lo, q_hi);
+			bool ab0 = v0 && (q0 == 1), ab1 = v1 && (q1 == 1);
+			if (__any_sync(0xffffffffu, (v0 && q0 == 2) || (v1 && q1 == 2))) {
+				if (v0 && q0 == 2)
+					ab0 = !(__dsub_rn(TimeIn<NS>::to_ms(rn[r][0]), TimeIn<NS>::to_ms(rs[r][0])) < target); // lib/codel.js:35-37
+				if (v1 && q1 == 2)
+					ab1 = !(__dsub_rn(TimeIn<NS>::to_ms(rn[r][1]), TimeIn<NS>::to_ms(rs[r][1])) < target);
+			}
 			A0[r] = __ballot_sync(0xffffffffu, ab0);
 			A1[r] = __ballot_sync(0xffffffffu, ab1);
 			if (FLAGS) {
@@ -266,18 +313,12 @@ __global__ void __launch_bounds__(TPB, 2) scan_kernel(const ScanParams p) {
 				C1[r] = __ballot_sync(0xffffffffu, v1) & ~A1[r];
 			}
 			// monotone clock (raw domain: ns-monotone implies ms-monotone)
-			raw_t prevn = __shfl_up_sync(0xffffffffu, rn[r][1], 1);
-			bool haveprevn = lane > 0;
-			if (r > 0) {
-				const raw_t pr = __shfl_sync(0xffffffffu, rn[r - 1][1], 31);
-				if (lane == 0) {
-					prevn = pr;
-					haveprevn = true;
-				}
-			} else if (lane == 0 && have_prev) {
-				prevn = prev_now;
-				haveprevn = true;
-			}
+			// the claim before this lane's pair: lane l-1's second claim; for lane 0 it is lane 31's
+			// second claim of the previous row (or the claim before the chunk) -- one rotated shuffle
+			// in which lane 31 (read by lane 0 only) offers that value
+			const raw_t offer = (lane == 31) ? (r > 0 ? rn[r > 0 ? r - 1 : 0][1] : prev_now) : rn[r][1];
+			const raw_t prevn = __shfl_sync(0xffffffffu, offer, (lane + 31) & 31);
+			const bool haveprevn = (lane > 0) || (r > 0) || have_prev;
 			if ((v1 && Raw<NS>::less(rn[r][1], rn[r][0])) || (v0 && haveprevn && Raw<NS>::less(rn[r][0], prevn)))
 				nonmono = true;
 		}
