@@ -9,7 +9,7 @@ namespace cb {
 
 constexpr int TILE = 2048;        // claims per scan tile (scan and prepare agree on it)
 constexpr int ETILE = 4096;       // claims per emit tile
-constexpr int TPB = 256;         // threads of a scan CTA: 16 warps x 256 claims
+constexpr int TPB = 256;         // threads of a scan CTA: 8 warps x 256 claims
 constexpr int WARPS = TPB / 32;
 constexpr int EVK = 8;          // class-change events a tile can hold before "overflow"
 constexpr double CODEL_INTERVAL = 100.0; // lib/codel.js:16
