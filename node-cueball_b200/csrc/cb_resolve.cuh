@@ -639,6 +639,16 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 		for (unsigned int k = tid; k < nidx; k += CTPB)
 			s_cidx[k] = p.idx_ms[k];
 	}
+	// every state-independent word the serial part reads, fetched now (one round trip, overlapped
+	// with the wait below) instead of one dependent access at a time afterwards
+	const unsigned int cj_exists = fallback ? 0u : bc->cj_exists, cj_closes = bc->cj_closes, anchored = bc->anchored;
+	const unsigned long long cj_close = bc->cj_close;
+	const double now0p100 = bc->now0p100, F_anchor = bc->F_anchor;
+	const unsigned int hasE_new = bc->hasE_new, trailing_marker = bc->trailing_marker;
+	const double E_val = bc->E_val;
+	double now_before_close = 0.0; // clock of the last claim of the inherited stretch
+	if (cj_exists && cj_close > 0)
+		now_before_close = now_at<NS>(p.now, cj_close - 1);
 	if (tid == 0) {
 		s_ncar = 0;
 		// ---- hand-over: wait until the previous batch has committed its state.  It was launched
@@ -659,12 +669,13 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 	}
 	const double F_in = g->F, D_in = g->D;
 	const int B_in = g->B;
+	const unsigned long long C_in = g->C, cursor_in = g->cursor;
 
 	// ---- the stretch inherited from the previous batch (claims [0, close) are all above target) --
-	if (bc->cj_exists) {
-		const unsigned long long close = bc->cj_close;
-		const double F = (F_in != 0.0) ? F_in : bc->now0p100; // F == 0: claim 0 opens the run itself
-		const int cb = claim_class(true, now_at<NS>(p.now, close - 1), F);
+	if (cj_exists) {
+		const unsigned long long close = cj_close;
+		const double F = (F_in != 0.0) ? F_in : now0p100; // F == 0: claim 0 opens the run itself
+		const int cb = claim_class(true, now_before_close, F);
 		// crossings: warp 0 -> first class >= 1, warp 1 -> first class 2 (independent searches)
 		if (cb >= 1 && warp < 2 && (warp == 0 || cb == 2)) {
 			Pred pr;
@@ -690,7 +701,7 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 				tmp[nc++] = evc[0];
 				if (cb == 2 && evc[1] != ~0ull)
 					tmp[nc++] = evc[1];
-				if (bc->cj_closes)
+				if (cj_closes)
 					tmp[nc++] = (close << 2);
 			}
 			for (unsigned int k = 0; k < nc; k++)
@@ -731,9 +742,9 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 	// the searches a failed speculation needs are warp-wide (3-4 dependent accesses, not 20+) ----
 	if (warp == 0) {
 		const bool wr = (lane == 0);
-		double D = g->D;
-		unsigned long long C = g->C;
-		int B = g->B;
+		double D = D_in;
+		unsigned long long C = C_in;
+		int B = B_in;
 		unsigned long long drops = 0;
 		unsigned int niv = 0;
 		const unsigned int k0 = EV_FRONT - s_ncar, nev = EV_FRONT + nevp;
@@ -810,17 +821,17 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 		}
 		// ---- final ControlledDelay state -------------------------------------------------
 		double F;
-		if (bc->anchored)
-			F = bc->F_anchor;
+		if (anchored)
+			F = F_anchor;
 		else // the whole batch is one above-target run without a reset: F is inherited, or opened by claim 0
-			F = (F_in != 0.0) ? F_in : bc->now0p100;
+			F = (F_in != 0.0) ? F_in : now0p100;
 		if (FLAGS) {
-			if (bc->hasE_new) {
+			if (hasE_new) {
 				if (wr) {
-					g->E = bc->E_val;
+					g->E = E_val;
 					g->hasE = 1;
 				}
-				if (bc->trailing_marker)
+				if (trailing_marker)
 					F = 0.0; // trailing empty(): lib/codel.js:93
 			}
 		}
@@ -836,7 +847,7 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 			bc->n_intervals = niv;
 			bc->gcounts[2] = p.n;
 			bc->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)
-			bc->cursor0 = g->cursor;
+			bc->cursor0 = cursor_in;
 			if (!FLAGS) {
 				const unsigned long long admits = p.n - drops;
 				bc->drops = drops;
@@ -846,7 +857,7 @@ __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) 
 				g->tot_admits += admits;
 				bc->gcounts[0] = drops;
 				bc->gcounts[1] = admits;
-				g->cursor += admits; // the emit kernel works from cursor0
+				g->cursor = cursor_in + admits; // the emit kernel works from cursor0
 				// the next batch's commit may go ahead (a flags batch finishes the cursor in its emit
 				// kernel, which then passes the chain on)
 				chain_post(p.link, g);
