@@ -74,9 +74,8 @@ struct Lane {
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr, *tile_now0 = nullptr;
 	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
 	double *ev_now = nullptr, *hj_F = nullptr, *idx_ms = nullptr;
-	cudaStream_t st = nullptr;    // the lane's scan kernel (lowest priority: it fills every SM)
-	cudaStream_t st_hi = nullptr; // prepare, commit, emit (highest priority: they take the first slot that frees up)
-	cudaEvent_t scan_done = nullptr, res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
+	cudaStream_t st = nullptr; // all four kernels of the lane's batch, in order (highest stream priority)
+	cudaEvent_t res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
 	bool used = false, coll_pending = false;
 	unsigned long long epoch = 0;
 };
@@ -113,6 +112,7 @@ struct cb_ctx {
 	// totals as of the last cb_batch_stats_get-style read, valid while no batch has been enqueued since
 	bool tot_valid = false;
 	unsigned long long tot_seq = 0, tot_drops_h = 0, tot_admits_h = 0, tot_epoch = 0, epoch = 0;
+	int prio_least = 0, prio_greatest = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
 	bool ring_next_ipc = false;            // ... opened from an IPC handle (to be closed)
@@ -179,8 +179,6 @@ int drain(cb_ctx *c) {
 	for (int l = 0; l < CB_LANES; l++) {
 		if (c->lane[l].st)
 			CU(c, cudaStreamSynchronize(c->lane[l].st));
-		if (c->lane[l].st_hi)
-			CU(c, cudaStreamSynchronize(c->lane[l].st_hi));
 	}
 	CU(c, cudaStreamSynchronize(c->st_coll));
 	CU(c, cudaStreamSynchronize(c->stream));
@@ -195,8 +193,9 @@ int lane_streams(cb_ctx *c, Lane &L) {
 		return CB_OK;
 	int least = 0, greatest = 0;
 	CU(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-	CU(c, cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, least));
-	CU(c, cudaStreamCreateWithPriority(&L.st_hi, cudaStreamNonBlocking, greatest));
+	c->prio_least = least;
+	c->prio_greatest = greatest;
+	CU(c, cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, greatest));
 	return CB_OK;
 }
 
@@ -207,8 +206,6 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 	if (L.used) {
 		if (L.st)
 			CU(c, cudaStreamSynchronize(L.st));
-		if (L.st_hi)
-			CU(c, cudaStreamSynchronize(L.st_hi));
 		if (L.coll_pending)
 			CU(c, cudaEventSynchronize(L.coll_done));
 	}
@@ -382,19 +379,29 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		CU(c, cudaStreamWaitEvent(s, in_ready, 0));
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[0], s));
-	if (flags)
+	if (piped) {
+		// the lane's stream has the highest priority (prepare / commit / emit take the first CTA slot
+		// that frees up); the scan, which fills every SM, is launched into it at the lowest
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3((unsigned)tiles);
+		cfg.blockDim = dim3(TPB);
+		cfg.stream = s;
+		cudaLaunchAttribute at[1];
+		at[0].id = cudaLaunchAttributePriority;
+		at[0].val.priority = c->prio_least;
+		cfg.attrs = at;
+		cfg.numAttrs = 1;
+		if (flags)
+			CU(c, cudaLaunchKernelEx(&cfg, scan_kernel<NS, true>, sp));
+		else
+			CU(c, cudaLaunchKernelEx(&cfg, scan_kernel<NS, false>, sp));
+	} else if (flags)
 		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s>>>(sp);
 	else
 		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s>>>(sp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s));
 	// prepare: independent of the ControlledDelay state, so it overlaps the other lanes' commits
-	cudaStream_t s_scan = s;
-	if (piped) {
-		CU(c, cudaEventRecord(L.scan_done, s_scan));
-		s = L.st_hi;
-		CU(c, cudaStreamWaitEvent(s, L.scan_done, 0));
-	}
 	if (flags)
 		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	else
@@ -418,10 +425,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	c->launches += 4;
 	CU(c, cudaGetLastError());
-	if (out_done || piped)
+	if (out_done || (piped && flags && c->comm))
 		CU(c, cudaEventRecord(L.emit_done, s));
-	if (piped) // the lane's next scan reuses this batch's scratch
-		CU(c, cudaStreamWaitEvent(s_scan, L.emit_done, 0));
 	L.used = true;
 	L.coll_pending = false;
 	c->last_lane = li;
@@ -742,7 +747,6 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		CU0(cudaMemset(L.ticket, 0, 64));
 		CU0(cudaEventCreateWithFlags(&L.res_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.join_ev, cudaEventDisableTiming));
-		CU0(cudaEventCreateWithFlags(&L.scan_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.emit_done, cudaEventDisableTiming));
 		CU0(cudaEventCreateWithFlags(&L.coll_done, cudaEventDisableTiming));
 	}
@@ -778,12 +782,6 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		g_nccl.CommDestroy(c->comm);
 	for (int l = 0; l < CB_LANES; l++) {
 		Lane &L = c->lane[l];
-		if (L.st_hi) {
-			cudaStreamSynchronize(L.st_hi);
-			cudaStreamDestroy(L.st_hi);
-		}
-		if (L.scan_done)
-			cudaEventDestroy(L.scan_done);
 		if (L.st) {
 			cudaStreamSynchronize(L.st);
 			cudaStreamDestroy(L.st);
@@ -854,9 +852,9 @@ extern "C" int cb_join(cb_ctx *c) {
 	if (c->last_lane >= 0 && c->depth > 1) {
 		for (int l = 0; l < CB_LANES; l++) {
 			Lane &L = c->lane[l];
-			if (!L.used || !L.st_hi)
+			if (!L.used || !L.st)
 				continue;
-			CU(c, cudaEventRecord(L.join_ev, L.st_hi));
+			CU(c, cudaEventRecord(L.join_ev, L.st));
 			CU(c, cudaStreamWaitEvent(c->stream, L.join_ev, 0));
 			if (L.coll_pending)
 				CU(c, cudaStreamWaitEvent(c->stream, L.coll_done, 0));
