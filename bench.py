@@ -38,6 +38,11 @@ import time
 # more hardware work queues than the default 8, so that the pipeline's streams do not share one
 # (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# the per-step collective is a 24-byte sum: one small CTA (see cb_comm_init); NCCL reads these once
+# per process, so they are set before torch initialises it
+if os.environ.get("CB_BENCH_NCCL_DEFAULTS") is None:
+    os.environ.setdefault("NCCL_NTHREADS", "128")
+    os.environ.setdefault("NCCL_MAX_CTAS", "1")
 
 import numpy as np
 

@@ -1226,6 +1226,11 @@ extern "C" int cb_comm_init(cb_ctx *c, int nranks, int rank, const void *unique_
 	if (!g_nccl.load())
 		return fail(c, CB_ENCCL, "libnccl.so.2 not found");
 	CU(c, cudaSetDevice(c->device));
+	// The only collective is a 24-byte sum, latency-bound: keep its kernel to one small CTA so that
+	// it fits the slot one retiring scan CTA frees (a 512+-thread CTA needs a whole SM's registers and
+	// waits for the scans of every batch in flight to drain).  The host application's settings win.
+	setenv("NCCL_NTHREADS", "128", 0);
+	setenv("NCCL_MAX_CTAS", "1", 0);
 	nccl_uid id;
 	memcpy(&id, unique_id, sizeof(id));
 	int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
