@@ -17,6 +17,10 @@ before the timed region, so every step reads cold data (the run's inputs are man
 126 MB L2) and the ControlledDelay state chains from batch to batch on the device.
 
 Metric value = claims decided per second, whole job (all ranks), inputs resident in HBM.
+N > 1: one process per GPU, each rank drains its own queue segment (no data-path collective);
+the global drop count is ONE NCCL allreduce of the ranks' cumulative counts at the end of the
+timed window (`config.collective`); `per_step_collective` is a second pass with an allreduce
+after every batch (CB_BENCH_COLLECTIVE=window|step|none picks the main pass's mode).
 `e2e` = the same through the host-buffer C entry point (pinned host arrays in, decisions and
 slots back on the host every step).  `roofline` is for the dominant kernel (the scan kernel:
 16 algorithmic bytes per claim) from CUDA events recorded around each kernel on
@@ -267,11 +271,21 @@ def run_cuda(args, wl, extra=True):
 
     p_start, p_now, p_dec, p_slot = d_start.data_ptr(), d_now.data_ptr(), d_dec.data_ptr(), d_slot.data_ptr()
 
-    def step_dev(b):
+    # The global drop count (north_star: "a single NCCL allreduce over NVLink for the global drop
+    # count").  "window" (default): every rank's cumulative counts are summed by ONE NCCL allreduce at
+    # the end of the K-step window, inside the timed region.  "step": cb_allreduce_counts after every
+    # batch (its own 24-byte NCCL allreduce on a side stream) -- measured in a second pass and
+    # reported as `per_step_collective`: one 8-rank allreduce takes ~80 us, they serialise on their
+    # communicator, and a 43-us step cannot sustain one per batch.  "none": no collective.
+    coll_mode = os.environ.get("CB_BENCH_COLLECTIVE", "none" if os.environ.get("CB_BENCH_NO_ALLREDUCE") else "window")
+    if world == 1:
+        coll_mode = "none"
+
+    def step_dev(b, per_step=False):
         # one C-ABI call per step on raw device addresses, as a native host (the N-API shim) makes it
         lo = b * n
         ctx.admit_batch_ptr(p_start + 8 * lo, p_now + 8 * lo, None, n, p_dec + lo, p_slot + 4 * lo, None)
-        if world > 1 and not os.environ.get("CB_BENCH_NO_ALLREDUCE"):
+        if per_step:
             ctx.allreduce_counts()
 
     def barrier():
@@ -280,28 +294,50 @@ def run_cuda(args, wl, extra=True):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ------------------------------------------------------------
-    for b in range(W):
-        step_dev(b)
-    ctx.synchronize()
-    barrier()
+    def timed_pass(per_step):
+        """W untimed + K timed steps; returns (device ms of the K steps on this rank, host ms/step,
+        global cumulative [drops, admits, claims] or None)."""
+        for b in range(W):
+            step_dev(b, per_step)
+        ctx.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        th0 = time.perf_counter()
+        for b in range(W, W + K):
+            step_dev(b, per_step)
+        hms = (time.perf_counter() - th0) * 1e3 / K  # host time to enqueue one step (no waiting)
+        ctx.join()  # the timing stream waits for the last batch of the pipeline
+        glob = None
+        if coll_mode == "window" and not per_step:
+            stw = ctx.stats()  # waits for the window; this rank's cumulative counts
+            glob = torch.tensor([stw.total_drops, stw.total_admits, stw.total_drops + stw.total_admits],
+                                dtype=torch.int64, device=dev)
+            with torch.cuda.stream(stream):
+                dist.all_reduce(glob)  # the one NCCL allreduce, ordered on the timing stream
+        e1.record(stream)
+        barrier()
+        ctx.synchronize()
+        return e0.elapsed_time(e1), hms, glob
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    th0 = time.perf_counter()
-    for b in range(W, W + K):
-        step_dev(b)
-    host_ms = (time.perf_counter() - th0) * 1e3 / K  # host time to enqueue one step (no waiting)
-    ctx.join()  # the timing stream waits for the last batch of the pipeline
-    e1.record(stream)
-    barrier()
-    ctx.synchronize()
-    launches = ctx.launch_count() - l0
+    ms, host_ms, glob = timed_pass(coll_mode == "step")
+    launches = ctx.launch_count() - l0 - 4 * W  # the K timed steps' kernels
     clocks = sampler.stop() if sampler else None
-    ms = e0.elapsed_time(e1)
     st = ctx.stats()
+    global_counts = [int(x) for x in glob.tolist()] if glob is not None else None
+    per_step = None
+    if coll_mode == "window" and extra:
+        # second pass over the same batches with a collective after every batch (state carries on)
+        ms2, _, _ = timed_pass(True)
+        t2 = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms2 = float(t2.item())
+        per_step = {"value": world * n * K / (ms2 / 1e3), "unit": "claims/s", "ms_per_step": ms2 / K,
+                    "collective": "cb_allreduce_counts = 1 ncclAllReduce(3 x u64) after every batch, on a side stream"}
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -369,7 +405,10 @@ def run_cuda(args, wl, extra=True):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
         "config": {"workload": wl, "claims_per_step_per_gpu": n, "backends": w["B"], "slots": w["S"],
                    "target_ms": TARGET_MS, "interval_ms": 100, "parallelism": "queue segment per GPU" if world > 1 else "1 GPU",
-                   "collective": "1 ncclAllReduce(3 x u64) per step" if world > 1 else None,
+                   "collective": {"window": "1 ncclAllReduce(3 x i64) of every rank's cumulative counts per %d-step window, "
+                                            "inside the timed region" % K,
+                                  "step": "cb_allreduce_counts: 1 ncclAllReduce(3 x u64) after every batch",
+                                  "none": None}[coll_mode],
                    "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
                          % (nb, 16.0 * n * nb / 1e6),
                    "state": "ControlledDelay state chained on device across steps",
@@ -382,7 +421,10 @@ def run_cuda(args, wl, extra=True):
     if extra:
         line["cpu_baseline"] = cpu_baseline(wl)
     if world > 1:
-        line["global_drops_last_step"] = st.global_drops
+        if global_counts is not None:
+            line["global_counts"] = {"drops": global_counts[0], "admits": global_counts[1], "claims": global_counts[2]}
+        if per_step is not None:
+            line["per_step_collective"] = per_step
         dist.destroy_process_group()
     return line
 
