@@ -521,3 +521,131 @@ cbo_shuffle(int32_t *arr, int32_t n, const double *us) /* lib/utils.js:207-217 *
 		arr[j] = tmp;
 	}
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Event-driven pool model: ConnectionPool#claim + the slot-idle handler + the handle's hard
+ * timeout, over the linked-list Queue above (lib/queue.js-faithful).
+ */
+typedef struct pool_handle {
+	double ch_started;   /* lib/connection-fsm.js:523 */
+	int64_t deadline_ns; /* started + claimTimeout */
+	int64_t ticket;
+	int state; /* 0 waiting, 1 claimed, 2 failed, 3 cancelled */
+} pool_handle;
+
+int cbo_pool_sim(cbo_codel *cd, int64_t nslots, uint64_t idle0, uint64_t cursor0, const uint8_t *ev_type,
+    const int64_t *ev_a, const int64_t *ev_b, size_t n_events, int64_t *res, double *timeouts_ms,
+    cbo_pool_result *out) {
+	size_t nclaims = 0, e;
+	for (e = 0; e < n_events; e++)
+		if (ev_type[e] == 0)
+			nclaims++;
+	pool_handle *handles = (pool_handle *)calloc(nclaims ? nclaims : 1, sizeof(pool_handle));
+	cbo_queue *waiters = cbo_queue_new();
+	if (!handles || !waiters)
+		return -1;
+	uint64_t idle = idle0, cursor = cursor0, nres = 0;
+	size_t nh = 0, first_live = 0;
+	cbo_pool_counters c = {0, 0, 0, 0};
+#define ADMIT(h)                                                                     \
+	do {                                                                         \
+		(h)->state = 1;                                                      \
+		res[3 * nres] = (h)->ticket;                                         \
+		res[3 * nres + 1] = 0;                                               \
+		res[3 * nres + 2] = nslots > 0 ? (int64_t)(cursor % (uint64_t)nslots) : -1; \
+		nres++;                                                              \
+		cursor++;                                                            \
+	} while (0)
+	for (e = 0; e < n_events; e++) {
+		const int ty = ev_type[e];
+		const int64_t a = ev_a[e], b = ev_b[e];
+		if (ty == 0 || ty == 1) {
+			/* hard timeouts that have come due, lib/connection-fsm.js:626-642 */
+			size_t t;
+			for (t = first_live; t < nh; t++) {
+				pool_handle *h = &handles[t];
+				if (h->state != 0) {
+					if (t == first_live)
+						first_live++;
+					continue;
+				}
+				if (a >= h->deadline_ns) {
+					h->state = 2;
+					c.claim_timeout++; /* connection-fsm.js:629-630 */
+					res[3 * nres] = h->ticket;
+					res[3 * nres + 1] = 3;
+					res[3 * nres + 2] = -1;
+					nres++;
+				}
+			}
+		}
+		if (ty == 0) {
+			const double now = cbo_ns_to_ms(a);
+			const double timeout = cbo_codel_get_max_idle(cd, now); /* pool.js:880 */
+			c.claim++;                                              /* pool.js:887 */
+			pool_handle *h = &handles[nh];
+			h->ticket = (int64_t)nh;
+			h->ch_started = now; /* connection-fsm.js:523 */
+			h->state = 0;
+			h->deadline_ns = a + (int64_t)(timeout * 1000000.0);
+			timeouts_ms[nh] = timeout;
+			nh++;
+			if (idle > 0) { /* pool.js:934-951 */
+				idle--;
+				ADMIT(h);
+			} else {
+				cbo_queue_push(waiters, h); /* pool.js:960 */
+				if (cbo_queue_length(waiters) > c.max_claim_queue) /* pool.js:962 */
+					c.max_claim_queue = cbo_queue_length(waiters);
+				c.queued_claim++; /* pool.js:963 */
+			}
+		} else if (ty == 1) {
+			const double now = cbo_ns_to_ms(a);
+			int64_t s;
+			for (s = 0; s < b; s++) { /* one handler run per slot */
+				int handed = 0;
+				while (cbo_queue_length(waiters) > 0) { /* pool.js:733 */
+					pool_handle *hdl = (pool_handle *)cbo_queue_shift(waiters);
+					const int drop = cbo_codel_overloaded(cd, now, hdl->ch_started); /* pool.js:735-736 */
+					if (hdl->state != 0) { /* pool.js:738-740 */
+						res[3 * nres] = hdl->ticket;
+						res[3 * nres + 1] = 2;
+						res[3 * nres + 2] = -1;
+						nres++;
+						continue;
+					}
+					if (drop) { /* pool.js:742-745 */
+						hdl->state = 2;
+						c.claim_timeout++; /* connection-fsm.js:633-638 */
+						res[3 * nres] = hdl->ticket;
+						res[3 * nres + 1] = 1;
+						res[3 * nres + 2] = -1;
+						nres++;
+						continue;
+					}
+					ADMIT(hdl); /* pool.js:747-748 */
+					handed = 1;
+					break;
+				}
+				if (!handed) {
+					cbo_codel_empty(cd, now); /* pool.js:751-753 */
+					idle++;                   /* pool.js:756 */
+				}
+			}
+		} else {
+			if (a >= 0 && (size_t)a < nh && handles[a].state == 0)
+				handles[a].state = 3; /* connection-fsm.js:580-587 */
+		}
+	}
+#undef ADMIT
+	out->n_res = nres;
+	out->idle = idle;
+	out->cursor = cursor;
+	out->queued = cbo_queue_length(waiters);
+	out->counters = c;
+	while (!cbo_queue_is_empty(waiters))
+		cbo_queue_shift(waiters);
+	cbo_queue_free(waiters);
+	free(handles);
+	return 0;
+}

@@ -117,6 +117,34 @@ int cbo_build_slots(int32_t B, int32_t S, const double *us, int32_t *keys_out,
 /* utils.shuffle, lib/utils.js:207-217, draws injected */
 void cbo_shuffle(int32_t *arr, int32_t n, const double *us);
 
+/*
+ * Event-driven pool model, same semantics as cb_pool_sim in
+ * oracle/js/driver.js, which drives the reference's own ControlledDelay / Queue:
+ *   ev_type 0  CLAIM at clock ev_a (ns): ConnectionPool#claim, lib/pool.js:874-885 (claimTimeout =
+ *              getMaxIdle()), :887 (counter), :929-966 (idle-first fast path, else enqueue + counters)
+ *           1  IDLE  at clock ev_a (ns): ev_b slots turn idle, the handler lib/pool.js:733-757 runs
+ *              once per slot, every clock read returning ev_a
+ *           2  CANCEL ticket ev_a (handle.cancel() while waiting, lib/connection-fsm.js:580-587)
+ * Before a clocked event, waiting handles whose hard timeout is due (clock >= started + claimTimeout,
+ * lib/connection-fsm.js:626-642) fail in ticket order.  res receives [ticket, code, slot] triples in
+ * resolution order (code 0 admitted, 1 CoDel drop, 2 skipped, 3 hard timeout; at most two per CLAIM: a handle
+ * that timed out is still dequeued, and skipped, later);
+ * timeouts_ms[ticket] = the claim's claimTimeout.
+ */
+typedef struct cbo_pool_counters {
+	uint64_t claim, queued_claim, max_claim_queue, claim_timeout; /* lib/pool.js:269-283 */
+} cbo_pool_counters;
+typedef struct cbo_pool_result {
+	uint64_t n_res;   /* triples written to res */
+	uint64_t idle;    /* slots on the idle queue at the end */
+	uint64_t cursor;  /* admits so far (slot = cursor mod nslots) */
+	uint64_t queued;  /* handles still on the waiter queue */
+	cbo_pool_counters counters;
+} cbo_pool_result;
+int cbo_pool_sim(cbo_codel *cd, int64_t nslots, uint64_t idle0, uint64_t cursor0, const uint8_t *ev_type,
+    const int64_t *ev_a, const int64_t *ev_b, size_t n_events, int64_t *res /* 6 per CLAIM */,
+    double *timeouts_ms /* 1 per CLAIM */, cbo_pool_result *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,10 @@
  *   cb_run_trace    the slot-idle drain loop           lib/pool.js:733-753
  *                   handle creation (ch_started)       lib/connection-fsm.js:523
  *                   enqueue                            lib/pool.js:960
+ *   cb_pool_sim     claim() enqueue side + idle-first   lib/pool.js:874-885,929-966
+ *                   the slot-idle handler, k slots      lib/pool.js:733-757
+ *                   the handle's hard timeout            lib/connection-fsm.js:626-642
+ *                   counters                             lib/pool.js:269-283,887,962-963
  *   cb_build_slots  preference-list random insertion   lib/pool.js:285-291
  *                   (Math.random replaced by injected draws) then the
  *                   reference's own planRebalance      lib/utils.js:239-393
@@ -282,4 +286,106 @@ function cb_bench(seed, n, p, target, nslots) {
 	var t2 = Date.now();
 	return { n: n, push_ms: t1 - t0, drain_ms: t2 - t1, drops: drops, admits: admits,
 	    lastslot: lastslot, state: cb_state(cd), checksum: cb_trace_checksum(tr) };
+}
+
+/*
+ * Event-driven pool model (SURVEY.md 8(f) row 1): the reference's ControlledDelay and Queue,
+ * verbatim, driven by the restated closures of ConnectionPool#claim / the slot-idle handler
+ * and the claim handle's hard timeout.
+ *
+ * job: { target, nslots, state|null, idle0, ev_type:[], ev_a:[], ev_b:[] }
+ *   ev_type 0  CLAIM at clock ev_a (ns)             -> ticket = number of CLAIMs before it
+ *           1  IDLE  at clock ev_a (ns), ev_b slots turn idle, one handler run per slot
+ *           2  CANCEL ticket ev_a                    (handle.cancel() while waiting)
+ * Before an event that carries a clock, every waiting handle whose hard timeout has come due
+ * (clock >= started + claimTimeout) fails with ClaimTimeoutError, oldest ticket first, as its
+ * S.timeout() would have fired.  Slots are anonymous; an admitted claim gets slot cursor % nslots
+ * (SURVEY A.4), whether it took an idle slot at claim() time or was handed one by the drain loop.
+ * Output: res = flat [ticket, code, slot]* in the order handles were resolved
+ *   code 0 admitted, 1 dropped by CoDel (hdl.timeout()), 2 skipped (not waiting when dequeued),
+ *        3 hard timeout; timeouts = claimTimeout per ticket; final state and counters.
+ */
+function cb_pool_sim(job) {
+	var cd = new ControlledDelay(job.target);
+	if (job.state) cb_set_state(cd, job.state);
+	var waiters = new Queue();
+	var handles = [], timeouts = [], res = [];
+	var idle = job.idle0 || 0, cursor = job.cursor || 0, S = job.nslots;
+	var counters = { 'claim': 0, 'queued-claim': 0, 'max-claim-queue': 0, 'claim-timeout': 0 };
+	var first_live = 0;	/* tickets below this are resolved (speeds up the timer scan) */
+	function admit(h) {
+		h.state = 'claimed';
+		res.push(h.ticket, 0, S > 0 ? (cursor % S) : -1);
+		cursor++;
+	}
+	function fire_timers(clock_ns) {
+		/* connection-fsm.js:626-642: S.timeout(ch_claimTimeout, onTimeout) in state 'waiting' */
+		for (var t = first_live; t < handles.length; t++) {
+			var h = handles[t];
+			if (h.state !== 'waiting') {
+				if (t === first_live) first_live++;
+				continue;
+			}
+			if (clock_ns >= h.deadline_ns) {
+				h.state = 'failed';
+				counters['claim-timeout']++;		/* connection-fsm.js:629-630 */
+				res.push(h.ticket, 3, -1);
+			}
+		}
+	}
+	var n = job.ev_type.length, e;
+	for (e = 0; e < n; e++) {
+		var ty = job.ev_type[e], a = job.ev_a[e], b = job.ev_b[e];
+		if (ty === 0) {
+			fire_timers(a);
+			__set_clock_ns(a);
+			var timeout = cd.getMaxIdle();			/* pool.js:880 */
+			counters['claim']++;				/* pool.js:887 */
+			var h = { ticket: handles.length, ch_started: utils.currentMillis(),	/* connection-fsm.js:523 */
+			    state: 'waiting', deadline_ns: a + timeout * 1000000 };
+			handles.push(h);
+			timeouts.push(timeout);
+			if (idle > 0) {					/* pool.js:934-951 */
+				idle--;
+				admit(h);
+			} else {
+				waiters.push(h);			/* pool.js:960 */
+				if (waiters.length > counters['max-claim-queue'])	/* pool.js:962 */
+					counters['max-claim-queue'] = waiters.length;
+				counters['queued-claim']++;		/* pool.js:963 */
+			}
+		} else if (ty === 1) {
+			fire_timers(a);
+			__set_clock_ns(a);
+			for (var s = 0; s < b; s++) {			/* one handler run per slot */
+				var handed = false;
+				while (waiters.length > 0) {		/* pool.js:733 */
+					var hdl = waiters.shift();
+					var drop = cd.overloaded(hdl.ch_started);	/* pool.js:735-736 */
+					if (hdl.state !== 'waiting') {		/* pool.js:738-740 */
+						res.push(hdl.ticket, 2, -1);
+						continue;
+					}
+					if (drop) {				/* pool.js:742-745 */
+						hdl.state = 'failed';
+						counters['claim-timeout']++;	/* connection-fsm.js:633-638 */
+						res.push(hdl.ticket, 1, -1);
+						continue;
+					}
+					admit(hdl);				/* pool.js:747-748 */
+					handed = true;
+					break;
+				}
+				if (!handed) {
+					cd.empty();				/* pool.js:751-753 */
+					idle++;					/* pool.js:756 */
+				}
+			}
+		} else {
+			var hc = handles[a];
+			if (hc && hc.state === 'waiting') hc.state = 'cancelled';	/* connection-fsm.js:580-587 */
+		}
+	}
+	return { res: res, timeouts: timeouts, state: cb_state(cd), counters: counters,
+	    idle: idle, cursor: cursor, queued: waiters.length };
 }

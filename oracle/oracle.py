@@ -76,8 +76,20 @@ def lib():
         L.cbo_build_slots.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cbo_pref_reshuffle.argtypes = [C.c_void_p, C.c_int32, C.c_double]
         L.cbo_shuffle.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.cbo_pool_sim.argtypes = [C.POINTER(Codel), C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(PoolResult)]
         _lib = L
     return _lib
+
+
+class PoolResult(C.Structure):
+    _fields_ = [("n_res", C.c_uint64), ("idle", C.c_uint64), ("cursor", C.c_uint64), ("queued", C.c_uint64),
+                ("claim", C.c_uint64), ("queued_claim", C.c_uint64), ("max_claim_queue", C.c_uint64),
+                ("claim_timeout", C.c_uint64)]
+
+    def counters(self):
+        return {"claim": self.claim, "queued-claim": self.queued_claim, "max-claim-queue": self.max_claim_queue,
+                "claim-timeout": self.claim_timeout}
 
 
 def _p(a):
@@ -157,3 +169,20 @@ def shuffle(arr, draws):
     draws = np.ascontiguousarray(draws, dtype=np.float64)
     lib().cbo_shuffle(_p(arr), arr.shape[0], _p(draws))
     return arr
+
+
+def pool_sim(cd, nslots, ev_type, ev_a, ev_b, idle0=0, cursor=0):
+    """The event-driven pool model (claim / slots idle / cancel); returns (res[k,3] int64 rows of
+    (ticket, code, slot), timeouts_ms per claim, PoolResult).  cd is advanced in place."""
+    ev_type = np.ascontiguousarray(ev_type, dtype=np.uint8)
+    ev_a = np.ascontiguousarray(ev_a, dtype=np.int64)
+    ev_b = np.ascontiguousarray(ev_b, dtype=np.int64)
+    nclaims = int((ev_type == 0).sum())
+    res = np.zeros(6 * max(nclaims, 1), np.int64)
+    tmo = np.zeros(max(nclaims, 1), np.float64)
+    out = PoolResult()
+    rc = lib().cbo_pool_sim(C.byref(cd), int(nslots), int(idle0), int(cursor), _p(ev_type), _p(ev_a), _p(ev_b),
+                            ev_type.shape[0], _p(res), _p(tmo), C.byref(out))
+    if rc != 0:
+        raise RuntimeError("oracle pool_sim failed")
+    return res[:3 * out.n_res].reshape(-1, 3).copy(), tmo[:nclaims].copy(), out

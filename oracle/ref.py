@@ -106,3 +106,14 @@ def gen_trace(seed, n, params):
 
 def bench(seed, n, params, target, nslots, timeout=3600):
     return call("cb_bench(%d,%d,%s,%s,%d)" % (seed, n, _lit(params), _lit(target), nslots), timeout=timeout)
+
+
+def pool_sim(target, nslots, ev_type, ev_a, ev_b, state=None, idle0=0, cursor=0, timeout=3600):
+    """The event-driven pool model (cb_pool_sim in driver.js) on the reference's own
+    ControlledDelay / Queue."""
+    if len(ev_a) and max(int(x) for x in ev_a) >= 2**53:
+        raise ValueError("JS harness carries total ns in a double: keep clocks below 2^53 ns")
+    job = {"target": target, "nslots": nslots, "state": state, "idle0": idle0, "cursor": cursor}
+    expr = ("(function(){var job=%s; job.ev_type=__read_array(); job.ev_a=__read_array(); "
+            "job.ev_b=__read_array(); return cb_pool_sim(job);})()" % _lit(job))
+    return call(expr, timeout=timeout, arrays=[ev_type, ev_a, ev_b])

@@ -117,3 +117,49 @@ def assert_state_equal(got, want, ctx=""):
     for k in ("count", "drop_next", "first_above_time", "last_empty"):
         assert same_bits(got[k], want[k]), "%s state.%s: got %r want %r" % (ctx, k, got[k], want[k])
     assert bool(got["dropping"]) == bool(want["dropping"]), "%s state.dropping" % ctx
+
+
+def gen_pool_events(seed, n_ev, tgt, backlog_mult, jitter):
+    """A pool event script (ev_type, ev_a, ev_b as lists; see cbo_pool_sim): an initial burst that
+    puts `backlog_mult x target` of sojourn on the queue, then arrivals and slot-idle events at about
+    the same rate, so that the sojourn stays between target and the hard timeout long enough for
+    CoDel to act; occasional cancels, multi-slot idle events, arrival pauses (queue drains, empty())
+    and service stalls."""
+    rng = np.random.RandomState(seed)
+    ms = 1_000_000
+    t = 10 ** 9
+    ty, a, b = [], [], []
+    nclaims = 0
+    svc = float(rng.choice([0.25, 0.5, 1.0]))
+    burst = int(backlog_mult * tgt / svc)
+    for i in range(burst):
+        ty.append(0)
+        a.append(t + i * 1000)
+        b.append(0)
+        nclaims += 1
+    tc = t + burst * 1000
+    ti = t + int(svc * ms)
+    while len(ty) < n_ev:
+        if tc <= ti:
+            ty.append(0)
+            a.append(tc)
+            b.append(0)
+            nclaims += 1
+            tc += max(1, int((svc + rng.uniform(-jitter, jitter) * svc) * ms))
+            if rng.rand() < 0.02:
+                ty.append(2)
+                a.append(int(rng.randint(max(0, nclaims - 40), nclaims)))
+                b.append(0)
+        else:
+            k = 1
+            if rng.rand() < 0.05:
+                k = int(rng.choice([2, 3]))
+            ty.append(1)
+            a.append(ti)
+            b.append(k)
+            ti += max(1, int((svc + rng.uniform(-jitter, jitter) * svc) * ms)) * k
+        if rng.rand() < 0.001:
+            tc += int(rng.uniform(150, 500)) * ms
+        if rng.rand() < 0.001:
+            ti += int(rng.uniform(5, 60)) * ms
+    return ty, a, b
