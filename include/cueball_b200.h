@@ -230,6 +230,45 @@ int cb_allreduce_counts(cb_ctx *ctx); /* async on the context's stream */
 int cb_ring_mailbox(cb_ctx *ctx, void *ipc_handle_out, size_t *len, void **local_ptr_out);
 int cb_ring_connect(cb_ctx *ctx, int nranks, int rank, const void *next_ipc_handle, void *next_local_ptr);
 
+/* ------------------------------------------------- pending-claim queue in HBM */
+
+/* The enqueue side and the event form of the drain loop.  STATUS: compiled,
+ * specified (tools/proto_queue.py) and checked on CPU against the pinned model of the reference (tests/test_proto_queue.py), NOT yet
+ * validated on hardware.
+ *
+ * cb_queue_push    n x ConnectionPool#claim (lib/pool.js:874-966): claimTimeout = getMaxIdle()
+ *                  (lib/codel.js:109-118) per claim, idle slots first, the rest appended to the device
+ *                  queue; tickets are first_ticket, first_ticket+1, ...  Enqueue clocks (start_ns) must
+ *                  be non-decreasing across pushes.  Timers due at start_ns[0] fire first.
+ * cb_queue_cancel  handle.cancel() of waiting handles (lib/connection-fsm.js:580-587).
+ * cb_queue_expire  hard timeouts due at now_ns (lib/connection-fsm.js:626-642) -> ClaimTimeoutError.
+ * cb_queue_idle    k slots turn idle at clock now_ns: the handler lib/pool.js:733-757 once per slot with
+ *                  every clock read returning now_ns.  One kernel: the claims at or above the target
+ *                  delay are a prefix of the FIFO (bisection), ControlledDelay#overloaded has a closed
+ *                  form along it, and the number of handles the k slots consume is a prefix-sum
+ *                  selection over the waiting bits.  Expires due timers first; calls codel.empty() when
+ *                  the queue runs dry with slots left, which then sit on the idle queue.
+ * cb_queue_results resolution records since the last call, in the order the reference would resolve
+ *                  the handles: (ticket, code, slot) with code 0 admitted (hdl.try), 1 dropped by CoDel
+ *                  (hdl.timeout()), 2 skipped (no longer waiting when dequeued), 3 hard timeout.
+ * All calls are synchronous.  The ControlledDelay state, admit cursor and counters are the context's
+ * (cb_codel_get_state, cb_batch_stats_get) and are shared with the batch entry points. */
+typedef struct cb_queue_info {
+	uint64_t head, tail;   /* absolute FIFO positions; tail - head handles are queued */
+	uint64_t next_ticket;
+	uint64_t idle;         /* slots on the idle queue (p_idleq.length) */
+	uint64_t claim, queued_claim, max_claim_queue, claim_timeout; /* lib/pool.js:269-283 counters */
+	uint64_t n_results;    /* records waiting for cb_queue_results */
+	uint32_t error, reserved;
+} cb_queue_info;
+int cb_queue_create(cb_ctx *ctx, size_t capacity, size_t result_capacity, uint64_t idle_slots);
+int cb_queue_push(cb_ctx *ctx, const int64_t *start_ns, size_t n, int64_t *first_ticket, double *timeouts_ms);
+int cb_queue_cancel(cb_ctx *ctx, const int64_t *tickets, size_t n);
+int cb_queue_expire(cb_ctx *ctx, int64_t now_ns);
+int cb_queue_idle(cb_ctx *ctx, int64_t now_ns, uint64_t k_slots);
+int cb_queue_results(cb_ctx *ctx, int64_t *triples, size_t cap_records, size_t *n_records);
+int cb_queue_info_get(cb_ctx *ctx, cb_queue_info *out);
+
 /* ------------------------------------------------------------- measurement */
 
 /* Per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg).

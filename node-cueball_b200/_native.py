@@ -26,6 +26,8 @@ SYMBOLS = [
     "cb_comm_unique_id", "cb_comm_init", "cb_allreduce_counts", "cb_profile_enable", "cb_profile_get",
     "cb_launch_count", "cb_debug_timestamps", "cb_debug_lane_timestamps",
     "cb_ring_mailbox", "cb_ring_connect",
+    "cb_queue_create", "cb_queue_push", "cb_queue_cancel", "cb_queue_expire", "cb_queue_idle", "cb_queue_results",
+    "cb_queue_info_get",
 ]
 
 
@@ -46,6 +48,18 @@ class BatchStats(C.Structure):
                 ("global_drops", C.c_uint64), ("global_admits", C.c_uint64), ("global_n", C.c_uint64),
                 ("state", CodelState), ("path", C.c_int32), ("n_events", C.c_uint32),
                 ("n_intervals", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class QueueInfo(C.Structure):
+    _fields_ = [("head", C.c_uint64), ("tail", C.c_uint64), ("next_ticket", C.c_uint64), ("idle", C.c_uint64),
+                ("claim", C.c_uint64), ("queued_claim", C.c_uint64), ("max_claim_queue", C.c_uint64),
+                ("claim_timeout", C.c_uint64), ("n_results", C.c_uint64), ("error", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+    def counters(self):
+        """The reference's counter names (lib/pool.js:269-283)."""
+        return {"claim": self.claim, "queued-claim": self.queued_claim, "max-claim-queue": self.max_claim_queue,
+                "claim-timeout": self.claim_timeout}
 
 
 class Backend(C.Structure):
@@ -114,6 +128,13 @@ def lib():
     L.cb_debug_lane_timestamps.argtypes = [vp, C.c_int, C.POINTER(u64)]
     L.cb_ring_mailbox.argtypes = [vp, vp, C.POINTER(sz), C.POINTER(vp)]
     L.cb_ring_connect.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cb_queue_create.argtypes = [vp, sz, sz, u64]
+    L.cb_queue_push.argtypes = [vp, vp, sz, C.POINTER(i64), vp]
+    L.cb_queue_cancel.argtypes = [vp, vp, sz]
+    L.cb_queue_expire.argtypes = [vp, i64]
+    L.cb_queue_idle.argtypes = [vp, i64, u64]
+    L.cb_queue_results.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.cb_queue_info_get.argtypes = [vp, C.POINTER(QueueInfo)]
     _lib = L
     return L
 

@@ -220,6 +220,41 @@ class Context(object):
         self._ck(self._L.cb_debug_timestamps(self._h, out))
         return list(out)
 
+    # ------------------------------------------------ pending-claim queue in HBM
+    def queue_create(self, capacity, result_capacity=None, idle_slots=0):
+        self._ck(self._L.cb_queue_create(self._h, int(capacity), int(result_capacity or 2 * capacity), int(idle_slots)))
+
+    def queue_push(self, start_ns, want_timeouts=False):
+        """n x claim(): returns (first_ticket, timeouts_ms or None)."""
+        start = np.ascontiguousarray(start_ns, dtype=np.int64)
+        first = C.c_int64()
+        tmo = np.empty(start.shape[0], np.float64) if want_timeouts else None
+        self._ck(self._L.cb_queue_push(self._h, _np_ptr(start), start.shape[0], C.byref(first), _np_ptr(tmo)))
+        return first.value, tmo
+
+    def queue_cancel(self, tickets):
+        t = np.ascontiguousarray(tickets, dtype=np.int64)
+        self._ck(self._L.cb_queue_cancel(self._h, _np_ptr(t), t.shape[0]))
+
+    def queue_expire(self, now_ns):
+        self._ck(self._L.cb_queue_expire(self._h, int(now_ns)))
+
+    def queue_idle(self, now_ns, k_slots):
+        self._ck(self._L.cb_queue_idle(self._h, int(now_ns), int(k_slots)))
+
+    def queue_results(self):
+        """Resolution records since the last call: int64 array of (ticket, code, slot) rows."""
+        info = self.queue_info()
+        buf = np.empty((max(int(info.n_results), 1), 3), np.int64)
+        n = C.c_size_t()
+        self._ck(self._L.cb_queue_results(self._h, _np_ptr(buf), buf.shape[0], C.byref(n)))
+        return buf[:n.value].copy()
+
+    def queue_info(self):
+        out = N.QueueInfo()
+        self._ck(self._L.cb_queue_info_get(self._h, C.byref(out)))
+        return out
+
     # ------------------------------------------------ one queue over several GPUs
     def ring_mailbox(self):
         """(ipc_handle: bytes, local_ptr: int) of this context's mailbox."""

@@ -17,6 +17,7 @@
 
 #include "cb_device.cuh"
 #include "cb_emit.cuh"
+#include "cb_queue.cuh"
 #include "cb_resolve.cuh"
 #include "cb_scan.cuh"
 #include "cb_topology.cuh"
@@ -112,6 +113,12 @@ struct cb_ctx {
 	// totals as of the last cb_batch_stats_get-style read, valid while no batch has been enqueued since
 	bool tot_valid = false;
 	unsigned long long tot_seq = 0, tot_drops_h = 0, tot_admits_h = 0, tot_epoch = 0, epoch = 0;
+	// the pending-claim queue resident in HBM (cb_queue_*)
+	QueueDev *d_q = nullptr;
+	long long *q_start = nullptr, *q_deadline = nullptr, *q_ticket = nullptr, *q_res = nullptr, *q_stage = nullptr;
+	unsigned char *q_waiting = nullptr;
+	double *q_tmo = nullptr;
+	size_t q_cap = 0, q_res_cap = 0, q_stage_cap = 0;
 	int prio_least = 0, prio_greatest = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
@@ -797,6 +804,10 @@ extern "C" void cb_destroy(cb_ctx *c) {
 				cudaEventDestroy(e);
 	}
 	ring_close(c);
+	void *qfrees[] = {c->d_q, c->q_start, c->q_deadline, c->q_ticket, c->q_res, c->q_stage, c->q_waiting, c->q_tmo};
+	for (void *p : qfrees)
+		if (p)
+			cudaFree(p);
 	void *frees[] = {c->g, c->d_chain, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight, c->d_ints,
 	    c->d_dbl};
 	for (void *p : frees)
@@ -1328,6 +1339,183 @@ extern "C" int cb_allreduce_counts(cb_ctx *c) {
 		CU(c, cudaEventRecord(L.coll_done, s));
 		L.coll_pending = true;
 	}
+	return CB_OK;
+}
+
+// =========================================================================== pending-claim queue
+// (kernels in cb_queue.cuh; synchronous calls: one small kernel each)
+static QueueParams queue_params(cb_ctx *c) {
+	QueueParams p;
+	p.q = c->d_q;
+	p.g = c->g;
+	p.start_ns = c->q_start;
+	p.deadline_ns = c->q_deadline;
+	p.ticket = c->q_ticket;
+	p.waiting = c->q_waiting;
+	p.mask = c->q_cap - 1;
+	p.res = c->q_res;
+	p.res_cap = c->q_res_cap;
+	p.nslots = c->nslots;
+	return p;
+}
+static int queue_ready(cb_ctx *c) {
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	if (!c->d_q)
+		return fail(c, CB_ESTATE, "cb_queue_create has not been called");
+	c->tot_valid = false;
+	return drain(c);
+}
+static int queue_check(cb_ctx *c) {
+	CU(c, cudaGetLastError());
+	QueueDev h;
+	CU(c, cudaMemcpyAsync(&h, c->d_q, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	if (h.err) { // report once: clear the device flag
+		const unsigned int zero = 0;
+		CU(c, cudaMemcpy((char *)c->d_q + offsetof(QueueDev, err), &zero, sizeof(zero), cudaMemcpyHostToDevice));
+	}
+	if (h.err & Q_ERR_FULL)
+		return fail(c, CB_ENOMEM, "pending-claim queue is full (%llu handles queued)", h.tail - h.head);
+	if (h.err & Q_ERR_RESULTS)
+		return fail(c, CB_ENOMEM, "result buffer overflow: call cb_queue_results more often");
+	if (h.err & Q_ERR_NONMONO)
+		return fail(c, CB_EINVAL, "enqueue clocks must be non-decreasing");
+	return CB_OK;
+}
+
+extern "C" int cb_queue_create(cb_ctx *c, size_t capacity, size_t result_capacity, uint64_t idle_slots) {
+	if (!c || capacity == 0 || result_capacity == 0)
+		return c ? fail(c, CB_EINVAL, "queue and result capacities must be positive") : CB_EINVAL;
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	size_t cap = 1024;
+	while (cap < capacity)
+		cap <<= 1;
+	void *old[] = {c->d_q, c->q_start, c->q_deadline, c->q_ticket, c->q_res, c->q_waiting};
+	for (void *p : old)
+		if (p)
+			cudaFree(p);
+	c->d_q = nullptr;
+	c->q_start = c->q_deadline = c->q_ticket = c->q_res = nullptr;
+	c->q_waiting = nullptr;
+	if ((rc = dev_alloc(c, &c->d_q, 1)) || (rc = dev_alloc(c, &c->q_start, cap)) ||
+	    (rc = dev_alloc(c, &c->q_deadline, cap)) || (rc = dev_alloc(c, &c->q_ticket, cap)) ||
+	    (rc = dev_alloc(c, &c->q_waiting, cap)) || (rc = dev_alloc(c, &c->q_res, result_capacity * 3)))
+		return rc;
+	QueueDev h;
+	memset(&h, 0, sizeof(h));
+	h.idle = idle_slots;
+	CU(c, cudaMemcpy(c->d_q, &h, sizeof(h), cudaMemcpyHostToDevice));
+	c->q_cap = cap;
+	c->q_res_cap = result_capacity;
+	return CB_OK;
+}
+
+static int queue_stage(cb_ctx *c, const int64_t *host, size_t n) {
+	if (n > c->q_stage_cap) {
+		if (c->q_stage)
+			cudaFree(c->q_stage);
+		if (c->q_tmo)
+			cudaFree(c->q_tmo);
+		c->q_stage = nullptr;
+		c->q_tmo = nullptr;
+		c->q_stage_cap = 0;
+		int rc;
+		if ((rc = dev_alloc(c, &c->q_stage, n + n / 2 + 64)) || (rc = dev_alloc(c, &c->q_tmo, n + n / 2 + 64)))
+			return rc;
+		c->q_stage_cap = n + n / 2 + 64;
+	}
+	CU(c, cudaMemcpyAsync(c->q_stage, host, n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+	return CB_OK;
+}
+
+extern "C" int cb_queue_push(cb_ctx *c, const int64_t *start_ns, size_t n, int64_t *first_ticket, double *timeouts_ms) {
+	if (!c || (n && !start_ns))
+		return c ? fail(c, CB_EINVAL, "start_ns must not be NULL") : CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc)
+		return rc;
+	QueueDev h;
+	CU(c, cudaMemcpy(&h, c->d_q, sizeof(h), cudaMemcpyDeviceToHost));
+	if (first_ticket)
+		*first_ticket = (int64_t)h.next_ticket;
+	if (n == 0)
+		return CB_OK;
+	if ((rc = queue_stage(c, start_ns, n)))
+		return rc;
+	queue_push_kernel<<<1, QTPB, 0, c->stream>>>(queue_params(c), c->q_stage, n, c->q_tmo);
+	c->launches += 1;
+	if (timeouts_ms)
+		CU(c, cudaMemcpyAsync(timeouts_ms, c->q_tmo, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	return queue_check(c);
+}
+
+extern "C" int cb_queue_cancel(cb_ctx *c, const int64_t *tickets, size_t n) {
+	if (!c || (n && !tickets))
+		return c ? fail(c, CB_EINVAL, "tickets must not be NULL") : CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc || n == 0)
+		return rc;
+	if ((rc = queue_stage(c, tickets, n)))
+		return rc;
+	queue_cancel_kernel<<<1, QTPB, 0, c->stream>>>(queue_params(c), c->q_stage, n);
+	c->launches += 1;
+	return queue_check(c);
+}
+
+extern "C" int cb_queue_expire(cb_ctx *c, int64_t now_ns) {
+	if (!c)
+		return CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc)
+		return rc;
+	queue_expire_kernel<<<1, QTPB, 0, c->stream>>>(queue_params(c), now_ns);
+	c->launches += 1;
+	return queue_check(c);
+}
+
+extern "C" int cb_queue_idle(cb_ctx *c, int64_t now_ns, uint64_t k_slots) {
+	if (!c)
+		return CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc)
+		return rc;
+	queue_idle_kernel<<<1, QTPB, 0, c->stream>>>(queue_params(c), now_ns, k_slots);
+	c->launches += 1;
+	return queue_check(c);
+}
+
+extern "C" int cb_queue_results(cb_ctx *c, int64_t *triples, size_t cap_records, size_t *n_records) {
+	if (!c || !n_records)
+		return CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc)
+		return rc;
+	QueueDev h;
+	CU(c, cudaMemcpy(&h, c->d_q, sizeof(h), cudaMemcpyDeviceToHost));
+	size_t n = (size_t)h.n_res;
+	if (n > c->q_res_cap)
+		n = c->q_res_cap;
+	if (n > cap_records)
+		return fail(c, CB_EINVAL, "%zu records are waiting, room for %zu", n, cap_records);
+	if (n && triples)
+		CU(c, cudaMemcpy(triples, c->q_res, n * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+	*n_records = n;
+	const unsigned long long zero = 0;
+	CU(c, cudaMemcpy((char *)c->d_q + offsetof(QueueDev, n_res), &zero, sizeof(zero), cudaMemcpyHostToDevice));
+	return CB_OK;
+}
+
+extern "C" int cb_queue_info_get(cb_ctx *c, cb_queue_info *out) {
+	if (!c || !out)
+		return CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc)
+		return rc;
+	static_assert(sizeof(cb_queue_info) == sizeof(QueueDev), "cb_queue_info mirrors QueueDev");
+	CU(c, cudaMemcpy(out, c->d_q, sizeof(*out), cudaMemcpyDeviceToHost));
 	return CB_OK;
 }
 
