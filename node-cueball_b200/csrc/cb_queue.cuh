@@ -22,7 +22,11 @@
 
 namespace cb {
 
+#ifdef CB_QTPB // the host emulation of tests/emu runs the same code with a narrower CTA
+constexpr int QTPB = CB_QTPB;
+#else
 constexpr int QTPB = 1024;
+#endif
 constexpr long long Q_ADMIT = 0, Q_DROP = 1, Q_SKIPPED = 2, Q_EXPIRED = 3;
 constexpr unsigned Q_ERR_NONMONO = 1u, Q_ERR_FULL = 2u, Q_ERR_RESULTS = 4u;
 
