@@ -412,8 +412,8 @@ def run_cuda(args, wl, extra=True):
                    "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
                          % (nb, 16.0 * n * nb / 1e6),
                    "state": "ControlledDelay state chained on device across steps",
-                   "pipeline": "up to 5 batches in flight (one lane each: scan on a low-priority stream, prepare/commit/emit on "
-                               "a high-priority one); commits ordered by a device-side chain word",
+                   "pipeline": "up to 5 batches in flight, one lane (stream) each; the scan is launched at low priority, "
+                               "prepare/commit/emit at high; commits ordered by a device-side chain word",
                    "admit_fraction": st.total_admits / max(st.total_admits + st.total_drops, 1)},
         "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "host_enqueue_ms_per_step": host_ms,

@@ -21,8 +21,8 @@ constexpr unsigned F_WAITING = 1u, F_EMPTY_AFTER = 2u;
 // Device-resident state.  DevState is the pool's persistent state (one per context): the
 // ControlledDelay fields and the admit cursor; consecutive batches chain through it without a
 // host round trip.  BatchCtl is the per-batch control block: up to CB_LANES batches are in
-// flight at once (scan of batch k+1 overlaps resolve of batch k and emit of batch k-1), each on
-// its own lane with its own BatchCtl and scratch.
+// flight at once (scans, prepares and emits of different batches overlap; only the commits are
+// ordered), each on its own lane with its own BatchCtl and scratch.
 struct DevState {
 	// ControlledDelay, lib/codel.js:24-32 (+ cd_last_empty :92)
 	double target;            // cd_targdelay

@@ -1,4 +1,4 @@
-// cb_scan.cuh -- pass 1 of the admission path: the streaming scan kernel (v3).
+// cb_scan.cuh -- pass 1 of the admission path: the streaming scan kernel.
 //
 // Reads every claim's (start, now[, flags]) exactly once from HBM (16 B/claim, 17 with
 // flags), evaluates ControlledDelay#canDrop (lib/codel.js:34-46) for ALL claims in parallel
@@ -11,7 +11,7 @@
 //       above                : F' = F ? F : now+100        PASS(now+100)
 // which compose associatively ("last CONST wins, then the first PASS fills a zero").  Every
 // non-zero F is `now[a] + 100` for some claim index a, so compositions are carried as
-// INDICES (integer-only, one 64-bit look-back descriptor per tile) and turned into doubles
+// INDICES (integer-only, one 64-bit code per warp chunk and per tile) and turned into doubles
 // only where a claim's class needs the value.
 //
 // Layout: a CTA owns a tile of 2048 consecutive claims, a warp a chunk of 256 = 4 rows of 64;

@@ -1,8 +1,9 @@
 // cueball_b200.cu -- the C ABI (include/cueball_b200.h) over the sm_100a kernels.
-// Host-side plumbing only: buffers, streams, launches, the batch pipeline (scan of batch k+1
-// overlaps resolve of batch k and emit of batch k-1 on three streams), the chunked
-// H2D/compute/D2H pipeline of the host-buffer entry points, and a dlopen()ed NCCL for the one
-// collective.
+// Host-side plumbing only: buffers, streams, launches, the batch pipeline (up to 8 lanes, one
+// stream each: a batch's scan -> prepare -> commit -> emit are stream-ordered, the commits of
+// consecutive batches are ordered on the device by the chain word / ring mailbox), the chunked
+// H2D/compute/D2H pipeline of the host-buffer entry points, the pending-claim queue entry points
+// and a dlopen()ed NCCL for the one collective.
 #include "../../include/cueball_b200.h"
 
 #include <cuda_runtime.h>
@@ -64,7 +65,7 @@ constexpr int CB_DEFAULT_DEPTH = 5;           // lanes used unless CB_PIPELINE_D
 constexpr int NBUF = 3;                       // staging buffers of the host-buffer pipeline
 constexpr size_t DEFAULT_CHUNK = 4u << 20;    // claims per pipeline chunk
 
-// per-batch scratch: everything one batch's three kernels hand to each other
+// per-batch scratch: everything one batch's four kernels hand to each other
 struct Lane {
 	size_t cap_tiles = 0;
 	BatchCtl *ctl = nullptr;
