@@ -66,3 +66,72 @@ def test_two_rank_segment_sharding_and_count_allreduce():
     assert not np.array_equal(segs[0][1], segs[1][1])
     again = bench.make_trace("c4", n * steps, 1)
     assert np.array_equal(again[1], segs[1][1])
+
+
+def _ring_worker(rank, world, port, m, steps, out):
+    """One logical queue over `world` ranks (cb_ring_connect): segment (k, r) follows
+    (k, r-1); the ControlledDelay state and the admit cursor are handed from rank to rank.  On the
+    GPUs the hand-over is a peer-memory mailbox written by the commit kernel; here it is a gloo
+    send/recv and the per-segment admission is stood in by the oracle."""
+    sys.path.insert(0, ROOT)
+    from cueball_b200 import tracegen
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = m * world * steps
+    start, now = tracegen.gen_trace(n, seed=99, t0=10 ** 12, de=1 << 9, target_ns=5_000_000, unit=1 << 13)
+    cd = O.new_codel(5)
+    box = torch.zeros(8, dtype=torch.float64)  # count, drop_next, first_above, dropping, hasE, E, cursor, seq
+    dec_all, slot_all = [], []
+    for k in range(steps):
+        seq = k * world + rank
+        if seq > 0:
+            dist.recv(box, src=(rank - 1) % world)
+            assert int(box[7].item()) == seq  # the mailbox sequence number the commit kernel waits for
+            cd.load({"count": box[0].item(), "drop_next": box[1].item(), "first_above_time": box[2].item(),
+                     "dropping": bool(box[3].item()), "last_empty": box[5].item() if box[4].item() else None})
+        cursor = int(box[6].item())
+        lo = seq * m
+        d, s, st = O.drain(cd, start[lo:lo + m], now[lo:lo + m], nslots=97, cursor=cursor)
+        dec_all.append(d)
+        slot_all.append(s)
+        stt = cd.as_dict()
+        le = stt["last_empty"]
+        box = torch.tensor([stt["count"], stt["drop_next"], stt["first_above_time"], float(stt["dropping"]),
+                            0.0 if le is None else 1.0, 0.0 if le is None else le, float(st.cursor), float(seq + 1)],
+                           dtype=torch.float64)
+        if not (k == steps - 1 and rank == world - 1):
+            dist.send(box, dst=(rank + 1) % world)
+    out.put((rank, np.concatenate(dec_all).tobytes(), np.concatenate(slot_all).tobytes(), cd.as_dict()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_one_logical_queue_protocol():
+    sys.path.insert(0, ROOT)
+    from cueball_b200 import tracegen
+    from oracle import oracle as O
+    world, m, steps = 2, 30_000, 4
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, m, steps, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(world):
+        r, d, s, st = out.get(timeout=120)
+        got[r] = (np.frombuffer(d, np.uint8), np.frombuffer(s, np.int32), st)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = m * world * steps
+    start, now = tracegen.gen_trace(n, seed=99, t0=10 ** 12, de=1 << 9, target_ns=5_000_000, unit=1 << 13)
+    cd = O.new_codel(5)
+    od, os_, ost = O.drain(cd, start, now, nslots=97)  # ONE sequential drain of the whole queue
+    for r in range(world):
+        idx = np.concatenate([np.arange((k * world + r) * m, (k * world + r + 1) * m) for k in range(steps)])
+        assert np.array_equal(got[r][0], od[idx]) and np.array_equal(got[r][1], os_[idx])
+    assert got[world - 1][2] == cd.as_dict()  # the last rank's state is the queue's
+    assert od.max() >= 1  # the trace does exercise drops
