@@ -89,6 +89,12 @@ struct ChainLink {
 	DevState *post_state;
 };
 
+// dynamic shared memory of a kernel (the host emulation of tests/emu substitutes a plain buffer)
+#ifndef CB_DYN_SHARED
+#define CB_DYN_SHARED(T, name) extern __shared__ __align__(16) T name[]
+#endif
+
+#ifndef CB_EMU // tests/emu/cuda_emu.h supplies host versions of the PTX helpers below
 __device__ __forceinline__ unsigned long long gtimer() {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -120,6 +126,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
 }
+#endif // CB_EMU
 
 __device__ __forceinline__ void chain_copy_state(DevState *dst, const DevState *src) {
 	dst->F = src->F;

@@ -49,9 +49,11 @@ struct EmitParams {
 	int vec_ok;                    // outputs suitably aligned for vector stores
 };
 
+#ifndef CB_EMU
 __device__ __forceinline__ unsigned int smem_u32(const void *p) {
 	return (unsigned int)__cvta_generic_to_shared(p);
 }
+#endif
 // x mod S without a 64-bit division: q = mulhi(x, floor((2^64-1)/S)) is floor(x/S) or one less
 __device__ __forceinline__ unsigned int fastmod(unsigned long long x, unsigned int S, unsigned long long magic) {
 	const unsigned long long q = __umul64hi(x, magic);
@@ -60,6 +62,7 @@ __device__ __forceinline__ unsigned int fastmod(unsigned long long x, unsigned i
 		r -= S;
 	return (unsigned int)r;
 }
+#ifndef CB_EMU
 __device__ __forceinline__ void wait_table(unsigned long long *mbar) {
 	unsigned int done = 0;
 	while (!done) {
@@ -71,6 +74,18 @@ __device__ __forceinline__ void wait_table(unsigned long long *mbar) {
 		             : "memory");
 	}
 }
+// one thread: start the TMA bulk copy of the slot->backend table into shared memory
+__device__ __forceinline__ void stage_table_async(unsigned char *dst, const void *src, unsigned int bytes,
+    unsigned long long *mbar) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	                 smem_u32(dst)),
+	    "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+	    : "memory");
+}
+#endif
 
 // drop bits of the 4 claims [i0, i0+4) and the number of (CoDel-level) drops before i0
 __device__ __forceinline__ unsigned int drops_general(const unsigned long long *iv_lo, const unsigned long long *iv_hi,
@@ -104,7 +119,7 @@ __device__ __forceinline__ unsigned int drops_general(const unsigned long long *
 
 template <bool FLAGS>
 __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
-	extern __shared__ __align__(16) unsigned char s_dyn[]; // backend table stage
+	CB_DYN_SHARED(unsigned char, s_dyn); // backend table stage
 	__shared__ __align__(8) unsigned long long s_mbar;
 	__shared__ unsigned int s_wsum[EG][EWARPS];
 	__shared__ unsigned long long s_tile_excl;
@@ -125,17 +140,8 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	const unsigned int S = (unsigned int)p.nslots;
 
 	// ---- per-CTA set-up --------------------------------------------------------------------
-	if (stage_table && tid == 0) { // TMA bulk copy of the slot->backend table
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar)));
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_mbar)),
-		    "r"((unsigned int)p.table_smem_bytes)
-		    : "memory");
-		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-		                 smem_u32(s_dyn)),
-		    "l"(p.slot_backend), "r"((unsigned int)p.table_smem_bytes), "r"(smem_u32(&s_mbar))
-		    : "memory");
-	}
+	if (stage_table && tid == 0) // TMA bulk copy of the slot->backend table
+		stage_table_async(s_dyn, p.slot_backend, (unsigned int)p.table_smem_bytes, &s_mbar);
 	const bool iv_smem = m <= IVS_MAX; // short interval lists live in shared memory
 	if (iv_smem) {
 		for (unsigned int k = tid; k < m; k += ETPB) {

@@ -269,7 +269,7 @@ constexpr int CTPB = 128;      // threads of the commit kernel
 
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p) {
-	extern __shared__ __align__(16) double s_idx[]; // clock (ms) at claim k*G, k < nidx
+	CB_DYN_SHARED(double, s_idx); // clock (ms) at claim k*G, k < nidx
 	__shared__ unsigned int s_warp[32];
 	__shared__ int s_wmax[32];
 	__shared__ unsigned int s_base;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p)
 // previous batch.  One small CTA; runs strictly in batch order.
 template <bool NS, bool FLAGS>
 __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) {
-	extern __shared__ __align__(16) double s_cidx[]; // the coarse clock index (prepare wrote it to idx_ms)
+	CB_DYN_SHARED(double, s_cidx); // the coarse clock index (prepare wrote it to idx_ms)
 	__shared__ unsigned long long s_evc[SEV_MAX], s_evq[SEV_MAX], s_evd[SEV_MAX];
 	__shared__ double s_evnow[SEV_MAX];
 	__shared__ unsigned int s_ncar;

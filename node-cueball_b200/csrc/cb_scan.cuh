@@ -48,6 +48,7 @@ constexpr unsigned int FC_NONE = 0xffffffffu; // tile record: no CONST claim in 
 constexpr int EVW = 4;                        // class-change events one warp chunk can hold
 
 // named barriers: arrive without waiting / wait for all TPB threads
+#ifndef CB_EMU
 __device__ __forceinline__ void bar_arrive(int id) {
 	__threadfence_block();
 	asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(TPB) : "memory");
@@ -55,6 +56,7 @@ __device__ __forceinline__ void bar_arrive(int id) {
 __device__ __forceinline__ void bar_sync(int id) {
 	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPB) : "memory");
 }
+#endif
 
 struct IAgg { // composed F-update in index form: F_out = isconst ? code : (F_in ? F_in : code)
 	bool isconst;
@@ -72,6 +74,7 @@ __device__ __forceinline__ unsigned long long iapply(const IAgg &a, unsigned lon
 	return a.isconst ? a.code : (in_code != CODE_ZERO ? in_code : a.code);
 }
 
+#ifndef CB_EMU
 __device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
 	uint4 r;
 	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -79,6 +82,7 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
 	             : "l"(p));
 	return r;
 }
+#endif
 
 struct ScanParams {
 	const void *start;

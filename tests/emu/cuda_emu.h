@@ -59,6 +59,16 @@ extern Barrier block_barrier;
 extern Barrier warp_barrier[64];
 extern unsigned long long warp_slot[64][32];
 
+/* every lane publishes one 64-bit value; returns a pointer to the warp's 32 slots, valid until
+ * the matching warp_release() */
+inline const unsigned long long *warp_publish(unsigned long long raw) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	warp_slot[warp][lane] = raw;
+	warp_barrier[warp].wait();
+	return warp_slot[warp];
+}
+inline void warp_release() { warp_barrier[threadIdx.x >> 5].wait(); }
+
 template <typename T> inline T shfl_from(T v, int src_lane, bool use_own) {
 	static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,11 +94,101 @@ template <typename T> inline T __shfl_up_sync(unsigned, T v, int delta) {
 }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_from(v, src, false); }
 inline unsigned int __ballot_sync(unsigned, bool pred) {
+	const unsigned long long *sl = emu::warp_publish(pred ? 1ull : 0ull);
 	unsigned int m = 0;
 	for (int l = 0; l < 32; l++)
-		m |= (emu::shfl_from<unsigned int>(pred ? 1u : 0u, l, false) & 1u) << l;
+		m |= (unsigned int)(sl[l] & 1ull) << l;
+	emu::warp_release();
 	return m;
 }
+inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
+inline bool __all_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lanemask) {
+	return emu::shfl_from(v, (int)((threadIdx.x & 31) ^ (unsigned)lanemask), false);
+}
+template <typename T> inline T __shfl_down_sync(unsigned, T v, int delta) {
+	const int lane = threadIdx.x & 31;
+	return emu::shfl_from(v, lane + delta, lane + delta > 31);
+}
+inline unsigned int __reduce_add_sync(unsigned, unsigned int v) {
+	const unsigned long long *sl = emu::warp_publish(v);
+	unsigned int s = 0;
+	for (int l = 0; l < 32; l++)
+		s += (unsigned int)sl[l];
+	emu::warp_release();
+	return s;
+}
+inline int __reduce_add_sync(unsigned m, int v) { return (int)__reduce_add_sync(m, (unsigned int)v); }
+inline int __ffs(unsigned int x) { return __builtin_ffs((int)x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __popc(unsigned int x) { return __builtin_popcount(x); }
+inline int __clz(unsigned int x) { return x ? __builtin_clz(x) : 32; }
+inline int __clz(int x) { return __clz((unsigned int)x); }
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+	return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+}
+template <typename T> inline T __ldg(const T *p) { return *p; }
+inline void __threadfence_block() {}
+#define __align__(n) __attribute__((aligned(n)))
+struct alignas(16) uint4 {
+	unsigned int x, y, z, w;
+};
+struct alignas(16) int4 {
+	int x, y, z, w;
+};
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline int atomicMax(int *p, int v) {
+	int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+	while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+	}
+	return old;
+}
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+	unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+	while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+	}
+	return old;
+}
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline unsigned int max(unsigned int a, unsigned int b) { return a > b ? a : b; }
+inline unsigned int min(unsigned int a, unsigned int b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) {
+	return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST);
+}
+
+/* dynamic shared memory: one buffer per (sequentially emulated) block */
+namespace emu {
+extern unsigned char dyn_smem[96 * 1024];
+/* named barriers (bar.arrive / bar.sync id, nthreads): arrivals are counted, a sync also waits */
+void named_arrive(int id);
+void named_sync(int id);
+} // namespace emu
+#define CB_EMU 1
+#define CB_DYN_SHARED(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
+
+/* host versions of the PTX helpers of csrc/cb_device.cuh, cb_scan.cuh, cb_emit.cuh */
+namespace cb {
+inline unsigned long long gtimer() { return 0; }
+inline unsigned long long ld_acquire(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return ld_acquire(p); }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { st_release(p, v); }
+inline double ld_relaxed_f64(const double *p) { return *(const volatile double *)p; }
+inline unsigned long long ld_relaxed_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+inline void bar_arrive(int id) { emu::named_arrive(id); }
+inline void bar_sync(int id) { emu::named_sync(id); }
+inline uint4 ld_stream_v4(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+inline void wait_table(unsigned long long *) {}
+inline void stage_table_async(unsigned char *dst, const void *src, unsigned int bytes, unsigned long long *) {
+	std::memcpy(dst, src, bytes);
+}
+} // namespace cb
 inline void __threadfence() {}
 inline void __threadfence_system() {}
 inline double __dadd_rn(double a, double b) { return a + b; }

@@ -7,28 +7,6 @@
 
 #include <cstdlib>
 
-thread_local emu_dim3 threadIdx, blockIdx;
-emu_dim3 blockDim, gridDim;
-namespace emu {
-Barrier block_barrier;
-Barrier warp_barrier[64];
-unsigned long long warp_slot[64][32];
-void launch(int threads, const std::function<void()> &body) {
-	block_barrier.reset(threads);
-	for (int w = 0; w < threads / 32; w++)
-		warp_barrier[w].reset(32);
-	blockDim.x = threads;
-	std::vector<std::thread> ts;
-	for (int t = 0; t < threads; t++)
-		ts.emplace_back([t, &body] {
-			threadIdx.x = (unsigned)t;
-			body();
-		});
-	for (auto &t : ts)
-		t.join();
-}
-} // namespace emu
-
 using namespace cb;
 
 struct EmuQueue {

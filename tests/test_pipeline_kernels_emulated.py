@@ -1,0 +1,124 @@
+"""The batch pipeline's CUDA kernels (scan -> prepare -> commit -> emit, csrc/cb_scan.cuh,
+cb_resolve.cuh, cb_emit.cuh) compiled for the HOST under the execution-model emulation of tests/emu
+and compared with the oracle: decisions, slots and the carried ControlledDelay state, batch after
+batch.  The same kernels run on the GPU in tests/test_gpu_parity.py; this file keeps their control
+flow and arithmetic under test on machines without one (and lets a kernel change be checked before
+GPU time is spent on it).  Batches without waiting-flags only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from cueball_b200 import tracegen
+from oracle import oracle as O
+
+EMU = os.path.join(util.ROOT, "tests", "emu")
+SO = os.path.join(EMU, "libpipeline_emu.so")
+FULL = os.environ.get("CB_EMU_FULL") == "1"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    csrc = os.path.join(util.ROOT, "node-cueball_b200", "csrc")
+    srcs = [os.path.join(EMU, "pipeline_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h")] + \
+           [os.path.join(csrc, f) for f in ("cb_device.cuh", "cb_scan.cuh", "cb_resolve.cuh", "cb_emit.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
+                               "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
+    L = C.CDLL(SO)
+    L.emu_pipe_create.restype = C.c_void_p
+    L.emu_pipe_create.argtypes = [C.c_double]
+    L.emu_pipe_destroy.argtypes = [C.c_void_p]
+    L.emu_pipe_set_state.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_uint64]
+    L.emu_pipe_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+    L.emu_pipe_admit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def aligned(arr):
+    """a 16-byte aligned copy (the kernels take their vector path only for aligned inputs)"""
+    raw = np.empty(arr.nbytes + 16, np.uint8)
+    off = (-raw.ctypes.data) % 16
+    out = raw[off:off + arr.nbytes].view(arr.dtype)
+    out[:] = arr
+    return out
+
+
+def get_state(L, p):
+    F, D, E = C.c_double(), C.c_double(), C.c_double()
+    Cn, cur, td, ta = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    B, hasE = C.c_int(), C.c_int()
+    L.emu_pipe_get_state(p, C.byref(F), C.byref(D), C.byref(Cn), C.byref(B), C.byref(hasE), C.byref(E), C.byref(cur),
+                         C.byref(td), C.byref(ta))
+    return ({"count": Cn.value, "drop_next": D.value, "first_above_time": F.value, "dropping": bool(B.value),
+             "last_empty": E.value if hasE.value else None}, cur.value, td.value, ta.value)
+
+
+def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False):
+    p = L.emu_pipe_create(float(target))
+    if state:
+        le = state.get("last_empty")
+        L.emu_pipe_set_state(p, state["first_above_time"], state["drop_next"], int(state["count"]),
+                             int(bool(state["dropping"])), 0 if le is None else 1, 0.0 if le is None else le, 0)
+    n = start.shape[0]
+    dec = aligned(np.full(n + 16, 255, np.uint8))
+    slot = aligned(np.full(n + 16, -7, np.int32))
+    paths = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        s = aligned(start[lo:hi]) if not unaligned else start[lo:hi].copy()
+        w = aligned(now[lo:hi]) if not unaligned else now[lo:hi].copy()
+        d = aligned(np.zeros(hi - lo, np.uint8))
+        sl = aligned(np.zeros(hi - lo, np.int32))
+        info = (C.c_uint64 * 4)()
+        L.emu_pipe_admit(p, s.ctypes.data, w.ctypes.data, hi - lo, nslots, d.ctypes.data, sl.ctypes.data, info)
+        dec[lo:hi] = d
+        slot[lo:hi] = sl
+        paths.append(int(info[0]))
+    st = get_state(L, p)
+    L.emu_pipe_destroy(p)
+    return dec[:n].copy(), slot[:n].copy(), st, paths
+
+
+def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True):
+    cd = O.new_codel(target, state)
+    od, os_, ost = O.drain(cd, start, now, None, nslots=nslots)
+    dec, slot, (st, cursor, td, ta), paths = run_batches(L, start, now, cuts, target, nslots, state)
+    assert np.array_equal(dec, od)
+    assert np.array_equal(slot, os_)
+    util.assert_state_equal(st, cd.as_dict())
+    assert (cursor, td, ta) == (ost.cursor, ost.drops, ost.admits)
+    if expect_parallel:
+        assert all(p == 0 for p in paths), paths
+    return od
+
+
+def test_small_trace_in_ragged_batches(emu):
+    n = 30_000 if FULL else 9_000
+    start, now = tracegen.gen_trace(n, seed=5, de=8_000, unit=1 << 10)
+    od = check(emu, start, now, [0, 1, 2_049, 4_096, n], 5, 97)
+    assert 0 < (od == 1).sum() < n  # drops and admits both occur
+
+
+def test_batch_starting_inside_a_dropping_episode(emu):
+    n = 7_000
+    start, now = tracegen.gen_trace(n, seed=9, de=20_000, unit=1 << 11, start_overloaded=True)
+    state = {"count": 9, "drop_next": float(now[0]) / 1e6 - 20.0, "first_above_time": float(now[0]) / 1e6 - 300.0,
+             "dropping": True, "last_empty": None}
+    check(emu, start, now, [0, 3_000, n], 5, 13, state)
+
+
+def test_non_monotone_clock_takes_the_sequential_path(emu):
+    n = 5_000
+    start, now = tracegen.gen_trace(n, seed=11, de=10_000, unit=1 << 10)
+    now = now.copy()
+    now[2_500:] -= 150_000_000  # the clock steps back 150 ms inside the batch
+    start = np.minimum(start, now)
+    cd = O.new_codel(5)
+    od, os_, ost = O.drain(cd, start, now, None, nslots=31)
+    dec, slot, (st, cursor, td, ta), paths = run_batches(emu, start, now, [0, n], 5, 31)
+    assert paths == [1]
+    assert np.array_equal(dec, od) and np.array_equal(slot, os_)
+    util.assert_state_equal(st, cd.as_dict())

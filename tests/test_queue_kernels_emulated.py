@@ -26,12 +26,12 @@ class QueueDev(C.Structure):
 
 @pytest.fixture(scope="module")
 def emu():
-    srcs = [os.path.join(EMU, "queue_emu.cpp"), os.path.join(EMU, "cuda_emu.h"),
+    srcs = [os.path.join(EMU, "queue_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h"),
             os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_queue.cuh"),
             os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_device.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
-                               "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0]])
+                               "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
     L = C.CDLL(SO)
     L.emu_queue_create.restype = C.c_void_p
     L.emu_queue_create.argtypes = [C.c_double, C.c_longlong, C.c_uint64, C.c_uint64, C.c_uint64]
