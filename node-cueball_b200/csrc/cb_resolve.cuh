@@ -71,6 +71,18 @@ struct ResolveParams {
 	int32_t *backend;
 	const int32_t *slot_backend;
 	int nslots;
+	// first_above_time hand-over of the F-chain variant of the commit kernel (else null)
+	struct FSlot *fslots;
+};
+
+// F-chain: first_above_time evolves independently of (drop_next, count, dropping), and a batch that
+// contains any below-target claim fixes its outgoing value without knowing the incoming one.  The
+// commit kernel of batch k therefore publishes F_out(k) in its prologue into slot k % FSLOTS, and
+// batch k+1 resolves its inherited stretch before the ControlledDelay state itself arrives.
+constexpr int FSLOTS = 16; // more than the batches that can be in flight
+struct FSlot {
+	unsigned long long seq; // k + 1 once F_out(k) is published
+	double F;
 };
 
 template <bool NS>
@@ -601,273 +613,23 @@ __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p)
 	}
 }
 
-// The commit kernel: everything that depends on the ControlledDelay state carried from the
-// previous batch.  One small CTA; runs strictly in batch order.
-template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p) {
-	CB_DYN_SHARED(double, s_cidx); // the coarse clock index (prepare wrote it to idx_ms)
-	__shared__ unsigned long long s_evc[SEV_MAX], s_evq[SEV_MAX], s_evd[SEV_MAX];
-	__shared__ double s_evnow[SEV_MAX];
-	__shared__ unsigned int s_ncar;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	DevState *g = p.g;
-	BatchCtl *bc = p.bc;
-	if (tid == 0)
-		bc->dbg[7] = gtimer();
-	const bool fallback = (bc->nonmono != 0u) || (bc->overflow != 0u);
+#define CB_COMMIT_NAME commit_kernel
+#define CB_COMMIT_FCHAIN 0
+#include "cb_commit_body.inc"
+#undef CB_COMMIT_NAME
+#undef CB_COMMIT_FCHAIN
+#define CB_COMMIT_NAME commit_fchain_kernel
+#define CB_COMMIT_FCHAIN 1
+#include "cb_commit_body.inc"
+#undef CB_COMMIT_NAME
+#undef CB_COMMIT_FCHAIN
 
-	// ---- everything that does not depend on the carried state: done while the previous batch's
-	// commit may still be running --------------------------------------------------------------
-	const unsigned int nevp = fallback ? 0u : bc->nev_prep;
-	const bool ev_smem = nevp + EV_FRONT <= SEV_MAX;
-	unsigned long long *evc = ev_smem ? s_evc : p.evc;
-	unsigned long long *ev_q = ev_smem ? s_evq : p.ev_q;
-	unsigned long long *ev_d = ev_smem ? s_evd : p.ev_d;
-	double *ev_now = ev_smem ? s_evnow : p.ev_now;
-	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
-	const unsigned long long G = stride * TILE;
-	if (!fallback) {
-		if (ev_smem) {
-			for (unsigned int k = tid; k < nevp; k += CTPB) {
-				s_evc[EV_FRONT + k] = p.evc[EV_FRONT + k];
-				s_evq[EV_FRONT + k] = p.ev_q[EV_FRONT + k];
-				s_evd[EV_FRONT + k] = p.ev_d[EV_FRONT + k];
-				s_evnow[EV_FRONT + k] = p.ev_now[EV_FRONT + k];
-			}
-		}
-		const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
-		for (unsigned int k = tid; k < nidx; k += CTPB)
-			s_cidx[k] = p.idx_ms[k];
-	}
-	// every state-independent word the serial part reads, fetched now (one round trip, overlapped
-	// with the wait below) instead of one dependent access at a time afterwards
-	const unsigned int cj_exists = fallback ? 0u : bc->cj_exists, cj_closes = bc->cj_closes, anchored = bc->anchored;
-	const unsigned long long cj_close = bc->cj_close;
-	const double now0p100 = bc->now0p100, F_anchor = bc->F_anchor;
-	const unsigned int hasE_new = bc->hasE_new, trailing_marker = bc->trailing_marker;
-	const double E_val = bc->E_val;
-	double now_before_close = 0.0; // clock of the last claim of the inherited stretch
-	if (cj_exists && cj_close > 0)
-		now_before_close = now_at<NS>(p.now, cj_close - 1);
-	if (tid == 0) {
-		s_ncar = 0;
-		// ---- hand-over: wait until the previous batch has committed its state.  It was launched
-		// before this one (possibly on another stream), so it is running or about to; the bound only
-		// keeps a broken chain from hanging the device.
-		chain_wait(p.link, g);
-		bc->dbg[12] = gtimer();
-	}
-	__syncthreads();
-	if (fallback) {
-		if (warp == 0) {
-			sequential_path<NS>(p, lane);
-			__syncwarp();
-			if (lane == 0)
-				chain_post(p.link, g);
-		}
-		return;
-	}
-	const double F_in = g->F, D_in = g->D;
-	const int B_in = g->B;
-	const unsigned long long C_in = g->C, cursor_in = g->cursor;
-
-	// ---- the stretch inherited from the previous batch (claims [0, close) are all above target) --
-	if (cj_exists) {
-		const unsigned long long close = cj_close;
-		const double F = (F_in != 0.0) ? F_in : now0p100; // F == 0: claim 0 opens the run itself
-		const int cb = claim_class(true, now_before_close, F);
-		// crossings: warp 0 -> first class >= 1, warp 1 -> first class 2 (independent searches)
-		if (cb >= 1 && warp < 2 && (warp == 0 || cb == 2)) {
-			Pred pr;
-			pr.x = F;
-			pr.level = warp + 1;
-			const unsigned long long pos = warp_search<NS>(p.now, s_cidx, G, 0, close, pr, lane);
-			if (warp == 0) {
-				const int c = claim_class(true, now_at<NS>(p.now, pos), F);
-				if (lane == 0)
-					evc[0] = (pos << 2) | (unsigned long long)c; // staged at slot 0, compacted below
-			} else {
-				bool separate = pos > 0 && claim_class(true, now_at<NS>(p.now, pos - 1), F) >= 1;
-				if (lane == 0)
-					evc[1] = separate ? ((pos << 2) | 2ull) : ~0ull;
-			}
-		}
-		__syncthreads();
-		if (tid == 0) {
-			// compact into [EV_FRONT - ncar, EV_FRONT): crossing(s), then the close event
-			unsigned long long tmp[3];
-			unsigned int nc = 0;
-			if (cb >= 1) {
-				tmp[nc++] = evc[0];
-				if (cb == 2 && evc[1] != ~0ull)
-					tmp[nc++] = evc[1];
-				if (cj_closes)
-					tmp[nc++] = (close << 2);
-			}
-			for (unsigned int k = 0; k < nc; k++)
-				evc[EV_FRONT - nc + k] = tmp[k];
-			s_ncar = nc;
-		}
-		__syncthreads();
-		// speculation for the carried run's events (one warp each)
-		const unsigned int nc = s_ncar;
-		if ((unsigned int)warp < nc) {
-			const unsigned int k = EV_FRONT - nc + warp;
-			const unsigned long long w = evc[k];
-			const int c = (int)(w & 3ull);
-			if (c != 0) {
-				const unsigned long long idx = w >> 2, q = close - 1;
-				const double nowk = now_at<NS>(p.now, idx);
-				Pred pr;
-				pr.level = 0;
-				unsigned long long d;
-				if (warp == 0 && idx == 0 && B_in) { // the batch opens inside a dropping episode
-					pr.x = D_in;
-					d = warp_search<NS>(p.now, s_cidx, G, idx, q + 1, pr, lane);
-				} else {
-					pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
-					d = warp_search<NS>(p.now, s_cidx, G, idx + 1, q + 1, pr, lane);
-				}
-				if (lane == 0) {
-					ev_now[k] = nowk;
-					ev_q[k] = q;
-					ev_d[k] = d;
-				}
-			}
-		}
-		__syncthreads();
-	}
-
-	// ---- 3. the serial chain over events: warp 0, every lane carrying the same scalars so that
-	// the searches a failed speculation needs are warp-wide (3-4 dependent accesses, not 20+) ----
-	if (warp == 0) {
-		const bool wr = (lane == 0);
-		double D = D_in;
-		unsigned long long C = C_in;
-		int B = B_in;
-		unsigned long long drops = 0;
-		unsigned int niv = 0;
-		const unsigned int k0 = EV_FRONT - s_ncar, nev = EV_FRONT + nevp;
-		if (k0 == nev || (evc[k0] >> 2) > 0)
-			B = 0; // the batch starts with class-0 claims
-		unsigned int k = k0;
-		while (k < nev) {
-			const unsigned long long w = evc[k];
-			const int c = (int)(w & 3ull);
-			if (c == 0) {
-				B = 0;
-				k++;
-				continue;
-			}
-			const unsigned long long pidx = w >> 2;
-			const bool has2 = (c == 1) && (k + 1 < nev) && ((evc[k + 1] & 3ull) == 2);
-			const unsigned long long q = ev_q[k];
-			if (B) { // lib/codel.js:62-68, episode carried in from the previous batch
-				const unsigned long long d = ev_d[k];
-				if (d <= q) {
-					if (wr) {
-						p.iv_lo[niv] = d;
-						p.iv_hi[niv] = q;
-						p.iv_cum[niv] = drops;
-					}
-					niv++;
-					drops += q - d + 1;
-					C += q - d + 1;
-				}
-			} else { // lib/codel.js:70-83
-				long long e = -1;
-				double now_e = ev_now[k];
-				unsigned long long dspec = ev_d[k];
-				bool cond1 = __dsub_rn(now_e, D) < CODEL_INTERVAL;
-				if (c == 2 || cond1) {
-					e = (long long)pidx;
-				} else if (has2) {
-					e = (long long)(evc[k + 1] >> 2);
-					now_e = ev_now[k + 1];
-					dspec = ev_d[k + 1];
-					cond1 = __dsub_rn(now_e, D) < CODEL_INTERVAL;
-				}
-				if (e >= 0) {
-					C = cond1 ? (C > 2 ? C - 2 : 1) : 1;
-					D = drop_next_after(now_e, C);
-					B = 1;
-					unsigned long long d = dspec;
-					if (C != 1) { // speculation assumed count == 1 (drop_next = now + 100)
-						Pred pr;
-						pr.level = 0;
-						pr.x = D;
-						d = warp_search<NS>(p.now, s_cidx, G, (unsigned long long)e + 1, q + 1, pr, lane);
-					}
-					if (wr) {
-						p.iv_lo[niv] = (unsigned long long)e;
-						p.iv_hi[niv] = (unsigned long long)e;
-						p.iv_cum[niv] = drops;
-					}
-					niv++;
-					drops += 1;
-					if (d <= q) {
-						if (wr) {
-							p.iv_lo[niv] = d;
-							p.iv_hi[niv] = q;
-							p.iv_cum[niv] = drops;
-						}
-						niv++;
-						drops += q - d + 1;
-						C += q - d + 1;
-					}
-				}
-			}
-			k += has2 ? 2 : 1;
-		}
-		// ---- final ControlledDelay state -------------------------------------------------
-		double F;
-		if (anchored)
-			F = F_anchor;
-		else // the whole batch is one above-target run without a reset: F is inherited, or opened by claim 0
-			F = (F_in != 0.0) ? F_in : now0p100;
-		if (FLAGS) {
-			if (hasE_new) {
-				if (wr) {
-					g->E = E_val;
-					g->hasE = 1;
-				}
-				if (trailing_marker)
-					F = 0.0; // trailing empty(): lib/codel.js:93
-			}
-		}
-		if (wr) {
-			bc->dbg[5] = gtimer();
-			g->F = F;
-			g->D = D;
-			g->C = C;
-			g->B = B;
-			bc->n = p.n;
-			bc->path = 0;
-			bc->n_events = nev - k0;
-			bc->n_intervals = niv;
-			bc->gcounts[2] = p.n;
-			bc->gcounts[3] = drops; // CoDel-level drops (incl. non-waiting handles)
-			bc->cursor0 = cursor_in;
-			if (!FLAGS) {
-				const unsigned long long admits = p.n - drops;
-				bc->drops = drops;
-				bc->admits = admits;
-				bc->skipped = 0;
-				g->tot_drops += drops;
-				g->tot_admits += admits;
-				bc->gcounts[0] = drops;
-				bc->gcounts[1] = admits;
-				g->cursor = cursor_in + admits; // the emit kernel works from cursor0
-				// the next batch's commit may go ahead (a flags batch finishes the cursor in its emit
-				// kernel, which then passes the chain on)
-				chain_post(p.link, g);
-			} else {
-				bc->drops = 0; // accumulated by the emit kernel (waiting handles only)
-				bc->admits = 0;
-				bc->skipped = 0;
-			}
-		}
-	}
+// one thread: seed the slot the first batch after a host-side state change reads
+__global__ void fchain_seed_kernel(const DevState *g, FSlot *fslots, unsigned long long seq) {
+	FSlot *prev = &fslots[(seq + FSLOTS - 1) % FSLOTS];
+	prev->F = g->F;
+	__threadfence();
+	st_release(&prev->seq, seq);
 }
 
 // ---- scalar entry points (one claim): ControlledDelay#overloaded / #empty ---------------

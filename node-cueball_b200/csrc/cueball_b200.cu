@@ -120,6 +120,9 @@ struct cb_ctx {
 	unsigned char *q_waiting = nullptr;
 	double *q_tmo = nullptr;
 	size_t q_cap = 0, q_res_cap = 0, q_stage_cap = 0;
+	// F-chain variant of the commit kernel (CB_FCHAIN=1; not yet validated on hardware)
+	bool fchain = false, fseed = true;
+	FSlot *d_fslots = nullptr;
 	int prio_least = 0, prio_greatest = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
@@ -341,6 +344,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.backend = d_backend;
 	rp.slot_backend = c->d_slot_backend;
 	rp.nslots = c->nslots;
+	const bool use_f = c->fchain && c->ring_n == 0;
+	rp.fslots = use_f ? c->d_fslots : nullptr;
 
 	EmitParams ep;
 	ep.flags = d_flags;
@@ -385,6 +390,10 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	}
 	if (in_ready)
 		CU(c, cudaStreamWaitEvent(s, in_ready, 0));
+	if (use_f && c->fseed) { // the state was set from the host: seed the slot this batch reads
+		fchain_seed_kernel<<<1, 1, 0, s>>>(c->g, c->d_fslots, c->chain_seq);
+		c->fseed = false;
+	}
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[0], s));
 	if (piped) {
@@ -418,7 +427,12 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	// commit(k) spins (one thread) on the chain word until batch k-1 has published its state, so
 	// the hand-over costs an L2 round trip instead of a cross-stream event (~5 us measured).
 	const size_t cidx_bytes = ((tiles + ((tiles + NIDX_MAX - 1) / NIDX_MAX) - 1) / ((tiles + NIDX_MAX - 1) / NIDX_MAX)) * sizeof(double);
-	if (flags)
+	if (use_f) {
+		if (flags)
+			commit_fchain_kernel<NS, true><<<1, CTPB, cidx_bytes, s>>>(rp);
+		else
+			commit_fchain_kernel<NS, false><<<1, CTPB, cidx_bytes, s>>>(rp);
+	} else if (flags)
 		commit_kernel<NS, true><<<1, CTPB, cidx_bytes, s>>>(rp);
 	else
 		commit_kernel<NS, false><<<1, CTPB, cidx_bytes, s>>>(rp);
@@ -745,6 +759,15 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
+	if (getenv("CB_FCHAIN") && atoi(getenv("CB_FCHAIN")) != 0) {
+		c->fchain = true;
+		CU0(cudaMalloc((void **)&c->d_fslots, FSLOTS * sizeof(FSlot)));
+		CU0(cudaMemset(c->d_fslots, 0, FSLOTS * sizeof(FSlot)));
+		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	}
 	CU0(cudaMalloc((void **)&c->d_chain, sizeof(ChainMem)));
 	CU0(cudaMemset(c->d_chain, 0, sizeof(ChainMem)));
 	for (int l = 0; l < CB_LANES; l++) {
@@ -805,6 +828,8 @@ extern "C" void cb_destroy(cb_ctx *c) {
 				cudaEventDestroy(e);
 	}
 	ring_close(c);
+	if (c->d_fslots)
+		cudaFree(c->d_fslots);
 	void *qfrees[] = {c->d_q, c->q_start, c->q_deadline, c->q_ticket, c->q_res, c->q_stage, c->q_waiting, c->q_tmo};
 	for (void *p : qfrees)
 		if (p)
@@ -900,6 +925,7 @@ extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
 	if (!c)
 		return CB_EINVAL;
 	c->tot_valid = false;
+	c->fseed = true;
 	// utils.assertClaimDelay, lib/utils.js:188-195: finite, > 0, integral
 	if (!isfinite(target_ms) || !(target_ms > 0) || target_ms != floor(target_ms))
 		return fail(c, CB_EINVAL, "targetClaimDelay must be a positive integer number of ms");
@@ -930,6 +956,7 @@ extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
 	if (!c || !in)
 		return CB_EINVAL;
 	c->tot_valid = false;
+	c->fseed = true;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	int rc = drain(c);
@@ -951,6 +978,7 @@ extern "C" int cb_codel_empty(cb_ctx *c, int64_t now_ns) {
 	if (!c)
 		return CB_EINVAL;
 	c->tot_valid = false;
+	c->fseed = true;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	int rc = drain(c);
@@ -983,6 +1011,7 @@ extern "C" int cb_codel_overloaded(cb_ctx *c, int64_t start_ns, int64_t now_ns, 
 	if (!c || !drop)
 		return CB_EINVAL;
 	c->tot_valid = false;
+	c->fseed = true;
 	if (!c->codel_ready)
 		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
 	int rc = drain(c);
@@ -1276,6 +1305,7 @@ extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next
 	if (!c)
 		return CB_EINVAL;
 	c->tot_valid = false;
+	c->fseed = true;
 	int rc = drain(c);
 	if (rc)
 		return rc;
@@ -1365,6 +1395,7 @@ static int queue_ready(cb_ctx *c) {
 	if (!c->d_q)
 		return fail(c, CB_ESTATE, "cb_queue_create has not been called");
 	c->tot_valid = false;
+	c->fseed = true;
 	return drain(c);
 }
 static int queue_check(cb_ctx *c) {

@@ -28,12 +28,17 @@ struct EmuPipe {
 	DevState g;
 	ChainMem chain;
 	unsigned long long seq;
+	int fchain;  /* use commit_fchain_kernel (the F-chain variant) */
+	int fseed;   /* the state was set from the host since the last batch */
+	FSlot fslots[FSLOTS];
 };
 
 extern "C" {
-EmuPipe *emu_pipe_create(double target) {
+EmuPipe *emu_pipe_create(double target, int fchain) {
 	EmuPipe *e = static_cast<EmuPipe *>(std::calloc(1, sizeof(EmuPipe)));
 	e->g.target = target;
+	e->fchain = fchain;
+	e->fseed = 1;
 	return e;
 }
 void emu_pipe_destroy(EmuPipe *e) { std::free(e); }
@@ -46,6 +51,7 @@ void emu_pipe_set_state(EmuPipe *e, double F, double D, unsigned long long C, in
 	e->g.hasE = hasE;
 	e->g.E = E;
 	e->g.cursor = cursor;
+	e->fseed = 1;
 }
 void emu_pipe_get_state(EmuPipe *e, double *F, double *D, unsigned long long *C, int *B, int *hasE, double *E,
     unsigned long long *cursor, unsigned long long *tot_drops, unsigned long long *tot_admits) {
@@ -139,6 +145,7 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, uns
 	rp.backend = nullptr;
 	rp.slot_backend = nullptr;
 	rp.nslots = nslots;
+	rp.fslots = e->fchain ? e->fslots : nullptr;
 
 	EmitParams ep;
 	ep.flags = nullptr;
@@ -164,7 +171,21 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, uns
 
 	run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, false>(sp); });
 	run_grid(1, RTPB, [&] { prepare_kernel<true, false>(rp); });
-	run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+	if (e->fchain) {
+		if (e->fseed) {
+			DevState *gp = &e->g;
+			FSlot *fs = e->fslots;
+			const unsigned long long sq = e->seq;
+			run_grid(1, 32, [=] {
+				if (threadIdx.x == 0)
+					fchain_seed_kernel(gp, fs, sq);
+			});
+			e->fseed = 0;
+		}
+		run_grid(1, CTPB, [&] { commit_fchain_kernel<true, false>(rp); });
+	} else {
+		run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+	}
 	const unsigned egrid = (unsigned)(etiles < 8 ? etiles : 8); /* persistent CTAs striding over the emit tiles */
 	run_grid(egrid, ETPB, [&] { emit_kernel<false>(ep); });
 	e->seq++;

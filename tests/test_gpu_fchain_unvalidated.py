@@ -1,0 +1,76 @@
+"""GPU parity tests of the F-chain variant of the commit kernel (CB_FCHAIN=1: first_above_time is
+handed from batch to batch ahead of the rest of the ControlledDelay state, so the inherited stretch
+is resolved before the state arrives).  The variant passes the CPU emulation
+(tests/test_pipeline_kernels_emulated.py) but has NOT run on hardware yet, so these tests are skipped
+unless CB_TEST_UNVALIDATED=1; the default library path does not use the kernel."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from cueball_b200 import tracegen
+from oracle import oracle as O
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CB_TEST_UNVALIDATED") != "1",
+                                 reason="commit_fchain_kernel not yet validated on hardware (set CB_TEST_UNVALIDATED=1)")]
+
+
+@pytest.fixture()
+def cb(monkeypatch):
+    monkeypatch.setenv("CB_FCHAIN", "1")
+    import cueball_b200
+    return cueball_b200
+
+
+@pytest.mark.parametrize("depth", [1, 3, 5, 8])
+@pytest.mark.parametrize("with_flags", [False, True], ids=["noflags", "flags"])
+def test_fchain_streams_of_small_batches(cb, depth, with_flags):
+    import torch
+    n, m, tgt, nslots = 2_000_000, 31_250, 5, 61
+    start, now = tracegen.gen_trace(n, seed=177, de=1_000, unit=1 << 13)
+    flags = util.make_flags(n, 5, cancel_mod=6, empty_mod=30_011) if with_flags else None
+    ctx = cb.Context(0)
+    ctx.codel_init(tgt)
+    ctx.backends_set(8, tracegen.gen_insert_draws(8), nslots)
+    ctx.set_pipeline_depth(depth)
+    dev = torch.device("cuda:0")
+    ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+    tf = torch.from_numpy(flags).to(dev) if with_flags else None
+    dec = torch.empty(n, dtype=torch.uint8, device=dev)
+    slot = torch.empty(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for lo in range(0, n, m):
+        k = min(m, n - lo)
+        ctx.admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo, tf.data_ptr() + lo if with_flags else None, k,
+                            dec.data_ptr() + lo, slot.data_ptr() + 4 * lo, None)
+    st = ctx.stats()
+    cd = O.new_codel(tgt)
+    od, os_, ost = O.drain(cd, start, now, flags, nslots=nslots)
+    assert np.array_equal(dec.cpu().numpy(), od)
+    assert np.array_equal(slot.cpu().numpy(), os_)
+    util.assert_state_equal({"count": st.state.count, "drop_next": st.state.drop_next,
+                             "first_above_time": st.state.first_above_time, "dropping": bool(st.state.dropping),
+                             "last_empty": st.state.last_empty if st.state.has_last_empty else None}, cd.as_dict())
+    assert st.cursor == ost.cursor and st.total_drops == ost.drops
+
+
+def test_fchain_after_host_side_state_changes(cb):
+    """set_state / empty() between batches reseed the hand-over slot."""
+    tgt, nslots, n = 5, 13, 400_000
+    start, now = tracegen.gen_trace(n, seed=178, de=2_000, unit=1 << 12, start_overloaded=True)
+    ctx = cb.Context(0)
+    ctx.codel_init(tgt)
+    ctx.backends_set(4, tracegen.gen_insert_draws(4), nslots)
+    cd = O.new_codel(tgt)
+    state = {"count": 5, "drop_next": float(now[0]) / 1e6 - 30.0, "first_above_time": float(now[0]) / 1e6 - 250.0,
+             "dropping": True, "last_empty": None}
+    for lo, hi in [(0, 150_000), (150_000, 260_000), (260_000, n)]:
+        ctx.set_state(state)
+        cd = O.new_codel(tgt, state)
+        dec, slot, _, st = ctx.admit_batch(start[lo:hi], now[lo:hi])
+        od, os_, _ = O.drain(cd, start[lo:hi], now[lo:hi], None, nslots=nslots, cursor=st.cursor - int((dec == 0).sum()))
+        assert np.array_equal(dec, od)
+        state = cd.as_dict()
+        state["count"] = int(state["count"])

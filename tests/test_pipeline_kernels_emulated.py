@@ -30,7 +30,7 @@ def emu():
                                "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
     L = C.CDLL(SO)
     L.emu_pipe_create.restype = C.c_void_p
-    L.emu_pipe_create.argtypes = [C.c_double]
+    L.emu_pipe_create.argtypes = [C.c_double, C.c_int]
     L.emu_pipe_destroy.argtypes = [C.c_void_p]
     L.emu_pipe_set_state.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_uint64]
     L.emu_pipe_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 9
@@ -57,8 +57,8 @@ def get_state(L, p):
              "last_empty": E.value if hasE.value else None}, cur.value, td.value, ta.value)
 
 
-def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False):
-    p = L.emu_pipe_create(float(target))
+def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False, fchain=0):
+    p = L.emu_pipe_create(float(target), int(fchain))
     if state:
         le = state.get("last_empty")
         L.emu_pipe_set_state(p, state["first_above_time"], state["drop_next"], int(state["count"]),
@@ -82,10 +82,10 @@ def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False
     return dec[:n].copy(), slot[:n].copy(), st, paths
 
 
-def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True):
+def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True, fchain=0):
     cd = O.new_codel(target, state)
     od, os_, ost = O.drain(cd, start, now, None, nslots=nslots)
-    dec, slot, (st, cursor, td, ta), paths = run_batches(L, start, now, cuts, target, nslots, state)
+    dec, slot, (st, cursor, td, ta), paths = run_batches(L, start, now, cuts, target, nslots, state, fchain=fchain)
     assert np.array_equal(dec, od)
     assert np.array_equal(slot, os_)
     util.assert_state_equal(st, cd.as_dict())
@@ -95,22 +95,40 @@ def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True)
     return od
 
 
-def test_small_trace_in_ragged_batches(emu):
+FCHAIN = pytest.mark.parametrize("fchain", [0, 1], ids=["commit", "commit_fchain"])
+
+
+@FCHAIN
+def test_small_trace_in_ragged_batches(emu, fchain):
     n = 30_000 if FULL else 9_000
     start, now = tracegen.gen_trace(n, seed=5, de=8_000, unit=1 << 10)
-    od = check(emu, start, now, [0, 1, 2_049, 4_096, n], 5, 97)
+    od = check(emu, start, now, [0, 1, 2_049, 4_096, n], 5, 97, fchain=fchain)
     assert 0 < (od == 1).sum() < n  # drops and admits both occur
 
 
-def test_batch_starting_inside_a_dropping_episode(emu):
+@FCHAIN
+def test_batch_starting_inside_a_dropping_episode(emu, fchain):
     n = 7_000
     start, now = tracegen.gen_trace(n, seed=9, de=20_000, unit=1 << 11, start_overloaded=True)
     state = {"count": 9, "drop_next": float(now[0]) / 1e6 - 20.0, "first_above_time": float(now[0]) / 1e6 - 300.0,
              "dropping": True, "last_empty": None}
-    check(emu, start, now, [0, 3_000, n], 5, 13, state)
+    check(emu, start, now, [0, 3_000, n], 5, 13, state, fchain=fchain)
 
 
-def test_non_monotone_clock_takes_the_sequential_path(emu):
+@FCHAIN
+def test_batches_cut_inside_long_overload_runs(emu, fchain):
+    """Batch boundaries inside above-target runs: inherited stretches with both class crossings,
+    batches that are one above-target run end to end (first_above_time passes through), episodes
+    carried across several batches."""
+    n = 12_288
+    start, now = tracegen.gen_trace(n, seed=21, de=30_000, unit=1 << 10, all_overloaded_from=1_500)
+    cuts = [0, 1_000, 2_048, 2_300, 4_096, 6_200, 8_192, 10_000, n]
+    od = check(emu, start, now, cuts, 5, 29, fchain=fchain)
+    assert (od == 1).sum() > 1_000
+
+
+@FCHAIN
+def test_non_monotone_clock_takes_the_sequential_path(emu, fchain):
     n = 5_000
     start, now = tracegen.gen_trace(n, seed=11, de=10_000, unit=1 << 10)
     now = now.copy()
@@ -118,7 +136,8 @@ def test_non_monotone_clock_takes_the_sequential_path(emu):
     start = np.minimum(start, now)
     cd = O.new_codel(5)
     od, os_, ost = O.drain(cd, start, now, None, nslots=31)
-    dec, slot, (st, cursor, td, ta), paths = run_batches(emu, start, now, [0, n], 5, 31)
-    assert paths == [1]
+    cuts = [0, 1_000, n, ]
+    dec, slot, (st, cursor, td, ta), paths = run_batches(emu, start, now, cuts, 5, 31, fchain=fchain)
+    assert paths == [0, 1]
     assert np.array_equal(dec, od) and np.array_equal(slot, os_)
     util.assert_state_equal(st, cd.as_dict())
