@@ -2,8 +2,8 @@
  * cb_emit.cuh: scan -> prepare -> commit -> emit) compiled for the host under tests/emu/cuda_emu.h
  * and run one CTA at a time, behind one C function shaped like cb_admit_batch_dev, so that
  * tests/test_pipeline_kernels_emulated.py can compare them with the oracle without a GPU.
- * Batches without waiting-flags only (the flags variant of the emit kernel has CTAs that wait for
- * one another, which needs them to run concurrently).  TEST INFRASTRUCTURE. */
+ * The flags variant of the emit kernel is run as ONE persistent CTA (its CTAs otherwise wait for one
+ * another, which would need them to run concurrently).  TEST INFRASTRUCTURE. */
 #include "../../node-cueball_b200/csrc/cb_scan.cuh"
 #include "../../node-cueball_b200/csrc/cb_resolve.cuh"
 #include "../../node-cueball_b200/csrc/cb_emit.cuh"
@@ -68,8 +68,8 @@ void emu_pipe_get_state(EmuPipe *e, double *F, double *D, unsigned long long *C,
 
 /* one batch, nanosecond clocks, no flags; mirrors enqueue_batch() of csrc/cueball_b200.cu.
  * info[0] = path, [1] = events, [2] = intervals, [3] = drops */
-int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, unsigned long long n, int nslots,
-    unsigned char *decision, int *slot, unsigned long long *info) {
+int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, const unsigned char *flags,
+    unsigned long long n, int nslots, unsigned char *decision, int *slot, unsigned long long *info) {
 	if (n == 0)
 		return 0;
 	const size_t tiles = (n + TILE - 1) / TILE, etiles = (n + ETILE - 1) / ETILE;
@@ -90,7 +90,7 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, uns
 	ScanParams sp;
 	sp.start = start;
 	sp.now = now;
-	sp.flags = nullptr;
+	sp.flags = flags;
 	sp.n = n;
 	sp.b = ctl;
 	sp.target = e->g.target;
@@ -106,7 +106,7 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, uns
 	ResolveParams rp;
 	rp.start = start;
 	rp.now = now;
-	rp.flags = nullptr;
+	rp.flags = flags;
 	rp.n = n;
 	rp.tiles = tiles;
 	rp.g = &e->g;
@@ -148,7 +148,7 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, uns
 	rp.fslots = e->fchain ? e->fslots : nullptr;
 
 	EmitParams ep;
-	ep.flags = nullptr;
+	ep.flags = flags;
 	ep.n = n;
 	ep.tiles = etiles;
 	ep.g = &e->g;
@@ -169,25 +169,36 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, uns
 	ep.ticket = ticket;
 	ep.vec_ok = (((uintptr_t)decision & 7) == 0) && (((uintptr_t)slot & 15) == 0);
 
-	run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, false>(sp); });
-	run_grid(1, RTPB, [&] { prepare_kernel<true, false>(rp); });
-	if (e->fchain) {
-		if (e->fseed) {
-			DevState *gp = &e->g;
-			FSlot *fs = e->fslots;
-			const unsigned long long sq = e->seq;
-			run_grid(1, 32, [=] {
-				if (threadIdx.x == 0)
-					fchain_seed_kernel(gp, fs, sq);
-			});
-			e->fseed = 0;
-		}
-		run_grid(1, CTPB, [&] { commit_fchain_kernel<true, false>(rp); });
-	} else {
-		run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+	if (e->fchain && e->fseed) {
+		DevState *gp = &e->g;
+		FSlot *fs = e->fslots;
+		const unsigned long long sq = e->seq;
+		run_grid(1, 32, [=] {
+			if (threadIdx.x == 0)
+				fchain_seed_kernel(gp, fs, sq);
+		});
+		e->fseed = 0;
 	}
-	const unsigned egrid = (unsigned)(etiles < 8 ? etiles : 8); /* persistent CTAs striding over the emit tiles */
-	run_grid(egrid, ETPB, [&] { emit_kernel<false>(ep); });
+	if (flags) {
+		/* the flags variant of the emit kernel chains tile admit counts through a look-back; with ONE
+		 * persistent CTA walking the tiles in order every look-back finds its predecessors done */
+		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, true>(sp); });
+		run_grid(1, RTPB, [&] { prepare_kernel<true, true>(rp); });
+		if (e->fchain)
+			run_grid(1, CTPB, [&] { commit_fchain_kernel<true, true>(rp); });
+		else
+			run_grid(1, CTPB, [&] { commit_kernel<true, true>(rp); });
+		run_grid(1, ETPB, [&] { emit_kernel<true>(ep); });
+	} else {
+		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, false>(sp); });
+		run_grid(1, RTPB, [&] { prepare_kernel<true, false>(rp); });
+		if (e->fchain)
+			run_grid(1, CTPB, [&] { commit_fchain_kernel<true, false>(rp); });
+		else
+			run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+		const unsigned egrid = (unsigned)(etiles < 8 ? etiles : 8); /* persistent CTAs striding over the emit tiles */
+		run_grid(egrid, ETPB, [&] { emit_kernel<false>(ep); });
+	}
 	e->seq++;
 	if (info) {
 		info[0] = (unsigned long long)ctl->path;

@@ -34,7 +34,8 @@ def emu():
     L.emu_pipe_destroy.argtypes = [C.c_void_p]
     L.emu_pipe_set_state.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_uint64]
     L.emu_pipe_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 9
-    L.emu_pipe_admit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emu_pipe_admit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
     return L
 
 
@@ -57,7 +58,7 @@ def get_state(L, p):
              "last_empty": E.value if hasE.value else None}, cur.value, td.value, ta.value)
 
 
-def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False, fchain=0):
+def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False, fchain=0, flags=None):
     p = L.emu_pipe_create(float(target), int(fchain))
     if state:
         le = state.get("last_empty")
@@ -73,7 +74,9 @@ def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False
         d = aligned(np.zeros(hi - lo, np.uint8))
         sl = aligned(np.zeros(hi - lo, np.int32))
         info = (C.c_uint64 * 4)()
-        L.emu_pipe_admit(p, s.ctypes.data, w.ctypes.data, hi - lo, nslots, d.ctypes.data, sl.ctypes.data, info)
+        f = np.ascontiguousarray(flags[lo:hi]) if flags is not None else None
+        L.emu_pipe_admit(p, s.ctypes.data, w.ctypes.data, f.ctypes.data if f is not None else None, hi - lo, nslots,
+                         d.ctypes.data, sl.ctypes.data, info)
         dec[lo:hi] = d
         slot[lo:hi] = sl
         paths.append(int(info[0]))
@@ -82,10 +85,11 @@ def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False
     return dec[:n].copy(), slot[:n].copy(), st, paths
 
 
-def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True, fchain=0):
+def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True, fchain=0, flags=None):
     cd = O.new_codel(target, state)
-    od, os_, ost = O.drain(cd, start, now, None, nslots=nslots)
-    dec, slot, (st, cursor, td, ta), paths = run_batches(L, start, now, cuts, target, nslots, state, fchain=fchain)
+    od, os_, ost = O.drain(cd, start, now, flags, nslots=nslots)
+    dec, slot, (st, cursor, td, ta), paths = run_batches(L, start, now, cuts, target, nslots, state, fchain=fchain,
+                                                         flags=flags)
     assert np.array_equal(dec, od)
     assert np.array_equal(slot, os_)
     util.assert_state_equal(st, cd.as_dict())
@@ -125,6 +129,20 @@ def test_batches_cut_inside_long_overload_runs(emu, fchain):
     cuts = [0, 1_000, 2_048, 2_300, 4_096, 6_200, 8_192, 10_000, n]
     od = check(emu, start, now, cuts, 5, 29, fchain=fchain)
     assert (od == 1).sum() > 1_000
+
+
+@FCHAIN
+def test_waiting_flags_and_empty_markers(emu, fchain):
+    """Cancelled handles (skipped after CoDel has advanced) and codel.empty() markers, including
+    markers on the last claim of a batch (the next batch starts with first_above_time reset)."""
+    n = 10_240
+    start, now = tracegen.gen_trace(n, seed=33, de=60_000, unit=1 << 10, all_overloaded_from=2_500)
+    flags = util.make_flags(n, 33, cancel_mod=5, empty_mod=3_001)
+    cuts = [0, 700, 2_048, 4_500, 8_192, n]
+    flags[cuts[2] - 1] |= 2  # markers exactly at batch boundaries
+    flags[cuts[4] - 1] |= 2
+    od = check(emu, start, now, cuts, 5, 23, fchain=fchain, flags=flags)
+    assert (od == 2).sum() > 1_000 and (od == 1).sum() > 100
 
 
 @FCHAIN
