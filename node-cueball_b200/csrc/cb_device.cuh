@@ -77,10 +77,22 @@ struct alignas(32) SumDesc {
 //   one queue over R GPUs (ring): wait_word is this rank's mailbox, written by the previous rank over
 //   NVLink peer memory; the state arrives in the mailbox (in_state) and is pushed on to the next
 //   rank's mailbox (post_state) before its word is released at system scope.
+// F-chain (commit_fchain_kernel): first_above_time evolves independently of (drop_next, count,
+// dropping), and a batch that contains any below-target claim fixes its outgoing value without
+// knowing the incoming one.  The commit kernel of a batch therefore publishes its outgoing value in
+// its prologue, into the slot its successor reads, and the successor resolves its inherited stretch
+// before the ControlledDelay state itself arrives.  A mailbox receives one value per step, so the
+// slot of queue position s in a ring of R is (s / R) % FSLOTS.
+constexpr int FSLOTS = 16; // more than the steps that can be in flight
+struct FSlot {
+	unsigned long long tag; // queue position of the batch this value is the INPUT of
+	double F;
+};
 struct ChainMem {
 	unsigned long long seq; // the chain word / mailbox sequence number
 	unsigned long long err; // hand-over timeouts (a broken chain must not hang the device)
 	DevState st;            // ring mode: the state handed to this rank
+	FSlot fs[FSLOTS];       // F-chain slots written by the predecessor (this context itself without a ring)
 };
 struct ChainLink {
 	unsigned long long *wait_word, *post_word, *err;

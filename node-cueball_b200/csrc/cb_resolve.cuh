@@ -71,18 +71,10 @@ struct ResolveParams {
 	int32_t *backend;
 	const int32_t *slot_backend;
 	int nslots;
-	// first_above_time hand-over of the F-chain variant of the commit kernel (else null)
-	struct FSlot *fslots;
-};
-
-// F-chain: first_above_time evolves independently of (drop_next, count, dropping), and a batch that
-// contains any below-target claim fixes its outgoing value without knowing the incoming one.  The
-// commit kernel of batch k therefore publishes F_out(k) in its prologue into slot k % FSLOTS, and
-// batch k+1 resolves its inherited stretch before the ControlledDelay state itself arrives.
-constexpr int FSLOTS = 16; // more than the batches that can be in flight
-struct FSlot {
-	unsigned long long seq; // k + 1 once F_out(k) is published
-	double F;
+	// first_above_time hand-over of the F-chain variant of the commit kernel (see FSlot; else null):
+	// slots this batch reads / writes (the next rank's mailbox in a ring) and the ring size (>= 1)
+	FSlot *f_in, *f_out;
+	unsigned long long f_ring;
 };
 
 template <bool NS>
@@ -625,11 +617,11 @@ __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p)
 #undef CB_COMMIT_FCHAIN
 
 // one thread: seed the slot the first batch after a host-side state change reads
-__global__ void fchain_seed_kernel(const DevState *g, FSlot *fslots, unsigned long long seq) {
-	FSlot *prev = &fslots[(seq + FSLOTS - 1) % FSLOTS];
+__global__ void fchain_seed_kernel(const DevState *g, FSlot *f_in, unsigned long long seq, unsigned long long ring) {
+	FSlot *prev = &f_in[(seq / ring) % FSLOTS];
 	prev->F = g->F;
 	__threadfence();
-	st_release(&prev->seq, seq);
+	st_release(&prev->tag, seq);
 }
 
 // ---- scalar entry points (one claim): ControlledDelay#overloaded / #empty ---------------

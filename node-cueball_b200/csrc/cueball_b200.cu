@@ -122,7 +122,6 @@ struct cb_ctx {
 	size_t q_cap = 0, q_res_cap = 0, q_stage_cap = 0;
 	// F-chain variant of the commit kernel (CB_FCHAIN=1; not yet validated on hardware)
 	bool fchain = false, fseed = true;
-	FSlot *d_fslots = nullptr;
 	int prio_least = 0, prio_greatest = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
@@ -344,8 +343,10 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.backend = d_backend;
 	rp.slot_backend = c->d_slot_backend;
 	rp.nslots = c->nslots;
-	const bool use_f = c->fchain && c->ring_n == 0;
-	rp.fslots = use_f ? c->d_fslots : nullptr;
+	const bool use_f = c->fchain;
+	rp.f_in = use_f ? c->d_chain->fs : nullptr;
+	rp.f_out = use_f ? (c->ring_n > 0 ? c->ring_next->fs : c->d_chain->fs) : nullptr;
+	rp.f_ring = c->ring_n > 0 ? (unsigned long long)c->ring_n : 1ull;
 
 	EmitParams ep;
 	ep.flags = d_flags;
@@ -390,8 +391,11 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	}
 	if (in_ready)
 		CU(c, cudaStreamWaitEvent(s, in_ready, 0));
-	if (use_f && c->fseed) { // the state was set from the host: seed the slot this batch reads
-		fchain_seed_kernel<<<1, 1, 0, s>>>(c->g, c->d_fslots, c->chain_seq);
+	if (use_f && c->fseed) {
+		// the state was set from the host: seed the slot this batch reads.  In a ring only the queue's
+		// first batch (rank 0) is seeded; every other batch gets its value from its predecessor.
+		if (c->ring_n == 0 || (c->ring_rank == 0 && c->chain_seq == 0))
+			fchain_seed_kernel<<<1, 1, 0, s>>>(c->g, c->d_chain->fs, rp.link.wait_val, rp.f_ring);
 		c->fseed = false;
 	}
 	if (c->prof)
@@ -761,8 +765,6 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
 	if (getenv("CB_FCHAIN") && atoi(getenv("CB_FCHAIN")) != 0) {
 		c->fchain = true;
-		CU0(cudaMalloc((void **)&c->d_fslots, FSLOTS * sizeof(FSlot)));
-		CU0(cudaMemset(c->d_fslots, 0, FSLOTS * sizeof(FSlot)));
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
@@ -828,8 +830,6 @@ extern "C" void cb_destroy(cb_ctx *c) {
 				cudaEventDestroy(e);
 	}
 	ring_close(c);
-	if (c->d_fslots)
-		cudaFree(c->d_fslots);
 	void *qfrees[] = {c->d_q, c->q_start, c->q_deadline, c->q_ticket, c->q_res, c->q_stage, c->q_waiting, c->q_tmo};
 	for (void *p : qfrees)
 		if (p)
@@ -1312,7 +1312,7 @@ extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next
 	ring_close(c);
 	if (nranks == 0) { // back to an independent queue: the chain word restarts at the batch count
 		c->chain_seq = 0;
-		CU(c, cudaMemset(c->d_chain, 0, 2 * sizeof(unsigned long long)));
+		CU(c, cudaMemset(c->d_chain, 0, sizeof(ChainMem))); // chain word, error count and the F-chain tags
 		return CB_OK;
 	}
 	if (nranks < 1 || rank < 0 || rank >= nranks)

@@ -30,7 +30,8 @@ struct EmuPipe {
 	unsigned long long seq;
 	int fchain;  /* use commit_fchain_kernel (the F-chain variant) */
 	int fseed;   /* the state was set from the host since the last batch */
-	FSlot fslots[FSLOTS];
+	EmuPipe *next; /* ring: the context whose mailbox this one writes (null: no ring) */
+	int ring_n, ring_rank;
 };
 
 extern "C" {
@@ -51,6 +52,16 @@ void emu_pipe_set_state(EmuPipe *e, double F, double D, unsigned long long C, in
 	e->g.hasE = hasE;
 	e->g.E = E;
 	e->g.cursor = cursor;
+	e->fseed = 1;
+}
+/* cb_ring_connect: this context drains segment (k, rank) of every step k and hands over to `next` */
+void emu_pipe_ring(EmuPipe *e, EmuPipe *next, int nranks, int rank) {
+	e->next = next;
+	e->ring_n = nranks;
+	e->ring_rank = rank;
+	e->seq = 0;
+	std::memset(&e->chain, 0, sizeof(e->chain));
+	e->chain.st = e->g;
 	e->fseed = 1;
 }
 void emu_pipe_get_state(EmuPipe *e, double *F, double *D, unsigned long long *C, int *B, int *hasE, double *E,
@@ -118,12 +129,19 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
 	rp.idx_ms = idx_ms;
 	rp.link.err = &e->chain.err;
 	rp.link.wait_word = &e->chain.seq;
-	rp.link.post_word = &e->chain.seq;
-	rp.link.wait_val = e->seq;
-	rp.link.post_val = e->seq + 1;
 	rp.link.timeout_ns = ~0ull;
-	rp.link.in_state = nullptr;
-	rp.link.post_state = nullptr;
+	if (e->ring_n > 0) { /* as enqueue_batch() does in ring mode */
+		rp.link.wait_val = e->seq * (unsigned long long)e->ring_n + (unsigned long long)e->ring_rank;
+		rp.link.in_state = &e->chain.st;
+		rp.link.post_word = &e->next->chain.seq;
+		rp.link.post_state = &e->next->chain.st;
+	} else {
+		rp.link.wait_val = e->seq;
+		rp.link.in_state = nullptr;
+		rp.link.post_word = &e->chain.seq;
+		rp.link.post_state = nullptr;
+	}
+	rp.link.post_val = rp.link.wait_val + 1;
 	rp.xev = xev;
 	rp.xcnt = xcnt;
 	rp.hj_lo = hj_lo;
@@ -145,7 +163,9 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
 	rp.backend = nullptr;
 	rp.slot_backend = nullptr;
 	rp.nslots = nslots;
-	rp.fslots = e->fchain ? e->fslots : nullptr;
+	rp.f_in = e->fchain ? e->chain.fs : nullptr;
+	rp.f_out = e->fchain ? (e->ring_n > 0 ? e->next->chain.fs : e->chain.fs) : nullptr;
+	rp.f_ring = e->ring_n > 0 ? (unsigned long long)e->ring_n : 1ull;
 
 	EmitParams ep;
 	ep.flags = flags;
@@ -170,13 +190,15 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
 	ep.vec_ok = (((uintptr_t)decision & 7) == 0) && (((uintptr_t)slot & 15) == 0);
 
 	if (e->fchain && e->fseed) {
-		DevState *gp = &e->g;
-		FSlot *fs = e->fslots;
-		const unsigned long long sq = e->seq;
-		run_grid(1, 32, [=] {
-			if (threadIdx.x == 0)
-				fchain_seed_kernel(gp, fs, sq);
-		});
+		if (e->ring_n == 0 || (e->ring_rank == 0 && e->seq == 0)) {
+			DevState *gp = &e->g;
+			FSlot *fs = e->chain.fs;
+			const unsigned long long sq = rp.link.wait_val, rn = rp.f_ring;
+			run_grid(1, 32, [=] {
+				if (threadIdx.x == 0)
+					fchain_seed_kernel(gp, fs, sq, rn);
+			});
+		}
 		e->fseed = 0;
 	}
 	if (flags) {

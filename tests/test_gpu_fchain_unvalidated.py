@@ -74,3 +74,43 @@ def test_fchain_after_host_side_state_changes(cb):
         assert np.array_equal(dec, od)
         state = cd.as_dict()
         state["count"] = int(state["count"])
+
+
+@pytest.mark.parametrize("R", [2, 4])
+def test_fchain_one_queue_over_a_ring_of_contexts(cb, R):
+    """The F-chain slots travel through the ring mailboxes like the rest of the state."""
+    import torch
+    tgt, nslots, steps = 5, 97, 6
+    rng = np.random.RandomState(500 + R)
+    seg = [[int(x) for x in rng.randint(1, 120_000, size=R)] for _ in range(steps)]
+    n = sum(sum(x) for x in seg)
+    start, now = tracegen.gen_trace(n, seed=291 + R, de=1_500, unit=1 << 13)
+    dev = torch.device("cuda:0")
+    ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+    dec = torch.empty(n, dtype=torch.uint8, device=dev)
+    slot = torch.empty(n, dtype=torch.int32, device=dev)
+    ctxs = []
+    for r in range(R):
+        c = cb.Context(0)
+        c.codel_init(tgt)
+        c.backends_set(16, tracegen.gen_insert_draws(16), nslots)
+        ctxs.append(c)
+    boxes = [c.ring_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.ring_connect(R, r, next_ptr=boxes[(r + 1) % R][1])
+    torch.cuda.synchronize()
+    lo = 0
+    for k in range(steps):
+        for r in range(R):
+            m = seg[k][r]
+            ctxs[r].admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo, None, m,
+                                    dec.data_ptr() + lo, slot.data_ptr() + 4 * lo, None)
+            lo += m
+    st = ctxs[R - 1].stats()
+    for c in ctxs:
+        c.synchronize()
+    cd = O.new_codel(tgt)
+    od, os_, ost = O.drain(cd, start, now, None, nslots=nslots)
+    assert np.array_equal(dec.cpu().numpy(), od)
+    assert np.array_equal(slot.cpu().numpy(), os_)
+    assert st.cursor == ost.cursor and st.total_drops == ost.drops

@@ -32,6 +32,7 @@ def emu():
     L.emu_pipe_create.restype = C.c_void_p
     L.emu_pipe_create.argtypes = [C.c_double, C.c_int]
     L.emu_pipe_destroy.argtypes = [C.c_void_p]
+    L.emu_pipe_ring.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.emu_pipe_set_state.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_uint64]
     L.emu_pipe_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 9
     L.emu_pipe_admit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
@@ -159,3 +160,42 @@ def test_non_monotone_clock_takes_the_sequential_path(emu, fchain):
     assert paths == [0, 1]
     assert np.array_equal(dec, od) and np.array_equal(slot, os_)
     util.assert_state_equal(st, cd.as_dict())
+
+
+@FCHAIN
+@pytest.mark.parametrize("R", [2, 3])
+def test_one_queue_over_a_ring_of_contexts(emu, fchain, R):
+    """cb_ring_connect's hand-over (state and cursor through the next context's mailbox; with the
+    F-chain variant also first_above_time, one slot per step) across R emulated contexts: segment
+    (k, r) follows (k, r-1); the result equals ONE sequential drain."""
+    tgt, nslots, steps = 5, 19, 4
+    rng = np.random.RandomState(40 + R)
+    seg = [[int(x) for x in rng.randint(300, 2_600, size=R)] for _ in range(steps)]
+    n = sum(sum(x) for x in seg)
+    start, now = tracegen.gen_trace(n, seed=61 + R, de=40_000, unit=1 << 10, all_overloaded_from=1_200)
+    pipes = [emu.emu_pipe_create(float(tgt), int(fchain)) for _ in range(R)]
+    for r in range(R):
+        emu.emu_pipe_ring(pipes[r], pipes[(r + 1) % R], R, r)
+    dec = np.zeros(n, np.uint8)
+    slot = np.zeros(n, np.int32)
+    lo = 0
+    for k in range(steps):
+        for r in range(R):
+            m = seg[k][r]
+            s, w = aligned(start[lo:lo + m]), aligned(now[lo:lo + m])
+            d, sl = aligned(np.zeros(m, np.uint8)), aligned(np.zeros(m, np.int32))
+            info = (C.c_uint64 * 4)()
+            emu.emu_pipe_admit(pipes[r], s.ctypes.data, w.ctypes.data, None, m, nslots, d.ctypes.data, sl.ctypes.data, info)
+            assert info[0] == 0
+            dec[lo:lo + m] = d
+            slot[lo:lo + m] = sl
+            lo += m
+    st, cursor, td, ta = get_state(emu, pipes[R - 1])  # the last rank's state is the queue's
+    for p in pipes:
+        emu.emu_pipe_destroy(p)
+    cd = O.new_codel(tgt)
+    od, os_, ost = O.drain(cd, start, now, None, nslots=nslots)
+    assert np.array_equal(dec, od) and np.array_equal(slot, os_)
+    util.assert_state_equal(st, cd.as_dict())
+    assert (cursor, td, ta) == (ost.cursor, ost.drops, ost.admits)
+    assert (od == 1).sum() > 500
