@@ -106,6 +106,15 @@ struct ChainLink {
 #define CB_DYN_SHARED(T, name) extern __shared__ __align__(16) T name[]
 #endif
 
+// Points where the code relies on the lanes of a warp (or the warps of a CTA) having executed the
+// preceding loads together before one of them goes on to overwrite what was read: true of converged
+// SIMT execution, not of the host emulation, whose threads are free-running.  Expands to nothing in
+// the CUDA build; the emulation makes it a block barrier.  (Round-2 item: pass such values through
+// shared memory instead, which removes the reliance altogether.)
+#ifndef CB_EMU_LOCKSTEP
+#define CB_EMU_LOCKSTEP()
+#endif
+
 #ifndef CB_EMU // tests/emu/cuda_emu.h supplies host versions of the PTX helpers below
 __device__ __forceinline__ unsigned long long gtimer() {
 	unsigned long long t;

@@ -6,6 +6,7 @@
  * on a machine without a GPU.  It says nothing about memory-model or performance behaviour on the
  * device.  TEST INFRASTRUCTURE: never part of the product library. */
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -45,9 +46,16 @@ public:
 			gen_++;
 			cv_.notify_all();
 		} else {
-			cv_.wait(lk, [&] { return gen_ != g; });
+			int waited = 0;
+			while (!cv_.wait_for(lk, std::chrono::seconds(1), [&] { return gen_ != g; })) {
+				if (++waited >= stall_seconds() || stall_flag())
+					report_stall("barrier");
+			}
 		}
 	}
+	static int stall_seconds();
+	static bool stall_flag();
+	static void report_stall(const char *what); /* prints the stuck thread's stack and aborts */
 
 private:
 	std::mutex m_;
@@ -58,11 +66,14 @@ private:
 extern Barrier block_barrier;
 extern Barrier warp_barrier[64];
 extern unsigned long long warp_slot[64][32];
+extern unsigned int dbg_collectives[2048]; /* warp collectives executed per thread of the running block */
+extern int dbg_exited[2048];
 
 /* every lane publishes one 64-bit value; returns a pointer to the warp's 32 slots, valid until
  * the matching warp_release() */
 inline const unsigned long long *warp_publish(unsigned long long raw) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	dbg_collectives[threadIdx.x]++;
 	warp_slot[warp][lane] = raw;
 	warp_barrier[warp].wait();
 	return warp_slot[warp];
@@ -74,6 +85,7 @@ template <typename T> inline T shfl_from(T v, int src_lane, bool use_own) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned long long raw = 0;
 	std::memcpy(&raw, &v, sizeof(T));
+	dbg_collectives[threadIdx.x]++;
 	warp_slot[warp][lane] = raw;
 	warp_barrier[warp].wait();
 	unsigned long long got = use_own ? raw : warp_slot[warp][src_lane & 31];
@@ -170,6 +182,7 @@ void named_arrive(int id);
 void named_sync(int id);
 } // namespace emu
 #define CB_EMU 1
+#define CB_EMU_LOCKSTEP() __syncthreads()
 #define CB_DYN_SHARED(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem)
 
 /* host versions of the PTX helpers of csrc/cb_device.cuh, cb_scan.cuh, cb_emit.cuh */

@@ -8,6 +8,7 @@
 #include "../../node-cueball_b200/csrc/cb_resolve.cuh"
 #include "../../node-cueball_b200/csrc/cb_emit.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 using namespace cb;
@@ -18,6 +19,8 @@ template <typename T> T *zalloc(size_t n) { return static_cast<T *>(std::calloc(
 template <typename F> void run_grid(unsigned grid, int threads, F kernel_call) {
 	gridDim.x = grid;
 	for (unsigned b = 0; b < grid; b++) {
+		if (std::getenv("CB_EMU_TRACE"))
+			std::fprintf(stderr, "[emu] block %u/%u x %d threads\n", b, grid, threads);
 		blockIdx.x = b;
 		emu::launch(threads, kernel_call);
 	}

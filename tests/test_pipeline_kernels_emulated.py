@@ -7,6 +7,7 @@ GPU time is spent on it).  Batches without waiting-flags only."""
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -20,14 +21,14 @@ SO = os.path.join(EMU, "libpipeline_emu.so")
 FULL = os.environ.get("CB_EMU_FULL") == "1"
 
 
-@pytest.fixture(scope="module")
-def emu():
+def load_emu():
+    """Build (if stale) and load the emulated pipeline library."""
     csrc = os.path.join(util.ROOT, "node-cueball_b200", "csrc")
     srcs = [os.path.join(EMU, "pipeline_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h")] + \
            [os.path.join(csrc, f) for f in ("cb_device.cuh", "cb_scan.cuh", "cb_resolve.cuh", "cb_emit.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
-                               "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-rdynamic", "-fPIC", "-shared", "-pthread",
+                               "-ffp-contract=off", "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
     L = C.CDLL(SO)
     L.emu_pipe_create.restype = C.c_void_p
     L.emu_pipe_create.argtypes = [C.c_double, C.c_int]
@@ -38,6 +39,11 @@ def emu():
     L.emu_pipe_admit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
     return L
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
 
 def aligned(arr):
@@ -199,3 +205,12 @@ def test_one_queue_over_a_ring_of_contexts(emu, fchain, R):
     util.assert_state_equal(st, cd.as_dict())
     assert (cursor, td, ta) == (ost.cursor, ost.drops, ost.admits)
     assert (od == 1).sum() > 500
+
+
+def test_a_few_fuzz_cases(emu):
+    """Twenty cases of tests/fuzz_emulated_pipeline.py (odd sizes, ragged cuts, carried-in states, flags,
+    both commit variants); the full fuzz is run by hand (`python tests/fuzz_emulated_pipeline.py 600`)."""
+    out = subprocess.run([sys.executable, os.path.join(util.ROOT, "tests", "fuzz_emulated_pipeline.py"), "0", "100000", "20"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "iterations 20 bad 0" in out.stdout, out.stdout[-2000:]
