@@ -6,6 +6,7 @@ Host-side mirror of the reference's interface for this path (names as in the ref
     Queue                    lib/queue.js
     planRebalance            lib/utils.js:239-393
     ConnectionPool           lib/pool.js (claim / release / resolver events / getStats)
+    StaticIpResolver, srvKey lib/resolver.js:1157-1171,1387-1456 (backend identity, event stream)
     ClaimTimeoutError ...    lib/errors.js
 
 All arithmetic runs in libcueball_b200.so (hand-written sm_100a CUDA behind the C ABI in
@@ -23,10 +24,11 @@ from .context import Context
 from .errors import ClaimHandleMisusedError, ClaimTimeoutError, NoBackendsError, PoolStoppingError
 from .pool import ConnectionPool, CueBallClaimHandle
 from .queue import Queue
+from .resolver import StaticIpResolver, process_backends, srvKey
 from .utils import assertClaimDelay, currentMillis, planRebalance
 
 __all__ = ["ADMIT", "DROP", "SKIPPED", "F_WAITING", "F_EMPTY_AFTER", "PATH_PARALLEL", "PATH_SEQUENTIAL",
            "BALANCE_UNIFORM", "BALANCE_SRV_WEIGHTED", "CueballError", "ControlledDelay", "Context",
            "ClaimHandleMisusedError", "ClaimTimeoutError", "NoBackendsError", "PoolStoppingError",
            "ConnectionPool", "CueBallClaimHandle", "Queue", "assertClaimDelay", "currentMillis",
-           "planRebalance", "_native"]
+           "planRebalance", "StaticIpResolver", "process_backends", "srvKey", "_native"]
