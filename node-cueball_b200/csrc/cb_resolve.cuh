@@ -271,350 +271,45 @@ constexpr int SEV_MAX = 1024;  // events kept in shared memory for the serial ch
 constexpr int EV_FRONT = 3;    // slots kept free in front of the event list for the carried run's events
 constexpr int CTPB = 128;      // threads of the commit kernel
 
-template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p) {
-	CB_DYN_SHARED(double, s_idx); // clock (ms) at claim k*G, k < nidx
-	__shared__ unsigned int s_warp[32];
-	__shared__ int s_wmax[32];
-	__shared__ unsigned int s_base;
-	__shared__ unsigned int s_nev;
-	__shared__ int s_fallback;
-	__shared__ long long s_prevconst; // last tile with a CONST claim seen so far (-1: none)
-	__shared__ unsigned int s_nheavy;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	BatchCtl *bc = p.bc;
-	using raw_t = typename TimeIn<NS>::raw_t;
-	if (tid == 0)
-		bc->dbg[6] = gtimer();
+#define CB_PREPARE_HEAD                                                                                    \
+	template <bool NS, bool FLAGS> __global__ void __launch_bounds__(RTPB, 1) prepare_kernel(const ResolveParams p)
+#include "cb_prepare_body.inc"
+#undef CB_PREPARE_HEAD
+#define CB_PREPARE_HEAD                                                                                    \
+	template <bool NS, bool FLAGS> __device__ __forceinline__ void prepare_part(const ResolveParams &p)
+#include "cb_prepare_body.inc"
+#undef CB_PREPARE_HEAD
 
-	// coarse clock index: every `stride`-th tile's first claim (loaded while thread 0 checks
-	// whether the scan kernel asked for the exact sequential path)
-	const unsigned long long stride = (p.tiles + NIDX_MAX - 1) / NIDX_MAX;
-	const unsigned long long G = stride * TILE;
-	const unsigned int nidx = (unsigned int)((p.tiles + stride - 1) / stride);
-	if (tid == 0) {
-		s_fallback = (bc->nonmono != 0u) || (bc->overflow != 0u);
-		s_base = 0;
-		s_prevconst = -1;
-		s_nheavy = 0;
-	}
-	for (unsigned int k = tid; k < nidx; k += RTPB) {
-		const double v = TimeIn<NS>::to_ms(reinterpret_cast<const raw_t *>(p.tile_now0)[(unsigned long long)k * stride]);
-		s_idx[k] = v;
-		p.idx_ms[k] = v; // the commit kernel searches the same index (from L2)
-	}
-	__syncthreads();
-	if (s_fallback)
-		return; // the commit kernel runs the exact sequential path
-	const unsigned long long carry_code = CODE_CARRY; // the carried first_above_time is the commit kernel's business
-	if (tid == 0) {
-		bc->cj_exists = 0;
-		bc->cj_close = 0;
-		bc->cj_closes = 0;
-	}
+#define CB_COMMIT_HEAD                                                                                     \
+	template <bool NS, bool FLAGS> __global__ void __launch_bounds__(CTPB, 1) commit_kernel(const ResolveParams p)
+#define CB_COMMIT_FCHAIN false
+#include "cb_commit_body.inc"
+#undef CB_COMMIT_HEAD
+#undef CB_COMMIT_FCHAIN
+#define CB_COMMIT_HEAD                                                                                     \
+	template <bool NS, bool FLAGS> __global__ void __launch_bounds__(CTPB, 1) commit_fchain_kernel(const ResolveParams p)
+#define CB_COMMIT_FCHAIN true
+#include "cb_commit_body.inc"
+#undef CB_COMMIT_HEAD
+#undef CB_COMMIT_FCHAIN
+#define CB_COMMIT_HEAD                                                                                     \
+	template <bool NS, bool FLAGS, bool FCHAIN_T> __device__ __forceinline__ void commit_part(const ResolveParams &p)
+#define CB_COMMIT_FCHAIN FCHAIN_T
+#include "cb_commit_body.inc"
+#undef CB_COMMIT_HEAD
+#undef CB_COMMIT_FCHAIN
 
-	if (tid == 0) bc->dbg[0] = gtimer();
-	// ---- A. pair closing tiles with the run they close; evaluate the inherited stretches ------
-	// One pass handles RT consecutive tiles per thread with every load of a stage issued
-	// together, so the pass costs a handful of dependent memory round trips, not RT of them.
-	// (slot `tiles` is a virtual closing tile at index n: the run still open at the end of the batch)
-	for (unsigned long long base = 0; base < p.tiles + 1; base += (unsigned long long)RTPB * RT) {
-		const unsigned long long t0 = base + (unsigned long long)tid * RT;
-		unsigned int fc[RT];
-		int T0l[RT]; // block-local slot of the opener, -1 = before this thread, resolved below
-		int lastc = -1;
-#pragma unroll
-		for (int k = 0; k < RT; k++)
-			fc[k] = (t0 + k < p.tiles) ? p.rec_fc[t0 + k] : ((t0 + k == p.tiles) ? 0u : FC_NONE);
-#pragma unroll
-		for (int k = 0; k < RT; k++) {
-			T0l[k] = lastc;
-			if (fc[k] != FC_NONE && t0 + k < p.tiles)
-				lastc = tid * RT + k;
-		}
-		int x = lastc;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const int y = __shfl_up_sync(0xffffffffu, x, o);
-			if (lane >= o)
-				x = max(x, y);
-		}
-		if (lane == 31)
-			s_wmax[warp] = x;
-		__syncthreads();
-		int wprev = -1;
-		for (int w = 0; w < warp; w++)
-			wprev = max(wprev, s_wmax[w]);
-		int ex = __shfl_up_sync(0xffffffffu, x, 1);
-		if (lane == 0)
-			ex = -1;
-		ex = max(ex, wprev);
-		const long long Tbefore = (ex >= 0) ? (long long)(base + ex) : s_prevconst;
-		// stage 1: the opener's record
-		long long T0[RT];
-		unsigned long long code0[RT];
-		unsigned int cend0[RT];
-#pragma unroll
-		for (int k = 0; k < RT; k++) {
-			T0[k] = (T0l[k] >= 0) ? (long long)(base + T0l[k]) : Tbefore;
-			code0[k] = carry_code;
-			cend0[k] = 0;
-			if (fc[k] != FC_NONE && T0[k] >= 0) {
-				code0[k] = p.rec_code[T0[k]];
-				cend0[k] = p.rec_cend[T0[k]];
-			}
-		}
-		// stage 2: clock at the run's defining claim and at the stretch's last claim
-		double Fv[RT], nb[RT];
-		bool stretch[RT];
-#pragma unroll
-		for (int k = 0; k < RT; k++) {
-			const unsigned long long lo = (unsigned long long)(T0[k] + 1) * TILE;
-			const unsigned long long close_idx = (t0 + k == p.tiles) ? p.n : (t0 + k) * TILE + fc[k];
-			stretch[k] = (fc[k] != FC_NONE) && (lo < close_idx);
-			Fv[k] = 0.0;
-			nb[k] = 0.0;
-			if (stretch[k] && code0[k] == CODE_CARRY) { // inherited from the previous batch: commit's job
-				stretch[k] = false;
-				bc->cj_exists = 1;
-				bc->cj_close = close_idx;
-				bc->cj_closes = (t0 + k == p.tiles) ? 0u : 1u;
-				code0[k] = CODE_ZERO;
-				cend0[k] = 4u; // marks "carried": no close event from here either
-			}
-			if (stretch[k]) {
-				Fv[k] = __dadd_rn(now_at<NS>(p.now, code0[k] == CODE_ZERO ? lo : code0[k] - 2), CODEL_INTERVAL);
-				nb[k] = now_at<NS>(p.now, close_idx - 1);
-			}
-		}
-		// stage 3: does the class rise inside the stretch?  close event?
-#pragma unroll
-		for (int k = 0; k < RT; k++) {
-			if (t0 + k > p.tiles)
-				continue;
-			const bool is_tail = (t0 + k == p.tiles);
-			unsigned int bits = 0;
-			if (fc[k] != FC_NONE) {
-				const unsigned long long close_idx = is_tail ? p.n : (t0 + k) * TILE + fc[k];
-				int final_c = (int)cend0[k];
-				if (stretch[k]) {
-					const int cb = claim_class(true, nb[k], Fv[k]);
-					if (cb > final_c) { // find where (two warps per such run, below)
-						const unsigned int h = atomicAdd(&s_nheavy, 1u);
-						p.hj_lo[h] = (unsigned long long)(T0[k] + 1) * TILE;
-						p.hj_b[h] = close_idx - 1;
-						p.hj_F[h] = Fv[k];
-						p.hj_info[h] = (unsigned int)(t0 + k) | ((cend0[k] & 3u) << 28) | ((unsigned int)cb << 30);
-						final_c = cb;
-					}
-				}
-				if (final_c >= 1 && final_c < 4 && !is_tail) { // the run ends at a CONST claim (class 0)
-					p.xev[(t0 + k) * 3 + 2] = (close_idx << 2);
-					bits = 4u;
-				}
-			}
-			p.xcnt[t0 + k] = bits;
-		}
-		__syncthreads();
-		if (tid == RTPB - 1) {
-			const int blockmax = max(x, wprev);
-			if (blockmax >= 0)
-				s_prevconst = (long long)(base + blockmax);
-		}
-		__syncthreads();
-	}
-	if (tid == 0) bc->dbg[1] = gtimer();
-	// long runs: the two possible class crossings are independent searches -> one warp each
-	const unsigned int nheavy = s_nheavy;
-	for (unsigned int sub = warp; sub < 2 * nheavy; sub += RTPB / 32) {
-		const unsigned int h = sub >> 1, level = 1 + (sub & 1u);
-		const unsigned int info = p.hj_info[h];
-		const unsigned int slot = info & 0x0fffffffu;
-		const int cend0 = (int)((info >> 28) & 3u), cb = (int)(info >> 30);
-		if ((level == 1 && cend0 != 0) || (level == 2 && cb != 2))
-			continue; // that crossing does not exist in this stretch
-		const unsigned long long lo = p.hj_lo[h], b = p.hj_b[h];
-		const double F = p.hj_F[h];
-		Pred pr;
-		pr.x = F;
-		pr.level = (int)level;
-		const unsigned long long pos = warp_search<NS>(p.now, s_idx, G, lo, b + 1, pr, lane); // exists: class(b) >= level
-		if (level == 1) {
-			const int c = claim_class(true, now_at<NS>(p.now, pos), F); // 1, or 2 when both crossings coincide
-			if (lane == 0) {
-				p.xev[slot * 3 + 0] = (pos << 2) | (unsigned long long)c;
-				atomicOr(&p.xcnt[slot], 1u);
-			}
-		} else {
-			// a separate event only if the class was already 1 just before it
-			bool separate = (cend0 == 1);
-			if (cend0 == 0 && pos > lo)
-				separate = claim_class(true, now_at<NS>(p.now, pos - 1), F) >= 1;
-			if (lane == 0 && separate) {
-				p.xev[slot * 3 + 1] = (pos << 2) | 2ull;
-				atomicOr(&p.xcnt[slot], 2u);
-			}
-		}
-	}
-	__syncthreads();
-
-	if (tid == 0) bc->dbg[2] = gtimer();
-	// ---- B. merge run events and local events into one ordered list -----------------------------
-	for (unsigned long long base = 0; base < p.tiles + 1; base += (unsigned long long)RTPB * RT) {
-		const unsigned long long t0 = base + (unsigned long long)tid * RT;
-		unsigned int xb[RT], lc[RT], cnt = 0;
-#pragma unroll
-		for (int k = 0; k < RT; k++) {
-			const bool in = t0 + k < p.tiles;
-			xb[k] = (t0 + k <= p.tiles) ? p.xcnt[t0 + k] : 0u;
-			lc[k] = in ? p.ev_count[t0 + k] : 0u;
-			cnt += __popc(xb[k]) + lc[k];
-		}
-		unsigned int x = cnt;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
-			if (lane >= o)
-				x += y;
-		}
-		if (lane == 31)
-			s_warp[warp] = x;
-		__syncthreads();
-		if (warp == 0) {
-			const unsigned int w = lane < RTPB / 32 ? s_warp[lane] : 0u;
-			unsigned int ws = w;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const unsigned int y = __shfl_up_sync(0xffffffffu, ws, o);
-				if (lane >= o)
-					ws += y;
-			}
-			s_warp[lane] = ws - w; // exclusive
-			if (lane == 31)
-				s_nev = ws;        // pass total
-		}
-		__syncthreads();
-		unsigned int off = s_base + s_warp[warp] + (x - cnt);
-		if (cnt) {
-			for (int k = 0; k < RT; k++) {
-				const unsigned long long t = t0 + k;
-				// run events of the tile's close come first (crossings <= close index <= local events)
-				if ((xb[k] & 1u) && off + EV_FRONT < p.ev_cap)
-					p.evc[EV_FRONT + off++] = p.xev[t * 3 + 0];
-				if ((xb[k] & 2u) && off + EV_FRONT < p.ev_cap)
-					p.evc[EV_FRONT + off++] = p.xev[t * 3 + 1];
-				if ((xb[k] & 4u) && off + EV_FRONT < p.ev_cap)
-					p.evc[EV_FRONT + off++] = p.xev[t * 3 + 2];
-				if (lc[k]) {
-					// a tile's events were appended unordered: sort its <= EVK entries by index
-					unsigned long long e[EVK];
-#pragma unroll
-					for (int j = 0; j < EVK; j++)
-						e[j] = (j < (int)lc[k]) ? p.ev[t * EVK + j] : ~0ull;
-#pragma unroll
-					for (int a = 1; a < EVK; a++) {
-#pragma unroll
-						for (int b = EVK - 1; b >= 1; b--) {
-							if (b >= a && e[b] < e[b - 1]) {
-								const unsigned long long tmp = e[b];
-								e[b] = e[b - 1];
-								e[b - 1] = tmp;
-							}
-						}
-					}
-#pragma unroll
-					for (int j = 0; j < EVK; j++)
-						if (j < (int)lc[k] && off + EV_FRONT < p.ev_cap)
-							p.evc[EV_FRONT + off++] = e[j];
-				}
-			}
-		}
-		__syncthreads();
-		if (tid == 0)
-			s_base += s_nev;
-		__syncthreads();
-	}
-	const unsigned int nev = s_base;
-	if (nev + EV_FRONT > p.ev_cap) // cannot happen with ev_cap = (tiles+1)*(EVK+3)+EV_FRONT
-		return;
-
-	if (tid == 0) bc->dbg[3] = gtimer();
-	// ---- 2. per event (one warp each): run end q, now at the event, speculated drop start
-	unsigned long long *evc = p.evc + EV_FRONT;
-	unsigned long long *ev_q = p.ev_q + EV_FRONT;
-	unsigned long long *ev_d = p.ev_d + EV_FRONT;
-	double *ev_now = p.ev_now + EV_FRONT;
-	for (unsigned int k = warp; k < nev; k += RTPB / 32) {
-		const unsigned long long w = evc[k];
-		const unsigned long long w1 = (k + 1 < nev) ? evc[k + 1] : 3ull, w2 = (k + 2 < nev) ? evc[k + 2] : 3ull;
-		const int c = (int)(w & 3ull);
-		const unsigned long long idx = w >> 2;
-		if (c == 0)
-			continue;
-		// the run ends right before the next class-0 event (at most two events ahead)
-		unsigned long long q = p.n - 1;
-		if ((w1 & 3ull) == 0)
-			q = (w1 >> 2) - 1;
-		else if ((w1 & 3ull) != 3ull && (w2 & 3ull) == 0)
-			q = (w2 >> 2) - 1;
-		const double nowk = now_at<NS>(p.now, idx);
-		unsigned long long d;
-		Pred pr;
-		pr.level = 0;
-		pr.x = __dadd_rn(nowk, CODEL_INTERVAL);
-		d = warp_search<NS>(p.now, s_idx, G, idx + 1, q + 1, pr, lane);
-		if (lane == 0) {
-			ev_now[k] = nowk;
-			ev_q[k] = q;
-			ev_d[k] = d;
-		}
-	}
-	__syncthreads();
-
-	if (tid == 0) bc->dbg[4] = gtimer();
-	// ---- hand-over to the commit kernel ---------------------------------------------------------
-	if (tid == 0) {
-		bc->nev_prep = nev;
-		// F after the batch's last claim when some tile fixes it inside the batch: the last tile with
-		// a CONST claim decides, later (all PASS) tiles inherit or, if it is 0, the first of them
-		// opens the run
-		const long long Tl = s_prevconst;
-		bc->anchored = (Tl >= 0) ? 1u : 0u;
-		double F = 0.0;
-		if (Tl >= 0) {
-			const unsigned long long code0 = p.rec_code[Tl];
-			if (code0 != CODE_ZERO)
-				F = __dadd_rn(now_at<NS>(p.now, code0 - 2), CODEL_INTERVAL);
-			else if ((unsigned long long)(Tl + 1) < p.tiles)
-				F = __dadd_rn(now_at<NS>(p.now, (unsigned long long)(Tl + 1) * TILE), CODEL_INTERVAL);
-		}
-		bc->F_anchor = F;
-		bc->now0p100 = __dadd_rn(now_at<NS>(p.now, 0), CODEL_INTERVAL);
-		bc->hasE_new = 0;
-		bc->trailing_marker = 0;
-		if (FLAGS) {
-			const unsigned long long lm = bc->last_marker_p1;
-			if (lm) {
-				bc->E_val = now_at<NS>(p.now, lm - 1); // lib/codel.js:92
-				bc->hasE_new = 1;
-				bc->trailing_marker = (lm == p.n) ? 1u : 0u;
-			}
-			bc->last_marker_p1 = 0;
-		}
-		bc->dbg[4] = gtimer();
-	}
+// Prepare and commit in ONE launch (512 threads): the state-independent half runs, then the same CTA
+// waits on the commit chain and finishes.  With the commits ordered on the device (chain word) a
+// kernel boundary between the two halves buys nothing, and it costs a launch on the host (the 1M-claim
+// step is launch-bound) and a launch latency on the device.  NOT yet validated on hardware: selected
+// only by CB_FUSED=1.
+template <bool NS, bool FLAGS, bool FCHAIN_T>
+__global__ void __launch_bounds__(RTPB, 1) resolve_fused_kernel(const ResolveParams p) {
+	prepare_part<NS, FLAGS>(p);
+	__syncthreads(); // prepare's global writes (events, control words) are visible to the whole CTA
+	commit_part<NS, FLAGS, FCHAIN_T>(p);
 }
-
-#define CB_COMMIT_NAME commit_kernel
-#define CB_COMMIT_FCHAIN 0
-#include "cb_commit_body.inc"
-#undef CB_COMMIT_NAME
-#undef CB_COMMIT_FCHAIN
-#define CB_COMMIT_NAME commit_fchain_kernel
-#define CB_COMMIT_FCHAIN 1
-#include "cb_commit_body.inc"
-#undef CB_COMMIT_NAME
-#undef CB_COMMIT_FCHAIN
 
 // one thread: seed the slot the first batch after a host-side state change reads
 __global__ void fchain_seed_kernel(const DevState *g, FSlot *f_in, unsigned long long seq, unsigned long long ring) {

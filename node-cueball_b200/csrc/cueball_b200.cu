@@ -122,6 +122,7 @@ struct cb_ctx {
 	size_t q_cap = 0, q_res_cap = 0, q_stage_cap = 0;
 	// F-chain variant of the commit kernel (CB_FCHAIN=1; not yet validated on hardware)
 	bool fchain = false, fseed = true;
+	bool fused = false; // CB_FUSED=1
 	int prio_least = 0, prio_greatest = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
@@ -422,8 +423,20 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s>>>(sp);
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s));
+	const bool fused = c->fused; // CB_FUSED=1: prepare + commit in one launch (not yet validated on hardware)
+	if (fused) {
+		if (use_f) {
+			if (flags)
+				resolve_fused_kernel<NS, true, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
+			else
+				resolve_fused_kernel<NS, false, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
+		} else if (flags)
+			resolve_fused_kernel<NS, true, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
+		else
+			resolve_fused_kernel<NS, false, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
+	}
 	// prepare: independent of the ControlledDelay state, so it overlaps the other lanes' commits
-	if (flags)
+	else if (flags)
 		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	else
 		prepare_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
@@ -431,7 +444,9 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	// commit(k) spins (one thread) on the chain word until batch k-1 has published its state, so
 	// the hand-over costs an L2 round trip instead of a cross-stream event (~5 us measured).
 	const size_t cidx_bytes = ((tiles + ((tiles + NIDX_MAX - 1) / NIDX_MAX) - 1) / ((tiles + NIDX_MAX - 1) / NIDX_MAX)) * sizeof(double);
-	if (use_f) {
+	if (fused) {
+		// the commit ran inside resolve_fused_kernel
+	} else if (use_f) {
 		if (flags)
 			commit_fchain_kernel<NS, true><<<1, CTPB, cidx_bytes, s>>>(rp);
 		else
@@ -449,7 +464,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	else
 		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
-	c->launches += 4;
+	c->launches += fused ? 3 : 4;
 	CU(c, cudaGetLastError());
 	if (out_done || (piped && flags && c->comm))
 		CU(c, cudaEventRecord(L.emit_done, s));
@@ -769,6 +784,20 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	}
+	if (getenv("CB_FUSED") && atoi(getenv("CB_FUSED")) != 0) {
+		c->fused = true;
+#define FUSED_ATTR(a, b, f)                                                                                 \
+	CU0(cudaFuncSetAttribute(resolve_fused_kernel<a, b, f>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8))
+		FUSED_ATTR(true, true, true);
+		FUSED_ATTR(true, true, false);
+		FUSED_ATTR(true, false, true);
+		FUSED_ATTR(true, false, false);
+		FUSED_ATTR(false, true, true);
+		FUSED_ATTR(false, true, false);
+		FUSED_ATTR(false, false, true);
+		FUSED_ATTR(false, false, false);
+#undef FUSED_ATTR
 	}
 	CU0(cudaMalloc((void **)&c->d_chain, sizeof(ChainMem)));
 	CU0(cudaMemset(c->d_chain, 0, sizeof(ChainMem)));

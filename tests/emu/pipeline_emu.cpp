@@ -32,16 +32,18 @@ struct EmuPipe {
 	ChainMem chain;
 	unsigned long long seq;
 	int fchain;  /* use commit_fchain_kernel (the F-chain variant) */
+	int fused;   /* prepare + commit in one launch (resolve_fused_kernel) */
 	int fseed;   /* the state was set from the host since the last batch */
 	EmuPipe *next; /* ring: the context whose mailbox this one writes (null: no ring) */
 	int ring_n, ring_rank;
 };
 
 extern "C" {
-EmuPipe *emu_pipe_create(double target, int fchain) {
+EmuPipe *emu_pipe_create(double target, int mode) { /* mode: bit 0 F-chain, bit 1 fused resolve */
 	EmuPipe *e = static_cast<EmuPipe *>(std::calloc(1, sizeof(EmuPipe)));
 	e->g.target = target;
-	e->fchain = fchain;
+	e->fchain = mode & 1;
+	e->fused = (mode >> 1) & 1;
 	e->fseed = 1;
 	return e;
 }
@@ -208,19 +210,33 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
 		/* the flags variant of the emit kernel chains tile admit counts through a look-back; with ONE
 		 * persistent CTA walking the tiles in order every look-back finds its predecessors done */
 		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, true>(sp); });
-		run_grid(1, RTPB, [&] { prepare_kernel<true, true>(rp); });
-		if (e->fchain)
-			run_grid(1, CTPB, [&] { commit_fchain_kernel<true, true>(rp); });
-		else
-			run_grid(1, CTPB, [&] { commit_kernel<true, true>(rp); });
+		if (e->fused) {
+			if (e->fchain)
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, true, true>(rp); });
+			else
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, true, false>(rp); });
+		} else {
+			run_grid(1, RTPB, [&] { prepare_kernel<true, true>(rp); });
+			if (e->fchain)
+				run_grid(1, CTPB, [&] { commit_fchain_kernel<true, true>(rp); });
+			else
+				run_grid(1, CTPB, [&] { commit_kernel<true, true>(rp); });
+		}
 		run_grid(1, ETPB, [&] { emit_kernel<true>(ep); });
 	} else {
 		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, false>(sp); });
-		run_grid(1, RTPB, [&] { prepare_kernel<true, false>(rp); });
-		if (e->fchain)
-			run_grid(1, CTPB, [&] { commit_fchain_kernel<true, false>(rp); });
-		else
-			run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+		if (e->fused) {
+			if (e->fchain)
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, false, true>(rp); });
+			else
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, false, false>(rp); });
+		} else {
+			run_grid(1, RTPB, [&] { prepare_kernel<true, false>(rp); });
+			if (e->fchain)
+				run_grid(1, CTPB, [&] { commit_fchain_kernel<true, false>(rp); });
+			else
+				run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+		}
 		const unsigned egrid = (unsigned)(etiles < 8 ? etiles : 8); /* persistent CTAs striding over the emit tiles */
 		run_grid(egrid, ETPB, [&] { emit_kernel<false>(ep); });
 	}

@@ -47,7 +47,7 @@ while (time.time() < t_end) if max_cases is None else (it < max_cases):
         state = {"count": int(rng.randint(0, 50)), "drop_next": t0 - float(rng.uniform(-50, 150)),
                  "first_above_time": float(rng.choice([0.0, t0 - float(rng.uniform(-50, 300))])),
                  "dropping": bool(rng.rand() < 0.5), "last_empty": None}
-    fchain = int(rng.rand() < 0.5)
+    fchain = int(rng.randint(0, 4))  # resolve-stage variant (mode bits of emu_pipe_create)
     if os.environ.get("CB_FUZZ_VERBOSE"):
         print("case", seed, dict(n=n, tgt=tgt, de=de, unit=unit, kw=kw, flags=flags is not None, cuts=cuts, fchain=fchain,
                                  state=state is not None), flush=True)

@@ -114,3 +114,36 @@ def test_fchain_one_queue_over_a_ring_of_contexts(cb, R):
     assert np.array_equal(dec.cpu().numpy(), od)
     assert np.array_equal(slot.cpu().numpy(), os_)
     assert st.cursor == ost.cursor and st.total_drops == ost.drops
+
+
+@pytest.mark.parametrize("fchain", ["0", "1"])
+def test_fused_resolve_kernel_streams_of_small_batches(monkeypatch, fchain):
+    """CB_FUSED=1: prepare and commit in one launch (3 launches per batch instead of 4)."""
+    import torch
+    monkeypatch.setenv("CB_FUSED", "1")
+    monkeypatch.setenv("CB_FCHAIN", fchain)
+    import cueball_b200 as cbm
+    n, m, tgt, nslots = 1_500_000, 46_875, 5, 61
+    start, now = tracegen.gen_trace(n, seed=377, de=1_000, unit=1 << 13)
+    flags = util.make_flags(n, 7, cancel_mod=6, empty_mod=30_011)
+    for fl in (None, flags):
+        ctx = cbm.Context(0)
+        ctx.codel_init(tgt)
+        ctx.backends_set(8, tracegen.gen_insert_draws(8), nslots)
+        dev = torch.device("cuda:0")
+        ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+        tf = torch.from_numpy(fl).to(dev) if fl is not None else None
+        dec = torch.empty(n, dtype=torch.uint8, device=dev)
+        slot = torch.empty(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count()
+        for lo in range(0, n, m):
+            ctx.admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo, tf.data_ptr() + lo if fl is not None else None,
+                                min(m, n - lo), dec.data_ptr() + lo, slot.data_ptr() + 4 * lo, None)
+        st = ctx.stats()
+        assert ctx.launch_count() - l0 <= 3 * ((n + m - 1) // m) + 1
+        cd = O.new_codel(tgt)
+        od, os_, ost = O.drain(cd, start, now, fl, nslots=nslots)
+        assert np.array_equal(dec.cpu().numpy(), od)
+        assert np.array_equal(slot.cpu().numpy(), os_)
+        assert st.cursor == ost.cursor and st.total_drops == ost.drops

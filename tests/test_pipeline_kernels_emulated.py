@@ -25,7 +25,8 @@ def load_emu():
     """Build (if stale) and load the emulated pipeline library."""
     csrc = os.path.join(util.ROOT, "node-cueball_b200", "csrc")
     srcs = [os.path.join(EMU, "pipeline_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h")] + \
-           [os.path.join(csrc, f) for f in ("cb_device.cuh", "cb_scan.cuh", "cb_resolve.cuh", "cb_emit.cuh")]
+           [os.path.join(csrc, f) for f in ("cb_device.cuh", "cb_scan.cuh", "cb_resolve.cuh", "cb_emit.cuh",
+                                            "cb_prepare_body.inc", "cb_commit_body.inc")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-rdynamic", "-fPIC", "-shared", "-pthread",
                                "-ffp-contract=off", "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
@@ -106,7 +107,11 @@ def check(L, start, now, cuts, target, nslots, state=None, expect_parallel=True,
     return od
 
 
-FCHAIN = pytest.mark.parametrize("fchain", [0, 1], ids=["commit", "commit_fchain"])
+# the resolve stage's variants: the validated kernels, the F-chain commit, prepare + commit fused into
+# one launch, and both together (mode bits of emu_pipe_create)
+_MODES = {0: "commit", 1: "commit_fchain", 2: "fused", 3: "fused_fchain"}
+_RUN = [0, 1, 2, 3] if FULL else [0, 3]  # default: what is validated and what round 2 should switch to
+FCHAIN = pytest.mark.parametrize("fchain", _RUN, ids=[_MODES[m] for m in _RUN])
 
 
 @FCHAIN
