@@ -184,6 +184,22 @@ def run_reference(args, wl):
             decided += n
     total = sum(times)
     value = decided / total
+    # context for the ratio: SpiderMonkey 1.7 is an interpreter from 2007; a JIT-compiling engine (V8 under
+    # Node.js, which is not installed here) would land between this number and the compiled C restatement
+    # of the same loop over the same linked-list queue, timed here on the same sample
+    port = None
+    try:
+        s, nw = tracegen.gen_trace(n, seed=tracegen.SEED, **{k: v for k, v in params.items()})
+        best = None
+        for _ in range(3):
+            cd = O.new_codel(TARGET_MS)
+            t0 = time.perf_counter()
+            O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        port = n / best
+    except Exception:
+        pass
     sample = ("%d claims per step of the %s trace spec (same generator, JS side); timed: the drain loop "
               "lib/pool.js:733-753 = Queue.shift + ControlledDelay.overloaded per claim" % (n, wl))
     line = {
@@ -195,7 +211,8 @@ def run_reference(args, wl):
                    "target_ms": TARGET_MS, "engine": ("reference lib/queue.js+lib/codel.js verbatim under SpiderMonkey 1.7 "
                                                       "(vendored in the reference tree; Node.js is not installed)"
                                                       if kind == "reference" else "C restatement (oracle/), linked-list queue")},
-        "cpu_baseline": {"value": value, "unit": "claims/s", "cores": 1, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "claims/s", "cores": 1, "kind": kind, "sample": sample,
+                         "c_restatement_linked_list_claims_per_s": port},
         "e2e": {"value": value, "unit": "claims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
