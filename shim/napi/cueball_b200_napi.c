@@ -1,14 +1,14 @@
 /*
  * shim/napi/cueball_b200_napi.c -- N-API addon over the C ABI of include/cueball_b200.h.
  *
- * NOT COMPILED IN THIS REPOSITORY'S ENVIRONMENT: there is no Node.js toolchain
+ * NOT BUILT IN THIS REPOSITORY'S ENVIRONMENT: there is no Node.js toolchain
  * (no `node`, no node_api.h).  It is the binding a maintainer would add
  * (see INTEGRATION.md); build with node-gyp against libcueball_b200.so:
  *
  *   { "targets": [{ "target_name": "cueball_b200", "sources": ["cueball_b200_napi.c"],
  *       "include_dirs": ["../../include"], "libraries": ["-lcueball_b200"] }] }
  *
- * JS surface (consumed by shim/js/*.js):
+ * JS surface (consumed by the modules under shim/js):
  *   create(device) -> ctx (external)                      destroy(ctx)
  *   codelInit(ctx, targetMs)                              new ControlledDelay(), lib/codel.js:24
  *   overloaded(ctx, startNs: BigInt, nowNs: BigInt) -> bool   lib/codel.js:56
