@@ -5,6 +5,7 @@ round end.  Nothing is measured."""
 import argparse
 import contextlib
 import json
+import os
 import sys
 import types
 
@@ -12,7 +13,9 @@ import numpy as np
 import pytest
 
 import util  # noqa: F401  (puts the repo root on sys.path)
-import bench
+
+bench = None  # imported by the `fakes` fixture: importing bench.py sets CUDA / NCCL environment defaults, which
+              # must not leak into a pytest process that goes on to run the GPU tests
 
 
 class FakeTensor(object):
@@ -119,6 +122,13 @@ class FakeContext(object):
 
 @pytest.fixture
 def fakes(monkeypatch):
+    global bench
+    for var in ("CUDA_DEVICE_MAX_CONNECTIONS", "NCCL_NTHREADS", "NCCL_MAX_CTAS"):
+        monkeypatch.setenv(var, os.environ.get(var, ""))  # restored (or removed again) after the test
+        if not os.environ[var]:
+            monkeypatch.delenv(var)
+    import bench as _bench
+    bench = _bench
     log = []
     ft, fdist = make_fake_torch(log)
     fcb = types.ModuleType("cueball_b200")
