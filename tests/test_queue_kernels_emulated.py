@@ -24,8 +24,8 @@ class QueueDev(C.Structure):
                 ("claim_timeout", C.c_uint64), ("n_res", C.c_uint64), ("err", C.c_uint32), ("pad", C.c_uint32)]
 
 
-@pytest.fixture(scope="module")
-def emu():
+def load_emu():
+    """Build (if stale) and load the emulated queue library."""
     srcs = [os.path.join(EMU, "queue_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h"),
             os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_queue.cuh"),
             os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_device.cuh")]
@@ -46,6 +46,11 @@ def emu():
     L.emu_queue_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.emu_queue_info.argtypes = [C.c_void_p, C.POINTER(QueueDev)]
     return L
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
 
 def run_emulated(L, target, nslots, ty, a, b, idle0, state=None, batch_pushes=False):
