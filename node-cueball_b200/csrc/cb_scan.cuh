@@ -37,6 +37,9 @@
 
 namespace cb {
 
+#ifndef CB_SCAN_MINBLOCKS // resident CTAs per SM the register budget is sized for (tuning knob:
+#define CB_SCAN_MINBLOCKS 4 // `make NVFLAGS+=-DCB_SCAN_MINBLOCKS=5`; 4 = 64 registers, measured in round 1)
+#endif
 constexpr int ROWS = 4;            // rows of 64 claims per warp chunk
 constexpr int CHUNK = ROWS * 64;   // 256 claims per warp
 static_assert(CHUNK * WARPS == TILE, "tile geometry");
@@ -167,7 +170,7 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 }
 
 template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(TPB, 4) scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const ScanParams p) {
 	using raw_t = typename Raw<NS>::t;
 	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
 	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
