@@ -38,7 +38,7 @@
 namespace cb {
 
 #ifndef CB_SCAN_MINBLOCKS // resident CTAs per SM the register budget is sized for (tuning knob:
-#define CB_SCAN_MINBLOCKS 4 // `make NVFLAGS+=-DCB_SCAN_MINBLOCKS=5`; 4 = 64 registers, measured in round 1)
+#define CB_SCAN_MINBLOCKS 4 // `make -B EXTRA=-DCB_SCAN_MINBLOCKS=5`; 4 = 64 registers, measured in round 1)
 #endif
 constexpr int ROWS = 4;            // rows of 64 claims per warp chunk
 constexpr int CHUNK = ROWS * 64;   // 256 claims per warp
