@@ -313,17 +313,19 @@ def run_cuda(args, wl, extra=True):
     # ---- device-resident timing ------------------------------------------------------------
     def timed_pass(per_step):
         """W untimed + K timed steps; returns (device ms of the K steps on this rank, host ms/step,
-        global cumulative [drops, admits, claims] or None)."""
+        global cumulative [drops, admits, claims] or None, kernels launched by the K steps)."""
         for b in range(W):
             step_dev(b, per_step)
         ctx.synchronize()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        lc0 = ctx.launch_count()
         th0 = time.perf_counter()
         for b in range(W, W + K):
             step_dev(b, per_step)
         hms = (time.perf_counter() - th0) * 1e3 / K  # host time to enqueue one step (no waiting)
+        nlaunch = ctx.launch_count() - lc0            # this library's kernels launched by the K timed steps
         ctx.join()  # the timing stream waits for the last batch of the pipeline
         glob = None
         if coll_mode == "window" and not per_step:
@@ -335,21 +337,19 @@ def run_cuda(args, wl, extra=True):
         e1.record(stream)
         barrier()
         ctx.synchronize()
-        return e0.elapsed_time(e1), hms, glob
+        return e0.elapsed_time(e1), hms, glob, nlaunch
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = ctx.launch_count()
-    ms, host_ms, glob = timed_pass(coll_mode == "step")
-    launches = ctx.launch_count() - l0 - 4 * W  # the K timed steps' kernels
+    ms, host_ms, glob, launches = timed_pass(coll_mode == "step")
     clocks = sampler.stop() if sampler else None
     st = ctx.stats()
     global_counts = [int(x) for x in glob.tolist()] if glob is not None else None
     per_step = None
     if coll_mode == "window" and extra:
         # second pass over the same batches with a collective after every batch (state carries on)
-        ms2, _, _ = timed_pass(True)
+        ms2, _, _, _ = timed_pass(True)
         t2 = torch.tensor([ms2], dtype=torch.float64, device=dev)
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         ms2 = float(t2.item())
