@@ -38,53 +38,8 @@ struct EmuPipe {
 	int ring_n, ring_rank;
 };
 
-extern "C" {
-EmuPipe *emu_pipe_create(double target, int mode) { /* mode: bit 0 F-chain, bit 1 fused resolve */
-	EmuPipe *e = static_cast<EmuPipe *>(std::calloc(1, sizeof(EmuPipe)));
-	e->g.target = target;
-	e->fchain = mode & 1;
-	e->fused = (mode >> 1) & 1;
-	e->fseed = 1;
-	return e;
-}
-void emu_pipe_destroy(EmuPipe *e) { std::free(e); }
-void emu_pipe_set_state(EmuPipe *e, double F, double D, unsigned long long C, int B, int hasE, double E,
-    unsigned long long cursor) {
-	e->g.F = F;
-	e->g.D = D;
-	e->g.C = C;
-	e->g.B = B;
-	e->g.hasE = hasE;
-	e->g.E = E;
-	e->g.cursor = cursor;
-	e->fseed = 1;
-}
-/* cb_ring_connect: this context drains segment (k, rank) of every step k and hands over to `next` */
-void emu_pipe_ring(EmuPipe *e, EmuPipe *next, int nranks, int rank) {
-	e->next = next;
-	e->ring_n = nranks;
-	e->ring_rank = rank;
-	e->seq = 0;
-	std::memset(&e->chain, 0, sizeof(e->chain));
-	e->chain.st = e->g;
-	e->fseed = 1;
-}
-void emu_pipe_get_state(EmuPipe *e, double *F, double *D, unsigned long long *C, int *B, int *hasE, double *E,
-    unsigned long long *cursor, unsigned long long *tot_drops, unsigned long long *tot_admits) {
-	*F = e->g.F;
-	*D = e->g.D;
-	*C = e->g.C;
-	*B = e->g.B;
-	*hasE = e->g.hasE;
-	*E = e->g.E;
-	*cursor = e->g.cursor;
-	*tot_drops = e->g.tot_drops;
-	*tot_admits = e->g.tot_admits;
-}
-
-/* one batch, nanosecond clocks, no flags; mirrors enqueue_batch() of csrc/cueball_b200.cu.
- * info[0] = path, [1] = events, [2] = intervals, [3] = drops */
-int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, const unsigned char *flags,
+template <bool NS>
+static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsigned char *flags,
     unsigned long long n, int nslots, unsigned char *decision, int *slot, unsigned long long *info) {
 	if (n == 0)
 		return 0;
@@ -209,33 +164,33 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
 	if (flags) {
 		/* the flags variant of the emit kernel chains tile admit counts through a look-back; with ONE
 		 * persistent CTA walking the tiles in order every look-back finds its predecessors done */
-		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, true>(sp); });
+		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<NS, true>(sp); });
 		if (e->fused) {
 			if (e->fchain)
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, true, true>(rp); });
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, true, true>(rp); });
 			else
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, true, false>(rp); });
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, true, false>(rp); });
 		} else {
-			run_grid(1, RTPB, [&] { prepare_kernel<true, true>(rp); });
+			run_grid(1, RTPB, [&] { prepare_kernel<NS, true>(rp); });
 			if (e->fchain)
-				run_grid(1, CTPB, [&] { commit_fchain_kernel<true, true>(rp); });
+				run_grid(1, CTPB, [&] { commit_fchain_kernel<NS, true>(rp); });
 			else
-				run_grid(1, CTPB, [&] { commit_kernel<true, true>(rp); });
+				run_grid(1, CTPB, [&] { commit_kernel<NS, true>(rp); });
 		}
 		run_grid(1, ETPB, [&] { emit_kernel<true>(ep); });
 	} else {
-		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<true, false>(sp); });
+		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<NS, false>(sp); });
 		if (e->fused) {
 			if (e->fchain)
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, false, true>(rp); });
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, false, true>(rp); });
 			else
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<true, false, false>(rp); });
+				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, false, false>(rp); });
 		} else {
-			run_grid(1, RTPB, [&] { prepare_kernel<true, false>(rp); });
+			run_grid(1, RTPB, [&] { prepare_kernel<NS, false>(rp); });
 			if (e->fchain)
-				run_grid(1, CTPB, [&] { commit_fchain_kernel<true, false>(rp); });
+				run_grid(1, CTPB, [&] { commit_fchain_kernel<NS, false>(rp); });
 			else
-				run_grid(1, CTPB, [&] { commit_kernel<true, false>(rp); });
+				run_grid(1, CTPB, [&] { commit_kernel<NS, false>(rp); });
 		}
 		const unsigned egrid = (unsigned)(etiles < 8 ? etiles : 8); /* persistent CTAs striding over the emit tiles */
 		run_grid(egrid, ETPB, [&] { emit_kernel<false>(ep); });
@@ -252,5 +207,62 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
 	for (void *p : fr)
 		std::free(p);
 	return 0;
+}
+
+
+extern "C" {
+EmuPipe *emu_pipe_create(double target, int mode) { /* mode: bit 0 F-chain, bit 1 fused resolve */
+	EmuPipe *e = static_cast<EmuPipe *>(std::calloc(1, sizeof(EmuPipe)));
+	e->g.target = target;
+	e->fchain = mode & 1;
+	e->fused = (mode >> 1) & 1;
+	e->fseed = 1;
+	return e;
+}
+void emu_pipe_destroy(EmuPipe *e) { std::free(e); }
+void emu_pipe_set_state(EmuPipe *e, double F, double D, unsigned long long C, int B, int hasE, double E,
+    unsigned long long cursor) {
+	e->g.F = F;
+	e->g.D = D;
+	e->g.C = C;
+	e->g.B = B;
+	e->g.hasE = hasE;
+	e->g.E = E;
+	e->g.cursor = cursor;
+	e->fseed = 1;
+}
+/* cb_ring_connect: this context drains segment (k, rank) of every step k and hands over to `next` */
+void emu_pipe_ring(EmuPipe *e, EmuPipe *next, int nranks, int rank) {
+	e->next = next;
+	e->ring_n = nranks;
+	e->ring_rank = rank;
+	e->seq = 0;
+	std::memset(&e->chain, 0, sizeof(e->chain));
+	e->chain.st = e->g;
+	e->fseed = 1;
+}
+void emu_pipe_get_state(EmuPipe *e, double *F, double *D, unsigned long long *C, int *B, int *hasE, double *E,
+    unsigned long long *cursor, unsigned long long *tot_drops, unsigned long long *tot_admits) {
+	*F = e->g.F;
+	*D = e->g.D;
+	*C = e->g.C;
+	*B = e->g.B;
+	*hasE = e->g.hasE;
+	*E = e->g.E;
+	*cursor = e->g.cursor;
+	*tot_drops = e->g.tot_drops;
+	*tot_admits = e->g.tot_admits;
+}
+
+/* one batch, nanosecond clocks, no flags; mirrors enqueue_batch() of csrc/cueball_b200.cu.
+ * info[0] = path, [1] = events, [2] = intervals, [3] = drops */
+int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, const unsigned char *flags,
+    unsigned long long n, int nslots, unsigned char *decision, int *slot, unsigned long long *info) {
+	return pipe_admit<true>(e, start, now, flags, n, nslots, decision, slot, info);
+}
+/* the _ms entry points: clocks already in double milliseconds */
+int emu_pipe_admit_ms(EmuPipe *e, const double *start, const double *now, const unsigned char *flags,
+    unsigned long long n, int nslots, unsigned char *decision, int *slot, unsigned long long *info) {
+	return pipe_admit<false>(e, start, now, flags, n, nslots, decision, slot, info);
 }
 }

@@ -39,6 +39,7 @@ def load_emu():
     L.emu_pipe_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 9
     L.emu_pipe_admit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
+    L.emu_pipe_admit_ms.argtypes = L.emu_pipe_admit.argtypes
     return L
 
 
@@ -83,8 +84,9 @@ def run_batches(L, start, now, cuts, target, nslots, state=None, unaligned=False
         sl = aligned(np.zeros(hi - lo, np.int32))
         info = (C.c_uint64 * 4)()
         f = np.ascontiguousarray(flags[lo:hi]) if flags is not None else None
-        L.emu_pipe_admit(p, s.ctypes.data, w.ctypes.data, f.ctypes.data if f is not None else None, hi - lo, nslots,
-                         d.ctypes.data, sl.ctypes.data, info)
+        admit = L.emu_pipe_admit_ms if start.dtype == np.float64 else L.emu_pipe_admit
+        admit(p, s.ctypes.data, w.ctypes.data, f.ctypes.data if f is not None else None, hi - lo, nslots,
+              d.ctypes.data, sl.ctypes.data, info)
         dec[lo:hi] = d
         slot[lo:hi] = sl
         paths.append(int(info[0]))
@@ -155,6 +157,25 @@ def test_waiting_flags_and_empty_markers(emu, fchain):
     flags[cuts[4] - 1] |= 2
     od = check(emu, start, now, cuts, 5, 23, fchain=fchain, flags=flags)
     assert (od == 2).sum() > 1_000 and (od == 1).sum() > 100
+
+
+@FCHAIN
+def test_millisecond_clock_entry_points(emu, fchain):
+    """The _ms variants of the kernels (clocks already in double milliseconds, as the reference holds
+    them): same decisions as the ns variants on the converted trace."""
+    n = 8_200
+    start, now = tracegen.gen_trace(n, seed=71, de=50_000, unit=1 << 10, all_overloaded_from=3_000)
+    to_ms = np.vectorize(O.ns_to_ms, otypes=[np.float64])
+    sm, nm = to_ms(start), to_ms(now)
+    flags = util.make_flags(n, 71, cancel_mod=7, empty_mod=2_003)
+    for fl in (None, flags):
+        cd = O.new_codel(5)
+        od, os_, ost = O.drain(cd, sm, nm, fl, nslots=41)
+        dec, slot, (st, cursor, td, ta), paths = run_batches(emu, sm, nm, [0, 2_048, 5_000, n], 5, 41, fchain=fchain, flags=fl)
+        assert paths == [0, 0, 0]
+        assert np.array_equal(dec, od) and np.array_equal(slot, os_)
+        util.assert_state_equal(st, cd.as_dict())
+        assert (cursor, td) == (ost.cursor, ost.drops)
 
 
 @FCHAIN
