@@ -11,7 +11,11 @@
 
 namespace cb {
 
+#ifdef CB_TOPO_TPB // the host emulation of tests/emu runs the same code with a narrower CTA
+constexpr int TOPO_TPB = CB_TOPO_TPB;
+#else
 constexpr int TOPO_TPB = 1024;
+#endif
 
 // insert `key` at index idx of keys[0..len): parallel shift-right by one, whole CTA
 __device__ void cta_insert(int32_t *keys, int len, int idx, int32_t key) {

@@ -156,6 +156,12 @@ inline int atomicMax(int *p, int v) {
 	}
 	return old;
 }
+inline int atomicMin(int *p, int v) {
+	int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+	while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+	}
+	return old;
+}
 inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
 	unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
 	while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {

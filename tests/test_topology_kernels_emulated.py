@@ -1,0 +1,115 @@
+"""The topology kernels (csrc/cb_topology.cuh: preference list insert / remove / reshuffle,
+planRebalance, slot table) compiled for the HOST under tests/emu and checked against the reference's
+own planRebalance known-answer tests (tests/golden/plan_rebalance_kat.json, recorded from
+test/utils.test.js under the reference engine), the randomized reference plans, and the oracle's
+preference-list operations."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from cueball_b200 import tracegen
+from oracle import oracle as O
+
+EMU = os.path.join(util.ROOT, "tests", "emu")
+SO = os.path.join(EMU, "libtopology_emu.so")
+PLAN = util.load_golden("plan_rebalance_kat.json")
+VP = C.c_void_p
+
+
+def load_emu():
+    srcs = [os.path.join(EMU, "topology_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h"),
+            os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_topology.cuh"),
+            os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_device.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-rdynamic", "-fPIC", "-shared", "-pthread",
+                               "-ffp-contract=off", "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
+    L = C.CDLL(SO)
+    L.emu_pref_build.argtypes = [VP, C.c_int, VP]
+    L.emu_pref_insert.argtypes = [VP, VP, C.c_int32, C.c_double]
+    L.emu_pref_remove.argtypes = [VP, VP, C.c_int32]
+    L.emu_pref_remove.restype = C.c_int
+    L.emu_pref_reshuffle.argtypes = [VP, VP, C.c_double]
+    L.emu_plan_rebalance.argtypes = [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP, VP]
+    L.emu_slot_table.argtypes = [VP, VP, VP, VP, C.c_int, VP]
+    return L
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
+
+
+def plan_emulated(L, c):
+    names = [k for k, _ in c["conns"]]
+    have = np.array([len(v) for _, v in c["conns"]], np.int32)
+    dead = np.array([1 if k in c["dead"] else 0 for k in names], np.uint8)
+    B = len(names)
+    want = np.zeros(max(B, 1), np.int32)
+    add = np.zeros(max(int(c["max"]), int(have.sum()), 1) + 1, np.int32)
+    rk = np.zeros(max(int(have.sum()), 1), np.int32)
+    ro = np.zeros(max(int(have.sum()), 1), np.int32)
+    na, nr = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    L.emu_plan_rebalance(have.ctypes.data, dead.ctypes.data, B, int(c["target"]), int(c["max"]), int(bool(c["singleton"])),
+                         want.ctypes.data, add.ctypes.data, na.ctypes.data, rk.ctypes.data, ro.ctypes.data, nr.ctypes.data)
+    conns = dict((k, v) for k, v in c["conns"])
+    return ([names[i] for i in add[:na[0]]], [conns[names[k]][o] for k, o in zip(rk[:nr[0]], ro[:nr[0]])])
+
+
+@pytest.mark.parametrize("c", PLAN["kat"], ids=[c["test"] for c in PLAN["kat"]])
+def test_plan_rebalance_kernel_on_the_reference_kats(emu, c):  # test/utils.test.js:13-285
+    add, rem = plan_emulated(emu, c)
+    assert add == c["add"] and rem == c["remove"]
+
+
+def test_plan_rebalance_kernel_on_random_reference_plans(emu):
+    for c in PLAN["random"][::5]:
+        add, rem = plan_emulated(emu, c)
+        assert add == c["add"] and rem == c["remove"], c
+
+
+def test_preference_list_and_slot_table_kernels(emu):
+    B, S = 150, 420  # several 64-thread chunks per shift
+    us = np.ascontiguousarray(tracegen.gen_insert_draws(B, 7), np.float64)
+    keys = np.zeros(B + 8, np.int32)
+    emu.emu_pref_build(keys.ctypes.data, B, us.ctypes.data)
+    okeys, oslots = O.build_slots(B, S, us)
+    assert keys[:B].tolist() == okeys.tolist()
+    # slot table from the oracle's plan.add (planRebalance({}, {}, S, S) over the preference list)
+    have = np.zeros(B, np.int32)
+    dead = np.zeros(B, np.uint8)
+    want = np.zeros(B, np.int32)
+    add = np.zeros(S + 1, np.int32)
+    na, nr = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    rk, ro = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    emu.emu_plan_rebalance(have.ctypes.data, dead.ctypes.data, B, S, S, 0, want.ctypes.data, add.ctypes.data,
+                           na.ctypes.data, rk.ctypes.data, ro.ctypes.data, nr.ctypes.data)
+    table = np.full(S + 12, -5, np.int32)
+    ns = np.zeros(1, np.int32)
+    emu.emu_slot_table(keys.ctypes.data, add.ctypes.data, na.ctypes.data, table.ctypes.data, S + 12, ns.ctypes.data)
+    assert ns[0] == S and table[:S].tolist() == oslots.tolist() and (table[S:] == -1).all()
+    # single events: removed (present and absent), added, reshuffle -- against a Python list
+    ref = keys[:B].tolist()
+    n = np.array([B], np.int32)
+    rng = np.random.RandomState(3)
+    for step in range(30):
+        r = rng.rand()
+        if r < 0.4 and len(ref) > 1:
+            k = int(rng.choice(ref))
+            assert emu.emu_pref_remove(keys.ctypes.data, n.ctypes.data, k) == 0
+            ref.remove(k)
+        elif r < 0.5:
+            assert emu.emu_pref_remove(keys.ctypes.data, n.ctypes.data, 10_000 + step) == -1
+        elif r < 0.8 and len(ref) < B:
+            k, u = 20_000 + step, float(rng.rand())
+            emu.emu_pref_insert(keys.ctypes.data, n.ctypes.data, k, u)
+            ref.insert(int(np.floor(u * (len(ref) + 1))), k)            # lib/pool.js:287-288
+        else:
+            u = float(rng.rand())
+            emu.emu_pref_reshuffle(keys.ctypes.data, n.ctypes.data, u)  # lib/pool.js:501-519
+            taken = ref.pop()
+            ref.insert(int(np.floor(u * (len(ref) + 1))), taken)
+        assert n[0] == len(ref) and keys[:n[0]].tolist() == ref
