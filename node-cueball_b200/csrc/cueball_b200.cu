@@ -80,6 +80,13 @@ struct Lane {
 	cudaEvent_t res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
 	bool used = false, coll_pending = false;
 	unsigned long long epoch = 0;
+	// CB_GRAPH=1 (not yet validated on hardware): the batch's kernels as one CUDA graph per
+	// (clock type, flags) variant, its node parameters rewritten per batch: one launch call per batch
+	struct Graph {
+		cudaGraph_t g = nullptr;
+		cudaGraphExec_t ex = nullptr;
+		cudaGraphNode_t n_scan = nullptr, n_res = nullptr, n_commit = nullptr, n_emit = nullptr;
+	} gr[2][2];
 };
 
 struct Staging {
@@ -123,6 +130,7 @@ struct cb_ctx {
 	// F-chain variant of the commit kernel (CB_FCHAIN=1; not yet validated on hardware)
 	bool fchain = false, fseed = true;
 	bool fused = false; // CB_FUSED=1
+	bool graph = false; // CB_GRAPH=1
 	int prio_least = 0, prio_greatest = 0;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
@@ -239,6 +247,73 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 	// the emit kernel's sum descriptors carry an epoch tag, so they only need zeroing once
 	CU(c, cudaMemset(L.sdesc, 0, cap * sizeof(SumDesc)));
 	L.cap_tiles = cap;
+	return CB_OK;
+}
+
+// CB_GRAPH=1: scan -> (prepare -> commit | fused resolve) -> emit as the nodes of one CUDA graph per lane and
+// variant.  The first batch of a variant builds and instantiates it; every later one rewrites the nodes'
+// parameters (pointers, sizes, grids) in the instantiated graph and launches it: one launch call per batch
+// instead of three or four.  The scan node keeps the lowest priority, the others the highest.
+template <bool NS>
+int graph_batch(cb_ctx *c, Lane &L, bool flags, bool use_f, bool fused, ScanParams &sp, ResolveParams &rp,
+    EmitParams &ep, size_t tiles, unsigned egrid, size_t cidx_bytes, cudaStream_t s) {
+	Lane::Graph &G = L.gr[NS ? 1 : 0][flags ? 1 : 0];
+	void *a_scan[] = {(void *)&sp}, *a_res[] = {(void *)&rp}, *a_emit[] = {(void *)&ep};
+	cudaKernelNodeParams k_scan = {}, k_res = {}, k_commit = {}, k_emit = {};
+	k_scan.func = flags ? (void *)scan_kernel<NS, true> : (void *)scan_kernel<NS, false>;
+	k_scan.gridDim = dim3((unsigned)tiles);
+	k_scan.blockDim = dim3(TPB);
+	k_scan.kernelParams = a_scan;
+	if (fused) {
+		k_res.func = use_f ? (flags ? (void *)resolve_fused_kernel<NS, true, true> : (void *)resolve_fused_kernel<NS, false, true>)
+		                   : (flags ? (void *)resolve_fused_kernel<NS, true, false> : (void *)resolve_fused_kernel<NS, false, false>);
+	} else {
+		k_res.func = flags ? (void *)prepare_kernel<NS, true> : (void *)prepare_kernel<NS, false>;
+		k_commit.func = use_f ? (flags ? (void *)commit_fchain_kernel<NS, true> : (void *)commit_fchain_kernel<NS, false>)
+		                      : (flags ? (void *)commit_kernel<NS, true> : (void *)commit_kernel<NS, false>);
+		k_commit.gridDim = dim3(1);
+		k_commit.blockDim = dim3(CTPB);
+		k_commit.sharedMemBytes = (unsigned)cidx_bytes;
+		k_commit.kernelParams = a_res;
+	}
+	k_res.gridDim = dim3(1);
+	k_res.blockDim = dim3(RTPB);
+	k_res.sharedMemBytes = (unsigned)(NIDX_MAX * sizeof(double));
+	k_res.kernelParams = a_res;
+	k_emit.func = flags ? (void *)emit_kernel<true> : (void *)emit_kernel<false>;
+	k_emit.gridDim = dim3(egrid);
+	k_emit.blockDim = dim3(ETPB);
+	k_emit.sharedMemBytes = (unsigned)ep.table_smem_bytes;
+	k_emit.kernelParams = a_emit;
+	if (!G.ex) {
+		CU(c, cudaGraphCreate(&G.g, 0));
+		CU(c, cudaGraphAddKernelNode(&G.n_scan, G.g, nullptr, 0, &k_scan));
+		CU(c, cudaGraphAddKernelNode(&G.n_res, G.g, &G.n_scan, 1, &k_res));
+		cudaGraphNode_t last = G.n_res;
+		if (!fused) {
+			CU(c, cudaGraphAddKernelNode(&G.n_commit, G.g, &G.n_res, 1, &k_commit));
+			last = G.n_commit;
+		}
+		CU(c, cudaGraphAddKernelNode(&G.n_emit, G.g, &last, 1, &k_emit));
+		cudaKernelNodeAttrValue lo, hi;
+		memset(&lo, 0, sizeof(lo));
+		memset(&hi, 0, sizeof(hi));
+		lo.priority = c->prio_least;
+		hi.priority = c->prio_greatest;
+		CU(c, cudaGraphKernelNodeSetAttribute(G.n_scan, cudaKernelNodeAttributePriority, &lo));
+		CU(c, cudaGraphKernelNodeSetAttribute(G.n_res, cudaKernelNodeAttributePriority, &hi));
+		if (G.n_commit)
+			CU(c, cudaGraphKernelNodeSetAttribute(G.n_commit, cudaKernelNodeAttributePriority, &hi));
+		CU(c, cudaGraphKernelNodeSetAttribute(G.n_emit, cudaKernelNodeAttributePriority, &hi));
+		CU(c, cudaGraphInstantiate(&G.ex, G.g, 0));
+	} else {
+		CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_scan, &k_scan));
+		CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_res, &k_res));
+		if (G.n_commit)
+			CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_commit, &k_commit));
+		CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_emit, &k_emit));
+	}
+	CU(c, cudaGraphLaunch(G.ex, s));
 	return CB_OK;
 }
 
@@ -401,6 +476,27 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	}
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[0], s));
+	if (piped && c->graph) {
+		const size_t stride0 = (tiles + NIDX_MAX - 1) / NIDX_MAX;
+		rc = graph_batch<NS>(c, L, flags, use_f, c->fused, sp, rp, ep, tiles, egrid, ((tiles + stride0 - 1) / stride0) * sizeof(double), s);
+		if (rc)
+			return rc;
+		c->chain_seq++;
+		if (c->comm) // the graph has no interior point to record: the collective starts after the emit
+			CU(c, cudaEventRecord(L.res_done, s));
+		c->launches += c->fused ? 3 : 4;
+		CU(c, cudaGetLastError());
+		if (out_done || (flags && c->comm))
+			CU(c, cudaEventRecord(L.emit_done, s));
+		L.used = true;
+		L.coll_pending = false;
+		c->last_lane = li;
+		c->last_flags = flags;
+		c->seq++;
+		if (out_done)
+			*out_done = L.emit_done;
+		return CB_OK;
+	}
 	if (piped) {
 		// the lane's stream has the highest priority (prepare / commit / emit take the first CTA slot
 		// that frees up); the scan, which fills every SM, is launched into it at the lowest
@@ -785,6 +881,7 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	}
+	c->graph = getenv("CB_GRAPH") && atoi(getenv("CB_GRAPH")) != 0;
 	if (getenv("CB_FUSED") && atoi(getenv("CB_FUSED")) != 0) {
 		c->fused = true;
 #define FUSED_ATTR(a, b, f)                                                                                 \
@@ -848,6 +945,13 @@ extern "C" void cb_destroy(cb_ctx *c) {
 			cudaStreamSynchronize(L.st);
 			cudaStreamDestroy(L.st);
 		}
+		for (int a = 0; a < 2; a++)
+			for (int b = 0; b < 2; b++) {
+				if (L.gr[a][b].ex)
+					cudaGraphExecDestroy(L.gr[a][b].ex);
+				if (L.gr[a][b].g)
+					cudaGraphDestroy(L.gr[a][b].g);
+			}
 		void *fr[] = {L.idx_ms, L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
 		    L.ev_q, L.ev_d, L.rec_code, L.xev, L.hj_lo, L.hj_b, L.tile_now0, L.iv_lo, L.iv_hi, L.iv_cum, L.ev_now, L.hj_F};
 		for (void *p : fr)

@@ -147,3 +147,38 @@ def test_fused_resolve_kernel_streams_of_small_batches(monkeypatch, fchain):
         assert np.array_equal(dec.cpu().numpy(), od)
         assert np.array_equal(slot.cpu().numpy(), os_)
         assert st.cursor == ost.cursor and st.total_drops == ost.drops
+
+
+@pytest.mark.parametrize("combo", ["", "fused", "fused+fchain"])
+def test_cuda_graph_launch_path(monkeypatch, combo):
+    """CB_GRAPH=1: a batch's kernels are one CUDA graph per lane and variant whose node parameters are
+    rewritten per batch (one launch call per batch); batches of different sizes, with and without flags."""
+    import torch
+    monkeypatch.setenv("CB_GRAPH", "1")
+    monkeypatch.setenv("CB_FUSED", "1" if "fused" in combo else "0")
+    monkeypatch.setenv("CB_FCHAIN", "1" if "fchain" in combo else "0")
+    import cueball_b200 as cbm
+    n, tgt, nslots = 1_600_000, 5, 61
+    start, now = tracegen.gen_trace(n, seed=477, de=1_000, unit=1 << 13)
+    flags = util.make_flags(n, 9, cancel_mod=6, empty_mod=30_011)
+    rng = np.random.RandomState(1)
+    cuts = sorted(set([0, n] + [int(x) for x in rng.randint(1, n, size=40)]))
+    for fl in (None, flags):
+        ctx = cbm.Context(0)
+        ctx.codel_init(tgt)
+        ctx.backends_set(8, tracegen.gen_insert_draws(8), nslots)
+        dev = torch.device("cuda:0")
+        ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+        tf = torch.from_numpy(fl).to(dev) if fl is not None else None
+        dec = torch.empty(n, dtype=torch.uint8, device=dev)
+        slot = torch.empty(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            ctx.admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo, tf.data_ptr() + lo if fl is not None else None,
+                                hi - lo, dec.data_ptr() + lo, slot.data_ptr() + 4 * lo, None)
+        st = ctx.stats()
+        cd = O.new_codel(tgt)
+        od, os_, ost = O.drain(cd, start, now, fl, nslots=nslots)
+        assert np.array_equal(dec.cpu().numpy(), od)
+        assert np.array_equal(slot.cpu().numpy(), os_)
+        assert st.cursor == ost.cursor and st.total_drops == ost.drops

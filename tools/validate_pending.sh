@@ -17,7 +17,9 @@ run queue_and_fchain   env CB_TEST_UNVALIDATED=1 timeout 900 python -m pytest te
 run suite_fchain       env CB_FCHAIN=1 timeout 600 python -m pytest tests -x -q -m gpu
 run suite_fused        env CB_FUSED=1 timeout 600 python -m pytest tests -x -q -m gpu
 run suite_fused_fchain env CB_FUSED=1 CB_FCHAIN=1 timeout 600 python -m pytest tests -x -q -m gpu
-for v in "" "CB_FCHAIN=1" "CB_FUSED=1" "CB_FUSED=1 CB_FCHAIN=1"; do
+run suite_graph        env CB_GRAPH=1 timeout 600 python -m pytest tests -x -q -m gpu
+run suite_graph_all    env CB_GRAPH=1 CB_FUSED=1 CB_FCHAIN=1 timeout 600 python -m pytest tests -x -q -m gpu
+for v in "" "CB_FCHAIN=1" "CB_FUSED=1" "CB_FUSED=1 CB_FCHAIN=1" "CB_GRAPH=1" "CB_GRAPH=1 CB_FUSED=1 CB_FCHAIN=1"; do
 	for w in c2 c3; do
 		env $v python bench.py --workload $w --no-extra 2>/dev/null | python -c "
 import json,sys
