@@ -1,8 +1,11 @@
-"""GPU parity tests of the F-chain variant of the commit kernel (CB_FCHAIN=1: first_above_time is
-handed from batch to batch ahead of the rest of the ControlledDelay state, so the inherited stretch
-is resolved before the state arrives).  The variant passes the CPU emulation
-(tests/test_pipeline_kernels_emulated.py) but has NOT run on hardware yet, so these tests are skipped
-unless CB_TEST_UNVALIDATED=1; the default library path does not use the kernel."""
+"""GPU parity tests of the launch-path variants written after round 1's GPU budget ran out:
+  CB_FCHAIN=1  F-chain variant of the commit kernel (first_above_time handed from batch to batch ahead
+               of the rest of the ControlledDelay state; through the mailboxes in a ring)
+  CB_FUSED=1   prepare + commit in one launch (resolve_fused_kernel)
+  CB_GRAPH=1   the batch's kernels as one CUDA graph per lane, node parameters rewritten per batch
+The kernels pass the CPU emulation (tests/test_pipeline_kernels_emulated.py) but have NOT run on
+hardware yet, so these tests are skipped unless CB_TEST_UNVALIDATED=1; the default library path uses
+none of the three."""
 import os
 
 import numpy as np
@@ -14,7 +17,7 @@ from oracle import oracle as O
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("CB_TEST_UNVALIDATED") != "1",
-                                 reason="commit_fchain_kernel not yet validated on hardware (set CB_TEST_UNVALIDATED=1)")]
+                                 reason="launch-path variants not yet validated on hardware (set CB_TEST_UNVALIDATED=1)")]
 
 
 @pytest.fixture()
