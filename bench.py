@@ -1,35 +1,45 @@
 #!/usr/bin/env python3
 """bench.py -- claim-queue admissions/sec (CoDel + backend-slot pick) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference] [--no-extra]
 
-A "step" is one pass of the hot path (scan -> resolve -> emit kernels behind
-cb_admit_batch_dev) over one batch of synthetic pending claims.  Workloads are the
-BASELINE.json configs:
+A "step" is one pass of the hot path (scan -> resolve -> emit kernels behind cb_admit_batch_dev)
+over one batch of synthetic pending claims.  Workloads are the BASELINE.json configs
+(SURVEY.md 8(d)); sizes are PER GPU and the same at every N (weak scaling):
 
-    c2  2^20 claims / step,   64 backends,  256 slots     (configs[1]; default at N=1)
-    c3  2^24 claims / step, 1024 backends, 4096 slots     (configs[2])
-    c4  2^23 claims / step / GPU, 4096 backends           (configs[3]: 64M over 8 GPUs)
-    c5  2^24 claims / step / GPU, sustained overload       (configs[4]: streamed chunks)
+    c3  2^24 claims / step, 1024 backends, 4096 slots    (configs[2]: the largest single-GPU config;
+                                                          the default at every N)
+    c2  2^20 claims / step,   64 backends,  256 slots    (configs[1]; extra key `c2` at N=1)
+    c4  2^23 claims / step / GPU, 4096 backends          (configs[3]: 64M over 8 GPUs; extra key at N>1)
+    c5  2^24 claims / step / GPU, sustained overload     (configs[4]; extra key at N>1)
 
-The (W+K) batches of a run are consecutive segments of ONE seeded trace, all resident in HBM
-before the timed region, so every step reads cold data (the run's inputs are many times the
-126 MB L2) and the ControlledDelay state chains from batch to batch on the device.
+The (W+K) batches of a run are consecutive segments of ONE seeded trace, generated on the device
+before the timed region (same generator as cueball_b200/tracegen.py, checked bit for bit in
+tests/), so every step reads cold data (the run's inputs are many times the 126 MB L2) and the
+ControlledDelay state chains from batch to batch on the device.
 
-Metric value = claims decided per second, whole job (all ranks), inputs resident in HBM.
-N > 1: one process per GPU, each rank drains its own queue segment (no data-path collective);
-the global drop count is ONE NCCL allreduce of the ranks' cumulative counts at the end of the
-timed window (`config.collective`); `per_step_collective` is a second pass with an allreduce
-after every batch (CB_BENCH_COLLECTIVE=window|step|none picks the main pass's mode).
-`e2e` = the same through the host-buffer C entry point (pinned host arrays in, decisions and
-slots back on the host every step).  `roofline` is for the dominant kernel (the scan kernel:
-16 algorithmic bytes per claim) from CUDA events recorded around each kernel on
-the launching stream in a separate profiling pass.  `cpu_baseline` is the C restatement of the
-reference path (oracle/, pinned bit-for-bit to the reference's own JS) on one host core.
+`value` = claims decided per second, whole job (all ranks), inputs resident in HBM, CUDA events on
+the launching stream, max over ranks.  Nothing in the timed region touches the host: no stats read,
+no torch collective.  N > 1: one process per GPU, each rank drains its own queue segment (no
+data-path collective); the GLOBAL drop/admit counts exist after every batch, device-side, through
+the peer-memory boards of cb_peers_* (a tiny kernel behind each batch's emit stores the counts into
+every rank's board over NVLink).  The north star's literal "single NCCL allreduce" is timed
+separately (`nccl_allreduce`).  `one_queue` is the other multi-GPU mode: ONE logical queue whose
+ControlledDelay state goes round a ring of device mailboxes, checked bit for bit against one
+sequential drain on a window.
+`parity` = the timed outputs against the C oracle in the same run: every decision and slot of the
+W+K steps, the drop/admit totals and the final ControlledDelay state (bit patterns).
+`e2e` = the same metric through the host-buffer C entry point (pinned host arrays in, decisions and
+slots back on the host every step), with the measured PCIe copy rates next to it.
+`roofline` is for the dominant kernel (the scan kernel: 16 algorithmic bytes per claim)
+from CUDA events recorded around each kernel on the launching stream in a separate profiling pass.
+`cpu_baseline` is the C restatement of the reference path (oracle/, pinned bit-for-bit to the
+reference's own JS) on one host core, on the full step size.
 
---impl reference times the reference's OWN JavaScript (lib/queue.js + lib/codel.js verbatim)
-under the SpiderMonkey engine vendored in the reference tree (oracle/_ref), one core -- the
-path is a sequential state machine and Node itself is single threaded.
+--impl reference times the reference's OWN JavaScript (lib/queue.js + lib/codel.js verbatim) under
+the SpiderMonkey engine vendored in the reference tree (oracle/_ref), one core -- the path is a
+sequential state machine and Node itself is single threaded -- on a bounded sample of the same
+workload (`config.reference_sample_claims_per_step`, the same key in both arms).
 """
 import argparse
 import json
@@ -42,8 +52,8 @@ import time
 # more hardware work queues than the default 8, so that the pipeline's streams do not share one
 # (must be set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# the per-step collective is a 24-byte sum: one small CTA (see cb_comm_init); NCCL reads these once
-# per process, so they are set before torch initialises it
+# the NCCL collective of the `nccl_allreduce` leg is a 24-byte sum: one small CTA (see cb_comm_init);
+# NCCL reads these once per process, so they are set before torch initialises it
 if os.environ.get("CB_BENCH_NCCL_DEFAULTS") is None:
     os.environ.setdefault("NCCL_NTHREADS", "128")
     os.environ.setdefault("NCCL_MAX_CTAS", "1")
@@ -62,16 +72,16 @@ WORKLOADS = {
     "c2": dict(n=1 << 20, B=64, S=256, gen={"unit": 1 << 19}),
     "c3": dict(n=1 << 24, B=1024, S=4096, gen={"unit": 1 << 19}),
     "c4": dict(n=1 << 23, B=4096, S=16384, gen={"unit": 1 << 19}),
-    "c5": dict(n=1 << 24, B=4096, S=16384, gen={"all_overloaded_from": 1 << 20}),
+    "c5": dict(n=1 << 24, B=4096, S=16384, gen={"unit": 1 << 19, "all_overloaded_from": 1 << 20}),
 }
 TARGET_MS = 5
+T0_NS, DE_NS = 10 ** 9, 1000
 ALG_BYTES_SCAN = 16      # start_ns 8 + now_ns 8 (read once by the scan kernel)
 ALG_BYTES_STEP = 21      # + decision 1 + slot 4
-REF_SAMPLE = 1 << 18     # claims per step for --impl reference (bounded CPU sample)
-
-
-def env_int(name, default):
-    return int(os.environ.get(name, default))
+REF_SAMPLE = {"c2": 1 << 20, "c3": 1 << 19, "c4": 1 << 19, "c5": 1 << 19}  # claims per step of the JS reference arm
+REF_QUEUE = 1 << 18      # the vendored engine's 64 MB heap holds one queue of 2^18 pending claims: a step's sample is
+                         # drained as consecutive queues of this depth
+METRIC = "claim-queue admissions/sec (CoDel + backend-slot pick)"
 
 
 def peaks():
@@ -80,6 +90,15 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(wl, world):
+    """The part of `config` that names the workload: identical in the CUDA arm and the reference arm."""
+    w = WORKLOADS[wl]
+    return {"workload": wl, "claims_per_step_per_gpu": w["n"], "backends": w["B"], "slots": w["S"],
+            "target_ms": TARGET_MS, "interval_ms": 100,
+            "parallelism": "queue segment per GPU" if world > 1 else "1 GPU",
+            "reference_sample_claims_per_step": REF_SAMPLE[wl]}
 
 
 def bind_to_gpu_numa(index):
@@ -115,8 +134,9 @@ class ClockSampler(object):
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(0.25)  # the sampler is up before the timed region starts
         except OSError:
             self.p = None
 
@@ -151,10 +171,59 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
-def make_trace(wl, total_claims, rank):
+# ------------------------------------------------------------------------------ trace on the device
+def gen_trace_torch(lo, hi, seed, dev, unit, all_overloaded_from=-1, start_overloaded=False, piece=1 << 24):
+    """Claims [lo, hi) of the trace tracegen.gen_trace(hi, seed=seed, t0=T0_NS, de=DE_NS, ...) would
+    produce, as int64 CUDA tensors, without generating the claims before `lo`: now_i is a running
+    maximum of start_j + soj_j, and since start advances DE_NS per claim while soj <= 61 * target,
+    only the last 61*target/DE_NS claims can hold the maximum.  (tests/test_bench_dryrun.py compares
+    this with the numpy generator bit for bit, on the CPU.)"""
+    import torch
+    target_ns = TARGET_MS * 1_000_000
+    healthy_span, over_span = (target_ns * 9) // 10, target_ns * 60
+    back = (target_ns + over_span) // DE_NS + 2
+    a = max(0, lo - back)
+    ph = tracegen.phases(seed, hi, unit, start_overloaded, all_overloaded_from)
+    M32 = 0xFFFFFFFF
+    start_out = torch.empty(hi - lo, dtype=torch.int64, device=dev)
+    now_out = torch.empty(hi - lo, dtype=torch.int64, device=dev)
+    carry = None
+    for p0 in range(a, hi, piece):
+        p1 = min(hi, p0 + piece)
+        idx = torch.arange(p0, p1, dtype=torch.int64, device=dev)
+        k = (((idx + 1) & M32) * 0x9E3779B9) & M32
+        x = (k ^ (seed & M32)) & M32
+        x = x ^ (x >> 16)
+        x = (x * 0x7FEB352D) & M32
+        x = x ^ (x >> 15)
+        x = (x * 0x846CA68B) & M32
+        h = x ^ (x >> 16)
+        start = T0_NS + idx * DE_NS
+        soj = h % healthy_span
+        for (b, e, over) in ph:
+            if over and e > p0 and b < p1:
+                bb, ee = max(b, p0) - p0, min(e, p1) - p0
+                soj[bb:ee] = target_ns + h[bb:ee] % over_span
+        now = torch.cummax(start + soj, 0).values
+        if carry is not None:
+            now = torch.clamp(now, min=carry)
+        carry = int(now[-1].item())
+        s0 = max(lo, p0)
+        if p1 > s0:
+            start_out[s0 - lo:p1 - lo] = start[s0 - p0:]
+            now_out[s0 - lo:p1 - lo] = now[s0 - p0:]
+        del idx, k, x, h, start, soj, now
+    return start_out, now_out
+
+
+def rank_seed(rank, salt=0):
+    return tracegen.SEED + 7919 * rank + salt
+
+
+def make_trace(wl, total_claims, rank, dev, salt=0):
+    """Rank `rank`'s queue segment of workload `wl`: per-rank seeded, deterministic (int64 tensors on `dev`)."""
     w = WORKLOADS[wl]
-    seed = tracegen.SEED + 7919 * rank
-    return tracegen.gen_trace(total_claims, seed=seed, target_ns=TARGET_MS * 1_000_000, **w["gen"])
+    return gen_trace_torch(0, total_claims, rank_seed(rank, salt), dev, w["gen"]["unit"], w["gen"].get("all_overloaded_from", -1))
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -163,56 +232,62 @@ def run_reference(args, wl):
     from oracle import oracle as O
     from oracle import ref
     w = WORKLOADS[wl]
-    n = min(REF_SAMPLE, w["n"])
-    params = dict(t0=10**9, de=1000, target_ns=TARGET_MS * 1_000_000, unit=w["gen"].get("unit", 1 << 16),
+    n = REF_SAMPLE[wl]
+    params = dict(t0=T0_NS, de=DE_NS, target_ns=TARGET_MS * 1_000_000, unit=w["gen"].get("unit", 1 << 16),
                   start_overloaded=False, all_overloaded_from=w["gen"].get("all_overloaded_from", -1))
     times, decided = [], 0
     kind = "reference" if ref.available() else "port"
+    parts = max(1, n // REF_QUEUE)
+    m = n // parts
     for step in range(args.warmup + args.steps):
-        seed = tracegen.SEED + step
-        if kind == "reference":
-            r = ref.bench(seed, n, params, TARGET_MS, w["S"])
-            dt = r["drain_ms"] / 1e3
-        else:
-            s, nw = tracegen.gen_trace(n, seed=seed, **{k: v for k, v in params.items()})
-            cd = O.new_codel(TARGET_MS)
-            t0 = time.perf_counter()
-            O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)
-            dt = time.perf_counter() - t0
+        dt = 0.0
+        for part in range(parts):
+            seed = tracegen.SEED + step * parts + part
+            if kind == "reference":
+                r = ref.bench(seed, m, params, TARGET_MS, w["S"])
+                dt += r["drain_ms"] / 1e3
+            else:
+                s, nw = tracegen.gen_trace(m, seed=seed, **{k: v for k, v in params.items()})
+                cd = O.new_codel(TARGET_MS)
+                t0 = time.perf_counter()
+                O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)
+                dt += time.perf_counter() - t0
         if step >= args.warmup:
             times.append(max(dt, 1e-9))
-            decided += n
+            decided += m * parts
     total = sum(times)
     value = decided / total
     # context for the ratio: SpiderMonkey 1.7 is an interpreter from 2007; a JIT-compiling engine (V8 under
     # Node.js, which is not installed here) would land between this number and the compiled C restatement
-    # of the same loop over the same linked-list queue, timed here on the same sample
+    # of the same loop over the same linked-list queue, timed here on ONE FULL step of the CUDA arm's size
     port = None
     try:
-        s, nw = tracegen.gen_trace(n, seed=tracegen.SEED, **{k: v for k, v in params.items()})
+        nfull = min(w["n"], 1 << 24)
+        s, nw = tracegen.gen_trace(nfull, seed=tracegen.SEED, **{k: v for k, v in params.items()})
         best = None
-        for _ in range(3):
+        for _ in range(2):
             cd = O.new_codel(TARGET_MS)
             t0 = time.perf_counter()
             O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-        port = n / best
+        port = nfull / best
     except Exception:
         pass
-    sample = ("%d claims per step of the %s trace spec (same generator, JS side); timed: the drain loop "
-              "lib/pool.js:733-753 = Queue.shift + ControlledDelay.overloaded per claim" % (n, wl))
+    sample = ("%d claims per step of the %s trace spec as %d queue(s) of %d pending claims (same generator, JS side; the "
+              "engine's heap holds one such queue; the CUDA arm's step is %d claims); timed: the drain loop "
+              "lib/pool.js:733-753 = Queue.shift + ControlledDelay.overloaded per claim" % (m * parts, wl, parts, m, w["n"]))
     line = {
-        "impl": "reference", "metric": "claim-queue admissions/sec (CoDel + backend-slot pick)",
+        "impl": "reference", "metric": METRIC,
         "value": value, "unit": "claims/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(len(times), 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
-        "config": {"workload": wl, "claims_per_step": n, "backends": w["B"], "slots": w["S"],
-                   "target_ms": TARGET_MS, "engine": ("reference lib/queue.js+lib/codel.js verbatim under SpiderMonkey 1.7 "
-                                                      "(vendored in the reference tree; Node.js is not installed)"
-                                                      if kind == "reference" else "C restatement (oracle/), linked-list queue")},
+        "config": workload_config(wl, args.gpus),
+        "engine": ("reference lib/queue.js+lib/codel.js verbatim under SpiderMonkey 1.7 (vendored in the reference "
+                   "tree; Node.js is not installed)" if kind == "reference" else "C restatement (oracle/), linked-list queue"),
         "cpu_baseline": {"value": value, "unit": "claims/s", "cores": 1, "kind": kind, "sample": sample,
-                         "c_restatement_linked_list_claims_per_s": port},
+                         "c_restatement_linked_list_claims_per_s": port,
+                         "c_restatement_sample": "one full step of the CUDA arm (%d claims), linked-list queue, 1 core" % min(w["n"], 1 << 24)},
         "e2e": {"value": value, "unit": "claims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -220,36 +295,474 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------ CUDA arm
-def cpu_baseline(wl):
-    """The oracle's C restatement (flat-array variant = the fastest honest CPU form), 1 core,
-    on a bounded sample of the same workload."""
+def cpu_baseline(wl, start, now):
+    """The oracle's C restatement (flat-array variant = the fastest honest CPU form), 1 core, on one
+    full step of the same workload (host arrays handed in by the caller)."""
     from oracle import oracle as O
     w = WORKLOADS[wl]
-    n = min(1 << 24, 4 * w["n"])
-    s, nw = tracegen.gen_trace(n, target_ns=TARGET_MS * 1_000_000, **w["gen"])
+    n = start.shape[0]
     best = None
     for _ in range(3):
         cd = O.new_codel(TARGET_MS)
         t0 = time.perf_counter()
-        O.drain(cd, s, nw, nslots=w["S"], variant="flat", want_out=True)
+        O.drain(cd, start, now, nslots=w["S"], variant="flat", want_out=True)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     cd = O.new_codel(TARGET_MS)
     t0 = time.perf_counter()
     m = min(n, 1 << 22)
-    O.drain(cd, s[:m], nw[:m], nslots=w["S"], variant="list", want_out=True)
+    O.drain(cd, start[:m], now[:m], nslots=w["S"], variant="list", want_out=True)
     dl = time.perf_counter() - t0
     return {"value": n / best, "unit": "claims/s", "cores": 1, "kind": "port",
-            "sample": "%d claims of the %s trace, best of 3; C restatement of lib/codel.js + lib/pool.js:733-753 over flat "
-                      "arrays (oracle/cueball_oracle.c, -O2 -ffp-contract=off)" % (n, wl),
+            "sample": "one full step (%d claims) of the %s trace, best of 3; C restatement of lib/codel.js + lib/pool.js:733-753 "
+                      "over flat arrays (oracle/cueball_oracle.c, -O2 -ffp-contract=off)" % (n, wl),
             "linked_list_variant_claims_per_s": m / dl}
+
+
+class Run(object):
+    """One rank's context, trace and buffers for one workload."""
+
+    def __init__(self, wl, K, W, world, rank, local, dev, stream, seed_salt=0):
+        import torch
+
+        import cueball_b200 as cb
+        self.cb, self.torch = cb, torch
+        self.wl, self.K, self.W, self.world, self.rank, self.dev, self.stream = wl, K, W, world, rank, dev, stream
+        w = WORKLOADS[wl]
+        self.w, self.n, self.nb = w, w["n"], W + K
+        self.d_start, self.d_now = make_trace(wl, self.n * self.nb, rank, dev, seed_salt)
+        self.d_dec = torch.empty(self.n * self.nb, dtype=torch.uint8, device=dev)
+        self.d_slot = torch.empty(self.n * self.nb, dtype=torch.int32, device=dev)
+        self.ctx = cb.Context(local)
+        self.ctx.codel_init(TARGET_MS)
+        self.ctx.backends_set(w["B"], tracegen.gen_insert_draws(w["B"]), w["S"])
+        self.ctx.set_stream(stream.cuda_stream)
+        torch.cuda.synchronize()
+        self.p = (self.d_start.data_ptr(), self.d_now.data_ptr(), self.d_dec.data_ptr(), self.d_slot.data_ptr())
+
+    def step(self, b):
+        # one C-ABI call per step on raw device addresses, as a native host (the N-API shim) makes it
+        lo, n = b * self.n, self.n
+        ps, pn, pd, psl = self.p
+        self.ctx.admit_batch_ptr(ps + 8 * lo, pn + 8 * lo, None, n, pd + lo, psl + 4 * lo, None)
+
+    def reset(self):
+        self.ctx.set_state({"count": 0, "drop_next": 0.0, "first_above_time": 0.0, "dropping": False, "last_empty": None})
+
+    def close(self):
+        self.ctx.synchronize()
+        self.ctx.close()
+        del self.d_start, self.d_now, self.d_dec, self.d_slot
+        self.torch.cuda.empty_cache()
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(xs, world, dev):
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [int(x) for x in xs]
+    t = torch.tensor(list(xs), dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(x) for x in t.tolist()]
+
+
+def timed_pass(run, per_step=None):
+    """W untimed + K timed steps; (device ms of the K steps on this rank, host ms/step to enqueue,
+    kernels launched by the K steps).  Nothing between the two events touches the host except the
+    enqueueing itself.  per_step: optional callable after every step (e.g. an NCCL allreduce)."""
+    torch = run.torch
+    W, K, ctx, stream = run.W, run.K, run.ctx, run.stream
+    for b in range(W):
+        run.step(b)
+        if per_step:
+            per_step()
+    ctx.synchronize()
+    barrier(run.world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    lc0 = ctx.launch_count()
+    th0 = time.perf_counter()
+    for b in range(W, W + K):
+        run.step(b)
+        if per_step:
+            per_step()
+    hms = (time.perf_counter() - th0) * 1e3 / K  # host time to enqueue one step (no waiting)
+    nlaunch = ctx.launch_count() - lc0            # this library's kernels launched by the K timed steps
+    ctx.join()  # the timing stream waits for the last batch of the pipeline (stream-ordered, no host wait)
+    e1.record(stream)
+    barrier(run.world)
+    ctx.synchronize()
+    return e0.elapsed_time(e1), hms, nlaunch
+
+
+def parity_check(run, full_limit=1 << 29):
+    """The outputs of the W+K steps just run against the C oracle (one sequential drain from the
+    initial state): every decision and slot, the totals, the final ControlledDelay state."""
+    from oracle import oracle as O
+    st = run.ctx.stats()
+    total = run.n * run.nb
+    t0 = time.perf_counter()
+    hs, hn = run.d_start.cpu().numpy(), run.d_now.cpu().numpy()
+    cd = O.new_codel(TARGET_MS)
+    od, os_, ost = O.drain(cd, hs, hn, None, nslots=run.w["S"])
+    lo = 0 if total <= full_limit else total - run.n
+    dec = run.d_dec[lo:].cpu().numpy()
+    slot = run.d_slot[lo:].cpu().numpy()
+    ok_dec = bool(np.array_equal(dec, od[lo:]))
+    ok_slot = bool(np.array_equal(slot, os_[lo:]))
+    ref = cd.as_dict()
+    got = {"count": float(st.state.count), "drop_next": st.state.drop_next, "first_above_time": st.state.first_above_time,
+           "dropping": bool(st.state.dropping)}
+    ok_state = all(np.float64(got[k]).tobytes() == np.float64(ref[k]).tobytes() for k in ("count", "drop_next", "first_above_time")) \
+        and got["dropping"] == ref["dropping"]
+    ok_tot = (st.total_drops == ost.drops and st.total_admits == ost.admits and st.cursor == ost.cursor)
+    kd = int((od[run.W * run.n:] == 1).sum())
+    return {"ok": bool(ok_dec and ok_slot and ok_state and ok_tot), "decisions": ok_dec, "slots": ok_slot, "state_bits": ok_state,
+            "totals": ok_tot, "claims_compared": int(total - lo), "claims_drained_by_oracle": int(total),
+            "timed_steps_drops": kd, "timed_steps_admits": int(run.K * run.n - kd),
+            "oracle": "oracle/cueball_oracle.c cbo_drain_batch_flat, one sequential drain of the W+K steps",
+            "seconds": round(time.perf_counter() - t0, 2)}, (hs, hn)
+
+
+def roofline(run, wl, ms, traffic):
+    """The dominant kernel's launch duration, with CUDA events on the launching stream, same inputs as the timed
+    steps.  `scan`: two events around a burst of back-to-back scan launches over min(K, 20) DIFFERENT batches (cold
+    data each) divided by the launch count -- one kernel alone between two events also measures its launch
+    latency (a few microseconds here).  `scan_isolated`, `resolve`, `emit`: events around each kernel of batches
+    run strictly one after the other."""
+    cb, torch = run.cb, run.torch
+    nbk = min(run.K, 20)
+    run.reset()
+    run.ctx.profile_enable(1)
+    for b in range(run.W, run.W + nbk):
+        lo, hi = b * run.n, (b + 1) * run.n
+        run.ctx.admit_batch_dev(run.d_start[lo:hi], run.d_now[lo:hi], None, run.d_dec[lo:hi], run.d_slot[lo:hi])
+    kms, kcnt = run.ctx.profile_get()
+    scan_iso = kms[cb._native.K_SCAN] / max(kcnt[cb._native.K_SCAN], 1)
+    run.ctx.profile_enable(2)  # scan kernel only
+    for b in range(run.W, run.W + 2):
+        run.step(b)
+    run.ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(run.stream)
+    for b in range(run.W, run.W + nbk):
+        run.step(b)
+    e1.record(run.stream)
+    torch.cuda.synchronize()
+    scan_ms = e0.elapsed_time(e1) / nbk
+    run.ctx.profile_enable(0)
+    run.reset()
+    peak, peak_src = peaks()
+    achieved = ALG_BYTES_SCAN * run.n / (scan_ms / 1e3) / 1e9
+    step_gbs = ALG_BYTES_STEP * run.n * run.K / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "cb::scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic.get(wl), "peak_source": peak_src,
+            "alg_bytes_per_claim": ALG_BYTES_SCAN, "alg_bytes_per_launch": ALG_BYTES_SCAN * run.n,
+            "timing": "CUDA events on the launching stream around %d back-to-back scan launches over %d different batches" % (nbk, nbk),
+            "kernel_ms": {"scan": scan_ms, "scan_isolated": scan_iso, "resolve": kms[1] / max(kcnt[1], 1),
+                          "emit": kms[2] / max(kcnt[2], 1)},
+            "step": {"alg_bytes_per_claim": ALG_BYTES_STEP, "achieved": step_gbs, "frac": step_gbs / peak}}
+
+
+def pcie_rates(dev, stream_a, stream_b):
+    """Measured pinned-memory copy rates of this GPU's PCIe link (GB/s): H2D alone, D2H alone, both at once."""
+    import torch
+    nb_in, nb_out = 256 << 20, 80 << 20
+    hi, ho = torch.empty(nb_in, dtype=torch.uint8).pin_memory(), torch.empty(nb_out, dtype=torch.uint8).pin_memory()
+    di, do = torch.empty(nb_in, dtype=torch.uint8, device=dev), torch.empty(nb_out, dtype=torch.uint8, device=dev)
+
+    def t(fn, reps=4):
+        best = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best
+
+    def h2d():
+        with torch.cuda.stream(stream_a):
+            di.copy_(hi, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(stream_b):
+            ho.copy_(do, non_blocking=True)
+
+    a, b = t(h2d), t(d2h)
+    both = t(lambda: (h2d(), d2h()))
+    return {"h2d_gbs": nb_in / a / 1e9, "d2h_gbs": nb_out / b / 1e9,
+            "duplex_gbs": {"h2d": nb_in / both / 1e9, "d2h": nb_out / both / 1e9,
+                           "note": "256 MiB in and 80 MiB out at once (the path's 16:5 byte ratio)"}}
+
+
+def e2e_leg(run, host_trace, pcie):
+    """Host buffers through the public entry point: pinned inputs in, decisions and slots back, every step."""
+    torch = run.torch
+    n, W = run.n, run.W
+    ke = min(run.K, 10)
+    hs_all, hn_all = host_trace
+    hs = torch.from_numpy(hs_all[W * n:(W + ke) * n]).pin_memory().numpy()
+    hn = torch.from_numpy(hn_all[W * n:(W + ke) * n]).pin_memory().numpy()
+    hdec = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+    hslot = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
+    run.ctx.set_stream(None)
+    run.reset()
+    for _ in range(3):  # warm the staging buffers, the copy engines and the clocks
+        run.ctx.admit_batch(hs[:n], hn[:n], out_decision=hdec, out_slot=hslot)
+    run.reset()
+    barrier(run.world)
+    t0 = time.perf_counter()
+    drops = 0
+    for b in range(ke):
+        _, _, _, est = run.ctx.admit_batch(hs[b * n:(b + 1) * n], hn[b * n:(b + 1) * n], out_decision=hdec, out_slot=hslot)
+        drops += est.drops  # the step's result is read on the host
+    barrier(run.world)
+    te = max_over_ranks(time.perf_counter() - t0, run.world, run.dev)
+    run.ctx.set_stream(run.stream.cuda_stream)
+    h2d, d2h = 16 * n, 5 * n + 176
+    step_s = te / ke
+    out = {"value": run.world * n * ke / te, "unit": "claims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": ke, "ms_per_step": step_s * 1e3, "host_memory": "pinned inputs and outputs", "drops_read_on_host": int(drops)}
+    if pcie:
+        bound_s = max(h2d / (pcie["duplex_gbs"]["h2d"] * 1e9), d2h / (pcie["duplex_gbs"]["d2h"] * 1e9))
+        out["pcie"] = pcie
+        out["frac_of_pcie"] = bound_s / step_s
+        out["pcie_bound_ms_per_step"] = bound_s * 1e3
+    return out
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
+def device_leg(wl, K, W, world, rank, local, dev, stream, want_parity=True, want_e2e=True, want_roof=True, pcie=None,
+               peers=False, sampler=None, want_cpu=False):
+    """One workload on this rank: timed pass (+ optional in-run parity, roofline, e2e).  Returns a dict (rank 0
+    fills the line from it)."""
+    import torch.distributed as dist
+    run = Run(wl, K, W, world, rank, local, dev, stream)
+    if peers and world > 1:
+        h, _ = run.ctx.peers_board()
+        hs = [None] * world
+        dist.all_gather_object(hs, h)
+        run.ctx.peers_connect(world, rank, handles=hs)
+    if sampler:
+        sampler.start()
+    ms, host_ms, launches = timed_pass(run)
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ms, world, dev)
+    out = {"ms": ms, "host_ms": host_ms, "launches": sum_over_ranks([launches], world, dev)[0], "clocks": clocks,
+           "value": world * run.n * K / (ms / 1e3)}
+    st = run.ctx.stats()
+    out["admit_fraction"] = st.total_admits / max(st.total_admits + st.total_drops, 1)
+    if peers and world > 1:
+        g = run.ctx.peers_counts()  # running global totals after this rank's last batch, from its own board
+        loc = sum_over_ranks([st.total_drops, st.total_admits, run.n * run.nb], world, dev)
+        out["global_counts"] = {"drops": int(g.drops), "admits": int(g.admits), "claims": int(g.n), "steps": int(g.steps),
+                                "equals_sum_of_ranks": [int(g.drops), int(g.admits), int(g.n)] == loc,
+                                "how": "cb_peers_*: per-batch counts stored into every rank's board over NVLink peer memory "
+                                       "(device-side, after every batch, inside the timed region); no collective"}
+        run.ctx.peers_connect(0, 0)
+    host_trace = None
+    if want_parity:
+        par, host_trace = parity_check(run)
+        oks = sum_over_ranks([1 if par["ok"] else 0], world, dev)[0]
+        par["ranks_ok"] = oks
+        par["ok"] = bool(oks == world)
+        out["parity"] = par
+    if want_roof:
+        out["roofline"] = roofline(run, wl, ms, load_traffic())
+    if want_cpu and rank == 0 and host_trace is not None:
+        n = run.n
+        out["cpu_baseline"] = cpu_baseline(wl, host_trace[0][W * n:(W + 1) * n], host_trace[1][W * n:(W + 1) * n])
+    if want_e2e:
+        if host_trace is None:
+            host_trace = (run.d_start.cpu().numpy(), run.d_now.cpu().numpy())
+        out["e2e"] = e2e_leg(run, host_trace, pcie)
+    run.close()
+    return out
+
+
+def nccl_leg(wl, K, W, world, rank, local, dev, stream):
+    """The north star's literal form: the ranks' counts summed by NCCL (cb_allreduce_counts: one 24-byte
+    ncclAllReduce on a side stream, device-ordered after the batch's resolve kernel, no host wait)
+    -- once per K-step window and, separately, after every batch."""
+    import torch.distributed as dist
+
+    import cueball_b200 as cb
+    run = Run(wl, K, W, world, rank, local, dev, stream, seed_salt=31)
+    obj = [cb.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    run.ctx.comm_init(world, rank, obj[0])
+    out = {}
+    # (a) once per window: the last timed batch's counts (each rank's batch counts; a cumulative sum is the
+    # running totals of cb_batch_stats) -- ONE collective per K steps
+    calls = {"i": 0}
+
+    def last_only():
+        calls["i"] += 1
+        if calls["i"] == W + K:
+            run.ctx.allreduce_counts()
+    ms, _, _ = timed_pass(run, per_step=last_only)
+    ms = max_over_ranks(ms, world, dev)
+    g = run.ctx.stats()
+    out["per_window"] = {"value": world * run.n * K / (ms / 1e3), "unit": "claims/s", "ms_per_step": ms / K,
+                         "collective": "1 ncclAllReduce(3 x u64) per %d-step window, asynchronous on a side stream" % K,
+                         "last_batch_global": {"drops": int(g.global_drops), "admits": int(g.global_admits), "claims": int(g.global_n)}}
+    # (b) after every batch
+    run.reset()
+    ms2, _, _ = timed_pass(run, per_step=run.ctx.allreduce_counts)
+    ms2 = max_over_ranks(ms2, world, dev)
+    out["per_step"] = {"value": world * run.n * K / (ms2 / 1e3), "unit": "claims/s", "ms_per_step": ms2 / K,
+                       "collective": "cb_allreduce_counts = 1 ncclAllReduce(3 x u64) after every batch, on a side stream "
+                                     "(an 8-rank 24-byte allreduce is ~80 us and they serialise on their communicator)"}
+    run.close()
+    return out
+
+
+def ring_leg(wl, K, W, world, rank, local, dev, stream):
+    """ONE logical queue over the GPUs: segment (k, r) of the queue is batch k of rank r; the ControlledDelay
+    state and the admit cursor travel round a ring of device mailboxes over NVLink peer memory.  Checked bit
+    for bit against one sequential drain (C oracle) of the queue's first steps."""
+    import torch
+    import torch.distributed as dist
+
+    import cueball_b200 as cb
+    from oracle import oracle as O
+    w = WORKLOADS[wl]
+    m, nb = w["n"], W + K
+    seed = tracegen.SEED + 101
+    unit = w["gen"]["unit"]
+    # this rank's segments of the one global trace, generated in place (see gen_trace_torch)
+    ds = torch.empty(m * nb, dtype=torch.int64, device=dev)
+    dn = torch.empty(m * nb, dtype=torch.int64, device=dev)
+    for k in range(nb):
+        lo = (k * world + rank) * m
+        s, nw = gen_trace_torch(lo, lo + m, seed, dev, unit)
+        ds[k * m:(k + 1) * m], dn[k * m:(k + 1) * m] = s, nw
+        del s, nw
+    dd = torch.empty(m * nb, dtype=torch.uint8, device=dev)
+    sl = torch.empty(m * nb, dtype=torch.int32, device=dev)
+    ctx = cb.Context(local)
+    ctx.codel_init(TARGET_MS)
+    ctx.backends_set(w["B"], tracegen.gen_insert_draws(w["B"]), w["S"])
+    handle, _ = ctx.ring_mailbox()
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    ctx.ring_connect(world, rank, next_handle=handles[(rank + 1) % world] if world > 1 else None)
+    ctx.set_stream(stream.cuda_stream)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(nb):
+        if k == W:
+            ctx.join()
+            e0.record(stream)
+        lo = k * m
+        ctx.admit_batch_ptr(ds.data_ptr() + 8 * lo, dn.data_ptr() + 8 * lo, None, m, dd.data_ptr() + lo, sl.data_ptr() + 4 * lo, None)
+    ctx.join()
+    e1.record(stream)
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    # window check: the queue's first kc steps, drained sequentially by the oracle on every rank's host
+    kc = max(1, min(nb, (1 << 27) // (m * world)))
+    gs, gn = gen_trace_torch(0, kc * world * m, seed, dev, unit)
+    hs, hn = gs.cpu().numpy(), gn.cpu().numpy()
+    del gs, gn
+    cd = O.new_codel(TARGET_MS)
+    od, os_, _ = O.drain(cd, hs, hn, None, nslots=w["S"])
+    ok = True
+    for k in range(kc):
+        lo = (k * world + rank) * m
+        ok = ok and bool(np.array_equal(dd[k * m:(k + 1) * m].cpu().numpy(), od[lo:lo + m]))
+        ok = ok and bool(np.array_equal(sl[k * m:(k + 1) * m].cpu().numpy(), os_[lo:lo + m]))
+    oks = sum_over_ranks([1 if ok else 0], world, dev)[0]
+    ctx.synchronize()
+    ctx.ring_connect(0, 0)
+    ctx.close()
+    del ds, dn, dd, sl
+    torch.cuda.empty_cache()
+    return {"value": world * m * K / (ms / 1e3), "unit": "claims/s", "ms_per_step": ms / K, "claims_per_segment": m,
+            "segments_per_step": world, "workload": wl,
+            "bit_exact_vs_one_sequential_drain": bool(oks == world),
+            "checked": "decisions and slots of the queue's first %d steps (%d claims) on every rank against ONE sequential "
+                       "drain by the C oracle" % (kc, kc * world * m),
+            "mode": "one logical queue: ControlledDelay state + admit cursor round a ring of device mailboxes over NVLink "
+                    "peer memory (cb_ring_*), F hand-over ahead of the state; no collective"}
+
+
+def stress_leg(local, dev, stream):
+    """SURVEY 8(d)'s non-monotone stress trace: the clock steps back 150 ms every 2^20 claims, so every batch takes
+    the exact sequential path (one warp runs lib/codel.js:56-86 claim by claim -- the count-2 / sqrt(count)
+    branch of :72-79 is only reachable this way).  Full parity against the oracle; the rate is the fallback's."""
+    import torch
+
+    import cueball_b200 as cb
+    from oracle import oracle as O
+    n, nb = 1 << 21, 3
+    start, now = tracegen.gen_trace(n * nb, seed=tracegen.SEED + 5, target_ns=TARGET_MS * 1_000_000, unit=1 << 18,
+                                    all_overloaded_from=1 << 16)
+    now = now.copy()
+    for j in range(1 << 20, n * nb, 1 << 20):
+        now[j:] -= 150_000_000  # the clock steps back 150 ms
+        now[j:] = np.maximum(now[j:], start[j:] - 10 ** 12)  # keep it an int64 clock; sojourn may go negative
+    ds, dn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+    dd = torch.empty(n * nb, dtype=torch.uint8, device=dev)
+    sl = torch.empty(n * nb, dtype=torch.int32, device=dev)
+    ctx = cb.Context(local)
+    ctx.codel_init(TARGET_MS)
+    ctx.backends_set(64, tracegen.gen_insert_draws(64), 256)
+    ctx.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for b in range(nb):
+        lo = b * n
+        ctx.admit_batch_ptr(ds.data_ptr() + 8 * lo, dn.data_ptr() + 8 * lo, None, n, dd.data_ptr() + lo, sl.data_ptr() + 4 * lo, None)
+    ctx.join()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    st = ctx.stats()
+    cd = O.new_codel(TARGET_MS)
+    od, os_, ost = O.drain(cd, start, now, None, nslots=256)
+    ref = cd.as_dict()
+    ok = bool(np.array_equal(dd.cpu().numpy(), od) and np.array_equal(sl.cpu().numpy(), os_) and st.total_drops == ost.drops
+              and np.float64(st.state.drop_next).tobytes() == np.float64(ref["drop_next"]).tobytes()
+              and float(st.state.count) == ref["count"])
+    ms = e0.elapsed_time(e1)
+    ctx.close()
+    return {"value": n * nb / (ms / 1e3), "unit": "claims/s", "claims": n * nb, "path": int(st.path),
+            "max_count_reached": float(ref["count"]), "bit_exact_vs_oracle": ok,
+            "note": "backwards clock: every batch runs the exact one-warp state machine (CB_PATH_SEQUENTIAL); this is "
+                    "the fallback's rate, not the streaming path's"}
 
 
 def run_cuda(args, wl, extra=True):
     import torch
     import torch.distributed as dist
-
-    import cueball_b200 as cb
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,196 +775,62 @@ def run_cuda(args, wl, extra=True):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    w = WORKLOADS[wl]
-    n, K, W = w["n"], args.steps, args.warmup
-    nb = W + K
-    start, now = make_trace(wl, n * nb, rank)
-
-    ctx = cb.Context(local)
-    ctx.codel_init(TARGET_MS)
-    ctx.backends_set(w["B"], tracegen.gen_insert_draws(w["B"]), w["S"])
     # a real (non-legacy-default) stream: the library's kernels and the timing events share it
     stream = torch.cuda.Stream(device=dev)
     assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
-    if world > 1:  # one communicator per context, id from rank 0
-        obj = [cb.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        ctx.comm_init(world, rank, obj[0])
+    K, W = args.steps, args.warmup
 
-    d_start = torch.from_numpy(start).to(dev)
-    d_now = torch.from_numpy(now).to(dev)
-    d_dec = torch.empty(n * nb, dtype=torch.uint8, device=dev)
-    d_slot = torch.empty(n * nb, dtype=torch.int32, device=dev)
-    torch.cuda.synchronize()
-
-    p_start, p_now, p_dec, p_slot = d_start.data_ptr(), d_now.data_ptr(), d_dec.data_ptr(), d_slot.data_ptr()
-
-    # The global drop count (north_star: "a single NCCL allreduce over NVLink for the global drop
-    # count").  "window" (default): every rank's cumulative counts are summed by ONE NCCL allreduce at
-    # the end of the K-step window, inside the timed region.  "step": cb_allreduce_counts after every
-    # batch (its own 24-byte NCCL allreduce on a side stream) -- measured in a second pass and
-    # reported as `per_step_collective`: one 8-rank allreduce takes ~80 us, they serialise on their
-    # communicator, and a 43-us step cannot sustain one per batch.  "none": no collective.
-    coll_mode = os.environ.get("CB_BENCH_COLLECTIVE", "none" if os.environ.get("CB_BENCH_NO_ALLREDUCE") else "window")
-    if world == 1:
-        coll_mode = "none"
-
-    def step_dev(b, per_step=False):
-        # one C-ABI call per step on raw device addresses, as a native host (the N-API shim) makes it
-        lo = b * n
-        ctx.admit_batch_ptr(p_start + 8 * lo, p_now + 8 * lo, None, n, p_dec + lo, p_slot + 4 * lo, None)
-        if per_step:
-            ctx.allreduce_counts()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ------------------------------------------------------------
-    def timed_pass(per_step):
-        """W untimed + K timed steps; returns (device ms of the K steps on this rank, host ms/step,
-        global cumulative [drops, admits, claims] or None, kernels launched by the K steps)."""
-        for b in range(W):
-            step_dev(b, per_step)
-        ctx.synchronize()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        lc0 = ctx.launch_count()
-        th0 = time.perf_counter()
-        for b in range(W, W + K):
-            step_dev(b, per_step)
-        hms = (time.perf_counter() - th0) * 1e3 / K  # host time to enqueue one step (no waiting)
-        nlaunch = ctx.launch_count() - lc0            # this library's kernels launched by the K timed steps
-        ctx.join()  # the timing stream waits for the last batch of the pipeline
-        glob = None
-        if coll_mode == "window" and not per_step:
-            stw = ctx.stats()  # waits for the window; this rank's cumulative counts
-            glob = torch.tensor([stw.total_drops, stw.total_admits, stw.total_drops + stw.total_admits],
-                                dtype=torch.int64, device=dev)
-            with torch.cuda.stream(stream):
-                dist.all_reduce(glob)  # the one NCCL allreduce, ordered on the timing stream
-        e1.record(stream)
-        barrier()
-        ctx.synchronize()
-        return e0.elapsed_time(e1), hms, glob, nlaunch
-
+    pcie = pcie_rates(dev, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)) if rank == 0 or world > 1 else None
     sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms, host_ms, glob, launches = timed_pass(coll_mode == "step")
-    clocks = sampler.stop() if sampler else None
-    st = ctx.stats()
-    global_counts = [int(x) for x in glob.tolist()] if glob is not None else None
-    per_step = None
-    if coll_mode == "window" and extra:
-        # second pass over the same batches with a collective after every batch (state carries on)
-        ms2, _, _, _ = timed_pass(True)
-        t2 = torch.tensor([ms2], dtype=torch.float64, device=dev)
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms2 = float(t2.item())
-        per_step = {"value": world * n * K / (ms2 / 1e3), "unit": "claims/s", "ms_per_step": ms2 / K,
-                    "collective": "cb_allreduce_counts = 1 ncclAllReduce(3 x u64) after every batch, on a side stream"}
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    value = world * n * K / (ms / 1e3)
-
-    # ---- per-kernel profile pass (CUDA events around each kernel, same stream) --------------
-    ctx.set_state({"count": 0, "drop_next": 0.0, "first_above_time": 0.0, "dropping": False, "last_empty": None})
-    ctx.profile_enable(True)
-    for b in range(W, W + min(K, 20)):
-        lo, hi = b * n, (b + 1) * n
-        ctx.admit_batch_dev(d_start[lo:hi], d_now[lo:hi], None, d_dec[lo:hi], d_slot[lo:hi])
-    kms, kcnt = ctx.profile_get()
-    ctx.profile_enable(False)
-    scan_ms = kms[cb._native.K_SCAN] / max(kcnt[cb._native.K_SCAN], 1)
-    peak, peak_src = peaks()
-    achieved = ALG_BYTES_SCAN * n / (scan_ms / 1e3) / 1e9
-    roof = {"bound": "hbm", "kernel": "cb::scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": TRAFFIC.get(wl), "peak_source": peak_src,
-            "alg_bytes_per_claim": ALG_BYTES_SCAN,
-            "kernel_ms": {"scan": scan_ms, "resolve": kms[1] / max(kcnt[1], 1), "emit": kms[2] / max(kcnt[2], 1)},
-            "step": {"alg_bytes_per_claim": ALG_BYTES_STEP,
-                     "achieved": ALG_BYTES_STEP * n * K / (ms / 1e3) / 1e9 / 1.0,
-                     "frac": ALG_BYTES_STEP * n * K / (ms / 1e3) / 1e9 / peak}}
-
-    # ---- end to end: host buffers through the public entry point ----------------------------
-    ke = min(K, 10)
-    hs = torch.from_numpy(start[W * n:(W + ke) * n]).pin_memory().numpy()
-    hn = torch.from_numpy(now[W * n:(W + ke) * n]).pin_memory().numpy()
-    hdec = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
-    hslot = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
-    ctx.set_stream(None)
-    ctx.set_state({"count": 0, "drop_next": 0.0, "first_above_time": 0.0, "dropping": False, "last_empty": None})
-    ctx.admit_batch(hs[:n], hn[:n])  # warm the staging buffers
-    ctx.admit_batch(hs[:n], hn[:n])
-    barrier()
-    t0 = time.perf_counter()
-    drops = 0
-    for b in range(ke):
-        dec, slot, _, est = ctx.admit_batch(hs[b * n:(b + 1) * n], hn[b * n:(b + 1) * n],
-                                            out_decision=hdec, out_slot=hslot)
-        drops += est.drops  # the step's result is read on the host
-    barrier()
-    te = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([te], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te = float(t.item())
-    e2e = {"value": world * n * ke / te, "unit": "claims/s", "h2d_bytes_per_step": 16 * n,
-           "d2h_bytes_per_step": 5 * n + 176, "steps": ke, "host_memory": "pinned inputs and outputs",
-           "cpu_affinity": ("%d CPUs of the GPU's NUMA node" % numa_cpus) if numa_cpus else "unbound"}
-
-    ctx.synchronize()
-    ctx.close()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return None
+    main = device_leg(wl, K, W, world, rank, local, dev, stream, want_parity=True, want_e2e=True, want_roof=True, pcie=pcie,
+                      peers=True, sampler=sampler, want_cpu=(extra and world == 1))
+    w = WORKLOADS[wl]
+    cfg = workload_config(wl, world)
     line = {
-        "metric": "claim-queue admissions/sec (CoDel + backend-slot pick)", "value": value, "unit": "claims/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "metric": METRIC, "value": main["value"], "unit": "claims/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": main["ms"] / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64+int64", "data": "synthetic",
-        "config": {"workload": wl, "claims_per_step_per_gpu": n, "backends": w["B"], "slots": w["S"],
-                   "target_ms": TARGET_MS, "interval_ms": 100, "parallelism": "queue segment per GPU" if world > 1 else "1 GPU",
-                   "collective": {"window": "1 ncclAllReduce(3 x i64) of every rank's cumulative counts per %d-step window, "
-                                            "inside the timed region" % K,
-                                  "step": "cb_allreduce_counts: 1 ncclAllReduce(3 x u64) after every batch",
-                                  "none": None}[coll_mode],
-                   "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
-                         % (nb, 16.0 * n * nb / 1e6),
-                   "state": "ControlledDelay state chained on device across steps",
-                   "pipeline": "up to 5 batches in flight, one lane (stream) each; the scan is launched at low priority, "
-                               "prepare/commit/emit at high; commits ordered by a device-side chain word",
-                   "admit_fraction": st.total_admits / max(st.total_admits + st.total_drops, 1)},
-        "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "host_enqueue_ms_per_step": host_ms,
+        "config": cfg,
+        "details": {
+            "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
+                  % (W + K, 16.0 * w["n"] * (W + K) / 1e6),
+            "state": "ControlledDelay state chained on device across steps",
+            "pipeline": "up to 5 batches in flight, one lane (stream) each; the scan is launched at low priority, "
+                        "resolve/emit at high; commits ordered by a device-side chain word",
+            "global_counts": "per batch, device-side, over peer-memory boards (cb_peers_*)" if world > 1 else None,
+            "timed_region": "CUDA events on the launching stream around the K steps; no host wait, no torch collective inside",
+            "admit_fraction": main["admit_fraction"],
+            "cpu_affinity": ("%d CPUs of the GPU's NUMA node" % numa_cpus) if numa_cpus else "unbound"},
+        "roofline": main.get("roofline"), "e2e": main.get("e2e"), "gpu_launches": main["launches"], "clocks": main["clocks"],
+        "host_enqueue_ms_per_step": main["host_ms"], "parity": main.get("parity"),
     }
+    if "global_counts" in main:
+        line["global_counts"] = main["global_counts"]
+    if "cpu_baseline" in main:
+        line["cpu_baseline"] = main["cpu_baseline"]
     if extra:
-        line["cpu_baseline"] = cpu_baseline(wl)
+        if world == 1:
+            # configs[1]: 1M claims per step (launch/latency-bound: 21 MB is 3.2 us at the roofline)
+            k2, w2 = 200, 10
+            c2 = device_leg("c2", k2, w2, world, rank, local, dev, stream, want_parity=True, want_e2e=True, want_roof=True,
+                            pcie=pcie)
+            line["c2"] = {"value": c2["value"], "unit": "claims/s", "ms_per_step": c2["ms"] / k2, "steps": k2, "warmup": w2,
+                          "host_enqueue_ms_per_step": c2["host_ms"], "gpu_launches": c2["launches"], "roofline": c2["roofline"],
+                          "e2e": c2["e2e"], "parity": c2["parity"], "config": workload_config("c2", 1)}
+            line["nonmonotone_stress"] = stress_leg(local, dev, stream)
+        else:
+            line["nccl_allreduce"] = nccl_leg(wl, K, W, world, rank, local, dev, stream)
+            line["one_queue"] = ring_leg("c4", K, W, world, rank, local, dev, stream)
+            for xw in ("c4", "c5"):
+                x = device_leg(xw, K, W, world, rank, local, dev, stream, want_parity=True, want_e2e=False, want_roof=(xw == "c4"),
+                               peers=True)
+                line[xw] = {"value": x["value"], "unit": "claims/s", "ms_per_step": x["ms"] / K, "gpu_launches": x["launches"],
+                            "parity": x["parity"], "global_counts": x.get("global_counts"), "roofline": x.get("roofline"),
+                            "admit_fraction": x["admit_fraction"], "config": workload_config(xw, world)}
     if world > 1:
-        if global_counts is not None:
-            line["global_counts"] = {"drops": global_counts[0], "admits": global_counts[1], "claims": global_counts[2]}
-        if per_step is not None:
-            line["per_step_collective"] = per_step
+        dist.barrier()
         dist.destroy_process_group()
-    return line
-
-
-# DRAM traffic per scan-kernel launch from `ncu --set full` captures (profiles/): bytes
-TRAFFIC = {}
-_tp = os.path.join(ROOT, "profiles", "traffic.json")
-if os.path.exists(_tp):
-    with open(_tp) as _f:
-        TRAFFIC = json.load(_f)
+    return line if rank == 0 else None
 
 
 def main():
@@ -461,12 +840,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the cpu_baseline leg and the c3 side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cpu_baseline leg and the extra keys")
     args = ap.parse_args()
-    wl = args.workload or ("c2" if args.gpus == 1 else "c4")
-    dk, dw = {"c2": (200, 10), "c3": (15, 4), "c4": (30, 5), "c5": (15, 4)}[wl]
+    wl = args.workload or "c3"
+    dk, dw = {"c2": (200, 10), "c3": (20, 5), "c4": (30, 5), "c5": (20, 5)}[wl]
     if args.impl == "reference":
-        dk, dw = 8, 3  # ~0.6 s of single-threaded JS per step
+        dk, dw = 8, 3  # seconds of single-threaded JS per step
     args.steps = args.steps if args.steps is not None else dk
     args.warmup = max(3, args.warmup if args.warmup is not None else dw)
     rank = int(os.environ.get("RANK", "0"))
@@ -475,14 +854,8 @@ def main():
             run_reference(args, wl)
         return
     line = run_cuda(args, wl, extra=not args.no_extra)
-    if line is None:
-        return
-    if not args.no_extra and args.gpus == 1 and wl == "c2":
-        # the HBM-roofline-relevant size: one 16M-claim batch per step (BASELINE config C3)
-        a3 = argparse.Namespace(gpus=1, steps=15, warmup=4)
-        c3 = run_cuda(a3, "c3", extra=False)
-        line["c3"] = {k: c3[k] for k in ("value", "unit", "ms_per_step", "steps", "roofline", "e2e", "gpu_launches")}
-    print(json.dumps(line))
+    if line is not None:
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":

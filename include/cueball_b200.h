@@ -116,7 +116,7 @@ int cb_abi_version(void);
  * after the work already queued on the caller's stream; its outputs are complete after
  * cb_join() (stream-ordered) or cb_synchronize()/cb_batch_stats_get() (host-blocking). */
 int cb_set_stream(cb_ctx *ctx, void *cuda_stream);
-int cb_set_pipeline_depth(cb_ctx *ctx, int depth); /* 1 = strictly in order on one stream; default 3 */
+int cb_set_pipeline_depth(cb_ctx *ctx, int depth); /* 1 = strictly in order on one stream; default 5 */
 int cb_join(cb_ctx *ctx);        /* the caller's stream waits for every batch enqueued so far */
 int cb_synchronize(cb_ctx *ctx); /* the host waits for every batch enqueued so far */
 /* pinned host memory for the *_batch host-buffer calls */
@@ -169,6 +169,10 @@ int cb_batch_stats_get(cb_ctx *ctx, cb_batch_stats *out);
 /* ControlledDelay#overloaded(start) for ONE claim (lib/codel.js:56-86): the scalar
  * form the unmodified pool.js loop calls; *drop = 0/1. */
 int cb_codel_overloaded(cb_ctx *ctx, int64_t start_ns, int64_t now_ns, int *drop);
+/* the same with both clocks as the reference's double milliseconds (utils.currentMillis(),
+ * lib/utils.js:198-204): what an unmodified pool.js hands over, p_codel.overloaded(hdl.ch_started),
+ * lib/pool.js:735-736 with lib/connection-fsm.js:523 */
+int cb_codel_overloaded_ms(cb_ctx *ctx, double start_ms, double now_ms, int *drop);
 
 /* ----------------------------------------- backends, preference list, slots */
 
@@ -204,6 +208,28 @@ int cb_plan_rebalance(cb_ctx *ctx, const int32_t *have, const uint8_t *dead, int
     int32_t target, int32_t max, int singleton, int32_t *want_out, int32_t *add_out,
     int32_t *n_add, int32_t *rm_key_out, int32_t *rm_ord_out, int32_t *n_rm);
 
+/* ------------------------------------------------------- resolver ingestion */
+
+/* the identity and the event stream either side of the preference list.
+ *   cb_srv_keys          srvKey() of n backends at once (lib/resolver.js:1157-1171): base64 of
+ *                        sha1(name || "||" || String(port) || "||" || ipaddr.js-normalised address), SHA-1 on
+ *                        the device.  keys_out: n x CB_SRVKEY_LEN characters, no terminator.  CB_EINVAL when
+ *                        an address is not an IP address (ipaddr.parse throws).
+ *   cb_resolver_process  CueBallDNSResolver#state_process (lib/resolver.js:1024-1108) on the context's
+ *                        backend map: `keys` are the srvKeys of the new SRV/A result in record order (a key that
+ *                        appears twice keeps its first position, the later record wins); outputs the 'removed'
+ *                        events (old map order) and then the 'added' events (new map order) the reference
+ *                        emits, as key ids for cb_backend_removed / cb_backend_added (ids are handed out here,
+ *                        0, 1, 2, ... in order of first appearance) plus, for 'added', the input row of the
+ *                        backend record.  An empty result changes nothing and sets *empty_set ('empty-set'
+ *                        counter, :1052-1061).  Output arrays may be NULL; room for n entries ('added') and for
+ *                        the current number of backends ('removed'). */
+#define CB_SRVKEY_LEN 28
+int cb_srv_keys(cb_ctx *ctx, const char *const *names, const int32_t *ports, const char *const *addresses, size_t n,
+    char *keys_out);
+int cb_resolver_process(cb_ctx *ctx, const char *keys, size_t n, int32_t *removed_ids, char *removed_keys,
+    int32_t *n_removed, int32_t *added_ids, int32_t *added_rows, int32_t *n_added, int32_t *empty_set);
+
 /* ----------------------------------------------------------------- multi-GPU */
 
 /* One process per GPU; the queue is sharded by contiguous segment, each rank's
@@ -212,6 +238,25 @@ int cb_plan_rebalance(cb_ctx *ctx, const int32_t *have, const uint8_t *dead, int
 int cb_comm_unique_id(void *out, size_t *bytes); /* ncclGetUniqueId; bytes in/out (>=128) */
 int cb_comm_init(cb_ctx *ctx, int nranks, int rank, const void *unique_id, size_t bytes);
 int cb_allreduce_counts(cb_ctx *ctx); /* async on the context's stream */
+
+/* The same global counts after EVERY batch without a collective: each rank owns a board in HBM; a tiny
+ * kernel behind the batch's emit kernel stores the batch's {drops, admits, n} into its row of every
+ * rank's board over NVLink peer memory (payload, then a system-scope tag), and sums the rows of its own
+ * board as they complete.  No rank waits for another on the data path (flow control only holds a rank
+ * that is 64 batches ahead of the slowest reader).  Every rank must submit the same number of batches.
+ *   cb_peers_board   : this context's board as a CUDA IPC handle (64 bytes) and/or a device pointer.
+ *   cb_peers_connect : join `nranks` (<= 16) as `rank`; boards by IPC handle (nranks x 64 bytes, entry
+ *                      `rank` ignored) or by pointer (contexts of this process); nranks == 0 disconnects.
+ *   cb_peers_counts  : running global totals after this rank's latest batch (waits, bounded, until every
+ *                      rank has posted it).  Counter 'claim-timeout' of the whole sharded pool,
+ *                      lib/pool.js:269-283. */
+typedef struct cb_global_counts {
+	uint64_t steps;  /* batches every rank has completed */
+	uint64_t drops, admits, n;
+} cb_global_counts;
+int cb_peers_board(cb_ctx *ctx, void *ipc_handle_out, size_t *len, void **local_ptr_out);
+int cb_peers_connect(cb_ctx *ctx, int nranks, int rank, const void *ipc_handles, void *const *local_ptrs);
+int cb_peers_counts(cb_ctx *ctx, cb_global_counts *out);
 
 /* One logical queue over R GPUs: batch k of rank r is the queue segment that
  * follows batch k of rank r-1 (and batch k of rank 0 follows batch k-1 of rank R-1), exactly as if
@@ -232,9 +277,9 @@ int cb_ring_connect(cb_ctx *ctx, int nranks, int rank, const void *next_ipc_hand
 
 /* ------------------------------------------------- pending-claim queue in HBM */
 
-/* The enqueue side and the event form of the drain loop.  STATUS: compiled,
- * specified (tools/proto_queue.py) and checked on CPU against the pinned model of the reference (tests/test_proto_queue.py), NOT yet
- * validated on hardware.
+/* The enqueue side and the event form of the drain loop.  Specified by
+ * tools/proto_queue.py, checked against the pinned model of the reference on CPU (tests/test_proto_queue.py)
+ * and on a B200 (tests/test_gpu_queue.py, tests/test_gpu_pool_mirror.py).
  *
  * cb_queue_push    n x ConnectionPool#claim (lib/pool.js:874-966): claimTimeout = getMaxIdle()
  *                  (lib/codel.js:109-118) per claim, idle slots first, the rest appended to the device
@@ -266,16 +311,23 @@ int cb_queue_push(cb_ctx *ctx, const int64_t *start_ns, size_t n, int64_t *first
 int cb_queue_cancel(cb_ctx *ctx, const int64_t *tickets, size_t n);
 int cb_queue_expire(cb_ctx *ctx, int64_t now_ns);
 int cb_queue_idle(cb_ctx *ctx, int64_t now_ns, uint64_t k_slots);
+/* up to k idle slots leave the idle queue (slots that went away with a topology change: setUnwanted on
+ * idle slots, lib/pool.js:601-631); *removed (may be NULL) = how many did */
+int cb_queue_trim_idle(cb_ctx *ctx, uint64_t k, uint64_t *removed);
 int cb_queue_results(cb_ctx *ctx, int64_t *triples, size_t cap_records, size_t *n_records);
 int cb_queue_info_get(cb_ctx *ctx, cb_queue_info *out);
 
 /* ------------------------------------------------------------- measurement */
 
 /* Per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg).
- * When enabled, every batch records events around each kernel; cb_profile_get
- * synchronises and returns accumulated milliseconds and launch counts. */
+ * on = 1: every batch records events around each kernel; cb_profile_get synchronises and returns
+ *         accumulated milliseconds and launch counts.
+ * on = 2: a device-buffer batch call launches ONLY its scan kernel, on the context's stream and without
+ *         events: the caller brackets a burst of such calls over different inputs with its own two events
+ *         (one kernel between two events also measures the launch latency; a burst averages it out).
+ * on = 0: off. */
 #define CB_K_SCAN 0    /* pass 1: timestamps -> CoDel classes / events (reads 16 B/claim) */
-#define CB_K_RESOLVE 1 /* prepare + commit kernels: episode resolution (serial over episodes, tiny) */
+#define CB_K_RESOLVE 1 /* resolve kernel (prepare + commit halves): episode resolution (serial over episodes, tiny) */
 #define CB_K_EMIT 2    /* pass 3: decisions + slots (writes 5 B/claim) */
 #define CB_K_COUNT 3
 int cb_profile_enable(cb_ctx *ctx, int on);

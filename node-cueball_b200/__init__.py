@@ -24,11 +24,11 @@ from .context import Context
 from .errors import ClaimHandleMisusedError, ClaimTimeoutError, NoBackendsError, PoolStoppingError
 from .pool import ConnectionPool, CueBallClaimHandle
 from .queue import Queue
-from .resolver import StaticIpResolver, process_backends, srvKey
+from .resolver import DeviceResolverState, StaticIpResolver, process_backends, srvKey
 from .utils import assertClaimDelay, currentMillis, planRebalance
 
 __all__ = ["ADMIT", "DROP", "SKIPPED", "F_WAITING", "F_EMPTY_AFTER", "PATH_PARALLEL", "PATH_SEQUENTIAL",
            "BALANCE_UNIFORM", "BALANCE_SRV_WEIGHTED", "CueballError", "ControlledDelay", "Context",
            "ClaimHandleMisusedError", "ClaimTimeoutError", "NoBackendsError", "PoolStoppingError",
            "ConnectionPool", "CueBallClaimHandle", "Queue", "assertClaimDelay", "currentMillis",
-           "planRebalance", "StaticIpResolver", "process_backends", "srvKey", "_native"]
+           "planRebalance", "StaticIpResolver", "DeviceResolverState", "process_backends", "srvKey", "_native"]

@@ -15,18 +15,20 @@ F_WAITING, F_EMPTY_AFTER = 1, 2
 PATH_PARALLEL, PATH_SEQUENTIAL = 0, 1
 BALANCE_UNIFORM, BALANCE_SRV_WEIGHTED = 0, 1
 K_SCAN, K_RESOLVE, K_EMIT, K_COUNT = 0, 1, 2, 3
+SRVKEY_LEN = 28
 
 # every symbol include/cueball_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
     "cb_create", "cb_destroy", "cb_last_error", "cb_abi_version", "cb_set_stream", "cb_set_pipeline_depth", "cb_join", "cb_synchronize",
     "cb_host_alloc", "cb_host_free", "cb_codel_init", "cb_codel_get_state", "cb_codel_set_state",
     "cb_codel_empty", "cb_codel_max_idle", "cb_admit_batch", "cb_admit_batch_ms", "cb_admit_batch_dev",
-    "cb_admit_batch_ms_dev", "cb_batch_stats_get", "cb_codel_overloaded", "cb_backends_set",
+    "cb_admit_batch_ms_dev", "cb_batch_stats_get", "cb_codel_overloaded", "cb_codel_overloaded_ms", "cb_backends_set",
     "cb_backend_added", "cb_backend_removed", "cb_reshuffle", "cb_backends_get", "cb_plan_rebalance",
     "cb_comm_unique_id", "cb_comm_init", "cb_allreduce_counts", "cb_profile_enable", "cb_profile_get",
     "cb_launch_count", "cb_debug_timestamps", "cb_debug_lane_timestamps",
-    "cb_ring_mailbox", "cb_ring_connect",
-    "cb_queue_create", "cb_queue_push", "cb_queue_cancel", "cb_queue_expire", "cb_queue_idle", "cb_queue_results",
+    "cb_srv_keys", "cb_resolver_process",
+    "cb_ring_mailbox", "cb_ring_connect", "cb_peers_board", "cb_peers_connect", "cb_peers_counts",
+    "cb_queue_create", "cb_queue_push", "cb_queue_cancel", "cb_queue_expire", "cb_queue_idle", "cb_queue_trim_idle", "cb_queue_results",
     "cb_queue_info_get",
 ]
 
@@ -48,6 +50,10 @@ class BatchStats(C.Structure):
                 ("global_drops", C.c_uint64), ("global_admits", C.c_uint64), ("global_n", C.c_uint64),
                 ("state", CodelState), ("path", C.c_int32), ("n_events", C.c_uint32),
                 ("n_intervals", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class GlobalCounts(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("drops", C.c_uint64), ("admits", C.c_uint64), ("n", C.c_uint64)]
 
 
 class QueueInfo(C.Structure):
@@ -110,6 +116,7 @@ def lib():
         getattr(L, name).argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
     L.cb_batch_stats_get.argtypes = [vp, C.POINTER(BatchStats)]
     L.cb_codel_overloaded.argtypes = [vp, i64, i64, C.POINTER(C.c_int)]
+    L.cb_codel_overloaded_ms.argtypes = [vp, dbl, dbl, C.POINTER(C.c_int)]
     L.cb_backends_set.argtypes = [vp, vp, i32, vp, i32, C.c_int]
     L.cb_backend_added.argtypes = [vp, i32, vp, dbl]
     L.cb_backend_removed.argtypes = [vp, i32]
@@ -128,11 +135,17 @@ def lib():
     L.cb_debug_lane_timestamps.argtypes = [vp, C.c_int, C.POINTER(u64)]
     L.cb_ring_mailbox.argtypes = [vp, vp, C.POINTER(sz), C.POINTER(vp)]
     L.cb_ring_connect.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.cb_srv_keys.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(C.c_char_p), sz, vp]
+    L.cb_resolver_process.argtypes = [vp, vp, sz, vp, vp, C.POINTER(i32), vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.cb_peers_board.argtypes = [vp, vp, C.POINTER(sz), C.POINTER(vp)]
+    L.cb_peers_connect.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.cb_peers_counts.argtypes = [vp, C.POINTER(GlobalCounts)]
     L.cb_queue_create.argtypes = [vp, sz, sz, u64]
     L.cb_queue_push.argtypes = [vp, vp, sz, C.POINTER(i64), vp]
     L.cb_queue_cancel.argtypes = [vp, vp, sz]
     L.cb_queue_expire.argtypes = [vp, i64]
     L.cb_queue_idle.argtypes = [vp, i64, u64]
+    L.cb_queue_trim_idle.argtypes = [vp, u64, C.POINTER(u64)]
     L.cb_queue_results.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.cb_queue_info_get.argtypes = [vp, C.POINTER(QueueInfo)]
     _lib = L

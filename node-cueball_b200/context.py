@@ -25,6 +25,8 @@ class Context(object):
             raise N.CueballError(rc, msg.decode() if msg else "cb_create failed")
         self.device = int(device)
 
+    _n_backends_known = 0  # backends in the context's resolver map (sizes cb_resolver_process's 'removed' buffers)
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.cb_destroy(self._h)
@@ -71,6 +73,12 @@ class Context(object):
     def overloaded(self, start_ns, now_ns):
         out = C.c_int()
         self._ck(self._L.cb_codel_overloaded(self._h, int(start_ns), int(now_ns), C.byref(out)))
+        return bool(out.value)
+
+    def overloaded_ms(self, start_ms, now_ms):
+        """ControlledDelay#overloaded with the reference's own double-millisecond clocks."""
+        out = C.c_int()
+        self._ck(self._L.cb_codel_overloaded_ms(self._h, float(start_ms), float(now_ms), C.byref(out)))
         return bool(out.value)
 
     # ---------------------------------------------------------------- batches
@@ -207,7 +215,9 @@ class Context(object):
 
     # ------------------------------------------------------------ measurement
     def profile_enable(self, on=True):
-        self._ck(self._L.cb_profile_enable(self._h, 1 if on else 0))
+        # True / 1: CUDA events around each kernel; 2: launch ONLY the scan kernel (the caller times a burst of
+        # back-to-back launches with its own events on the context's stream); False / 0: off
+        self._ck(self._L.cb_profile_enable(self._h, int(on)))
 
     def profile_get(self):
         ms = (C.c_double * N.K_COUNT)()
@@ -242,6 +252,11 @@ class Context(object):
     def queue_idle(self, now_ns, k_slots):
         self._ck(self._L.cb_queue_idle(self._h, int(now_ns), int(k_slots)))
 
+    def queue_trim_idle(self, k):
+        out = C.c_uint64()
+        self._ck(self._L.cb_queue_trim_idle(self._h, int(k), C.byref(out)))
+        return int(out.value)
+
     def queue_results(self):
         """Resolution records since the last call: int64 array of (ticket, code, slot) rows."""
         info = self.queue_info()
@@ -268,6 +283,63 @@ class Context(object):
         hb = C.create_string_buffer(next_handle, len(next_handle)) if next_handle else None
         self._ck(self._L.cb_ring_connect(self._h, int(nranks), int(rank), hb,
                                          C.c_void_p(next_ptr) if next_ptr else None))
+
+    # ------------------------------------------------ resolver ingestion
+    def srv_keys(self, backends):
+        """srvKey() of a list of {name, port, address} (lib/resolver.js:1157-1171), SHA-1 on the device."""
+        n = len(backends)
+        if n == 0:
+            return []
+        names = (C.c_char_p * n)(*[str(b["name"]).encode() for b in backends])
+        addrs = (C.c_char_p * n)(*[str(b["address"]).encode() for b in backends])
+        ports = (C.c_int32 * n)(*[int(b["port"]) for b in backends])
+        out = C.create_string_buffer(n * N.SRVKEY_LEN)
+        self._ck(self._L.cb_srv_keys(self._h, names, ports, addrs, n, out))
+        raw = out.raw
+        return [raw[k * N.SRVKEY_LEN:(k + 1) * N.SRVKEY_LEN].decode() for k in range(n)]
+
+    def resolver_process(self, keys):
+        """state_process (lib/resolver.js:1024-1108) on the context's backend map.  Returns
+        (removed [(key, id)], added [(key, id, input row)], empty_set)."""
+        n = len(keys)
+        blob = "".join(keys).encode()
+        assert len(blob) == n * N.SRVKEY_LEN
+        cap = n + self._n_backends_known + 1
+        rid = (C.c_int32 * cap)()
+        rkeys = C.create_string_buffer(cap * N.SRVKEY_LEN)
+        aid, arow = (C.c_int32 * (n + 1))(), (C.c_int32 * (n + 1))()
+        nr, na, empty = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self._L.cb_resolver_process(self._h, blob, n, rid, rkeys, C.byref(nr), aid, arow, C.byref(na), C.byref(empty)))
+        removed = [(rkeys.raw[j * N.SRVKEY_LEN:(j + 1) * N.SRVKEY_LEN].decode(), rid[j]) for j in range(nr.value)]
+        added = [(keys[arow[j]], aid[j], arow[j]) for j in range(na.value)]
+        self._n_backends_known += na.value - nr.value
+        return removed, added, bool(empty.value)
+
+    # ------------------------------------------------ per-batch global counts over peer memory
+    def peers_board(self):
+        """(ipc_handle: bytes, local_ptr: int) of this context's count board."""
+        buf = C.create_string_buffer(64)
+        ln = C.c_size_t(64)
+        ptr = C.c_void_p()
+        self._ck(self._L.cb_peers_board(self._h, buf, C.byref(ln), C.byref(ptr)))
+        return buf.raw[:ln.value], int(ptr.value)
+
+    def peers_connect(self, nranks, rank, handles=None, ptrs=None):
+        """handles: list of nranks 64-byte IPC handles (other processes); ptrs: list of nranks device
+        pointers (contexts of this process).  nranks == 0 disconnects."""
+        hb = None
+        if handles:
+            raw = b"".join((h if h is not None else b"\0" * 64).ljust(64, b"\0") for h in handles)
+            hb = C.create_string_buffer(raw, len(raw))
+        pa = None
+        if ptrs:
+            pa = (C.c_void_p * len(ptrs))(*[C.c_void_p(p) if p else None for p in ptrs])
+        self._ck(self._L.cb_peers_connect(self._h, int(nranks), int(rank), hb, pa))
+
+    def peers_counts(self):
+        out = N.GlobalCounts()
+        self._ck(self._L.cb_peers_counts(self._h, C.byref(out)))
+        return out
 
     def debug_lane_timestamps(self, lane):
         out = (C.c_uint64 * 16)()

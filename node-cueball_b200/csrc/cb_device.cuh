@@ -39,6 +39,7 @@ struct BatchCtl {
 	unsigned long long n, drops, admits, skipped;
 	unsigned long long cursor0;    // admit cursor before this batch (read by the emit kernel)
 	unsigned long long gcounts[4]; // {drops, admits, n, CoDel-level drops}: [0..2] = allreduce buffer
+	unsigned long long lcounts[4]; // this rank's {drops, admits, n} of the batch (posted to the peer boards)
 	// set by the scan kernel, consumed + reset by the resolve kernel
 	unsigned int nonmono;          // clock went backwards inside the batch
 	unsigned int overflow;         // a tile found more than EVK events

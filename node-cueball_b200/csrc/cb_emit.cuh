@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 				g->tot_admits += admits;
 				bc->gcounts[0] = drops;
 				bc->gcounts[1] = admits;
+				bc->lcounts[0] = drops;
+				bc->lcounts[1] = admits;
 				chain_post(p.link, g); // the next batch's commit may read the cursor now
 			}
 		}

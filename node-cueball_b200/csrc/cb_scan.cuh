@@ -11,16 +11,23 @@
 //       above                : F' = F ? F : now+100        PASS(now+100)
 // which compose associatively ("last CONST wins, then the first PASS fills a zero").  Every
 // non-zero F is `now[a] + 100` for some claim index a, so compositions are carried as
-// INDICES (integer-only, one 64-bit code per warp chunk and per tile) and turned into doubles
+// INDICES (integer-only, one 64-bit code per chunk and per tile) and turned into doubles
 // only where a claim's class needs the value.
 //
-// Layout: a CTA owns a tile of 2048 consecutive claims, a warp a chunk of 256 = 4 rows of 64;
-// in a row lane l owns claims 2l and 2l+1, i.e. one fully coalesced 128-bit load per array
-// per row, no shared-memory staging.  Phase 1 (integers only) classifies above/below --
-// sojourn vs target is decided on the int64 nanoseconds whenever the gap to the target
-// exceeds the worst-case rounding of the millisecond doubles, and exactly as
-// utils.currentMillis() (lib/utils.js:198-204) otherwise -- and builds the row/warp/tile
-// compositions.  Phase 2 touches FP64 only in rows that contain above-target claims.
+// Execution (round 2): every WARP streams tiles of its own.  A tile is 2048 consecutive claims,
+// walked as 8 chunks of 256 = 4 rows of 64; in a row lane l owns claims 2l and 2l+1.  The chunks
+// of a warp's tiles flow through a private ring of SC_NST shared-memory stages filled by TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx, issued by the warp's own lane 0 two chunks ahead of
+// the one being worked on), so the HBM stream never waits for the arithmetic and no warp ever
+// waits for another: there is no CTA-wide barrier, no cross-warp exchange, and what the
+// tile-level composition needs from the previous chunk is simply still in registers.  A stage
+// also holds the two claims in front of its chunk (16 B): the clock must not step back across a
+// chunk boundary and the class of the claim before a tile decides whether the tile anchors itself.
+// Phase 1 (integers only) classifies above/below -- sojourn vs target is decided on the int64
+// nanoseconds whenever the gap to the target exceeds the worst-case rounding of the millisecond
+// doubles, and exactly as utils.currentMillis() (lib/utils.js:198-204) otherwise -- and builds the
+// chunk compositions from ballots.  Phase 2 touches FP64 only in rows that contain above-target
+// claims whose F is determined inside the tile.
 //
 // Tiles are INDEPENDENT: there is no look-back.  A tile classifies only the claims whose F
 // is determined inside the tile (everything from its first CONST claim on).  Its leading PASS
@@ -37,29 +44,33 @@
 
 namespace cb {
 
-#ifndef CB_SCAN_MINBLOCKS // resident CTAs per SM the register budget is sized for (tuning knob:
-#define CB_SCAN_MINBLOCKS 4 // `make -B EXTRA=-DCB_SCAN_MINBLOCKS=5`; 4 = 64 registers, measured in round 1)
+constexpr int ROWS = 4;               // rows of 64 claims per chunk
+constexpr int CHUNK = ROWS * 64;      // 256 claims: one stage of a warp's ring
+constexpr int CHUNKS = TILE / CHUNK;  // 8 chunks per tile
+static_assert(CHUNK * CHUNKS == TILE, "tile geometry");
+
+// streaming geometry (tuning knobs: `make -B EXTRA="-DCB_SCAN_WARPS=.. -DCB_SCAN_NST=.. -DCB_SCAN_MINBLOCKS=.."`)
+#ifndef CB_SCAN_WARPS
+#define CB_SCAN_WARPS 8 // warps per CTA; each streams tiles of its own
 #endif
-constexpr int ROWS = 4;            // rows of 64 claims per warp chunk
-constexpr int CHUNK = ROWS * 64;   // 256 claims per warp
-static_assert(CHUNK * WARPS == TILE, "tile geometry");
+#ifndef CB_SCAN_NST
+#define CB_SCAN_NST 3 // chunk stages per warp
+#endif
+#ifndef CB_SCAN_MINBLOCKS
+#define CB_SCAN_MINBLOCKS 2 // resident CTAs per SM the register budget is sized for
+#endif
+constexpr int SC_WARPS = CB_SCAN_WARPS;
+constexpr int SC_TPB = SC_WARPS * 32;
+constexpr int SC_NST = CB_SCAN_NST;
+constexpr int SC_LEAD = 16;                      // the two claims in front of the chunk
+constexpr int SC_ARR = SC_LEAD + CHUNK * 8;      // one array of a stage: lead + 256 x 8 B
+constexpr int SC_STAGE = 2 * SC_ARR;             // start array, then now array
+constexpr int SC_SMEM = SC_WARPS * SC_NST * SC_STAGE; // dynamic shared memory of a scan CTA
 
 // index-coded F: 0 = F is 0, 1 = the batch's carried-in F, a+2 = now[a] + 100
 constexpr unsigned long long CODE_ZERO = 0, CODE_CARRY = 1;
 constexpr unsigned long long DESC_CODE_MASK = (1ull << 40) - 1;
 constexpr unsigned int FC_NONE = 0xffffffffu; // tile record: no CONST claim in the tile
-constexpr int EVW = 4;                        // class-change events one warp chunk can hold
-
-// named barriers: arrive without waiting / wait for all TPB threads
-#ifndef CB_EMU
-__device__ __forceinline__ void bar_arrive(int id) {
-	__threadfence_block();
-	asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(TPB) : "memory");
-}
-__device__ __forceinline__ void bar_sync(int id) {
-	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TPB) : "memory");
-}
-#endif
 
 struct IAgg { // composed F-update in index form: F_out = isconst ? code : (F_in ? F_in : code)
 	bool isconst;
@@ -73,17 +84,42 @@ __device__ __forceinline__ IAgg icompose(const IAgg &a, const IAgg &b) { // a fi
 	r.code = (a.code != CODE_ZERO) ? a.code : b.code;
 	return r;
 }
-__device__ __forceinline__ unsigned long long iapply(const IAgg &a, unsigned long long in_code) {
-	return a.isconst ? a.code : (in_code != CODE_ZERO ? in_code : a.code);
-}
 
-#ifndef CB_EMU
-__device__ __forceinline__ uint4 ld_stream_v4(const void *p) {
-	uint4 r;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-	             : "l"(p));
-	return r;
+#ifndef CB_EMU // tests/emu/cuda_emu.h supplies host versions
+__device__ __forceinline__ unsigned int sc_smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar, unsigned int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { // make the initialised barriers visible to the async proxy
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, unsigned int bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sc_smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16); streamed data:
+// evict-first in L2
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *mbar,
+    unsigned long long policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+	                 sc_smem_u32(dst)),
+	    "l"(src), "r"(bytes), "r"(sc_smem_u32(mbar)), "l"(policy)
+	    : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned int parity) {
+	unsigned int done = 0;
+	while (!done) {
+		asm volatile("{\n\t.reg .pred q;\n\t"
+		             "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+		             "selp.u32 %0, 1, 0, q;\n\t}"
+		             : "=r"(done)
+		             : "r"(sc_smem_u32(mbar)), "r"(parity)
+		             : "memory");
+	}
 }
 #endif
 
@@ -100,61 +136,29 @@ struct ScanParams {
 	unsigned int *rec_cend;        // [tiles] valid when rec_fc != FC_NONE
 	void *tile_now0;               // [tiles] raw clock of the tile's first claim (coarse search index)
 	unsigned int *ev_count;   // [tiles]
-	unsigned long long *ev;   // [tiles][EVK]  (index << 2) | class
-	int vec_ok;               // start/now 16-byte aligned
+	unsigned long long *ev;   // [tiles][EVK]  (index << 2) | class, in index order
+	int vec_ok;               // start/now 16-byte aligned: chunks are staged by TMA bulk copies
 	long long target_ns;      // target in ns (integer-domain sojourn test)
+};
+
+template <typename T> struct alignas(16) Pair {
+	T x, y;
 };
 
 template <bool NS> struct Raw;
 template <> struct Raw<true> {
 	using t = long long;
-	// sojourn vs target in the integer domain; returns 0 below, 1 above, 2 = too close
-	static __device__ __forceinline__ int quick(long long st, long long nw, long long tgt) {
-		// e = sojourn - target in ns; the double-millisecond comparison of lib/codel.js:35-37 can
-		// only disagree with sign(e) when |e| < m, m = 2 + now>>50 ns (> 2.5 ulp(now_ms))
-		const unsigned int mh = (unsigned int)(nw >> 50);
-		const long long s = nw - st - (tgt - 2) + (long long)mh; // e + m
-		if (s < 0)
-			return 0; // e < -m: certainly below target
-		if ((unsigned long long)s >= 2ull * (mh + 2u))
-			return 1; // e >= m: certainly at/above target
-		return 2;
-	}
-	// the same test against two precomputed bounds (lo = tgt - m, hi = tgt + m for a margin m that
-	// is at least every claim's own 2 + now>>50): sojourn < lo -> 0, sojourn >= hi -> 1, else 2
-	static __device__ __forceinline__ int quick2(long long st, long long nw, long long lo, long long hi) {
-		const long long e = nw - st;
-		return e < lo ? 0 : (e >= hi ? 1 : 2);
-	}
-	static __device__ __forceinline__ long long margin_of(long long hi_or) { return 2 + (hi_or >> 18); }
-	static __device__ __forceinline__ long long hi_word(long long x) { return x >> 32; }
-	static __device__ __forceinline__ bool less(long long a, long long b) { return a < b; }
+	static __device__ __forceinline__ long long lowest() { return (long long)0x8000000000000000ull; }
 };
 template <> struct Raw<false> {
 	using t = double;
-	static __device__ __forceinline__ int quick(double, double, long long) { return 2; }
-	static __device__ __forceinline__ int quick2(double, double, long long, long long) { return 2; }
-	static __device__ __forceinline__ long long margin_of(long long) { return 0; }
-	static __device__ __forceinline__ long long hi_word(double) { return 0; }
-	static __device__ __forceinline__ bool less(double a, double b) { return a < b; }
+	static __device__ __forceinline__ double lowest() { return -1.0 / 0.0; }
 };
 
+// lib/codel.js:35-37 in the clock's own unit: sojourn >= target, compared as the reference compares it
 template <bool NS>
-__device__ __forceinline__ bool is_above(typename Raw<NS>::t st, typename Raw<NS>::t nw, long long tgt_ns,
-    double target) {
-	const int q = Raw<NS>::quick(st, nw, tgt_ns);
-	if (q != 2)
-		return q == 1;
-	return !(__dsub_rn(TimeIn<NS>::to_ms(nw), TimeIn<NS>::to_ms(st)) < target); // lib/codel.js:35-37
-}
-
-template <bool NS>
-__device__ __forceinline__ bool is_above2(typename Raw<NS>::t st, typename Raw<NS>::t nw, long long lo, long long hi,
-    double target) {
-	const int q = Raw<NS>::quick2(st, nw, lo, hi);
-	if (q != 2)
-		return q == 1;
-	return !(__dsub_rn(TimeIn<NS>::to_ms(nw), TimeIn<NS>::to_ms(st)) < target); // lib/codel.js:35-37
+__device__ __forceinline__ bool is_above(typename Raw<NS>::t st, typename Raw<NS>::t nw, double target) {
+	return !(__dsub_rn(TimeIn<NS>::to_ms(nw), TimeIn<NS>::to_ms(st)) < target);
 }
 
 // value of an index-coded F
@@ -169,182 +173,180 @@ __device__ __forceinline__ double materialise(unsigned long long code, const voi
 	return __dadd_rn(TimeIn<NS>::to_ms(v), CODEL_INTERVAL);
 }
 
-template <bool NS, bool FLAGS>
-__global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const ScanParams p) {
+// ---- one chunk of 256 claims, already in the stage `st` --------------------------------------
+// Tile-level state a warp carries from chunk to chunk (all lanes hold the same values).
+struct TileState {
+	IAgg agg;             // composition of the chunks seen so far
+	unsigned int fc;      // tile-local position of the first CONST claim, or FC_NONE
+	bool known;           // F in front of the next claim is determined inside this tile
+	double F;             // ... its value (meaningful when known)
+	int c_last;           // class of the claim before the next row
+	unsigned int evn;     // class-change events found so far
+	unsigned int carry_mk; // FLAGS: the claim before the next row carries an empty() marker
+};
+
+template <bool NS, bool FLAGS, bool FULL>
+__device__ __forceinline__ void scan_chunk(const ScanParams &p, const unsigned char *st, unsigned long long t,
+    unsigned long long cs, int sub, int lane, unsigned int lt_mask, TileState &T, bool &nonmono,
+    unsigned long long &last_marker) {
 	using raw_t = typename Raw<NS>::t;
-	__shared__ unsigned long long s_wagg[WARPS]; // isconst << 63 | code
-	__shared__ unsigned int s_wfc[WARPS];        // chunk-local position of the warp's first CONST claim
-	__shared__ unsigned int s_evn[WARPS];                 // per-warp event counters (no cross-warp init race)
-	__shared__ unsigned long long s_ev[WARPS][EVW];
-	__shared__ unsigned int s_leftclosed;                 // the claim before the tile is below target
-
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const unsigned long long t = blockIdx.x;
-	if (tid == 0 && blockIdx.x == 0)
-		p.b->dbg[8] = gtimer(); // timeline stamp (tools/pipeline_timeline.py)
-	const unsigned long long ts = t * (unsigned long long)TILE;
-	const unsigned long long cs = ts + (unsigned long long)warp * CHUNK; // chunk start
-	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
-	const raw_t *gnow = reinterpret_cast<const raw_t *>(p.now);
+	using pair_t = Pair<raw_t>;
+	const raw_t *ss = reinterpret_cast<const raw_t *>(st + SC_LEAD);
+	const raw_t *sn = reinterpret_cast<const raw_t *>(st + SC_ARR + SC_LEAD);
 	const double target = p.target;
-	const long long tgt_ns = p.target_ns;
-	const unsigned int lt_mask = (1u << lane) - 1u;
-	if (lane == 0)
-		s_evn[warp] = 0;
-	__syncwarp();
-
-	// ---- loads: one 128-bit load per array per row (claims 2l, 2l+1) -----------------------
-	raw_t rs[ROWS][2], rn[ROWS][2];
-	unsigned int fl[ROWS]; // this lane's two flag bytes per row
-	const bool full = (cs + CHUNK <= p.n);
-	if (full && p.vec_ok) {
-		uint4 a[ROWS], b[ROWS];
-#pragma unroll
-		for (int r = 0; r < ROWS; r++)
-			a[r] = ld_stream_v4(gstart + cs + r * 64 + 2 * lane);
-#pragma unroll
-		for (int r = 0; r < ROWS; r++)
-			b[r] = ld_stream_v4(gnow + cs + r * 64 + 2 * lane);
-#pragma unroll
-		for (int r = 0; r < ROWS; r++) {
-			unsigned long long x0 = ((unsigned long long)a[r].y << 32) | a[r].x;
-			unsigned long long x1 = ((unsigned long long)a[r].w << 32) | a[r].z;
-			unsigned long long y0 = ((unsigned long long)b[r].y << 32) | b[r].x;
-			unsigned long long y1 = ((unsigned long long)b[r].w << 32) | b[r].z;
-			rs[r][0] = *reinterpret_cast<raw_t *>(&x0);
-			rs[r][1] = *reinterpret_cast<raw_t *>(&x1);
-			rn[r][0] = *reinterpret_cast<raw_t *>(&y0);
-			rn[r][1] = *reinterpret_cast<raw_t *>(&y1);
-		}
-	} else {
-#pragma unroll
-		for (int r = 0; r < ROWS; r++) {
-#pragma unroll
-			for (int j = 0; j < 2; j++) {
-				const unsigned long long i = cs + r * 64 + 2 * lane + j;
-				rs[r][j] = (i < p.n) ? gstart[i] : raw_t(0);
-				rn[r][j] = (i < p.n) ? gnow[i] : raw_t(0);
-			}
-		}
+	int nvt = CHUNK; // valid claims in the chunk
+	if (!FULL) {
+		const unsigned long long rem = p.n - cs;
+		nvt = rem >= (unsigned long long)CHUNK ? CHUNK : (int)rem;
 	}
+	// FLAGS: this lane's two flag bytes per row, straight from global memory (1 B/claim)
+	unsigned int fl[ROWS];
 #pragma unroll
 	for (int r = 0; r < ROWS; r++) {
 		fl[r] = 0x0101u; // waiting, no markers
 		if (FLAGS) {
 			const unsigned long long i = cs + r * 64 + 2 * lane;
-			unsigned int f0 = (i < p.n) ? p.flags[i] : 0u;
-			unsigned int f1 = (i + 1 < p.n) ? p.flags[i + 1] : 0u;
+			const unsigned int f0 = (FULL || i < p.n) ? p.flags[i] : 0u;
+			const unsigned int f1 = (FULL || i + 1 < p.n) ? p.flags[i + 1] : 0u;
 			fl[r] = f0 | (f1 << 8);
 		}
 	}
-	// The claim just before this warp's chunk (same address in every lane: one broadcast
-	// transaction): its class may end an "ok" run exactly at the chunk boundary, its marker
-	// resets F in front of our first claim, and the clock must not step back across it.
-	const bool have_prev = (cs > 0) && (cs < p.n);
-	raw_t prev_now = raw_t(0);
-	unsigned int prev_bits = 0; // bit0 above, bit1 marker-before, bit2 own marker
-	if (have_prev) {
-		const raw_t pstart = gstart[cs - 1];
-		prev_now = gnow[cs - 1];
-		const unsigned int pf = FLAGS ? p.flags[cs - 1] : 1u, ppf = (FLAGS && cs >= 2) ? p.flags[cs - 2] : 0u;
-		prev_bits = (is_above<NS>(pstart, prev_now, tgt_ns, target) ? 1u : 0u) | ((ppf & F_EMPTY_AFTER) ? 2u : 0u) |
-		    ((pf & F_EMPTY_AFTER) ? 4u : 0u);
-	}
 
-	// ---- phase 1: above bits, CONST/PASS types (integers only) --------------------------------
-	// One margin for all of this lane's claims: the OR of their clocks' high words bounds each
-	// claim's own now>>50 from above, and a wider margin only sends a claim within a few ns of the
-	// target to the exact double comparison.  (A negative clock makes the margin negative: every
-	// claim then takes the exact path.)
-	long long q_lo, q_hi;
-	{
-		long long hi_or = 0;
-#pragma unroll
-		for (int r = 0; r < ROWS; r++)
-			hi_or |= Raw<NS>::hi_word(rn[r][0]) | Raw<NS>::hi_word(rn[r][1]);
-		const long long m = Raw<NS>::margin_of(hi_or);
-		q_lo = tgt_ns - m;
-		q_hi = tgt_ns + m;
-		if (m < 2) { // negative clocks: no shortcut
-			q_lo = (long long)0x8000000000000000ull;
-			q_hi = (long long)0x7fffffffffffffffull;
+	// ---- phase 1: above bits (integers only on the nanosecond clock) ----------------------------
+	// e = sojourn - target in ns.  The double-millisecond comparison of lib/codel.js:35-37 can only
+	// disagree with sign(e) when |e| < m_i = 2 + now_i>>50 ns (> 2.5 ulp(now_ms)).  One margin for the
+	// chunk: its last clock bounds every now_i from above when the clock is monotone (and when it is
+	// not, the batch takes the exact sequential path and nothing computed here is used).  A negative
+	// first clock switches the shortcut off.  d = e + m: d < 0 below, d >= 2m above, else exact.
+	unsigned int mine = 0; // bit 2r / 2r+1: this lane's claim of row r, slot 0 / 1, is at or above target
+	bool near = false;
+	long long lo = 0;
+	unsigned long long W = 0;
+	if (NS) {
+		const long long nfirst = *reinterpret_cast<const long long *>(sn);
+		const long long nlast = *reinterpret_cast<const long long *>(sn + (nvt - 1));
+		const long long m = 2 + (nlast >> 50);
+		lo = p.target_ns - m;
+		W = 2ull * (unsigned long long)m;
+		if (nfirst < 0 || nlast < 0) { // a negative clock: no shortcut, every claim is compared exactly
+			W = ~0ull;
+			near = true;
 		}
 	}
-	unsigned int A0[ROWS], A1[ROWS], C0[ROWS], C1[ROWS]; // ballots: above / CONST-type, per claim slot
-	int nv[ROWS];                                        // valid claims in the row
-	bool nonmono = false;
-	unsigned long long last_marker = 0;
-	auto phase1 = [&](auto full_tag) {
-		constexpr bool FULL = decltype(full_tag)::value; // every claim of the chunk exists
-		unsigned int carry_mk = (prev_bits >> 2) & 1u;   // marker of the claim before the row (warp-uniform)
+#pragma unroll
+	for (int r = 0; r < ROWS; r++) {
+		const pair_t S = *reinterpret_cast<const pair_t *>(ss + r * 64 + 2 * lane);
+		const pair_t N = *reinterpret_cast<const pair_t *>(sn + r * 64 + 2 * lane);
+		const raw_t P = sn[r * 64 + 2 * lane - 1]; // the claim before this lane's pair (the lead for lane 0 of row 0)
+		const bool v0 = FULL || (r * 64 + 2 * lane < nvt), v1 = FULL || (r * 64 + 2 * lane + 1 < nvt);
+		bool ab0, ab1;
+		if (NS) {
+			const long long d0 = (long long)N.x - (long long)S.x - lo, d1 = (long long)N.y - (long long)S.y - lo;
+			ab0 = d0 >= 0; // provisional for a near claim: redone below
+			ab1 = d1 >= 0;
+			near |= (v0 && (unsigned long long)d0 < W) || (v1 && (unsigned long long)d1 < W);
+		} else {
+			ab0 = is_above<NS>(S.x, N.x, target);
+			ab1 = is_above<NS>(S.y, N.y, target);
+		}
+		mine |= ((v0 && ab0) ? 1u : 0u) << (2 * r);
+		mine |= ((v1 && ab1) ? 1u : 0u) << (2 * r + 1);
+		// monotone clock (raw domain: ns-monotone implies ms-monotone)
+		if ((v0 && N.x < P) || (v1 && N.y < N.x))
+			nonmono = true;
+	}
+	if (NS && __any_sync(0xffffffffu, near)) { // some claim within the margin of the target: exact comparison
 #pragma unroll
 		for (int r = 0; r < ROWS; r++) {
-			const unsigned long long rbase = cs + r * 64;
-			if (FULL) {
-				nv[r] = 64;
-			} else {
-				const long long rem = (long long)p.n - (long long)rbase;
-				nv[r] = rem >= 64 ? 64 : (rem > 0 ? (int)rem : 0);
+			const pair_t S = *reinterpret_cast<const pair_t *>(ss + r * 64 + 2 * lane);
+			const pair_t N = *reinterpret_cast<const pair_t *>(sn + r * 64 + 2 * lane);
+			const bool v0 = FULL || (r * 64 + 2 * lane < nvt), v1 = FULL || (r * 64 + 2 * lane + 1 < nvt);
+			const long long d0 = (long long)N.x - (long long)S.x - lo, d1 = (long long)N.y - (long long)S.y - lo;
+			if (v0 && ((unsigned long long)d0 < W || W == ~0ull)) {
+				const bool ab = is_above<NS>(S.x, N.x, target); // lib/codel.js:35-37
+				mine = (mine & ~(1u << (2 * r))) | ((ab ? 1u : 0u) << (2 * r));
 			}
-			const bool v0 = FULL || (2 * lane < nv[r]), v1 = FULL || (2 * lane + 1 < nv[r]);
-			// integer test first; the exact double comparison only if some claim of the row is within
-			// the margin of the target (one warp-uniform branch per row instead of one per claim)
-			const int q0 = Raw<NS>::quick2(rs[r][0], rn[r][0], q_lo, q_hi);
-			const int q1 = Raw<NS>::quick2(rs[r][1], rn[r][1], q_lo, q_hi);
-			bool ab0 = v0 && (q0 == 1), ab1 = v1 && (q1 == 1);
-			if (__any_sync(0xffffffffu, (v0 && q0 == 2) || (v1 && q1 == 2))) {
-				if (v0 && q0 == 2)
-					ab0 = !(__dsub_rn(TimeIn<NS>::to_ms(rn[r][0]), TimeIn<NS>::to_ms(rs[r][0])) < target); // lib/codel.js:35-37
-				if (v1 && q1 == 2)
-					ab1 = !(__dsub_rn(TimeIn<NS>::to_ms(rn[r][1]), TimeIn<NS>::to_ms(rs[r][1])) < target);
+			if (v1 && ((unsigned long long)d1 < W || W == ~0ull)) {
+				const bool ab = is_above<NS>(S.y, N.y, target);
+				mine = (mine & ~(2u << (2 * r))) | ((ab ? 2u : 0u) << (2 * r));
 			}
-			A0[r] = __ballot_sync(0xffffffffu, ab0);
-			A1[r] = __ballot_sync(0xffffffffu, ab1);
-			if (FLAGS) {
-				const unsigned int mk0 = (fl[r] >> 1) & 1u, mk1 = (fl[r] >> 9) & 1u; // own markers
-				unsigned int up = __shfl_up_sync(0xffffffffu, mk1, 1);
-				if (lane == 0)
-					up = carry_mk;
-				carry_mk = __shfl_sync(0xffffffffu, mk1, 31);
-				if (v1 && mk1)
-					last_marker = rbase + 2 * lane + 2;
-				else if (v0 && mk0)
-					last_marker = rbase + 2 * lane + 1;
-				C0[r] = __ballot_sync(0xffffffffu, v0 && (!ab0 || up != 0));
-				C1[r] = __ballot_sync(0xffffffffu, v1 && (!ab1 || mk0 != 0));
-			} else if (FULL) {
-				C0[r] = ~A0[r]; // without markers a claim is CONST-type iff it is below target
-				C1[r] = ~A1[r];
-			} else {
-				C0[r] = __ballot_sync(0xffffffffu, v0) & ~A0[r];
-				C1[r] = __ballot_sync(0xffffffffu, v1) & ~A1[r];
-			}
-			// monotone clock (raw domain: ns-monotone implies ms-monotone)
-			// the claim before this lane's pair: lane l-1's second claim; for lane 0 it is lane 31's
-			// second claim of the previous row (or the claim before the chunk) -- one rotated shuffle
-			// in which lane 31 (read by lane 0 only) offers that value
-			const raw_t offer = (lane == 31) ? (r > 0 ? rn[r > 0 ? r - 1 : 0][1] : prev_now) : rn[r][1];
-			const raw_t prevn = __shfl_sync(0xffffffffu, offer, (lane + 31) & 31);
-			const bool haveprevn = (lane > 0) || (r > 0) || have_prev;
-			if ((v1 && Raw<NS>::less(rn[r][1], rn[r][0])) || (v0 && haveprevn && Raw<NS>::less(rn[r][0], prevn)))
-				nonmono = true;
 		}
-	};
-	if (full)
-		phase1(std::true_type{});
-	else
-		phase1(std::false_type{});
+	}
+	// ---- uniform chunks (nearly all of them): no ballots, no per-row work ----------------------------
+	if (FULL && !FLAGS) {
+		if (__all_sync(0xffffffffu, mine == 0u)) {
+			// every claim is below target: CONST(0) throughout, class 0, F ends at 0
+			T.agg.isconst = true;
+			T.agg.code = CODE_ZERO;
+			if (T.fc == FC_NONE)
+				T.fc = (unsigned int)(sub * CHUNK);
+			if (T.c_last != 0) { // the run that was open closes at the chunk's first claim
+				if (lane == 0 && T.evn < (unsigned int)EVK)
+					p.ev[t * EVK + T.evn] = (cs << 2);
+				T.evn++;
+			}
+			T.known = true;
+			T.c_last = 0;
+			T.F = 0.0;
+			return;
+		}
+		if (!T.known && __all_sync(0xffffffffu, mine == 0xffu)) {
+			// every claim is above target and the run was opened in an earlier tile: PASS throughout
+			if (T.agg.code == CODE_ZERO)
+				T.agg.code = cs + 2; // the chunk's first claim fills a zero F
+			return;
+		}
+	}
+	unsigned int A0[ROWS], A1[ROWS]; // ballots: claim slot 0 / 1 is at or above target
+#pragma unroll
+	for (int r = 0; r < ROWS; r++) {
+		A0[r] = __ballot_sync(0xffffffffu, (mine >> (2 * r)) & 1u);
+		A1[r] = __ballot_sync(0xffffffffu, (mine >> (2 * r + 1)) & 1u);
+	}
+	// ---- CONST / PASS types ------------------------------------------------------------------------
+	unsigned int C0[ROWS], C1[ROWS]; // ballots: the claim is CONST-type (below target, or a marker precedes it)
+	int nv[ROWS];                    // valid claims in the row
+#pragma unroll
+	for (int r = 0; r < ROWS; r++) {
+		const unsigned long long rbase = cs + r * 64;
+		if (FULL) {
+			nv[r] = 64;
+		} else {
+			const int rem = nvt - r * 64;
+			nv[r] = rem >= 64 ? 64 : (rem > 0 ? rem : 0);
+		}
+		const bool v0 = FULL || (2 * lane < nv[r]), v1 = FULL || (2 * lane + 1 < nv[r]);
+		if (FLAGS) {
+			const unsigned int mk0 = (fl[r] >> 1) & 1u, mk1 = (fl[r] >> 9) & 1u; // own markers
+			unsigned int up = __shfl_up_sync(0xffffffffu, mk1, 1);
+			if (lane == 0)
+				up = T.carry_mk;
+			T.carry_mk = __shfl_sync(0xffffffffu, mk1, 31);
+			if (v1 && mk1)
+				last_marker = rbase + 2 * lane + 2;
+			else if (v0 && mk0)
+				last_marker = rbase + 2 * lane + 1;
+			const bool ab0 = (A0[r] >> lane) & 1u, ab1 = (A1[r] >> lane) & 1u;
+			C0[r] = __ballot_sync(0xffffffffu, v0 && (!ab0 || up != 0));
+			C1[r] = __ballot_sync(0xffffffffu, v1 && (!ab1 || mk0 != 0));
+		} else if (FULL) {
+			C0[r] = ~A0[r]; // without markers a claim is CONST-type iff it is below target
+			C1[r] = ~A1[r];
+		} else {
+			C0[r] = __ballot_sync(0xffffffffu, v0) & ~A0[r];
+			C1[r] = __ballot_sync(0xffffffffu, v1) & ~A1[r];
+		}
+	}
 
 	// ---- chunk composition in index form, straight from the ballots -------------------------------
-	IAgg wagg;
-	unsigned int wfc = FC_NONE; // chunk-local position of the first CONST claim
 	{
+		IAgg wagg;
+		unsigned int wfc = FC_NONE; // chunk-local position of the first CONST claim
 		unsigned int cm_l = 0, c1_l = 0, a0_l = 0, a1_l = 0, cm_f = 0, c0_f = 0;
-		int r_l = -1, r_f = -1, nvt = 0;
+		int r_l = -1, r_f = -1;
 #pragma unroll
 		for (int r = 0; r < ROWS; r++) {
 			const unsigned int cm = C0[r] | C1[r];
-			nvt += nv[r];
 			if (cm) {
 				if (r_f < 0) {
 					r_f = r;
@@ -371,112 +373,45 @@ __global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const Scan
 			wfc = r_f * 64 + 2 * Lf + (((c0_f >> Lf) & 1u) ? 0 : 1);
 		} else {
 			wagg.isconst = false;
-			wagg.code = nvt > 0 ? (cs + 2) : CODE_ZERO;
+			wagg.code = cs + 2; // nvt > 0: the chunk's first claim fills a zero F
 		}
-	}
-	if (lane == 0) {
-		s_wagg[warp] = ((unsigned long long)wagg.isconst << 63) | wagg.code;
-		s_wfc[warp] = wfc;
-		if (warp == 0)
-			s_leftclosed = (t > 0 && !(prev_bits & 1u)) ? 1u : 0u;
-	}
-	// Only warps whose leading claims inherit F from an earlier warp (and warp 0, which writes the
-	// tile's record) wait for the others; everybody else just signals and moves on.
-	const bool first_is_pass = nv[0] > 0 && !((C0[0]) & 1u);
-	const bool prev_above = have_prev && (prev_bits & 1u) && !(prev_bits & 2u);
-	const bool need_wex = (warp == 0) || first_is_pass || prev_above;
-	IAgg wex;
-	wex.isconst = false;
-	wex.code = CODE_ZERO;
-	bool left_closed = false;
-	if (need_wex) {
-		bar_sync(1);
-		left_closed = s_leftclosed != 0u;
-		// nearest earlier warp with a CONST claim: lane w looks at warp w's aggregate, one ballot
-		const unsigned long long xw = (lane < WARPS) ? s_wagg[lane] : 0ull;
-		const unsigned int cmask = __ballot_sync(0xffffffffu, (lane < warp) && (xw >> 63));
-		if (cmask) {
-			const int w = 31 - __clz(cmask);
-			wex.isconst = true;
-			wex.code = __shfl_sync(0xffffffffu, xw, w) & DESC_CODE_MASK;
-			const unsigned long long nxt = __shfl_sync(0xffffffffu, xw, (w + 1) & 31) & DESC_CODE_MASK;
-			if (wex.code == CODE_ZERO && w + 1 < warp)
-				wex.code = nxt; // the PASS warp after it sets F
-		} else if (warp > 0) {
-			wex.code = __shfl_sync(0xffffffffu, xw, 0) & DESC_CODE_MASK; // all earlier warps are PASS: the first one's claim
-		}
-	} else {
-		bar_arrive(1);
-	}
-
-	// ---- the tile's record (thread 0): where the inherited run closes, what the tile leaves open
-	if (tid == 0) {
-		IAgg tile_agg;
-		tile_agg.isconst = false;
-		tile_agg.code = CODE_ZERO;
-		unsigned int fc = FC_NONE;
-#pragma unroll
-		for (int w = 0; w < WARPS; w++) {
-			IAgg a;
-			const unsigned long long x = s_wagg[w];
-			a.isconst = (x >> 63) != 0;
-			a.code = x & DESC_CODE_MASK;
-			tile_agg = icompose(tile_agg, a);
-			if (fc == FC_NONE && s_wfc[w] != FC_NONE)
-				fc = w * CHUNK + s_wfc[w];
-		}
-		if (left_closed)
-			fc = 0; // nothing crosses the tile's left edge: it anchors itself (resolve sees an empty stretch)
-		p.rec_fc[t] = fc;
-		p.rec_code[t] = tile_agg.code;
-		reinterpret_cast<raw_t *>(p.tile_now0)[t] = rn[0][0]; // thread 0 owns the tile's first claim
+		T.agg = icompose(T.agg, wagg);
+		if (T.fc == FC_NONE && wfc != FC_NONE)
+			T.fc = (unsigned int)(sub * CHUNK) + wfc;
 	}
 
 	// ---- phase 2: classes and events, FP64 only in rows with above-target claims ---------------
-	// `known`: F before the next claim is determined inside this tile.  Leading PASS claims of
-	// the tile (before its first CONST claim) are left to the resolve kernel.
-	// `known`: F before the chunk's first claim is determined inside this tile.
-	//   - an earlier warp of the tile has a CONST claim (wex.isconst), or
-	//   - the tile is left-closed (the claim before it is below target, so F is 0 at its edge and
-	//     the tile's first claim opens whatever run there is), or
-	//   - this warp needs nothing from before (its first claim is CONST-type, previous claim not ok)
-	bool known = wex.isconst || left_closed || !need_wex || (warp == 0 && !first_is_pass && !prev_above);
-	const bool prev_ok_possible = known && prev_above;
-	double F = 0.0; // F in force before the chunk's first claim (before its marker-before reset)
-	if ((wex.isconst || (left_closed && warp > 0)) && (first_is_pass || prev_ok_possible))
-		F = materialise<NS>(wex.code, p.now, nullptr); // never CODE_CARRY inside a tile
-	int c_last = 0; // class of the claim before the current row
-	if (prev_ok_possible && F != 0.0)
-		c_last = claim_class(true, TimeIn<NS>::to_ms(prev_now), F);
+	// Leading PASS claims of the tile (before its first CONST claim) are left to the resolve kernel.
 #pragma unroll
 	for (int r = 0; r < ROWS; r++) {
-		if (nv[r] == 0)
+		if (!FULL && nv[r] == 0)
 			break;
 		const unsigned long long rbase = cs + r * 64;
 		const unsigned int cmr = C0[r] | C1[r];
-		if (!known && cmr == 0u)
+		if (!T.known && cmr == 0u)
 			continue; // still inside the run inherited from an earlier tile: nothing to classify
-		// first classifiable position of the row (64 = none masked): the row's first CONST claim
+		// first classifiable position of the row: the row's first CONST claim
 		int fpos = 0;
-		if (!known) {
+		if (!T.known) {
 			const int Lf = __ffs(cmr) - 1;
 			fpos = 2 * Lf + (((C0[r] >> Lf) & 1u) ? 0 : 1);
 		}
-		known = true;
+		T.known = true;
 		if ((A0[r] | A1[r]) == 0u) { // nobody above target: every class is 0, F ends at 0
-			if (c_last != 0 && lane == 0) {
-				unsigned int pos = atomicAdd(&s_evn[warp], 1u);
-				if (pos < EVW)
-					s_ev[warp][pos] = (rbase << 2);
+			if (T.c_last != 0) {
+				if (lane == 0 && T.evn < (unsigned int)EVK)
+					p.ev[t * EVK + T.evn] = (rbase << 2);
+				T.evn++;
 			}
-			c_last = 0;
-			F = 0.0;
+			T.c_last = 0;
+			T.F = 0.0;
 			continue;
 		}
-		const bool v0 = 2 * lane < nv[r], v1 = 2 * lane + 1 < nv[r];
+		const pair_t N = *reinterpret_cast<const pair_t *>(sn + r * 64 + 2 * lane);
+		const bool v0 = FULL || (2 * lane < nv[r]), v1 = FULL || (2 * lane + 1 < nv[r]);
 		const bool ab0 = (A0[r] >> lane) & 1u, ab1 = (A1[r] >> lane) & 1u;
 		const bool k0 = (C0[r] >> lane) & 1u, k1 = (C1[r] >> lane) & 1u; // CONST-type
-		const double n0 = TimeIn<NS>::to_ms(rn[r][0]), n1 = TimeIn<NS>::to_ms(rn[r][1]);
+		const double n0 = TimeIn<NS>::to_ms(N.x), n1 = TimeIn<NS>::to_ms(N.y);
 		// lane summary: F after my two claims if F were 0 before them
 		double lv;
 		if (k1) {
@@ -489,8 +424,7 @@ __global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const Scan
 			lv = v0 ? __dadd_rn(n0, CODEL_INTERVAL) : 0.0;
 		}
 		// F before my claim 0: last CONST lane before me, then the PASS lane after it
-		const unsigned int cm = C0[r] | C1[r];
-		const unsigned int prior = cm & lt_mask;
+		const unsigned int prior = cmr & lt_mask;
 		const int Lq = prior ? (31 - __clz(prior)) : 0;
 		const double vq = __shfl_sync(0xffffffffu, lv, Lq);
 		const int nx = prior ? (Lq + 1) : 0;
@@ -499,7 +433,7 @@ __global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const Scan
 		if (prior)
 			Fp = (vq != 0.0) ? vq : ((nx < lane) ? vnx : 0.0);
 		else
-			Fp = (F != 0.0) ? F : ((lane > 0) ? vnx : 0.0);
+			Fp = (T.F != 0.0) ? T.F : ((lane > 0) ? vnx : 0.0);
 		// my two claims in order
 		int c0 = 0, c1 = 0;
 		{
@@ -516,33 +450,169 @@ __global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const Scan
 			c0 = 0; // unclassified (inherited run): no class, no event
 		if (2 * lane + 1 < fpos)
 			c1 = 0;
-		// events
+		// events, in index order
 		int cprev = __shfl_up_sync(0xffffffffu, v1 ? c1 : c0, 1);
 		if (lane == 0)
-			cprev = c_last;
-		if (v0 && c0 != cprev) {
-			unsigned int pos = atomicAdd(&s_evn[warp], 1u);
-			if (pos < EVW)
-				s_ev[warp][pos] = ((rbase + 2 * lane) << 2) | (unsigned long long)c0;
-		}
-		if (v1 && c1 != c0) {
-			unsigned int pos = atomicAdd(&s_evn[warp], 1u);
-			if (pos < EVW)
-				s_ev[warp][pos] = ((rbase + 2 * lane + 1) << 2) | (unsigned long long)c1;
+			cprev = T.c_last;
+		const bool e0 = v0 && c0 != cprev, e1 = v1 && c1 != c0;
+		const unsigned int E0 = __ballot_sync(0xffffffffu, e0), E1 = __ballot_sync(0xffffffffu, e1);
+		if (E0 | E1) {
+			unsigned int pos = T.evn + __popc(E0 & lt_mask) + __popc(E1 & lt_mask);
+			if (e0) {
+				if (pos < (unsigned int)EVK)
+					p.ev[t * EVK + pos] = ((rbase + 2 * lane) << 2) | (unsigned long long)c0;
+				pos++;
+			}
+			if (e1 && pos < (unsigned int)EVK)
+				p.ev[t * EVK + pos] = ((rbase + 2 * lane + 1) << 2) | (unsigned long long)c1;
+			T.evn += __popc(E0) + __popc(E1);
 		}
 		// carry to the next row: state after the row's last valid claim
 		const int Lend = (nv[r] - 1) >> 1;
-		F = __shfl_sync(0xffffffffu, Fp, Lend);
-		c_last = __shfl_sync(0xffffffffu, (nv[r] & 1) ? c0 : c1, Lend);
+		T.F = __shfl_sync(0xffffffffu, Fp, Lend);
+		T.c_last = __shfl_sync(0xffffffffu, (nv[r] & 1) ? c0 : c1, Lend);
+	}
+}
+
+template <bool NS, bool FLAGS>
+__global__ void __launch_bounds__(SC_TPB, CB_SCAN_MINBLOCKS) scan_kernel(const ScanParams p) {
+	using raw_t = typename Raw<NS>::t;
+	CB_DYN_SHARED(unsigned char, s_dyn); // SC_WARPS x SC_NST stages
+	__shared__ __align__(8) unsigned long long s_mbar[SC_WARPS * SC_NST];
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0 && blockIdx.x == 0)
+		p.b->dbg[8] = gtimer(); // timeline stamp (tools/pipeline_timeline.py)
+	// chunk and tile numbers fit 32 bits (n < 2^39); only addresses are 64-bit
+	const unsigned int tiles = (unsigned int)((p.n + TILE - 1) / TILE);
+	const unsigned int nfull = (unsigned int)(p.n / CHUNK);                 // chunks with all 256 claims
+	const unsigned int nchunks = (unsigned int)((p.n + CHUNK - 1) / CHUNK); // chunks with any claim
+	// warp gw walks tiles gw, gw + GW, gw + 2 GW, ...; consecutive tiles go to consecutive CTAs, so a
+	// batch with fewer tiles than warps still spreads over every SM
+	const unsigned int gw = (unsigned int)warp * gridDim.x + blockIdx.x;
+	const unsigned int GW = gridDim.x * SC_WARPS;
+	if (gw >= tiles)
+		return;
+	unsigned char *wbase = s_dyn + (size_t)warp * SC_NST * SC_STAGE;
+	unsigned long long *mbar = s_mbar + warp * SC_NST;
+	const unsigned int lt_mask = (1u << lane) - 1u;
+	const bool vec = p.vec_ok != 0;
+	unsigned long long policy = 0;
+	if (lane == 0) {
+#pragma unroll
+		for (int s = 0; s < SC_NST; s++)
+			mbar_init(&mbar[s], 1);
+		mbar_init_fence();
+		policy = l2_evict_first_policy();
+	}
+	__syncwarp();
+
+	// lane 0: start the bulk copies of chunk `c` (a batch-wide chunk number) into stage sg; a partial
+	// chunk or unaligned arrays are filled by hand when their turn comes
+	auto issue = [&](unsigned int c, int sg) {
+		if (!vec || c >= nfull)
+			return;
+		unsigned char *st = wbase + sg * SC_STAGE;
+		const unsigned int lead = c ? (unsigned int)SC_LEAD : 0u; // the two claims in front (none before claim 0)
+		const unsigned int bytes = (unsigned int)(CHUNK * 8) + lead;
+		const size_t off = (size_t)c * (CHUNK * 8) - lead;
+		mbar_expect_tx(&mbar[sg], 2u * bytes);
+		bulk_g2s(st + SC_LEAD - lead, reinterpret_cast<const unsigned char *>(p.start) + off, bytes, &mbar[sg], policy);
+		bulk_g2s(st + SC_ARR + SC_LEAD - lead, reinterpret_cast<const unsigned char *>(p.now) + off, bytes, &mbar[sg], policy);
+	};
+	// the chunk SC_NST ahead of (tile t, chunk sub) in this warp's walk
+	auto ahead = [&](unsigned int t, int sub) {
+		const int s2 = sub + SC_NST;
+		return s2 < CHUNKS ? t * CHUNKS + (unsigned int)s2
+		                   : (t + GW < tiles ? (t + GW) * CHUNKS + (unsigned int)(s2 - CHUNKS) : 0xffffffffu);
+	};
+	static_assert(SC_NST <= CHUNKS, "the prologue stays inside the first tile");
+	if (lane == 0) {
+#pragma unroll
+		for (int s = 0; s < SC_NST; s++)
+			issue(gw * CHUNKS + (unsigned int)s, s);
 	}
 
-	// class of the tile's last claim (the warp that owns it), for the run the tile leaves open
-	{
-		unsigned long long te = ts + TILE;
-		if (te > p.n)
-			te = p.n;
-		if (lane == 0 && cs < te && te <= cs + CHUNK)
-			p.rec_cend[t] = (unsigned int)c_last;
+	unsigned int phases = 0; // parity each stage's barrier completes next
+	int sg = 0;
+	bool nonmono = false;
+	unsigned long long last_marker = 0;
+	const raw_t *gstart = reinterpret_cast<const raw_t *>(p.start);
+	const raw_t *gnow = reinterpret_cast<const raw_t *>(p.now);
+	for (unsigned int t = gw; t < tiles; t += GW) {
+		const unsigned long long ts = (unsigned long long)t * TILE;
+		TileState T;
+		T.agg.isconst = false;
+		T.agg.code = CODE_ZERO;
+		T.fc = FC_NONE;
+		T.known = false;
+		T.F = 0.0;
+		T.c_last = 0;
+		T.evn = 0;
+		T.carry_mk = 0;
+		bool left_closed = false;
+		raw_t first_now = raw_t(0);
+#pragma unroll 1
+		for (int sub = 0; sub < CHUNKS; sub++) {
+			const unsigned int c = t * CHUNKS + (unsigned int)sub;
+			if (c >= nchunks)
+				break; // only in the batch's last tile: nothing follows
+			const unsigned long long cs = ts + (unsigned long long)sub * CHUNK;
+			unsigned char *st = wbase + sg * SC_STAGE;
+			const bool full = c < nfull;
+			if (vec && full) {
+				mbar_wait(&mbar[sg], (phases >> sg) & 1u);
+				phases ^= 1u << sg;
+				if (c == 0 && lane == 0) { // nothing precedes claim 0: a clock no claim can step back from
+					*reinterpret_cast<raw_t *>(st + SC_ARR + SC_LEAD - 8) = Raw<NS>::lowest();
+					mbar_init_fence(); // ordered before the bulk copy that later refills this stage (async proxy)
+				}
+			} else {
+				// by hand: the two claims in front, the valid claims, zeros behind them
+				raw_t *ds = reinterpret_cast<raw_t *>(st), *dn = reinterpret_cast<raw_t *>(st + SC_ARR);
+				for (int j = lane; j < CHUNK + 2; j += 32) {
+					const long long i = (long long)cs - 2 + j;
+					const bool ok = i >= 0 && (unsigned long long)i < p.n;
+					ds[j] = ok ? gstart[i] : raw_t(0);
+					dn[j] = ok ? gnow[i] : (i < 0 ? Raw<NS>::lowest() : raw_t(0));
+				}
+			}
+			__syncwarp();
+			if (sub == 0) {
+				// The claim just before the tile: if it is below target F is 0 at the tile's edge and the
+				// tile's first claim opens whatever run there is; its marker resets F in front of our
+				// first claim.
+				const raw_t *ss = reinterpret_cast<const raw_t *>(st + SC_LEAD);
+				const raw_t *sn = reinterpret_cast<const raw_t *>(st + SC_ARR + SC_LEAD);
+				first_now = sn[0];
+				if (t > 0) {
+					left_closed = !is_above<NS>(ss[-1], sn[-1], p.target);
+					if (FLAGS)
+						T.carry_mk = (p.flags[ts - 1] & F_EMPTY_AFTER) ? 1u : 0u;
+				}
+				T.known = left_closed;
+			}
+			if (full)
+				scan_chunk<NS, FLAGS, true>(p, st, t, cs, sub, lane, lt_mask, T, nonmono, last_marker);
+			else
+				scan_chunk<NS, FLAGS, false>(p, st, t, cs, sub, lane, lt_mask, T, nonmono, last_marker);
+			__syncwarp(); // every lane is done with the stage: refill it with the chunk SC_NST ahead
+			if (lane == 0)
+				issue(ahead(t, sub), sg);
+			sg = (sg + 1 == SC_NST) ? 0 : sg + 1;
+		}
+		// ---- the tile's record: where the inherited run closes, what the tile leaves open ----------
+		if (lane == 0) {
+			p.rec_fc[t] = left_closed ? 0u : T.fc; // left-closed: nothing crosses the tile's left edge, it anchors itself
+			p.rec_code[t] = T.agg.code;
+			p.rec_cend[t] = (unsigned int)T.c_last;
+			reinterpret_cast<raw_t *>(p.tile_now0)[t] = first_now;
+			p.ev_count[t] = T.evn > (unsigned int)EVK ? (unsigned int)EVK : T.evn;
+			if (T.evn > (unsigned int)EVK)
+				p.b->overflow = 1u;
+			if (t + 1 == tiles)
+				p.b->dbg[9] = gtimer(); // the last tile's warp is among the last to retire
+		}
 	}
 	if (FLAGS) {
 		unsigned long long m = last_marker;
@@ -556,38 +626,6 @@ __global__ void __launch_bounds__(TPB, CB_SCAN_MINBLOCKS) scan_kernel(const Scan
 	}
 	if (nonmono)
 		p.b->nonmono = 1u;
-	// ---- flush: warp 0 gathers every warp's events into the tile's slots ------------------------
-	if (warp != 0) {
-		bar_arrive(2);
-		return;
-	}
-	bar_sync(2);
-	{
-		unsigned int cnt = 0;
-		bool over = false;
-#pragma unroll
-		for (int w = 0; w < WARPS; w++) {
-			const unsigned int cw = s_evn[w];
-			over |= cw > (unsigned int)EVW;
-			const unsigned int use = cw > (unsigned int)EVW ? (unsigned int)EVW : cw;
-			if ((unsigned int)lane < use) {
-				if (cnt + lane < (unsigned int)EVK)
-					p.ev[t * EVK + cnt + lane] = s_ev[w][lane];
-			}
-			cnt += use;
-		}
-		if (cnt > (unsigned int)EVK) {
-			over = true;
-			cnt = EVK;
-		}
-		if (lane == 0) {
-			if (over)
-				p.b->overflow = 1u;
-			p.ev_count[t] = cnt;
-			if (t + 1 == gridDim.x)
-				p.b->dbg[9] = gtimer(); // the last tile's CTA is among the last to retire
-		}
-	}
 }
 
 } // namespace cb

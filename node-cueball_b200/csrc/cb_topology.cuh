@@ -1,8 +1,7 @@
 // cb_topology.cuh -- backend preference list, planRebalance and the slot table, on device.
 //
 // These run once per topology change (resolver 'added'/'removed', decoherence reshuffle,
-// rebalance), not per claim, and are inherently sequential in the reference, so they are
-// small single-CTA kernels whose job is to keep the whole claim path -- including the table
+// rebalance), not per claim: single-CTA kernels whose job is to keep the whole claim path -- including the table
 // the emit kernel stages through TMA -- resident on the GPU and bit-identical to
 //   lib/pool.js:285-313,501-519   (preference list)
 //   lib/utils.js:239-393          (planRebalance)
@@ -101,27 +100,93 @@ __global__ void __launch_bounds__(TOPO_TPB, 1) pref_reshuffle_kernel(int32_t *ke
 	cta_insert(keys, n - 1, idx, taken);
 }
 
-// utils.planRebalance, lib/utils.js:239-393.  One thread: the algorithm is a sequential
-// round-robin with data-dependent early exits; `empties.length > 0` (:331-339) is kept as
-// two running counters instead of the reference's O(B) filter per replacement.
-// Keys are positions 0..B-1; see include/cueball_b200.h for the output format.
-__global__ void plan_rebalance_kernel(const int32_t *have, const uint8_t *dead, int B, int target,
-    int max, int singleton, int32_t *want, int32_t *add, int32_t *n_add, int32_t *rm_key,
-    int32_t *rm_ord, int32_t *n_rm) {
-	if (threadIdx.x != 0 || blockIdx.x != 0)
-		return;
-	long long done = 0, replacements = 0;
-	int ring = 0;
-	int alive = 0, alive_undef = 0, dead_undef = 0;
-	for (int k = 0; k < B; k++) {
-		want[k] = -1; // wantedSpares[k] === undefined
-		if (dead[k])
-			dead_undef++;
-		else {
-			alive++;
-			alive_undef++;
-		}
+// ---- block-wide helpers (TOPO_TPB threads) ----------------------------------------------------
+// sum of one long long per thread; every thread gets the total.  s_w: 32 long longs of shared memory.
+__device__ __forceinline__ long long topo_block_sum(long long v, long long *s_w) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads(); // s_w may still be read from the previous call
+	if (lane == 0)
+		s_w[warp] = v;
+	__syncthreads();
+	long long t = 0;
+	for (int w = 0; w < TOPO_TPB / 32; w++)
+		t += s_w[w];
+	return t;
+}
+// exclusive prefix sum of one int per thread; `total` = the block's sum (all threads).
+__device__ __forceinline__ int topo_block_excl_scan(int v, long long *s_w, int &total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int y = __shfl_up_sync(0xffffffffu, x, o);
+		if (lane >= o)
+			x += y;
 	}
+	__syncthreads();
+	if (lane == 31)
+		s_w[warp] = x;
+	__syncthreads();
+	int before = 0, t = 0;
+	for (int w = 0; w < TOPO_TPB / 32; w++) {
+		if (w < warp)
+			before += (int)s_w[w];
+		t += (int)s_w[w];
+	}
+	total = t;
+	return before + x - v;
+}
+
+// utils.planRebalance, lib/utils.js:239-393, one CTA.
+//   1. The round-robin over `target` slots (:266-290) in closed form: position k of the preference list is
+//      visited v_k = floor(target / B) + [k < target mod B] times; an alive backend takes v_k slots (one in
+//      singleton mode), a dead one exactly one (its monitor) and asks for v_k replacements.  Per key, in
+//      parallel; `done` and `replacements` are block sums.  Without dead backends -- every slot-table build of
+//      the claim path -- this is the whole computation.
+//   2. Only when replacements are wanted (dead backends): the replacement walk (:293-366), whose early exits
+//      depend on the running totals, by one thread exactly as the reference writes it; `empties.length > 0`
+//      (:331-339) is two running counters instead of the reference's O(B) filter per step.
+//   3. plan.remove (reverse key order, oldest first, :372-382) and plan.add (forward key order, :383-390) from
+//      exclusive scans of the per-key differences; every output element is placed by its own thread (binary
+//      search over the offsets), so a table of 16 384 slots over 4 096 backends is filled in a few passes.
+// Keys are positions 0..B-1; see include/cueball_b200.h for the output format.  scratch: 2 (B + 1) ints.
+__global__ void __launch_bounds__(TOPO_TPB, 1) plan_rebalance_kernel(const int32_t *have, const uint8_t *dead, int B,
+    int target, int max, int singleton, int32_t *want, int32_t *add, int32_t *n_add, int32_t *rm_key,
+    int32_t *rm_ord, int32_t *n_rm, int32_t *scratch) {
+	__shared__ long long s_w[32];
+	const int tid = threadIdx.x;
+	// ---- 1. the first loop in closed form -----------------------------------------------------------
+	const int q = B > 0 ? target / B : 0, r = B > 0 ? target % B : 0;
+	long long p_done = 0, p_repl = 0, p_alive = 0, p_aundef = 0, p_dundef = 0;
+	for (int k = tid; k < B; k += TOPO_TPB) {
+		const int v = q + (k < r ? 1 : 0);
+		int w;
+		if (!dead[k]) {
+			w = singleton ? (v > 0 ? 1 : 0) : v;
+			p_alive++;
+			if (v == 0)
+				p_aundef++;
+		} else {
+			w = v > 0 ? 1 : 0;
+			p_repl += v;
+			if (v == 0)
+				p_dundef++;
+		}
+		p_done += w;
+		want[k] = v > 0 ? w : -1; // -1: wantedSpares[k] === undefined
+	}
+	long long done = topo_block_sum(p_done, s_w);
+	long long replacements = topo_block_sum(p_repl, s_w);
+	const int alive = (int)topo_block_sum(p_alive, s_w);
+	int alive_undef = (int)topo_block_sum(p_aundef, s_w);
+	int dead_undef = (int)topo_block_sum(p_dundef, s_w);
+	__syncthreads(); // want[] is in place for the thread that walks the replacements
+	// ---- 2. replacements for dead backends (:293-366) ---------------------------------------------------
+	if (tid == 0 && B > 0 && replacements > 0) {
+		int ring = r;
 #define CB_DEFINE(k)                       \
 	if (want[k] < 0) {                     \
 		want[k] = 0;                       \
@@ -130,29 +195,6 @@ __global__ void plan_rebalance_kernel(const int32_t *have, const uint8_t *dead, 
 		else                               \
 			alive_undef--;                 \
 	}
-	if (B > 0) {
-		for (int i = 0; i < target; ++i) { // :266-290
-			int k = ring;
-			ring = (ring + 1 == B) ? 0 : ring + 1;
-			CB_DEFINE(k);
-			if (!dead[k]) {
-				if (singleton) {
-					if (want[k] == 0) {
-						want[k] = 1;
-						++done;
-					}
-				} else {
-					++want[k];
-					++done;
-				}
-				continue;
-			}
-			if (want[k] == 0) {
-				want[k] = 1;
-				++done;
-			}
-			++replacements;
-		}
 		if (done + replacements > max) // :293-294
 			replacements = max - done;
 		for (long long i = 0; i < replacements; ++i) { // :300-366
@@ -192,37 +234,75 @@ __global__ void plan_rebalance_kernel(const int32_t *have, const uint8_t *dead, 
 				break;
 			}
 		}
-	}
 #undef CB_DEFINE
-	int na = 0, nr = 0;
-	for (int k = 0; k < B; k++)
-		if (want[k] < 0)
-			want[k] = 0;
-	for (int k = B - 1; k >= 0; k--) { // :372-382 remove: reverse key order, oldest first
-		int h = have[k], ord = 0;
-		while (h > want[k]) {
-			if (rm_key) {
-				rm_key[nr] = k;
-				rm_ord[nr] = ord;
+	}
+	__syncthreads();
+	// ---- 3. the plan's lists ------------------------------------------------------------------------------
+	int32_t *off_add = scratch, *off_rm = scratch + (B + 1);
+	int carry_a = 0, carry_r = 0;
+	for (int base = 0; base < B; base += TOPO_TPB) {
+		const int k = base + tid;   // forward key order
+		const int kr = B - 1 - k;   // reverse key order
+		int a = 0, d = 0;
+		if (k < B) {
+			int w = want[k];
+			if (w < 0) {
+				w = 0;
+				want[k] = 0;
 			}
-			nr++;
-			ord++;
-			--h;
+			a = w > have[k] ? w - have[k] : 0;
+			int wr = want[kr];
+			if (wr < 0)
+				wr = 0;
+			d = have[kr] > wr ? have[kr] - wr : 0;
+		}
+		int ta, tr;
+		const int ea = topo_block_excl_scan(a, s_w, ta);
+		const int er = topo_block_excl_scan(d, s_w, tr);
+		if (k < B) {
+			off_add[k] = carry_a + ea;
+			off_rm[k] = carry_r + er; // indexed by reverse position j = B-1-key
+		}
+		carry_a += ta;
+		carry_r += tr;
+	}
+	if (tid == 0) {
+		off_add[B] = carry_a;
+		off_rm[B] = carry_r;
+		if (n_add)
+			*n_add = carry_a;
+		if (n_rm)
+			*n_rm = carry_r;
+	}
+	__syncthreads();
+	const int na = carry_a, nr = carry_r;
+	if (add) {
+		for (int s = tid; s < na; s += TOPO_TPB) { // the key whose span of plan.add holds element s
+			int lo = 0, hi = B; // last k with off_add[k] <= s
+			while (hi - lo > 1) {
+				const int mid = (lo + hi) >> 1;
+				if (off_add[mid] <= s)
+					lo = mid;
+				else
+					hi = mid;
+			}
+			add[s] = lo;
 		}
 	}
-	for (int k = 0; k < B; k++) { // :383-390 add: forward key order
-		int h = have[k];
-		while (h < want[k]) {
-			if (add)
-				add[na] = k;
-			na++;
-			++h;
+	if (rm_key) {
+		for (int s = tid; s < nr; s += TOPO_TPB) {
+			int lo = 0, hi = B;
+			while (hi - lo > 1) {
+				const int mid = (lo + hi) >> 1;
+				if (off_rm[mid] <= s)
+					lo = mid;
+				else
+					hi = mid;
+			}
+			rm_key[s] = B - 1 - lo;
+			rm_ord[s] = s - off_rm[lo]; // oldest connection of the key first
 		}
 	}
-	if (n_add)
-		*n_add = na;
-	if (n_rm)
-		*n_rm = nr;
 }
 
 // slot table: slot s belongs to backend keys[add[s]] (plan.add order = addConnection

@@ -9,7 +9,11 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
+#include <arpa/inet.h>
 #include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,7 +22,9 @@
 
 #include "cb_device.cuh"
 #include "cb_emit.cuh"
+#include "cb_peers.cuh"
 #include "cb_queue.cuh"
+#include "cb_resolver.cuh"
 #include "cb_resolve.cuh"
 #include "cb_scan.cuh"
 #include "cb_topology.cuh"
@@ -75,17 +81,17 @@ struct Lane {
 	unsigned long long *ev = nullptr, *evc = nullptr, *ev_q = nullptr, *ev_d = nullptr;
 	unsigned long long *rec_code = nullptr, *xev = nullptr, *hj_lo = nullptr, *hj_b = nullptr, *tile_now0 = nullptr;
 	unsigned long long *iv_lo = nullptr, *iv_hi = nullptr, *iv_cum = nullptr;
-	double *ev_now = nullptr, *hj_F = nullptr, *idx_ms = nullptr;
+	double *ev_now = nullptr, *hj_F = nullptr;
 	cudaStream_t st = nullptr; // all four kernels of the lane's batch, in order (highest stream priority)
 	cudaEvent_t res_done = nullptr, emit_done = nullptr, coll_done = nullptr, join_ev = nullptr;
 	bool used = false, coll_pending = false;
 	unsigned long long epoch = 0;
-	// CB_GRAPH=1 (not yet validated on hardware): the batch's kernels as one CUDA graph per
-	// (clock type, flags) variant, its node parameters rewritten per batch: one launch call per batch
+	// graph launch mode: the batch's kernels as one CUDA graph per (clock type, flags) variant, its
+	// node parameters rewritten per batch: one launch call per batch
 	struct Graph {
 		cudaGraph_t g = nullptr;
 		cudaGraphExec_t ex = nullptr;
-		cudaGraphNode_t n_scan = nullptr, n_res = nullptr, n_commit = nullptr, n_emit = nullptr;
+		cudaGraphNode_t n_scan = nullptr, n_res = nullptr, n_emit = nullptr;
 	} gr[2][2];
 };
 
@@ -113,6 +119,7 @@ struct cb_ctx {
 	uint64_t launches = 0;
 	// batch pipeline
 	int depth = CB_DEFAULT_DEPTH;
+	bool depth_auto = true;            // small batches (latency-bound) use every lane unless the host chose a depth
 	Lane lane[CB_LANES];
 	unsigned long long seq = 0;        // batches enqueued so far
 	ChainMem *d_chain = nullptr;           // the chain word; in ring mode this rank's mailbox
@@ -127,37 +134,78 @@ struct cb_ctx {
 	unsigned char *q_waiting = nullptr;
 	double *q_tmo = nullptr;
 	size_t q_cap = 0, q_res_cap = 0, q_stage_cap = 0;
-	// F-chain variant of the commit kernel (CB_FCHAIN=1; not yet validated on hardware)
-	bool fchain = false, fseed = true;
-	bool fused = false; // CB_FUSED=1
-	bool graph = false; // CB_GRAPH=1
+	bool fseed = true;  // the state was set from the host: the next batch's F slot needs seeding
+	int graph_mode = -1; // -1: graph launch for batches of at most graph_max_tiles tiles; 0 never; 1 always (CB_GRAPH)
+	size_t graph_max_tiles = 1024;
 	int prio_least = 0, prio_greatest = 0;
+	// per-batch global counts over peer memory (cb_peers_*)
+	PeerBoard *d_board = nullptr;          // this rank's board
+	PeerBoard **d_peer_ptrs = nullptr;     // device array of the ranks' boards (peer memory)
+	void *peer_ipc[PB_MAXR] = {};          // boards opened from IPC handles (to be closed)
+	int peers_n = 0, peers_rank = 0;
+	unsigned long long peer_step = 0;      // batches posted since cb_peers_connect
+	unsigned long long *d_peer_out = nullptr;
 	int ring_n = 0, ring_rank = 0;
 	ChainMem *ring_next = nullptr;         // the next rank's mailbox
 	bool ring_next_ipc = false;            // ... opened from an IPC handle (to be closed)
 	int last_lane = -1;
 	bool last_flags = false;
 	int emit_grid = 148 * 4;           // persistent emit CTAs (from the device's SM count)
+	int scan_ctas = 148 * CB_SCAN_MINBLOCKS; // scan CTAs resident at once
+	int scan_tpw = 2;                  // tiles a scan warp streams before its CTA retires (measured: 1, 2, 3, persistent)
 	// topology
 	int B = 0, nslots = 0, target_slots = 0, mode = CB_BALANCE_UNIFORM, key_cap = 0, slot_cap = 0;
 	int32_t *d_keys = nullptr, *d_want = nullptr, *d_add = nullptr, *d_slot_backend = nullptr;
-	int32_t *d_prio = nullptr, *d_weight = nullptr;
+	int32_t *d_prio = nullptr, *d_weight = nullptr, *d_plan_scratch = nullptr;
 	int *d_ints = nullptr; // [0]=len [1]=n_add [2]=nslots [3]=status [4]=n_rm [5]=scalar out
 	double *d_dbl = nullptr;
 	// host-buffer pipeline
 	size_t chunk = DEFAULT_CHUNK, stage_cap = 0;
 	Staging st[NBUF];
+	// pinned landing zone of fetch_stats: {chain word, error count}, DevState, BatchCtl in one synchronisation
+	struct StatsStage {
+		unsigned long long chain[2];
+		DevState st;
+		BatchCtl ctl;
+	} *h_stats = nullptr;
 	// profiling
 	bool prof = false;
+	bool prof_scan_only = false; // cb_profile_enable(ctx, 2): launch only the scan kernel (burst timing by the caller)
 	cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
 	double prof_ms[CB_K_COUNT] = {0, 0, 0};
 	uint64_t prof_n[CB_K_COUNT] = {0, 0, 0};
+	// resolver ingestion (cb_resolver_process): r_backends of lib/resolver.js:1024-1108 as srvKey -> key id,
+	// in insertion order
+	std::vector<std::string> r_keys;
+	std::unordered_map<std::string, int32_t> r_ids;
+	int32_t r_next_id = 0;
 	// nccl
 	nccl_comm_t comm = nullptr;
 	int nranks = 1, rank = 0;
 };
 
 namespace {
+
+// Every entry point runs with the context's device current and leaves the caller's device as it found it
+// (a host with contexts on several GPUs, or one that switches devices between calls).
+struct DevGuard {
+	int prev = -1;
+	explicit DevGuard(const cb_ctx *c) {
+		if (!c)
+			return;
+		int cur = -1;
+		if (cudaGetDevice(&cur) == cudaSuccess && cur != c->device) {
+			prev = cur;
+			cudaSetDevice(c->device);
+		}
+	}
+	~DevGuard() {
+		if (prev >= 0)
+			cudaSetDevice(prev);
+	}
+	DevGuard(const DevGuard &) = delete;
+	DevGuard &operator=(const DevGuard &) = delete;
+};
 
 int fail(cb_ctx *c, int code, const char *fmt, ...) {
 	va_list ap;
@@ -193,6 +241,15 @@ static int ring_close(cb_ctx *c) {
 	return CB_OK;
 }
 
+static void peers_close(cb_ctx *c) {
+	for (int r = 0; r < PB_MAXR; r++) {
+		if (c->peer_ipc[r])
+			cudaIpcCloseMemHandle(c->peer_ipc[r]);
+		c->peer_ipc[r] = nullptr;
+	}
+	c->peers_n = 0;
+}
+
 // wait for every batch in flight (and the main stream)
 int drain(cb_ctx *c) {
 	for (int l = 0; l < CB_LANES; l++) {
@@ -216,6 +273,20 @@ int lane_streams(cb_ctx *c, Lane &L) {
 	c->prio_greatest = greatest;
 	CU(c, cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, greatest));
 	return CB_OK;
+}
+
+// The scan's grid: every warp streams up to `scan_tpw` tiles of its own (consecutive tiles on consecutive
+// CTAs).  A CTA's life is bounded on purpose: the single-CTA resolve kernel and the emit kernel of the
+// batches ahead in the pipeline run at a higher priority and take the SM slots retiring scan CTAs free;
+// fully persistent scan CTAs would hold every SM until the whole batch is read.  Small batches still get
+// one CTA per SM slot.
+unsigned scan_grid(const cb_ctx *c, size_t tiles) {
+	const size_t per_cta = (size_t)SC_WARPS * (size_t)c->scan_tpw;
+	size_t g = (tiles + per_cta - 1) / per_cta;
+	const size_t spread = tiles < (size_t)c->scan_ctas ? tiles : (size_t)c->scan_ctas;
+	if (g < spread)
+		g = spread;
+	return (unsigned)g;
 }
 
 int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
@@ -242,40 +313,49 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 	    (rc = dev_alloc(c, &L.ev_now, evcap)) || (rc = dev_alloc(c, &L.iv_lo, evcap + 8)) ||
 	    (rc = dev_alloc(c, &L.iv_hi, evcap + 8)) || (rc = dev_alloc(c, &L.iv_cum, evcap + 8)))
 		return rc;
-	if (!L.idx_ms && (rc = dev_alloc(c, &L.idx_ms, NIDX_MAX)))
-		return rc;
 	// the emit kernel's sum descriptors carry an epoch tag, so they only need zeroing once
 	CU(c, cudaMemset(L.sdesc, 0, cap * sizeof(SumDesc)));
 	L.cap_tiles = cap;
 	return CB_OK;
 }
 
-// CB_GRAPH=1: scan -> (prepare -> commit | fused resolve) -> emit as the nodes of one CUDA graph per lane and
-// variant.  The first batch of a variant builds and instantiates it; every later one rewrites the nodes'
-// parameters (pointers, sizes, grids) in the instantiated graph and launches it: one launch call per batch
-// instead of three or four.  The scan node keeps the lowest priority, the others the highest.
+// Graph launch mode: scan -> resolve -> emit as the nodes of one CUDA graph per lane and variant.  The
+// first batch of a variant builds and instantiates it; every later one rewrites the nodes' parameters
+// (pointers, sizes, grids) in the instantiated graph and launches it: one launch call per batch instead
+// of three.  The scan node keeps the lowest priority, the others the highest.
+PeerLink peer_link(const cb_ctx *c, unsigned long long step) {
+	PeerLink pl;
+	pl.mine = c->d_board;
+	pl.peers = c->d_peer_ptrs;
+	pl.R = c->peers_n;
+	pl.me = c->peers_rank;
+	pl.step = step;
+	pl.timeout_ns = 30000000000ull; // the other ranks are other processes: allow for start-up skew
+	return pl;
+}
+// behind the batch's emit kernel, on its stream: publish the batch's counts to every rank's board
+int peers_post(cb_ctx *c, Lane &L, cudaStream_t s) {
+	if (c->peers_n <= 0)
+		return CB_OK;
+	peer_post_kernel<<<1, 32, 0, s>>>(peer_link(c, c->peer_step), L.ctl);
+	c->peer_step++;
+	c->launches++;
+	CU(c, cudaGetLastError());
+	return CB_OK;
+}
+
 template <bool NS>
-int graph_batch(cb_ctx *c, Lane &L, bool flags, bool use_f, bool fused, ScanParams &sp, ResolveParams &rp,
-    EmitParams &ep, size_t tiles, unsigned egrid, size_t cidx_bytes, cudaStream_t s) {
+int graph_batch(cb_ctx *c, Lane &L, bool flags, ScanParams &sp, ResolveParams &rp, EmitParams &ep, size_t tiles,
+    unsigned egrid, cudaStream_t s) {
 	Lane::Graph &G = L.gr[NS ? 1 : 0][flags ? 1 : 0];
 	void *a_scan[] = {(void *)&sp}, *a_res[] = {(void *)&rp}, *a_emit[] = {(void *)&ep};
-	cudaKernelNodeParams k_scan = {}, k_res = {}, k_commit = {}, k_emit = {};
+	cudaKernelNodeParams k_scan = {}, k_res = {}, k_emit = {};
 	k_scan.func = flags ? (void *)scan_kernel<NS, true> : (void *)scan_kernel<NS, false>;
-	k_scan.gridDim = dim3((unsigned)tiles);
-	k_scan.blockDim = dim3(TPB);
+	k_scan.gridDim = dim3(scan_grid(c, tiles));
+	k_scan.blockDim = dim3(SC_TPB);
+	k_scan.sharedMemBytes = (unsigned)SC_SMEM;
 	k_scan.kernelParams = a_scan;
-	if (fused) {
-		k_res.func = use_f ? (flags ? (void *)resolve_fused_kernel<NS, true, true> : (void *)resolve_fused_kernel<NS, false, true>)
-		                   : (flags ? (void *)resolve_fused_kernel<NS, true, false> : (void *)resolve_fused_kernel<NS, false, false>);
-	} else {
-		k_res.func = flags ? (void *)prepare_kernel<NS, true> : (void *)prepare_kernel<NS, false>;
-		k_commit.func = use_f ? (flags ? (void *)commit_fchain_kernel<NS, true> : (void *)commit_fchain_kernel<NS, false>)
-		                      : (flags ? (void *)commit_kernel<NS, true> : (void *)commit_kernel<NS, false>);
-		k_commit.gridDim = dim3(1);
-		k_commit.blockDim = dim3(CTPB);
-		k_commit.sharedMemBytes = (unsigned)cidx_bytes;
-		k_commit.kernelParams = a_res;
-	}
+	k_res.func = flags ? (void *)resolve_kernel<NS, true> : (void *)resolve_kernel<NS, false>;
 	k_res.gridDim = dim3(1);
 	k_res.blockDim = dim3(RTPB);
 	k_res.sharedMemBytes = (unsigned)(NIDX_MAX * sizeof(double));
@@ -289,12 +369,7 @@ int graph_batch(cb_ctx *c, Lane &L, bool flags, bool use_f, bool fused, ScanPara
 		CU(c, cudaGraphCreate(&G.g, 0));
 		CU(c, cudaGraphAddKernelNode(&G.n_scan, G.g, nullptr, 0, &k_scan));
 		CU(c, cudaGraphAddKernelNode(&G.n_res, G.g, &G.n_scan, 1, &k_res));
-		cudaGraphNode_t last = G.n_res;
-		if (!fused) {
-			CU(c, cudaGraphAddKernelNode(&G.n_commit, G.g, &G.n_res, 1, &k_commit));
-			last = G.n_commit;
-		}
-		CU(c, cudaGraphAddKernelNode(&G.n_emit, G.g, &last, 1, &k_emit));
+		CU(c, cudaGraphAddKernelNode(&G.n_emit, G.g, &G.n_res, 1, &k_emit));
 		cudaKernelNodeAttrValue lo, hi;
 		memset(&lo, 0, sizeof(lo));
 		memset(&hi, 0, sizeof(hi));
@@ -302,22 +377,18 @@ int graph_batch(cb_ctx *c, Lane &L, bool flags, bool use_f, bool fused, ScanPara
 		hi.priority = c->prio_greatest;
 		CU(c, cudaGraphKernelNodeSetAttribute(G.n_scan, cudaKernelNodeAttributePriority, &lo));
 		CU(c, cudaGraphKernelNodeSetAttribute(G.n_res, cudaKernelNodeAttributePriority, &hi));
-		if (G.n_commit)
-			CU(c, cudaGraphKernelNodeSetAttribute(G.n_commit, cudaKernelNodeAttributePriority, &hi));
 		CU(c, cudaGraphKernelNodeSetAttribute(G.n_emit, cudaKernelNodeAttributePriority, &hi));
 		CU(c, cudaGraphInstantiate(&G.ex, G.g, 0));
 	} else {
 		CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_scan, &k_scan));
 		CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_res, &k_res));
-		if (G.n_commit)
-			CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_commit, &k_commit));
 		CU(c, cudaGraphExecKernelNodeSetParams(G.ex, G.n_emit, &k_emit));
 	}
 	CU(c, cudaGraphLaunch(G.ex, s));
 	return CB_OK;
 }
 
-// Enqueue the four kernels of one batch.  depth 1 (or profiling): all on the main stream, in
+// Enqueue the three kernels (scan, resolve, emit) of one batch.  depth 1 (or profiling): all on the main stream, in
 // order.  depth > 1: the batch goes to its lane's stream (lanes rotate), the commit kernels are
 // chained across lanes by one event, so consecutive batches overlap; `in_ready` (optional) gates
 // the scan on the batch's inputs, and the batch's emit_done event is returned through `out_done`.
@@ -330,12 +401,16 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		*out_done = nullptr;
 	if (n == 0)
 		return CB_OK;
-	if (n > (1ull << 40))
+	if (n >= (1ull << 39))
 		return fail(c, CB_EINVAL, "batch too large");
-	const bool piped = (c->depth > 1) && !c->prof;
-	const int li = piped ? (int)(c->seq % (unsigned long long)c->depth) : 0;
-	Lane &L = c->lane[li];
 	const size_t tiles = (n + TILE - 1) / TILE;      // scan / prepare tiles
+	// A batch of up to 2M claims is bound by the latency of its three dependent kernels (~40 us), not by
+	// bandwidth: more batches in flight is the only lever (measured at 1M claims: 11.6 us per step with 5
+	// lanes, 9.0 with 8).
+	const int depth = (c->depth_auto && c->depth > 1 && tiles <= c->graph_max_tiles) ? CB_LANES : c->depth;
+	const bool piped = (depth > 1) && !c->prof;
+	const int li = piped ? (int)(c->seq % (unsigned long long)depth) : 0;
+	Lane &L = c->lane[li];
 	const size_t etiles = (n + ETILE - 1) / ETILE;   // emit tiles
 	int rc = ensure_scratch(c, L, tiles);
 	if (rc)
@@ -343,7 +418,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	if (piped) {
 		// size every active lane on the first batch of a new size: the allocations (which synchronise)
 		// happen once, up front, not one lane at a time over the next `depth` batches
-		for (int l = 0; l < c->depth; l++)
+		for (int l = 0; l < depth; l++)
 			if ((rc = ensure_scratch(c, c->lane[l], tiles)) || (rc = lane_streams(c, c->lane[l])))
 				return rc;
 	}
@@ -378,7 +453,6 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.rec_code = L.rec_code;
 	rp.rec_cend = L.rec_cend;
 	rp.tile_now0 = L.tile_now0;
-	rp.idx_ms = L.idx_ms;
 	{
 		ChainLink &ln = rp.link;
 		ln.err = &c->d_chain->err;
@@ -419,9 +493,8 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	rp.backend = d_backend;
 	rp.slot_backend = c->d_slot_backend;
 	rp.nslots = c->nslots;
-	const bool use_f = c->fchain;
-	rp.f_in = use_f ? c->d_chain->fs : nullptr;
-	rp.f_out = use_f ? (c->ring_n > 0 ? c->ring_next->fs : c->d_chain->fs) : nullptr;
+	rp.f_in = c->d_chain->fs;
+	rp.f_out = c->ring_n > 0 ? c->ring_next->fs : c->d_chain->fs;
 	rp.f_ring = c->ring_n > 0 ? (unsigned long long)c->ring_n : 1ull;
 
 	EmitParams ep;
@@ -467,27 +540,29 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	}
 	if (in_ready)
 		CU(c, cudaStreamWaitEvent(s, in_ready, 0));
-	if (use_f && c->fseed) {
+	if (c->fseed) {
 		// the state was set from the host: seed the slot this batch reads.  In a ring only the queue's
 		// first batch (rank 0) is seeded; every other batch gets its value from its predecessor.
 		if (c->ring_n == 0 || (c->ring_rank == 0 && c->chain_seq == 0))
 			fchain_seed_kernel<<<1, 1, 0, s>>>(c->g, c->d_chain->fs, rp.link.wait_val, rp.f_ring);
 		c->fseed = false;
 	}
-	if (c->prof)
+	if (c->prof && !c->prof_scan_only)
 		CU(c, cudaEventRecord(c->pe[0], s));
-	if (piped && c->graph) {
-		const size_t stride0 = (tiles + NIDX_MAX - 1) / NIDX_MAX;
-		rc = graph_batch<NS>(c, L, flags, use_f, c->fused, sp, rp, ep, tiles, egrid, ((tiles + stride0 - 1) / stride0) * sizeof(double), s);
+	const bool use_graph = piped && (c->graph_mode == 1 || (c->graph_mode < 0 && tiles <= c->graph_max_tiles));
+	if (use_graph) {
+		rc = graph_batch<NS>(c, L, flags, sp, rp, ep, tiles, egrid, s);
 		if (rc)
 			return rc;
 		c->chain_seq++;
 		if (c->comm) // the graph has no interior point to record: the collective starts after the emit
 			CU(c, cudaEventRecord(L.res_done, s));
-		c->launches += c->fused ? 3 : 4;
+		c->launches += 3;
 		CU(c, cudaGetLastError());
 		if (out_done || (flags && c->comm))
 			CU(c, cudaEventRecord(L.emit_done, s));
+		if ((rc = peers_post(c, L, s)))
+			return rc;
 		L.used = true;
 		L.coll_pending = false;
 		c->last_lane = li;
@@ -501,8 +576,9 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		// the lane's stream has the highest priority (prepare / commit / emit take the first CTA slot
 		// that frees up); the scan, which fills every SM, is launched into it at the lowest
 		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3((unsigned)tiles);
-		cfg.blockDim = dim3(TPB);
+		cfg.gridDim = dim3(scan_grid(c, tiles));
+		cfg.blockDim = dim3(SC_TPB);
+		cfg.dynamicSmemBytes = SC_SMEM;
 		cfg.stream = s;
 		cudaLaunchAttribute at[1];
 		at[0].id = cudaLaunchAttributePriority;
@@ -514,43 +590,24 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		else
 			CU(c, cudaLaunchKernelEx(&cfg, scan_kernel<NS, false>, sp));
 	} else if (flags)
-		scan_kernel<NS, true><<<(unsigned)tiles, TPB, 0, s>>>(sp);
+		scan_kernel<NS, true><<<scan_grid(c, tiles), SC_TPB, SC_SMEM, s>>>(sp);
 	else
-		scan_kernel<NS, false><<<(unsigned)tiles, TPB, 0, s>>>(sp);
+		scan_kernel<NS, false><<<scan_grid(c, tiles), SC_TPB, SC_SMEM, s>>>(sp);
+	if (c->prof_scan_only) { // measurement: back-to-back scan launches, timed by the caller's events on this stream
+		c->launches += 1;
+		CU(c, cudaGetLastError());
+		return CB_OK;
+	}
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[1], s));
-	const bool fused = c->fused; // CB_FUSED=1: prepare + commit in one launch (not yet validated on hardware)
-	if (fused) {
-		if (use_f) {
-			if (flags)
-				resolve_fused_kernel<NS, true, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-			else
-				resolve_fused_kernel<NS, false, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-		} else if (flags)
-			resolve_fused_kernel<NS, true, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-		else
-			resolve_fused_kernel<NS, false, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-	}
-	// prepare: independent of the ControlledDelay state, so it overlaps the other lanes' commits
-	else if (flags)
-		prepare_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
+	// resolve = prepare_part (independent of the ControlledDelay state: overlaps the other lanes' commits)
+	// + commit_part, the only stage that is serial across batches.  The order is kept inside the kernel:
+	// commit(k) spins (one thread) on the chain word until batch k-1 has published its state, so the
+	// hand-over costs an L2 round trip instead of a cross-stream event (~5 us measured).
+	if (flags)
+		resolve_kernel<NS, true><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	else
-		prepare_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
-	// commit: the only stage that is serial across batches.  The order is kept inside the kernels:
-	// commit(k) spins (one thread) on the chain word until batch k-1 has published its state, so
-	// the hand-over costs an L2 round trip instead of a cross-stream event (~5 us measured).
-	const size_t cidx_bytes = ((tiles + ((tiles + NIDX_MAX - 1) / NIDX_MAX) - 1) / ((tiles + NIDX_MAX - 1) / NIDX_MAX)) * sizeof(double);
-	if (fused) {
-		// the commit ran inside resolve_fused_kernel
-	} else if (use_f) {
-		if (flags)
-			commit_fchain_kernel<NS, true><<<1, CTPB, cidx_bytes, s>>>(rp);
-		else
-			commit_fchain_kernel<NS, false><<<1, CTPB, cidx_bytes, s>>>(rp);
-	} else if (flags)
-		commit_kernel<NS, true><<<1, CTPB, cidx_bytes, s>>>(rp);
-	else
-		commit_kernel<NS, false><<<1, CTPB, cidx_bytes, s>>>(rp);
+		resolve_kernel<NS, false><<<1, RTPB, NIDX_MAX * sizeof(double), s>>>(rp);
 	c->chain_seq++;
 	if (c->prof)
 		CU(c, cudaEventRecord(c->pe[2], s));
@@ -560,10 +617,12 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		emit_kernel<true><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
 	else
 		emit_kernel<false><<<egrid, ETPB, ep.table_smem_bytes, s>>>(ep);
-	c->launches += fused ? 3 : 4;
+	c->launches += 3;
 	CU(c, cudaGetLastError());
 	if (out_done || (piped && flags && c->comm))
 		CU(c, cudaEventRecord(L.emit_done, s));
+	if ((rc = peers_post(c, L, s)))
+		return rc;
 	L.used = true;
 	L.coll_pending = false;
 	c->last_lane = li;
@@ -588,17 +647,21 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
 	int rc = drain(c);
 	if (rc)
 		return rc;
-	DevState h;
-	BatchCtl b;
-	memset(&b, 0, sizeof(b));
-	unsigned long long chain[2] = {0, 0};
-	CU(c, cudaMemcpy(chain, c->d_chain, sizeof(chain), cudaMemcpyDeviceToHost));
+	// three small device-to-host copies into pinned memory, one wait (a blocking cudaMemcpy each costs ~10 us)
+	if (!c->h_stats)
+		CU(c, cudaMallocHost((void **)&c->h_stats, sizeof(*c->h_stats)));
+	memset(&c->h_stats->ctl, 0, sizeof(BatchCtl));
+	CU(c, cudaMemcpyAsync(c->h_stats->chain, c->d_chain, sizeof(c->h_stats->chain), cudaMemcpyDeviceToHost, c->s_out));
+	CU(c, cudaMemcpyAsync(&c->h_stats->st, c->g, sizeof(DevState), cudaMemcpyDeviceToHost, c->s_out));
+	if (c->last_lane >= 0)
+		CU(c, cudaMemcpyAsync(&c->h_stats->ctl, c->lane[c->last_lane].ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, c->s_out));
+	CU(c, cudaStreamSynchronize(c->s_out));
+	const unsigned long long *chain = c->h_stats->chain;
+	const DevState &h = c->h_stats->st;
+	const BatchCtl &b = c->h_stats->ctl;
 	if (chain[1] != 0 || (c->ring_n == 0 && chain[0] != c->chain_seq))
 		return fail(c, CB_ESTATE, "commit chain broken: %llu of %llu batches committed, %llu hand-over timeouts", chain[0],
 		    c->chain_seq, chain[1]);
-	CU(c, cudaMemcpy(&h, c->g, sizeof(h), cudaMemcpyDeviceToHost));
-	if (c->last_lane >= 0)
-		CU(c, cudaMemcpy(&b, c->lane[c->last_lane].ctl, sizeof(b), cudaMemcpyDeviceToHost));
 	c->tot_valid = true;
 	c->tot_seq = c->chain_seq;
 	c->tot_epoch = c->epoch;
@@ -684,22 +747,31 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 	rc = ensure_staging(c, n);
 	if (rc)
 		return rc;
-	// Staging chunk: a batch that would fit one chunk is still cut in ~3 so that the copy-in of
-	// one piece overlaps the kernels and the copy-out of the previous ones (measured with
-	// tools/e2e_breakdown.py: 1M claims 1.04 ms as one chunk, 0.50-0.54 ms as 2-4 chunks).
-	size_t chunk = c->chunk;
+	// Staging chunks.  The H2D copies run back to back on the copy engine; a chunk's kernels and its D2H
+	// overlap the copy-in of the chunks behind it, so what the call pays beyond the PCIe time of its inputs
+	// is the LAST chunk's kernels and copy-out.  Chunks therefore shrink towards the end (40 % of what is left,
+	// at most c->chunk, at least 64K claims): the exposed tail is a few tens of microseconds at any size.
+	std::vector<size_t> plan;
 	{
-		size_t third = ((n + 2) / 3 + ETILE - 1) / ETILE * ETILE;
-		const size_t floor_chunk = 64 * (size_t)ETILE; // 256K claims: below this the per-chunk cost wins
-		if (third < floor_chunk)
-			third = floor_chunk;
-		if (third < chunk)
-			chunk = third;
+		const size_t floor_chunk = 16 * (size_t)ETILE; // 64K claims: below this the per-chunk cost wins
+		size_t left = n;
+		while (left > 0) {
+			size_t m = ((left * 2 / 5) + ETILE - 1) / ETILE * ETILE;
+			if (m > c->chunk)
+				m = c->chunk;
+			if (m < floor_chunk)
+				m = floor_chunk;
+			if (m > left || (left - m < floor_chunk / 2 && left <= c->stage_cap))
+				m = left; // a sliver would cost more than it saves (the staging buffers hold stage_cap claims)
+			plan.push_back(m);
+			left -= m;
+		}
 	}
-	const size_t nchunks = (n + chunk - 1) / chunk;
+	const size_t nchunks = plan.size();
+	size_t lo = 0;
 	for (size_t ci = 0; ci < nchunks; ci++) {
 		Staging &s = c->st[ci % NBUF];
-		const size_t lo = ci * chunk, m = (n - lo < chunk) ? n - lo : chunk;
+		const size_t m = plan[ci];
 		if (ci >= NBUF)
 			CU(c, cudaStreamWaitEvent(c->s_in, s.out_done, 0));
 		CU(c, cudaMemcpyAsync(s.start, (const char *)start + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
@@ -721,6 +793,7 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		if (backend)
 			CU(c, cudaMemcpyAsync(backend + lo, s.backend, m * 4, cudaMemcpyDeviceToHost, c->s_out));
 		CU(c, cudaEventRecord(s.out_done, c->s_out));
+		lo += m;
 	}
 	const double T2 = dbg_t ? tnow() : 0;
 	CU(c, cudaStreamSynchronize(c->s_out));
@@ -766,8 +839,8 @@ int rebuild_slots(cb_ctx *c) {
 		// have = 0, dead = 0: reuse d_want's neighbour buffers as zeroed inputs
 		int32_t *d_have = c->d_add + c->slot_cap; // zeroed tail, see cb_backends_set
 		uint8_t *d_dead = (uint8_t *)(d_have + c->key_cap);
-		plan_rebalance_kernel<<<1, 1, 0, s>>>(d_have, d_dead, c->B, c->nslots, c->nslots, 0, c->d_want, c->d_add,
-		    d_nadd, nullptr, nullptr, c->d_ints + 4);
+		plan_rebalance_kernel<<<1, TOPO_TPB, 0, s>>>(d_have, d_dead, c->B, c->nslots, c->nslots, 0, c->d_want, c->d_add,
+		    d_nadd, nullptr, nullptr, c->d_ints + 4, c->d_plan_scratch);
 	}
 	slot_table_kernel<<<8, 256, 0, s>>>(c->d_keys, c->d_add, d_nadd, c->d_slot_backend, c->slot_cap, d_nslots);
 	c->launches += 2;
@@ -798,7 +871,8 @@ int ensure_topology(cb_ctx *c, int keys, int slots) {
 	int rc;
 	if ((rc = dev_alloc(c, &c->d_keys, kc)) || (rc = dev_alloc(c, &c->d_want, kc)) ||
 	    (rc = dev_alloc(c, &c->d_prio, kc)) || (rc = dev_alloc(c, &c->d_weight, kc)) ||
-	    (rc = dev_alloc(c, &c->d_add, (size_t)sc + kc + kc)) || (rc = dev_alloc(c, &c->d_slot_backend, sc)))
+	    (rc = dev_alloc(c, &c->d_add, (size_t)sc + kc + kc)) || (rc = dev_alloc(c, &c->d_slot_backend, sc)) ||
+	    (rc = dev_alloc(c, &c->d_plan_scratch, 2 * ((size_t)kc + 1))))
 		return rc;
 	CU(c, cudaMemset(c->d_add, 0, ((size_t)sc + kc + kc) * sizeof(int32_t)));
 	CU(c, cudaMemset(c->d_prio, 0, sizeof(int32_t) * kc));
@@ -842,20 +916,32 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	cb_ctx *c = new (std::nothrow) cb_ctx();
 	if (!c)
 		return fail(nullptr, CB_ENOMEM, "out of host memory");
+	int prev_dev = -1;
+	if (cudaGetDevice(&prev_dev) != cudaSuccess)
+		prev_dev = -1;
 	c->device = device;
 	c->emit_grid = prop.multiProcessorCount * 4;
+	c->scan_ctas = prop.multiProcessorCount * CB_SCAN_MINBLOCKS;
+	if (getenv("CB_SCAN_CTAS") && atoi(getenv("CB_SCAN_CTAS")) > 0) // tuning knobs (measurement only)
+		c->scan_ctas = atoi(getenv("CB_SCAN_CTAS"));
+	if (getenv("CB_SCAN_TPW") && atoi(getenv("CB_SCAN_TPW")) > 0)
+		c->scan_tpw = atoi(getenv("CB_SCAN_TPW"));
 	const char *ck = getenv("CB_CHUNK");
 	if (ck && atoll(ck) >= ETILE)
 		c->chunk = ((size_t)atoll(ck) + ETILE - 1) / ETILE * ETILE;
 	const char *dp = getenv("CB_PIPELINE_DEPTH");
-	if (dp && atoi(dp) >= 1 && atoi(dp) <= CB_LANES)
+	if (dp && atoi(dp) >= 1 && atoi(dp) <= CB_LANES) {
 		c->depth = atoi(dp);
+		c->depth_auto = false;
+	}
 #define CU0(call)                                                                          \
 	do {                                                                                   \
 		cudaError_t e_ = (call);                                                           \
 		if (e_ != cudaSuccess) {                                                           \
 			fail(nullptr, CB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_));              \
 			cb_destroy(c);                                                                 \
+			if (prev_dev >= 0)                                                             \
+				cudaSetDevice(prev_dev);                                                   \
 			return CB_ECUDA;                                                               \
 		}                                                                                  \
 	} while (0)
@@ -874,28 +960,8 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
-	if (getenv("CB_FCHAIN") && atoi(getenv("CB_FCHAIN")) != 0) {
-		c->fchain = true;
-		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-		CU0(cudaFuncSetAttribute(commit_fchain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-		CU0(cudaFuncSetAttribute(commit_fchain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	}
-	c->graph = getenv("CB_GRAPH") && atoi(getenv("CB_GRAPH")) != 0;
-	if (getenv("CB_FUSED") && atoi(getenv("CB_FUSED")) != 0) {
-		c->fused = true;
-#define FUSED_ATTR(a, b, f)                                                                                 \
-	CU0(cudaFuncSetAttribute(resolve_fused_kernel<a, b, f>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8))
-		FUSED_ATTR(true, true, true);
-		FUSED_ATTR(true, true, false);
-		FUSED_ATTR(true, false, true);
-		FUSED_ATTR(true, false, false);
-		FUSED_ATTR(false, true, true);
-		FUSED_ATTR(false, true, false);
-		FUSED_ATTR(false, false, true);
-		FUSED_ATTR(false, false, false);
-#undef FUSED_ATTR
-	}
+	if (getenv("CB_GRAPH")) // measurement override of the launch mode: 0 = never a graph, 1 = always
+		c->graph_mode = atoi(getenv("CB_GRAPH")) != 0 ? 1 : 0;
 	CU0(cudaMalloc((void **)&c->d_chain, sizeof(ChainMem)));
 	CU0(cudaMemset(c->d_chain, 0, sizeof(ChainMem)));
 	for (int l = 0; l < CB_LANES; l++) {
@@ -914,22 +980,38 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	CU0(cudaMalloc((void **)&c->d_dbl, 64 * sizeof(double)));
 	for (int k = 0; k < 4; k++)
 		CU0(cudaEventCreate(&c->pe[k]));
-	CU0(cudaFuncSetAttribute(prepare_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(prepare_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(prepare_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(prepare_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(commit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(commit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(commit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
-	CU0(cudaFuncSetAttribute(commit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+	CU0(cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+	CU0(cudaFuncSetAttribute(scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+	CU0(cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+	CU0(cudaFuncSetAttribute(resolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(resolve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
+	CU0(cudaFuncSetAttribute(resolve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NIDX_MAX * 8));
 	CU0(cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
 	CU0(cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+	{
+		// one shared-memory carveout for every kernel of the pipeline: the scan needs nearly all of an SM's
+		// shared memory, and an SM whose carveout differs between consecutive kernels is reconfigured (drained)
+		// at every switch
+		const void *fns[] = {(const void *)scan_kernel<true, true>, (const void *)scan_kernel<true, false>,
+		    (const void *)scan_kernel<false, true>, (const void *)scan_kernel<false, false>,
+		    (const void *)resolve_kernel<true, true>, (const void *)resolve_kernel<true, false>,
+		    (const void *)resolve_kernel<false, true>, (const void *)resolve_kernel<false, false>,
+		    (const void *)emit_kernel<true>, (const void *)emit_kernel<false>, (const void *)peer_post_kernel,
+		    (const void *)fchain_seed_kernel};
+		for (const void *f : fns)
+			CU0(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+	}
 #undef CU0
+	if (prev_dev >= 0 && prev_dev != device) // the caller's current device is left as it was
+		cudaSetDevice(prev_dev);
 	*out = c;
 	return CB_OK;
 }
 
 extern "C" void cb_destroy(cb_ctx *c) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return;
 	cudaSetDevice(c->device);
@@ -952,7 +1034,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 				if (L.gr[a][b].g)
 					cudaGraphDestroy(L.gr[a][b].g);
 			}
-		void *fr[] = {L.idx_ms, L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
+		void *fr[] = {L.ctl, L.sdesc, L.ev_count, L.rec_fc, L.rec_cend, L.xcnt, L.hj_info, L.ticket, L.ev, L.evc,
 		    L.ev_q, L.ev_d, L.rec_code, L.xev, L.hj_lo, L.hj_b, L.tile_now0, L.iv_lo, L.iv_hi, L.iv_cum, L.ev_now, L.hj_F};
 		for (void *p : fr)
 			if (p)
@@ -963,12 +1045,19 @@ extern "C" void cb_destroy(cb_ctx *c) {
 				cudaEventDestroy(e);
 	}
 	ring_close(c);
+	peers_close(c);
+	if (c->d_board)
+		cudaFree(c->d_board);
+	if (c->d_peer_ptrs)
+		cudaFree(c->d_peer_ptrs);
+	if (c->d_peer_out)
+		cudaFree(c->d_peer_out);
 	void *qfrees[] = {c->d_q, c->q_start, c->q_deadline, c->q_ticket, c->q_res, c->q_stage, c->q_waiting, c->q_tmo};
 	for (void *p : qfrees)
 		if (p)
 			cudaFree(p);
 	void *frees[] = {c->g, c->d_chain, c->d_keys, c->d_want, c->d_add, c->d_slot_backend, c->d_prio, c->d_weight, c->d_ints,
-	    c->d_dbl};
+	    c->d_dbl, c->d_plan_scratch};
 	for (void *p : frees)
 		if (p)
 			cudaFree(p);
@@ -983,6 +1072,8 @@ extern "C" void cb_destroy(cb_ctx *c) {
 		if (s.out_done)
 			cudaEventDestroy(s.out_done);
 	}
+	if (c->h_stats)
+		cudaFreeHost(c->h_stats);
 	for (int k = 0; k < 4; k++)
 		if (c->pe[k])
 			cudaEventDestroy(c->pe[k]);
@@ -995,6 +1086,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 }
 
 extern "C" int cb_set_stream(cb_ctx *c, void *stream) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	int rc = drain(c);
@@ -1006,17 +1098,20 @@ extern "C" int cb_set_stream(cb_ctx *c, void *stream) {
 }
 
 extern "C" int cb_set_pipeline_depth(cb_ctx *c, int depth) {
+	DevGuard dev_guard_(c);
 	if (!c || depth < 1 || depth > CB_LANES)
 		return c ? fail(c, CB_EINVAL, "pipeline depth must be 1..%d", CB_LANES) : CB_EINVAL;
 	int rc = drain(c);
 	if (rc)
 		return rc;
 	c->depth = depth;
+	c->depth_auto = false;
 	return CB_OK;
 }
 
 // make the main (caller's) stream wait for every batch enqueued so far
 extern "C" int cb_join(cb_ctx *c) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	if (c->last_lane >= 0 && c->depth > 1) {
@@ -1034,12 +1129,14 @@ extern "C" int cb_join(cb_ctx *c) {
 }
 
 extern "C" int cb_synchronize(cb_ctx *c) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	return drain(c);
 }
 
 extern "C" void *cb_host_alloc(cb_ctx *c, size_t bytes) {
+	DevGuard dev_guard_(c);
 	void *p = nullptr;
 	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
 		if (c)
@@ -1055,6 +1152,7 @@ extern "C" void cb_host_free(cb_ctx *, void *p) {
 
 // =============================================================================== CoDel
 extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	c->tot_valid = false;
@@ -1075,6 +1173,7 @@ extern "C" int cb_codel_init(cb_ctx *c, double target_ms) {
 }
 
 extern "C" int cb_codel_get_state(cb_ctx *c, cb_codel_state *out) {
+	DevGuard dev_guard_(c);
 	if (!c || !out)
 		return CB_EINVAL;
 	cb_batch_stats st;
@@ -1086,6 +1185,7 @@ extern "C" int cb_codel_get_state(cb_ctx *c, cb_codel_state *out) {
 }
 
 extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
+	DevGuard dev_guard_(c);
 	if (!c || !in)
 		return CB_EINVAL;
 	c->tot_valid = false;
@@ -1108,6 +1208,7 @@ extern "C" int cb_codel_set_state(cb_ctx *c, const cb_codel_state *in) {
 }
 
 extern "C" int cb_codel_empty(cb_ctx *c, int64_t now_ns) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	c->tot_valid = false;
@@ -1125,6 +1226,7 @@ extern "C" int cb_codel_empty(cb_ctx *c, int64_t now_ns) {
 }
 
 extern "C" int cb_codel_max_idle(cb_ctx *c, int64_t now_ns, double *out_ms) {
+	DevGuard dev_guard_(c);
 	if (!c || !out_ms)
 		return CB_EINVAL;
 	if (!c->codel_ready)
@@ -1141,6 +1243,7 @@ extern "C" int cb_codel_max_idle(cb_ctx *c, int64_t now_ns, double *out_ms) {
 }
 
 extern "C" int cb_codel_overloaded(cb_ctx *c, int64_t start_ns, int64_t now_ns, int *drop) {
+	DevGuard dev_guard_(c);
 	if (!c || !drop)
 		return CB_EINVAL;
 	c->tot_valid = false;
@@ -1158,32 +1261,56 @@ extern "C" int cb_codel_overloaded(cb_ctx *c, int64_t start_ns, int64_t now_ns, 
 	return CB_OK;
 }
 
+extern "C" int cb_codel_overloaded_ms(cb_ctx *c, double start_ms, double now_ms, int *drop) {
+	DevGuard dev_guard_(c);
+	if (!c || !drop)
+		return CB_EINVAL;
+	c->tot_valid = false;
+	c->fseed = true;
+	if (!c->codel_ready)
+		return fail(c, CB_ESTATE, "cb_codel_init has not been called");
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	overloaded_one_ms_kernel<<<1, 1, 0, c->stream>>>(c->g, start_ms, now_ms, c->d_ints + 5);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(drop, c->d_ints + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return CB_OK;
+}
+
 // =============================================================================== batches
 extern "C" int cb_admit_batch(cb_ctx *c, const int64_t *start_ns, const int64_t *now_ns, const uint8_t *flags,
     size_t n, uint8_t *decision, int32_t *slot, int32_t *backend, cb_batch_stats *stats) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	return host_batch<true>(c, start_ns, now_ns, flags, n, decision, slot, backend, stats);
 }
 extern "C" int cb_admit_batch_ms(cb_ctx *c, const double *start_ms, const double *now_ms, const uint8_t *flags,
     size_t n, uint8_t *decision, int32_t *slot, int32_t *backend, cb_batch_stats *stats) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	return host_batch<false>(c, start_ms, now_ms, flags, n, decision, slot, backend, stats);
 }
 extern "C" int cb_admit_batch_dev(cb_ctx *c, const int64_t *d_start, const int64_t *d_now, const uint8_t *d_flags,
     size_t n, uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	return enqueue_batch<true>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend, nullptr, nullptr);
 }
 extern "C" int cb_admit_batch_ms_dev(cb_ctx *c, const double *d_start, const double *d_now, const uint8_t *d_flags,
     size_t n, uint8_t *d_decision, int32_t *d_slot, int32_t *d_backend) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	return enqueue_batch<false>(c, d_start, d_now, d_flags, n, d_decision, d_slot, d_backend, nullptr, nullptr);
 }
 extern "C" int cb_batch_stats_get(cb_ctx *c, cb_batch_stats *out) {
+	DevGuard dev_guard_(c);
 	if (!c || !out)
 		return CB_EINVAL;
 	return fetch_stats(c, out);
@@ -1192,6 +1319,7 @@ extern "C" int cb_batch_stats_get(cb_ctx *c, cb_batch_stats *out) {
 // ============================================================================== topology
 extern "C" int cb_backends_set(cb_ctx *c, const cb_backend *tbl, int32_t B, const double *insert_u, int32_t nslots,
     int mode) {
+	DevGuard dev_guard_(c);
 	if (!c || B < 0 || nslots < 0 || (B > 0 && !insert_u))
 		return c ? fail(c, CB_EINVAL, "bad backend table arguments") : CB_EINVAL;
 	if (mode != CB_BALANCE_UNIFORM && mode != CB_BALANCE_SRV_WEIGHTED)
@@ -1244,6 +1372,7 @@ extern "C" int cb_backends_set(cb_ctx *c, const cb_backend *tbl, int32_t B, cons
 }
 
 extern "C" int cb_backend_added(cb_ctx *c, int32_t key, const cb_backend *be, double u) {
+	DevGuard dev_guard_(c);
 	if (!c || key < 0 || !(u >= 0.0 && u < 1.0))
 		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
 	{
@@ -1267,6 +1396,7 @@ extern "C" int cb_backend_added(cb_ctx *c, int32_t key, const cb_backend *be, do
 }
 
 extern "C" int cb_backend_removed(cb_ctx *c, int32_t key) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	{
@@ -1287,6 +1417,7 @@ extern "C" int cb_backend_removed(cb_ctx *c, int32_t key) {
 }
 
 extern "C" int cb_reshuffle(cb_ctx *c, double u) {
+	DevGuard dev_guard_(c);
 	if (!c || !(u >= 0.0 && u < 1.0))
 		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
 	if (c->B <= 1)
@@ -1304,6 +1435,7 @@ extern "C" int cb_reshuffle(cb_ctx *c, double u) {
 
 extern "C" int cb_backends_get(cb_ctx *c, int32_t *n_keys, int32_t *keys_out, int32_t *n_slots,
     int32_t *slot_backend_out) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	if (n_keys)
@@ -1322,6 +1454,7 @@ extern "C" int cb_backends_get(cb_ctx *c, int32_t *n_keys, int32_t *keys_out, in
 extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *dead, int32_t B, int32_t target,
     int32_t max, int singleton, int32_t *want_out, int32_t *add_out, int32_t *n_add, int32_t *rm_key_out,
     int32_t *rm_ord_out, int32_t *n_rm) {
+	DevGuard dev_guard_(c);
 	if (!c || B < 0 || (B > 0 && (!have || !dead)))
 		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
 	if (target < 0) // mod_assert.ok(target >= 0), lib/utils.js:248
@@ -1335,7 +1468,7 @@ extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *
 		total_have += have[k];
 	}
 	size_t nb = (size_t)(B > 0 ? B : 1), na = (size_t)max + 1, nr = (size_t)total_have + 1;
-	int32_t *d_have = nullptr, *d_want = nullptr, *d_add = nullptr, *d_rk = nullptr, *d_ro = nullptr;
+	int32_t *d_have = nullptr, *d_want = nullptr, *d_add = nullptr, *d_rk = nullptr, *d_ro = nullptr, *d_scr = nullptr;
 	uint8_t *d_dead = nullptr;
 	int *d_cnt = nullptr;
 	CU(c, cudaMalloc((void **)&d_have, nb * 4));
@@ -1345,13 +1478,14 @@ extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *
 	CU(c, cudaMalloc((void **)&d_rk, nr * 4));
 	CU(c, cudaMalloc((void **)&d_ro, nr * 4));
 	CU(c, cudaMalloc((void **)&d_cnt, 8));
+	CU(c, cudaMalloc((void **)&d_scr, 2 * (nb + 1) * 4));
 	cudaStream_t s = c->stream;
 	if (B > 0) {
 		CU(c, cudaMemcpyAsync(d_have, have, nb * 4, cudaMemcpyHostToDevice, s));
 		CU(c, cudaMemcpyAsync(d_dead, dead, nb, cudaMemcpyHostToDevice, s));
 	}
-	plan_rebalance_kernel<<<1, 1, 0, s>>>(d_have, d_dead, B, target, max, singleton, d_want, d_add, d_cnt, d_rk,
-	    d_ro, d_cnt + 1);
+	plan_rebalance_kernel<<<1, TOPO_TPB, 0, s>>>(d_have, d_dead, B, target, max, singleton, d_want, d_add, d_cnt, d_rk,
+	    d_ro, d_cnt + 1, d_scr);
 	c->launches++;
 	CU(c, cudaGetLastError());
 	int cnt[2] = {0, 0};
@@ -1376,6 +1510,7 @@ extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *
 	cudaFree(d_rk);
 	cudaFree(d_ro);
 	cudaFree(d_cnt);
+	cudaFree(d_scr);
 	return CB_OK;
 }
 
@@ -1395,6 +1530,7 @@ extern "C" int cb_comm_unique_id(void *out, size_t *bytes) {
 }
 
 extern "C" int cb_comm_init(cb_ctx *c, int nranks, int rank, const void *unique_id, size_t bytes) {
+	DevGuard dev_guard_(c);
 	if (!c || nranks < 1 || rank < 0 || rank >= nranks || !unique_id || bytes < sizeof(nccl_uid))
 		return c ? fail(c, CB_EINVAL, "bad communicator arguments") : CB_EINVAL;
 	if (!g_nccl.load())
@@ -1419,6 +1555,7 @@ extern "C" int cb_comm_init(cb_ctx *c, int nranks, int rank, const void *unique_
 
 // ---- one logical queue over several GPUs ------------------------------------------------------
 extern "C" int cb_ring_mailbox(cb_ctx *c, void *ipc_handle_out, size_t *len, void **local_ptr_out) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	if (ipc_handle_out) {
@@ -1435,6 +1572,7 @@ extern "C" int cb_ring_mailbox(cb_ctx *c, void *ipc_handle_out, size_t *len, voi
 }
 
 extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next_ipc_handle, void *next_local_ptr) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	c->tot_valid = false;
@@ -1466,6 +1604,17 @@ extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next
 		c->ring_next = (ChainMem *)ptr;
 		c->ring_next_ipc = true;
 	} else {
+		// a mailbox of another context of this process: if it lives on another GPU this device needs
+		// peer access to it (the IPC path enables it lazily)
+		cudaPointerAttributes pa;
+		if (cudaPointerGetAttributes(&pa, next_local_ptr) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+		    pa.device != c->device) {
+			cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+				return fail(c, CB_ECUDA, "no peer access from device %d to device %d: %s", c->device, pa.device,
+				    cudaGetErrorString(e));
+			(void)cudaGetLastError();
+		}
 		c->ring_next = (ChainMem *)next_local_ptr;
 	}
 	// this rank's mailbox: sequence 0, holding this rank's current state (rank 0 starts the queue
@@ -1480,7 +1629,121 @@ extern "C" int cb_ring_connect(cb_ctx *c, int nranks, int rank, const void *next
 	return CB_OK;
 }
 
+// ---- per-batch global counts over peer memory ---------------------------------------------------
+static int peers_board(cb_ctx *c) {
+	if (c->d_board)
+		return CB_OK;
+	CU(c, cudaMalloc((void **)&c->d_board, sizeof(PeerBoard)));
+	CU(c, cudaMemset(c->d_board, 0, sizeof(PeerBoard)));
+	CU(c, cudaMalloc((void **)&c->d_peer_ptrs, sizeof(PeerBoard *) * PB_MAXR));
+	CU(c, cudaMalloc((void **)&c->d_peer_out, 4 * sizeof(unsigned long long)));
+	return CB_OK;
+}
+
+extern "C" int cb_peers_board(cb_ctx *c, void *ipc_handle_out, size_t *len, void **local_ptr_out) {
+	DevGuard dev_guard_(c);
+	if (!c)
+		return CB_EINVAL;
+	int rc = peers_board(c);
+	if (rc)
+		return rc;
+	if (ipc_handle_out) {
+		if (!len || *len < sizeof(cudaIpcMemHandle_t))
+			return fail(c, CB_EINVAL, "the IPC handle needs %zu bytes", sizeof(cudaIpcMemHandle_t));
+		cudaIpcMemHandle_t h;
+		CU(c, cudaIpcGetMemHandle(&h, c->d_board));
+		memcpy(ipc_handle_out, &h, sizeof(h));
+		*len = sizeof(h);
+	}
+	if (local_ptr_out)
+		*local_ptr_out = c->d_board;
+	return CB_OK;
+}
+
+extern "C" int cb_peers_connect(cb_ctx *c, int nranks, int rank, const void *ipc_handles, void *const *local_ptrs) {
+	DevGuard dev_guard_(c);
+	if (!c)
+		return CB_EINVAL;
+	int rc = drain(c);
+	if (rc)
+		return rc;
+	peers_close(c);
+	if (nranks == 0)
+		return CB_OK;
+	if (nranks < 1 || nranks > PB_MAXR || rank < 0 || rank >= nranks)
+		return fail(c, CB_EINVAL, "bad peer geometry (at most %d ranks)", PB_MAXR);
+	if (nranks > 1 && !ipc_handles && !local_ptrs)
+		return fail(c, CB_EINVAL, "give the ranks' boards as IPC handles or as pointers of this process");
+	if ((rc = peers_board(c)))
+		return rc;
+	CU(c, cudaMemset(c->d_board, 0, sizeof(PeerBoard)));
+	PeerBoard *ptrs[PB_MAXR] = {};
+	for (int r = 0; r < nranks; r++) {
+		if (r == rank) {
+			ptrs[r] = c->d_board;
+		} else if (local_ptrs && local_ptrs[r]) {
+			cudaPointerAttributes pa;
+			if (cudaPointerGetAttributes(&pa, local_ptrs[r]) == cudaSuccess && pa.type == cudaMemoryTypeDevice &&
+			    pa.device != c->device) {
+				cudaError_t e = cudaDeviceEnablePeerAccess(pa.device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+					return fail(c, CB_ECUDA, "no peer access from device %d to device %d: %s", c->device, pa.device,
+					    cudaGetErrorString(e));
+				(void)cudaGetLastError();
+			}
+			ptrs[r] = (PeerBoard *)local_ptrs[r];
+		} else if (ipc_handles) {
+			cudaIpcMemHandle_t h;
+			memcpy(&h, (const char *)ipc_handles + (size_t)r * sizeof(h), sizeof(h));
+			void *ptr = nullptr;
+			cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) {
+				peers_close(c);
+				return fail(c, CB_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+			}
+			c->peer_ipc[r] = ptr;
+			ptrs[r] = (PeerBoard *)ptr;
+		} else {
+			return fail(c, CB_EINVAL, "no board given for rank %d", r);
+		}
+	}
+	CU(c, cudaMemcpy(c->d_peer_ptrs, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+	c->peers_n = nranks;
+	c->peers_rank = rank;
+	c->peer_step = 0;
+	return CB_OK;
+}
+
+extern "C" int cb_peers_counts(cb_ctx *c, cb_global_counts *out) {
+	DevGuard dev_guard_(c);
+	if (!c || !out)
+		return CB_EINVAL;
+	if (c->peers_n <= 0)
+		return fail(c, CB_ESTATE, "cb_peers_connect has not been called");
+	// after every batch enqueued so far (their post kernels are on the lanes' streams)
+	int rc = cb_join(c);
+	if (rc)
+		return rc;
+	peer_counts_kernel<<<1, 32, 0, c->stream>>>(peer_link(c, c->peer_step), c->peer_step, c->d_peer_out);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	unsigned long long h[4] = {0, 0, 0, 0};
+	CU(c, cudaMemcpyAsync(h, c->d_peer_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	unsigned long long err = 0;
+	CU(c, cudaMemcpy(&err, (char *)c->d_board + offsetof(PeerBoard, err), sizeof(err), cudaMemcpyDeviceToHost));
+	if (err != 0 || h[0] < c->peer_step)
+		return fail(c, CB_ESTATE, "peer boards: %llu of %llu steps complete on every rank, %llu time-outs", h[0],
+		    c->peer_step, err);
+	out->steps = h[0];
+	out->drops = h[1];
+	out->admits = h[2];
+	out->n = h[3];
+	return CB_OK;
+}
+
 extern "C" int cb_allreduce_counts(cb_ctx *c) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	if (!c->comm)
@@ -1503,6 +1766,136 @@ extern "C" int cb_allreduce_counts(cb_ctx *c) {
 		CU(c, cudaEventRecord(L.coll_done, s));
 		L.coll_pending = true;
 	}
+	return CB_OK;
+}
+
+// =========================================================================== resolver ingestion
+// ipaddr.js parse(address).toNormalizedString() (package.json: ipaddr.js >=1.1 <2): IPv4 dotted quad; IPv6 eight
+// groups in lowercase hex without leading zeros and without '::' compression.  false: not an IP address.
+static bool normalise_address(const char *addr, std::string *out) {
+	unsigned char b[16];
+	char buf[64];
+	if (inet_pton(AF_INET, addr, b) == 1) {
+		snprintf(buf, sizeof(buf), "%u.%u.%u.%u", b[0], b[1], b[2], b[3]);
+		*out = buf;
+		return true;
+	}
+	if (inet_pton(AF_INET6, addr, b) == 1) {
+		std::string r;
+		for (int g = 0; g < 8; g++) {
+			snprintf(buf, sizeof(buf), g ? ":%x" : "%x", (unsigned)((b[2 * g] << 8) | b[2 * g + 1]));
+			r += buf;
+		}
+		*out = r;
+		return true;
+	}
+	return false;
+}
+
+extern "C" int cb_srv_keys(cb_ctx *c, const char *const *names, const int32_t *ports, const char *const *addresses,
+    size_t n, char *keys_out) {
+	DevGuard dev_guard_(c);
+	if (!c || (n && (!names || !ports || !addresses || !keys_out)))
+		return c ? fail(c, CB_EINVAL, "names, ports, addresses and keys_out are required") : CB_EINVAL;
+	if (n == 0)
+		return CB_OK;
+	if (n > (1u << 24))
+		return fail(c, CB_EINVAL, "too many backends");
+	// the hashed bytes: name || "||" || String(port) || "||" || normalised address (lib/resolver.js:1157-1171)
+	std::string blob;
+	std::vector<unsigned int> offs(n + 1);
+	for (size_t k = 0; k < n; k++) {
+		offs[k] = (unsigned int)blob.size();
+		if (!names[k] || !addresses[k])
+			return fail(c, CB_EINVAL, "backend %zu: name and address are required", k);
+		std::string norm;
+		if (!normalise_address(addresses[k], &norm))
+			return fail(c, CB_EINVAL, "backend %zu: '%s' is not an IP address", k, addresses[k]); // ipaddr.parse throws
+		blob += names[k];
+		blob += "||";
+		blob += std::to_string(ports[k]);
+		blob += "||";
+		blob += norm;
+	}
+	offs[n] = (unsigned int)blob.size();
+	unsigned char *d_blob = nullptr;
+	unsigned int *d_offs = nullptr;
+	char *d_keys = nullptr;
+	CU(c, cudaMalloc((void **)&d_blob, blob.size() + 16));
+	CU(c, cudaMalloc((void **)&d_offs, (n + 1) * sizeof(unsigned int)));
+	CU(c, cudaMalloc((void **)&d_keys, n * SRVKEY_LEN));
+	cudaStream_t s = c->stream;
+	CU(c, cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+	CU(c, cudaMemcpyAsync(d_offs, offs.data(), (n + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+	srv_key_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_blob, d_offs, (int)n, d_keys);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(keys_out, d_keys, n * SRVKEY_LEN, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaStreamSynchronize(s));
+	cudaFree(d_blob);
+	cudaFree(d_offs);
+	cudaFree(d_keys);
+	return CB_OK;
+}
+
+extern "C" int cb_resolver_process(cb_ctx *c, const char *keys, size_t n, int32_t *removed_ids, char *removed_keys,
+    int32_t *n_removed, int32_t *added_ids, int32_t *added_rows, int32_t *n_added, int32_t *empty_set) {
+	DevGuard dev_guard_(c);
+	if (!c || (n && !keys) || !n_removed || !n_added)
+		return c ? fail(c, CB_EINVAL, "keys, n_removed and n_added are required") : CB_EINVAL;
+	*n_removed = 0;
+	*n_added = 0;
+	if (empty_set)
+		*empty_set = 0;
+	// newBackends: the keys in first-appearance order (a later duplicate overwrites the value, not the position)
+	std::vector<std::string> nk;
+	std::vector<int32_t> nrow;
+	std::unordered_map<std::string, int32_t> seen;
+	for (size_t k = 0; k < n; k++) {
+		std::string key(keys + k * SRVKEY_LEN, SRVKEY_LEN);
+		auto it = seen.find(key);
+		if (it == seen.end()) {
+			seen.emplace(key, (int32_t)nk.size());
+			nk.push_back(key);
+			nrow.push_back((int32_t)k);
+		} else {
+			nrow[it->second] = (int32_t)k; // the later record wins, lib/resolver.js:1043
+		}
+	}
+	if (nk.empty()) { // 'empty-set': report it and change nothing, lib/resolver.js:1052-1061
+		if (empty_set)
+			*empty_set = 1;
+		return CB_OK;
+	}
+	int32_t nr = 0, na = 0;
+	for (const std::string &k : c->r_keys) { // removed: old key order, :1063-1066
+		if (seen.find(k) == seen.end()) {
+			if (removed_ids)
+				removed_ids[nr] = c->r_ids[k];
+			if (removed_keys)
+				memcpy(removed_keys + (size_t)nr * SRVKEY_LEN, k.data(), SRVKEY_LEN);
+			nr++;
+		}
+	}
+	std::unordered_map<std::string, int32_t> ids;
+	for (size_t j = 0; j < nk.size(); j++) { // added: new key order, :1067-1070
+		auto it = c->r_ids.find(nk[j]);
+		if (it == c->r_ids.end()) {
+			const int32_t id = c->r_next_id++;
+			ids.emplace(nk[j], id);
+			if (added_ids)
+				added_ids[na] = id;
+			if (added_rows)
+				added_rows[na] = nrow[j];
+			na++;
+		} else {
+			ids.emplace(nk[j], it->second);
+		}
+	}
+	c->r_keys.swap(nk); // this.r_backends = newBackends, :1072
+	c->r_ids.swap(ids);
+	*n_removed = nr;
+	*n_added = na;
 	return CB_OK;
 }
 
@@ -1550,6 +1943,7 @@ static int queue_check(cb_ctx *c) {
 }
 
 extern "C" int cb_queue_create(cb_ctx *c, size_t capacity, size_t result_capacity, uint64_t idle_slots) {
+	DevGuard dev_guard_(c);
 	if (!c || capacity == 0 || result_capacity == 0)
 		return c ? fail(c, CB_EINVAL, "queue and result capacities must be positive") : CB_EINVAL;
 	int rc = drain(c);
@@ -1597,6 +1991,7 @@ static int queue_stage(cb_ctx *c, const int64_t *host, size_t n) {
 }
 
 extern "C" int cb_queue_push(cb_ctx *c, const int64_t *start_ns, size_t n, int64_t *first_ticket, double *timeouts_ms) {
+	DevGuard dev_guard_(c);
 	if (!c || (n && !start_ns))
 		return c ? fail(c, CB_EINVAL, "start_ns must not be NULL") : CB_EINVAL;
 	int rc = queue_ready(c);
@@ -1618,6 +2013,7 @@ extern "C" int cb_queue_push(cb_ctx *c, const int64_t *start_ns, size_t n, int64
 }
 
 extern "C" int cb_queue_cancel(cb_ctx *c, const int64_t *tickets, size_t n) {
+	DevGuard dev_guard_(c);
 	if (!c || (n && !tickets))
 		return c ? fail(c, CB_EINVAL, "tickets must not be NULL") : CB_EINVAL;
 	int rc = queue_ready(c);
@@ -1631,6 +2027,7 @@ extern "C" int cb_queue_cancel(cb_ctx *c, const int64_t *tickets, size_t n) {
 }
 
 extern "C" int cb_queue_expire(cb_ctx *c, int64_t now_ns) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	int rc = queue_ready(c);
@@ -1642,6 +2039,7 @@ extern "C" int cb_queue_expire(cb_ctx *c, int64_t now_ns) {
 }
 
 extern "C" int cb_queue_idle(cb_ctx *c, int64_t now_ns, uint64_t k_slots) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	int rc = queue_ready(c);
@@ -1652,7 +2050,27 @@ extern "C" int cb_queue_idle(cb_ctx *c, int64_t now_ns, uint64_t k_slots) {
 	return queue_check(c);
 }
 
+extern "C" int cb_queue_trim_idle(cb_ctx *c, uint64_t k, uint64_t *removed) {
+	DevGuard dev_guard_(c);
+	if (!c)
+		return CB_EINVAL;
+	int rc = queue_ready(c);
+	if (rc)
+		return rc;
+	// slots that went away with a topology change leave the idle queue (setUnwanted on idle slots,
+	// lib/pool.js:601-631); a bookkeeping word, no kernel
+	QueueDev h;
+	CU(c, cudaMemcpy(&h, c->d_q, sizeof(h), cudaMemcpyDeviceToHost));
+	const unsigned long long take = k < h.idle ? k : h.idle;
+	h.idle -= take;
+	CU(c, cudaMemcpy((char *)c->d_q + offsetof(QueueDev, idle), &h.idle, sizeof(h.idle), cudaMemcpyHostToDevice));
+	if (removed)
+		*removed = take;
+	return CB_OK;
+}
+
 extern "C" int cb_queue_results(cb_ctx *c, int64_t *triples, size_t cap_records, size_t *n_records) {
+	DevGuard dev_guard_(c);
 	if (!c || !n_records)
 		return CB_EINVAL;
 	int rc = queue_ready(c);
@@ -1674,6 +2092,7 @@ extern "C" int cb_queue_results(cb_ctx *c, int64_t *triples, size_t cap_records,
 }
 
 extern "C" int cb_queue_info_get(cb_ctx *c, cb_queue_info *out) {
+	DevGuard dev_guard_(c);
 	if (!c || !out)
 		return CB_EINVAL;
 	int rc = queue_ready(c);
@@ -1686,12 +2105,14 @@ extern "C" int cb_queue_info_get(cb_ctx *c, cb_queue_info *out) {
 
 // =========================================================================== measurement
 extern "C" int cb_profile_enable(cb_ctx *c, int on) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	int rc = drain(c); // batches in flight were enqueued under the other mode
 	if (rc)
 		return rc;
 	c->prof = on != 0;
+	c->prof_scan_only = on == 2;
 	for (int k = 0; k < CB_K_COUNT; k++) {
 		c->prof_ms[k] = 0;
 		c->prof_n[k] = 0;
@@ -1699,6 +2120,7 @@ extern "C" int cb_profile_enable(cb_ctx *c, int on) {
 	return CB_OK;
 }
 extern "C" int cb_profile_get(cb_ctx *c, double ms_out[CB_K_COUNT], uint64_t launches_out[CB_K_COUNT]) {
+	DevGuard dev_guard_(c);
 	if (!c)
 		return CB_EINVAL;
 	for (int k = 0; k < CB_K_COUNT; k++) {
@@ -1712,6 +2134,7 @@ extern "C" int cb_profile_get(cb_ctx *c, double ms_out[CB_K_COUNT], uint64_t lau
 extern "C" uint64_t cb_launch_count(const cb_ctx *c) { return c ? c->launches : 0; }
 
 extern "C" int cb_debug_lane_timestamps(cb_ctx *c, int lane, uint64_t out[16]) {
+	DevGuard dev_guard_(c);
 	if (!c || !out || lane < 0 || lane >= CB_LANES)
 		return CB_EINVAL;
 	int rc = drain(c);
@@ -1727,6 +2150,7 @@ extern "C" int cb_debug_lane_timestamps(cb_ctx *c, int lane, uint64_t out[16]) {
 }
 
 extern "C" int cb_debug_timestamps(cb_ctx *c, uint64_t out[16]) {
+	DevGuard dev_guard_(c);
 	if (!c || !out)
 		return CB_EINVAL;
 	int rc = drain(c);

@@ -1,48 +1,56 @@
 """ConnectionPool -- the claim()/release() surface of the reference's lib/pool.js for the
-claim-queue path, with the admission work done by the CUDA library.
+claim-queue path, with the pending-claim FIFO and the admission work resident on the GPU.
 
 What is mirrored (reference file:line):
   claim([options,] cb) -> handle{cancel()}          lib/pool.js:859-969
       options.timeout forbidden with targetClaimDelay   :874-878
       timeout = codel.getMaxIdle()                      :880
       idle-first fast path / enqueue on p_waiters       :929-966
+  claim handle hard timeout -> ClaimTimeoutError    lib/connection-fsm.js:626-642
+  handle.cancel(): waiting -> cancelled (stays in the FIFO, skipped at dequeue),
+                   claimed -> released                  lib/connection-fsm.js:580-587
   slot goes idle -> drain loop                      lib/pool.js:715-760
       shift, codel.overloaded(hdl.ch_started), skip non-waiting, timeout() or try()
       queue emptied with the slot still idle -> codel.empty(), slot onto p_idleq
   on_resolver_added / on_resolver_removed / reshuffle   lib/pool.js:285-313, 501-519
-  getStats() counters                               lib/pool.js:269-283, 834-857
+  getStats(): counters + the five fields of           lib/pool.js:269-283, 834-857
   handle states waiting/claimed/released/closed/cancelled/failed
                                                     lib/connection-fsm.js:489-808
 
+Every event is ONE device call: claim() is cb_queue_push (enqueue clock, getMaxIdle, idle-first
+fast path and the timers that came due, in one kernel), a slot turning idle is cb_queue_idle (the
+whole drain of lib/pool.js:733-757 for k slots in closed form: never per claim, never a trial
+batch), cancel() is cb_queue_cancel, the timer sweep cb_queue_expire.  The resolution records the
+device appends -- (ticket, code, slot) in the order the reference would resolve the handles -- are
+turned into the handles' callbacks here.  tests/test_gpu_pool_mirror.py replays the pinned event
+scripts of the reference's pool model through this class and compares records and counters exactly.
+
 What is NOT here (out of scope, stays in Node in a real deployment): sockets, the slot and
 socket FSMs, retry/backoff, the FIR low-pass filter and the churn limiter.  A "slot" here is
-an integer; its backend comes from the device-side slot table.
-
-The drain is batched: when k slots are idle at clock `now`, the waiters are examined in
-FIFO order exactly as k consecutive runs of the reference loop would (each run ends at its
-first admit).  That prefix is found with one trial device batch over the queue and committed
-with a second batch over the prefix, so CoDel's state only ever advances over claims that
-were really dequeued.
+an integer (admitted claim j of the pool's life takes slot j mod nslots); its
+backend comes from the device-side slot table.  A pool WITHOUT targetClaimDelay has no CoDel
+(lib/pool.js:195-200): nothing on its path is accelerated, and it runs as a plain host FIFO.
 """
 import time
 
 import numpy as np
 
-from . import _native as N
 from .context import Context
 from .errors import ClaimHandleMisusedError, ClaimTimeoutError, NoBackendsError, PoolStoppingError
-from .queue import Queue, snapshot
 from .utils import assertClaimDelay
+
+R_ADMIT, R_CODEL_DROP, R_SKIPPED, R_HARD_TIMEOUT = 0, 1, 2, 3  # codes of cb_queue_results
 
 
 class CueBallClaimHandle(object):
     """lib/connection-fsm.js:489-808 reduced to what the claim queue touches."""
 
-    def __init__(self, pool, callback, started_ns, claim_timeout_ms):
+    def __init__(self, pool, callback, started_ns, claim_timeout_ms, ticket):
         self.ch_pool = pool
         self.ch_callback = callback
         self.ch_started_ns = started_ns  # ch_started, :523
         self.ch_claimTimeout = claim_timeout_ms
+        self.ch_ticket = ticket
         self.ch_state = "waiting"
         self.ch_slot = None
         self.ch_backend = None
@@ -50,15 +58,17 @@ class CueBallClaimHandle(object):
     def isInState(self, s):
         return self.ch_state == s
 
-    def cancel(self):  # :580
+    def cancel(self):  # :580-587
         if self.ch_state == "waiting":
             self.ch_state = "cancelled"
+            self.ch_pool._cancelled(self)
+        elif self.ch_state == "claimed":
+            self.release()
 
-    def timeout(self):  # :589, :633-638
+    def timeout(self):  # :589, :633-638 (the counter is the device's: cb_queue_info.claim_timeout)
         if self.ch_state != "waiting":
             return
         self.ch_state = "failed"
-        self.ch_pool._incrCounter("claim-timeout")
         if self.ch_callback:
             self.ch_callback(ClaimTimeoutError(self.ch_pool), None, None)
 
@@ -90,33 +100,68 @@ class ConnectionPool(object):
         self._clock = options.get("clock") or time.monotonic_ns
         self._random = options.get("random") or np.random.random
         self._ctx = options.get("context") or Context(options.get("device", 0))
+        self._capacity = int(options.get("queueCapacity", 1 << 16))
+        # how many of the table's slots are connected and idle when the first claim arrives (the reference's
+        # connections come up over time; default: all of them)
+        self._initial_idle = options.get("initialIdleSlots")
         self.p_codel = None
         if options.get("targetClaimDelay") is not None:
             self._ctx.codel_init(options["targetClaimDelay"])  # lib/pool.js:197-200
             self.p_codel = self._ctx
-        self.p_waiters = Queue()
-        self.p_idleq = Queue()
         self.p_keys = []       # preference list as the caller's keys (device holds indices)
         self._key_ids = {}
+        self._id_to_key = {}
         self._next_id = 0
-        self.p_counters = {}
-        self._pending_idle = 0
         self._stopping = False
         self._slot_backend = np.zeros(0, np.int32)
-        self._id_to_key = {}
+        self._handles = {}     # ticket -> handle, until the device resolves it
+        self._claimed = 0      # slots held by claimed handles
+        self._queue_ready = False
+        self.records = []      # every (ticket, code, slot) the device produced, in order (observability/tests)
+        # the pool without CoDel: a plain host FIFO (nothing to accelerate)
+        self._host_waiters = []
+        self._host_idle = 0
+        self._host_counters = {}
+        self._host_cursor = 0
         self._ctx.backends_set(0, [], self.p_max)  # empty preference list, `maximum` slots wanted
 
-    # ------------------------------------------------------------ counters
-    def _incrCounter(self, c, n=1):  # lib/pool.js:269-275
-        self.p_counters[c] = self.p_counters.get(c, 0) + n
+    # ------------------------------------------------------------ device queue
+    def _ensure_queue(self, idle_slots):
+        if not self._queue_ready:
+            if self._initial_idle is not None:
+                idle_slots = self._initial_idle
+            self._ctx.queue_create(self._capacity, 4 * self._capacity, int(idle_slots))
+            self._queue_ready = True
 
-    def _hwmCounter(self, c, v):  # lib/pool.js:277-283
-        if self.p_counters.get(c, 0) < v:
-            self.p_counters[c] = v
+    def _dispatch(self):
+        """Turn the device's resolution records into handle transitions, in the device's order."""
+        for ticket, code, slot in self._ctx.queue_results().tolist():
+            self.records.append((ticket, code, slot))
+            h = self._handles.pop(ticket, None)
+            if h is None:
+                continue
+            if code == R_ADMIT:  # lib/pool.js:747 / :934-951
+                self._claimed += 1
+                h.try_(slot, int(self._slot_backend[slot]) if slot < len(self._slot_backend) else -1)
+            elif code in (R_CODEL_DROP, R_HARD_TIMEOUT):  # lib/pool.js:742-745 / connection-fsm.js:626-642
+                h.timeout()
+            # R_SKIPPED: the handle left 'waiting' before it was dequeued (lib/pool.js:738-740)
 
-    def getStats(self):  # lib/pool.js:834-857 (the fields that exist on this path)
-        return {"counters": dict(self.p_counters), "totalConnections": self.p_max,
-                "idleConnections": self.p_idleq.length, "waiterCount": self.p_waiters.length}
+    # ------------------------------------------------------------ counters / stats
+    def getStats(self):  # lib/pool.js:834-857: exactly these five keys
+        if self.p_codel is None:
+            return {"counters": dict(self._host_counters), "totalConnections": len(self._slot_backend),
+                    "idleConnections": self._host_idle, "pendingConnections": 0,
+                    "waiterCount": len(self._host_waiters)}
+        if not self._queue_ready:
+            return {"counters": {}, "totalConnections": len(self._slot_backend),
+                    "idleConnections": len(self._slot_backend), "pendingConnections": 0, "waiterCount": 0}
+        info = self._ctx.queue_info()
+        # a counter exists once it has been bumped (lib/pool.js:269-283)
+        counters = {k: v for k, v in info.counters().items() if v}
+        return {"counters": counters, "totalConnections": len(self._slot_backend),
+                "idleConnections": int(info.idle), "pendingConnections": 0,
+                "waiterCount": int(info.tail - info.head)}
 
     # ------------------------------------------------------------ resolver
     def on_resolver_added(self, k, backend=None):  # lib/pool.js:285-291
@@ -157,106 +202,139 @@ class ConnectionPool(object):
     def _refresh_slots(self):
         keys, slots = self._ctx.backends_get()
         assert [self._id_to_key[int(i)] for i in keys] == self.p_keys, "preference list diverged"
-        old = self._slot_backend
+        old_n = len(self._slot_backend)
         self._slot_backend = slots
-        # (re)build the idle queue for slots that are not claimed: a topology change in the
-        # reference closes/opens sockets; in this model every slot of the new table starts idle
-        if len(old) != len(slots):
-            self.p_idleq = Queue()
-            for s in range(len(slots)):
-                self.p_idleq.push(s)
+        new_n = len(slots)
+        if new_n == old_n:
+            return
+        # A topology change in the reference opens / closes sockets; in this model the slots of the
+        # new table that no claimed handle holds are idle.  New slots turn idle as an event (they
+        # drain waiters, lib/pool.js:715); slots that went away leave the idle queue.
+        if self.p_codel is None:
+            self._host_idle = max(0, new_n - self._claimed)
+            self._host_drain(self._clock())
+            return
+        if not self._queue_ready:
+            return  # created with the table's size at the first claim / idle event
+        idle_now = int(self._ctx.queue_info().idle)
+        want_idle = max(0, new_n - self._claimed)
+        if want_idle > idle_now:
+            self._ctx.queue_idle(self._clock(), want_idle - idle_now)
+            self._dispatch()
+        elif want_idle < idle_now:
+            self._ctx.queue_trim_idle(idle_now - want_idle)
 
     # --------------------------------------------------------------- claim
     def claim(self, options=None, cb=None):  # lib/pool.js:859-969
         if callable(options) and cb is None:
             cb, options = options, {}
         options = options or {}
-        if self.p_codel is not None:
-            if isinstance(options.get("timeout"), (int, float)):
-                raise Exception("options.timeout not allowed when targetDelay has been set")  # :875-878
-            timeout = self._ctx.max_idle(self._clock())  # :880
-        elif isinstance(options.get("timeout"), (int, float)):
-            timeout = options["timeout"]
-        else:
-            timeout = float("inf")
-        self._incrCounter("claim")  # :887
-        if self._stopping:
+        if self.p_codel is not None and isinstance(options.get("timeout"), (int, float)):
+            raise Exception("options.timeout not allowed when targetDelay has been set")  # :875-878
+        if self._stopping:  # :889-899
             if cb:
                 cb(PoolStoppingError(), None, None)
             return {"cancel": lambda: None}
-        handle = CueBallClaimHandle(self, cb, self._clock(), timeout)
-        # tryNext, :929-966
-        while self.p_idleq.length > 0:
-            slot = self.p_idleq.shift()
-            handle.try_(slot, int(self._slot_backend[slot]))
+        now = self._clock()
+        if self.p_codel is None:
+            return self._host_claim(options, cb, now)
+        if options.get("errorOnEmpty") and len(self.p_keys) < 1:  # :953-957
+            handle = CueBallClaimHandle(self, cb, now, float("inf"), -1)
+            handle.ch_state = "failed"
+            if cb:
+                cb(NoBackendsError(), None, None)
+            return handle
+        self._ensure_queue(len(self._slot_backend))
+        # one kernel: timers that came due, getMaxIdle (:880), idle slot first (:934-951), else enqueue (:960-965)
+        ticket, tmo = self._ctx.queue_push([now], want_timeouts=True)
+        handle = CueBallClaimHandle(self, cb, now, float(tmo[0]), ticket)
+        self._handles[ticket] = handle
+        self._dispatch()
+        return handle
+
+    def stop(self):
+        self._stopping = True
+
+    # ---------------------------------------------------------- events
+    def _cancelled(self, handle):
+        if self.p_codel is None:
+            return  # stays in the host FIFO, skipped at dequeue
+        self._ctx.queue_cancel([handle.ch_ticket])
+        self._handles.pop(handle.ch_ticket, None)
+
+    def _slot_released(self, slot):
+        """A slot FSM returned to 'idle' (lib/connection-fsm.js:1141-1147 -> pool.js:715)."""
+        self._claimed -= 1
+        self.slots_idle(1)
+
+    def slots_idle(self, k, now_ns=None):
+        """k slots turned idle at one clock value: the handler of lib/pool.js:715-760 once per slot."""
+        k = int(k)
+        if k <= 0:
+            return
+        now = self._clock() if now_ns is None else now_ns
+        if self.p_codel is None:
+            self._host_idle += k
+            self._host_drain(now)
+            return
+        self._ensure_queue(len(self._slot_backend))
+        self._ctx.queue_idle(now, k)
+        self._dispatch()
+
+    def expire(self, now_ns=None):
+        """Fire the claim timers that have come due (each handle's S.timeout(claimTimeout),
+        lib/connection-fsm.js:626-642).  claim() and slots_idle() do this first anyway; a host with
+        long checkouts calls it from its own timer."""
+        now = self._clock() if now_ns is None else now_ns
+        if self.p_codel is None:
+            self._host_expire(now)
+            return
+        if self._queue_ready:
+            self._ctx.queue_expire(now)
+            self._dispatch()
+
+    # ---------------------------------------------------------- the pool without CoDel (host only)
+    def _hc(self, c, n=1):
+        self._host_counters[c] = self._host_counters.get(c, 0) + n
+
+    def _host_claim(self, options, cb, now):
+        timeout = options["timeout"] if isinstance(options.get("timeout"), (int, float)) else float("inf")
+        self._hc("claim")
+        self._host_expire(now)
+        handle = CueBallClaimHandle(self, cb, now, timeout, -1)
+        if self._host_idle > 0:
+            self._host_idle -= 1
+            self._host_admit(handle)
             return handle
         if options.get("errorOnEmpty") and len(self.p_keys) < 1:
             handle.ch_state = "failed"
             if cb:
                 cb(NoBackendsError(), None, None)
             return handle
-        self.p_waiters.push(handle)
-        self._hwmCounter("max-claim-queue", self.p_waiters.length)
-        self._incrCounter("queued-claim")
+        self._host_waiters.append(handle)
+        if self._host_counters.get("max-claim-queue", 0) < len(self._host_waiters):
+            self._host_counters["max-claim-queue"] = len(self._host_waiters)
+        self._hc("queued-claim")
         return handle
 
-    def stop(self):
-        self._stopping = True
+    def _host_admit(self, handle):
+        n = len(self._slot_backend)
+        slot = self._host_cursor % n if n else -1
+        self._host_cursor += 1
+        self._claimed += 1
+        handle.try_(slot, int(self._slot_backend[slot]) if n else -1)
 
-    # ---------------------------------------------------------- drain loop
-    def _slot_released(self, slot):
-        """A slot FSM returned to 'idle' (lib/connection-fsm.js:1141-1147 -> pool.js:715)."""
-        self._drain([slot], self._clock())
-
-    def slots_idle(self, slots, now_ns=None):
-        """Several slots turned idle at (about) the same clock value."""
-        self._drain(list(slots), self._clock() if now_ns is None else now_ns)
-
-    def _drain(self, slots, now_ns):
-        k = len(slots)
-        if k == 0:
-            return
-        handles = self.p_waiters.take_all()
-        n = len(handles)
-        if n == 0:  # lib/pool.js:751-757
-            if self.p_codel is not None:
-                self._ctx.codel_empty(now_ns)
-            for s in slots:
-                self.p_idleq.push(s)
-            return
-        start, flags = snapshot(handles)
-        now = np.full(n, now_ns, dtype=np.int64)
-        if self.p_codel is not None:
-            saved = self._ctx.get_state().as_dict()
-            dec, _, _, _ = self._ctx.admit_batch(start, now, flags, want_slot=False)
-            adm = np.flatnonzero(dec == N.ADMIT)
-            if adm.size >= k:
-                L = int(adm[k - 1]) + 1
-            else:
-                L = n
-            if L < n:  # commit only the prefix that k runs of the loop would have dequeued
-                saved["count"] = int(saved["count"])
-                self._ctx.set_state(saved)
-                dec, _, _, _ = self._ctx.admit_batch(start[:L], now[:L], flags[:L], want_slot=False)
-        else:
-            dec = np.where(flags & 1, N.ADMIT, N.SKIPPED).astype(np.uint8)
-            adm = np.flatnonzero(dec == N.ADMIT)
-            L = int(adm[k - 1]) + 1 if adm.size >= k else n
-            dec = dec[:L]
-        free = list(slots)
-        for i in range(L):
-            h = handles[i]
-            if dec[i] == N.SKIPPED:
-                continue
-            if dec[i] == N.DROP:
+    def _host_expire(self, now):
+        for h in self._host_waiters:
+            if h.ch_state == "waiting" and now >= h.ch_started_ns + h.ch_claimTimeout * 1e6:
+                self._hc("claim-timeout")
                 h.timeout()
+
+    def _host_drain(self, now):
+        self._host_expire(now)
+        while self._host_idle > 0 and self._host_waiters:
+            h = self._host_waiters.pop(0)
+            if h.ch_state != "waiting":
                 continue
-            s = free.pop(0)
-            h.try_(s, int(self._slot_backend[s]) if s < len(self._slot_backend) else -1)
-        for h in handles[L:]:  # untouched tail goes back in FIFO order
-            self.p_waiters.push(h)
-        if free:  # queue drained with slots still idle: lib/pool.js:751-757
-            if self.p_codel is not None:
-                self._ctx.codel_empty(now_ns)
-            for s in free:
-                self.p_idleq.push(s)
+            self._host_idle -= 1
+            self._host_admit(h)

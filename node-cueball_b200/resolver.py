@@ -1,7 +1,8 @@
 """Resolver side of the path: backend identity and the 'added'/'removed'
-event stream that feeds ConnectionPool.on_resolver_added/removed.  Host logic only (there is nothing
-here for a GPU to do: a few thousand short strings per topology change); names and behaviour follow
-the reference:
+event stream that feeds ConnectionPool.on_resolver_added/removed; names and behaviour follow the
+reference.  The functions below are the host mirror; the same two steps sit behind the C ABI for a native
+host (cb_srv_keys: SHA-1 of a whole result set on the device; cb_resolver_process: the diff) and are
+reached from here through DeviceResolverState:
 
     srvKey(srv)                    lib/resolver.js:1157-1171  sha1(name || port || normalised address), base64
     StaticIpResolver               lib/resolver.js:1387-1456  fixed backend list; emission order = list order
@@ -135,3 +136,30 @@ def process_backends(old_backends, srvs):
     removed = [k for k in old_backends if k not in new_backends]
     added = [k for k in new_backends if k not in old_backends]
     return new_backends, removed, added
+
+
+class DeviceResolverState(object):
+    """state_process through the C ABI: the srvKeys of a result set are computed on the device
+    (cb_srv_keys) and diffed against the context's backend map (cb_resolver_process); the events go to a
+    ConnectionPool mirror in the reference's order (every 'removed', then every 'added')."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+
+    def process(self, srvs):
+        """`srvs` as for process_backends.  Returns (removed_keys, added [(key, backend)], empty_set)."""
+        rows = []
+        for srv in srvs:
+            for addr in list(srv.get("addresses_v6") or []) + list(srv.get("addresses_v4") or []):
+                rows.append({"name": srv["name"], "port": srv["port"], "address": addr})
+        keys = self._ctx.srv_keys(rows)
+        removed, added, empty = self._ctx.resolver_process(keys)
+        return [k for k, _ in removed], [(k, rows[row]) for k, _, row in added], empty
+
+    def feed(self, pool, srvs):
+        removed, added, empty = self.process(srvs)
+        for k in removed:
+            pool.on_resolver_removed(k)
+        for k, be in added:
+            pool.on_resolver_added(k, be)
+        return removed, [k for k, _ in added], empty

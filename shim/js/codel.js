@@ -18,12 +18,22 @@ function ControlledDelay(targetClaimDelay, ctx) {
 	this.cd_targdelay = targetClaimDelay;
 }
 /*
- * `start` is hdl.ch_started.  The reference stamps it with utils.currentMillis() (double
- * ms); with this shim the handle keeps the BigInt nanoseconds (ch_started_ns) and the
- * device does the ms conversion exactly as lib/utils.js:198-204.
+ * `start` is hdl.ch_started.  The reference stamps it with utils.currentMillis() (a Number, double
+ * milliseconds, lib/connection-fsm.js:523): that call shape works unchanged -- the clock is then read
+ * the same way (lib/utils.js:198-204) and the comparison runs on the doubles, as in lib/codel.js:56-86.
+ * A host that keeps BigInt nanoseconds on the handle (ch_started_ns) passes those instead and the
+ * device does the ms conversion itself.  Anything else throws, like mod_assert.number(start).
  */
-ControlledDelay.prototype.overloaded = function (start_ns) {
-	return (native.overloaded(this.cd_ctx, start_ns, hrns()));
+function currentMillis() {	/* lib/utils.js:198-204 */
+	var t = process.hrtime();
+	return (t[0] * 1000 + t[1] / 1000000);
+}
+ControlledDelay.prototype.overloaded = function (start) {
+	if (typeof (start) === 'bigint')
+		return (native.overloaded(this.cd_ctx, start, hrns()));
+	if (typeof (start) !== 'number')
+		throw (new TypeError('start (number) is required'));
+	return (native.overloadedMs(this.cd_ctx, start, currentMillis()));
 };
 ControlledDelay.prototype.empty = function () { native.empty(this.cd_ctx, hrns()); };
 ControlledDelay.prototype.getMaxIdle = function () {

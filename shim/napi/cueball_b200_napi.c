@@ -12,6 +12,8 @@
  *   create(device) -> ctx (external)                      destroy(ctx)
  *   codelInit(ctx, targetMs)                              new ControlledDelay(), lib/codel.js:24
  *   overloaded(ctx, startNs: BigInt, nowNs: BigInt) -> bool   lib/codel.js:56
+ *   overloadedMs(ctx, startMs: Number, nowMs: Number) -> bool  the same on the reference's own double-ms clock
+ *                                                          (hdl.ch_started as lib/connection-fsm.js:523 stamps it)
  *   empty(ctx, nowNs)                                     lib/codel.js:91
  *   getMaxIdle(ctx, nowNs) -> ms                          lib/codel.js:109
  *   admitBatch(ctx, start: BigInt64Array, now: BigInt64Array, flags: Uint8Array|null,
@@ -23,7 +25,9 @@
  *              -> {want: Int32Array, add: Int32Array, rmKey: Int32Array, rmOrd: Int32Array}
  *                                                          lib/utils.js:239-393
  * Errors: CB_EINVAL -> throws (the reference throws AssertionError for programmer errors);
- * everything else -> throws Error(cb_last_error()).
+ * everything else -> throws Error(cb_last_error()).  Arguments are validated before the C ABI sees them:
+ * a clock must be a BigInt that fits int64 (a Number is NOT silently read as 0), typed arrays must have the
+ * element type named above and at least as many elements as the batch.
  */
 #include <node_api.h>
 #include <stdint.h>
@@ -39,14 +43,21 @@
 		}                                                             \
 	} while (0)
 
+/* NULL (with a TypeError pending) unless `v` is a context made by create(): callers return at once */
 static cb_ctx *
 get_ctx(napi_env env, napi_value v)
 {
 	void *p = NULL;
-	if (napi_get_value_external(env, v, &p) != napi_ok || p == NULL)
+	if (napi_get_value_external(env, v, &p) != napi_ok || p == NULL) {
 		napi_throw_type_error(env, NULL, "ctx expected");
+		return NULL;
+	}
 	return (cb_ctx *)p;
 }
+#define GET_CTX(ctx, env, v)                   \
+	cb_ctx *ctx = get_ctx((env), (v));         \
+	if (ctx == NULL)                           \
+		return NULL
 
 static napi_value
 throw_cb(napi_env env, cb_ctx *ctx, int rc)
@@ -82,27 +93,54 @@ CodelInit(napi_env env, napi_callback_info info)
 {
 	size_t argc = 2; napi_value argv[2]; double target;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
+	GET_CTX(ctx, env, argv[0]);
 	NAPI_CALL(env, napi_get_value_double(env, argv[1], &target));
 	int rc = cb_codel_init(ctx, target);
 	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
 }
 
-static int64_t
-big(napi_env env, napi_value v)
+/* a clock in nanoseconds: a BigInt that fits int64; anything else throws (false is returned) */
+static bool
+big(napi_env env, napi_value v, int64_t *out)
 {
-	int64_t x = 0; bool lossless = false;
-	napi_get_value_bigint_int64(env, v, &x, &lossless);
-	return x;
+	bool lossless = false;
+	*out = 0;
+	if (napi_get_value_bigint_int64(env, v, out, &lossless) != napi_ok || !lossless) {
+		napi_throw_type_error(env, NULL, "clock must be a BigInt of nanoseconds that fits int64 "
+		    "(use overloadedMs for the reference's double milliseconds)");
+		return false;
+	}
+	return true;
 }
 
 static napi_value
 Overloaded(napi_env env, napi_callback_info info)
 {
-	size_t argc = 3; napi_value argv[3], out; int drop = 0;
+	size_t argc = 3; napi_value argv[3], out; int drop = 0; int64_t st, nw;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	int rc = cb_codel_overloaded(ctx, big(env, argv[1]), big(env, argv[2]), &drop);
+	GET_CTX(ctx, env, argv[0]);
+	if (!big(env, argv[1], &st) || !big(env, argv[2], &nw)) return NULL;
+	int rc = cb_codel_overloaded(ctx, st, nw, &drop);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_get_boolean(env, drop != 0, &out));
+	return out;
+}
+
+/* the reference's own call shape: hdl.ch_started and the clock as double milliseconds (lib/codel.js:56-58) */
+static napi_value
+OverloadedMs(napi_env env, napi_callback_info info)
+{
+	size_t argc = 3; napi_value argv[3], out; int drop = 0; double st, nw; napi_valuetype t1, t2;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	GET_CTX(ctx, env, argv[0]);
+	if (napi_typeof(env, argv[1], &t1) != napi_ok || napi_typeof(env, argv[2], &t2) != napi_ok ||
+	    t1 != napi_number || t2 != napi_number) {
+		napi_throw_type_error(env, "AssertionError", "start (number) is required");	/* mod_assert.number, lib/codel.js:57 */
+		return NULL;
+	}
+	NAPI_CALL(env, napi_get_value_double(env, argv[1], &st));
+	NAPI_CALL(env, napi_get_value_double(env, argv[2], &nw));
+	int rc = cb_codel_overloaded_ms(ctx, st, nw, &drop);
 	if (rc != CB_OK) return throw_cb(env, ctx, rc);
 	NAPI_CALL(env, napi_get_boolean(env, drop != 0, &out));
 	return out;
@@ -111,45 +149,78 @@ Overloaded(napi_env env, napi_callback_info info)
 static napi_value
 Empty(napi_env env, napi_callback_info info)
 {
-	size_t argc = 2; napi_value argv[2];
+	size_t argc = 2; napi_value argv[2]; int64_t nw;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	int rc = cb_codel_empty(ctx, big(env, argv[1]));
+	GET_CTX(ctx, env, argv[0]);
+	if (!big(env, argv[1], &nw)) return NULL;
+	int rc = cb_codel_empty(ctx, nw);
 	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
 }
 
 static napi_value
 GetMaxIdle(napi_env env, napi_callback_info info)
 {
-	size_t argc = 2; napi_value argv[2], out; double ms = 0;
+	size_t argc = 2; napi_value argv[2], out; double ms = 0; int64_t nw;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	int rc = cb_codel_max_idle(ctx, big(env, argv[1]), &ms);
+	GET_CTX(ctx, env, argv[0]);
+	if (!big(env, argv[1], &nw)) return NULL;
+	int rc = cb_codel_max_idle(ctx, nw, &ms);
 	if (rc != CB_OK) return throw_cb(env, ctx, rc);
 	NAPI_CALL(env, napi_create_double(env, ms, &out));
 	return out;
 }
 
+/*
+ * A typed array argument of element type `want` with at least `need` elements.  *ok = false (with a
+ * TypeError pending) when it is something else or too short; null / undefined is allowed only when
+ * `optional` and yields NULL with *ok = true.
+ */
 static void *
-typed(napi_env env, napi_value v, size_t *len)
+typed(napi_env env, napi_value v, napi_typedarray_type want, size_t need, bool optional, const char *what,
+    size_t *len, bool *ok)
 {
-	napi_valuetype t; void *data = NULL; napi_typedarray_type tt; napi_value ab; size_t off;
-	if (napi_typeof(env, v, &t) != napi_ok || t == napi_null || t == napi_undefined) return NULL;
-	if (napi_get_typedarray_info(env, v, &tt, len, &data, &ab, &off) != napi_ok) return NULL;
+	napi_valuetype t; void *data = NULL; napi_typedarray_type tt; napi_value ab; size_t off, n = 0;
+	*ok = false;
+	if (len) *len = 0;
+	if (napi_typeof(env, v, &t) != napi_ok) {
+		napi_throw_type_error(env, NULL, what);
+		return NULL;
+	}
+	if (t == napi_null || t == napi_undefined) {
+		if (optional) *ok = true;
+		else napi_throw_type_error(env, NULL, what);
+		return NULL;
+	}
+	if (napi_get_typedarray_info(env, v, &tt, &n, &data, &ab, &off) != napi_ok || tt != want || n < need) {
+		napi_throw_type_error(env, NULL, what);
+		return NULL;
+	}
+	if (len) *len = n;
+	*ok = true;
 	return data;
 }
 
 static napi_value
 AdmitBatch(napi_env env, napi_callback_info info)
 {
-	size_t argc = 6, n = 0, m = 0; napi_value argv[6], out, v;
+	size_t argc = 6, n = 0; napi_value argv[6], out, v; bool ok;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	const int64_t *start = typed(env, argv[1], &n);
-	const int64_t *now = typed(env, argv[2], &m);
-	const uint8_t *flags = typed(env, argv[3], &m);
-	uint8_t *decision = typed(env, argv[4], &m);
-	int32_t *slot = typed(env, argv[5], &m);
+	if (argc < 6) {
+		napi_throw_type_error(env, NULL, "admitBatch(ctx, start, now, flags, decision, slot)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	/* the batch is as long as `start`; every other array must hold at least that many elements */
+	const int64_t *start = typed(env, argv[1], napi_bigint64_array, 0, false, "start: BigInt64Array expected", &n, &ok);
+	if (!ok) return NULL;
+	const int64_t *now = typed(env, argv[2], napi_bigint64_array, n, false, "now: BigInt64Array of start's length expected", NULL, &ok);
+	if (!ok) return NULL;
+	const uint8_t *flags = typed(env, argv[3], napi_uint8_array, n, true, "flags: Uint8Array of start's length (or null) expected", NULL, &ok);
+	if (!ok) return NULL;
+	uint8_t *decision = typed(env, argv[4], napi_uint8_array, n, false, "decision: Uint8Array of start's length expected", NULL, &ok);
+	if (!ok) return NULL;
+	int32_t *slot = typed(env, argv[5], napi_int32_array, n, true, "slot: Int32Array of start's length (or null) expected", NULL, &ok);
+	if (!ok) return NULL;
 	cb_batch_stats st;
 	int rc = cb_admit_batch(ctx, start, now, flags, n, decision, slot, NULL, &st);
 	if (rc != CB_OK) return throw_cb(env, ctx, rc);
@@ -165,8 +236,9 @@ BackendAdded(napi_env env, napi_callback_info info)
 {
 	size_t argc = 3; napi_value argv[3]; int32_t key; double u;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	napi_get_value_int32(env, argv[1], &key); napi_get_value_double(env, argv[2], &u);
+	GET_CTX(ctx, env, argv[0]);
+	NAPI_CALL(env, napi_get_value_int32(env, argv[1], &key));
+	NAPI_CALL(env, napi_get_value_double(env, argv[2], &u));
 	int rc = cb_backend_added(ctx, key, NULL, u);
 	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
 }
@@ -176,8 +248,8 @@ BackendRemoved(napi_env env, napi_callback_info info)
 {
 	size_t argc = 2; napi_value argv[2]; int32_t key;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	napi_get_value_int32(env, argv[1], &key);
+	GET_CTX(ctx, env, argv[0]);
+	NAPI_CALL(env, napi_get_value_int32(env, argv[1], &key));
 	int rc = cb_backend_removed(ctx, key);
 	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
 }
@@ -187,8 +259,8 @@ Reshuffle(napi_env env, napi_callback_info info)
 {
 	size_t argc = 2; napi_value argv[2]; double u;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	napi_get_value_double(env, argv[1], &u);
+	GET_CTX(ctx, env, argv[0]);
+	NAPI_CALL(env, napi_get_value_double(env, argv[1], &u));
 	int rc = cb_reshuffle(ctx, u);
 	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
 }
@@ -206,14 +278,28 @@ i32array(napi_env env, const int32_t *src, size_t n)
 static napi_value
 PlanRebalance(napi_env env, napi_callback_info info)
 {
-	size_t argc = 6, B = 0, m = 0; napi_value argv[6], out; int32_t target, max; bool single = false;
+	size_t argc = 6, B = 0; napi_value argv[6], out; int32_t target, max; bool single = false, ok;
 	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-	cb_ctx *ctx = get_ctx(env, argv[0]);
-	const int32_t *have = typed(env, argv[1], &B);
-	const uint8_t *dead = typed(env, argv[2], &m);
-	napi_get_value_int32(env, argv[3], &target); napi_get_value_int32(env, argv[4], &max);
+	if (argc < 5) {
+		napi_throw_type_error(env, NULL, "planRebalance(ctx, have, dead, target, max[, singleton])");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	const int32_t *have = typed(env, argv[1], napi_int32_array, 0, false, "have: Int32Array expected", &B, &ok);
+	if (!ok) return NULL;
+	const uint8_t *dead = typed(env, argv[2], napi_uint8_array, B, false, "dead: Uint8Array of have's length expected", NULL, &ok);
+	if (!ok) return NULL;
+	NAPI_CALL(env, napi_get_value_int32(env, argv[3], &target));
+	NAPI_CALL(env, napi_get_value_int32(env, argv[4], &max));
 	if (argc > 5) napi_get_value_bool(env, argv[5], &single);
-	size_t tot = 0; for (size_t k = 0; k < B; k++) tot += (size_t)have[k];
+	size_t tot = 0;
+	for (size_t k = 0; k < B; k++) {
+		if (have[k] < 0) {
+			napi_throw_type_error(env, "AssertionError", "have[] must be >= 0");
+			return NULL;
+		}
+		tot += (size_t)have[k];
+	}
 	int32_t *want = calloc(B + 1, 4), *add = calloc((size_t)(max > 0 ? max : 0) + 1, 4);
 	int32_t *rk = calloc(tot + 1, 4), *ro = calloc(tot + 1, 4), na = 0, nr = 0;
 	int rc = cb_plan_rebalance(ctx, have, dead, (int32_t)B, target, max, single, want, add, &na, rk, ro, &nr);
@@ -235,6 +321,7 @@ Init(napi_env env, napi_value exports)
 		{ "create", NULL, Create, NULL, NULL, NULL, napi_default, NULL },
 		{ "codelInit", NULL, CodelInit, NULL, NULL, NULL, napi_default, NULL },
 		{ "overloaded", NULL, Overloaded, NULL, NULL, NULL, napi_default, NULL },
+		{ "overloadedMs", NULL, OverloadedMs, NULL, NULL, NULL, napi_default, NULL },
 		{ "empty", NULL, Empty, NULL, NULL, NULL, napi_default, NULL },
 		{ "getMaxIdle", NULL, GetMaxIdle, NULL, NULL, NULL, napi_default, NULL },
 		{ "admitBatch", NULL, AdmitBatch, NULL, NULL, NULL, napi_default, NULL },

@@ -182,7 +182,7 @@ inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) 
 
 /* dynamic shared memory: one buffer per (sequentially emulated) block */
 namespace emu {
-extern unsigned char dyn_smem[96 * 1024];
+extern unsigned char dyn_smem[232 * 1024];
 /* named barriers (bar.arrive / bar.sync id, nthreads): arrivals are counted, a sync also waits */
 void named_arrive(int id);
 void named_sync(int id);
@@ -200,9 +200,26 @@ inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return l
 inline void st_release_sys(unsigned long long *p, unsigned long long v) { st_release(p, v); }
 inline double ld_relaxed_f64(const double *p) { return *(const volatile double *)p; }
 inline unsigned long long ld_relaxed_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
-inline void bar_arrive(int id) { emu::named_arrive(id); }
-inline void bar_sync(int id) { emu::named_sync(id); }
-inline uint4 ld_stream_v4(const void *p) { return *reinterpret_cast<const uint4 *>(p); }
+/* mbarrier + TMA bulk copy (csrc/cb_scan.cuh): the barrier word holds the pending transaction bytes in its low half
+ * and the number of completed phases in its high half; a bulk copy is a memcpy that completes its bytes at once */
+inline void mbar_init(unsigned long long *mbar, unsigned int) { __atomic_store_n(mbar, 0ull, __ATOMIC_RELEASE); }
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(unsigned long long *mbar, unsigned int bytes) { __atomic_fetch_add(mbar, (unsigned long long)bytes, __ATOMIC_ACQ_REL); }
+inline void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *mbar, unsigned long long) {
+	std::memcpy(dst, src, bytes);
+	const unsigned long long left = __atomic_sub_fetch(mbar, (unsigned long long)bytes, __ATOMIC_ACQ_REL);
+	if ((left & 0xffffffffull) == 0)
+		__atomic_fetch_add(mbar, 1ull << 32, __ATOMIC_ACQ_REL); /* the phase completes */
+}
+inline unsigned long long l2_evict_first_policy() { return 0; }
+inline void mbar_wait(unsigned long long *mbar, unsigned int parity) { /* phase `parity` has completed */
+	int spins = 0;
+	while ((((__atomic_load_n(mbar, __ATOMIC_ACQUIRE) >> 32) & 1ull) == (unsigned long long)parity)) {
+		std::this_thread::yield();
+		if (++spins > 200000000)
+			emu::Barrier::report_stall("mbarrier");
+	}
+}
 inline void wait_table(unsigned long long *) {}
 inline void stage_table_async(unsigned char *dst, const void *src, unsigned int bytes, unsigned long long *) {
 	std::memcpy(dst, src, bytes);

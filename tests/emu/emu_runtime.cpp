@@ -42,7 +42,7 @@ void Barrier::report_stall(const char *what) {
 Barrier block_barrier;
 Barrier warp_barrier[64];
 unsigned long long warp_slot[64][32];
-unsigned char dyn_smem[96 * 1024];
+alignas(128) unsigned char dyn_smem[232 * 1024];
 unsigned int dbg_collectives[2048];
 int dbg_exited[2048];
 

@@ -16,6 +16,12 @@ using namespace cb;
 namespace {
 template <typename T> T *zalloc(size_t n) { return static_cast<T *>(std::calloc(n + 8, sizeof(T))); }
 
+/* the scan's persistent grid: a few CTAs, so that warps walk several tiles each (the library uses the SM count) */
+unsigned scan_grid(size_t tiles) {
+	const char *e = std::getenv("CB_EMU_SCAN_GRID");
+	const size_t g = e ? (size_t)std::atoi(e) : 3;
+	return (unsigned)(tiles < g ? tiles : g);
+}
 template <typename F> void run_grid(unsigned grid, int threads, F kernel_call) {
 	gridDim.x = grid;
 	for (unsigned b = 0; b < grid; b++) {
@@ -31,8 +37,6 @@ struct EmuPipe {
 	DevState g;
 	ChainMem chain;
 	unsigned long long seq;
-	int fchain;  /* use commit_fchain_kernel (the F-chain variant) */
-	int fused;   /* prepare + commit in one launch (resolve_fused_kernel) */
 	int fseed;   /* the state was set from the host since the last batch */
 	EmuPipe *next; /* ring: the context whose mailbox this one writes (null: no ring) */
 	int ring_n, ring_rank;
@@ -55,7 +59,7 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	                   *hj_lo = zalloc<unsigned long long>(cap + 1), *hj_b = zalloc<unsigned long long>(cap + 1),
 	                   *tile_now0 = zalloc<unsigned long long>(cap), *iv_lo = zalloc<unsigned long long>(evcap + 8),
 	                   *iv_hi = zalloc<unsigned long long>(evcap + 8), *iv_cum = zalloc<unsigned long long>(evcap + 8);
-	double *ev_now = zalloc<double>(evcap), *hj_F = zalloc<double>(cap + 1), *idx_ms = zalloc<double>(NIDX_MAX);
+	double *ev_now = zalloc<double>(evcap), *hj_F = zalloc<double>(cap + 1);
 	SumDesc *sdesc = zalloc<SumDesc>(cap);
 
 	ScanParams sp;
@@ -86,7 +90,6 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	rp.rec_code = rec_code;
 	rp.rec_cend = rec_cend;
 	rp.tile_now0 = tile_now0;
-	rp.idx_ms = idx_ms;
 	rp.link.err = &e->chain.err;
 	rp.link.wait_word = &e->chain.seq;
 	rp.link.timeout_ns = ~0ull;
@@ -123,8 +126,8 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	rp.backend = nullptr;
 	rp.slot_backend = nullptr;
 	rp.nslots = nslots;
-	rp.f_in = e->fchain ? e->chain.fs : nullptr;
-	rp.f_out = e->fchain ? (e->ring_n > 0 ? e->next->chain.fs : e->chain.fs) : nullptr;
+	rp.f_in = e->chain.fs;
+	rp.f_out = e->ring_n > 0 ? e->next->chain.fs : e->chain.fs;
 	rp.f_ring = e->ring_n > 0 ? (unsigned long long)e->ring_n : 1ull;
 
 	EmitParams ep;
@@ -149,7 +152,7 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	ep.ticket = ticket;
 	ep.vec_ok = (((uintptr_t)decision & 7) == 0) && (((uintptr_t)slot & 15) == 0);
 
-	if (e->fchain && e->fseed) {
+	if (e->fseed) {
 		if (e->ring_n == 0 || (e->ring_rank == 0 && e->seq == 0)) {
 			DevState *gp = &e->g;
 			FSlot *fs = e->chain.fs;
@@ -164,34 +167,12 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	if (flags) {
 		/* the flags variant of the emit kernel chains tile admit counts through a look-back; with ONE
 		 * persistent CTA walking the tiles in order every look-back finds its predecessors done */
-		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<NS, true>(sp); });
-		if (e->fused) {
-			if (e->fchain)
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, true, true>(rp); });
-			else
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, true, false>(rp); });
-		} else {
-			run_grid(1, RTPB, [&] { prepare_kernel<NS, true>(rp); });
-			if (e->fchain)
-				run_grid(1, CTPB, [&] { commit_fchain_kernel<NS, true>(rp); });
-			else
-				run_grid(1, CTPB, [&] { commit_kernel<NS, true>(rp); });
-		}
+		run_grid(scan_grid(tiles), SC_TPB, [&] { scan_kernel<NS, true>(sp); });
+		run_grid(1, RTPB, [&] { resolve_kernel<NS, true>(rp); });
 		run_grid(1, ETPB, [&] { emit_kernel<true>(ep); });
 	} else {
-		run_grid((unsigned)tiles, TPB, [&] { scan_kernel<NS, false>(sp); });
-		if (e->fused) {
-			if (e->fchain)
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, false, true>(rp); });
-			else
-				run_grid(1, RTPB, [&] { resolve_fused_kernel<NS, false, false>(rp); });
-		} else {
-			run_grid(1, RTPB, [&] { prepare_kernel<NS, false>(rp); });
-			if (e->fchain)
-				run_grid(1, CTPB, [&] { commit_fchain_kernel<NS, false>(rp); });
-			else
-				run_grid(1, CTPB, [&] { commit_kernel<NS, false>(rp); });
-		}
+		run_grid(scan_grid(tiles), SC_TPB, [&] { scan_kernel<NS, false>(sp); });
+		run_grid(1, RTPB, [&] { resolve_kernel<NS, false>(rp); });
 		const unsigned egrid = (unsigned)(etiles < 8 ? etiles : 8); /* persistent CTAs striding over the emit tiles */
 		run_grid(egrid, ETPB, [&] { emit_kernel<false>(ep); });
 	}
@@ -203,7 +184,7 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 		info[3] = ctl->drops;
 	}
 	void *fr[] = {ctl, ev_count, rec_fc, rec_cend, xcnt, hj_info, ticket, ev, evc, ev_q, ev_d, rec_code, xev, hj_lo, hj_b,
-	    tile_now0, iv_lo, iv_hi, iv_cum, ev_now, hj_F, idx_ms, sdesc};
+	    tile_now0, iv_lo, iv_hi, iv_cum, ev_now, hj_F, sdesc};
 	for (void *p : fr)
 		std::free(p);
 	return 0;
@@ -211,11 +192,9 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 
 
 extern "C" {
-EmuPipe *emu_pipe_create(double target, int mode) { /* mode: bit 0 F-chain, bit 1 fused resolve */
+EmuPipe *emu_pipe_create(double target, int) { /* (second argument: unused, kept for the callers' signature) */
 	EmuPipe *e = static_cast<EmuPipe *>(std::calloc(1, sizeof(EmuPipe)));
 	e->g.target = target;
-	e->fchain = mode & 1;
-	e->fused = (mode >> 1) & 1;
 	e->fseed = 1;
 	return e;
 }

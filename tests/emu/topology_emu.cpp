@@ -4,6 +4,8 @@
 #define CB_TOPO_TPB 64
 #include "../../node-cueball_b200/csrc/cb_topology.cuh"
 
+#include <vector>
+
 using namespace cb;
 
 namespace {
@@ -31,7 +33,9 @@ void emu_pref_reshuffle(int32_t *keys, const int *len, double u) {
 }
 void emu_plan_rebalance(const int32_t *have, const uint8_t *dead, int B, int target, int max, int singleton,
     int32_t *want, int32_t *add, int32_t *n_add, int32_t *rm_key, int32_t *rm_ord, int32_t *n_rm) {
-	one_cta(32, [&] { plan_rebalance_kernel(have, dead, B, target, max, singleton, want, add, n_add, rm_key, rm_ord, n_rm); });
+	std::vector<int32_t> scratch(2 * (size_t)(B + 1) + 2);
+	int32_t *scr = scratch.data();
+	one_cta(TOPO_TPB, [&] { plan_rebalance_kernel(have, dead, B, target, max, singleton, want, add, n_add, rm_key, rm_ord, n_rm, scr); });
 }
 void emu_slot_table(const int32_t *keys, const int32_t *add, const int32_t *n_add, int32_t *slot_backend, int cap,
     int *nslots_out) {

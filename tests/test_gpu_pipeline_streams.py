@@ -1,13 +1,8 @@
-"""GPU parity tests of the launch-path variants written after round 1's GPU budget ran out:
-  CB_FCHAIN=1  F-chain variant of the commit kernel (first_above_time handed from batch to batch ahead
-               of the rest of the ControlledDelay state; through the mailboxes in a ring)
-  CB_FUSED=1   prepare + commit in one launch (resolve_fused_kernel)
-  CB_GRAPH=1   the batch's kernels as one CUDA graph per lane, node parameters rewritten per batch
-The kernels pass the CPU emulation (tests/test_pipeline_kernels_emulated.py) but have NOT run on
-hardware yet, so these tests are skipped unless CB_TEST_UNVALIDATED=1; the default library path uses
-none of the three."""
-import os
-
+"""GPU parity tests of the batch pipeline under streams of small batches: the resolve kernel's F
+hand-over (first_above_time handed from batch to batch ahead of the rest of the ControlledDelay
+state; through the mailboxes in a ring), every pipeline depth, host-side state changes between
+batches, and both launch modes (stream launches / one CUDA graph per lane whose node parameters are
+rewritten per batch).  First run on a B200 at the start of round 2 (profiles/r02_validate_pending.txt)."""
 import numpy as np
 import pytest
 
@@ -15,14 +10,11 @@ import util
 from cueball_b200 import tracegen
 from oracle import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CB_TEST_UNVALIDATED") != "1",
-                                 reason="launch-path variants not yet validated on hardware (set CB_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture()
-def cb(monkeypatch):
-    monkeypatch.setenv("CB_FCHAIN", "1")
+def cb():
     import cueball_b200
     return cueball_b200
 
@@ -119,12 +111,9 @@ def test_fchain_one_queue_over_a_ring_of_contexts(cb, R):
     assert st.cursor == ost.cursor and st.total_drops == ost.drops
 
 
-@pytest.mark.parametrize("fchain", ["0", "1"])
-def test_fused_resolve_kernel_streams_of_small_batches(monkeypatch, fchain):
-    """CB_FUSED=1: prepare and commit in one launch (3 launches per batch instead of 4)."""
+def test_three_launches_per_batch():
+    """scan, resolve (prepare + commit in one launch), emit: 3 launches per batch."""
     import torch
-    monkeypatch.setenv("CB_FUSED", "1")
-    monkeypatch.setenv("CB_FCHAIN", fchain)
     import cueball_b200 as cbm
     n, m, tgt, nslots = 1_500_000, 46_875, 5, 61
     start, now = tracegen.gen_trace(n, seed=377, de=1_000, unit=1 << 13)
@@ -152,14 +141,13 @@ def test_fused_resolve_kernel_streams_of_small_batches(monkeypatch, fchain):
         assert st.cursor == ost.cursor and st.total_drops == ost.drops
 
 
-@pytest.mark.parametrize("combo", ["", "fused", "fused+fchain"])
-def test_cuda_graph_launch_path(monkeypatch, combo):
-    """CB_GRAPH=1: a batch's kernels are one CUDA graph per lane and variant whose node parameters are
-    rewritten per batch (one launch call per batch); batches of different sizes, with and without flags."""
+@pytest.mark.parametrize("graph", ["0", "1"], ids=["streams", "graph"])
+def test_launch_modes(monkeypatch, graph):
+    """CB_GRAPH=1 forces the graph launch mode (a batch's kernels are one CUDA graph per lane and variant whose
+    node parameters are rewritten per batch: one launch call per batch), CB_GRAPH=0 plain stream launches; by
+    default the library picks by batch size.  Batches of different sizes, with and without flags."""
     import torch
-    monkeypatch.setenv("CB_GRAPH", "1")
-    monkeypatch.setenv("CB_FUSED", "1" if "fused" in combo else "0")
-    monkeypatch.setenv("CB_FCHAIN", "1" if "fchain" in combo else "0")
+    monkeypatch.setenv("CB_GRAPH", graph)
     import cueball_b200 as cbm
     n, tgt, nslots = 1_600_000, 5, 61
     start, now = tracegen.gen_trace(n, seed=477, de=1_000, unit=1 << 13)
@@ -185,3 +173,46 @@ def test_cuda_graph_launch_path(monkeypatch, combo):
         assert np.array_equal(dec.cpu().numpy(), od)
         assert np.array_equal(slot.cpu().numpy(), os_)
         assert st.cursor == ost.cursor and st.total_drops == ost.drops
+
+
+@pytest.mark.parametrize("R,steps", [(2, 5), (3, 80)])
+def test_global_counts_over_peer_boards(cb, R, steps):
+    """cb_peers_*: every batch's {drops, admits, n} is stored into every rank's board over peer memory and
+    summed there; the running totals equal the sum of the ranks' own totals (80 steps wrap the 64-slot boards,
+    so the flow-control words are exercised too).  Contexts of one process stand in for the ranks."""
+    import torch
+    tgt, nslots, m = 5, 61, 20_000
+    dev = torch.device("cuda:0")
+    ctxs, traces, outs = [], [], []
+    for r in range(R):
+        c = cb.Context(0)
+        c.codel_init(tgt)
+        c.backends_set(8, tracegen.gen_insert_draws(8), nslots)
+        ctxs.append(c)
+        s, n = tracegen.gen_trace(steps * m, seed=900 + r, de=1_000 + 300 * r, unit=1 << 12)
+        traces.append((s, n, torch.from_numpy(s).to(dev), torch.from_numpy(n).to(dev)))
+        outs.append((torch.empty(steps * m, dtype=torch.uint8, device=dev), torch.empty(steps * m, dtype=torch.int32, device=dev)))
+    boards = [c.peers_board() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.peers_connect(R, r, ptrs=[b[1] for b in boards])
+    torch.cuda.synchronize()
+    for k in range(steps):
+        for r, c in enumerate(ctxs):
+            _, _, ts, tn = traces[r]
+            dec, slot = outs[r]
+            lo = k * m
+            c.admit_batch_ptr(ts.data_ptr() + 8 * lo, tn.data_ptr() + 8 * lo, None, m, dec.data_ptr() + lo,
+                              slot.data_ptr() + 4 * lo, None)
+    want_d = want_a = 0
+    for r in range(R):
+        cd = O.new_codel(tgt)
+        od, _, ost = O.drain(cd, traces[r][0], traces[r][1], None, nslots=nslots)
+        assert np.array_equal(outs[r][0].cpu().numpy(), od)
+        want_d += ost.drops
+        want_a += ost.admits
+    for c in ctxs:
+        g = c.peers_counts()
+        assert (g.steps, g.drops, g.admits, g.n) == (steps, want_d, want_a, R * steps * m)
+    for c in ctxs:
+        c.peers_connect(0, 0)
+        c.close()

@@ -1,8 +1,7 @@
 """GPU parity tests of the device-resident pending-claim queue (cb_queue_*) against
 the pinned pool-model oracle.  The kernels follow tools/proto_queue.py, which passes the same
-comparisons on CPU (tests/test_proto_queue.py), but they have NOT run on hardware yet: the round's
-GPU budget was spent before this row was reached.  They are therefore skipped unless
-CB_TEST_UNVALIDATED=1, so that an unvalidated feature cannot mask the validated suite."""
+comparisons on CPU (tests/test_proto_queue.py); validated on a B200 at the start of round 2
+(profiles/r02_validate_pending.txt)."""
 import os
 
 import numpy as np
@@ -11,9 +10,7 @@ import pytest
 import util
 from oracle import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CB_TEST_UNVALIDATED") != "1",
-                                 reason="cb_queue_* not yet validated on hardware (set CB_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 G = util.load_golden("pool_sim_golden.json")
 

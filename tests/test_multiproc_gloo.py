@@ -1,7 +1,7 @@
 """world_size-2 CPU test (gloo) of the multi-GPU host logic: every rank owns a contiguous
 queue segment with its own ControlledDelay and the job's global drop/admit counts come from
-ONE sum-allreduce of three integers per step -- exactly what cb_allreduce_counts does with NCCL
-on the GPUs (bench.py --gpus N).  On CPU the per-rank admission is stood in by the oracle; the
+ONE sum of three integers per step -- what cb_allreduce_counts does with NCCL and what the peer-memory
+boards of cb_peers_* do without a collective on the GPUs (bench.py --gpus N).  On CPU the per-rank admission is stood in by the oracle; the
 test checks the sharding (bench.make_trace is per-rank seeded and deterministic) and that the
 reduced counts equal the counts of the segments processed one after the other."""
 import os
@@ -22,7 +22,7 @@ def _worker(rank, world, port, n, steps, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    start, now = bench.make_trace("c4", n * steps, rank)
+    start, now = (t.numpy() for t in bench.make_trace("c4", n * steps, rank, torch.device("cpu")))
     cd = O.new_codel(bench.TARGET_MS)
     cursor, tot = 0, np.zeros(3, np.int64)
     for s in range(steps):
@@ -56,7 +56,7 @@ def test_two_rank_segment_sharding_and_count_allreduce():
     want = np.zeros(3, np.int64)
     segs = []
     for r in range(world):
-        start, now = bench.make_trace("c4", n * steps, r)
+        start, now = (t.numpy() for t in bench.make_trace("c4", n * steps, r, torch.device("cpu")))
         segs.append((start, now))
         cd = O.new_codel(bench.TARGET_MS)
         _, _, st = O.drain(cd, start, now, nslots=64, want_out=False)
@@ -64,8 +64,8 @@ def test_two_rank_segment_sharding_and_count_allreduce():
     assert got == want.tolist()
     # segments of different ranks are different traces (per-rank seeds), same rank reproducible
     assert not np.array_equal(segs[0][1], segs[1][1])
-    again = bench.make_trace("c4", n * steps, 1)
-    assert np.array_equal(again[1], segs[1][1])
+    again = bench.make_trace("c4", n * steps, 1, torch.device("cpu"))
+    assert np.array_equal(again[1].numpy(), segs[1][1])
 
 
 def _ring_worker(rank, world, port, m, steps, out):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/sass_hashes.py <lib.so> [--write profiles/validated_sass.json] -- per-kernel md5 of the SASS
+"""tools/sass_hashes.py <lib.so> [--write profiles/validated_sass.json [note]] -- per-kernel md5 of the SASS
 (cuobjdump -sass, addresses and comments stripped).  Used to pin which device code actually ran on
 hardware: a kernel whose hash differs from profiles/validated_sass.json has changed since the last
 GPU validation (tests/test_validated_sass.py)."""
@@ -28,7 +28,8 @@ def kernel_hashes(so):
 if __name__ == "__main__":
     h = kernel_hashes(sys.argv[1])
     if len(sys.argv) > 3 and sys.argv[2] == "--write":
+        note = sys.argv[4] if len(sys.argv) > 4 else "md5 of each kernel's SASS (tools/sass_hashes.py)"
         with open(sys.argv[3], "w") as f:
-            json.dump(h, f, indent=1)
+            json.dump({"_note": note, "kernels": h}, f, indent=1)
     for k, v in h.items():
         print(v, k)
