@@ -22,8 +22,8 @@ ControlledDelay state chains from batch to batch on the device.
 the launching stream, max over ranks.  Nothing in the timed region touches the host: no stats read,
 no torch collective.  N > 1: one process per GPU, each rank drains its own queue segment (no
 data-path collective); the GLOBAL drop/admit counts exist after every batch, device-side, through
-the peer-memory boards of cb_peers_* (a tiny kernel behind each batch's emit stores the counts into
-every rank's board over NVLink).  The north star's literal "single NCCL allreduce" is timed
+the peer-memory boards of cb_peers_* (the last CTA of each batch's emit kernel stores the counts
+into every rank's board over NVLink).  The north star's literal "single NCCL allreduce" is timed
 separately (`nccl_allreduce`).  `one_queue` is the other multi-GPU mode: ONE logical queue whose
 ControlledDelay state goes round a ring of device mailboxes, checked bit for bit against one
 sequential drain on a window.
@@ -565,18 +565,28 @@ def device_leg(wl, K, W, world, rank, local, dev, stream, want_parity=True, want
     fills the line from it)."""
     import torch.distributed as dist
     run = Run(wl, K, W, world, rank, local, dev, stream)
+    peers = peers and os.environ.get("CB_BENCH_PEERS", "1") != "0"  # measurement knob: the same pass without the boards
     if peers and world > 1:
         h, _ = run.ctx.peers_board()
         hs = [None] * world
         dist.all_gather_object(hs, h)
         run.ctx.peers_connect(world, rank, handles=hs)
+    elif peers and os.environ.get("CB_BENCH_PEERS") == "self":  # one rank posting to its own board (cost of the post kernel)
+        run.ctx.peers_connect(1, 0)
     if sampler:
         sampler.start()
     ms, host_ms, launches = timed_pass(run)
     clocks = sampler.stop() if sampler else None
+    ms_rank = ms
     ms = max_over_ranks(ms, world, dev)
     out = {"ms": ms, "host_ms": host_ms, "launches": sum_over_ranks([launches], world, dev)[0], "clocks": clocks,
            "value": world * run.n * K / (ms / 1e3)}
+    if world > 1:  # every rank's own device time of the K steps (the line's ms_per_step is the maximum)
+        import torch
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = ms_rank / K
+        dist.all_reduce(t)
+        out["ms_per_step_by_rank"] = [round(x, 5) for x in t.tolist()]
     st = run.ctx.stats()
     out["admit_fraction"] = st.total_admits / max(st.total_admits + st.total_drops, 1)
     if peers and world > 1:
@@ -625,7 +635,7 @@ def nccl_leg(wl, K, W, world, rank, local, dev, stream):
 
     def last_only():
         calls["i"] += 1
-        if calls["i"] == W + K:
+        if calls["i"] == 1 or calls["i"] == W + K:  # the first call (warm-up) sets up the communicator's channels
             run.ctx.allreduce_counts()
     ms, _, _ = timed_pass(run, per_step=last_only)
     ms = max_over_ranks(ms, world, dev)
@@ -806,6 +816,8 @@ def run_cuda(args, wl, extra=True):
     }
     if "global_counts" in main:
         line["global_counts"] = main["global_counts"]
+    if "ms_per_step_by_rank" in main:
+        line["ms_per_step_by_rank"] = main["ms_per_step_by_rank"]
     if "cpu_baseline" in main:
         line["cpu_baseline"] = main["cpu_baseline"]
     if extra:

@@ -17,6 +17,7 @@
 // of a warp covers one contiguous 128 B (decisions) or 512 B (slots / backends) span.
 #pragma once
 #include "cb_device.cuh"
+#include "cb_peers.cuh"
 
 namespace cb {
 
@@ -45,7 +46,8 @@ struct EmitParams {
 	SumDesc *sdesc;
 	unsigned long long epoch;
 	ChainLink link; // a flags batch passes the commit chain on from here (its cursor is final then)
-	unsigned int *ticket;          // CTA completion counter (flags variant finalisation)
+	unsigned int *ticket;          // CTA completion counter (the last CTA finalises a flags batch and posts the counts)
+	PeerLink peer;                 // peer.mine == nullptr: no boards connected
 	int vec_ok;                    // outputs suitably aligned for vector stores
 };
 
@@ -130,8 +132,11 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	BatchCtl *bc = p.bc;
 	if (tid == 0 && blockIdx.x == 0)
 		bc->dbg[10] = gtimer(); // timeline stamp (tools/pipeline_timeline.py)
-	if (bc->path == 1) // the sequential path already wrote every output
+	if (bc->path == 1) { // the sequential path already wrote every output (and its counts are final)
+		if (p.peer.mine && blockIdx.x == 0 && tid == 0)
+			peer_post(p.peer, bc);
 		return;
+	}
 	const bool want_backend = (p.backend != nullptr) && (p.nslots > 0);
 	const bool stage_table = want_backend && (p.table_smem_bytes > 0);
 	const unsigned int m = bc->n_intervals;
@@ -452,8 +457,9 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 
 	if (tid == 0 && blockIdx.x == gridDim.x - 1)
 		bc->dbg[11] = gtimer();
-	// ---- flags variant: the last CTA to finish publishes the batch totals -----------------
-	if (FLAGS) {
+	// ---- the last CTA to finish: a flags batch's totals (its admit cursor is final only now) and the
+	// counts for the other ranks' boards ---------------------------------------------------------------
+	if (FLAGS || p.peer.mine) {
 		__threadfence();
 		__syncthreads();
 		if (tid == 0) {
@@ -461,17 +467,21 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 			if (done == gridDim.x - 1) {
 				*p.ticket = 0;
 				__threadfence();
-				const unsigned long long admits = ld_relaxed_u64(&p.sdesc[p.tiles - 1].incl);
-				const unsigned long long drops = atomicAdd(&bc->drops, 0ull);
-				bc->admits = admits;
-				g->cursor = bc->cursor0 + admits;
-				g->tot_drops += drops;
-				g->tot_admits += admits;
-				bc->gcounts[0] = drops;
-				bc->gcounts[1] = admits;
-				bc->lcounts[0] = drops;
-				bc->lcounts[1] = admits;
-				chain_post(p.link, g); // the next batch's commit may read the cursor now
+				if (FLAGS) {
+					const unsigned long long admits = ld_relaxed_u64(&p.sdesc[p.tiles - 1].incl);
+					const unsigned long long drops = atomicAdd(&bc->drops, 0ull);
+					bc->admits = admits;
+					g->cursor = bc->cursor0 + admits;
+					g->tot_drops += drops;
+					g->tot_admits += admits;
+					bc->gcounts[0] = drops;
+					bc->gcounts[1] = admits;
+					bc->lcounts[0] = drops;
+					bc->lcounts[1] = admits;
+					chain_post(p.link, g); // the next batch's commit may read the cursor now
+				}
+				if (p.peer.mine)
+					peer_post(p.peer, bc);
 			}
 		}
 	}

@@ -5,8 +5,8 @@
 // then the tag at system scope).  A rank then finds the global counts of step s by reading its own
 // board: once all R rows carry tag s+1 the sums are the counts of step s over the whole sharded
 // queue, and the running totals are the pool's global 'claim-timeout' counter (lib/pool.js:269-283)
-// as of that step.  Nothing on the data path waits for this: the post is one tiny kernel behind the
-// batch's emit kernel, on the batch's own stream, and ranks never block one another (a rank that runs
+// as of that step.  Nothing on the data path waits for this: the post is done by one thread of the
+// last CTA of the batch's emit kernel (no extra launch), and ranks never block one another (a rank that runs
 // ahead is only held once it is PB_SLOTS batches in front of the slowest reader: flow control through
 // the ack words, which each rank stores into its peers' boards the same way).
 // The literal "single NCCL allreduce" of the north star stays available (cb_allreduce_counts).
@@ -84,10 +84,9 @@ __device__ __forceinline__ void peer_finalise(const PeerLink &pl) {
 	atomicExch(&b->lock, 0u);
 }
 
-// one thread, behind the batch's emit kernel: publish this batch's counts to every rank, then finalise
-__global__ void peer_post_kernel(const PeerLink pl, const BatchCtl *bc) {
-	if (threadIdx.x != 0)
-		return;
+// one thread, once the batch's counts are final (the last CTA of its emit kernel): publish them to every rank,
+// then finalise whatever is complete on this rank's board
+__device__ __forceinline__ void peer_post(const PeerLink &pl, const BatchCtl *bc) {
 	const unsigned long long s = pl.step;
 	const unsigned long long drops = bc->lcounts[0], admits = bc->lcounts[1], n = bc->lcounts[2];
 	const unsigned long long t0 = gtimer();

@@ -325,7 +325,7 @@ int ensure_scratch(cb_ctx *c, Lane &L, size_t tiles) {
 // of three.  The scan node keeps the lowest priority, the others the highest.
 PeerLink peer_link(const cb_ctx *c, unsigned long long step) {
 	PeerLink pl;
-	pl.mine = c->d_board;
+	pl.mine = c->peers_n > 0 ? c->d_board : nullptr;
 	pl.peers = c->d_peer_ptrs;
 	pl.R = c->peers_n;
 	pl.me = c->peers_rank;
@@ -333,17 +333,6 @@ PeerLink peer_link(const cb_ctx *c, unsigned long long step) {
 	pl.timeout_ns = 30000000000ull; // the other ranks are other processes: allow for start-up skew
 	return pl;
 }
-// behind the batch's emit kernel, on its stream: publish the batch's counts to every rank's board
-int peers_post(cb_ctx *c, Lane &L, cudaStream_t s) {
-	if (c->peers_n <= 0)
-		return CB_OK;
-	peer_post_kernel<<<1, 32, 0, s>>>(peer_link(c, c->peer_step), L.ctl);
-	c->peer_step++;
-	c->launches++;
-	CU(c, cudaGetLastError());
-	return CB_OK;
-}
-
 template <bool NS>
 int graph_batch(cb_ctx *c, Lane &L, bool flags, ScanParams &sp, ResolveParams &rp, EmitParams &ep, size_t tiles,
     unsigned egrid, cudaStream_t s) {
@@ -518,6 +507,13 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	ep.epoch = L.epoch;
 	ep.ticket = L.ticket;
 	ep.link = rp.link;
+	// counts for the other ranks' boards, posted by the emit kernel's last CTA; a batch takes a board step only
+	// when its emit kernel really runs (the scan-only measurement mode launches none)
+	ep.peer = peer_link(c, c->prof_scan_only ? ~0ull : c->peer_step);
+	if (c->prof_scan_only)
+		ep.peer.mine = nullptr;
+	else if (c->peers_n > 0)
+		c->peer_step++;
 	ep.vec_ok = (((uintptr_t)d_decision & 7) == 0) && (((uintptr_t)d_slot & 15) == 0) &&
 	    (((uintptr_t)d_backend & 15) == 0);
 	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
@@ -561,8 +557,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		CU(c, cudaGetLastError());
 		if (out_done || (flags && c->comm))
 			CU(c, cudaEventRecord(L.emit_done, s));
-		if ((rc = peers_post(c, L, s)))
-			return rc;
+
 		L.used = true;
 		L.coll_pending = false;
 		c->last_lane = li;
@@ -621,8 +616,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	CU(c, cudaGetLastError());
 	if (out_done || (piped && flags && c->comm))
 		CU(c, cudaEventRecord(L.emit_done, s));
-	if ((rc = peers_post(c, L, s)))
-		return rc;
+
 	L.used = true;
 	L.coll_pending = false;
 	c->last_lane = li;
@@ -643,8 +637,9 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	return CB_OK;
 }
 
-int fetch_stats(cb_ctx *c, cb_batch_stats *out) {
-	int rc = drain(c);
+int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool drained = false) {
+	// `drained`: the caller has already waited for every batch (host_batch: its last copy-out has landed)
+	int rc = drained ? CB_OK : drain(c);
 	if (rc)
 		return rc;
 	// three small device-to-host copies into pinned memory, one wait (a blocking cudaMemcpy each costs ~10 us)
@@ -749,14 +744,15 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		return rc;
 	// Staging chunks.  The H2D copies run back to back on the copy engine; a chunk's kernels and its D2H
 	// overlap the copy-in of the chunks behind it, so what the call pays beyond the PCIe time of its inputs
-	// is the LAST chunk's kernels and copy-out.  Chunks therefore shrink towards the end (40 % of what is left,
-	// at most c->chunk, at least 64K claims): the exposed tail is a few tens of microseconds at any size.
+	// is the LAST chunk's kernels and copy-out.  Chunks therefore shrink towards the end (half of what is left,
+	// at most c->chunk, at least 128K claims -- a chunk's kernels are latency-bound below that, and every chunk
+	// costs two small copies): the exposed tail is a few tens of microseconds at any size.
 	std::vector<size_t> plan;
 	{
-		const size_t floor_chunk = 16 * (size_t)ETILE; // 64K claims: below this the per-chunk cost wins
+		const size_t floor_chunk = 32 * (size_t)ETILE; // 128K claims: below this the per-chunk cost wins
 		size_t left = n;
 		while (left > 0) {
-			size_t m = ((left * 2 / 5) + ETILE - 1) / ETILE * ETILE;
+			size_t m = ((left / 2) + ETILE - 1) / ETILE * ETILE;
 			if (m > c->chunk)
 				m = c->chunk;
 			if (m < floor_chunk)
@@ -802,7 +798,7 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		fprintf(stderr, "[cb e2e] n=%zu chunks=%zu  entry sync+state %.0f us | enqueue %.0f us | wait %.0f us\n", n, nchunks,
 		    T1 - T0, T2 - T1, T3 - T2);
 	if (stats) {
-		rc = fetch_stats(c, stats);
+		rc = fetch_stats(c, stats, decision || slot || backend); // outputs copied out => every kernel has finished
 		if (rc)
 			return rc;
 		// totals of the whole call, not of its last chunk
@@ -998,7 +994,7 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		    (const void *)scan_kernel<false, true>, (const void *)scan_kernel<false, false>,
 		    (const void *)resolve_kernel<true, true>, (const void *)resolve_kernel<true, false>,
 		    (const void *)resolve_kernel<false, true>, (const void *)resolve_kernel<false, false>,
-		    (const void *)emit_kernel<true>, (const void *)emit_kernel<false>, (const void *)peer_post_kernel,
+		    (const void *)emit_kernel<true>, (const void *)emit_kernel<false>,
 		    (const void *)fchain_seed_kernel};
 		for (const void *f : fns)
 			CU0(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));

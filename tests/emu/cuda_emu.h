@@ -238,3 +238,8 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
 	return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
 }
 inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned int atomicCAS(unsigned int *p, unsigned int cmp, unsigned int v) {
+	__atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+	return cmp; /* the value found */
+}
+inline unsigned int atomicExch(unsigned int *p, unsigned int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }

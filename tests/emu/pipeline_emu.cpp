@@ -149,6 +149,12 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	ep.sdesc = sdesc;
 	ep.epoch = 1;
 	ep.link = rp.link;
+	ep.peer.mine = nullptr; /* no peer boards in the emulation */
+	ep.peer.peers = nullptr;
+	ep.peer.R = 0;
+	ep.peer.me = 0;
+	ep.peer.step = 0;
+	ep.peer.timeout_ns = 0;
 	ep.ticket = ticket;
 	ep.vec_ok = (((uintptr_t)decision & 7) == 0) && (((uintptr_t)slot & 15) == 0);
 

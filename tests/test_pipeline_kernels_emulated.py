@@ -25,7 +25,7 @@ def load_emu():
     """Build (if stale) and load the emulated pipeline library."""
     csrc = os.path.join(util.ROOT, "node-cueball_b200", "csrc")
     srcs = [os.path.join(EMU, "pipeline_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h")] + \
-           [os.path.join(csrc, f) for f in ("cb_device.cuh", "cb_scan.cuh", "cb_resolve.cuh", "cb_emit.cuh")]
+           [os.path.join(csrc, f) for f in ("cb_device.cuh", "cb_scan.cuh", "cb_resolve.cuh", "cb_emit.cuh", "cb_peers.cuh")]
     # CB_EMU_DEFS="-DCB_SCAN_WARPS=1 -DCB_SCAN_NST=2" (with CB_EMU_SCAN_GRID=1) makes one warp walk many tiles
     # through a short stage ring: the fuzz runs use it to exercise the scan kernel's streaming loop
     defs = os.environ.get("CB_EMU_DEFS", "").split()
