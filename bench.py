@@ -22,8 +22,8 @@ ControlledDelay state chains from batch to batch on the device.
 the launching stream, max over ranks.  Nothing in the timed region touches the host: no stats read,
 no torch collective.  N > 1: one process per GPU, each rank drains its own queue segment (no
 data-path collective); the GLOBAL drop/admit counts exist after every batch, device-side, through
-the peer-memory boards of cb_peers_* (the last CTA of each batch's emit kernel stores the counts
-into every rank's board over NVLink).  The north star's literal "single NCCL allreduce" is timed
+the peer-memory boards of cb_peers_* (each batch stores its counts into its rank's board; an extra CTA
+of its emit kernel reads the other ranks' rows over NVLink).  The north star's literal "single NCCL allreduce" is timed
 separately (`nccl_allreduce`).  `one_queue` is the other multi-GPU mode: ONE logical queue whose
 ControlledDelay state goes round a ring of device mailboxes, checked bit for bit against one
 sequential drain on a window.
@@ -42,6 +42,7 @@ sequential state machine and Node itself is single threaded -- on a bounded samp
 workload (`config.reference_sample_claims_per_step`, the same key in both arms).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -384,23 +385,57 @@ def sum_over_ranks(xs, world, dev):
     return [int(x) for x in t.tolist()]
 
 
+def _realtime(on, saved=None):
+    """SCHED_FIFO for the enqueueing thread while the timed steps are submitted (best effort: needs CAP_SYS_NICE)."""
+    try:
+        if on:
+            saved = (os.sched_getscheduler(0), os.sched_getparam(0))
+            os.sched_setscheduler(0, os.SCHED_FIFO, os.sched_param(10))
+            return saved
+        if saved is not None:
+            os.sched_setscheduler(0, saved[0], saved[1])
+    except (OSError, AttributeError, PermissionError):
+        pass
+    return None
+
+
 def timed_pass(run, per_step=None):
     """W untimed + K timed steps; (device ms of the K steps on this rank, host ms/step to enqueue,
     kernels launched by the K steps).  Nothing between the two events touches the host except the
     enqueueing itself.  per_step: optional callable after every step (e.g. an NCCL allreduce)."""
     torch = run.torch
     W, K, ctx, stream = run.W, run.K, run.ctx, run.stream
-    for b in range(W):
+    idle = os.environ.get("CB_BENCH_IDLE_RANKS") == "1" and run.rank != 0  # diagnosis: only rank 0 works
+    # The last two of the W warm-up steps run AFTER the barrier, device-ordered in front of the first event (cb_join:
+    # a stream wait, no host wait): a cross-rank barrier leaves the GPU idle for up to milliseconds, and the timed
+    # steps should meet the clocks and memory state of a running pipeline, not of an idle GPU.
+    rewarm = 0 if os.environ.get("CB_BENCH_REWARM") == "0" else min(2, W)
+    for b in range(W - rewarm):
+        if idle:
+            break
         run.step(b)
         if per_step:
             per_step()
     ctx.synchronize()
     barrier(run.world)
+    for b in range(W - rewarm, W):
+        if idle:
+            break
+        run.step(b)
+        if per_step:
+            per_step()
+    ctx.join()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the K steps are ~1 ms of GPU time fed by this thread: keep the collector and the scheduler out of the way
+    gc_was = gc.isenabled()
+    gc.disable()
+    rt = _realtime(True)
     e0.record(stream)
     lc0 = ctx.launch_count()
     th0 = time.perf_counter()
     for b in range(W, W + K):
+        if idle:
+            break
         run.step(b)
         if per_step:
             per_step()
@@ -408,6 +443,9 @@ def timed_pass(run, per_step=None):
     nlaunch = ctx.launch_count() - lc0            # this library's kernels launched by the K timed steps
     ctx.join()  # the timing stream waits for the last batch of the pipeline (stream-ordered, no host wait)
     e1.record(stream)
+    _realtime(False, rt)
+    if gc_was:
+        gc.enable()
     barrier(run.world)
     ctx.synchronize()
     return e0.elapsed_time(e1), hms, nlaunch
@@ -589,13 +627,15 @@ def device_leg(wl, K, W, world, rank, local, dev, stream, want_parity=True, want
         out["ms_per_step_by_rank"] = [round(x, 5) for x in t.tolist()]
     st = run.ctx.stats()
     out["admit_fraction"] = st.total_admits / max(st.total_admits + st.total_drops, 1)
-    if peers and world > 1:
+    if peers and world > 1 and os.environ.get("CB_PEERS_DEBUG"):
+        run.ctx.peers_connect(0, 0)  # measurement variants of the post: nothing to read back
+    elif peers and world > 1:
         g = run.ctx.peers_counts()  # running global totals after this rank's last batch, from its own board
         loc = sum_over_ranks([st.total_drops, st.total_admits, run.n * run.nb], world, dev)
         out["global_counts"] = {"drops": int(g.drops), "admits": int(g.admits), "claims": int(g.n), "steps": int(g.steps),
                                 "equals_sum_of_ranks": [int(g.drops), int(g.admits), int(g.n)] == loc,
-                                "how": "cb_peers_*: per-batch counts stored into every rank's board over NVLink peer memory "
-                                       "(device-side, after every batch, inside the timed region); no collective"}
+                                "how": "cb_peers_*: per-batch counts in each rank's board, the other ranks' rows read over NVLink peer "
+                                       "memory (device-side, after every batch, inside the timed region); no collective"}
         run.ctx.peers_connect(0, 0)
     host_trace = None
     if want_parity:
@@ -687,6 +727,9 @@ def ring_leg(wl, K, W, world, rank, local, dev, stream):
     ctx.set_stream(stream.cuda_stream)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc_was = gc.isenabled()
+    gc.disable()
+    rt = _realtime(True)
     for k in range(nb):
         if k == W:
             ctx.join()
@@ -695,6 +738,9 @@ def ring_leg(wl, K, W, world, rank, local, dev, stream):
         ctx.admit_batch_ptr(ds.data_ptr() + 8 * lo, dn.data_ptr() + 8 * lo, None, m, dd.data_ptr() + lo, sl.data_ptr() + 4 * lo, None)
     ctx.join()
     e1.record(stream)
+    _realtime(False, rt)
+    if gc_was:
+        gc.enable()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     # window check: the queue's first kc steps, drained sequentially by the oracle on every rank's host
@@ -790,10 +836,11 @@ def run_cuda(args, wl, extra=True):
     assert stream.cuda_stream != 0
     K, W = args.steps, args.warmup
 
-    pcie = pcie_rates(dev, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)) if rank == 0 or world > 1 else None
-    sampler = ClockSampler(local) if rank == 0 else None
-    main = device_leg(wl, K, W, world, rank, local, dev, stream, want_parity=True, want_e2e=True, want_roof=True, pcie=pcie,
-                      peers=True, sampler=sampler, want_cpu=(extra and world == 1))
+    fast = os.environ.get("CB_BENCH_FAST") == "1"  # diagnosis only: the timed pass and nothing else (the line is incomplete)
+    pcie = pcie_rates(dev, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)) if (rank == 0 or world > 1) and not fast else None
+    sampler = ClockSampler(local) if rank == 0 and os.environ.get("CB_BENCH_SAMPLER", "1") != "0" else None
+    main = device_leg(wl, K, W, world, rank, local, dev, stream, want_parity=not fast, want_e2e=not fast, want_roof=not fast, pcie=pcie,
+                      peers=True, sampler=sampler, want_cpu=(extra and world == 1 and not fast))
     w = WORKLOADS[wl]
     cfg = workload_config(wl, world)
     line = {
@@ -808,7 +855,9 @@ def run_cuda(args, wl, extra=True):
             "pipeline": "up to 5 batches in flight, one lane (stream) each; the scan is launched at low priority, "
                         "resolve/emit at high; commits ordered by a device-side chain word",
             "global_counts": "per batch, device-side, over peer-memory boards (cb_peers_*)" if world > 1 else None,
-            "timed_region": "CUDA events on the launching stream around the K steps; no host wait, no torch collective inside",
+            "timed_region": "barrier + synchronize, the last 2 warm-up steps (device-ordered, so the timed steps start on a busy GPU), "
+                            "CUDA event, the K steps, cb_join (stream-ordered), CUDA event, barrier + synchronize; no host wait and "
+                            "no torch collective inside",
             "admit_fraction": main["admit_fraction"],
             "cpu_affinity": ("%d CPUs of the GPU's NUMA node" % numa_cpus) if numa_cpus else "unbound"},
         "roofline": main.get("roofline"), "e2e": main.get("e2e"), "gpu_launches": main["launches"], "clocks": main["clocks"],

@@ -239,11 +239,11 @@ int cb_comm_unique_id(void *out, size_t *bytes); /* ncclGetUniqueId; bytes in/ou
 int cb_comm_init(cb_ctx *ctx, int nranks, int rank, const void *unique_id, size_t bytes);
 int cb_allreduce_counts(cb_ctx *ctx); /* async on the context's stream */
 
-/* The same global counts after EVERY batch without a collective: each rank owns a board in HBM; the last
- * CTA of the batch's emit kernel stores the batch's {drops, admits, n} into its row of every
- * rank's board over NVLink peer memory (payload, then a system-scope tag), and sums the rows of its own
- * board as they complete.  No rank waits for another on the data path (flow control only holds a rank
- * that is 64 batches ahead of the slowest reader).  Every rank must submit the same number of batches.
+/* The same global counts after EVERY batch without a collective: each rank owns a board in HBM and stores
+ * the batch's {drops, admits, n} into it (self-tagged 16-byte words); one thread of an extra CTA of the
+ * batch's emit kernel then reads that batch's row of every rank's board over NVLink peer memory and keeps
+ * running totals.  No rank waits for another on the data path (flow control only holds a rank that is 64
+ * batches ahead of the slowest reader).  Every rank must submit the same number of batches.
  *   cb_peers_board   : this context's board as a CUDA IPC handle (64 bytes) and/or a device pointer.
  *   cb_peers_connect : join `nranks` (<= 16) as `rank`; boards by IPC handle (nranks x 64 bytes, entry
  *                      `rank` ignored) or by pointer (contexts of this process); nranks == 0 disconnects.

@@ -47,7 +47,8 @@ struct EmitParams {
 	unsigned long long epoch;
 	ChainLink link; // a flags batch passes the commit chain on from here (its cursor is final then)
 	unsigned int *ticket;          // CTA completion counter (the last CTA finalises a flags batch and posts the counts)
-	PeerLink peer;                 // peer.mine == nullptr: no boards connected
+	PeerLink peer;                 // count boards (peer.mine == nullptr: none): the grid then has ONE extra CTA, the last,
+	                               // which handles no tile: it posts the batch's counts and reads the other ranks' rows
 	int vec_ok;                    // outputs suitably aligned for vector stores
 };
 
@@ -132,11 +133,18 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	BatchCtl *bc = p.bc;
 	if (tid == 0 && blockIdx.x == 0)
 		bc->dbg[10] = gtimer(); // timeline stamp (tools/pipeline_timeline.py)
-	if (bc->path == 1) { // the sequential path already wrote every output (and its counts are final)
-		if (p.peer.mine && blockIdx.x == 0 && tid == 0)
+	// Count boards: the remote reads of the other ranks' rows take NVLink round trips.  They run in a CTA of
+	// their own beside the tile CTAs, so nothing waits for them (in the resolve kernel they delayed this kernel's
+	// start, and the pipelined step with it: 58 -> 62-66 us on two GPUs).  A batch with waiting flags knows its
+	// counts only when its last tile CTA is done and posts from there.
+	const unsigned int tile_ctas = gridDim.x - (p.peer.mine ? 1u : 0u);
+	if (p.peer.mine && blockIdx.x == tile_ctas) {
+		if (tid == 0 && (!FLAGS || bc->path == 1))
 			peer_post(p.peer, bc);
 		return;
 	}
+	if (bc->path == 1) // the sequential path already wrote every output
+		return;
 	const bool want_backend = (p.backend != nullptr) && (p.nslots > 0);
 	const bool stage_table = want_backend && (p.table_smem_bytes > 0);
 	const unsigned int m = bc->n_intervals;
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 	const int32_t *tb = reinterpret_cast<const int32_t *>(s_dyn);
 	bool table_ready = false;
 
-	for (unsigned long long t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+	for (unsigned long long t = blockIdx.x; t < p.tiles; t += tile_ctas) {
 		const unsigned long long ts = t * (unsigned long long)ETILE;
 		unsigned long long te = ts + ETILE;
 		if (te > p.n)
@@ -455,19 +463,19 @@ __global__ void __launch_bounds__(ETPB, 4) emit_kernel(const EmitParams p) {
 			__syncthreads(); // s_wsum / s_tile_excl are reused by the next tile
 	}
 
-	if (tid == 0 && blockIdx.x == gridDim.x - 1)
+	if (tid == 0 && blockIdx.x == tile_ctas - 1)
 		bc->dbg[11] = gtimer();
 	// ---- the last CTA to finish: a flags batch's totals (its admit cursor is final only now) and the
 	// counts for the other ranks' boards ---------------------------------------------------------------
-	if (FLAGS || p.peer.mine) {
+	if (FLAGS) {
 		__threadfence();
 		__syncthreads();
 		if (tid == 0) {
 			unsigned int done = atomicAdd(p.ticket, 1u);
-			if (done == gridDim.x - 1) {
+			if (done == tile_ctas - 1) {
 				*p.ticket = 0;
 				__threadfence();
-				if (FLAGS) {
+				{
 					const unsigned long long admits = ld_relaxed_u64(&p.sdesc[p.tiles - 1].incl);
 					const unsigned long long drops = atomicAdd(&bc->drops, 0ull);
 					bc->admits = admits;

@@ -143,6 +143,7 @@ struct cb_ctx {
 	PeerBoard **d_peer_ptrs = nullptr;     // device array of the ranks' boards (peer memory)
 	void *peer_ipc[PB_MAXR] = {};          // boards opened from IPC handles (to be closed)
 	int peers_n = 0, peers_rank = 0;
+	unsigned int peers_dbg = 0;            // CB_PEERS_DEBUG (measurement only)
 	unsigned long long peer_step = 0;      // batches posted since cb_peers_connect
 	unsigned long long *d_peer_out = nullptr;
 	int ring_n = 0, ring_rank = 0;
@@ -331,6 +332,9 @@ PeerLink peer_link(const cb_ctx *c, unsigned long long step) {
 	pl.me = c->peers_rank;
 	pl.step = step;
 	pl.timeout_ns = 30000000000ull; // the other ranks are other processes: allow for start-up skew
+	pl.dbg = c->peers_dbg;
+	if (c->peers_dbg & 1u) // measurement: boards connected, nothing posted
+		pl.mine = nullptr;
 	return pl;
 }
 template <bool NS>
@@ -514,12 +518,14 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		ep.peer.mine = nullptr;
 	else if (c->peers_n > 0)
 		c->peer_step++;
+
 	ep.vec_ok = (((uintptr_t)d_decision & 7) == 0) && (((uintptr_t)d_slot & 15) == 0) &&
 	    (((uintptr_t)d_backend & 15) == 0);
 	// persistent CTAs stride over the tiles; with flags the admit-count look-back needs every
 	// earlier tile to be resident or earlier in the same CTA's sequence: both hold for a grid
 	// within the resident capacity (a CTA visits its tiles in increasing order)
-	const unsigned egrid = (unsigned)(etiles < (size_t)c->emit_grid ? etiles : (size_t)c->emit_grid);
+	// (+1 CTA that handles no tile when count boards are connected: see emit_kernel)
+	const unsigned egrid = (unsigned)(etiles < (size_t)c->emit_grid ? etiles : (size_t)c->emit_grid) + (ep.peer.mine ? 1u : 0u);
 
 	// One stream per lane: scan -> prepare -> commit -> emit of a batch are stream-ordered, batches
 	// of different lanes overlap freely.  The only cross-lane edge is the ControlledDelay state:
@@ -956,6 +962,8 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
+	if (getenv("CB_PEERS_DEBUG"))
+		c->peers_dbg = (unsigned int)atoi(getenv("CB_PEERS_DEBUG"));
 	if (getenv("CB_GRAPH")) // measurement override of the launch mode: 0 = never a graph, 1 = always
 		c->graph_mode = atoi(getenv("CB_GRAPH")) != 0 ? 1 : 0;
 	CU0(cudaMalloc((void **)&c->d_chain, sizeof(ChainMem)));

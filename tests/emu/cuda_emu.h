@@ -198,6 +198,18 @@ inline unsigned long long ld_acquire(const unsigned long long *p) { return __ato
 inline void st_release(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return ld_acquire(p); }
 inline void st_release_sys(unsigned long long *p, unsigned long long v) { st_release(p, v); }
+inline void st_relaxed_sys(unsigned long long *p, unsigned long long v) { st_release(p, v); }
+struct PeerWord;
+template <typename W> inline void st_word(W *p, unsigned long long tag, unsigned long long v) {
+	p->v = v;
+	__atomic_store_n(&p->tag, tag, __ATOMIC_RELEASE);
+}
+template <typename W> inline W ld_word(const W *p) {
+	W w;
+	w.tag = __atomic_load_n(&p->tag, __ATOMIC_ACQUIRE);
+	w.v = p->v;
+	return w;
+}
 inline double ld_relaxed_f64(const double *p) { return *(const volatile double *)p; }
 inline unsigned long long ld_relaxed_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 /* mbarrier + TMA bulk copy (csrc/cb_scan.cuh): the barrier word holds the pending transaction bytes in its low half

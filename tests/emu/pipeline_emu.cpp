@@ -155,6 +155,7 @@ static int pipe_admit(EmuPipe *e, const void *start, const void *now, const unsi
 	ep.peer.me = 0;
 	ep.peer.step = 0;
 	ep.peer.timeout_ns = 0;
+	ep.peer.dbg = 0;
 	ep.ticket = ticket;
 	ep.vec_ok = (((uintptr_t)decision & 7) == 0) && (((uintptr_t)slot & 15) == 0);
 
