@@ -750,15 +750,17 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		return rc;
 	// Staging chunks.  The H2D copies run back to back on the copy engine; a chunk's kernels and its D2H
 	// overlap the copy-in of the chunks behind it, so what the call pays beyond the PCIe time of its inputs
-	// is the LAST chunk's kernels and copy-out.  Chunks therefore shrink towards the end (half of what is left,
-	// at most c->chunk, at least 128K claims -- a chunk's kernels are latency-bound below that, and every chunk
+	// is the LAST chunk's kernels and copy-out.  Chunks therefore shrink towards the end (40 % of what is left,
+	// at most c->chunk, at least 64K claims -- a chunk's kernels are latency-bound below that, and every chunk
 	// costs two small copies): the exposed tail is a few tens of microseconds at any size.
 	std::vector<size_t> plan;
 	{
-		const size_t floor_chunk = 32 * (size_t)ETILE; // 128K claims: below this the per-chunk cost wins
+		size_t floor_chunk = 16 * (size_t)ETILE; // 64K claims: below this the per-chunk cost wins
+		if (floor_chunk > c->chunk)
+			floor_chunk = c->chunk; // (a caller-set staging chunk smaller than that: CB_CHUNK)
 		size_t left = n;
 		while (left > 0) {
-			size_t m = ((left / 2) + ETILE - 1) / ETILE * ETILE;
+			size_t m = ((left * 2 / 5) + ETILE - 1) / ETILE * ETILE;
 			if (m > c->chunk)
 				m = c->chunk;
 			if (m < floor_chunk)
