@@ -153,7 +153,7 @@ def fakes(monkeypatch):
                                                                           **({"all_overloaded_from": 4096} if k == "c5" else {})))
                                              for k, v in bench.WORKLOADS.items()})
     monkeypatch.setattr(bench, "bind_to_gpu_numa", lambda i: 4)
-    monkeypatch.setattr(bench, "ClockSampler", lambda i: types.SimpleNamespace(start=lambda: None, stop=lambda: {"sm_mhz": 1}))
+    monkeypatch.setattr(bench, "ClockSampler", lambda i, n=1: types.SimpleNamespace(start=lambda: None, stop=lambda: {"sm_mhz": 1}))
     monkeypatch.setattr(bench, "pcie_rates", lambda dev, a, b: {"h2d_gbs": 50.0, "d2h_gbs": 50.0,
                                                                    "duplex_gbs": {"h2d": 45.0, "d2h": 20.0}})
     monkeypatch.setattr(bench, "stress_leg", lambda local, dev, stream: {"value": 1.0, "bit_exact_vs_oracle": True})
