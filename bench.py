@@ -856,7 +856,7 @@ def run_cuda(args, wl, extra=True):
             "l2": "inputs larger than L2: %d consecutive batches of one trace resident in HBM (%.0f MB), each read once"
                   % (W + K, 16.0 * w["n"] * (W + K) / 1e6),
             "state": "ControlledDelay state chained on device across steps",
-            "pipeline": "up to 5 batches in flight, one lane (stream) each; the scan is launched at low priority, "
+            "pipeline": "up to 8 batches in flight, one lane (stream) each; the scan is launched at low priority, "
                         "resolve/emit at high; commits ordered by a device-side chain word",
             "global_counts": "per batch, device-side, over peer-memory boards (cb_peers_*)" if world > 1 else None,
             "timed_region": "barrier + synchronize, the last 2 warm-up steps (device-ordered, so the timed steps start on a busy GPU), "

@@ -116,7 +116,7 @@ int cb_abi_version(void);
  * after the work already queued on the caller's stream; its outputs are complete after
  * cb_join() (stream-ordered) or cb_synchronize()/cb_batch_stats_get() (host-blocking). */
 int cb_set_stream(cb_ctx *ctx, void *cuda_stream);
-int cb_set_pipeline_depth(cb_ctx *ctx, int depth); /* 1 = strictly in order on one stream; default 5 */
+int cb_set_pipeline_depth(cb_ctx *ctx, int depth); /* 1 = strictly in order on one stream; default 8, at most 12 */
 int cb_join(cb_ctx *ctx);        /* the caller's stream waits for every batch enqueued so far */
 int cb_synchronize(cb_ctx *ctx); /* the host waits for every batch enqueued so far */
 /* pinned host memory for the *_batch host-buffer calls */

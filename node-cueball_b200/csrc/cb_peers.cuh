@@ -23,8 +23,9 @@ constexpr int PB_SLOTS = 64; // batches a rank may run ahead of the slowest read
 // kernel's last CTA or from a kernel of its own; with system-scope fences or without any) grew the 58-us
 // step to 72-82 us, while the peer mapping alone cost nothing.  The only remote stores left are the
 // flow-control acks, one per rank every PB_ACK_EVERY steps.
-// A record is three self-tagged 16-byte words {tag, value}, each written and read by ONE 128-bit access,
-// so a word whose tag reads step+1 carries that step's value: no payload-then-flag ordering, no fences.
+// A rank's record of a batch is ONE self-tagged 16-byte word {step+1 : 32 | drops : 32, admits : 32 | n : 32}
+// (a batch has fewer than 2^32 claims), written and read by ONE 128-bit access, so a word whose tag reads
+// step+1 carries that step's counts: no payload-then-flag ordering, no fences, one remote load per rank per step.
 struct alignas(16) PeerWord {
 	unsigned long long tag; // step + 1
 	unsigned long long v;
@@ -35,7 +36,7 @@ struct alignas(64) PeerRec {
 };
 constexpr int PB_ACK_EVERY = 16; // a reader tells the writers how far it has read once per this many steps
 struct PeerBoard {
-	PeerRec own[PB_SLOTS];           // own[s % PB_SLOTS]: THIS rank's counts of its batch s (stored locally, read by everyone)
+	PeerWord own[PB_SLOTS];          // own[s % PB_SLOTS]: THIS rank's counts of its batch s (stored locally, read by everyone)
 	PeerRec glob[PB_SLOTS];          // glob[s % PB_SLOTS]: running global totals after step s (this rank's finaliser)
 	unsigned long long ack[PB_MAXR]; // ack[r]: steps rank r has read from this board (stored by rank r, rarely)
 	unsigned long long gdone;        // steps this rank has finalised
@@ -74,20 +75,16 @@ __device__ __forceinline__ void peer_finalise(const PeerLink &pl, bool flush_ack
 	__threadfence();
 	unsigned long long g = b->gdone;
 	while (true) {
-		PeerWord w[PB_MAXR][3];
-		for (int r = 0; r < pl.R; r++) {
-			const PeerRec *q = &pl.peers[r]->own[g % PB_SLOTS];
-			w[r][0] = ld_word(&q->drops);
-			w[r][1] = ld_word(&q->admits);
-			w[r][2] = ld_word(&q->n);
-		}
+		PeerWord w[PB_MAXR];
+		for (int r = 0; r < pl.R; r++)
+			w[r] = ld_word(&pl.peers[r]->own[g % PB_SLOTS]);
 		unsigned long long d = 0, a = 0, n = 0;
 		bool all = true;
 		for (int r = 0; r < pl.R; r++) {
-			all = all && w[r][0].tag == g + 1 && w[r][1].tag == g + 1 && w[r][2].tag == g + 1;
-			d += w[r][0].v;
-			a += w[r][1].v;
-			n += w[r][2].v;
+			all = all && (unsigned int)(w[r].tag >> 32) == (unsigned int)(g + 1);
+			d += w[r].tag & 0xffffffffull;
+			a += w[r].v >> 32;
+			n += w[r].v & 0xffffffffull;
 		}
 		if (!all)
 			break;
@@ -128,10 +125,8 @@ __device__ __forceinline__ void peer_post(const PeerLink &pl, const BatchCtl *bc
 			}
 		}
 	}
-	PeerRec *d = &pl.mine->own[s % PB_SLOTS];
-	st_word(&d->drops, s + 1, bc->lcounts[0]);
-	st_word(&d->admits, s + 1, bc->lcounts[1]);
-	st_word(&d->n, s + 1, bc->lcounts[2]);
+	st_word(&pl.mine->own[s % PB_SLOTS], ((s + 1) << 32) | (bc->lcounts[0] & 0xffffffffull),
+	    (bc->lcounts[1] << 32) | (bc->lcounts[2] & 0xffffffffull));
 	if (!(pl.dbg & 4u))
 		peer_finalise(pl, false);
 }

@@ -66,8 +66,12 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0;
 
-constexpr int CB_LANES = 8;                   // most batches in flight (lanes)
-constexpr int CB_DEFAULT_DEPTH = 5;           // lanes used unless CB_PIPELINE_DEPTH / cb_set_pipeline_depth says otherwise
+constexpr int CB_LANES = 12;                  // most batches in flight (lanes)
+// Lanes used unless CB_PIPELINE_DEPTH / cb_set_pipeline_depth says otherwise.  A batch's emit kernel only gets
+// the SM slots retiring scan CTAs of later batches free, so a batch stays in flight for several steps: with 5
+// lanes the step was lane-bound at every size (C3: 59.4 us, 63.3 on two GPUs with count boards; 8 lanes: 56.6 / 56.0;
+// C2: 11.6 -> 9.1 us).
+constexpr int CB_DEFAULT_DEPTH = 8;
 constexpr int NBUF = 3;                       // staging buffers of the host-buffer pipeline
 constexpr size_t DEFAULT_CHUNK = 4u << 20;    // claims per pipeline chunk
 
@@ -119,7 +123,6 @@ struct cb_ctx {
 	uint64_t launches = 0;
 	// batch pipeline
 	int depth = CB_DEFAULT_DEPTH;
-	bool depth_auto = true;            // small batches (latency-bound) use every lane unless the host chose a depth
 	Lane lane[CB_LANES];
 	unsigned long long seq = 0;        // batches enqueued so far
 	ChainMem *d_chain = nullptr;           // the chain word; in ring mode this rank's mailbox
@@ -396,11 +399,10 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 		return CB_OK;
 	if (n >= (1ull << 39))
 		return fail(c, CB_EINVAL, "batch too large");
+	if (c->peers_n > 0 && n >= (1ull << 32))
+		return fail(c, CB_EINVAL, "count boards are connected: a batch must have fewer than 2^32 claims");
 	const size_t tiles = (n + TILE - 1) / TILE;      // scan / prepare tiles
-	// A batch of up to 2M claims is bound by the latency of its three dependent kernels (~40 us), not by
-	// bandwidth: more batches in flight is the only lever (measured at 1M claims: 11.6 us per step with 5
-	// lanes, 9.0 with 8).
-	const int depth = (c->depth_auto && c->depth > 1 && tiles <= c->graph_max_tiles) ? CB_LANES : c->depth;
+	const int depth = c->depth;
 	const bool piped = (depth > 1) && !c->prof;
 	const int li = piped ? (int)(c->seq % (unsigned long long)depth) : 0;
 	Lane &L = c->lane[li];
@@ -934,10 +936,8 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	if (ck && atoll(ck) >= ETILE)
 		c->chunk = ((size_t)atoll(ck) + ETILE - 1) / ETILE * ETILE;
 	const char *dp = getenv("CB_PIPELINE_DEPTH");
-	if (dp && atoi(dp) >= 1 && atoi(dp) <= CB_LANES) {
+	if (dp && atoi(dp) >= 1 && atoi(dp) <= CB_LANES)
 		c->depth = atoi(dp);
-		c->depth_auto = false;
-	}
 #define CU0(call)                                                                          \
 	do {                                                                                   \
 		cudaError_t e_ = (call);                                                           \
@@ -1111,7 +1111,6 @@ extern "C" int cb_set_pipeline_depth(cb_ctx *c, int depth) {
 	if (rc)
 		return rc;
 	c->depth = depth;
-	c->depth_auto = false;
 	return CB_OK;
 }
 

@@ -19,7 +19,7 @@ def cb():
     return cueball_b200
 
 
-@pytest.mark.parametrize("depth", [1, 3, 5, 8])
+@pytest.mark.parametrize("depth", [1, 3, 8, 12])
 @pytest.mark.parametrize("with_flags", [False, True], ids=["noflags", "flags"])
 def test_fchain_streams_of_small_batches(cb, depth, with_flags):
     import torch
