@@ -147,6 +147,7 @@ struct cb_ctx {
 	void *peer_ipc[PB_MAXR] = {};          // boards opened from IPC handles (to be closed)
 	int peers_n = 0, peers_rank = 0;
 	unsigned int peers_dbg = 0;            // CB_PEERS_DEBUG (measurement only)
+	unsigned long long peer_timeout_ns = 30000000000ull; // how long a kernel waits for another rank (CB_PEER_TIMEOUT_MS)
 	unsigned long long peer_step = 0;      // batches posted since cb_peers_connect
 	unsigned long long *d_peer_out = nullptr;
 	int ring_n = 0, ring_rank = 0;
@@ -334,7 +335,7 @@ PeerLink peer_link(const cb_ctx *c, unsigned long long step) {
 	pl.R = c->peers_n;
 	pl.me = c->peers_rank;
 	pl.step = step;
-	pl.timeout_ns = 30000000000ull; // the other ranks are other processes: allow for start-up skew
+	pl.timeout_ns = c->peer_timeout_ns; // the other ranks are other processes: allow for start-up skew
 	pl.dbg = c->peers_dbg;
 	if (c->peers_dbg & 1u) // measurement: boards connected, nothing posted
 		pl.mine = nullptr;
@@ -457,7 +458,7 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 			ln.in_state = &c->d_chain->st;
 			ln.post_word = &c->ring_next->seq;
 			ln.post_state = &c->ring_next->st;
-			ln.timeout_ns = 30000000000ull; // the other ranks are other processes: allow for start-up skew
+			ln.timeout_ns = c->peer_timeout_ns; // the other ranks are other processes: allow for start-up skew
 		} else {
 			ln.wait_val = c->chain_seq;
 			ln.in_state = nullptr;
@@ -964,6 +965,8 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
 	CU0(cudaMemset(c->g, 0, sizeof(DevState)));
+	if (getenv("CB_PEER_TIMEOUT_MS") && atoll(getenv("CB_PEER_TIMEOUT_MS")) > 0)
+		c->peer_timeout_ns = (unsigned long long)atoll(getenv("CB_PEER_TIMEOUT_MS")) * 1000000ull;
 	if (getenv("CB_PEERS_DEBUG"))
 		c->peers_dbg = (unsigned int)atoi(getenv("CB_PEERS_DEBUG"));
 	if (getenv("CB_GRAPH")) // measurement override of the launch mode: 0 = never a graph, 1 = always

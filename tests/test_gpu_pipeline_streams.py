@@ -216,3 +216,33 @@ def test_global_counts_over_peer_boards(cb, R, steps):
     for c in ctxs:
         c.peers_connect(0, 0)
         c.close()
+
+
+def test_a_stalled_rank_times_out_instead_of_hanging(cb, monkeypatch):
+    """One queue over a ring of two contexts in which rank 0 never submits its segment: rank 1's commit waits on
+    its mailbox, gives up after the hand-over timeout (CB_PEER_TIMEOUT_MS; 30 s by default) and the next stats
+    read reports the broken chain (CB_ESTATE) instead of hanging the device."""
+    import time
+    import torch
+    monkeypatch.setenv("CB_PEER_TIMEOUT_MS", "200")
+    tgt, m = 5, 50_000
+    start, now = tracegen.gen_trace(m, seed=77, de=1_000, unit=1 << 12)
+    dev = torch.device("cuda:0")
+    ts, tn = torch.from_numpy(start).to(dev), torch.from_numpy(now).to(dev)
+    dec = torch.empty(m, dtype=torch.uint8, device=dev)
+    ctxs = []
+    for r in range(2):
+        c = cb.Context(0)
+        c.codel_init(tgt)
+        ctxs.append(c)
+    boxes = [c.ring_mailbox() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.ring_connect(2, r, next_ptr=boxes[(r + 1) % 2][1])
+    t0 = time.time()
+    ctxs[1].admit_batch_ptr(ts.data_ptr(), tn.data_ptr(), None, m, dec.data_ptr(), None, None)  # rank 0 never runs
+    with pytest.raises(cb.CueballError) as e:
+        ctxs[1].stats()
+    assert "chain broken" in str(e.value) and time.time() - t0 < 10.0
+    for c in ctxs:
+        c.ring_connect(0, 0)
+        c.close()
