@@ -226,6 +226,20 @@ int fail(cb_ctx *c, int code, const char *fmt, ...) {
 			return fail((c), CB_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while (0)
 
+// a device allocation that lives as long as the call that made it (freed on every return path)
+struct ScopedDev {
+	void *p = nullptr;
+	~ScopedDev() {
+		if (p)
+			cudaFree(p);
+	}
+	cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+	ScopedDev() = default;
+	ScopedDev(const ScopedDev &) = delete;
+	ScopedDev &operator=(const ScopedDev &) = delete;
+};
+
 template <typename T> int dev_alloc(cb_ctx *c, T **p, size_t count) {
 	if (*p) {
 		cudaFree(*p);
@@ -1476,17 +1490,19 @@ extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *
 		total_have += have[k];
 	}
 	size_t nb = (size_t)(B > 0 ? B : 1), na = (size_t)max + 1, nr = (size_t)total_have + 1;
-	int32_t *d_have = nullptr, *d_want = nullptr, *d_add = nullptr, *d_rk = nullptr, *d_ro = nullptr, *d_scr = nullptr;
-	uint8_t *d_dead = nullptr;
-	int *d_cnt = nullptr;
-	CU(c, cudaMalloc((void **)&d_have, nb * 4));
-	CU(c, cudaMalloc((void **)&d_want, nb * 4));
-	CU(c, cudaMalloc((void **)&d_dead, nb));
-	CU(c, cudaMalloc((void **)&d_add, na * 4));
-	CU(c, cudaMalloc((void **)&d_rk, nr * 4));
-	CU(c, cudaMalloc((void **)&d_ro, nr * 4));
-	CU(c, cudaMalloc((void **)&d_cnt, 8));
-	CU(c, cudaMalloc((void **)&d_scr, 2 * (nb + 1) * 4));
+	ScopedDev b_have, b_want, b_add, b_rk, b_ro, b_dead, b_cnt, b_scr;
+	CU(c, b_have.alloc(nb * 4));
+	CU(c, b_want.alloc(nb * 4));
+	CU(c, b_dead.alloc(nb));
+	CU(c, b_add.alloc(na * 4));
+	CU(c, b_rk.alloc(nr * 4));
+	CU(c, b_ro.alloc(nr * 4));
+	CU(c, b_cnt.alloc(8));
+	CU(c, b_scr.alloc(2 * (nb + 1) * 4));
+	int32_t *d_have = b_have.as<int32_t>(), *d_want = b_want.as<int32_t>(), *d_add = b_add.as<int32_t>();
+	int32_t *d_rk = b_rk.as<int32_t>(), *d_ro = b_ro.as<int32_t>(), *d_scr = b_scr.as<int32_t>();
+	uint8_t *d_dead = b_dead.as<uint8_t>();
+	int *d_cnt = b_cnt.as<int>();
 	cudaStream_t s = c->stream;
 	if (B > 0) {
 		CU(c, cudaMemcpyAsync(d_have, have, nb * 4, cudaMemcpyHostToDevice, s));
@@ -1511,14 +1527,6 @@ extern "C" int cb_plan_rebalance(cb_ctx *c, const int32_t *have, const uint8_t *
 		*n_add = cnt[0];
 	if (n_rm)
 		*n_rm = cnt[1];
-	cudaFree(d_have);
-	cudaFree(d_want);
-	cudaFree(d_dead);
-	cudaFree(d_add);
-	cudaFree(d_rk);
-	cudaFree(d_ro);
-	cudaFree(d_cnt);
-	cudaFree(d_scr);
 	return CB_OK;
 }
 
@@ -1826,23 +1834,19 @@ extern "C" int cb_srv_keys(cb_ctx *c, const char *const *names, const int32_t *p
 		blob += norm;
 	}
 	offs[n] = (unsigned int)blob.size();
-	unsigned char *d_blob = nullptr;
-	unsigned int *d_offs = nullptr;
-	char *d_keys = nullptr;
-	CU(c, cudaMalloc((void **)&d_blob, blob.size() + 16));
-	CU(c, cudaMalloc((void **)&d_offs, (n + 1) * sizeof(unsigned int)));
-	CU(c, cudaMalloc((void **)&d_keys, n * SRVKEY_LEN));
+	ScopedDev d_blob, d_offs, d_keys;
+	CU(c, d_blob.alloc(blob.size() + 16));
+	CU(c, d_offs.alloc((n + 1) * sizeof(unsigned int)));
+	CU(c, d_keys.alloc(n * SRVKEY_LEN));
 	cudaStream_t s = c->stream;
-	CU(c, cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
-	CU(c, cudaMemcpyAsync(d_offs, offs.data(), (n + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, s));
-	srv_key_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_blob, d_offs, (int)n, d_keys);
+	CU(c, cudaMemcpyAsync(d_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+	CU(c, cudaMemcpyAsync(d_offs.p, offs.data(), (n + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+	srv_key_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_blob.as<unsigned char>(), d_offs.as<unsigned int>(), (int)n,
+	    d_keys.as<char>());
 	c->launches++;
 	CU(c, cudaGetLastError());
-	CU(c, cudaMemcpyAsync(keys_out, d_keys, n * SRVKEY_LEN, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaMemcpyAsync(keys_out, d_keys.p, n * SRVKEY_LEN, cudaMemcpyDeviceToHost, s));
 	CU(c, cudaStreamSynchronize(s));
-	cudaFree(d_blob);
-	cudaFree(d_offs);
-	cudaFree(d_keys);
 	return CB_OK;
 }
 
