@@ -195,6 +195,11 @@ int cb_reshuffle(cb_ctx *ctx, double u);
 int cb_backends_get(cb_ctx *ctx, int32_t *n_keys, int32_t *keys_out, int32_t *n_slots,
     int32_t *slot_backend_out);
 
+/* utils.shuffle(array), lib/utils.js:207-217 (Fisher-Yates from the top; exported by the reference, no caller
+ * in lib/): arr[n] is permuted in place, us[t] in [0,1) stands in for the t-th Math.random().  One kernel,
+ * every output position traced independently (cb_topology.cuh). */
+int cb_shuffle(cb_ctx *ctx, int32_t *arr, size_t n, const double *us);
+
 /*
  * utils.planRebalance(connections, dead, target, max, singleton): lib/utils.js:239-393,
  * callers lib/pool.js:590 and lib/set.js:408.  Keys are positions 0..B-1 in the caller's

@@ -23,7 +23,7 @@ SYMBOLS = [
     "cb_host_alloc", "cb_host_free", "cb_codel_init", "cb_codel_get_state", "cb_codel_set_state",
     "cb_codel_empty", "cb_codel_max_idle", "cb_admit_batch", "cb_admit_batch_ms", "cb_admit_batch_dev",
     "cb_admit_batch_ms_dev", "cb_batch_stats_get", "cb_codel_overloaded", "cb_codel_overloaded_ms", "cb_backends_set",
-    "cb_backend_added", "cb_backend_removed", "cb_reshuffle", "cb_backends_get", "cb_plan_rebalance",
+    "cb_backend_added", "cb_backend_removed", "cb_reshuffle", "cb_backends_get", "cb_plan_rebalance", "cb_shuffle",
     "cb_comm_unique_id", "cb_comm_init", "cb_allreduce_counts", "cb_profile_enable", "cb_profile_get",
     "cb_launch_count", "cb_debug_timestamps", "cb_debug_lane_timestamps",
     "cb_srv_keys", "cb_resolver_process",
@@ -121,6 +121,7 @@ def lib():
     L.cb_backend_added.argtypes = [vp, i32, vp, dbl]
     L.cb_backend_removed.argtypes = [vp, i32]
     L.cb_reshuffle.argtypes = [vp, dbl]
+    L.cb_shuffle.argtypes = [vp, vp, sz, vp]
     L.cb_backends_get.argtypes = [vp, C.POINTER(i32), vp, C.POINTER(i32), vp]
     L.cb_plan_rebalance.argtypes = [vp, vp, vp, i32, i32, i32, C.c_int, vp, vp, C.POINTER(i32), vp, vp,
                                     C.POINTER(i32)]

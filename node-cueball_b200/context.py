@@ -175,6 +175,15 @@ class Context(object):
     def reshuffle(self, u):
         self._ck(self._L.cb_reshuffle(self._h, float(u)))
 
+    def shuffle(self, arr, us):
+        """utils.shuffle (lib/utils.js:207-217) of an int32 array with injected draws; returns the permuted copy."""
+        a = np.array(arr, dtype=np.int32)
+        us = np.ascontiguousarray(us, dtype=np.float64)
+        if us.shape[0] < a.shape[0]:
+            raise ValueError("one draw per element is required")
+        self._ck(self._L.cb_shuffle(self._h, _np_ptr(a), a.shape[0], _np_ptr(us)))
+        return a
+
     def backends_get(self):
         nk, ns = C.c_int32(), C.c_int32()
         self._ck(self._L.cb_backends_get(self._h, C.byref(nk), None, C.byref(ns), None))

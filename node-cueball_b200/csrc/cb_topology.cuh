@@ -374,4 +374,40 @@ __global__ void weighted_want_kernel(const int32_t *keys, int B, const int32_t *
 	*n_add = na;
 }
 
+// ----------------------------------------------------------------------------- utils.shuffle
+// lib/utils.js:207-217: i = n; while (i > 0) { j = floor(random() * i); --i; swap(a[i], a[j]); } with the
+// draws injected (us[t] is the t-th Math.random()).  The loop is a chain of n transpositions, but its result
+// has a per-position form: step i (the one that swaps a[i] with a[j_i], j_i <= i) is the LAST one that touches
+// position i, so out[i] is what sat at j_i just before it.  Walking the earlier steps (i+1, i+2, ... n-1)
+// backwards in time, the element under the finger moves only when a step's j equals the finger's position
+// (then it came from that step's i).  Every output position follows its own finger: n independent walks over
+// the shared list of j's, which the CTA stages through shared memory tile by tile -- O(n^2 / threads), no
+// serial chain.  j_i = floor(us[n-1-i] * (i+1)).
+constexpr int SHUF_TILE = 2048;
+__device__ __forceinline__ int shuffle_j(const double *us, int n, int i) {
+	return (int)floor(__dmul_rn(us[n - 1 - i], (double)(i + 1)));
+}
+__global__ void __launch_bounds__(TOPO_TPB) shuffle_kernel(const int32_t *in, int32_t *out, const double *us, int n) {
+	__shared__ int32_t sj[SHUF_TILE];
+	for (int p0 = (int)blockIdx.x * TOPO_TPB; p0 < n; p0 += (int)gridDim.x * TOPO_TPB) { // uniform in the CTA
+		const int p = p0 + (int)threadIdx.x;
+		int pos = p < n ? shuffle_j(us, n, p) : -1;
+		for (int base = p0 + 1; base < n; base += SHUF_TILE) {
+			const int lim = n - base < SHUF_TILE ? n - base : SHUF_TILE;
+			__syncthreads();
+			for (int k = (int)threadIdx.x; k < lim; k += TOPO_TPB)
+				sj[k] = shuffle_j(us, n, base + k);
+			__syncthreads();
+			if (p < n) {
+				int k = p + 1 - base;
+				for (k = k < 0 ? 0 : k; k < lim; k++)
+					if (sj[k] == pos)
+						pos = base + k;
+			}
+		}
+		if (p < n)
+			out[p] = in[pos];
+	}
+}
+
 } // namespace cb

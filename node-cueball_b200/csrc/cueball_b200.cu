@@ -166,6 +166,10 @@ struct cb_ctx {
 	double *d_dbl = nullptr;
 	// host-buffer pipeline
 	size_t chunk = DEFAULT_CHUNK, stage_cap = 0;
+	size_t chunk_floor = 16 * (size_t)ETILE; // host-buffer path: smallest staging chunk (CB_CHUNK_FLOOR)
+	int chunk_pct = 40;                      // ... and the share of the remainder a chunk takes (CB_CHUNK_PCT)
+	cudaStream_t s_in2 = nullptr;            // CB_H2D_SPLIT=1: the `now` array travels on a second copy stream
+	cudaEvent_t ev_in2 = nullptr;
 	Staging st[NBUF];
 	// pinned landing zone of fetch_stats: {chain word, error count}, DevState, BatchCtl in one synchronisation
 	struct StatsStage {
@@ -660,12 +664,9 @@ int enqueue_batch(cb_ctx *c, const void *d_start, const void *d_now, const uint8
 	return CB_OK;
 }
 
-int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool drained = false) {
-	// `drained`: the caller has already waited for every batch (host_batch: its last copy-out has landed)
-	int rc = drained ? CB_OK : drain(c);
-	if (rc)
-		return rc;
-	// three small device-to-host copies into pinned memory, one wait (a blocking cudaMemcpy each costs ~10 us)
+// three small device-to-host copies into pinned memory behind whatever s_out already holds (a blocking
+// cudaMemcpy each costs ~10 us); valid once s_out has been waited for
+int enqueue_stats_copies(cb_ctx *c) {
 	if (!c->h_stats)
 		CU(c, cudaMallocHost((void **)&c->h_stats, sizeof(*c->h_stats)));
 	memset(&c->h_stats->ctl, 0, sizeof(BatchCtl));
@@ -673,7 +674,20 @@ int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool drained = false) {
 	CU(c, cudaMemcpyAsync(&c->h_stats->st, c->g, sizeof(DevState), cudaMemcpyDeviceToHost, c->s_out));
 	if (c->last_lane >= 0)
 		CU(c, cudaMemcpyAsync(&c->h_stats->ctl, c->lane[c->last_lane].ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, c->s_out));
-	CU(c, cudaStreamSynchronize(c->s_out));
+	return CB_OK;
+}
+
+int fetch_stats(cb_ctx *c, cb_batch_stats *out, bool copied = false) {
+	// `copied`: the caller (host_batch) queued the copies behind its last copy-out and has waited for s_out
+	if (!copied) {
+		int rc = drain(c);
+		if (rc)
+			return rc;
+		rc = enqueue_stats_copies(c);
+		if (rc)
+			return rc;
+		CU(c, cudaStreamSynchronize(c->s_out));
+	}
 	const unsigned long long *chain = c->h_stats->chain;
 	const DevState &h = c->h_stats->st;
 	const BatchCtl &b = c->h_stats->ctl;
@@ -772,12 +786,12 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 	// costs two small copies): the exposed tail is a few tens of microseconds at any size.
 	std::vector<size_t> plan;
 	{
-		size_t floor_chunk = 16 * (size_t)ETILE; // 64K claims: below this the per-chunk cost wins
+		size_t floor_chunk = c->chunk_floor; // 64K claims: below this the per-chunk cost wins
 		if (floor_chunk > c->chunk)
 			floor_chunk = c->chunk; // (a caller-set staging chunk smaller than that: CB_CHUNK)
 		size_t left = n;
 		while (left > 0) {
-			size_t m = ((left * 2 / 5) + ETILE - 1) / ETILE * ETILE;
+			size_t m = ((left / 100 * c->chunk_pct) + ETILE - 1) / ETILE * ETILE;
 			if (m > c->chunk)
 				m = c->chunk;
 			if (m < floor_chunk)
@@ -790,16 +804,37 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 	}
 	const size_t nchunks = plan.size();
 	size_t lo = 0;
+	bool all_waited = (decision || slot || backend) && n > 0;
+	std::vector<cudaEvent_t> dbg_ev; // CB_DEBUG_E2E: when each chunk's inputs and outputs landed (device clock)
+	cudaEvent_t dbg_ev0 = nullptr;
+	if (dbg_t) {
+		CU(c, cudaEventCreate(&dbg_ev0));
+		CU(c, cudaEventRecord(dbg_ev0, c->s_in));
+	}
 	for (size_t ci = 0; ci < nchunks; ci++) {
 		Staging &s = c->st[ci % NBUF];
 		const size_t m = plan[ci];
 		if (ci >= NBUF)
 			CU(c, cudaStreamWaitEvent(c->s_in, s.out_done, 0));
 		CU(c, cudaMemcpyAsync(s.start, (const char *)start + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
-		CU(c, cudaMemcpyAsync(s.now, (const char *)now + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
+		if (c->s_in2) {
+			if (ci >= NBUF)
+				CU(c, cudaStreamWaitEvent(c->s_in2, s.out_done, 0));
+			CU(c, cudaMemcpyAsync(s.now, (const char *)now + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in2));
+			CU(c, cudaEventRecord(c->ev_in2, c->s_in2));
+			CU(c, cudaStreamWaitEvent(c->s_in, c->ev_in2, 0));
+		} else {
+			CU(c, cudaMemcpyAsync(s.now, (const char *)now + lo * 8, m * 8, cudaMemcpyHostToDevice, c->s_in));
+		}
 		if (flags)
 			CU(c, cudaMemcpyAsync(s.flags, flags + lo, m, cudaMemcpyHostToDevice, c->s_in));
 		CU(c, cudaEventRecord(s.in_done, c->s_in));
+		if (dbg_t) {
+			cudaEvent_t e;
+			CU(c, cudaEventCreate(&e));
+			CU(c, cudaEventRecord(e, c->s_in));
+			dbg_ev.push_back(e);
+		}
 		cudaEvent_t done = nullptr;
 		rc = enqueue_batch<NS>(c, s.start, s.now, flags ? s.flags : nullptr, m, decision ? s.decision : nullptr,
 		    slot ? s.slot : nullptr, backend ? s.backend : nullptr, s.in_done, &done);
@@ -807,6 +842,8 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 			return rc;
 		if (done)
 			CU(c, cudaStreamWaitEvent(c->s_out, done, 0));
+		else
+			all_waited = false;
 		if (decision)
 			CU(c, cudaMemcpyAsync(decision + lo, s.decision, m, cudaMemcpyDeviceToHost, c->s_out));
 		if (slot)
@@ -814,16 +851,37 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 		if (backend)
 			CU(c, cudaMemcpyAsync(backend + lo, s.backend, m * 4, cudaMemcpyDeviceToHost, c->s_out));
 		CU(c, cudaEventRecord(s.out_done, c->s_out));
+		if (dbg_t) {
+			cudaEvent_t e;
+			CU(c, cudaEventCreate(&e));
+			CU(c, cudaEventRecord(e, c->s_out));
+			dbg_ev.push_back(e);
+		}
 		lo += m;
 	}
+	// with outputs copied out, s_out runs behind every kernel of the call: the statistics ride the same wait
+	const bool stats_inline = stats && all_waited;
+	if (stats_inline && (rc = enqueue_stats_copies(c)))
+		return rc;
 	const double T2 = dbg_t ? tnow() : 0;
 	CU(c, cudaStreamSynchronize(c->s_out));
 	const double T3 = dbg_t ? tnow() : 0;
-	if (dbg_t)
+	if (dbg_t) {
 		fprintf(stderr, "[cb e2e] n=%zu chunks=%zu  entry sync+state %.0f us | enqueue %.0f us | wait %.0f us\n", n, nchunks,
 		    T1 - T0, T2 - T1, T3 - T2);
+		for (size_t k = 0; k + 1 < dbg_ev.size(); k += 2) {
+			float a = 0, b = 0;
+			cudaEventElapsedTime(&a, dbg_ev0, dbg_ev[k]);
+			cudaEventElapsedTime(&b, dbg_ev0, dbg_ev[k + 1]);
+			fprintf(stderr, "[cb e2e]   chunk %zu (%zu claims): in by %.0f us, out by %.0f us\n", k / 2, plan[k / 2], a * 1e3,
+			    b * 1e3);
+			cudaEventDestroy(dbg_ev[k]);
+			cudaEventDestroy(dbg_ev[k + 1]);
+		}
+		cudaEventDestroy(dbg_ev0);
+	}
 	if (stats) {
-		rc = fetch_stats(c, stats, decision || slot || backend); // outputs copied out => every kernel has finished
+		rc = fetch_stats(c, stats, stats_inline);
 		if (rc)
 			return rc;
 		// totals of the whole call, not of its last chunk
@@ -947,6 +1005,12 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 		c->scan_ctas = atoi(getenv("CB_SCAN_CTAS"));
 	if (getenv("CB_SCAN_TPW") && atoi(getenv("CB_SCAN_TPW")) > 0)
 		c->scan_tpw = atoi(getenv("CB_SCAN_TPW"));
+	if (const char *e = getenv("CB_CHUNK_FLOOR"))
+		if (atoll(e) >= (long long)ETILE)
+			c->chunk_floor = (size_t)atoll(e) / ETILE * ETILE;
+	if (const char *e = getenv("CB_CHUNK_PCT"))
+		if (atoi(e) >= 5 && atoi(e) <= 100)
+			c->chunk_pct = atoi(e);
 	const char *ck = getenv("CB_CHUNK");
 	if (ck && atoll(ck) >= ETILE)
 		c->chunk = ((size_t)atoll(ck) + ETILE - 1) / ETILE * ETILE;
@@ -975,6 +1039,11 @@ extern "C" int cb_create(cb_ctx **out, int device) {
 	}
 	CU0(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
 	CU0(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+	if (const char *e = getenv("CB_H2D_SPLIT"))
+		if (atoi(e) == 1) {
+			CU0(cudaStreamCreateWithFlags(&c->s_in2, cudaStreamNonBlocking));
+			CU0(cudaEventCreateWithFlags(&c->ev_in2, cudaEventDisableTiming));
+		}
 	CU0(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
 	c->stream = c->own_stream;
 	CU0(cudaMalloc((void **)&c->g, sizeof(DevState)));
@@ -1038,7 +1107,7 @@ extern "C" void cb_destroy(cb_ctx *c) {
 	if (!c)
 		return;
 	cudaSetDevice(c->device);
-	cudaStream_t all[] = {c->st_coll, c->s_in, c->s_out, c->own_stream};
+	cudaStream_t all[] = {c->st_coll, c->s_in, c->s_in2, c->s_out, c->own_stream};
 	for (cudaStream_t s : all)
 		if (s)
 			cudaStreamSynchronize(s);
@@ -1102,6 +1171,8 @@ extern "C" void cb_destroy(cb_ctx *c) {
 			cudaEventDestroy(c->pe[k]);
 	if (c->ev_user)
 		cudaEventDestroy(c->ev_user);
+	if (c->ev_in2)
+		cudaEventDestroy(c->ev_in2);
 	for (cudaStream_t s : all)
 		if (s)
 			cudaStreamDestroy(s);
@@ -1453,6 +1524,35 @@ extern "C" int cb_reshuffle(cb_ctx *c, double u) {
 	c->launches++;
 	CU(c, cudaGetLastError());
 	return rebuild_slots(c);
+}
+
+extern "C" int cb_shuffle(cb_ctx *c, int32_t *arr, size_t n, const double *us) {
+	DevGuard dev_guard_(c);
+	if (!c || (n && (!arr || !us)))
+		return c ? fail(c, CB_EINVAL, "bad arguments") : CB_EINVAL;
+	if (n >= (1ull << 31))
+		return fail(c, CB_EINVAL, "array too long");
+	for (size_t k = 0; k < n; k++)
+		if (!(us[k] >= 0.0 && us[k] < 1.0))
+			return fail(c, CB_EINVAL, "us[%zu] is not in [0,1)", k);
+	if (n < 2)
+		return CB_OK; // one transposition of an element with itself, or nothing
+	ScopedDev d_in, d_out, d_us;
+	CU(c, d_in.alloc(n * 4));
+	CU(c, d_out.alloc(n * 4));
+	CU(c, d_us.alloc(n * 8));
+	cudaStream_t s = c->stream;
+	CU(c, cudaMemcpyAsync(d_in.p, arr, n * 4, cudaMemcpyHostToDevice, s));
+	CU(c, cudaMemcpyAsync(d_us.p, us, n * 8, cudaMemcpyHostToDevice, s));
+	size_t ctas = (n + TOPO_TPB - 1) / TOPO_TPB;
+	if (ctas > (size_t)c->emit_grid / 2)
+		ctas = (size_t)c->emit_grid / 2; // two CTAs of 1024 threads per SM
+	shuffle_kernel<<<(unsigned)ctas, TOPO_TPB, 0, s>>>(d_in.as<int32_t>(), d_out.as<int32_t>(), d_us.as<double>(), (int)n);
+	c->launches++;
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(arr, d_out.p, n * 4, cudaMemcpyDeviceToHost, s));
+	CU(c, cudaStreamSynchronize(s));
+	return CB_OK;
 }
 
 extern "C" int cb_backends_get(cb_ctx *c, int32_t *n_keys, int32_t *keys_out, int32_t *n_slots,

@@ -43,6 +43,20 @@ def planRebalance(connections, dead, target, max, singleton=False, context=None)
     return {"add": [keys[i] for i in add], "remove": [connections[keys[k]][o] for k, o in rem]}
 
 
+def shuffle(array, draws=None, context=None):
+    """lib/utils.js:207-217: Fisher-Yates in place, returns the array.  `draws` (one float in [0,1) per
+    element, in the order the reference would call Math.random()) default to random.random(); the
+    permutation itself is computed by the CUDA library (cb_shuffle) on the element indices."""
+    import random
+    n = len(array)
+    if draws is None:
+        draws = [random.random() for _ in range(n)]
+    perm = (context or _ctx()).shuffle(list(range(n)), draws)
+    items = [array[int(i)] for i in perm]
+    array[:] = items
+    return array
+
+
 def assertClaimDelay(delay):
     """lib/utils.js:188-195"""
     if delay is None:

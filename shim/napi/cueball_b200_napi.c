@@ -22,6 +22,7 @@
  *   backendAdded(ctx, key, u) / backendRemoved(ctx, key) / reshuffle(ctx, u)
  *                                                          lib/pool.js:285-313, 501-519
  *   planRebalance(ctx, have: Int32Array, dead: Uint8Array, target, max, singleton)
+ *   shuffle(ctx, draws: Float64Array) -> Int32Array (the permutation of utils.shuffle)
  *              -> {want: Int32Array, add: Int32Array, rmKey: Int32Array, rmOrd: Int32Array}
  *                                                          lib/utils.js:239-393
  * Errors: CB_EINVAL -> throws (the reference throws AssertionError for programmer errors);
@@ -314,6 +315,28 @@ PlanRebalance(napi_env env, napi_callback_info info)
 	return rc == CB_OK ? out : throw_cb(env, ctx, rc);
 }
 
+/* shuffle(ctx, draws: Float64Array) -> Int32Array: the permutation utils.shuffle (lib/utils.js:207-217) applies
+ * to an array of draws.length elements when Math.random() returns draws[0], draws[1], ... */
+static napi_value
+Shuffle(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2, n = 0; napi_value argv[2]; bool ok;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 2) {
+		napi_throw_type_error(env, NULL, "shuffle(ctx, draws)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	const double *us = typed(env, argv[1], napi_float64_array, 0, false, "draws: Float64Array expected", &n, &ok);
+	if (!ok) return NULL;
+	int32_t *perm = calloc(n + 1, 4);
+	for (size_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+	int rc = cb_shuffle(ctx, perm, n, us);
+	napi_value out = rc == CB_OK ? i32array(env, perm, n) : NULL;
+	free(perm);
+	return rc == CB_OK ? out : throw_cb(env, ctx, rc);
+}
+
 static napi_value
 Init(napi_env env, napi_value exports)
 {
@@ -329,6 +352,7 @@ Init(napi_env env, napi_value exports)
 		{ "backendRemoved", NULL, BackendRemoved, NULL, NULL, NULL, napi_default, NULL },
 		{ "reshuffle", NULL, Reshuffle, NULL, NULL, NULL, napi_default, NULL },
 		{ "planRebalance", NULL, PlanRebalance, NULL, NULL, NULL, napi_default, NULL },
+		{ "shuffle", NULL, Shuffle, NULL, NULL, NULL, napi_default, NULL },
 	};
 	napi_define_properties(env, exports, sizeof (d) / sizeof (d[0]), d);
 	return exports;

@@ -37,6 +37,13 @@ void emu_plan_rebalance(const int32_t *have, const uint8_t *dead, int B, int tar
 	int32_t *scr = scratch.data();
 	one_cta(TOPO_TPB, [&] { plan_rebalance_kernel(have, dead, B, target, max, singleton, want, add, n_add, rm_key, rm_ord, n_rm, scr); });
 }
+void emu_shuffle(const int32_t *in, int32_t *out, const double *us, int n, int ctas) {
+	gridDim.x = (unsigned)ctas;
+	for (unsigned b = 0; b < (unsigned)ctas; b++) {
+		blockIdx.x = b;
+		emu::launch(TOPO_TPB, [&] { shuffle_kernel(in, out, us, n); });
+	}
+}
 void emu_slot_table(const int32_t *keys, const int32_t *add, const int32_t *n_add, int32_t *slot_backend, int cap,
     int *nslots_out) {
 	gridDim.x = 4;

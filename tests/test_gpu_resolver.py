@@ -67,3 +67,34 @@ def test_resolver_process_matches_state_process(cb):
             assert be == new[k] or cb.srvKey(be) == k
         old = new
     ctx.close()
+
+
+def test_utils_shuffle_kernel(cb):
+    """utils.shuffle (lib/utils.js:207-217) through cb_shuffle: the results recorded from
+    the reference engine (tests/golden/slots_golden.json), random arrays against the oracle's loop at sizes
+    round the CTA (1024) and staging-tile (2048) edges and beyond one wave of CTAs, and the reference-shaped
+    wrapper utils.shuffle on a list of objects."""
+    from cueball_b200 import tracegen
+    from cueball_b200 import utils as U
+    from oracle import oracle as O
+
+    ctx = cb.Context(0)
+    slots = util.load_golden("slots_golden.json")
+    for c in slots["shuffle"]:
+        us = tracegen.gen_insert_draws(c["n"], c["seed"])
+        assert ctx.shuffle(np.arange(c["n"]), us).tolist() == c["result"]
+    rng = np.random.RandomState(2024)
+    for n in (0, 1, 2, 3, 1023, 1024, 1025, 2048, 2049, 3073, 40_000, 400_000):
+        us = rng.rand(n)
+        if n > 4:
+            us[rng.randint(n)] = 0.0
+            us[rng.randint(n)] = np.nextafter(1.0, 0.0)
+        arr = rng.randint(-2**31, 2**31 - 1, size=n, dtype=np.int64).astype(np.int32)
+        assert np.array_equal(ctx.shuffle(arr, us), O.shuffle(arr, us)), n
+    names = ["b%d" % k for k in range(257)]
+    us = rng.rand(len(names))
+    want = [names[i] for i in O.shuffle(np.arange(len(names)), us)]
+    got = U.shuffle(list(names), draws=us.tolist(), context=ctx)
+    assert got == want
+    with pytest.raises(cb.CueballError):
+        ctx.shuffle(np.arange(4), [0.1, 0.2, 1.0, 0.3])

@@ -35,6 +35,7 @@ def load_emu():
     L.emu_pref_reshuffle.argtypes = [VP, VP, C.c_double]
     L.emu_plan_rebalance.argtypes = [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP, VP]
     L.emu_slot_table.argtypes = [VP, VP, VP, VP, C.c_int, VP]
+    L.emu_shuffle.argtypes = [VP, VP, VP, C.c_int, C.c_int]
     return L
 
 
@@ -113,3 +114,31 @@ def test_preference_list_and_slot_table_kernels(emu):
             taken = ref.pop()
             ref.insert(int(np.floor(u * (len(ref) + 1))), taken)
         assert n[0] == len(ref) and keys[:n[0]].tolist() == ref
+
+
+def shuffle_emulated(L, arr, us, ctas):
+    arr = np.ascontiguousarray(arr, np.int32)
+    us = np.ascontiguousarray(us, np.float64)
+    out = np.full(arr.shape[0], -7, np.int32)
+    L.emu_shuffle(arr.ctypes.data, out.ctypes.data, us.ctypes.data, arr.shape[0], ctas)
+    return out
+
+
+def test_shuffle_kernel_golden_and_random(emu):
+    """utils.shuffle (lib/utils.js:207-217): the per-position walk of shuffle_kernel against the results recorded
+    from the reference engine, then against the oracle's loop at sizes around the CTA width (64 here) and the
+    2048-entry staging tile, with one CTA and with several."""
+    slots = util.load_golden("slots_golden.json")
+    for c in slots["shuffle"]:
+        us = tracegen.gen_insert_draws(c["n"], c["seed"])
+        assert shuffle_emulated(emu, np.arange(c["n"]), us, 1).tolist() == c["result"]
+    rng = np.random.RandomState(77)
+    for n in (1, 2, 3, 63, 64, 65, 127, 300, 2047, 2048, 2049, 2113, 4500):
+        us = rng.rand(n)
+        if n > 4:
+            us[rng.randint(n)] = 0.0                      # j = 0
+            us[rng.randint(n)] = np.nextafter(1.0, 0.0)   # j = i (a transposition with itself)
+        arr = rng.randint(-1000, 1000, size=n).astype(np.int32)
+        want = O.shuffle(arr, us)
+        for ctas in (1, 3):
+            assert np.array_equal(shuffle_emulated(emu, arr, us, ctas), want), (n, ctas)
