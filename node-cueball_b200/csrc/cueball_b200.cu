@@ -166,7 +166,7 @@ struct cb_ctx {
 	double *d_dbl = nullptr;
 	// host-buffer pipeline
 	size_t chunk = DEFAULT_CHUNK, stage_cap = 0;
-	size_t chunk_floor = 16 * (size_t)ETILE; // host-buffer path: smallest staging chunk (CB_CHUNK_FLOOR)
+	size_t chunk_floor = 32 * (size_t)ETILE; // host-buffer path: smallest staging chunk (CB_CHUNK_FLOOR)
 	int chunk_pct = 40;                      // ... and the share of the remainder a chunk takes (CB_CHUNK_PCT)
 	cudaStream_t s_in2 = nullptr;            // CB_H2D_SPLIT=1: the `now` array travels on a second copy stream
 	cudaEvent_t ev_in2 = nullptr;
@@ -782,11 +782,12 @@ int host_batch(cb_ctx *c, const void *start, const void *now, const uint8_t *fla
 	// Staging chunks.  The H2D copies run back to back on the copy engine; a chunk's kernels and its D2H
 	// overlap the copy-in of the chunks behind it, so what the call pays beyond the PCIe time of its inputs
 	// is the LAST chunk's kernels and copy-out.  Chunks therefore shrink towards the end (40 % of what is left,
-	// at most c->chunk, at least 64K claims -- a chunk's kernels are latency-bound below that, and every chunk
-	// costs two small copies): the exposed tail is a few tens of microseconds at any size.
+	// at most c->chunk, at least 128K claims -- every chunk costs two copies whose fixed cost on the copy engine
+	// is ~10 us each, and a chunk's kernels are latency-bound below that): the exposed tail is ~50 us at any
+	// size (measured with CB_DEBUG_E2E=1: the last chunk's outputs land 45-50 us after its inputs).
 	std::vector<size_t> plan;
 	{
-		size_t floor_chunk = c->chunk_floor; // 64K claims: below this the per-chunk cost wins
+		size_t floor_chunk = c->chunk_floor; // 128K claims: below this the per-chunk cost wins
 		if (floor_chunk > c->chunk)
 			floor_chunk = c->chunk; // (a caller-set staging chunk smaller than that: CB_CHUNK)
 		size_t left = n;

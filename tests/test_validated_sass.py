@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(util.ROOT, "tools"))
 import sass_hashes  # noqa: E402
 
 SO = os.path.join(util.ROOT, "node-cueball_b200", "libcueball_b200.so")
-UNVALIDATED_OK = ("shuffle_kernel",)  # kernels allowed to exist without a hardware run yet (its GPU test is not gated)
+UNVALIDATED_OK = ()  # kernels allowed to exist without a hardware run (none: every kernel of the build is pinned)
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
