@@ -116,6 +116,9 @@ class ConnectionPool(object):
         self._slot_backend = np.zeros(0, np.int32)
         self._handles = {}     # ticket -> handle, until the device resolves it
         self._claimed = 0      # slots held by claimed handles
+        self._busy_slots = {}  # slot -> how many claimed handles hold it (1; the kang snapshot counts them)
+        self.p_backends = {}   # key -> backend object as the resolver gave it (lib/pool.js:285-291)
+        self.p_spares = int(options.get("spares", 0))
         self._queue_ready = False
         self.records = []      # every (ticket, code, slot) the device produced, in order (observability/tests)
         # the pool without CoDel: a plain host FIFO (nothing to accelerate)
@@ -142,6 +145,7 @@ class ConnectionPool(object):
                 continue
             if code == R_ADMIT:  # lib/pool.js:747 / :934-951
                 self._claimed += 1
+                self._busy_slots[slot] = self._busy_slots.get(slot, 0) + 1
                 h.try_(slot, int(self._slot_backend[slot]) if slot < len(self._slot_backend) else -1)
             elif code in (R_CODEL_DROP, R_HARD_TIMEOUT):  # lib/pool.js:742-745 / connection-fsm.js:626-642
                 h.timeout()
@@ -163,6 +167,24 @@ class ConnectionPool(object):
                 "idleConnections": int(info.idle), "pendingConnections": 0,
                 "waiterCount": int(info.tail - info.head)}
 
+    def toKangSnapshot(self):
+        """What the pool monitor publishes for a pool (lib/pool-monitor.js:91-133 getPool): backends,
+        per-backend connection counts by slot state, dead backends, pool state, counters and the
+        spares/maximum options.  A slot of this model is 'busy' while a claimed handle holds it and 'idle'
+        otherwise (the reference's other slot states belong to socket management, outside the path);
+        the resolver fields are the host's."""
+        conns = {k: {} for k in self.p_keys}
+        for slot, kid in enumerate(self._slot_backend.tolist()):
+            k = self._id_to_key.get(int(kid))
+            if k is None:
+                continue
+            st = "busy" if self._busy_slots.get(slot) else "idle"
+            d = conns.setdefault(k, {})
+            d[st] = d.get(st, 0) + 1
+        return {"backends": dict(self.p_backends), "connections": conns, "dead_backends": [],
+                "state": "stopping" if self._stopping else "running", "counters": self.getStats()["counters"],
+                "options": {"spares": self.p_spares, "maximum": self.p_max}}
+
     # ------------------------------------------------------------ resolver
     def on_resolver_added(self, k, backend=None):  # lib/pool.js:285-291
         kid = self._key_ids.get(k)
@@ -174,6 +196,7 @@ class ConnectionPool(object):
         u = float(self._random())
         idx = int(np.floor(u * (len(self.p_keys) + 1)))
         self.p_keys.insert(idx, k)
+        self.p_backends[k] = backend if backend is not None else {"key": k}
         self._ctx.backend_added(kid, u, *self._srv(backend))
         self._refresh_slots()
 
@@ -181,6 +204,7 @@ class ConnectionPool(object):
         if k not in self._key_ids or k not in self.p_keys:
             raise AssertionError("resolver key %s not found" % k)
         self.p_keys.remove(k)
+        self.p_backends.pop(k, None)
         self._ctx.backend_removed(self._key_ids[k])
         self._refresh_slots()
 
@@ -265,6 +289,10 @@ class ConnectionPool(object):
     def _slot_released(self, slot):
         """A slot FSM returned to 'idle' (lib/connection-fsm.js:1141-1147 -> pool.js:715)."""
         self._claimed -= 1
+        if self._busy_slots.get(slot, 0) > 1:
+            self._busy_slots[slot] -= 1
+        else:
+            self._busy_slots.pop(slot, None)
         self.slots_idle(1)
 
     def slots_idle(self, k, now_ns=None):
@@ -322,6 +350,8 @@ class ConnectionPool(object):
         slot = self._host_cursor % n if n else -1
         self._host_cursor += 1
         self._claimed += 1
+        if slot >= 0:
+            self._busy_slots[slot] = self._busy_slots.get(slot, 0) + 1
         handle.try_(slot, int(self._slot_backend[slot]) if n else -1)
 
     def _host_expire(self, now):

@@ -121,3 +121,30 @@ def test_waiters_time_out_without_any_release(cb):
     pool.expire()
     assert w.isInState("failed") and isinstance(errs[0], cb.ClaimTimeoutError)
     assert pool.getStats()["counters"]["claim-timeout"] == 1
+
+
+def test_kang_snapshot_shape(cb):
+    """What lib/pool-monitor.js:91-133 publishes for a pool: backends, per-backend connection counts by slot
+    state, dead backends, state, counters, options."""
+    clock = {"now": 10 ** 9}
+    draws = iter([0.1, 0.9, 0.4])
+    pool = cb.ConnectionPool({"targetClaimDelay": 5, "maximum": 4, "spares": 2, "clock": lambda: clock["now"],
+                              "random": lambda: next(draws)})
+    for k in ("b0", "b1"):
+        pool.on_resolver_added(k, {"address": "10.0.0.%s" % k[1], "port": 80})
+    hs = [pool.claim(lambda *a: None) for _ in range(5)]
+    assert [h.ch_state for h in hs] == ["claimed"] * 4 + ["waiting"]
+    snap = pool.toKangSnapshot()
+    assert set(snap) == {"backends", "connections", "dead_backends", "state", "counters", "options"}
+    assert snap["backends"] == {"b0": {"address": "10.0.0.0", "port": 80}, "b1": {"address": "10.0.0.1", "port": 80}}
+    assert snap["connections"] == {"b0": {"busy": 2}, "b1": {"busy": 2}}
+    assert snap["state"] == "running" and snap["dead_backends"] == []
+    assert snap["options"] == {"spares": 2, "maximum": 4}
+    assert snap["counters"] == {"claim": 5, "queued-claim": 1, "max-claim-queue": 1}
+    clock["now"] += 1_000_000
+    hs[0].release()                  # the waiter takes the slot at once: still four busy
+    hs[1].release()
+    snap = pool.toKangSnapshot()
+    assert sorted(sum((list(v.items()) for v in snap["connections"].values()), [])) == [("busy", 1), ("busy", 2), ("idle", 1)]
+    pool.stop()
+    assert pool.toKangSnapshot()["state"] == "stopping"
