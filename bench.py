@@ -420,8 +420,17 @@ def timed_pass(run, per_step=None):
         run.step(b)
         if per_step:
             per_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the K steps are ~1 ms of GPU time fed by this thread: keep the collector and the scheduler out of the way
+    gc_was = gc.isenabled()
+    gc.disable()
     ctx.synchronize()
     barrier(run.world)
+    rt = _realtime(True)
+    # Nothing slow between here and the first timed step: with the count boards connected the ranks' batches are
+    # coupled on the device (a batch's counts need every rank's post), so the re-warm steps end at the same moment
+    # on every rank -- the first event is ordered behind them and must already be in the stream by then, or the
+    # ranks whose host was early would time the others' lateness as their own steps.
     for b in range(W - rewarm, W):
         if idle:
             break
@@ -429,11 +438,6 @@ def timed_pass(run, per_step=None):
         if per_step:
             per_step()
     ctx.join()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the K steps are ~1 ms of GPU time fed by this thread: keep the collector and the scheduler out of the way
-    gc_was = gc.isenabled()
-    gc.disable()
-    rt = _realtime(True)
     e0.record(stream)
     lc0 = ctx.launch_count()
     th0 = time.perf_counter()
@@ -679,7 +683,7 @@ def nccl_leg(wl, K, W, world, rank, local, dev, stream):
 
     def last_only():
         calls["i"] += 1
-        if calls["i"] == 1 or calls["i"] == W + K:  # the first call (warm-up) sets up the communicator's channels
+        if calls["i"] <= W or calls["i"] == W + K:  # the warm-up steps' calls set up the communicator's channels
             run.ctx.allreduce_counts()
     ms, _, _ = timed_pass(run, per_step=last_only)
     ms = max_over_ranks(ms, world, dev)
