@@ -91,4 +91,12 @@ unsigned long long emu_queue_results(EmuQueue *e, long long *out, unsigned long 
 	return n;
 }
 void emu_queue_info(EmuQueue *e, QueueDev *out) { *out = e->q; }
+/* what the host side of the library does without a kernel: the slot table's size after a topology
+ * change (queue_params() reads the context's nslots) and cb_queue_trim_idle's bookkeeping word */
+void emu_queue_set_nslots(EmuQueue *e, long long nslots) { e->nslots = nslots; }
+unsigned long long emu_queue_trim_idle(EmuQueue *e, unsigned long long k) {
+	const unsigned long long take = k < e->q.idle ? k : e->q.idle;
+	e->q.idle -= take;
+	return take;
+}
 }

@@ -1,0 +1,157 @@
+"""EmuContext -- TEST INFRASTRUCTURE: the slice of cueball_b200.Context that the host mirror
+`ConnectionPool` (node-cueball_b200/pool.py) calls, served by the library's own kernels compiled for the
+HOST (tests/emu: csrc/cb_queue.cuh and csrc/cb_topology.cuh under the execution-model emulation) instead of
+by the GPU.  It lets the `-m "not gpu"` suite replay the pinned pool-model scripts through the REAL pool.py
+(handles, callbacks, getStats, the kang snapshot) in this container; on the GPU box the same scripts go
+through the real C ABI (tests/test_gpu_pool_mirror.py).  Nothing in the product imports this module, and the
+product's Context has no such mode: without the CUDA library and a device cb_create fails.
+
+The host-side glue mirrored here is what csrc/cueball_b200.cu does around the kernels:
+rebuild_slots() = plan_rebalance_kernel(have = 0, dead = 0, target = max = the wanted slots) +
+slot_table_kernel; cb_queue_create rounds the capacity up to a power of two >= 1024; cb_queue_push reads
+next_ticket before the kernel; cb_queue_trim_idle is a bookkeeping word."""
+import ctypes as C
+import types
+
+import numpy as np
+
+import test_queue_kernels_emulated as TQ
+import test_topology_kernels_emulated as TT
+
+
+class EmuContext(object):
+    KEY_CAP = 256
+
+    def __init__(self):
+        self.Q = TQ.load_emu()
+        self.Q.emu_queue_set_nslots.argtypes = [C.c_void_p, C.c_longlong]
+        self.Q.emu_queue_trim_idle.argtypes = [C.c_void_p, C.c_uint64]
+        self.Q.emu_queue_trim_idle.restype = C.c_uint64
+        self.T = TT.load_emu()
+        self.target = None
+        self.q = None
+        self.keys = np.zeros(self.KEY_CAP, np.int32)
+        self.nkeys = np.zeros(1, np.int32)
+        self.want_slots = 0
+        self.slot_backend = np.zeros(0, np.int32)
+        self.launches = 0
+
+    # ------------------------------------------------------------------ CoDel
+    def codel_init(self, target_ms):
+        self.target = float(target_ms)
+
+    # --------------------------------------------------------------- topology
+    def _rebuild(self):
+        B, S = int(self.nkeys[0]), int(self.want_slots)
+        if B <= 0 or S <= 0:
+            self.slot_backend = np.zeros(0, np.int32)
+        else:
+            have, dead = np.zeros(B, np.int32), np.zeros(B, np.uint8)
+            want, add = np.zeros(B, np.int32), np.zeros(S + 1, np.int32)
+            na, nr = np.zeros(1, np.int32), np.zeros(1, np.int32)
+            self.T.emu_plan_rebalance(have.ctypes.data, dead.ctypes.data, B, S, S, 0, want.ctypes.data, add.ctypes.data,
+                                      na.ctypes.data, None, None, nr.ctypes.data)
+            table = np.zeros(S + 8, np.int32)
+            ns = np.zeros(1, np.int32)
+            self.T.emu_slot_table(self.keys.ctypes.data, add.ctypes.data, na.ctypes.data, table.ctypes.data, S + 8, ns.ctypes.data)
+            self.slot_backend = table[:int(ns[0])].copy()
+            self.launches += 2
+        if self.q:
+            self.Q.emu_queue_set_nslots(self.q, len(self.slot_backend))
+
+    def backends_set(self, nbackends, insert_u, nslots, table=None, mode=0):
+        assert table is None and mode == 0, "the emulated context serves the uniform mode only"
+        self.want_slots = int(nslots)
+        self.nkeys[0] = int(nbackends)
+        if nbackends:
+            us = np.ascontiguousarray(insert_u, dtype=np.float64)
+            self.T.emu_pref_build(self.keys.ctypes.data, int(nbackends), us.ctypes.data)
+        self._rebuild()
+
+    def backend_added(self, key, u, priority=0, weight=0):
+        assert 0 <= key and self.nkeys[0] + 1 < self.KEY_CAP and 0.0 <= u < 1.0
+        self.T.emu_pref_insert(self.keys.ctypes.data, self.nkeys.ctypes.data, int(key), float(u))
+        self._rebuild()
+
+    def backend_removed(self, key):
+        if self.T.emu_pref_remove(self.keys.ctypes.data, self.nkeys.ctypes.data, int(key)) != 0:
+            raise AssertionError("resolver key %d not found" % key)
+        self._rebuild()
+
+    def reshuffle(self, u):
+        if self.nkeys[0] <= 1:
+            return
+        self.T.emu_pref_reshuffle(self.keys.ctypes.data, self.nkeys.ctypes.data, float(u))
+        self._rebuild()
+
+    def backends_get(self):
+        return self.keys[:int(self.nkeys[0])].copy(), self.slot_backend.copy()
+
+    # ------------------------------------------------------ pending-claim queue
+    def queue_create(self, capacity, result_capacity=None, idle_slots=0):
+        assert self.target is not None, "cb_codel_init has not been called"
+        cap = 1024
+        while cap < capacity:
+            cap <<= 1
+        if self.q:
+            self.Q.emu_queue_destroy(self.q)
+        self.q = self.Q.emu_queue_create(self.target, len(self.slot_backend), cap, int(result_capacity or 2 * capacity),
+                                         int(idle_slots))
+        self._res_cap = int(result_capacity or 2 * capacity)
+
+    def queue_info(self):
+        from cueball_b200 import _native as N
+        raw = TQ.QueueDev()
+        self.Q.emu_queue_info(self.q, C.byref(raw))
+        assert raw.err == 0, "queue error flags %#x" % raw.err
+        out = N.QueueInfo()
+        C.memmove(C.byref(out), C.byref(raw), C.sizeof(out))
+        return out
+
+    def queue_push(self, start_ns, want_timeouts=False):
+        start = np.ascontiguousarray(start_ns, dtype=np.int64)
+        first = int(self.queue_info().next_ticket)
+        tmo = np.empty(start.shape[0], np.float64) if want_timeouts else None
+        self.Q.emu_queue_push(self.q, start.ctypes.data, start.shape[0], None if tmo is None else tmo.ctypes.data)
+        self.launches += 1
+        return first, tmo
+
+    def queue_cancel(self, tickets):
+        t = np.ascontiguousarray(tickets, dtype=np.int64)
+        self.Q.emu_queue_cancel(self.q, t.ctypes.data, t.shape[0])
+        self.launches += 1
+
+    def queue_expire(self, now_ns):
+        self.Q.emu_queue_expire(self.q, int(now_ns))
+        self.launches += 1
+
+    def queue_idle(self, now_ns, k_slots):
+        self.Q.emu_queue_idle(self.q, int(now_ns), int(k_slots))
+        self.launches += 1
+
+    def queue_trim_idle(self, k):
+        return int(self.Q.emu_queue_trim_idle(self.q, int(k)))
+
+    def queue_results(self):
+        buf = np.empty((max(self._res_cap, 1), 3), np.int64)
+        n = self.Q.emu_queue_results(self.q, buf.ctypes.data, buf.shape[0])
+        return buf[:n].copy()
+
+    # ------------------------------------------------------------------ state
+    def stats(self):
+        F, D, E = C.c_double(), C.c_double(), C.c_double()
+        Cn, cur = C.c_uint64(), C.c_uint64()
+        B, hasE = C.c_int(), C.c_int()
+        self.Q.emu_queue_get_state(self.q, C.byref(F), C.byref(D), C.byref(Cn), C.byref(B), C.byref(hasE), C.byref(E),
+                                   C.byref(cur))
+        state = types.SimpleNamespace(count=Cn.value, drop_next=D.value, first_above_time=F.value, dropping=B.value,
+                                      has_last_empty=hasE.value, last_empty=E.value)
+        return types.SimpleNamespace(cursor=cur.value, state=state)
+
+    def launch_count(self):
+        return self.launches
+
+    def close(self):
+        if self.q:
+            self.Q.emu_queue_destroy(self.q)
+            self.q = None

@@ -1,0 +1,90 @@
+"""The host mirror `ConnectionPool` (node-cueball_b200/pool.py: claim() / cancel() / release() / expire() /
+getStats() / toKangSnapshot(), lib/pool.js:859-969, lib/connection-fsm.js:580-642, lib/pool-monitor.js:91-133)
+replayed in THIS container, without a GPU: the pool runs on tests/emu_context.EmuContext, which serves the
+Context calls pool.py makes with the library's own queue and topology kernels compiled for the host
+(tests/emu).  Same scripts, same checks as tests/test_gpu_pool_mirror.py (whose helpers are reused), so the
+mirror's host logic -- records -> handle transitions and callbacks, counters, the snapshot shapes -- is pinned
+to the pool-model oracle on the CPU as well.  An emulated launch costs ~20 ms, so the default run replays the
+head of three golden scripts; CB_EMU_FULL=1 replays all twelve and six random ones."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+import test_gpu_pool_mirror as GP
+import util
+from emu_context import EmuContext
+
+FULL = os.environ.get("CB_EMU_FULL") == "1"
+QUICK = ["hard_timeouts_t5", "pauses_and_stalls_t10", "idle_slots_first_t5"]
+CASES = GP.G["cases"] if FULL else [c for c in GP.G["cases"] if c["name"] in QUICK]
+HEAD = None if FULL else 260
+
+
+@pytest.fixture(scope="module")
+def cb():
+    """The package with ConnectionPool bound to an emulated context (everything else is the real thing)."""
+    import cueball_b200 as real
+
+    def pool(options):
+        o = dict(options)
+        o["context"] = EmuContext()
+        return real.ConnectionPool(o)
+    return types.SimpleNamespace(ConnectionPool=pool, ClaimTimeoutError=real.ClaimTimeoutError,
+                                 ClaimHandleMisusedError=real.ClaimHandleMisusedError)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_pool_mirror_on_golden_scripts_emulated(cb, case):
+    GP.check(cb, case["target"], case["nslots"], case["ev_type"][:HEAD], case["ev_a"][:HEAD], case["ev_b"][:HEAD],
+             case["idle0"])
+
+
+@pytest.mark.parametrize("seed", range(6) if FULL else [5])
+def test_pool_mirror_on_random_scripts_emulated(cb, seed):
+    rng = np.random.RandomState(7000 + seed)
+    tgt = int(rng.choice([2, 5, 10, 20]))
+    ty, a, b = util.gen_pool_events(9000 + seed, 600 if FULL else 220, tgt, float(rng.choice([2.0, 5.0, 9.0, 12.0])),
+                                    float(rng.choice([0.0, 0.1, 0.5])))
+    GP.check(cb, tgt, int(rng.choice([3, 11, 37])), ty, a, b, seed % 3)
+
+
+def test_cancel_of_a_claimed_handle_releases_it_emulated(cb):
+    GP.test_cancel_of_a_claimed_handle_releases_it(cb)
+
+
+def test_waiters_time_out_without_any_release_emulated(cb):
+    GP.test_waiters_time_out_without_any_release(cb)
+
+
+def test_kang_snapshot_shape_emulated(cb):
+    GP.test_kang_snapshot_shape(cb)
+
+
+def test_topology_changes_move_idle_slots(cb):
+    """_refresh_slots: the slots of a grown table turn idle as an event (they drain waiters, lib/pool.js:715);
+    the slots of a table that shrank to nothing leave the idle queue (setUnwanted, lib/pool.js:601-631)."""
+    clock = {"now": 10 ** 9}
+    draws = iter([0.2, 0.7, 0.5])
+    got = []
+    pool = cb.ConnectionPool({"targetClaimDelay": 5, "maximum": 3, "clock": lambda: clock["now"],
+                              "random": lambda: next(draws)})
+    waiting = [pool.claim(lambda e, h, c: got.append((e, c))) for _ in range(2)]  # no backend yet: both wait
+    assert [h.ch_state for h in waiting] == ["waiting", "waiting"]
+    assert pool.getStats()["totalConnections"] == 0
+    clock["now"] += 1_000_000
+    pool.on_resolver_added("b0", {})          # 3 slots appear and drain the two waiters
+    assert [h.ch_state for h in waiting] == ["claimed", "claimed"]
+    assert [c["slot"] for _, c in got] == [0, 1] and all(e is None for e, _ in got)
+    st = pool.getStats()
+    assert (st["totalConnections"], st["idleConnections"], st["waiterCount"]) == (3, 1, 0)
+    pool.on_resolver_added("b1", {})          # same table size: nothing moves
+    assert pool.getStats()["idleConnections"] == 1
+    assert sorted(pool.toKangSnapshot()["connections"]) == ["b0", "b1"]
+    pool.on_resolver_removed("b0")
+    pool.on_resolver_removed("b1")            # no backend, no slots: the idle one is gone
+    st = pool.getStats()
+    assert (st["totalConnections"], st["idleConnections"]) == (0, 0)
+    with pytest.raises(AssertionError):
+        pool.on_resolver_removed("b1")
