@@ -14,6 +14,10 @@ What is mirrored (reference file:line):
       queue emptied with the slot still idle -> codel.empty(), slot onto p_idleq
   on_resolver_added / on_resolver_removed / reshuffle   lib/pool.js:285-313, 501-519
   getStats(): counters + the five fields of           lib/pool.js:269-283, 834-857
+  toKangSnapshot()                                    lib/pool-monitor.js:91-133
+  the low-pass filter of the pool's size (FIRFilter, genTaps, the 5 Hz sampler) and
+  _rebalance's target: busy + extras + spares, clamped from below by the filter
+                                                    lib/pool.js:44-100, 251-262, 541-592
   handle states waiting/claimed/released/closed/cancelled/failed
                                                     lib/connection-fsm.js:489-808
 
@@ -26,11 +30,14 @@ turned into the handles' callbacks here.  tests/test_gpu_pool_mirror.py replays 
 scripts of the reference's pool model through this class and compares records and counters exactly.
 
 What is NOT here (out of scope, stays in Node in a real deployment): sockets, the slot and
-socket FSMs, retry/backoff, the FIR low-pass filter and the churn limiter.  A "slot" here is
+socket FSMs, retry/backoff and the churn limiter that paces how a rebalance plan is applied
+(lib/pool.js:599-658).  The low-pass filter is host arithmetic (128 multiply-adds five times a
+second, summed in the reference's order): its INPUT -- busy slots -- is the device queue's counters.  A "slot" here is
 an integer (admitted claim j of the pool's life takes slot j mod nslots); its
 backend comes from the device-side slot table.  A pool WITHOUT targetClaimDelay has no CoDel
 (lib/pool.js:195-200): nothing on its path is accelerated, and it runs as a plain host FIFO.
 """
+import math
 import time
 
 import numpy as np
@@ -40,6 +47,73 @@ from .errors import ClaimHandleMisusedError, ClaimTimeoutError, NoBackendsError,
 from .utils import assertClaimDelay
 
 R_ADMIT, R_CODEL_DROP, R_SKIPPED, R_HARD_TIMEOUT = 0, 1, 2, 3  # codes of cb_queue_results
+
+LP_RATE = 5                           # sample rate of the filter, Hz (lib/pool.js:44)
+LP_INT = int(round(1000 / LP_RATE))   # one sampling interval, ms (lib/pool.js:46)
+
+
+def genTaps(count, tc):
+    """EMA taps exp(tc * i) normalised to sum 1 (lib/pool.js:64-76), summed in the reference's order."""
+    taps = [math.exp(tc * i) for i in range(count)]
+    total = 0.0
+    for t in taps:
+        total += t
+    return [t / total for t in taps]
+
+
+LP_TAPS = genTaps(128, -0.2)          # lib/pool.js:48
+
+
+class FIRFilter(object):
+    """A FIR filter over a circular buffer (lib/pool.js:78-100); get() accumulates newest sample first,
+    one rounding per multiply and per add, exactly as the reference's loop does."""
+
+    def __init__(self, taps):
+        self.f_taps = taps
+        self.f_buf = [0.0] * len(taps)
+        self.f_ptr = 0
+
+    def put(self, v):
+        self.f_buf[self.f_ptr] = float(v)
+        self.f_ptr += 1
+        if self.f_ptr == len(self.f_taps):
+            self.f_ptr = 0
+
+    def get(self):
+        n = len(self.f_taps)
+        i = self.f_ptr - 1
+        if i < 0:
+            i += n
+        acc = 0.0
+        for j in range(n):
+            acc += self.f_buf[i] * self.f_taps[j]
+            i -= 1
+            if i < 0:
+                i += n
+        return acc
+
+
+def rebalanceTarget(lpf, total, idleq, initq, waiters, spares_wanted, maximum):
+    """The size _rebalance asks planRebalance for (lib/pool.js:563-586): busy + extras + spares, never
+    below what the filter remembers of the recent load.  Returns (target, clamped)."""
+    spares = idleq + initq - waiters
+    if spares < 0:
+        spares = 0
+    busy = total - spares
+    if busy < 0:
+        busy = 0
+    extras = waiters - initq
+    if extras < 0:
+        extras = 0
+    target = busy + extras + spares_wanted
+    mn = math.ceil(lpf.get())
+    clamped = False
+    if target < mn * 1.05:
+        target = mn
+        clamped = True
+    if target > maximum:
+        target = maximum
+    return int(target), clamped
 
 
 class CueBallClaimHandle(object):
@@ -119,6 +193,9 @@ class ConnectionPool(object):
         self._busy_slots = {}  # slot -> how many claimed handles hold it (1; the kang snapshot counts them)
         self.p_backends = {}   # key -> backend object as the resolver gave it (lib/pool.js:285-291)
         self.p_spares = int(options.get("spares", 0))
+        self.p_lpf = FIRFilter(LP_TAPS)      # lib/pool.js:189
+        self.p_lastRebalClamped = False      # lib/pool.js:247
+        self.p_lastRebalance = None          # what the last rebalance() asked for (observability)
         self._queue_ready = False
         self.records = []      # every (ticket, code, slot) the device produced, in order (observability/tests)
         # the pool without CoDel: a plain host FIFO (nothing to accelerate)
@@ -184,6 +261,46 @@ class ConnectionPool(object):
         return {"backends": dict(self.p_backends), "connections": conns, "dead_backends": [],
                 "state": "stopping" if self._stopping else "running", "counters": self.getStats()["counters"],
                 "options": {"spares": self.p_spares, "maximum": self.p_max}}
+
+    # ------------------------------------------------------------ sizing (low-pass filter, _rebalance's target)
+    def _occupancy(self):
+        """(connections, idle slots, waiters) from the device queue's counters; initq is empty in this model
+        (a slot of the table is connected)."""
+        total = len(self._slot_backend)
+        if self.p_codel is None:
+            return total, self._host_idle, len(self._host_waiters)
+        if not self._queue_ready:
+            return total, total, 0
+        info = self._ctx.queue_info()
+        return total, int(info.idle), int(info.tail - info.head)
+
+    def lpTick(self):
+        """The body of the pool's 5 Hz sampler (lib/pool.js:251-262; the host calls it every LP_INT ms):
+        feeds busy + spares to the filter and, while the last rebalance was clamped, rebalances again."""
+        conns, spares, _ = self._occupancy()
+        self.p_lpf.put(conns - spares + self.p_spares)
+        if self.p_lastRebalClamped:
+            return self.rebalance()
+        return None
+
+    def rebalance(self):
+        """_rebalance up to the plan (lib/pool.js:541-592): the target size, then planRebalance over the
+        connections per backend in preference order -- on the device (cb_plan_rebalance).  Returns
+        {"target", "clamped", "add": [key...], "remove": [(key, index of the connection)...]} or None when
+        the reference returns early (:521-526).  Applying the plan (sockets, the churn limiter of :599-658)
+        is the host's."""
+        if len(self.p_keys) < 1 or self._stopping:
+            return None
+        total, idle, waiters = self._occupancy()
+        target, clamped = rebalanceTarget(self.p_lpf, total, idle, 0, waiters, self.p_spares, self.p_max)
+        self.p_lastRebalClamped = clamped
+        ids = [self._key_ids[k] for k in self.p_keys]
+        have = [int((self._slot_backend == i).sum()) for i in ids]
+        _, add, remove = self._ctx.plan_rebalance(have, [0] * len(ids), target, self.p_max)
+        plan = {"target": target, "clamped": clamped, "add": [self.p_keys[int(i)] for i in add],
+                "remove": [(self.p_keys[int(k)], int(o)) for k, o in remove]}
+        self.p_lastRebalance = plan
+        return plan
 
     # ------------------------------------------------------------ resolver
     def on_resolver_added(self, k, backend=None):  # lib/pool.js:285-291

@@ -649,3 +649,75 @@ int cbo_pool_sim(cbo_codel *cd, int64_t nslots, uint64_t idle0, uint64_t cursor0
 	free(handles);
 	return 0;
 }
+
+/* ------------------------------------------------------------------ low-pass filter, lib/pool.js:44-100 */
+void
+cbo_lpf_taps(double *taps)
+{
+	/* genTaps(128, -0.2), lib/pool.js:64-76: taps[i] = exp(tc * i), then each divided by their sum */
+	const double tc = -0.2;
+	double sum = 0.0;
+	int i;
+	for (i = 0; i < CBO_LPF_TAPS; ++i) {
+		taps[i] = exp(tc * i);
+		sum += taps[i];
+	}
+	for (i = 0; i < CBO_LPF_TAPS; ++i)
+		taps[i] /= sum;
+}
+
+size_t
+cbo_lpf_run(int64_t p_spares, int64_t max, const uint8_t *ty, const int64_t *a, const int64_t *b,
+    const int64_t *c, const int64_t *d, size_t n_events, double *out)
+{
+	double taps[CBO_LPF_TAPS], buf[CBO_LPF_TAPS];
+	int ptr = 0;		/* f_ptr, lib/pool.js:80 */
+	size_t e, k = 0;
+	int i, j;
+	cbo_lpf_taps(taps);
+	memset(buf, 0, sizeof (buf));
+	for (e = 0; e < n_events; e++) {
+		if (ty[e] == 0) {
+			/* the sampler, lib/pool.js:251-258, into FIRFilter.put, :82-87 */
+			const int64_t busy0 = a[e] - b[e];
+			buf[ptr++] = (double)(busy0 + p_spares);
+			if (ptr == CBO_LPF_TAPS)
+				ptr = 0;
+			continue;
+		}
+		/* FIRFilter.get, lib/pool.js:88-100: newest sample times taps[0], walking back round the ring */
+		double acc = 0.0;
+		i = ptr - 1;
+		if (i < 0)
+			i += CBO_LPF_TAPS;
+		for (j = 0; j < CBO_LPF_TAPS; ++j) {
+			acc += buf[i] * taps[j];
+			if (--i < 0)
+				i += CBO_LPF_TAPS;
+		}
+		/* _rebalance, lib/pool.js:563-586 */
+		int64_t spares = b[e] + c[e] - d[e];
+		if (spares < 0)
+			spares = 0;
+		int64_t busy = a[e] - spares;
+		if (busy < 0)
+			busy = 0;
+		int64_t extras = d[e] - c[e];
+		if (extras < 0)
+			extras = 0;
+		double target = (double)(busy + extras + p_spares);
+		const double min = ceil(acc);
+		double clamped = 0.0;
+		if (target < min * 1.05) {
+			target = min;
+			clamped = 1.0;
+		}
+		if (target > (double)max)
+			target = (double)max;
+		out[3 * k] = target;
+		out[3 * k + 1] = clamped;
+		out[3 * k + 2] = acc;
+		k++;
+	}
+	return (k);
+}

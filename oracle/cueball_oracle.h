@@ -145,6 +145,20 @@ int cbo_pool_sim(cbo_codel *cd, int64_t nslots, uint64_t idle0, uint64_t cursor0
     const int64_t *ev_a, const int64_t *ev_b, size_t n_events, int64_t *res /* 6 per CLAIM */,
     double *timeouts_ms /* 1 per CLAIM */, cbo_pool_result *out);
 
+/*
+ * The pool's low-pass filter and sizing arithmetic ("LPF clamp input"), same event
+ * format as cb_lpf_run in oracle/js/driver.js, which drives the reference's own FIRFilter:
+ *   cbo_lpf_taps     genTaps(128, -0.2), lib/pool.js:64-76
+ *   ty 0  the 5 Hz sampler, lib/pool.js:251-258: a = connections, b = idleq + initq   -> put(busy + spares)
+ *   ty 1  _rebalance's target, lib/pool.js:556-587: a = total, b = idleq, c = initq, d = waiters
+ *         -> out[3k..] = target, clamped (0/1), FIRFilter.get() (lib/pool.js:90-100)
+ * Returns the number of ty-1 events.
+ */
+#define CBO_LPF_TAPS 128
+void cbo_lpf_taps(double *taps /* CBO_LPF_TAPS */);
+size_t cbo_lpf_run(int64_t spares, int64_t max, const uint8_t *ty, const int64_t *a, const int64_t *b,
+    const int64_t *c, const int64_t *d, size_t n_events, double *out /* 3 per ty-1 event */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,9 @@
  *                   the slot-idle handler, k slots      lib/pool.js:733-757
  *                   the handle's hard timeout            lib/connection-fsm.js:626-642
  *                   counters                             lib/pool.js:269-283,887,962-963
+ *   cb_lpf_run      the pool's 5 Hz sampler body        lib/pool.js:251-258 (setInterval closure)
+ *                   and _rebalance's target sizing     lib/pool.js:556-587, around the reference's
+ *                   own FIRFilter / LP_TAPS            lib/pool.js:44-100 (verbatim, module ./pool_lpf)
  *   cb_build_slots  preference-list random insertion   lib/pool.js:285-291
  *                   (Math.random replaced by injected draws) then the
  *                   reference's own planRebalance      lib/utils.js:239-393
@@ -24,6 +27,7 @@
 var ControlledDelay = __mods['./codel'].ControlledDelay;
 var Queue = __mods['./queue'];
 var utils = __mods['./utils'];
+var pool_lpf = __mods['./pool_lpf'];
 
 function __json(v) {
 	var t = typeof (v), i, r;
@@ -388,4 +392,46 @@ function cb_pool_sim(job) {
 	}
 	return { res: res, timeouts: timeouts, state: cb_state(cd), counters: counters,
 	    idle: idle, cursor: cursor, queued: waiters.length };
+}
+
+/*
+ * The pool's sizing arithmetic around the reference's own FIRFilter (lib/pool.js:44-100, verbatim).
+ * One event per sampler tick or rebalance, flat arrays:
+ *   ty 0: the 5 Hz sampler (lib/pool.js:251-258): conns=a, idleq+initq=b        -> lpf.put(busy + spares)
+ *   ty 1: _rebalance's target (lib/pool.js:556-587): total=a, idleq=b, initq=c, waiters=d
+ *         -> out: target, clamped (0/1), lpf.get()
+ * job: { spares, max }.  Returns { taps, out: flat [target, clamped, lpf]* for the ty-1 events }.
+ */
+function cb_lpf_run(job) {
+	var lpf = new pool_lpf.FIRFilter(pool_lpf.LP_TAPS);
+	var out = [], n = job.ty.length;
+	for (var e = 0; e < n; e++) {
+		if (job.ty[e] === 0) {
+			var conns = job.a[e];
+			var sp = job.b[e];				/* p_idleq.length + p_initq.length, pool.js:256 */
+			var bz = conns - sp;				/* pool.js:257 */
+			lpf.put(bz + job.spares);			/* pool.js:258 */
+			continue;
+		}
+		var total = job.a[e];
+		var spares = job.b[e] + job.c[e] - job.d[e];		/* pool.js:563-564 */
+		if (spares < 0) spares = 0;
+		var busy = total - spares;				/* pool.js:567 */
+		if (busy < 0) busy = 0;
+		var extras = job.d[e] - job.c[e];			/* pool.js:570 */
+		if (extras < 0) extras = 0;
+		var target = busy + extras + job.spares;		/* pool.js:574 */
+		var g = lpf.get();
+		var min = Math.ceil(g);					/* pool.js:576 */
+		var clamped = 0;
+		if (target < min * 1.05) {				/* pool.js:577-583 */
+			target = min;
+			clamped = 1;
+		}
+		if (target > job.max) target = job.max;			/* pool.js:585-586 */
+		out.push(target, clamped, g);
+	}
+	var taps = [];
+	for (var i = 0; i < pool_lpf.LP_TAPS.length; i++) taps.push(pool_lpf.LP_TAPS[i]);
+	return { taps: taps, out: out, lp_int: pool_lpf.LP_INT };
 }

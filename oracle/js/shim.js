@@ -21,6 +21,12 @@ if (!Object.defineProperty) Object.defineProperty = function (o, n, d) {
 if (!Number.isFinite) Number.isFinite = function (v) {
 	return typeof (v) === 'number' && isFinite(v); };
 
+/* lib/pool.js:65,79 keep the filter taps and the sample ring in Float64Arrays: an Array of Numbers holds
+ * the same doubles (SM 1.7 has no typed arrays) */
+if (typeof (Float64Array) === 'undefined') {
+	var Float64Array = function (n) { var a = new Array(n); for (var i = 0; i < n; i++) a[i] = 0.0; return a; };
+}
+
 var __mods = {}, __tests = {};
 /* harness clock: integer seconds + integer nanoseconds, like process.hrtime() */
 var __hr_secs = 0, __hr_ns = 0;

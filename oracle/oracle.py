@@ -186,3 +186,23 @@ def pool_sim(cd, nslots, ev_type, ev_a, ev_b, idle0=0, cursor=0):
     if rc != 0:
         raise RuntimeError("oracle pool_sim failed")
     return res[:3 * out.n_res].reshape(-1, 3).copy(), tmo[:nclaims].copy(), out
+
+
+def lpf_taps():
+    """genTaps(128, -0.2) of lib/pool.js:64-76."""
+    t = np.zeros(128, np.float64)
+    lib().cbo_lpf_taps(_p(t))
+    return t
+
+
+def lpf_run(spares, mx, ty, a, b, c, d):
+    """The pool's sampler / _rebalance target events (see cueball_oracle.h); returns rows of
+    (target, clamped, lpf.get()) for the ty-1 events."""
+    ty = np.ascontiguousarray(ty, dtype=np.uint8)
+    arrs = [np.ascontiguousarray(x, dtype=np.int64) for x in (a, b, c, d)]
+    out = np.zeros(3 * max(int((ty == 1).sum()), 1), np.float64)
+    L = lib()
+    L.cbo_lpf_run.restype = C.c_size_t
+    k = L.cbo_lpf_run(C.c_int64(int(spares)), C.c_int64(int(mx)), _p(ty), _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]),
+                      C.c_size_t(ty.shape[0]), _p(out))
+    return out[:3 * k].reshape(-1, 3).copy()

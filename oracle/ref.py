@@ -117,3 +117,12 @@ def pool_sim(target, nslots, ev_type, ev_a, ev_b, state=None, idle0=0, cursor=0,
     expr = ("(function(){var job=%s; job.ev_type=__read_array(); job.ev_a=__read_array(); "
             "job.ev_b=__read_array(); return cb_pool_sim(job);})()" % _lit(job))
     return call(expr, timeout=timeout, arrays=[ev_type, ev_a, ev_b])
+
+
+def lpf_run(spares, mx, ty, a, b, c, d):
+    """The pool's low-pass filter (lib/pool.js:44-100, verbatim) under the sampler and _rebalance's target
+    arithmetic (cb_lpf_run in driver.js)."""
+    job = {"spares": spares, "max": mx}
+    expr = ("(function(){var job=%s; job.ty=__read_array(); job.a=__read_array(); job.b=__read_array(); "
+            "job.c=__read_array(); job.d=__read_array(); return cb_lpf_run(job);})()" % _lit(job))
+    return call(expr, arrays=[ty, a, b, c, d])

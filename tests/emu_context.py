@@ -84,6 +84,21 @@ class EmuContext(object):
         self.T.emu_pref_reshuffle(self.keys.ctypes.data, self.nkeys.ctypes.data, float(u))
         self._rebuild()
 
+    def plan_rebalance(self, have, dead, target, mx, singleton=False):
+        """cb_plan_rebalance: plan_rebalance_kernel over caller-supplied connection counts."""
+        have = np.ascontiguousarray(have, dtype=np.int32)
+        dead = np.ascontiguousarray(dead, dtype=np.uint8)
+        B = have.shape[0]
+        tot = max(int(have.sum()) if B else 0, 0) + 1
+        want, add = np.zeros(max(B, 1), np.int32), np.zeros(max(int(mx), tot) + 1, np.int32)
+        rk, ro = np.zeros(tot, np.int32), np.zeros(tot, np.int32)
+        na, nr = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self.T.emu_plan_rebalance(have.ctypes.data, dead.ctypes.data, B, int(target), int(mx), int(bool(singleton)),
+                                  want.ctypes.data, add.ctypes.data, na.ctypes.data, rk.ctypes.data, ro.ctypes.data,
+                                  nr.ctypes.data)
+        self.launches += 1
+        return want[:B].copy(), add[:na[0]].copy(), list(zip(rk[:nr[0]].tolist(), ro[:nr[0]].tolist()))
+
     def backends_get(self):
         return self.keys[:int(self.nkeys[0])].copy(), self.slot_backend.copy()
 

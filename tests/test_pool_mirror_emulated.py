@@ -88,3 +88,11 @@ def test_topology_changes_move_idle_slots(cb):
     assert (st["totalConnections"], st["idleConnections"]) == (0, 0)
     with pytest.raises(AssertionError):
         pool.on_resolver_removed("b1")
+
+
+def test_sizing_loop_emulated(cb):
+    """lpTick() / rebalance(): the filter's input from the queue's counters, the plan from the planRebalance
+    kernel, every step against the oracle (the scenario of tests/test_gpu_zz_sizing.py)."""
+    import test_gpu_zz_sizing as Z
+    plans = Z.sizing_scenario(cb)
+    assert plans[0]["target"] == 2 and not plans[0]["clamped"]  # idle pool: busy 0 + spares 2; the filter still remembers less

@@ -163,3 +163,26 @@ def gen_pool_events(seed, n_ev, tgt, backlog_mult, jitter):
         if rng.rand() < 0.001:
             ti += int(rng.uniform(5, 60)) * ms
     return ty, a, b
+
+
+def gen_lpf_events(seed, n_ev, peak):
+    """A pool's life as the low-pass filter sees it: sampler ticks (ty 0: a = connections, b = idleq + initq)
+    interleaved with rebalances (ty 1: a = total connections, b = idleq, c = initq, d = waiters).  The load
+    follows a seeded random walk with ramps and bursts so that the clamp (lib/pool.js:577-583) switches both ways."""
+    rng = np.random.RandomState(seed)
+    ty, a, b, c, d = [], [], [], [], []
+    conns, busy = int(rng.randint(0, peak // 2 + 1)), 0
+    trend = 0
+    for _ in range(n_ev):
+        if rng.rand() < 0.05:
+            trend = int(rng.choice([-2, -1, 0, 1, 2]))
+        busy = int(np.clip(busy + trend + rng.randint(-2, 3) + (rng.randint(5, 15) if rng.rand() < 0.03 else 0), 0, peak))
+        conns = int(np.clip(max(conns + rng.randint(-1, 2), busy), 0, peak))
+        initq = int(rng.randint(0, 3)) if conns > busy else 0
+        idle = max(0, conns - busy - initq)
+        waiters = int(rng.randint(0, 2 * peak)) if (busy >= conns and rng.rand() < 0.5) else 0
+        if rng.rand() < 0.7:
+            ty.append(0); a.append(conns); b.append(idle + initq); c.append(0); d.append(0)  # noqa: E702
+        else:
+            ty.append(1); a.append(conns); b.append(idle); c.append(initq); d.append(waiters)  # noqa: E702
+    return ty, a, b, c, d
