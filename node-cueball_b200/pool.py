@@ -37,6 +37,7 @@ an integer (admitted claim j of the pool's life takes slot j mod nslots, SURVEY.
 backend comes from the device-side slot table.  A pool WITHOUT targetClaimDelay has no CoDel
 (lib/pool.js:195-200): nothing on its path is accelerated, and it runs as a plain host FIFO.
 """
+import heapq
 import math
 import time
 
@@ -189,6 +190,7 @@ class ConnectionPool(object):
         self._stopping = False
         self._slot_backend = np.zeros(0, np.int32)
         self._handles = {}     # ticket -> handle, until the device resolves it
+        self._deadlines = []   # heap of (deadline ns, ticket) of the handles above (entries go stale, see nextDeadline)
         self._claimed = 0      # slots held by claimed handles
         self._busy_slots = {}  # slot -> how many claimed handles hold it (1; the kang snapshot counts them)
         self.p_backends = {}   # key -> backend object as the resolver gave it (lib/pool.js:285-291)
@@ -390,8 +392,16 @@ class ConnectionPool(object):
         ticket, tmo = self._ctx.queue_push([now], want_timeouts=True)
         handle = CueBallClaimHandle(self, cb, now, float(tmo[0]), ticket)
         self._handles[ticket] = handle
+        heapq.heappush(self._deadlines, (now + int(float(tmo[0]) * 1e6), ticket))
         self._dispatch()
         return handle
+
+    def nextDeadline(self):
+        """The earliest clock value (ns) at which a waiting handle's claim timer fires (its S.timeout(claimTimeout),
+        lib/connection-fsm.js:626-642), or None: when a host with its own timer should call expire()."""
+        while self._deadlines and self._deadlines[0][1] not in self._handles:
+            heapq.heappop(self._deadlines)
+        return self._deadlines[0][0] if self._deadlines else None
 
     def stop(self):
         self._stopping = True

@@ -25,6 +25,17 @@
  *   shuffle(ctx, draws: Float64Array) -> Int32Array (the permutation of utils.shuffle)
  *              -> {want: Int32Array, add: Int32Array, rmKey: Int32Array, rmOrd: Int32Array}
  *                                                          lib/utils.js:239-393
+ *   the pending-claim queue resident in HBM (cb_queue_*; what shim/js/pool_queue.js drives):
+ *   queueCreate(ctx, capacity, resultCapacity, idleSlots)
+ *   queuePush(ctx, startNs: BigInt64Array, timeouts: Float64Array|null) -> first ticket (BigInt)
+ *                                                          n x ConnectionPool#claim, lib/pool.js:874-966
+ *   queueCancel(ctx, tickets: BigInt64Array)              handle.cancel(), lib/connection-fsm.js:580-587
+ *   queueExpire(ctx, nowNs)                               the handles' claim timers, lib/connection-fsm.js:626-642
+ *   queueIdle(ctx, nowNs, k)                              k slots turned idle: the handler lib/pool.js:733-757
+ *   queueTrimIdle(ctx, k) -> removed                      idle slots that went away, lib/pool.js:601-631
+ *   queueResults(ctx, out: BigInt64Array) -> records written: (ticket, code, slot) triples, resolution order
+ *   queueInfo(ctx) -> {claim, queuedClaim, maxClaimQueue, claimTimeout, idle, queued, nResults}
+ *                                                          lib/pool.js:269-283 counters, p_idleq/p_waiters lengths
  * Errors: CB_EINVAL -> throws (the reference throws AssertionError for programmer errors);
  * everything else -> throws Error(cb_last_error()).  Arguments are validated before the C ABI sees them:
  * a clock must be a BigInt that fits int64 (a Number is NOT silently read as 0), typed arrays must have the
@@ -337,6 +348,165 @@ Shuffle(napi_env env, napi_callback_info info)
 	return rc == CB_OK ? out : throw_cb(env, ctx, rc);
 }
 
+/* a non-negative count that fits the C ABI's size_t / uint64_t: a Number (integers below 2^53) */
+static bool
+count_arg(napi_env env, napi_value v, const char *what, uint64_t *out)
+{
+	double d = -1.0;
+	*out = 0;
+	if (napi_get_value_double(env, v, &d) != napi_ok || !(d >= 0.0) || d > 9007199254740992.0 || d != (double)(uint64_t)d) {
+		napi_throw_type_error(env, NULL, what);
+		return false;
+	}
+	*out = (uint64_t)d;
+	return true;
+}
+
+static napi_value
+QueueCreate(napi_env env, napi_callback_info info)
+{
+	size_t argc = 4; napi_value argv[4]; uint64_t cap, rcap, idle;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 4) {
+		napi_throw_type_error(env, NULL, "queueCreate(ctx, capacity, resultCapacity, idleSlots)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	if (!count_arg(env, argv[1], "capacity: a positive integer expected", &cap) ||
+	    !count_arg(env, argv[2], "resultCapacity: a positive integer expected", &rcap) ||
+	    !count_arg(env, argv[3], "idleSlots: a non-negative integer expected", &idle))
+		return NULL;
+	int rc = cb_queue_create(ctx, (size_t)cap, (size_t)rcap, idle);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+QueuePush(napi_env env, napi_callback_info info)
+{
+	size_t argc = 3, n = 0; napi_value argv[3], out; bool ok; int64_t first = 0;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 3) {
+		napi_throw_type_error(env, NULL, "queuePush(ctx, startNs, timeouts)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	const int64_t *start = typed(env, argv[1], napi_bigint64_array, 0, false, "startNs: BigInt64Array expected", &n, &ok);
+	if (!ok) return NULL;
+	double *tmo = typed(env, argv[2], napi_float64_array, n, true, "timeouts: Float64Array of startNs's length (or null) expected", NULL, &ok);
+	if (!ok) return NULL;
+	int rc = cb_queue_push(ctx, start, n, &first, tmo);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_create_bigint_int64(env, first, &out));
+	return out;
+}
+
+static napi_value
+QueueCancel(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2, n = 0; napi_value argv[2]; bool ok;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 2) {
+		napi_throw_type_error(env, NULL, "queueCancel(ctx, tickets)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	const int64_t *tickets = typed(env, argv[1], napi_bigint64_array, 0, false, "tickets: BigInt64Array expected", &n, &ok);
+	if (!ok) return NULL;
+	int rc = cb_queue_cancel(ctx, tickets, n);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+QueueExpire(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2]; int64_t nw;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 2) {
+		napi_throw_type_error(env, NULL, "queueExpire(ctx, nowNs)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	if (!big(env, argv[1], &nw)) return NULL;
+	int rc = cb_queue_expire(ctx, nw);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+QueueIdle(napi_env env, napi_callback_info info)
+{
+	size_t argc = 3; napi_value argv[3]; int64_t nw; uint64_t k;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 3) {
+		napi_throw_type_error(env, NULL, "queueIdle(ctx, nowNs, k)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	if (!big(env, argv[1], &nw) || !count_arg(env, argv[2], "k: a non-negative integer expected", &k)) return NULL;
+	int rc = cb_queue_idle(ctx, nw, k);
+	return rc == CB_OK ? NULL : throw_cb(env, ctx, rc);
+}
+
+static napi_value
+QueueTrimIdle(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2; napi_value argv[2], out; uint64_t k, removed = 0;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 2) {
+		napi_throw_type_error(env, NULL, "queueTrimIdle(ctx, k)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	if (!count_arg(env, argv[1], "k: a non-negative integer expected", &k)) return NULL;
+	int rc = cb_queue_trim_idle(ctx, k, &removed);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_create_double(env, (double)removed, &out));
+	return out;
+}
+
+/* queueResults(ctx, out: BigInt64Array) -> number of (ticket, code, slot) records written into `out`;
+ * `out` must have room for every waiting record (3 elements each; queueInfo().nResults), else CB_EINVAL */
+static napi_value
+QueueResults(napi_env env, napi_callback_info info)
+{
+	size_t argc = 2, len = 0, n = 0; napi_value argv[2], out; bool ok;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 2) {
+		napi_throw_type_error(env, NULL, "queueResults(ctx, out)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	int64_t *triples = typed(env, argv[1], napi_bigint64_array, 3, false, "out: BigInt64Array of 3 elements per record expected", &len, &ok);
+	if (!ok) return NULL;
+	int rc = cb_queue_results(ctx, triples, len / 3, &n);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_create_double(env, (double)n, &out));
+	return out;
+}
+
+static napi_value
+QueueInfo(napi_env env, napi_callback_info info)
+{
+	size_t argc = 1; napi_value argv[1], out, v; cb_queue_info qi;
+	NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+	if (argc < 1) {
+		napi_throw_type_error(env, NULL, "queueInfo(ctx)");
+		return NULL;
+	}
+	GET_CTX(ctx, env, argv[0]);
+	int rc = cb_queue_info_get(ctx, &qi);
+	if (rc != CB_OK) return throw_cb(env, ctx, rc);
+	NAPI_CALL(env, napi_create_object(env, &out));
+	/* counters are exact as Numbers below 2^53 (the reference's are Numbers, lib/pool.js:269-283) */
+	napi_create_double(env, (double)qi.claim, &v);            napi_set_named_property(env, out, "claim", v);
+	napi_create_double(env, (double)qi.queued_claim, &v);     napi_set_named_property(env, out, "queuedClaim", v);
+	napi_create_double(env, (double)qi.max_claim_queue, &v);  napi_set_named_property(env, out, "maxClaimQueue", v);
+	napi_create_double(env, (double)qi.claim_timeout, &v);    napi_set_named_property(env, out, "claimTimeout", v);
+	napi_create_double(env, (double)qi.idle, &v);             napi_set_named_property(env, out, "idle", v);
+	napi_create_double(env, (double)(qi.tail - qi.head), &v); napi_set_named_property(env, out, "queued", v);
+	napi_create_double(env, (double)qi.n_results, &v);        napi_set_named_property(env, out, "nResults", v);
+	return out;
+}
+
 static napi_value
 Init(napi_env env, napi_value exports)
 {
@@ -353,6 +523,14 @@ Init(napi_env env, napi_value exports)
 		{ "reshuffle", NULL, Reshuffle, NULL, NULL, NULL, napi_default, NULL },
 		{ "planRebalance", NULL, PlanRebalance, NULL, NULL, NULL, napi_default, NULL },
 		{ "shuffle", NULL, Shuffle, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueCreate", NULL, QueueCreate, NULL, NULL, NULL, napi_default, NULL },
+		{ "queuePush", NULL, QueuePush, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueCancel", NULL, QueueCancel, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueExpire", NULL, QueueExpire, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueIdle", NULL, QueueIdle, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueTrimIdle", NULL, QueueTrimIdle, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueResults", NULL, QueueResults, NULL, NULL, NULL, napi_default, NULL },
+		{ "queueInfo", NULL, QueueInfo, NULL, NULL, NULL, napi_default, NULL },
 	};
 	napi_define_properties(env, exports, sizeof (d) / sizeof (d[0]), d);
 	return exports;

@@ -54,6 +54,7 @@ napi_status napi_get_value_double(napi_env env, napi_value value, double *result
 napi_status napi_get_value_int32(napi_env env, napi_value value, int32_t *result);
 napi_status napi_get_value_bool(napi_env env, napi_value value, bool *result);
 napi_status napi_get_value_bigint_int64(napi_env env, napi_value value, int64_t *result, bool *lossless);
+napi_status napi_create_bigint_int64(napi_env env, int64_t value, napi_value *result);
 napi_status napi_create_external(napi_env env, void *data, napi_finalize finalize_cb, void *finalize_hint,
     napi_value *result);
 napi_status napi_get_value_external(napi_env env, napi_value value, void **result);

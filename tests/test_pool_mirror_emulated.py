@@ -32,7 +32,8 @@ def cb():
         o["context"] = EmuContext()
         return real.ConnectionPool(o)
     return types.SimpleNamespace(ConnectionPool=pool, ClaimTimeoutError=real.ClaimTimeoutError,
-                                 ClaimHandleMisusedError=real.ClaimHandleMisusedError)
+                                 ClaimHandleMisusedError=real.ClaimHandleMisusedError,
+                                 PoolStoppingError=real.PoolStoppingError)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
@@ -96,3 +97,16 @@ def test_sizing_loop_emulated(cb):
     import test_gpu_zz_sizing as Z
     plans = Z.sizing_scenario(cb)
     assert plans[0]["target"] == 2 and not plans[0]["clamped"]  # idle pool: busy 0 + spares 2; the filter still remembers less
+
+
+def test_reference_codel_tests_emulated(cb):
+    """test/codel.test.js restated (tests/test_gpu_zz_codel_load_runs.py): 'implicit high timeout', and one load run
+    shortened to 1.5 s of claims (CB_EMU_FULL=1: the reference's 5 s, targets 300 and 1000 ms)."""
+    import test_gpu_zz_codel_load_runs as Z
+    Z.implicit_high_timeout(cb)
+    if FULL:
+        for delay in (300, 1000):
+            Z.load_run(cb, delay)
+    else:
+        res = Z.load_run(cb, 300, claim_ms=1500)
+        assert res["count"] == 750
