@@ -32,6 +32,9 @@ class Queue(object):
     def isEmpty(self):  # lib/queue.js:46-48
         return self.q_len == 0
 
+    def peek(self):  # lib/queue.js:49-51: the SENTINEL's value, i.e. always null
+        return None
+
     def push(self, v):  # lib/queue.js:52-56
         n = QueueNode(self, v)
         self._nodes.append(n)

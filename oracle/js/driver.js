@@ -16,6 +16,8 @@
  *   cb_lpf_run      the pool's 5 Hz sampler body        lib/pool.js:251-258 (setInterval closure)
  *                   and _rebalance's target sizing     lib/pool.js:556-587, around the reference's
  *                   own FIRFilter / LP_TAPS            lib/pool.js:44-100 (verbatim, module ./pool_lpf)
+ *   cb_queue_ops    a script of push / shift / node.remove / forEach / peek on the reference's own
+ *                   Queue (lib/queue.js, verbatim): pins the host mirror node-cueball_b200/queue.py
  *   cb_build_slots  preference-list random insertion   lib/pool.js:285-291
  *                   (Math.random replaced by injected draws) then the
  *                   reference's own planRebalance      lib/utils.js:239-393
@@ -434,4 +436,48 @@ function cb_lpf_run(job) {
 	var taps = [];
 	for (var i = 0; i < pool_lpf.LP_TAPS.length; i++) taps.push(pool_lpf.LP_TAPS[i]);
 	return { taps: taps, out: out, lp_int: pool_lpf.LP_INT };
+}
+
+/*
+ * A script of operations on the reference's own Queue (lib/queue.js, verbatim).  op[i], arg[i]:
+ *   0 push(arg)            1 shift() (skipped by the harness when the queue is empty: the reference has no guard,
+ *                            SURVEY A.3 quirk 7)
+ *   2 node.remove() of the arg-th pushed node, if it is still linked
+ *   3 forEach: collect the values in order, removing (from inside the callback) every node whose value is
+ *     divisible by arg
+ *   4 peek()
+ * Returns per op [result, length, isEmpty]: result = the shifted value / 1 when a remove happened / the number of
+ * values visited plus 1000 x the number removed / -1 for a null peek / -2 for a skipped op.
+ */
+function cb_queue_ops(op, arg) {
+	var q = new Queue(), nodes = [], linked = [], out = [], vals;
+	for (var i = 0; i < op.length; i++) {
+		var r = -2, a = arg[i];
+		if (op[i] === 0) {
+			nodes.push(q.push(a)); linked.push(true); r = nodes.length - 1;
+		} else if (op[i] === 1) {
+			if (q.length > 0) {
+				r = q.shift();
+				for (var k = 0; k < nodes.length; k++)
+					if (linked[k] && nodes[k].n_value === r && nodes[k].n_next === null) linked[k] = false;
+			}
+		} else if (op[i] === 2) {
+			if (a < nodes.length && linked[a]) { nodes[a].remove(); linked[a] = false; r = 1; }
+		} else if (op[i] === 3) {
+			vals = 0; var removed = 0;
+			q.forEach(function (v, n) {
+				vals++;
+				if (a > 0 && v % a === 0) {
+					n.remove(); removed++;
+					for (var k = 0; k < nodes.length; k++) if (nodes[k] === n) linked[k] = false;
+				}
+			});
+			r = vals + 1000 * removed;
+		} else if (op[i] === 4) {
+			var p = q.peek();
+			r = (p === null) ? -1 : p;
+		}
+		out.push(r, q.length, q.isEmpty() ? 1 : 0);
+	}
+	return out;
 }

@@ -126,3 +126,9 @@ def lpf_run(spares, mx, ty, a, b, c, d):
     expr = ("(function(){var job=%s; job.ty=__read_array(); job.a=__read_array(); job.b=__read_array(); "
             "job.c=__read_array(); job.d=__read_array(); return cb_lpf_run(job);})()" % _lit(job))
     return call(expr, arrays=[ty, a, b, c, d])
+
+
+def queue_ops(op, arg):
+    """A script of operations on the reference's own Queue (cb_queue_ops in driver.js): rows of
+    (result, length, isEmpty)."""
+    return call("cb_queue_ops(__read_array(),__read_array())", arrays=[op, arg])

@@ -186,3 +186,23 @@ def gen_lpf_events(seed, n_ev, peak):
         else:
             ty.append(1); a.append(conns); b.append(idle); c.append(initq); d.append(waiters)  # noqa: E702
     return ty, a, b, c, d
+
+
+def gen_queue_ops(seed, n_ops):
+    """A script for cb_queue_ops / the Queue mirror: unique pushed values, shifts, removals of nodes that may or may
+    not still be linked, forEach passes that remove from inside the callback, peeks."""
+    rng = np.random.RandomState(seed)
+    op, arg, pushed = [], [], 0
+    for _ in range(n_ops):
+        r = rng.rand()
+        if r < 0.45:
+            op.append(0); arg.append(pushed + 1); pushed += 1                    # noqa: E702
+        elif r < 0.70:
+            op.append(1); arg.append(0)                                          # noqa: E702
+        elif r < 0.85:
+            op.append(2); arg.append(int(rng.randint(0, max(pushed, 1))))        # noqa: E702
+        elif r < 0.95:
+            op.append(3); arg.append(int(rng.choice([0, 2, 3, 7])))              # noqa: E702
+        else:
+            op.append(4); arg.append(0)                                          # noqa: E702
+    return op, arg
