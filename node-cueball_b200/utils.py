@@ -61,7 +61,7 @@ def assertClaimDelay(delay):
     """lib/utils.js:188-195"""
     if delay is None:
         return
-    if not isinstance(delay, (int, float)) or delay != delay or delay in (float("inf"), float("-inf")):
+    if isinstance(delay, bool) or not isinstance(delay, (int, float)) or delay != delay or delay in (float("inf"), float("-inf")):
         raise AssertionError("options.targetClaimDelay (finite) is required")
     if not delay > 0:
         raise AssertionError("options.targetClaimDelay > 0")

@@ -58,3 +58,24 @@ def test_shift_on_an_empty_queue_is_the_callers_bug():
     from cueball_b200 import Queue
     with pytest.raises(IndexError):
         Queue().shift()
+
+
+# utils.assertClaimDelay (lib/utils.js:188-195): outcomes recorded from the reference's own function under the
+# oracle engine (with the engine-side assert-plus stand-in of oracle/js/shim.js)
+CLAIM_DELAY_CASES = [("undefined", None, "ok"), ("null", None, "ok"), ("5", 5, "ok"), ("1", 1, "ok"), ("0", 0, "throws"),
+                     ("-1", -1, "throws"), ("2.5", 2.5, "throws"), ("NaN", float("nan"), "throws"),
+                     ("Infinity", float("inf"), "throws"), ("'5'", "5", "throws"), ("true", True, "throws"),
+                     ("1e15", 1e15, "ok"), ("300", 300, "ok")]
+
+
+@pytest.mark.parametrize("js,py,want", CLAIM_DELAY_CASES, ids=[c[0] for c in CLAIM_DELAY_CASES])
+def test_assert_claim_delay(js, py, want):
+    from cueball_b200 import assertClaimDelay
+    if ref.available():
+        got = ref.call("(function(){try{utils.assertClaimDelay(%s);return 'ok';}catch(e){return 'throws';}})()" % js)
+        assert got == want
+    if want == "ok":
+        assertClaimDelay(py)
+    else:
+        with pytest.raises(AssertionError):
+            assertClaimDelay(py)
