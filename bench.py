@@ -37,9 +37,10 @@ from CUDA events recorded around each kernel on the launching stream in a separa
 reference's own JS) on one host core, on the full step size.
 
 --impl reference times the reference's OWN JavaScript (lib/queue.js + lib/codel.js verbatim) under
-the SpiderMonkey engine vendored in the reference tree (oracle/_ref), one core -- the path is a
-sequential state machine and Node itself is single threaded -- on a bounded sample of the same
-workload (`config.reference_sample_claims_per_step`, the same key in both arms).
+the SpiderMonkey engine vendored in the reference tree (oracle/_ref): one pool's drain is a sequential
+state machine on one core (Node itself is single threaded); with --gpus N the job is N independent
+pools, so N reference processes run at once on N cores.  Each pool drains a bounded sample of the same
+workload per step (`config.reference_sample_claims_per_step`, the same key in both arms).
 """
 import argparse
 import gc
@@ -233,33 +234,45 @@ def make_trace(wl, total_claims, rank, dev, salt=0):
 
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args, wl):
-    """The reference's own CPU implementation of the path on this box's host cores."""
+    """The reference's own CPU implementation of the path on this box's host cores.  One pool's drain is a
+    sequential state machine on one thread (Node itself is single threaded); the --gpus N job is N independent pools
+    (a queue segment per GPU), whose CPU counterpart is N reference processes, one pool each, running at once on N cores."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from oracle import oracle as O
     from oracle import ref
     w = WORKLOADS[wl]
     n = REF_SAMPLE[wl]
+    pools = max(1, args.gpus)
     params = dict(t0=T0_NS, de=DE_NS, target_ns=TARGET_MS * 1_000_000, unit=w["gen"].get("unit", 1 << 16),
                   start_overloaded=False, all_overloaded_from=w["gen"].get("all_overloaded_from", -1))
     times, decided = [], 0
     kind = "reference" if ref.available() else "port"
     parts = max(1, n // REF_QUEUE)
     m = n // parts
-    for step in range(args.warmup + args.steps):
+
+    def one_pool(step, pool):
+        """One pool's sample of this step: `parts` consecutive queues of m pending claims; seconds in the drain loop."""
         dt = 0.0
         for part in range(parts):
-            seed = tracegen.SEED + step * parts + part
+            seed = tracegen.SEED + (step * pools + pool) * parts + part
             if kind == "reference":
-                r = ref.bench(seed, m, params, TARGET_MS, w["S"])
+                r = ref.bench(seed, m, params, TARGET_MS, w["S"])  # its own OS process (the engine's shell)
                 dt += r["drain_ms"] / 1e3
             else:
                 s, nw = tracegen.gen_trace(m, seed=seed, **{k: v for k, v in params.items()})
                 cd = O.new_codel(TARGET_MS)
                 t0 = time.perf_counter()
-                O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)
+                O.drain(cd, s, nw, nslots=w["S"], variant="list", want_out=True)  # ctypes releases the GIL
                 dt += time.perf_counter() - t0
-        if step >= args.warmup:
-            times.append(max(dt, 1e-9))
-            decided += m * parts
+        return dt
+
+    with ThreadPoolExecutor(max_workers=pools) as ex:
+        for step in range(args.warmup + args.steps):
+            dts = list(ex.map(lambda p: one_pool(step, p), range(pools)))
+            if step >= args.warmup:
+                times.append(max(max(dts), 1e-9))  # the pools run at once: the step takes as long as the slowest
+                decided += m * parts * pools
     total = sum(times)
     value = decided / total
     # context for the ratio: SpiderMonkey 1.7 is an interpreter from 2007; a JIT-compiling engine (V8 under
@@ -279,9 +292,10 @@ def run_reference(args, wl):
         port = nfull / best
     except Exception:
         pass
-    sample = ("%d claims per step of the %s trace spec as %d queue(s) of %d pending claims (same generator, JS side; the "
-              "engine's heap holds one such queue; the CUDA arm's step is %d claims); timed: the drain loop "
-              "lib/pool.js:733-753 = Queue.shift + ControlledDelay.overloaded per claim" % (m * parts, wl, parts, m, w["n"]))
+    sample = ("%d pool(s) at once, one OS process and core each; per pool and step %d claims of the %s trace spec as %d "
+              "queue(s) of %d pending claims (same generator, JS side; the engine's heap holds one such queue; the CUDA "
+              "arm's step is %d claims per GPU); timed: the drain loop lib/pool.js:733-753 = Queue.shift + "
+              "ControlledDelay.overloaded per claim, the slowest pool of each step" % (pools, m * parts, wl, parts, m, w["n"]))
     line = {
         "impl": "reference", "metric": METRIC,
         "value": value, "unit": "claims/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -290,7 +304,8 @@ def run_reference(args, wl):
         "config": workload_config(wl, args.gpus),
         "engine": ("reference lib/queue.js+lib/codel.js verbatim under SpiderMonkey 1.7 (vendored in the reference "
                    "tree; Node.js is not installed)" if kind == "reference" else "C restatement (oracle/), linked-list queue"),
-        "cpu_baseline": {"value": value, "unit": "claims/s", "cores": 1, "kind": kind, "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "claims/s", "cores": pools, "host_cpus": os.cpu_count(), "kind": kind,
+                         "sample": sample,
                          "c_restatement_linked_list_claims_per_s": port,
                          "c_restatement_sample": "one full step of the CUDA arm (%d claims), linked-list queue, 1 core" % min(w["n"], 1 << 24)},
         "e2e": {"value": value, "unit": "claims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
