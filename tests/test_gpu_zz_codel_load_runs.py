@@ -11,8 +11,9 @@ so on top of the reference's assertions the event script the run generated (clai
 replayed through the pool-model oracle (cbo_pool_sim, pinned to the reference's lib/codel.js + lib/queue.js)
 and every (ticket, code, slot) record and counter must match exactly.
 
-(The file sorts last among the GPU tests on purpose: it was written after the round's GPU time was spent; the
-same scenarios run on the CPU through the emulated context -- tests/test_pool_mirror_emulated.py.)"""
+(The file sorts last among the GPU tests: it was written after the round's last full GPU session; its scenarios ran
+green on a B200 through tools/gpu_zz_quick.py -- profiles/r02_late_gpu_tests.jsonl -- and run on the CPU through the
+emulated context, tests/test_pool_mirror_emulated.py.)"""
 import heapq
 
 import numpy as np

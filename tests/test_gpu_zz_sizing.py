@@ -4,8 +4,9 @@ host mirror of the reference's arithmetic (pinned to the reference's own FIRFilt
 tests/test_lpf_golden.py), the plan from the device's planRebalance (cb_plan_rebalance).  Every step is
 compared with the oracle (cbo_lpf_run + cbo_plan_rebalance) driven with the same occupancy.
 
-(The file sorts last among the GPU tests on purpose: it was written after the round's GPU time was spent and
-has only run on the CPU, through the emulated context -- tests/test_pool_mirror_emulated.py.)"""
+(The file sorts last among the GPU tests: it was written after the round's last full GPU session; its scenarios ran
+green on a B200 through tools/gpu_zz_quick.py -- profiles/r02_late_gpu_tests.jsonl -- and run on the CPU through the
+emulated context, tests/test_pool_mirror_emulated.py.)"""
 import numpy as np
 import pytest
 
