@@ -172,6 +172,8 @@ class ConnectionPool(object):
     def __init__(self, options):
         assertClaimDelay(options.get("targetClaimDelay"))
         self.p_max = int(options.get("maximum", 0))
+        self.p_uuid = options.get("uuid")        # lib/pool.js:137: named in the errors' messages
+        self.p_domain = options.get("domain")
         self._clock = options.get("clock") or time.monotonic_ns
         self._random = options.get("random") or np.random.random
         self._ctx = options.get("context") or Context(options.get("device", 0))
@@ -202,6 +204,7 @@ class ConnectionPool(object):
         self.records = []      # every (ticket, code, slot) the device produced, in order (observability/tests)
         # the pool without CoDel: a plain host FIFO (nothing to accelerate)
         self._host_waiters = []
+        self._host_started = False
         self._host_idle = 0
         self._host_counters = {}
         self._host_cursor = 0
@@ -354,7 +357,11 @@ class ConnectionPool(object):
         # new table that no claimed handle holds are idle.  New slots turn idle as an event (they
         # drain waiters, lib/pool.js:715); slots that went away leave the idle queue.
         if self.p_codel is None:
-            self._host_idle = max(0, new_n - self._claimed)
+            if self._initial_idle is not None and not self._host_started:
+                self._host_idle = min(int(self._initial_idle), new_n)  # the rest connect later: slots_idle()
+            else:
+                self._host_idle = max(0, new_n - self._claimed)
+            self._host_started = True
             self._host_drain(self._clock())
             return
         if not self._queue_ready:
@@ -376,7 +383,7 @@ class ConnectionPool(object):
             raise Exception("options.timeout not allowed when targetDelay has been set")  # :875-878
         if self._stopping:  # :889-899
             if cb:
-                cb(PoolStoppingError(), None, None)
+                cb(PoolStoppingError(self), None, None)
             return {"cancel": lambda: None}
         now = self._clock()
         if self.p_codel is None:
@@ -385,7 +392,7 @@ class ConnectionPool(object):
             handle = CueBallClaimHandle(self, cb, now, float("inf"), -1)
             handle.ch_state = "failed"
             if cb:
-                cb(NoBackendsError(), None, None)
+                cb(NoBackendsError(self), None, None)
             return handle
         self._ensure_queue(len(self._slot_backend))
         # one kernel: timers that came due, getMaxIdle (:880), idle slot first (:934-951), else enqueue (:960-965)
@@ -464,7 +471,7 @@ class ConnectionPool(object):
         if options.get("errorOnEmpty") and len(self.p_keys) < 1:
             handle.ch_state = "failed"
             if cb:
-                cb(NoBackendsError(), None, None)
+                cb(NoBackendsError(self), None, None)
             return handle
         self._host_waiters.append(handle)
         if self._host_counters.get("max-claim-queue", 0) < len(self._host_waiters):

@@ -33,7 +33,7 @@ def cb():
         return real.ConnectionPool(o)
     return types.SimpleNamespace(ConnectionPool=pool, ClaimTimeoutError=real.ClaimTimeoutError,
                                  ClaimHandleMisusedError=real.ClaimHandleMisusedError,
-                                 PoolStoppingError=real.PoolStoppingError)
+                                 PoolStoppingError=real.PoolStoppingError, NoBackendsError=real.NoBackendsError)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
@@ -110,3 +110,83 @@ def test_reference_codel_tests_emulated(cb):
     else:
         res = Z.load_run(cb, 300, claim_ms=1500)
         assert res["count"] == 750
+
+
+# ---------------------------------------------------------------- test/pool.test.js, the claim-queue parts, restated
+def _plain_pool(cb, clock, **kw):
+    """A pool WITHOUT targetClaimDelay, as test/pool.test.js makes them (spares 2, maximum 2 unless given): no CoDel,
+    per-claim options.timeout; the mirror runs it as a plain host FIFO."""
+    opts = {"maximum": 2, "spares": 2, "clock": lambda: clock["now"], "random": lambda: 0.5}
+    opts.update(kw)
+    return cb.ConnectionPool(opts)
+
+
+def test_empty_pool(cb):
+    """test/pool.test.js:106-134: errorOnEmpty -> NoBackendsError at once; a plain claim times out."""
+    import cueball_b200 as real
+    clock = {"now": 10 ** 9}
+    pool = _plain_pool(cb, clock, maximum=4)
+    errs = []
+    pool.claim({"errorOnEmpty": True}, lambda e, h, c: errs.append(e))
+    assert isinstance(errs[0], real.NoBackendsError) and "no backend" in str(errs[0]).lower()
+    pool.claim({"timeout": 100}, lambda e, h, c: errs.append(e))
+    assert len(errs) == 1
+    clock["now"] += 100 * 1_000_000
+    pool.expire()
+    assert isinstance(errs[1], cb.ClaimTimeoutError) and "timed out" in str(errs[1]).lower()
+
+
+def test_pool_with_one_backend(cb):
+    """test/pool.test.js:136-203: claims time out while the two connections are still connecting, succeed once
+    they are up, and the third concurrent claim times out again."""
+    clock = {"now": 10 ** 9}
+    pool = _plain_pool(cb, clock, initialIdleSlots=0)
+    pool.on_resolver_added("b1", {})
+    assert pool.getStats()["totalConnections"] == 2
+    log = []
+    pool.claim({"timeout": 100}, lambda e, h, c: log.append(("first", e, h, c)))
+    clock["now"] += 100 * 1_000_000
+    pool.expire()
+    assert isinstance(log[0][1], cb.ClaimTimeoutError)
+    pool.slots_idle(2)                                   # c.connect() on both
+    pool.claim({"timeout": 100}, lambda e, h, c: log.append(("again", e, h, c)))
+    pool.claim({"timeout": 100}, lambda e, h, c: log.append(("once more", e, h, c)))
+    assert [x[1] for x in log[1:]] == [None, None] and all(x[2] is not None and x[3] is not None for x in log[1:])
+    assert sorted(x[3]["slot"] for x in log[1:]) == [0, 1]
+    pool.claim({"timeout": 100}, lambda e, h, c: log.append(("empty", e, h, c)))
+    assert len(log) == 3
+    clock["now"] += 100 * 1_000_000
+    pool.expire()
+    assert isinstance(log[3][1], cb.ClaimTimeoutError)
+
+
+def test_claim_cancellation(cb):
+    """test/pool.test.js:727-780: a cancelled claim's callback never fires -- not when a slot turns up, not when
+    its timeout would have come due."""
+    clock = {"now": 10 ** 9}
+    pool = _plain_pool(cb, clock, initialIdleSlots=0)
+    pool.on_resolver_added("b1", {})
+    fired = []
+    claim = pool.claim({"timeout": 100}, lambda e, h, c: fired.append(e))
+    claim.cancel()
+    pool.slots_idle(2)
+    clock["now"] += 150 * 1_000_000
+    pool.expire()
+    assert fired == [] and claim.isInState("cancelled")
+    assert pool.getStats()["idleConnections"] == 2
+    pool.stop()
+
+
+def test_getstats_shape_issue_132(cb):
+    """test/pool.test.js:902-966 (cueball#132): five keys; zeros before a backend exists, then 2 / 2 / 0 / 0."""
+    clock = {"now": 10 ** 9}
+    pool = _plain_pool(cb, clock)
+    s = pool.getStats()
+    assert isinstance(s, dict) and len(s) == 5 and isinstance(s["counters"], dict)
+    assert (s["totalConnections"], s["idleConnections"], s["pendingConnections"], s["waiterCount"]) == (0, 0, 0, 0)
+    pool.on_resolver_added("b1", {})
+    s = pool.getStats()
+    assert len(s) == 5 and isinstance(s["counters"], dict)
+    assert (s["totalConnections"], s["idleConnections"], s["pendingConnections"], s["waiterCount"]) == (2, 2, 0, 0)
+    assert pool.toKangSnapshot()["connections"] == {"b1": {"idle": 2}}
+    pool.stop()
