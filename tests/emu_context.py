@@ -99,6 +99,17 @@ class EmuContext(object):
         self.launches += 1
         return want[:B].copy(), add[:na[0]].copy(), list(zip(rk[:nr[0]].tolist(), ro[:nr[0]].tolist()))
 
+    def shuffle(self, arr, us):
+        """cb_shuffle: utils.shuffle of an int32 array with injected draws (shuffle_kernel)."""
+        a = np.array(arr, dtype=np.int32)
+        us = np.ascontiguousarray(us, dtype=np.float64)
+        if a.shape[0] < 2:
+            return a
+        out = np.zeros_like(a)
+        self.T.emu_shuffle(a.ctypes.data, out.ctypes.data, us.ctypes.data, a.shape[0], 3)
+        self.launches += 1
+        return out
+
     def backends_get(self):
         return self.keys[:int(self.nkeys[0])].copy(), self.slot_backend.copy()
 
