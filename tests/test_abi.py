@@ -65,3 +65,11 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 assert "oracle" not in src.replace("no reference oracle", ""), fn
+
+
+def test_every_exported_entry_point_is_placed_in_integration_md():
+    """INTEGRATION.md's table says which reference interface each C-ABI entry point replaces: none may be missing."""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        doc = f.read()
+    missing = [n for n in declared_symbols() if not re.search(r"\b%s\b" % n, doc)]
+    assert not missing, missing
