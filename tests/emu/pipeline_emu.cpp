@@ -246,6 +246,32 @@ int emu_pipe_admit(EmuPipe *e, const long long *start, const long long *now, con
     unsigned long long n, int nslots, unsigned char *decision, int *slot, unsigned long long *info) {
 	return pipe_admit<true>(e, start, now, flags, n, nslots, decision, slot, info);
 }
+/* the scalar entry points (cb_codel_overloaded / _ms / _empty / _max_idle): one-thread kernels on the context's state */
+int emu_pipe_overloaded(EmuPipe *e, long long start_ns, long long now_ns) {
+	int out = 0;
+	DevState *g = &e->g;
+	run_grid(1, 1, [&] { overloaded_one_kernel(g, start_ns, now_ns, &out); });
+	e->fseed = 1; /* the state changed outside the batch chain */
+	return out;
+}
+int emu_pipe_overloaded_ms(EmuPipe *e, double start_ms, double now_ms) {
+	int out = 0;
+	DevState *g = &e->g;
+	run_grid(1, 1, [&] { overloaded_one_ms_kernel(g, start_ms, now_ms, &out); });
+	e->fseed = 1;
+	return out;
+}
+void emu_pipe_empty(EmuPipe *e, long long now_ns) {
+	DevState *g = &e->g;
+	run_grid(1, 1, [&] { empty_kernel(g, now_ns); });
+	e->fseed = 1;
+}
+double emu_pipe_max_idle(EmuPipe *e, long long now_ns) {
+	double out = 0.0;
+	const DevState *g = &e->g;
+	run_grid(1, 1, [&] { max_idle_kernel(g, now_ns, &out); });
+	return out;
+}
 /* the _ms entry points: clocks already in double milliseconds */
 int emu_pipe_admit_ms(EmuPipe *e, const double *start, const double *now, const unsigned char *flags,
     unsigned long long n, int nslots, unsigned char *decision, int *slot, unsigned long long *info) {

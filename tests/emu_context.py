@@ -15,6 +15,7 @@ import types
 
 import numpy as np
 
+import test_pipeline_kernels_emulated as TP
 import test_queue_kernels_emulated as TQ
 import test_topology_kernels_emulated as TT
 
@@ -30,6 +31,7 @@ class EmuContext(object):
         self.T = TT.load_emu()
         self.target = None
         self.q = None
+        self.pipe = None
         self.keys = np.zeros(self.KEY_CAP, np.int32)
         self.nkeys = np.zeros(1, np.int32)
         self.want_slots = 0
@@ -38,7 +40,82 @@ class EmuContext(object):
 
     # ------------------------------------------------------------------ CoDel
     def codel_init(self, target_ms):
+        from cueball_b200.utils import assertClaimDelay
+        assertClaimDelay(target_ms)  # cb_codel_init returns CB_EINVAL for what utils.assertClaimDelay rejects
         self.target = float(target_ms)
+        if getattr(self, "pipe", None):
+            self.P.emu_pipe_destroy(self.pipe)
+        self.pipe = None
+
+    def _pipe(self):
+        """The scalar and batch entry points run on the emulated batch pipeline (tests/emu/pipeline_emu.cpp).  In the
+        library they share ONE DevState with the queue; the two emulation libraries each keep their own, so one
+        emulated context serves either the queue events or the scalar/batch calls, not a mix."""
+        assert self.q is None, "this emulated context already serves the queue (separate state)"
+        if self.pipe is None:
+            self.P = TP.load_emu()
+            self.P.emu_pipe_overloaded.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong]
+            self.P.emu_pipe_overloaded_ms.argtypes = [C.c_void_p, C.c_double, C.c_double]
+            self.P.emu_pipe_empty.argtypes = [C.c_void_p, C.c_longlong]
+            self.P.emu_pipe_max_idle.argtypes = [C.c_void_p, C.c_longlong]
+            self.P.emu_pipe_max_idle.restype = C.c_double
+            self.pipe = self.P.emu_pipe_create(self.target, 0)
+        return self.pipe
+
+    def overloaded(self, start_ns, now_ns):
+        p = self._pipe()
+        self.launches += 1
+        return bool(self.P.emu_pipe_overloaded(p, int(start_ns), int(now_ns)))
+
+    def overloaded_ms(self, start_ms, now_ms):
+        p = self._pipe()
+        self.launches += 1
+        return bool(self.P.emu_pipe_overloaded_ms(p, float(start_ms), float(now_ms)))
+
+    def codel_empty(self, now_ns):
+        p = self._pipe()
+        self.launches += 1
+        self.P.emu_pipe_empty(p, int(now_ns))
+
+    def max_idle(self, now_ns):
+        p = self._pipe()
+        self.launches += 1
+        return float(self.P.emu_pipe_max_idle(p, int(now_ns)))
+
+    def get_state(self):
+        from cueball_b200 import _native as N
+        p = self._pipe()
+        d, cursor, _, _ = TP.get_state(self.P, p)
+        st = N.CodelState()
+        st.target_ms, st.count, st.drop_next, st.first_above_time = self.target, int(d["count"]), d["drop_next"], d["first_above_time"]
+        st.dropping = 1 if d["dropping"] else 0
+        st.has_last_empty = 0 if d["last_empty"] is None else 1
+        st.last_empty = 0.0 if d["last_empty"] is None else d["last_empty"]
+        self._cursor = cursor
+        return st
+
+    def set_state(self, d):
+        le = d.get("last_empty")
+        p = self._pipe()
+        self.P.emu_pipe_set_state(p, float(d["first_above_time"]), float(d["drop_next"]), int(d["count"]),
+                                  1 if d["dropping"] else 0, 0 if le is None else 1, 0.0 if le is None else float(le), 0)
+
+    def admit_batch(self, start, now, flags=None, **kw):
+        """cb_admit_batch / cb_admit_batch_ms on host arrays: (decision, slot, None, stats)."""
+        start, now = TP.aligned(np.ascontiguousarray(start)), TP.aligned(np.ascontiguousarray(now))
+        n = start.shape[0]
+        dec, slot = TP.aligned(np.zeros(n, np.uint8)), TP.aligned(np.zeros(n, np.int32))
+        info = (C.c_uint64 * 4)()
+        f = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        p = self._pipe()
+        fn = self.P.emu_pipe_admit_ms if start.dtype == np.float64 else self.P.emu_pipe_admit
+        fn(p, start.ctypes.data, now.ctypes.data, None if f is None else f.ctypes.data, n,
+           len(self.slot_backend), dec.ctypes.data, slot.ctypes.data, info)
+        self.launches += 3
+        st = types.SimpleNamespace(n=n, drops=int((dec == 1).sum()), admits=int((dec == 0).sum()),
+                                   skipped=int((dec == 2).sum()), path=int(info[0]), n_events=int(info[1]),
+                                   n_intervals=int(info[2]), state=self.get_state())
+        return dec.copy(), slot.copy(), None, st
 
     # --------------------------------------------------------------- topology
     def _rebuild(self):
@@ -116,6 +193,7 @@ class EmuContext(object):
     # ------------------------------------------------------ pending-claim queue
     def queue_create(self, capacity, result_capacity=None, idle_slots=0):
         assert self.target is not None, "cb_codel_init has not been called"
+        assert self.pipe is None, "this emulated context already serves the scalar/batch calls (separate state)"
         cap = 1024
         while cap < capacity:
             cap <<= 1
