@@ -3,6 +3,7 @@
  * (64-thread CTA via CB_TOPO_TPB) behind plain C functions.  TEST INFRASTRUCTURE. */
 #define CB_TOPO_TPB 64
 #include "../../node-cueball_b200/csrc/cb_topology.cuh"
+#include "../../node-cueball_b200/csrc/cb_resolver.cuh"
 
 #include <vector>
 
@@ -42,6 +43,16 @@ void emu_shuffle(const int32_t *in, int32_t *out, const double *us, int n, int c
 	for (unsigned b = 0; b < (unsigned)ctas; b++) {
 		blockIdx.x = b;
 		emu::launch(TOPO_TPB, [&] { shuffle_kernel(in, out, us, n); });
+	}
+}
+/* srvKey of n messages (csrc/cb_resolver.cuh: SHA-1 + base64, one thread per message), 128-thread CTAs as
+ * cb_srv_keys launches them */
+void emu_srv_keys(const unsigned char *msgs, const unsigned int *offs, int n, char *keys) {
+	const unsigned ctas = (unsigned)((n + 127) / 128);
+	gridDim.x = ctas;
+	for (unsigned b = 0; b < ctas; b++) {
+		blockIdx.x = b;
+		emu::launch(128, [&] { srv_key_kernel(msgs, offs, n, keys); });
 	}
 }
 void emu_slot_table(const int32_t *keys, const int32_t *add, const int32_t *n_add, int32_t *slot_backend, int cap,

@@ -23,7 +23,8 @@ VP = C.c_void_p
 def load_emu():
     srcs = [os.path.join(EMU, "topology_emu.cpp"), os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "cuda_emu.h"),
             os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_topology.cuh"),
-            os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_device.cuh")]
+            os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_device.cuh"),
+            os.path.join(util.ROOT, "node-cueball_b200", "csrc", "cb_resolver.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-rdynamic", "-fPIC", "-shared", "-pthread",
                                "-ffp-contract=off", "-I", os.path.join(EMU, "stub"), "-o", SO, srcs[0], srcs[1]])
@@ -36,6 +37,7 @@ def load_emu():
     L.emu_plan_rebalance.argtypes = [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP, VP]
     L.emu_slot_table.argtypes = [VP, VP, VP, VP, C.c_int, VP]
     L.emu_shuffle.argtypes = [VP, VP, VP, C.c_int, C.c_int]
+    L.emu_srv_keys.argtypes = [VP, VP, C.c_int, VP]
     return L
 
 
@@ -142,3 +144,22 @@ def test_shuffle_kernel_golden_and_random(emu):
         want = O.shuffle(arr, us)
         for ctas in (1, 3):
             assert np.array_equal(shuffle_emulated(emu, arr, us, ctas), want), (n, ctas)
+
+
+def test_srv_key_kernel_against_hashlib(emu):
+    """csrc/cb_resolver.cuh: base64(sha1(message)) per thread -- message lengths across every padding boundary
+    (55/56, 63/64, 119/120 bytes), the srvKey strings of lib/resolver.js:1157-1171 among them."""
+    import base64
+    import hashlib
+    rng = np.random.RandomState(17)
+    msgs = [b"", b"a", b"svc.example.com||8080||10.0.0.1", b"_http._tcp.foo||80||2001:db8::1"]
+    msgs += [bytes(rng.randint(0, 256, n).astype(np.uint8)) for n in list(range(50, 70)) + list(range(115, 125)) + [200, 300]]
+    msgs += [("backend%d.dc.example.com||%d||10.%d.%d.%d" % (i, 1000 + i, i % 256, (7 * i) % 256, (13 * i) % 256)).encode()
+             for i in range(120)]   # more than one CTA
+    blob = np.frombuffer(b"".join(msgs) + b"\0" * 16, dtype=np.uint8).copy()
+    offs = np.zeros(len(msgs) + 1, np.uint32)
+    offs[1:] = np.cumsum([len(m) for m in msgs])
+    keys = np.zeros(len(msgs) * 28, np.uint8)
+    emu.emu_srv_keys(blob.ctypes.data, offs.ctypes.data, len(msgs), keys.ctypes.data)
+    got = [keys[28 * k:28 * k + 28].tobytes().decode() for k in range(len(msgs))]
+    assert got == [base64.b64encode(hashlib.sha1(m).digest()).decode() for m in msgs]
