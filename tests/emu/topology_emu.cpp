@@ -45,6 +45,11 @@ void emu_shuffle(const int32_t *in, int32_t *out, const double *us, int n, int c
 		emu::launch(TOPO_TPB, [&] { shuffle_kernel(in, out, us, n); });
 	}
 }
+/* CB_BALANCE_SRV_WEIGHTED (extension): want[] by preference position and the add list, as rebuild_slots() launches it */
+void emu_weighted_want(const int32_t *keys, int B, const int32_t *prio, const int32_t *weight, int S, int32_t *want,
+    int32_t *add, int32_t *n_add) {
+	one_cta(1, [&] { weighted_want_kernel(keys, B, prio, weight, S, want, add, n_add); });
+}
 /* srvKey of n messages (csrc/cb_resolver.cuh: SHA-1 + base64, one thread per message), 128-thread CTAs as
  * cb_srv_keys launches them */
 void emu_srv_keys(const unsigned char *msgs, const unsigned int *offs, int n, char *keys) {

@@ -38,6 +38,7 @@ def load_emu():
     L.emu_slot_table.argtypes = [VP, VP, VP, VP, C.c_int, VP]
     L.emu_shuffle.argtypes = [VP, VP, VP, C.c_int, C.c_int]
     L.emu_srv_keys.argtypes = [VP, VP, C.c_int, VP]
+    L.emu_weighted_want.argtypes = [VP, C.c_int, VP, VP, C.c_int, VP, VP, VP]
     return L
 
 
@@ -163,3 +164,42 @@ def test_srv_key_kernel_against_hashlib(emu):
     emu.emu_srv_keys(blob.ctypes.data, offs.ctypes.data, len(msgs), keys.ctypes.data)
     got = [keys[28 * k:28 * k + 28].tobytes().decode() for k in range(len(msgs))]
     assert got == [base64.b64encode(hashlib.sha1(m).digest()).decode() for m in msgs]
+
+
+def weighted_spec(keys, prio, weight, S):
+    """The documented rule of the CB_BALANCE_SRV_WEIGHTED extension (no reference behaviour exists),
+    stated independently of the kernel: only the backends of the numerically lowest priority take slots; S slots are
+    apportioned by weight with the largest-remainder method, ties to the earlier position in the preference list; a tier
+    whose weights are all zero is uniform."""
+    best = min(prio[k] for k in keys)
+    tier = [i for i, k in enumerate(keys) if prio[k] == best]
+    wsum = sum(weight[keys[i]] for i in tier)
+    w = {i: (weight[keys[i]] if wsum > 0 else 1) for i in tier}
+    tot = wsum if wsum > 0 else len(tier)
+    want = [0] * len(keys)
+    for i in tier:
+        want[i] = S * w[i] // tot
+    left = S - sum(want)
+    order = sorted(tier, key=lambda i: (-(S * w[i] % tot), i))
+    for i in order[:left]:
+        want[i] += 1
+    return want
+
+
+def test_weighted_want_kernel_against_its_specification(emu):
+    rng = np.random.RandomState(23)
+    for trial in range(60):
+        B = int(rng.randint(1, 40))
+        S = int(rng.randint(0, 300))
+        keys = rng.permutation(B).astype(np.int32)
+        prio = rng.randint(0, 3, B).astype(np.int32)
+        weight = (rng.randint(0, 20, B) * (rng.rand(B) < (0.0 if trial % 7 == 0 else 0.8))).astype(np.int32)
+        want = np.zeros(B, np.int32)
+        add = np.zeros(S + 1, np.int32)
+        na = np.zeros(1, np.int32)
+        emu.emu_weighted_want(keys.ctypes.data, B, prio.ctypes.data, weight.ctypes.data, S, want.ctypes.data,
+                              add.ctypes.data, na.ctypes.data)
+        spec = weighted_spec(keys.tolist(), prio.tolist(), weight.tolist(), S)
+        assert want.tolist() == spec, (trial, B, S)
+        assert na[0] == S == sum(spec)
+        assert add[:S].tolist() == [i for i, c in enumerate(spec) for _ in range(c)]
