@@ -218,6 +218,10 @@ class ConnectionPool(object):
             self._ctx.queue_create(self._capacity, 4 * self._capacity, int(idle_slots))
             self._queue_ready = True
 
+    def _idle_before_the_queue(self):
+        n = len(self._slot_backend)
+        return n if self._initial_idle is None else min(int(self._initial_idle), n)
+
     def _dispatch(self):
         """Turn the device's resolution records into handle transitions, in the device's order."""
         for ticket, code, slot in self._ctx.queue_results().tolist():
@@ -239,9 +243,9 @@ class ConnectionPool(object):
             return {"counters": dict(self._host_counters), "totalConnections": len(self._slot_backend),
                     "idleConnections": self._host_idle, "pendingConnections": 0,
                     "waiterCount": len(self._host_waiters)}
-        if not self._queue_ready:
+        if not self._queue_ready:  # no claim yet: the queue is created with this many idle slots (_ensure_queue)
             return {"counters": {}, "totalConnections": len(self._slot_backend),
-                    "idleConnections": len(self._slot_backend), "pendingConnections": 0, "waiterCount": 0}
+                    "idleConnections": self._idle_before_the_queue(), "pendingConnections": 0, "waiterCount": 0}
         info = self._ctx.queue_info()
         # a counter exists once it has been bumped (lib/pool.js:269-283)
         counters = {k: v for k, v in info.counters().items() if v}
@@ -275,7 +279,7 @@ class ConnectionPool(object):
         if self.p_codel is None:
             return total, self._host_idle, len(self._host_waiters)
         if not self._queue_ready:
-            return total, total, 0
+            return total, self._idle_before_the_queue(), 0
         info = self._ctx.queue_info()
         return total, int(info.idle), int(info.tail - info.head)
 
