@@ -190,3 +190,10 @@ def test_getstats_shape_issue_132(cb):
     assert (s["totalConnections"], s["idleConnections"], s["pendingConnections"], s["waiterCount"]) == (2, 2, 0, 0)
     assert pool.toKangSnapshot()["connections"] == {"b1": {"idle": 2}}
     pool.stop()
+
+
+def test_config_c1_emulated(cb):
+    """BASELINE.json configs[0] (StaticResolver, 4 backends, 256 claim()s, target 5 ms) through the mirror."""
+    import test_gpu_zz_codel_load_runs as Z
+    res = Z.config_c1(cb)
+    assert res["successes"] > 0

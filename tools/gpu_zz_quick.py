@@ -33,9 +33,12 @@ def main():
     import test_gpu_zz_sizing as ZS
     todo = [("kang_snapshot", lambda: GP.test_kang_snapshot_shape(cb)),
             ("sizing_loop", lambda: ZS.sizing_scenario(cb) and None),
-            ("implicit_high_timeout", lambda: ZL.implicit_high_timeout(cb))]
-    for d in (300, 5000, 1000, 500, 1500, 2000, 2500):
-        todo.append(("load_run_%d" % d, (lambda d=d: {k: v for k, v in ZL.load_run(cb, d).items() if k != "delays"})))
+            ("implicit_high_timeout", lambda: ZL.implicit_high_timeout(cb)),
+            ("config_c1", lambda: {k: v for k, v in ZL.config_c1(cb).items() if k not in ("delays", "pool")})]
+    if os.environ.get("CB_ZZ_ONLY"):
+        todo = [t for t in todo if t[0] in os.environ["CB_ZZ_ONLY"].split(",")]
+    for d in (() if os.environ.get("CB_ZZ_ONLY") else (300, 5000, 1000, 500, 1500, 2000, 2500)):
+        todo.append(("load_run_%d" % d, (lambda d=d: {k: v for k, v in ZL.load_run(cb, d).items() if k not in ("delays", "pool")})))
     bad = 0
     for name, fn in todo:
         t = time.time()
