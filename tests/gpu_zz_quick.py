@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/gpu_zz_quick.py -- the GPU tests written after the round's last full GPU session, called directly (no
+"""tests/gpu_zz_quick.py -- the GPU tests written after the round's last full GPU session, called directly (no
 pytest, no torch import: a fresh box pages those in for about a minute) so that they fit in the seconds of GPU
 budget that were left.  Appends one JSON line per scenario to gpurun_out/zz_quick.jsonl as it goes."""
 import json

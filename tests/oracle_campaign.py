@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""tools/oracle_campaign.py <seconds> [first_seed] -- pin the oracle's C restatement to the reference harder than the
+"""tests/oracle_campaign.py <seconds> [first_seed] -- pin the oracle's C restatement to the reference harder than the
 test suite has time for: fresh random traces (ragged cuts, carried state, cancelled handles, empty() markers, backwards
 clock steps), pool event scripts, planRebalance inputs, sizing scripts and Queue operation scripts through the REFERENCE'S
 OWN JavaScript under the engine vendored in the reference tree (oracle/_ref; needs /root/reference to have been built
@@ -12,7 +12,7 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, HERE)
 import numpy as np  # noqa: E402
 
 import util  # noqa: E402

@@ -12,7 +12,7 @@ replayed through the pool-model oracle (cbo_pool_sim, pinned to the reference's 
 and every (ticket, code, slot) record and counter must match exactly.
 
 (The file sorts last among the GPU tests: it was written after the round's last full GPU session; its scenarios ran
-green on a B200 through tools/gpu_zz_quick.py -- profiles/r02_late_gpu_tests.jsonl -- and run on the CPU through the
+green on a B200 through tests/gpu_zz_quick.py -- profiles/r02_late_gpu_tests.jsonl -- and run on the CPU through the
 emulated context, tests/test_pool_mirror_emulated.py.)"""
 import heapq
 

@@ -5,7 +5,7 @@ tests/test_lpf_golden.py), the plan from the device's planRebalance (cb_plan_reb
 compared with the oracle (cbo_lpf_run + cbo_plan_rebalance) driven with the same occupancy.
 
 (The file sorts last among the GPU tests: it was written after the round's last full GPU session; its scenarios ran
-green on a B200 through tools/gpu_zz_quick.py -- profiles/r02_late_gpu_tests.jsonl -- and run on the CPU through the
+green on a B200 through tests/gpu_zz_quick.py -- profiles/r02_late_gpu_tests.jsonl -- and run on the CPU through the
 emulated context, tests/test_pool_mirror_emulated.py.)"""
 import pytest
 
