@@ -2,7 +2,7 @@
 """tests/fuzz_emulated_pipeline.py <seconds> [first_seed [cases]] -- random small traces (odd sizes, ragged batch
 cuts, carried-in states, waiting flags and empty() markers, both commit variants) through the
 emulated batch pipeline (tests/emu) against the oracle.  Prints every mismatch and a summary;
-round 1 ran about 2 900 cases clean.  A stalled barrier (lanes that disagree about reaching a collective)
+round 1 ran about 2 900 cases clean, round 2's final build 14 398 (tests/emu/README.md).  A stalled barrier (lanes that disagree about reaching a collective)
 is reported with the stuck threads' stacks by the emulator instead of hanging."""
 import os
 import sys
