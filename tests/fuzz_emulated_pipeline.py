@@ -36,6 +36,10 @@ while (time.time() < t_end) if max_cases is None else (it < max_cases):
     if r < 0.25: kw["start_overloaded"] = True
     elif r < 0.5: kw["all_overloaded_from"] = int(rng.randint(0, max(1, n)))
     start, now = tracegen.gen_trace(n, seed=seed, de=de, unit=unit, target_ns=tgt * 1_000_000, **kw)
+    if rng.rand() < float(os.environ.get("CB_FUZZ_BACKSTEP", "0.1")) and n > 1:
+        # the clock steps back here and there: the batch takes the exact one-warp path (lib/codel.js:72-79's count - 2 /
+        # sqrt(count) branch is only reachable this way)
+        now = now - (rng.rand(n) < float(rng.choice([0.002, 0.02, 0.2]))).astype(np.int64) * int(rng.choice([1_000, 3_000_000, 150_000_000]))
     flags = None
     if rng.rand() < 0.4:
         flags = util.make_flags(n, seed, cancel_mod=int(rng.choice([0, 3, 9])), empty_mod=int(rng.choice([0, 97, 1501])))
