@@ -222,6 +222,29 @@ def test_reference_arm_shares_the_config(monkeypatch, capsys):
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["value"] == line["value"]
 
 
+def test_reference_arm_runs_one_pool_per_gpu(monkeypatch, capsys):
+    """--impl reference --gpus 2: the job is two independent pools, so two reference pools run at once (one core each);
+    the line's config is the CUDA arm's, its value the aggregate over the slowest pool's time."""
+    import bench as b
+    from oracle import ref
+    monkeypatch.setattr(b, "REF_SAMPLE", {k: 8192 for k in b.REF_SAMPLE})
+    monkeypatch.setattr(ref, "available", lambda: False)  # the C port stands in: quick
+    monkeypatch.setitem(b.WORKLOADS, "c3", dict(b.WORKLOADS["c3"], n=1 << 16))  # the full-step C port leg stays small
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3"])
+    monkeypatch.delenv("RANK", raising=False)
+    b.main()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    cfg = b.workload_config("c3", 2)
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["config"] == cfg
+    assert cfg["parallelism"] == "queue segment per GPU"
+    assert line["cpu_baseline"]["cores"] == 2 and line["cpu_baseline"]["kind"] == "port"
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["gpu_launches"] == 0
+    # rank 1 of the same launch prints nothing
+    monkeypatch.setenv("RANK", "1")
+    b.main()
+    assert capsys.readouterr().out.strip() == ""
+
+
 @pytest.mark.parametrize("kw", [{}, {"all_overloaded_from": 5000}])
 def test_device_trace_generator_matches_numpy(kw):
     """bench.gen_trace_torch (run on the CPU here) against tracegen.gen_trace, bit for bit: whole traces and
