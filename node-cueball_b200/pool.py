@@ -169,6 +169,8 @@ class CueBallClaimHandle(object):
 
 
 class ConnectionPool(object):
+    _DEADLINE_SLACK = 1024  # stale entries tolerated in the deadline heap before it is rebuilt
+
     def __init__(self, options):
         assertClaimDelay(options.get("targetClaimDelay"))
         self.p_max = int(options.get("maximum", 0))
@@ -404,6 +406,9 @@ class ConnectionPool(object):
         handle = CueBallClaimHandle(self, cb, now, float(tmo[0]), ticket)
         self._handles[ticket] = handle
         heapq.heappush(self._deadlines, (now + int(float(tmo[0]) * 1e6), ticket))
+        if len(self._deadlines) > 2 * len(self._handles) + self._DEADLINE_SLACK:  # resolved handles' entries: drop them in bulk
+            self._deadlines = [e for e in self._deadlines if e[1] in self._handles]
+            heapq.heapify(self._deadlines)
         self._dispatch()
         return handle
 

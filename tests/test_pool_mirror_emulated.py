@@ -197,3 +197,29 @@ def test_config_c1_emulated(cb):
     import test_gpu_zz_codel_load_runs as Z
     res = Z.config_c1(cb)
     assert res["successes"] > 0
+
+
+def test_next_deadline_survives_heap_compaction(cb):
+    """nextDeadline() keeps (deadline, ticket) entries lazily; claim() rebuilds the heap once resolved handles' entries
+    outnumber the live ones: the answer must not change."""
+    clock = {"now": 10 ** 9}
+    pool = cb.ConnectionPool({"targetClaimDelay": 5, "maximum": 1, "clock": lambda: clock["now"], "random": lambda: 0.5})
+    pool._DEADLINE_SLACK = 4
+    pool.on_resolver_added("b0", {})
+    held = pool.claim(lambda *a: None)
+    assert held.isInState("claimed") and pool.nextDeadline() is None
+    waiters = []
+    for i in range(12):                       # admitted one after the other: their entries go stale
+        clock["now"] += 100_000
+        w = pool.claim(lambda *a: None)
+        waiters.append(w)
+        held.release()
+        held = w
+        assert held.isInState("claimed")
+    assert len(pool._deadlines) <= 2 + pool._DEADLINE_SLACK + 1   # 13 claims so far, 12 of them resolved
+    clock["now"] += 100_000
+    last = pool.claim(lambda *a: None)
+    assert last.isInState("waiting")
+    assert pool.nextDeadline() == last.ch_started_ns + int(last.ch_claimTimeout * 1e6)
+    last.cancel()
+    assert pool.nextDeadline() is None
