@@ -37,6 +37,7 @@ an integer (admitted claim j of the pool's life takes slot j mod nslots, SURVEY.
 backend comes from the device-side slot table.  A pool WITHOUT targetClaimDelay has no CoDel
 (lib/pool.js:195-200): nothing on its path is accelerated, and it runs as a plain host FIFO.
 """
+import collections
 import heapq
 import math
 import time
@@ -203,7 +204,8 @@ class ConnectionPool(object):
         self.p_lastRebalClamped = False      # lib/pool.js:247
         self.p_lastRebalance = None          # what the last rebalance() asked for (observability)
         self._queue_ready = False
-        self.records = []      # every (ticket, code, slot) the device produced, in order (observability/tests)
+        # the last (ticket, code, slot) records the device produced, in order (observability/tests; bounded)
+        self.records = collections.deque(maxlen=int(options.get("recordHistory", 1 << 16)))
         # the pool without CoDel: a plain host FIFO (nothing to accelerate)
         self._host_waiters = []
         self._host_started = False
